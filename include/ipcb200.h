@@ -1,0 +1,216 @@
+/* ipcb200.h — C ABI of the B200-native per-step contact pipeline.
+ *
+ * This is the drop-in boundary for ONE path of ipc-sim/ipc-toolkit (v1.6.0):
+ *
+ *   CollisionMesh -> BroadPhase -> Candidates -> NormalCollisions::build
+ *                 -> BarrierPotential {(), gradient, hessian}
+ *                 -> compute_collision_free_stepsize
+ *
+ * Every entry point names the reference interface (file:line under the
+ * reference tree's src/ipc/) it replaces.  The signatures hold only plain
+ * pointers and sizes: no Eigen, no torch, no C++ types.
+ *
+ * Conventions
+ *  - Matrices are COLUMN-major like Eigen::MatrixXd / MatrixXi:
+ *    V(i,k) = V[i + k*ld], ld >= rows ("ConstRef" semantics,
+ *    utils/eigen_ext.hpp:17).  Index type is int32 (config.hpp.in:30-34).
+ *  - The global DOF of vertex v, axis k is 3*v+k (VERTEX_DERIVATIVE_LAYOUT =
+ *    RowMajor, config.hpp.in:45).
+ *  - Pair lists are returned row-major: pairs[2*i+0], pairs[2*i+1].
+ *  - Functions return 0 on success, non-zero on error; ipcb_last_error()
+ *    gives the thread-local message (the C++ adapters rethrow it as
+ *    std::runtime_error, like log_and_throw_error, utils/logger.cpp:41-45).
+ *  - Functions ending in _dev take DEVICE pointers (same layout) and never
+ *    touch host memory except for scalar outputs that are documented as host.
+ *    The host variants stage through the context's device buffers.
+ *  - All calls are synchronous at the API edge (one CUDA stream per context),
+ *    matching the blocking TBB-parallel reference entry points.
+ *
+ * There is NO CPU fallback in this library: ipcb_ctx_create fails when no
+ * CUDA device is usable.  The CPU restatement lives in oracle/ (test
+ * infrastructure, prefix ipco_) and exports the host half of this ABI.
+ */
+#ifndef IPCB200_H
+#define IPCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef IPCB_PREFIX
+#define IPCB_PREFIX ipcb_
+#endif
+#define IPCB_CAT2(a, b) a##b
+#define IPCB_CAT(a, b) IPCB_CAT2(a, b)
+#define IPCB_FN(name) IPCB_CAT(IPCB_PREFIX, name)
+
+typedef struct ipcb_ctx ipcb_ctx;
+
+/* candidate / collision kinds (candidates/candidates.hpp:240-244) */
+enum { IPCB_VV = 0, IPCB_EV = 1, IPCB_EE = 2, IPCB_FV = 3, IPCB_EF = 4, IPCB_FF = 5 };
+
+/* PSDProjectionMethod (utils/eigen_ext.hpp:202-206) */
+enum { IPCB_PSD_NONE = 0, IPCB_PSD_CLAMP = 1, IPCB_PSD_ABS = 2 };
+
+/* NarrowPhaseCCD implementations (ccd/tight_inclusion_ccd.hpp, ccd/additive_ccd.hpp) */
+enum { IPCB_CCD_TIGHT_INCLUSION = 0, IPCB_CCD_ADDITIVE = 1 };
+
+/* broad phase predicate: FLOAT = the default LBVH's outward-rounded float
+ * boxes (broad_phase/lbvh.cpp:29-41, lbvh.hpp:66-70); DOUBLE = BruteForce /
+ * HashGrid double boxes (broad_phase/aabb.cpp:29-33).  Cross-check switch. */
+enum { IPCB_BOXES_FLOAT = 0, IPCB_BOXES_DOUBLE = 1 };
+
+/* flags for collisions_build (collisions/normal/normal_collisions.hpp:191-194) */
+enum { IPCB_USE_AREA_WEIGHTING = 1 };
+
+/* CCD parameters; defaults are the reference's (tight_inclusion_ccd.hpp:11-19,
+ * additive_ccd.hpp:21-26).  A value <= 0 for tolerance / conservative_rescaling
+ * or == 0 for max_iterations selects the default of `kind`. */
+typedef struct ipcb_ccd_params {
+    int32_t kind;                  /* IPCB_CCD_* */
+    double tolerance;              /* TI only; default 1e-6 */
+    int64_t max_iterations;        /* default 10'000'000; < 0 = unlimited */
+    double conservative_rescaling; /* default 0.8 (TI) / 0.9 (Additive) */
+} ipcb_ccd_params;
+
+/* BarrierPotential(dhat, stiffness, use_physical_barrier)
+ * (potentials/barrier_potential.hpp, barrier_potential.cpp:62-99) */
+typedef struct ipcb_barrier_params {
+    double dhat;
+    double stiffness;
+    int32_t use_physical_barrier;
+} ipcb_barrier_params;
+
+/* ---- context ------------------------------------------------------------ */
+int IPCB_FN(ctx_create)(int device, ipcb_ctx** out);
+void IPCB_FN(ctx_destroy)(ipcb_ctx* ctx);
+const char* IPCB_FN(last_error)(void);
+/* "cuda-sm100a" for the product, "oracle-cpu" for the oracle. */
+const char* IPCB_FN(backend_name)(void);
+/* CUDA stream handle of the context (cudaStream_t as void*), NULL for oracle. */
+void* IPCB_FN(ctx_stream)(ipcb_ctx* ctx);
+
+/* ---- CollisionMesh (collision_mesh.cpp:15-127) -------------------------- */
+/* Builds faces_to_edges (:510-543, error "Unable to find edge!"), codim
+ * vertex / edge lists (:145-183) and vertex / edge areas (:309-374) on the
+ * host and keeps device mirrors.  E is nE x 2, F is nF x 3. */
+int IPCB_FN(mesh_set)(ipcb_ctx* ctx, int32_t nV, const double* rest_positions, int32_t ld_rest,
+                      int32_t nE, const int32_t* E, int32_t ldE, int32_t nF, const int32_t* F, int32_t ldF);
+int IPCB_FN(mesh_num_codim_vertices)(ipcb_ctx* ctx, int32_t* n);
+int IPCB_FN(mesh_num_codim_edges)(ipcb_ctx* ctx, int32_t* n);
+int IPCB_FN(mesh_faces_to_edges)(ipcb_ctx* ctx, int32_t* f2e /* nF x 3 col-major, ld = nF */);
+int IPCB_FN(mesh_areas)(ipcb_ctx* ctx, double* vertex_areas /* nV */, double* edge_areas /* nE */);
+
+/* ---- BroadPhase (broad_phase/broad_phase.hpp:19-133) -------------------- */
+/* build(V,E,F,r) :12-23 and build(V0,V1,E,F,r) :25-41 of broad_phase.cpp on
+ * the context's mesh; detect_* replaces the six pure virtuals (:71-97).
+ * `boxes` selects the predicate (IPCB_BOXES_*). */
+int IPCB_FN(broad_build_static)(ipcb_ctx* ctx, const double* V, int32_t ld, double inflation_radius, int32_t boxes);
+int IPCB_FN(broad_build_swept)(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld,
+                               double inflation_radius, int32_t boxes);
+int IPCB_FN(broad_detect)(ipcb_ctx* ctx, int32_t kind, int64_t* count);
+int IPCB_FN(broad_fetch)(ipcb_ctx* ctx, int32_t kind, int32_t* pairs /* count x 2 */);
+/* vertex boxes of the last build as 6 floats per vertex (min xyz, max xyz) or
+ * 6 doubles when built with IPCB_BOXES_DOUBLE (aabb.cpp:35-87, lbvh.cpp:29-41) */
+int IPCB_FN(broad_vertex_boxes)(ipcb_ctx* ctx, void* boxes /* nV x 6 row-major */);
+
+/* ---- Candidates (candidates/candidates.cpp:43-222) ---------------------- */
+/* 3D: EE + FV from the main broad phase, VV between codim vertices, EV
+ * between codim edges and codim vertices.  counts[k], k = IPCB_VV..IPCB_FV.
+ * Pair order: VV (v0,v1), EV (edge,vertex), EE (ea,eb), FV (face,vertex). */
+int IPCB_FN(candidates_build_static)(ipcb_ctx* ctx, const double* V, int32_t ld, double inflation_radius,
+                                     int64_t counts[4]);
+int IPCB_FN(candidates_build_swept)(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld,
+                                    double inflation_radius, int64_t counts[4]);
+int IPCB_FN(candidates_fetch)(ipcb_ctx* ctx, int32_t kind, int32_t* pairs);
+/* Replace the resident candidates by caller-provided ones (the reference's
+ * public-data Candidates container, candidates.hpp:240-244). */
+int IPCB_FN(candidates_set)(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_t* pairs);
+
+/* ---- NormalCollisions::build (collisions/normal/normal_collisions.cpp) --- */
+/* build(mesh,V,dhat,dmin,bp) :20-36 — runs candidates_build_static with
+ * r = 0.5*(dhat+dmin), then the candidate overload. */
+int IPCB_FN(collisions_build)(ipcb_ctx* ctx, const double* V, int32_t ld, double dhat, double dmin, int32_t flags,
+                              int64_t counts[4]);
+/* build(candidates,mesh,V,dhat,dmin) :38-158 on the RESIDENT candidates
+ * (IPC set type; dedup with weight accumulation, builder.cpp:547-689). */
+int IPCB_FN(collisions_build_from_candidates)(ipcb_ctx* ctx, const double* V, int32_t ld, double dhat, double dmin,
+                                              int32_t flags, int64_t counts[4]);
+/* ids: count x 2 (VV (v0<v1), EV (edge,vertex), EE (ea<eb), FV (face,vertex)),
+ * sorted lexicographically; weight: count; eps_x, dtype: EE only (may be NULL) */
+int IPCB_FN(collisions_fetch)(ipcb_ctx* ctx, int32_t kind, int32_t* ids, double* weight, double* eps_x,
+                              uint8_t* dtype);
+/* compute_minimum_distance (normal_collisions.cpp:209-233): min squared distance, +inf if empty */
+int IPCB_FN(collisions_min_distance)(ipcb_ctx* ctx, const double* V, int32_t ld, double* min_dist_sqr);
+
+/* ---- BarrierPotential (potentials/potential.cpp:36-222) ----------------- */
+int IPCB_FN(barrier_energy)(ipcb_ctx* ctx, const double* V, int32_t ld, const ipcb_barrier_params* bp, double* energy);
+int IPCB_FN(barrier_gradient)(ipcb_ctx* ctx, const double* V, int32_t ld, const ipcb_barrier_params* bp,
+                              double* grad /* 3*nV */);
+/* Assembles H (3nV x 3nV, compressed column == compressed row of the
+ * symmetric matrix, indices ascending, duplicates summed, exact-zero local
+ * entries skipped: utils/local_to_global.hpp:263-305) and returns nnz. */
+int IPCB_FN(barrier_hessian)(ipcb_ctx* ctx, const double* V, int32_t ld, const ipcb_barrier_params* bp,
+                             int32_t psd_mode, int64_t* nnz);
+int IPCB_FN(barrier_hessian_fetch)(ipcb_ctx* ctx, int32_t* outer /* 3nV+1 */, int32_t* inner /* nnz */,
+                                   double* values /* nnz */);
+
+/* ---- CCD (ipc.cpp:45-101, candidates.cpp:252-292) ----------------------- */
+/* compute_collision_free_stepsize(mesh,V0,V1,min_distance,bp,ccd):
+ * candidates_build_swept with r = 0.5*min_distance, then the earliest time of
+ * impact over all candidates (1.0 if there are none). */
+int IPCB_FN(ccd_stepsize)(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double min_distance,
+                          const ipcb_ccd_params* ccd, double* step);
+/* Candidates::compute_collision_free_stepsize on the RESIDENT candidates */
+int IPCB_FN(ccd_stepsize_from_candidates)(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld,
+                                          double min_distance, const ipcb_ccd_params* ccd, double* step);
+/* NarrowPhaseCCD batch (ccd/narrow_phase_ccd.hpp:8-119): n independent
+ * queries; x_t0 / x_t1 hold 12 doubles per query (4 points xyz: EE ea0 ea1 eb0
+ * eb1; FV p t0 t1 t2; EV p e0 e1 -; VV p0 p1 - -).  hit[i] in {0,1}, toi[i]
+ * valid when hit (+inf otherwise). tmax in [0,1]. */
+int IPCB_FN(ccd_narrow_phase)(ipcb_ctx* ctx, int32_t kind, int64_t n, const double* x_t0, const double* x_t1,
+                              double min_distance, double tmax, const ipcb_ccd_params* ccd, uint8_t* hit,
+                              double* toi);
+
+#ifndef IPCB_ORACLE
+/* ---- device-resident variants (product only) ---------------------------- */
+/* V*, grad are DEVICE pointers (col-major, ld); scalar results are written to
+ * HOST memory unless the name says _devout, in which case the pointer is a
+ * device pointer and the call does not synchronise the stream. */
+int IPCB_FN(collisions_build_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, double dhat, double dmin,
+                                  int32_t flags, int64_t counts[4]);
+int IPCB_FN(collisions_build_from_candidates_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, double dhat,
+                                                  double dmin, int32_t flags, int64_t counts[4]);
+int IPCB_FN(barrier_energy_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, const ipcb_barrier_params* bp,
+                                double* d_energy /* device, 1 double */);
+int IPCB_FN(barrier_gradient_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, const ipcb_barrier_params* bp,
+                                  double* d_grad /* device, 3*nV */);
+int IPCB_FN(barrier_hessian_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, const ipcb_barrier_params* bp,
+                                 int32_t psd_mode, int64_t* nnz);
+/* device pointers to the resident CSR of the last barrier_hessian (valid until the next one) */
+int IPCB_FN(barrier_hessian_dev_ptrs)(ipcb_ctx* ctx, const int32_t** d_outer, const int32_t** d_inner,
+                                      const double** d_values);
+int IPCB_FN(candidates_build_swept_dev)(ipcb_ctx* ctx, const double* dV0, const double* dV1, int32_t ld,
+                                        double inflation_radius, int64_t counts[4]);
+int IPCB_FN(ccd_stepsize_dev)(ipcb_ctx* ctx, const double* dV0, const double* dV1, int32_t ld, double min_distance,
+                              const ipcb_ccd_params* ccd, double* d_step /* device, 1 double */);
+int IPCB_FN(ccd_stepsize_from_candidates_dev)(ipcb_ctx* ctx, const double* dV0, const double* dV1, int32_t ld,
+                                              double min_distance, const ipcb_ccd_params* ccd, double* d_step);
+/* Multi-GPU sharding: this context processes only the slice
+ * [rank*n/world, (rank+1)*n/world) of the Morton-ordered query leaves in the
+ * broad phase, hence a disjoint shard of candidates / collisions.  Energy,
+ * gradient and step size then need a sum / sum / min all-reduce by the caller
+ * (NCCL), the Hessian is the rank's additive contribution. */
+int IPCB_FN(ctx_set_shard)(ipcb_ctx* ctx, int32_t rank, int32_t world);
+/* number of kernels this context has launched so far (bench.py gpu_launches) */
+int IPCB_FN(ctx_launch_count)(ipcb_ctx* ctx, int64_t* n);
+/* per-stage device time of the last call in ms, by stage name; returns the number of stages filled */
+int IPCB_FN(ctx_stage_times)(ipcb_ctx* ctx, int32_t max_stages, const char** names, float* ms);
+#endif
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPCB200_H */

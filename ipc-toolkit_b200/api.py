@@ -1,0 +1,453 @@
+"""Host-side mirror of the reference's Python interface (``ipctk``) for the
+per-step contact path, on top of the C ABI (include/ipcb200.h).
+
+Names, argument meaning and error behaviour follow the reference's pybind11
+module (python/src/**): ``CollisionMesh``, ``Candidates``, ``NormalCollisions``,
+``BarrierPotential``, ``compute_collision_free_stepsize``,
+``TightInclusionCCD`` / ``AdditiveCCD``, ``PSDProjectionMethod``.
+
+``make_api(lib)`` returns a namespace bound to one loaded library: the product
+(``ipcb_``; CUDA, no CPU fallback) or — from tests only — the CPU oracle.
+
+State model: a ``CollisionMesh`` owns the library context (device mirrors of
+the mesh, the broad phase, and ONE resident candidate set and ONE resident
+collision set).  ``Candidates`` / ``NormalCollisions`` objects are handles to
+that resident state plus a lazily fetched host copy (the
+public host containers are the compatibility path; the timed path never
+materialises them).  Building a newer set on the same mesh invalidates older
+handles (using them raises ``RuntimeError``).
+"""
+import ctypes as C
+import enum
+import types
+
+import numpy as np
+
+try:  # loaded as a package module or stand-alone by oracle/pyoracle.py
+    from . import _abi
+except ImportError:  # pragma: no cover
+    import _abi
+
+VV, EV, EE, FV, EF, FF = range(6)
+
+
+class PSDProjectionMethod(enum.IntEnum):  # utils/eigen_ext.hpp:202-206
+    NONE = 0
+    CLAMP = 1
+    ABS = 2
+
+
+class TightInclusionCCD:  # ccd/tight_inclusion_ccd.hpp:11-19
+    DEFAULT_TOLERANCE = 1e-6
+    DEFAULT_MAX_ITERATIONS = 10_000_000
+    DEFAULT_CONSERVATIVE_RESCALING = 0.8
+    SMALL_TOI = 1e-6
+
+    def __init__(self, tolerance=DEFAULT_TOLERANCE, max_iterations=DEFAULT_MAX_ITERATIONS,
+                 conservative_rescaling=DEFAULT_CONSERVATIVE_RESCALING):
+        self.tolerance = tolerance
+        self.max_iterations = max_iterations
+        self.conservative_rescaling = conservative_rescaling
+
+    def _params(self):
+        return _abi.CcdParams(0, self.tolerance, self.max_iterations, self.conservative_rescaling)
+
+
+class AdditiveCCD:  # ccd/additive_ccd.hpp:21-26
+    DEFAULT_MAX_ITERATIONS = 10_000_000
+    DEFAULT_CONSERVATIVE_RESCALING = 0.9
+
+    def __init__(self, max_iterations=DEFAULT_MAX_ITERATIONS, conservative_rescaling=DEFAULT_CONSERVATIVE_RESCALING):
+        self.max_iterations = max_iterations
+        self.conservative_rescaling = conservative_rescaling
+
+    def _params(self):
+        return _abi.CcdParams(1, 0.0, self.max_iterations, self.conservative_rescaling)
+
+
+def _f64(a):
+    """column-major float64 view/copy (Eigen::MatrixXd layout) and its leading dimension"""
+    a = np.asfortranarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.c_void_p), (a.shape[0] if a.ndim == 2 else a.size)
+
+
+def _i32(a, cols):
+    a = np.asarray(a, dtype=np.int32)
+    if a.size == 0:
+        a = a.reshape(0, cols)
+    a = np.asfortranarray(a)
+    return a, a.ctypes.data_as(C.c_void_p), max(a.shape[0], 1)
+
+
+def edges_from_faces(faces):
+    """unique undirected edges of a triangle list (the reference uses igl::edges)"""
+    f = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
+    e = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+    e.sort(axis=1)
+    return np.unique(e, axis=0).astype(np.int32)
+
+
+def make_api(lib):
+    ns = types.SimpleNamespace()
+    ns.lib = lib
+    ns.PSDProjectionMethod = PSDProjectionMethod
+    ns.TightInclusionCCD = TightInclusionCCD
+    ns.AdditiveCCD = AdditiveCCD
+    ns.edges_from_faces = edges_from_faces
+
+    class CollisionMesh:
+        """ipc::CollisionMesh(rest_positions, edges, faces) — collision_mesh.cpp:15-127"""
+
+        def __init__(self, rest_positions, edges=None, faces=None, device=0):
+            rest = np.asarray(rest_positions, dtype=np.float64)
+            if rest.ndim != 2 or rest.shape[1] != 3:
+                raise ValueError("only 3D meshes are supported on this path (rest_positions must be N x 3)")
+            self.rest_positions = rest
+            self.edges = np.zeros((0, 2), np.int32) if edges is None else np.asarray(edges, np.int32).reshape(-1, 2)
+            self.faces = np.zeros((0, 3), np.int32) if faces is None else np.asarray(faces, np.int32).reshape(-1, 3)
+            self._ctx = C.c_void_p()
+            lib.check(lib.ctx_create(device, C.byref(self._ctx)))
+            r, rp, rld = _f64(rest)
+            e, ep, eld = _i32(self.edges, 2)
+            f, fp, fld = _i32(self.faces, 3)
+            lib.check(lib.mesh_set(self._ctx, rest.shape[0], rp, rld, e.shape[0], ep, eld, f.shape[0], fp, fld))
+            self._cand_gen = 0
+            self._coll_gen = 0
+
+        def __del__(self):
+            if getattr(self, "_ctx", None):
+                lib.ctx_destroy(self._ctx)
+                self._ctx = None
+
+        def num_vertices(self):
+            return self.rest_positions.shape[0]
+
+        def num_edges(self):
+            return self.edges.shape[0]
+
+        def num_faces(self):
+            return self.faces.shape[0]
+
+        def dim(self):
+            return 3
+
+        def num_codim_vertices(self):
+            n = C.c_int32()
+            lib.check(lib.mesh_num_codim_vertices(self._ctx, C.byref(n)))
+            return n.value
+
+        def num_codim_edges(self):
+            n = C.c_int32()
+            lib.check(lib.mesh_num_codim_edges(self._ctx, C.byref(n)))
+            return n.value
+
+        def faces_to_edges(self):
+            out = np.zeros((self.num_faces(), 3), np.int32, order="F")
+            lib.check(lib.mesh_faces_to_edges(self._ctx, out.ctypes.data_as(C.c_void_p)))
+            return out
+
+        def vertex_areas(self):
+            return self._areas()[0]
+
+        def edge_areas(self):
+            return self._areas()[1]
+
+        def _areas(self):
+            va = np.zeros(self.num_vertices())
+            ea = np.zeros(self.num_edges())
+            lib.check(lib.mesh_areas(self._ctx, va.ctypes.data_as(C.c_void_p), ea.ctypes.data_as(C.c_void_p)))
+            return va, ea
+
+    class BroadPhase:
+        """The CUDA LBVH behind ipc::BroadPhase (broad_phase/broad_phase.hpp:19-133).
+
+        build(...) then detect_*_candidates() -> (n, 2) int32 arrays sorted
+        lexicographically (unordered kinds as (min, max))."""
+
+        FLOAT, DOUBLE = 0, 1
+
+        def __init__(self, mesh, boxes=0):
+            self.mesh = mesh
+            self.boxes = boxes
+
+        def name(self):
+            return "CudaLBVH" if lib.has_device_api else "OracleLBVH"
+
+        def build(self, vertices_t0, vertices_t1=None, inflation_radius=0.0):
+            v0, p0, ld = _f64(vertices_t0)
+            if vertices_t1 is None:
+                lib.check(lib.broad_build_static(self.mesh._ctx, p0, ld, inflation_radius, self.boxes))
+            else:
+                v1, p1, _ = _f64(vertices_t1)
+                lib.check(lib.broad_build_swept(self.mesh._ctx, p0, p1, ld, inflation_radius, self.boxes))
+
+        def vertex_boxes(self):
+            out = np.zeros((self.mesh.num_vertices(), 6), np.float32 if self.boxes == 0 else np.float64)
+            lib.check(lib.broad_vertex_boxes(self.mesh._ctx, out.ctypes.data_as(C.c_void_p)))
+            return out
+
+        def _detect(self, kind):
+            n = C.c_int64()
+            lib.check(lib.broad_detect(self.mesh._ctx, kind, C.byref(n)))
+            out = np.zeros((n.value, 2), np.int32)
+            if n.value:
+                lib.check(lib.broad_fetch(self.mesh._ctx, kind, out.ctypes.data_as(C.c_void_p)))
+            return out
+
+        def detect_vertex_vertex_candidates(self):
+            return self._detect(VV)
+
+        def detect_edge_vertex_candidates(self):
+            return self._detect(EV)
+
+        def detect_edge_edge_candidates(self):
+            return self._detect(EE)
+
+        def detect_face_vertex_candidates(self):
+            return self._detect(FV)
+
+        def detect_edge_face_candidates(self):
+            return self._detect(EF)
+
+        def detect_face_face_candidates(self):
+            return self._detect(FF)
+
+    class Candidates:
+        """ipc::Candidates — candidates/candidates.cpp:43-292"""
+
+        def __init__(self):
+            self.mesh = None
+            self._gen = -1
+            self._counts = [0, 0, 0, 0]
+            self._host = {}
+
+        def build(self, mesh, vertices_t0, vertices_t1_or_radius=None, inflation_radius=0.0, broad_phase=None):
+            # build(mesh, V, r) or build(mesh, V0, V1, r) like the two C++ overloads
+            counts = (C.c_int64 * 4)()
+            v0, p0, ld = _f64(vertices_t0)
+            if vertices_t1_or_radius is None or np.isscalar(vertices_t1_or_radius):
+                r = inflation_radius if vertices_t1_or_radius is None else float(vertices_t1_or_radius)
+                lib.check(lib.candidates_build_static(mesh._ctx, p0, ld, r, counts))
+            else:
+                v1, p1, _ = _f64(vertices_t1_or_radius)
+                lib.check(lib.candidates_build_swept(mesh._ctx, p0, p1, ld, inflation_radius, counts))
+            self._bind(mesh, counts)
+
+        def _bind(self, mesh, counts):
+            self.mesh = mesh
+            mesh._cand_gen += 1
+            self._gen = mesh._cand_gen
+            self._counts = list(counts)
+            self._host = {}
+
+        def _live(self):
+            if self.mesh is None or self._gen != self.mesh._cand_gen:
+                raise RuntimeError("stale Candidates handle: a newer candidate set was built on this mesh")
+
+        def _get(self, kind):
+            self._live()
+            if kind not in self._host:
+                out = np.zeros((self._counts[kind], 2), np.int32)
+                if out.size:
+                    lib.check(lib.candidates_fetch(self.mesh._ctx, kind, out.ctypes.data_as(C.c_void_p)))
+                self._host[kind] = out
+            return self._host[kind]
+
+        vv_candidates = property(lambda self: self._get(VV))
+        ev_candidates = property(lambda self: self._get(EV))
+        ee_candidates = property(lambda self: self._get(EE))
+        fv_candidates = property(lambda self: self._get(FV))
+
+        def set(self, mesh, vv=None, ev=None, ee=None, fv=None):
+            """fill the container by hand (the reference's containers are public data)"""
+            counts = []
+            for kind, arr in enumerate((vv, ev, ee, fv)):
+                a = np.ascontiguousarray(np.zeros((0, 2)) if arr is None else arr, dtype=np.int32).reshape(-1, 2)
+                lib.check(lib.candidates_set(mesh._ctx, kind, a.shape[0], a.ctypes.data_as(C.c_void_p)))
+                counts.append(a.shape[0])
+            self._bind(mesh, counts)
+
+        def size(self):
+            return int(sum(self._counts))
+
+        __len__ = size
+
+        def empty(self):
+            return self.size() == 0
+
+        def compute_collision_free_stepsize(self, mesh, vertices_t0, vertices_t1, min_distance=0.0, narrow_phase_ccd=None):
+            self._live()
+            ccd = (narrow_phase_ccd or TightInclusionCCD())._params()
+            v0, p0, ld = _f64(vertices_t0)
+            v1, p1, _ = _f64(vertices_t1)
+            step = C.c_double()
+            lib.check(lib.ccd_stepsize_from_candidates(mesh._ctx, p0, p1, ld, min_distance, C.byref(ccd), C.byref(step)))
+            return step.value
+
+        def is_step_collision_free(self, mesh, vertices_t0, vertices_t1, min_distance=0.0, narrow_phase_ccd=None):
+            # candidates.cpp:224-250: no candidate has an impact in [0, 1]
+            return self.compute_collision_free_stepsize(mesh, vertices_t0, vertices_t1, min_distance, narrow_phase_ccd) >= 1.0
+
+    class NormalCollisions:
+        """ipc::NormalCollisions — collisions/normal/normal_collisions.cpp:20-158 (IPC set type)"""
+
+        def __init__(self):
+            self.mesh = None
+            self._gen = -1
+            self._counts = [0, 0, 0, 0]
+            self._host = {}
+            self.use_area_weighting = False
+
+        def set_use_area_weighting(self, v):
+            self.use_area_weighting = bool(v)
+
+        def build(self, *args, **kw):
+            """build(mesh, V, dhat, dmin=0, broad_phase=None) or build(candidates, mesh, V, dhat, dmin=0)"""
+            counts = (C.c_int64 * 4)()
+            flags = 1 if self.use_area_weighting else 0
+            if isinstance(args[0], Candidates):
+                cand, mesh, V, dhat = args[:4]
+                dmin = args[4] if len(args) > 4 else kw.get("dmin", 0.0)
+                cand._live()
+                v, p, ld = _f64(V)
+                lib.check(lib.collisions_build_from_candidates(mesh._ctx, p, ld, dhat, dmin, flags, counts))
+            else:
+                mesh, V, dhat = args[:3]
+                dmin = args[3] if len(args) > 3 else kw.get("dmin", 0.0)
+                v, p, ld = _f64(V)
+                lib.check(lib.collisions_build(mesh._ctx, p, ld, dhat, dmin, flags, counts))
+                mesh._cand_gen += 1  # the resident candidates were rebuilt too
+            self.mesh = mesh
+            mesh._coll_gen += 1
+            self._gen = mesh._coll_gen
+            self._counts = list(counts)
+            self._host = {}
+            self.dmin = dmin
+
+        def _live(self):
+            if self.mesh is None or self._gen != self.mesh._coll_gen:
+                raise RuntimeError("stale NormalCollisions handle: a newer collision set was built on this mesh")
+
+        def _get(self, kind):
+            self._live()
+            if kind not in self._host:
+                n = self._counts[kind]
+                ids = np.zeros((n, 2), np.int32)
+                w = np.zeros(n)
+                eps = np.zeros(n)
+                dt = np.zeros(n, np.uint8)
+                if n:
+                    lib.check(lib.collisions_fetch(self.mesh._ctx, kind, ids.ctypes.data_as(C.c_void_p),
+                                                   w.ctypes.data_as(C.c_void_p), eps.ctypes.data_as(C.c_void_p),
+                                                   dt.ctypes.data_as(C.c_void_p)))
+                self._host[kind] = types.SimpleNamespace(ids=ids, weight=w, eps_x=eps, dtype=dt)
+            return self._host[kind]
+
+        vv_collisions = property(lambda self: self._get(VV))
+        ev_collisions = property(lambda self: self._get(EV))
+        ee_collisions = property(lambda self: self._get(EE))
+        fv_collisions = property(lambda self: self._get(FV))
+
+        def counts(self):
+            return list(self._counts)
+
+        def size(self):
+            return int(sum(self._counts))
+
+        __len__ = size
+
+        def empty(self):
+            return self.size() == 0
+
+        def compute_minimum_distance(self, mesh, vertices):
+            self._live()
+            v, p, ld = _f64(vertices)
+            out = C.c_double()
+            lib.check(lib.collisions_min_distance(mesh._ctx, p, ld, C.byref(out)))
+            return out.value
+
+    class BarrierPotential:
+        """ipc::BarrierPotential(dhat, stiffness, use_physical_barrier) — potentials/potential.cpp:36-222"""
+
+        def __init__(self, dhat, stiffness=1.0, use_physical_barrier=False):
+            self.dhat = dhat
+            self.stiffness = stiffness
+            self.use_physical_barrier = use_physical_barrier
+
+        def _bp(self):
+            return _abi.BarrierParams(self.dhat, self.stiffness, int(self.use_physical_barrier))
+
+        def __call__(self, collisions, mesh, X):
+            collisions._live()
+            x, p, ld = _f64(X)
+            e = C.c_double()
+            bp = self._bp()
+            lib.check(lib.barrier_energy(mesh._ctx, p, ld, C.byref(bp), C.byref(e)))
+            return e.value
+
+        def gradient(self, collisions, mesh, X):
+            collisions._live()
+            x, p, ld = _f64(X)
+            g = np.zeros(3 * mesh.num_vertices())
+            bp = self._bp()
+            lib.check(lib.barrier_gradient(mesh._ctx, p, ld, C.byref(bp), g.ctypes.data_as(C.c_void_p)))
+            return g
+
+        def hessian(self, collisions, mesh, X, project_hessian_to_psd=PSDProjectionMethod.NONE):
+            import scipy.sparse as sp
+
+            collisions._live()
+            x, p, ld = _f64(X)
+            nnz = C.c_int64()
+            bp = self._bp()
+            lib.check(lib.barrier_hessian(mesh._ctx, p, ld, C.byref(bp), int(project_hessian_to_psd), C.byref(nnz)))
+            n = 3 * mesh.num_vertices()
+            outer = np.zeros(n + 1, np.int32)
+            inner = np.zeros(nnz.value, np.int32)
+            vals = np.zeros(nnz.value)
+            lib.check(lib.barrier_hessian_fetch(mesh._ctx, outer.ctypes.data_as(C.c_void_p),
+                                                inner.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p)))
+            return sp.csc_matrix((vals, inner, outer), shape=(n, n))
+
+    def compute_collision_free_stepsize(mesh, vertices_t0, vertices_t1, min_distance=0.0, broad_phase=None,
+                                        narrow_phase_ccd=None):
+        """ipc::compute_collision_free_stepsize — ipc.cpp:45-101"""
+        ccd = (narrow_phase_ccd or TightInclusionCCD())._params()
+        v0, p0, ld = _f64(vertices_t0)
+        v1, p1, _ = _f64(vertices_t1)
+        step = C.c_double()
+        lib.check(lib.ccd_stepsize(mesh._ctx, p0, p1, ld, min_distance, C.byref(ccd), C.byref(step)))
+        mesh._cand_gen += 1
+        return step.value
+
+    def is_step_collision_free(mesh, vertices_t0, vertices_t1, min_distance=0.0, broad_phase=None, narrow_phase_ccd=None):
+        """ipc::is_step_collision_free — ipc.cpp:20-43"""
+        return compute_collision_free_stepsize(mesh, vertices_t0, vertices_t1, min_distance, broad_phase,
+                                               narrow_phase_ccd) >= 1.0
+
+    def narrow_phase_ccd(kind, x_t0, x_t1, min_distance=0.0, tmax=1.0, ccd=None, mesh=None):
+        """batched NarrowPhaseCCD queries (ccd/narrow_phase_ccd.hpp:8-119): x_* are (n, 4, 3) arrays"""
+        a = np.ascontiguousarray(x_t0, dtype=np.float64).reshape(-1, 12)
+        b = np.ascontiguousarray(x_t1, dtype=np.float64).reshape(-1, 12)
+        n = a.shape[0]
+        hit = np.zeros(n, np.uint8)
+        toi = np.zeros(n)
+        params = (ccd or TightInclusionCCD())._params()
+        own = None
+        if mesh is None:
+            own = CollisionMesh(np.zeros((1, 3)))
+            mesh = own
+        lib.check(lib.ccd_narrow_phase(mesh._ctx, kind, n, a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                       min_distance, tmax, C.byref(params), hit.ctypes.data_as(C.c_void_p),
+                                       toi.ctypes.data_as(C.c_void_p)))
+        return hit.astype(bool), toi
+
+    ns.CollisionMesh = CollisionMesh
+    ns.BroadPhase = BroadPhase
+    ns.Candidates = Candidates
+    ns.NormalCollisions = NormalCollisions
+    ns.BarrierPotential = BarrierPotential
+    ns.compute_collision_free_stepsize = compute_collision_free_stepsize
+    ns.is_step_collision_free = is_step_collision_free
+    ns.narrow_phase_ccd = narrow_phase_ccd
+    return ns

@@ -1,0 +1,1203 @@
+// oracle/oracle.cpp — TEST INFRASTRUCTURE ONLY (CPU restatement, never shipped).
+//
+// CPU restatement of ipc-toolkit v1.6.0's per-step contact pipeline, exported
+// through the host half of include/ipcb200.h with the prefix ipco_.  Only
+// tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs may load this library; the product (libipcb200.so) never does.
+//
+// Each block cites the reference file:line (under src/ipc/) it follows.
+// OpenMP parallelises the same loops the reference parallelises with TBB.
+#define IPCB_ORACLE 1
+#define IPCB_PREFIX ipco_
+#include "../include/ipcb200.h"
+
+#include "geom.hpp"
+#include "eig.hpp"
+#include "ccd.hpp"
+
+#include <omp.h>
+#include <parallel/algorithm>
+#include <array>
+#include <atomic>
+#include <cfloat>
+#include <cstdio>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+using namespace oracle;
+
+namespace {
+
+thread_local std::string g_error;
+int fail(const std::string& msg)
+{
+    g_error = msg;
+    return 1;
+}
+
+struct Box {
+    double lo[3], hi[3];
+};
+inline bool overlaps(const Box& a, const Box& b)
+{
+    // closed-interval test: aabb.cpp:29-33 (double) / lbvh.hpp:66-70 (float)
+    return a.lo[0] <= b.hi[0] && b.lo[0] <= a.hi[0] && a.lo[1] <= b.hi[1] && b.lo[1] <= a.hi[1] && a.lo[2] <= b.hi[2]
+        && b.lo[2] <= a.hi[2];
+}
+inline Box box_union(const Box& a, const Box& b)
+{
+    Box r;
+    for (int c = 0; c < 3; c++) {
+        r.lo[c] = std::min(a.lo[c], b.lo[c]);
+        r.hi[c] = std::max(a.hi[c], b.hi[c]);
+    }
+    return r;
+}
+
+using Pair = std::array<int32_t, 2>;
+
+struct Coll {
+    int32_t a, b;
+    double w;
+    double eps_x;
+    uint8_t dtype;
+};
+
+} // namespace
+
+struct ipcb_ctx {
+    int nV = 0, nE = 0, nF = 0;
+    std::vector<V3> rest;
+    std::vector<int32_t> E, F, F2E; // row-major nE x 2, nF x 3, nF x 3
+    std::vector<int32_t> codim_vertices, codim_edges;
+    std::vector<double> vertex_areas, edge_areas;
+    // broad phase
+    int boxes_mode = IPCB_BOXES_FLOAT;
+    bool built = false;
+    std::vector<Box> vbox, ebox, fbox;
+    std::vector<Pair> detected[6];
+    int broad_method = 0; // 0 = auto (LBVH above 2048 boxes), 1 = brute force, 2 = LBVH
+    // candidates + collisions
+    std::vector<Pair> cand[4];
+    std::vector<Coll> coll[4];
+    double dmin = 0;
+    // hessian
+    std::vector<int32_t> outer, inner;
+    std::vector<double> vals;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// boxes: broad_phase/aabb.cpp:35-126, lbvh.cpp:29-41
+Box vertex_box(V3 p, double r, int mode)
+{
+    Box b;
+    const double inf = std::numeric_limits<double>::infinity();
+    const float finf = std::numeric_limits<float>::infinity();
+    for (int c = 0; c < 3; c++) {
+        double lo = std::nextafter(p[c] - r, -inf);
+        double hi = std::nextafter(p[c] + r, inf);
+        if (mode == IPCB_BOXES_FLOAT) {
+            lo = std::nextafter(float(lo), -finf);
+            hi = std::nextafter(float(hi), finf);
+        }
+        b.lo[c] = lo;
+        b.hi[c] = hi;
+    }
+    return b;
+}
+
+void build_boxes(ipcb_ctx* ctx, const std::vector<V3>& V0, const std::vector<V3>* V1, double r, int mode)
+{
+    const int nV = ctx->nV;
+    ctx->boxes_mode = mode;
+    ctx->vbox.resize(nV);
+#pragma omp parallel for
+    for (int i = 0; i < nV; i++) {
+        Box b = vertex_box(V0[i], r, mode);
+        if (V1) b = box_union(b, vertex_box((*V1)[i], r, mode)); // aabb.hpp:42-50
+        ctx->vbox[i] = b;
+    }
+    ctx->ebox.resize(ctx->nE);
+#pragma omp parallel for
+    for (int i = 0; i < ctx->nE; i++) ctx->ebox[i] = box_union(ctx->vbox[ctx->E[2 * i]], ctx->vbox[ctx->E[2 * i + 1]]);
+    ctx->fbox.resize(ctx->nF);
+#pragma omp parallel for
+    for (int i = 0; i < ctx->nF; i++)
+        ctx->fbox[i] = box_union(box_union(ctx->vbox[ctx->F[3 * i]], ctx->vbox[ctx->F[3 * i + 1]]), ctx->vbox[ctx->F[3 * i + 2]]);
+    ctx->built = true;
+}
+
+// ---------------------------------------------------------------------------
+// Morton code: math/morton.hpp:23-63
+inline uint64_t expand_bits_2(uint64_t v)
+{
+    v = (v | v << 32) & 0x1F00000000FFFFull;
+    v = (v | v << 16) & 0x1F0000FF0000FFull;
+    v = (v | v << 8) & 0x100F00F00F00F00Full;
+    v = (v | v << 4) & 0x10C30C30C30C30C3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+inline uint64_t morton_3D(double x, double y, double z)
+{
+    constexpr double scale = double(1ull << 21);
+    x = std::clamp(x * scale, 0.0, scale - 1);
+    y = std::clamp(y * scale, 0.0, scale - 1);
+    z = std::clamp(z * scale, 0.0, scale - 1);
+    return (expand_bits_2(uint64_t(x)) << 2) | (expand_bits_2(uint64_t(y)) << 1) | expand_bits_2(uint64_t(z));
+}
+
+// ---------------------------------------------------------------------------
+// CPU LBVH (broad_phase/lbvh.cpp:134-330 builds with Apetrei's bottom-up pass;
+// here the equivalent radix tree is built with Karras' per-node range search.
+// The candidate SET does not depend on the tree: SURVEY §7 hard part 1).
+struct LBVH {
+    struct Node {
+        Box box;
+        int left, right; // children (index into nodes); leaf: left = -1, right = primitive id
+        int last;        // last (rightmost) sorted leaf below this node
+    };
+    int n = 0;
+    std::vector<Node> nodes; // [0, n-1) internal, [n-1, 2n-1) leaves in Morton order
+    std::vector<int> order;  // sorted position -> primitive id
+
+    void build(const std::vector<Box>& boxes)
+    {
+        n = int(boxes.size());
+        nodes.clear();
+        order.clear();
+        if (n == 0) return;
+        Box mesh = boxes[0];
+        for (const Box& b : boxes) mesh = box_union(mesh, b); // broad_phase.cpp:93-125
+        struct Key {
+            uint64_t code;
+            int id;
+        };
+        std::vector<Key> keys(n);
+#pragma omp parallel for
+        for (int i = 0; i < n; i++) { // lbvh.cpp:150-168
+            double m[3];
+            for (int c = 0; c < 3; c++) {
+                const double w = mesh.hi[c] - mesh.lo[c];
+                m[c] = w > 0 ? (0.5 * (boxes[i].lo[c] + boxes[i].hi[c]) - mesh.lo[c]) / w : 0.0;
+            }
+            keys[i] = { morton_3D(m[0], m[1], m[2]), i };
+        }
+        __gnu_parallel::sort(keys.begin(), keys.end(), [](const Key& a, const Key& b) {
+            return a.code != b.code ? a.code < b.code : a.id < b.id;
+        });
+        order.resize(n);
+        nodes.resize(2 * n - 1);
+        for (int i = 0; i < n; i++) {
+            order[i] = keys[i].id;
+            nodes[n - 1 + i] = { boxes[keys[i].id], -1, keys[i].id, i };
+        }
+        if (n == 1) return;
+        auto delta = [&](int i, int j) -> int { // lbvh.cpp:104-131
+            if (j < 0 || j >= n) return -1;
+            const uint64_t a = keys[i].code, b = keys[j].code;
+            if (a == b) return 64 + __builtin_clz(unsigned(i) ^ unsigned(j));
+            return __builtin_clzll(a ^ b);
+        };
+        std::vector<int> parent(2 * n - 1, -1);
+#pragma omp parallel for
+        for (int i = 0; i < n - 1; i++) {
+            const int d = delta(i, i + 1) > delta(i, i - 1) ? 1 : -1;
+            const int dmin = delta(i, i - d);
+            int lmax = 2;
+            while (delta(i, i + lmax * d) > dmin) lmax *= 2;
+            int l = 0;
+            for (int t = lmax / 2; t >= 1; t /= 2)
+                if (delta(i, i + (l + t) * d) > dmin) l += t;
+            const int j = i + l * d;
+            const int dnode = delta(i, j);
+            int s = 0;
+            int t = l;
+            do {
+                t = (t + 1) >> 1;
+                if (delta(i, i + (s + t) * d) > dnode) s += t;
+            } while (t > 1);
+            const int gamma = i + s * d + std::min(d, 0);
+            const int lo = std::min(i, j), hi = std::max(i, j);
+            const int left = (lo == gamma) ? (n - 1 + gamma) : gamma;
+            const int right = (hi == gamma + 1) ? (n - 1 + gamma + 1) : gamma + 1;
+            nodes[i].left = left;
+            nodes[i].right = right;
+            nodes[i].last = hi;
+            parent[left] = i;
+            parent[right] = i;
+        }
+        // bottom-up refit
+        std::vector<std::atomic<int>> visits(n - 1);
+        for (auto& v : visits) v.store(0);
+#pragma omp parallel for
+        for (int i = 0; i < n; i++) {
+            int node = parent[n - 1 + i];
+            while (node >= 0) {
+                if (visits[node].fetch_add(1) == 0) break;
+                nodes[node].box = box_union(nodes[nodes[node].left].box, nodes[nodes[node].right].box);
+                node = parent[node];
+            }
+        }
+    }
+
+    // all leaves whose box overlaps q; triangular: only sorted leaves > query_leaf (lbvh.cpp:368-460)
+    template <typename Emit> void query(const Box& q, int query_leaf, bool triangular, const Emit& emit) const
+    {
+        if (n == 0) return;
+        if (n == 1) {
+            if (!triangular && overlaps(nodes[0].box, q)) emit(nodes[0].right);
+            return;
+        }
+        int stack[128];
+        int sp = 0;
+        stack[sp++] = 0;
+        while (sp) {
+            const Node& node = nodes[stack[--sp]];
+            for (int child : { node.left, node.right }) {
+                const Node& c = nodes[child];
+                if (!overlaps(c.box, q)) continue;
+                if (triangular && c.last <= query_leaf) continue;
+                if (c.left < 0) {
+                    emit(c.right);
+                } else {
+                    stack[sp++] = child;
+                }
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// detection over two box sets with a can_collide predicate
+// (brute_force.cpp:15-61 / lbvh.cpp:692-797); pairs are (a in A, b in B);
+// same-set detection reports each unordered pair once as (min, max).
+template <typename CanCollide>
+void detect_pairs(const ipcb_ctx* ctx, const std::vector<Box>& A, const std::vector<Box>& B, bool same, const CanCollide& can_collide,
+                  std::vector<Pair>& out)
+{
+    out.clear();
+    const int nA = int(A.size()), nB = int(B.size());
+    if (nA == 0 || nB == 0 || (same && nA < 2)) return;
+    const bool brute = ctx->broad_method == 1 || (ctx->broad_method == 0 && std::max(nA, nB) <= 2048);
+    std::vector<std::vector<Pair>> local(omp_get_max_threads());
+    if (brute) {
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int i = 0; i < nA; i++) {
+            auto& mine = local[omp_get_thread_num()];
+            for (int j = same ? i + 1 : 0; j < nB; j++)
+                if (overlaps(A[i], B[j]) && can_collide(i, j)) mine.push_back({ i, j });
+        }
+    } else {
+        LBVH target;
+        target.build(B);
+        if (same) {
+#pragma omp parallel for schedule(dynamic, 64)
+            for (int qi = 0; qi < nA; qi++) {
+                auto& mine = local[omp_get_thread_num()];
+                const int i = target.order[qi];
+                target.query(A[i], qi, true, [&](int j) {
+                    if (can_collide(i, j)) mine.push_back({ std::min(i, j), std::max(i, j) });
+                });
+            }
+        } else {
+            LBVH source; // query leaves in Morton order like lbvh.cpp:633-690
+            source.build(A);
+#pragma omp parallel for schedule(dynamic, 64)
+            for (int qi = 0; qi < nA; qi++) {
+                auto& mine = local[omp_get_thread_num()];
+                const int i = source.order[qi];
+                target.query(A[i], -1, false, [&](int j) {
+                    if (can_collide(i, j)) mine.push_back({ i, j });
+                });
+            }
+        }
+    }
+    size_t total = 0;
+    for (auto& l : local) total += l.size();
+    out.reserve(total);
+    for (auto& l : local) out.insert(out.end(), l.begin(), l.end()); // utils/merge_thread_local.hpp:21-84
+}
+
+void sort_pairs(std::vector<Pair>& p) { __gnu_parallel::sort(p.begin(), p.end()); }
+
+// share-a-vertex rejection (lbvh.cpp:801-873) with can_vertices_collide == true
+void broad_detect_kind(ipcb_ctx* ctx, int kind, std::vector<Pair>& out)
+{
+    const int32_t* E = ctx->E.data();
+    const int32_t* F = ctx->F.data();
+    switch (kind) {
+    case IPCB_VV:
+        detect_pairs(ctx, ctx->vbox, ctx->vbox, true, [](int, int) { return true; }, out);
+        break;
+    case IPCB_EV:
+        detect_pairs(ctx, ctx->ebox, ctx->vbox, false, [=](int e, int v) { return v != E[2 * e] && v != E[2 * e + 1]; }, out);
+        break;
+    case IPCB_EE:
+        detect_pairs(
+            ctx, ctx->ebox, ctx->ebox, true,
+            [=](int a, int b) {
+                return E[2 * a] != E[2 * b] && E[2 * a] != E[2 * b + 1] && E[2 * a + 1] != E[2 * b] && E[2 * a + 1] != E[2 * b + 1];
+            },
+            out);
+        break;
+    case IPCB_FV:
+        detect_pairs(ctx, ctx->fbox, ctx->vbox, false, [=](int f, int v) { return v != F[3 * f] && v != F[3 * f + 1] && v != F[3 * f + 2]; },
+                     out);
+        break;
+    case IPCB_EF:
+        detect_pairs(
+            ctx, ctx->ebox, ctx->fbox, false,
+            [=](int e, int f) {
+                for (int a = 0; a < 2; a++)
+                    for (int b = 0; b < 3; b++)
+                        if (E[2 * e + a] == F[3 * f + b]) return false;
+                return true;
+            },
+            out);
+        break;
+    case IPCB_FF:
+        detect_pairs(
+            ctx, ctx->fbox, ctx->fbox, true,
+            [=](int fa, int fb) {
+                for (int a = 0; a < 3; a++)
+                    for (int b = 0; b < 3; b++)
+                        if (F[3 * fa + a] == F[3 * fb + b]) return false;
+                return true;
+            },
+            out);
+        break;
+    }
+    sort_pairs(out);
+}
+
+std::vector<V3> load_vertices(int n, const double* V, int ld)
+{
+    std::vector<V3> out(n);
+    for (int i = 0; i < n; i++) out[i] = { V[i], V[i + ld], V[i + 2 * size_t(ld)] };
+    return out;
+}
+
+// Candidates::build (candidates/candidates.cpp:43-222), 3D
+void candidates_build(ipcb_ctx* ctx, const std::vector<V3>& V0, const std::vector<V3>* V1, double r)
+{
+    for (auto& c : ctx->cand) c.clear();
+    build_boxes(ctx, V0, V1, r, IPCB_BOXES_FLOAT);
+    broad_detect_kind(ctx, IPCB_EE, ctx->cand[IPCB_EE]); // broad_phase.cpp:79-91
+    broad_detect_kind(ctx, IPCB_FV, ctx->cand[IPCB_FV]);
+    const auto& cv = ctx->codim_vertices;
+    const auto& ce = ctx->codim_edges;
+    if (!cv.empty()) { // :66-77 codim vertices vs codim vertices
+        std::vector<Box> vb(cv.size());
+        for (size_t i = 0; i < cv.size(); i++) vb[i] = ctx->vbox[cv[i]];
+        std::vector<Pair> vv;
+        detect_pairs(ctx, vb, vb, true, [](int, int) { return true; }, vv);
+        for (auto& p : vv) p = { std::min(cv[p[0]], cv[p[1]]), std::max(cv[p[0]], cv[p[1]]) };
+        sort_pairs(vv);
+        ctx->cand[IPCB_VV] = vv;
+    }
+    if (!cv.empty() && !ce.empty()) { // :83-116 codim edges vs codim vertices
+        std::vector<Box> vb(cv.size()), eb(ce.size());
+        for (size_t i = 0; i < cv.size(); i++) vb[i] = ctx->vbox[cv[i]];
+        for (size_t i = 0; i < ce.size(); i++) eb[i] = ctx->ebox[ce[i]];
+        std::vector<Pair> ev;
+        // codim vertices are never endpoints of an edge, so no share-vertex case
+        detect_pairs(ctx, eb, vb, false, [](int, int) { return true; }, ev);
+        for (auto& p : ev) p = { ce[p[0]], cv[p[1]] };
+        sort_pairs(ev);
+        ctx->cand[IPCB_EV] = ev;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// stencils (candidates/*.cpp vertex_ids): VV [v0,v1]; EV [v,e0,e1];
+// EE [ea0,ea1,eb0,eb1]; FV [v,f0,f1,f2]
+int stencil_ids(const ipcb_ctx* ctx, int kind, int a, int b, int32_t ids[4])
+{
+    const int32_t* E = ctx->E.data();
+    const int32_t* F = ctx->F.data();
+    switch (kind) {
+    case IPCB_VV: ids[0] = a, ids[1] = b; return 2;
+    case IPCB_EV: ids[0] = b, ids[1] = E[2 * a], ids[2] = E[2 * a + 1]; return 3;
+    case IPCB_EE: ids[0] = E[2 * a], ids[1] = E[2 * a + 1], ids[2] = E[2 * b], ids[3] = E[2 * b + 1]; return 4;
+    default: ids[0] = b, ids[1] = F[3 * a], ids[2] = F[3 * a + 1], ids[3] = F[3 * a + 2]; return 4;
+    }
+}
+
+// NormalCollisions::build(candidates, ...) — normal_collisions.cpp:38-158 with
+// the IPC set type, builder.cpp:26-336 (classification + reduction) and
+// :547-689 (merge with weight accumulation, weight == 0 dropped)
+void collisions_build(ipcb_ctx* ctx, const std::vector<V3>& V, double dhat, double dmin, int flags)
+{
+    const bool area = flags & IPCB_USE_AREA_WEIGHTING;
+    const double offset_sqr = (dmin + dhat) * (dmin + dhat);
+    auto is_active = [&](double d_sqr) { return d_sqr < offset_sqr; };
+    const int32_t* E = ctx->E.data();
+    const int32_t* F = ctx->F.data();
+    const int nt = omp_get_max_threads();
+    std::vector<std::vector<Coll>> loc[4];
+    for (auto& l : loc) l.resize(nt);
+    auto add_vv = [&](int t, int vi, int vj, double w) { loc[IPCB_VV][t].push_back({ std::min(vi, vj), std::max(vi, vj), w, 0, 0 }); };
+    auto add_ev = [&](int t, int ei, int vi, double w) { loc[IPCB_EV][t].push_back({ ei, vi, w, 0, 0 }); };
+
+    const auto& vvc = ctx->cand[IPCB_VV];
+#pragma omp parallel for
+    for (size_t i = 0; i < vvc.size(); i++) { // builder.cpp:26-56
+        const int t = omp_get_thread_num();
+        const int vi = vvc[i][0], vj = vvc[i][1];
+        if (!is_active(point_point_distance(V[vi], V[vj]))) continue;
+        add_vv(t, vi, vj, area ? 0.5 * (ctx->vertex_areas[vi] + ctx->vertex_areas[vj]) : 1);
+    }
+    const auto& evc = ctx->cand[IPCB_EV];
+#pragma omp parallel for
+    for (size_t i = 0; i < evc.size(); i++) { // builder.cpp:58-138
+        const int t = omp_get_thread_num();
+        const int ei = evc[i][0], vi = evc[i][1];
+        const V3 v = V[vi], e0 = V[E[2 * ei]], e1 = V[E[2 * ei + 1]];
+        const PE dtype = point_edge_distance_type(v, e0, e1);
+        if (!is_active(point_edge_distance(v, e0, e1, dtype))) continue;
+        const double w = area ? 0.5 * ctx->vertex_areas[vi] : 1;
+        switch (dtype) {
+        case PE_P_E0: add_vv(t, vi, E[2 * ei], w); break;
+        case PE_P_E1: add_vv(t, vi, E[2 * ei + 1], w); break;
+        default: add_ev(t, ei, vi, w); break;
+        }
+    }
+    const auto& eec = ctx->cand[IPCB_EE];
+#pragma omp parallel for
+    for (size_t i = 0; i < eec.size(); i++) { // builder.cpp:140-237
+        const int t = omp_get_thread_num();
+        const int eai = eec[i][0], ebi = eec[i][1];
+        const int ea0i = E[2 * eai], ea1i = E[2 * eai + 1], eb0i = E[2 * ebi], eb1i = E[2 * ebi + 1];
+        const V3 ea0 = V[ea0i], ea1 = V[ea1i], eb0 = V[eb0i], eb1 = V[eb1i];
+        const EE actual_dtype = edge_edge_distance_type(ea0, ea1, eb0, eb1);
+        if (!is_active(edge_edge_distance(ea0, ea1, eb0, eb1, actual_dtype))) continue;
+        const double eps_x = edge_edge_mollifier_threshold(ctx->rest[ea0i], ctx->rest[ea1i], ctx->rest[eb0i], ctx->rest[eb1i]);
+        const double ee_cross_norm_sqr = edge_edge_cross_squarednorm(ea0, ea1, eb0, eb1);
+        const EE dtype = ee_cross_norm_sqr < eps_x ? EE_EA_EB : actual_dtype;
+        const double w = area ? 0.25 * (ctx->edge_areas[eai] + ctx->edge_areas[ebi]) : 1;
+        switch (dtype) {
+        case EE_EA0_EB0: add_vv(t, ea0i, eb0i, w); break;
+        case EE_EA0_EB1: add_vv(t, ea0i, eb1i, w); break;
+        case EE_EA1_EB0: add_vv(t, ea1i, eb0i, w); break;
+        case EE_EA1_EB1: add_vv(t, ea1i, eb1i, w); break;
+        case EE_EA_EB0: add_ev(t, eai, eb0i, w); break;
+        case EE_EA_EB1: add_ev(t, eai, eb1i, w); break;
+        case EE_EA0_EB: add_ev(t, ebi, ea0i, w); break;
+        case EE_EA1_EB: add_ev(t, ebi, ea1i, w); break;
+        default: loc[IPCB_EE][t].push_back({ eai, ebi, w, eps_x, uint8_t(actual_dtype) }); break;
+        }
+    }
+    const auto& fvc = ctx->cand[IPCB_FV];
+#pragma omp parallel for
+    for (size_t i = 0; i < fvc.size(); i++) { // builder.cpp:239-336
+        const int t = omp_get_thread_num();
+        const int fi = fvc[i][0], vi = fvc[i][1];
+        const int f0i = F[3 * fi], f1i = F[3 * fi + 1], f2i = F[3 * fi + 2];
+        const V3 v = V[vi], f0 = V[f0i], f1 = V[f1i], f2 = V[f2i];
+        const PT dtype = point_triangle_distance_type(v, f0, f1, f2);
+        if (!is_active(point_triangle_distance(v, f0, f1, f2, dtype))) continue;
+        const double w = area ? 0.25 * ctx->vertex_areas[vi] : 1;
+        switch (dtype) {
+        case PT_P_T0: add_vv(t, vi, f0i, w); break;
+        case PT_P_T1: add_vv(t, vi, f1i, w); break;
+        case PT_P_T2: add_vv(t, vi, f2i, w); break;
+        case PT_P_E0: add_ev(t, ctx->F2E[3 * fi + 0], vi, w); break;
+        case PT_P_E1: add_ev(t, ctx->F2E[3 * fi + 1], vi, w); break;
+        case PT_P_E2: add_ev(t, ctx->F2E[3 * fi + 2], vi, w); break;
+        default: loc[IPCB_FV][t].push_back({ fi, vi, w, 0, 0 }); break;
+        }
+    }
+    // merge (builder.cpp:604-689); canonical order = sorted by (a, b, dtype)
+    for (int k = 0; k < 4; k++) {
+        std::vector<Coll> all;
+        for (auto& l : loc[k]) all.insert(all.end(), l.begin(), l.end());
+        __gnu_parallel::stable_sort(all.begin(), all.end(), [](const Coll& x, const Coll& y) {
+            if (x.a != y.a) return x.a < y.a;
+            if (x.b != y.b) return x.b < y.b;
+            return x.dtype < y.dtype;
+        });
+        std::vector<Coll>& out = ctx->coll[k];
+        out.clear();
+        for (const Coll& c : all) {
+            if (k != IPCB_FV && !out.empty() && out.back().a == c.a && out.back().b == c.b && out.back().dtype == c.dtype) {
+                out.back().w += c.w;
+            } else {
+                out.push_back(c);
+            }
+        }
+        if (k != IPCB_FV) {
+            out.erase(std::remove_if(out.begin(), out.end(), [](const Coll& c) { return c.w == 0; }), out.end());
+        }
+    }
+    ctx->dmin = dmin; // normal_collisions.cpp:154-157
+}
+
+// ---------------------------------------------------------------------------
+// per-collision calculus: potentials/normal_potential.cpp:127-232,
+// barrier_potential.cpp:62-99
+struct Barrier {
+    double dhat, kappa;
+    bool physical;
+    double scale(double dmin) const
+    {
+        // physical barrier: dhat / units(x_hat) with ClampedLogBarrier::units(x) = x * x
+        // (barrier/barrier.hpp:133-137, potentials/barrier_potential.cpp:68-70)
+        const double xhat = (2 * dmin + dhat) * dhat;
+        return physical ? dhat / (xhat * xhat) : 1.0;
+    }
+    double f(double d_sqr, double dmin) const
+    {
+        return kappa * (barrier(d_sqr - dmin * dmin, (2 * dmin + dhat) * dhat) * (physical ? scale(dmin) : 1.0));
+    }
+    double df(double d_sqr, double dmin) const
+    {
+        return kappa * (barrier_first_derivative(d_sqr - dmin * dmin, (2 * dmin + dhat) * dhat) * (physical ? scale(dmin) : 1.0));
+    }
+    double ddf(double d_sqr, double dmin) const
+    {
+        return kappa * (barrier_second_derivative(d_sqr - dmin * dmin, (2 * dmin + dhat) * dhat) * (physical ? scale(dmin) : 1.0));
+    }
+};
+
+Embed collision_embed(int kind, const Coll& c)
+{
+    switch (kind) {
+    case IPCB_VV: return { PRIM_PP, 2, { 0, 1, 0, 0 } };
+    case IPCB_EV: return embed_point_edge(PE_P_E);            // collisions/normal/edge_vertex.hpp:28-32
+    case IPCB_EE: return embed_edge_edge(EE(c.dtype));        // collisions/normal/edge_edge.hpp:96
+    default: return embed_point_triangle(PT_P_T);             // collisions/normal/face_vertex.hpp:28-32
+    }
+}
+
+double collision_energy(int kind, const Coll& c, const V3* x, const Barrier& B, double dmin)
+{
+    const double d = prim_value(collision_embed(kind, c), x);
+    double m = 1;
+    if (kind == IPCB_EE) m = edge_edge_mollifier(edge_edge_cross_squarednorm(x[0], x[1], x[2], x[3]), c.eps_x);
+    return c.w * m * B.f(d, dmin);
+}
+
+// local gradient (n = 3 * npts)
+void collision_gradient(int kind, const Coll& c, const V3* x, const Barrier& B, double dmin, double* g)
+{
+    const int n = 3 * (kind == IPCB_VV ? 2 : kind == IPCB_EV ? 3 : 4);
+    double m = 1;
+    double s = 0;
+    if (kind == IPCB_EE) {
+        s = edge_edge_cross_squarednorm(x[0], x[1], x[2], x[3]);
+        m = edge_edge_mollifier(s, c.eps_x);
+    }
+    if (m <= 0) { // normal_potential.cpp:143-147
+        for (int i = 0; i < n; i++) g[i] = 0;
+        return;
+    }
+    Deriv D;
+    embed_deriv(collision_embed(kind, c), x, D);
+    const double f = B.f(D.val, dmin), grad_f = B.df(D.val, dmin);
+    if (kind != IPCB_EE) {
+        for (int i = 0; i < n; i++) g[i] = (c.w * grad_f) * D.g[i];
+        return;
+    }
+    Deriv S;
+    if (s < c.eps_x) {
+        edge_edge_cross_squarednorm_deriv(x[0], x[1], x[2], x[3], S);
+    } else {
+        S.zero();
+    }
+    const double dm = edge_edge_mollifier_gradient(s, c.eps_x);
+    for (int i = 0; i < n; i++) {
+        const double grad_m = s < c.eps_x ? dm * S.g[i] : 0.0;
+        g[i] = (c.w * f) * grad_m + (c.w * m * grad_f) * D.g[i];
+    }
+}
+
+// local hessian (n x n col-major, ld 12), PSD-projected
+void collision_hessian(int kind, const Coll& c, const V3* x, const Barrier& B, double dmin, int psd_mode, double* H)
+{
+    const int n = 3 * (kind == IPCB_VV ? 2 : kind == IPCB_EV ? 3 : 4);
+    Deriv D;
+    embed_deriv(collision_embed(kind, c), x, D);
+    const double d = D.val;
+    auto h = [&](int r, int cc) -> double& { return H[r + 12 * cc]; };
+    if (kind != IPCB_EE) {
+        const double grad_f = B.df(d, dmin), hess_f = B.ddf(d, dmin);
+        for (int j = 0; j < n; j++)
+            for (int i = 0; i < n; i++) h(i, j) = (c.w * hess_f) * D.g[i] * D.g[j] + (c.w * grad_f) * D.h(i, j);
+    } else {
+        const double s = edge_edge_cross_squarednorm(x[0], x[1], x[2], x[3]);
+        const double m = edge_edge_mollifier(s, c.eps_x);
+        Deriv S;
+        double grad_m[12], hess_m[144];
+        if (s < c.eps_x) {
+            edge_edge_cross_squarednorm_deriv(x[0], x[1], x[2], x[3], S);
+            const double dm = edge_edge_mollifier_gradient(s, c.eps_x), ddm = edge_edge_mollifier_hessian(s, c.eps_x);
+            for (int i = 0; i < 12; i++) grad_m[i] = dm * S.g[i];
+            for (int j = 0; j < 12; j++)
+                for (int i = 0; i < 12; i++) hess_m[i + 12 * j] = (dm * S.h(i, j)) + ((ddm * S.g[i]) * S.g[j]);
+        } else {
+            for (double& v : grad_m) v = 0;
+            for (double& v : hess_m) v = 0;
+        }
+        const double f = B.f(d, dmin);
+        if (m <= 0) { // normal_potential.cpp:184-189
+            for (int j = 0; j < 12; j++)
+                for (int i = 0; i < 12; i++) h(i, j) = (c.w * f) * hess_m[i + 12 * j];
+            return; // NOTE: the reference returns before project_to_psd here
+        }
+        const double grad_f = B.df(d, dmin), hess_f = B.ddf(d, dmin);
+        const double weighted_m = c.w * m;
+        for (int j = 0; j < 12; j++)
+            for (int i = 0; i < 12; i++) {
+                const double gfgm_ij = (c.w * grad_f) * D.g[i] * grad_m[j];
+                const double gfgm_ji = (c.w * grad_f) * D.g[j] * grad_m[i];
+                h(i, j) = (c.w * f) * hess_m[i + 12 * j] + gfgm_ij + gfgm_ji + (weighted_m * hess_f) * D.g[i] * D.g[j]
+                    + (weighted_m * grad_f) * D.h(i, j);
+            }
+    }
+    project_to_psd(n, H, 12, psd_mode);
+}
+
+template <typename Fn> void for_each_collision(const ipcb_ctx* ctx, const Fn& fn)
+{
+    for (int k = 0; k < 4; k++) {
+        const auto& cs = ctx->coll[k];
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < cs.size(); i++) fn(k, cs[i]);
+    }
+}
+
+ipcb_ccd_params resolve_ccd(const ipcb_ccd_params* p)
+{
+    ipcb_ccd_params r = p ? *p : ipcb_ccd_params { IPCB_CCD_TIGHT_INCLUSION, 0, 0, 0 };
+    if (r.kind == IPCB_CCD_ADDITIVE) {
+        if (r.max_iterations == 0) r.max_iterations = AdditiveCCD::DEFAULT_MAX_ITERATIONS;
+        if (r.conservative_rescaling <= 0) r.conservative_rescaling = AdditiveCCD::DEFAULT_CONSERVATIVE_RESCALING;
+    } else {
+        if (r.tolerance <= 0) r.tolerance = TightInclusionCCD::DEFAULT_TOLERANCE;
+        if (r.max_iterations == 0) r.max_iterations = TightInclusionCCD::DEFAULT_MAX_ITERATIONS;
+        if (r.conservative_rescaling <= 0) r.conservative_rescaling = TightInclusionCCD::DEFAULT_CONSERVATIVE_RESCALING;
+    }
+    return r;
+}
+
+bool narrow_ccd(int kind, const V3* t0, const V3* t1, double min_distance, double tmax, const ipcb_ccd_params& p, double& toi)
+{
+    if (p.kind == IPCB_CCD_ADDITIVE) {
+        AdditiveCCD a;
+        a.max_iterations = long(p.max_iterations);
+        a.conservative_rescaling = p.conservative_rescaling;
+        switch (kind) {
+        case IPCB_VV: return a.point_point_ccd(t0, t1, toi, min_distance, tmax);
+        case IPCB_EV: return a.point_edge_ccd(t0, t1, toi, min_distance, tmax);
+        case IPCB_EE: return a.edge_edge_ccd(t0, t1, toi, min_distance, tmax);
+        default: return a.point_triangle_ccd(t0, t1, toi, min_distance, tmax);
+        }
+    }
+    TightInclusionCCD ti;
+    ti.tolerance = p.tolerance;
+    ti.max_iterations = long(p.max_iterations);
+    ti.conservative_rescaling = p.conservative_rescaling;
+    switch (kind) {
+    case IPCB_VV: return ti.point_point_ccd(t0, t1, toi, min_distance, tmax);
+    case IPCB_EV: return ti.point_edge_ccd(t0, t1, toi, min_distance, tmax);
+    case IPCB_EE: return ti.edge_edge_ccd(t0, t1, toi, min_distance, tmax);
+    default: return ti.point_triangle_ccd(t0, t1, toi, min_distance, tmax);
+    }
+}
+
+// Candidates::compute_collision_free_stepsize (candidates.cpp:252-292)
+double stepsize_from_candidates(const ipcb_ctx* ctx, const std::vector<V3>& V0, const std::vector<V3>& V1, double min_distance,
+                                const ipcb_ccd_params& p)
+{
+    size_t total = 0;
+    for (auto& c : ctx->cand) total += c.size();
+    if (total == 0) return 1.0;
+    std::atomic<double> earliest_toi(1.0);
+    for (int k = 0; k < 4; k++) {
+        const auto& cs = ctx->cand[k];
+#pragma omp parallel for schedule(dynamic, 256)
+        for (size_t i = 0; i < cs.size(); i++) {
+            const double tmax = earliest_toi.load(std::memory_order_relaxed);
+            int32_t ids[4];
+            const int n = stencil_ids(ctx, k, cs[i][0], cs[i][1], ids);
+            V3 t0[4], t1[4];
+            for (int j = 0; j < n; j++) t0[j] = V0[ids[j]], t1[j] = V1[ids[j]];
+            double toi = std::numeric_limits<double>::infinity();
+            if (narrow_ccd(k, t0, t1, min_distance, tmax, p, toi)) {
+                double prev = earliest_toi.load(std::memory_order_relaxed);
+                while (toi < prev && !earliest_toi.compare_exchange_weak(prev, toi, std::memory_order_relaxed)) { }
+            }
+        }
+    }
+    return earliest_toi.load();
+}
+
+} // namespace
+
+// ===========================================================================
+// C ABI
+extern "C" {
+
+int ipco_ctx_create(int, ipcb_ctx** out)
+{
+    *out = new ipcb_ctx();
+    return 0;
+}
+void ipco_ctx_destroy(ipcb_ctx* ctx) { delete ctx; }
+const char* ipco_last_error(void) { return g_error.c_str(); }
+const char* ipco_backend_name(void) { return "oracle-cpu"; }
+void* ipco_ctx_stream(ipcb_ctx*) { return nullptr; }
+
+// oracle-only knobs (tests): broad phase method 0 auto / 1 brute force / 2 LBVH
+int ipco_set_broad_method(ipcb_ctx* ctx, int method)
+{
+    ctx->broad_method = method;
+    return 0;
+}
+int ipco_num_threads(void) { return omp_get_max_threads(); }
+void ipco_set_num_threads(int n) { omp_set_num_threads(n); }
+
+// CollisionMesh: collision_mesh.cpp:15-127, :145-183, :309-374, :510-543
+int ipco_mesh_set(ipcb_ctx* ctx, int32_t nV, const double* rest, int32_t ld_rest, int32_t nE, const int32_t* E, int32_t ldE,
+                  int32_t nF, const int32_t* F, int32_t ldF)
+{
+    ctx->nV = nV, ctx->nE = nE, ctx->nF = nF;
+    ctx->rest = load_vertices(nV, rest, ld_rest);
+    ctx->E.resize(2 * size_t(nE));
+    ctx->F.resize(3 * size_t(nF));
+    for (int i = 0; i < nE; i++)
+        for (int k = 0; k < 2; k++) {
+            const int v = E[i + size_t(ldE) * k];
+            if (v < 0 || v >= nV) return fail("edge vertex id out of range");
+            ctx->E[2 * i + k] = v;
+        }
+    for (int i = 0; i < nF; i++)
+        for (int k = 0; k < 3; k++) {
+            const int v = F[i + size_t(ldF) * k];
+            if (v < 0 || v >= nV) return fail("face vertex id out of range");
+            ctx->F[3 * i + k] = v;
+        }
+    // faces_to_edges (:510-543)
+    std::unordered_map<uint64_t, int> edge_map;
+    edge_map.reserve(nE * 2);
+    auto key = [](int a, int b) { return (uint64_t(uint32_t(std::min(a, b))) << 32) | uint32_t(std::max(a, b)); };
+    for (int i = 0; i < nE; i++) edge_map.emplace(key(ctx->E[2 * i], ctx->E[2 * i + 1]), i);
+    ctx->F2E.resize(3 * size_t(nF));
+    for (int i = 0; i < nF; i++)
+        for (int k = 0; k < 3; k++) {
+            auto it = edge_map.find(key(ctx->F[3 * i + k], ctx->F[3 * i + (k + 1) % 3]));
+            if (it == edge_map.end()) return fail("Unable to find edge!");
+            ctx->F2E[3 * i + k] = it->second;
+        }
+    // codim vertices / edges (:145-183)
+    std::vector<char> is_codim_v(nV, 1), is_codim_e(nE, 1);
+    for (int v : ctx->E) is_codim_v[v] = 0;
+    for (int e : ctx->F2E) is_codim_e[e] = 0;
+    ctx->codim_vertices.clear();
+    ctx->codim_edges.clear();
+    for (int i = 0; i < nV; i++)
+        if (is_codim_v[i]) ctx->codim_vertices.push_back(i);
+    for (int i = 0; i < nE; i++)
+        if (is_codim_e[i]) ctx->codim_edges.push_back(i);
+    // areas (:309-374)
+    auto edge_len = [&](int i) { return std::sqrt(sqnorm(ctx->rest[ctx->E[2 * i]] - ctx->rest[ctx->E[2 * i + 1]])); };
+    std::vector<double> vea(nV, -1), vfa(nV, -1);
+    for (int i = 0; i < nE; i++) {
+        const double len = edge_len(i);
+        for (int k = 0; k < 2; k++) {
+            double& a = vea[ctx->E[2 * i + k]];
+            a = std::max(a, 0.0);
+            a += 0.5 * len;
+        }
+    }
+    ctx->edge_areas.assign(nE, -1);
+    for (int i = 0; i < nF; i++) {
+        const V3 a = ctx->rest[ctx->F[3 * i]], b = ctx->rest[ctx->F[3 * i + 1]], c = ctx->rest[ctx->F[3 * i + 2]];
+        const double face_area = 0.5 * std::sqrt(sqnorm(cross(b - a, c - a))); // geometry/area.cpp triangle_area
+        for (int k = 0; k < 3; k++) {
+            double& va = vfa[ctx->F[3 * i + k]];
+            va = std::max(va, 0.0);
+            va += face_area / 3.0;
+            double& ea = ctx->edge_areas[ctx->F2E[3 * i + k]];
+            ea = std::max(ea, 0.0);
+            ea += face_area / 3.0;
+        }
+    }
+    ctx->vertex_areas.resize(nV);
+    for (int i = 0; i < nV; i++) ctx->vertex_areas[i] = vfa[i] < 0 ? (vea[i] < 0 ? 1.0 : vea[i]) : vfa[i];
+    for (int i = 0; i < nE; i++)
+        if (ctx->edge_areas[i] < 0) ctx->edge_areas[i] = edge_len(i);
+    ctx->built = false;
+    for (auto& c : ctx->cand) c.clear();
+    for (auto& c : ctx->coll) c.clear();
+    return 0;
+}
+int ipco_mesh_num_codim_vertices(ipcb_ctx* ctx, int32_t* n)
+{
+    *n = int32_t(ctx->codim_vertices.size());
+    return 0;
+}
+int ipco_mesh_num_codim_edges(ipcb_ctx* ctx, int32_t* n)
+{
+    *n = int32_t(ctx->codim_edges.size());
+    return 0;
+}
+int ipco_mesh_faces_to_edges(ipcb_ctx* ctx, int32_t* f2e)
+{
+    for (int i = 0; i < ctx->nF; i++)
+        for (int k = 0; k < 3; k++) f2e[i + size_t(ctx->nF) * k] = ctx->F2E[3 * i + k];
+    return 0;
+}
+int ipco_mesh_areas(ipcb_ctx* ctx, double* va, double* ea)
+{
+    std::copy(ctx->vertex_areas.begin(), ctx->vertex_areas.end(), va);
+    std::copy(ctx->edge_areas.begin(), ctx->edge_areas.end(), ea);
+    return 0;
+}
+
+int ipco_broad_build_static(ipcb_ctx* ctx, const double* V, int32_t ld, double r, int32_t boxes)
+{
+    build_boxes(ctx, load_vertices(ctx->nV, V, ld), nullptr, r, boxes);
+    return 0;
+}
+int ipco_broad_build_swept(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double r, int32_t boxes)
+{
+    const auto v1 = load_vertices(ctx->nV, V1, ld);
+    build_boxes(ctx, load_vertices(ctx->nV, V0, ld), &v1, r, boxes);
+    return 0;
+}
+int ipco_broad_detect(ipcb_ctx* ctx, int32_t kind, int64_t* count)
+{
+    if (!ctx->built) return fail("broad phase not built");
+    if (kind < 0 || kind > 5) return fail("bad candidate kind");
+    broad_detect_kind(ctx, kind, ctx->detected[kind]);
+    *count = int64_t(ctx->detected[kind].size());
+    return 0;
+}
+int ipco_broad_fetch(ipcb_ctx* ctx, int32_t kind, int32_t* pairs)
+{
+    std::memcpy(pairs, ctx->detected[kind].data(), ctx->detected[kind].size() * sizeof(Pair));
+    return 0;
+}
+int ipco_broad_vertex_boxes(ipcb_ctx* ctx, void* boxes)
+{
+    for (int i = 0; i < ctx->nV; i++)
+        for (int c = 0; c < 3; c++) {
+            if (ctx->boxes_mode == IPCB_BOXES_FLOAT) {
+                static_cast<float*>(boxes)[6 * i + c] = float(ctx->vbox[i].lo[c]);
+                static_cast<float*>(boxes)[6 * i + 3 + c] = float(ctx->vbox[i].hi[c]);
+            } else {
+                static_cast<double*>(boxes)[6 * i + c] = ctx->vbox[i].lo[c];
+                static_cast<double*>(boxes)[6 * i + 3 + c] = ctx->vbox[i].hi[c];
+            }
+        }
+    return 0;
+}
+
+static void fill_counts4(const std::vector<Pair>* c, int64_t counts[4])
+{
+    for (int k = 0; k < 4; k++) counts[k] = int64_t(c[k].size());
+}
+int ipco_candidates_build_static(ipcb_ctx* ctx, const double* V, int32_t ld, double r, int64_t counts[4])
+{
+    candidates_build(ctx, load_vertices(ctx->nV, V, ld), nullptr, r);
+    fill_counts4(ctx->cand, counts);
+    return 0;
+}
+int ipco_candidates_build_swept(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double r, int64_t counts[4])
+{
+    const auto v1 = load_vertices(ctx->nV, V1, ld);
+    candidates_build(ctx, load_vertices(ctx->nV, V0, ld), &v1, r);
+    fill_counts4(ctx->cand, counts);
+    return 0;
+}
+int ipco_candidates_fetch(ipcb_ctx* ctx, int32_t kind, int32_t* pairs)
+{
+    if (kind < 0 || kind > 3) return fail("bad candidate kind");
+    std::memcpy(pairs, ctx->cand[kind].data(), ctx->cand[kind].size() * sizeof(Pair));
+    return 0;
+}
+int ipco_candidates_set(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_t* pairs)
+{
+    if (kind < 0 || kind > 3) return fail("bad candidate kind");
+    ctx->cand[kind].resize(count);
+    std::memcpy(ctx->cand[kind].data(), pairs, count * sizeof(Pair));
+    return 0;
+}
+
+static void coll_counts(ipcb_ctx* ctx, int64_t counts[4])
+{
+    for (int k = 0; k < 4; k++) counts[k] = int64_t(ctx->coll[k].size());
+}
+int ipco_collisions_build_from_candidates(ipcb_ctx* ctx, const double* V, int32_t ld, double dhat, double dmin, int32_t flags,
+                                          int64_t counts[4])
+{
+    collisions_build(ctx, load_vertices(ctx->nV, V, ld), dhat, dmin, flags);
+    coll_counts(ctx, counts);
+    return 0;
+}
+int ipco_collisions_build(ipcb_ctx* ctx, const double* V, int32_t ld, double dhat, double dmin, int32_t flags, int64_t counts[4])
+{
+    const auto v = load_vertices(ctx->nV, V, ld);
+    candidates_build(ctx, v, nullptr, 0.5 * (dhat + dmin)); // normal_collisions.cpp:30
+    collisions_build(ctx, v, dhat, dmin, flags);
+    coll_counts(ctx, counts);
+    return 0;
+}
+int ipco_collisions_fetch(ipcb_ctx* ctx, int32_t kind, int32_t* ids, double* weight, double* eps_x, uint8_t* dtype)
+{
+    if (kind < 0 || kind > 3) return fail("bad collision kind");
+    const auto& cs = ctx->coll[kind];
+    for (size_t i = 0; i < cs.size(); i++) {
+        if (ids) ids[2 * i] = cs[i].a, ids[2 * i + 1] = cs[i].b;
+        if (weight) weight[i] = cs[i].w;
+        if (eps_x) eps_x[i] = cs[i].eps_x;
+        if (dtype) dtype[i] = cs[i].dtype;
+    }
+    return 0;
+}
+int ipco_collisions_min_distance(ipcb_ctx* ctx, const double* Vp, int32_t ld, double* out)
+{
+    const auto V = load_vertices(ctx->nV, Vp, ld);
+    double best = std::numeric_limits<double>::infinity();
+    for (int k = 0; k < 4; k++)
+        for (const Coll& c : ctx->coll[k]) {
+            int32_t ids[4];
+            const int n = stencil_ids(ctx, k, c.a, c.b, ids);
+            V3 x[4];
+            for (int j = 0; j < n; j++) x[j] = V[ids[j]];
+            best = std::min(best, prim_value(collision_embed(k, c), x));
+        }
+    *out = best;
+    return 0;
+}
+
+int ipco_barrier_energy(ipcb_ctx* ctx, const double* Vp, int32_t ld, const ipcb_barrier_params* bp, double* energy)
+{
+    const auto V = load_vertices(ctx->nV, Vp, ld);
+    const Barrier B = { bp->dhat, bp->stiffness, bp->use_physical_barrier != 0 };
+    double total = 0;
+    for (int k = 0; k < 4; k++) {
+        const auto& cs = ctx->coll[k];
+        double sum = 0;
+#pragma omp parallel for reduction(+ : sum) schedule(static)
+        for (size_t i = 0; i < cs.size(); i++) {
+            int32_t ids[4];
+            const int n = stencil_ids(ctx, k, cs[i].a, cs[i].b, ids);
+            V3 x[4];
+            for (int j = 0; j < n; j++) x[j] = V[ids[j]];
+            sum += collision_energy(k, cs[i], x, B, ctx->dmin);
+        }
+        total += sum;
+    }
+    *energy = total;
+    return 0;
+}
+
+int ipco_barrier_gradient(ipcb_ctx* ctx, const double* Vp, int32_t ld, const ipcb_barrier_params* bp, double* grad)
+{
+    const auto V = load_vertices(ctx->nV, Vp, ld);
+    const Barrier B = { bp->dhat, bp->stiffness, bp->use_physical_barrier != 0 };
+    const size_t ndof = 3 * size_t(ctx->nV);
+    const int nt = omp_get_max_threads();
+    std::vector<std::vector<double>> loc(nt); // tbb::combinable<VectorXd> (potential.cpp:74-94)
+    for (int k = 0; k < 4; k++) {
+        const auto& cs = ctx->coll[k];
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < cs.size(); i++) {
+            auto& mine = loc[omp_get_thread_num()];
+            if (mine.empty()) mine.assign(ndof, 0.0);
+            int32_t ids[4];
+            const int n = stencil_ids(ctx, k, cs[i].a, cs[i].b, ids);
+            V3 x[4];
+            for (int j = 0; j < n; j++) x[j] = V[ids[j]];
+            double g[12];
+            collision_gradient(k, cs[i], x, B, ctx->dmin, g);
+            for (int j = 0; j < n; j++) // utils/local_to_global.hpp:21-45 (RowMajor)
+                for (int c = 0; c < 3; c++) mine[3 * size_t(ids[j]) + c] += g[3 * j + c];
+        }
+    }
+    std::fill(grad, grad + ndof, 0.0);
+    for (auto& l : loc)
+        if (!l.empty())
+            for (size_t i = 0; i < ndof; i++) grad[i] += l[i];
+    return 0;
+}
+
+int ipco_barrier_hessian(ipcb_ctx* ctx, const double* Vp, int32_t ld, const ipcb_barrier_params* bp, int32_t psd_mode, int64_t* nnz)
+{
+    const auto V = load_vertices(ctx->nV, Vp, ld);
+    const Barrier B = { bp->dhat, bp->stiffness, bp->use_physical_barrier != 0 };
+    const int ndof = 3 * ctx->nV;
+    struct Trip {
+        int32_t col, row;
+        double val;
+    };
+    const int nt = omp_get_max_threads();
+    std::vector<std::vector<Trip>> loc(nt);
+    for (int k = 0; k < 4; k++) {
+        const auto& cs = ctx->coll[k];
+#pragma omp parallel for schedule(static)
+        for (size_t i = 0; i < cs.size(); i++) {
+            auto& mine = loc[omp_get_thread_num()];
+            int32_t ids[4];
+            const int n = stencil_ids(ctx, k, cs[i].a, cs[i].b, ids);
+            V3 x[4];
+            for (int j = 0; j < n; j++) x[j] = V[ids[j]];
+            double H[144];
+            collision_hessian(k, cs[i], x, B, ctx->dmin, psd_mode, H);
+            // utils/local_to_global.hpp:263-305: exact zeros are skipped
+            for (int a = 0; a < n; a++)
+                for (int b = 0; b < n; b++)
+                    for (int r = 0; r < 3; r++)
+                        for (int c = 0; c < 3; c++) {
+                            const double val = H[(3 * a + r) + 12 * (3 * b + c)];
+                            if (val != 0) mine.push_back({ 3 * ids[b] + c, 3 * ids[a] + r, val });
+                        }
+        }
+    }
+    std::vector<Trip> all;
+    size_t total = 0;
+    for (auto& l : loc) total += l.size();
+    all.reserve(total);
+    for (auto& l : loc) all.insert(all.end(), l.begin(), l.end());
+    // setFromTriplets (potential.cpp:218): compressed columns, rows ascending, duplicates summed
+    __gnu_parallel::stable_sort(all.begin(), all.end(), [](const Trip& a, const Trip& b) {
+        return a.col != b.col ? a.col < b.col : a.row < b.row;
+    });
+    ctx->outer.assign(ndof + 1, 0);
+    ctx->inner.clear();
+    ctx->vals.clear();
+    for (size_t i = 0; i < all.size();) {
+        size_t j = i;
+        double s = 0;
+        while (j < all.size() && all[j].col == all[i].col && all[j].row == all[i].row) s += all[j++].val;
+        ctx->inner.push_back(all[i].row);
+        ctx->vals.push_back(s);
+        ctx->outer[all[i].col + 1]++;
+        i = j;
+    }
+    for (int c = 0; c < ndof; c++) ctx->outer[c + 1] += ctx->outer[c];
+    *nnz = int64_t(ctx->inner.size());
+    return 0;
+}
+int ipco_barrier_hessian_fetch(ipcb_ctx* ctx, int32_t* outer, int32_t* inner, double* values)
+{
+    std::copy(ctx->outer.begin(), ctx->outer.end(), outer);
+    std::copy(ctx->inner.begin(), ctx->inner.end(), inner);
+    std::copy(ctx->vals.begin(), ctx->vals.end(), values);
+    return 0;
+}
+
+int ipco_ccd_stepsize_from_candidates(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double min_distance,
+                                      const ipcb_ccd_params* ccd, double* step)
+{
+    *step = stepsize_from_candidates(ctx, load_vertices(ctx->nV, V0, ld), load_vertices(ctx->nV, V1, ld), min_distance, resolve_ccd(ccd));
+    return 0;
+}
+int ipco_ccd_stepsize(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double min_distance, const ipcb_ccd_params* ccd,
+                      double* step)
+{
+    const auto v0 = load_vertices(ctx->nV, V0, ld), v1 = load_vertices(ctx->nV, V1, ld);
+    candidates_build(ctx, v0, &v1, 0.5 * min_distance); // ipc.cpp:95-96
+    *step = stepsize_from_candidates(ctx, v0, v1, min_distance, resolve_ccd(ccd));
+    return 0;
+}
+int ipco_ccd_narrow_phase(ipcb_ctx*, int32_t kind, int64_t n, const double* x_t0, const double* x_t1, double min_distance, double tmax,
+                          const ipcb_ccd_params* ccd, uint8_t* hit, double* toi)
+{
+    if (kind < 0 || kind > 3) return fail("bad candidate kind");
+    const ipcb_ccd_params p = resolve_ccd(ccd);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = 0; i < n; i++) {
+        V3 t0[4], t1[4];
+        for (int j = 0; j < 4; j++) {
+            t0[j] = { x_t0[12 * i + 3 * j], x_t0[12 * i + 3 * j + 1], x_t0[12 * i + 3 * j + 2] };
+            t1[j] = { x_t1[12 * i + 3 * j], x_t1[12 * i + 3 * j + 1], x_t1[12 * i + 3 * j + 2] };
+        }
+        double t = std::numeric_limits<double>::infinity();
+        const bool h = narrow_ccd(kind, t0, t1, min_distance, tmax, p, t);
+        hit[i] = h;
+        toi[i] = h ? t : std::numeric_limits<double>::infinity();
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Unit-level exports used by tests/ to pin the restatement against the
+// reference's known-answer tests (tests/src/tests/distance/*.cpp etc.)
+int ipco_unit_distance_type(int kind, const double* x)
+{
+    const V3* p = reinterpret_cast<const V3*>(x);
+    switch (kind) {
+    case IPCB_EV: return point_edge_distance_type(p[0], p[1], p[2]);
+    case IPCB_EE: return edge_edge_distance_type(p[0], p[1], p[2], p[3]);
+    case IPCB_FV: return point_triangle_distance_type(p[0], p[1], p[2], p[3]);
+    default: return 0;
+    }
+}
+// value / gradient (12) / hessian (12x12 col-major) of the squared distance of
+// a stencil with an explicit distance type (dtype < 0: AUTO)
+int ipco_unit_distance(int kind, const double* x, int dtype, double* val, double* grad, double* hess)
+{
+    const V3* p = reinterpret_cast<const V3*>(x);
+    Embed em;
+    try {
+        switch (kind) {
+        case IPCB_VV: em = { PRIM_PP, 2, { 0, 1, 0, 0 } }; break;
+        case IPCB_EV: em = embed_point_edge(dtype < 0 ? point_edge_distance_type(p[0], p[1], p[2]) : PE(dtype)); break;
+        case IPCB_EE: em = embed_edge_edge(dtype < 0 ? edge_edge_distance_type(p[0], p[1], p[2], p[3]) : EE(dtype)); break;
+        default: em = embed_point_triangle(dtype < 0 ? point_triangle_distance_type(p[0], p[1], p[2], p[3]) : PT(dtype)); break;
+        }
+    } catch (const std::exception& e) {
+        return fail(e.what());
+    }
+    Deriv D;
+    embed_deriv(em, p, D);
+    if (val) *val = prim_value(em, p);
+    if (grad) std::copy(D.g, D.g + 12, grad);
+    if (hess) std::copy(D.H, D.H + 144, hess);
+    return 0;
+}
+// mollifier pieces: out[0] = cross sqnorm, out[1] = m(x, eps), grad (12), hess (12x12) of m
+int ipco_unit_mollifier(const double* x, double eps_x, double* out, double* grad, double* hess)
+{
+    const V3* p = reinterpret_cast<const V3*>(x);
+    Deriv S;
+    edge_edge_cross_squarednorm_deriv(p[0], p[1], p[2], p[3], S);
+    const double s = edge_edge_cross_squarednorm(p[0], p[1], p[2], p[3]);
+    out[0] = s;
+    out[1] = edge_edge_mollifier(s, eps_x);
+    const double dm = edge_edge_mollifier_gradient(s, eps_x), ddm = edge_edge_mollifier_hessian(s, eps_x);
+    for (int i = 0; i < 12; i++) grad[i] = s < eps_x ? dm * S.g[i] : 0;
+    for (int j = 0; j < 12; j++)
+        for (int i = 0; i < 12; i++) hess[i + 12 * j] = s < eps_x ? dm * S.h(i, j) + ddm * S.g[i] * S.g[j] : 0;
+    return 0;
+}
+double ipco_unit_mollifier_threshold(const double* rest)
+{
+    const V3* p = reinterpret_cast<const V3*>(rest);
+    return edge_edge_mollifier_threshold(p[0], p[1], p[2], p[3]);
+}
+void ipco_unit_barrier(double d, double dhat, double out[3])
+{
+    out[0] = barrier(d, dhat);
+    out[1] = barrier_first_derivative(d, dhat);
+    out[2] = barrier_second_derivative(d, dhat);
+}
+int ipco_unit_project_to_psd(int n, double* A, int mode)
+{
+    try {
+        project_to_psd(n, A, n, mode);
+    } catch (const std::exception& e) {
+        return fail(e.what());
+    }
+    return 0;
+}
+uint64_t ipco_unit_morton_3D(double x, double y, double z) { return morton_3D(x, y, z); }
+
+} // extern "C"
