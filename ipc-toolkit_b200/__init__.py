@@ -10,7 +10,7 @@ Because the directory name carries a hyphen, import it through the
 """
 import os as _os
 
-from . import _abi
+from . import _abi, scenes  # noqa: F401
 from .api import make_api as _make_api, edges_from_faces, PSDProjectionMethod, TightInclusionCCD, AdditiveCCD  # noqa: F401
 
 _HERE = _os.path.dirname(_os.path.abspath(__file__))

@@ -1,7 +1,8 @@
 """ctypes declarations for the C ABI in include/ipcb200.h.
 
-The same declarations bind the product library (prefix ``ipcb_``) and the CPU
-oracle (prefix ``ipco_``, host half only).  Nothing here computes anything.
+The declarations are keyed by a symbol prefix: the product library uses
+``ipcb_``; the test-only CPU checker binds the host half of the same table
+with its own prefix from its own directory.  Nothing here computes anything.
 """
 import ctypes as C
 

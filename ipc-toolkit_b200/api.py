@@ -23,7 +23,7 @@ import types
 
 import numpy as np
 
-try:  # loaded as a package module or stand-alone by oracle/pyoracle.py
+try:  # loaded as a package module, or stand-alone by path (the test-only checker does that)
     from . import _abi
 except ImportError:  # pragma: no cover
     import _abi

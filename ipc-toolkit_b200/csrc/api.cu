@@ -1,0 +1,589 @@
+// api.cu — extern "C" entry points of libipcb200.so (include/ipcb200.h).
+// Host variants stage caller buffers into the context's device buffers and call
+// the device path; there is no CPU implementation of any stage in this library.
+#include "ctx.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <unordered_map>
+
+using namespace ipcb;
+
+namespace {
+thread_local std::string g_error;
+
+template <typename F> int guarded(F&& f)
+{
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        g_error = e.what();
+        return 1;
+    } catch (...) {
+        g_error = "unknown error";
+        return 1;
+    }
+}
+
+void use_device(ipcb_ctx* ctx) { IPCB_CUDA(cudaSetDevice(ctx->device)); }
+
+template <typename T> void upload(ipcb_ctx* ctx, Buf<T>& dst, const std::vector<T>& src)
+{
+    dst.reserve(std::max<size_t>(src.size(), 1));
+    if (!src.empty()) IPCB_CUDA(cudaMemcpyAsync(dst.p, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice, ctx->stream));
+}
+
+void begin_call(ipcb_ctx* ctx)
+{
+    use_device(ctx);
+    ctx->stage_ms.clear();
+}
+
+// stage host positions and convert to the AoS device layout
+void stage_positions(ipcb_ctx* ctx, const double* V, int ld, bool second)
+{
+    Stage st(ctx, second ? "h2d_positions_t1" : "h2d_positions");
+    Buf<double>& stage = second ? ctx->stageB : ctx->stageA;
+    upload_positions(ctx, V, ld, stage);
+    convert_positions(ctx, stage.p, ctx->nV, second ? ctx->X1 : ctx->X0);
+}
+
+void fill_counts(const PairList* lists, int64_t counts[4])
+{
+    for (int k = 0; k < 4; k++) counts[k] = lists[k].count;
+}
+void coll_counts(const ipcb_ctx* ctx, int64_t counts[4])
+{
+    for (int k = 0; k < 4; k++) counts[k] = ctx->coll[k].count;
+}
+void require_collisions(const ipcb_ctx* ctx)
+{
+    if (!ctx->coll_valid) throw Error("no collision set has been built on this context");
+}
+} // namespace
+
+extern "C" {
+
+const char* ipcb_last_error(void) { return g_error.c_str(); }
+const char* ipcb_backend_name(void) { return "cuda-sm100a"; }
+
+int ipcb_ctx_create(int device, ipcb_ctx** out)
+{
+    return guarded([&] {
+        int count = 0;
+        const cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw Error(std::string("ipcb200 needs a CUDA device and has no CPU fallback (cudaGetDeviceCount: ")
+                        + cudaGetErrorString(e) + ")");
+        if (device < 0 || device >= count) throw Error("invalid CUDA device index");
+        IPCB_CUDA(cudaSetDevice(device));
+        ipcb_ctx* ctx = new ipcb_ctx();
+        ctx->device = device;
+        IPCB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->pinned.init(32);
+        ctx->dCounters.reserve(32);
+        IPCB_CUDA(cudaMemsetAsync(ctx->dCounters.p, 0, 32 * sizeof(unsigned long long), ctx->stream));
+        ctx->dScalar.reserve(64);
+        *out = ctx;
+    });
+}
+void ipcb_ctx_destroy(ipcb_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+void* ipcb_ctx_stream(ipcb_ctx* ctx) { return ctx->stream; }
+
+int ipcb_ctx_set_shard(ipcb_ctx* ctx, int32_t rank, int32_t world)
+{
+    return guarded([&] {
+        if (world < 1 || rank < 0 || rank >= world) throw Error("bad shard");
+        ctx->shard_rank = rank;
+        ctx->shard_world = world;
+    });
+}
+int ipcb_ctx_launch_count(ipcb_ctx* ctx, int64_t* n)
+{
+    *n = ctx->launches;
+    return 0;
+}
+int ipcb_ctx_stage_times(ipcb_ctx* ctx, int32_t max_stages, const char** names, float* ms)
+{
+    ctx->stage_names_keepalive.clear();
+    for (auto& s : ctx->stage_ms) ctx->stage_names_keepalive.push_back(s.first);
+    int n = 0;
+    for (size_t i = 0; i < ctx->stage_ms.size() && n < max_stages; i++, n++) {
+        names[n] = ctx->stage_names_keepalive[i].c_str();
+        ms[n] = ctx->stage_ms[i].second;
+    }
+    return n;
+}
+
+// ---- CollisionMesh: collision_mesh.cpp:15-127 (host tables) + device mirrors
+int ipcb_mesh_set(ipcb_ctx* ctx, int32_t nV, const double* rest, int32_t ld_rest, int32_t nE, const int32_t* E, int32_t ldE,
+                  int32_t nF, const int32_t* F, int32_t ldF)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (nV < 0 || nE < 0 || nF < 0) throw Error("negative mesh size");
+        ctx->nV = nV, ctx->nE = nE, ctx->nF = nF;
+        ctx->rest.resize(3 * size_t(nV));
+        for (int i = 0; i < nV; i++)
+            for (int k = 0; k < 3; k++) ctx->rest[3 * size_t(i) + k] = rest[i + size_t(ld_rest) * k];
+        ctx->hE.resize(2 * size_t(nE));
+        ctx->hF.resize(3 * size_t(nF));
+        for (int i = 0; i < nE; i++)
+            for (int k = 0; k < 2; k++) {
+                const int v = E[i + size_t(ldE) * k];
+                if (v < 0 || v >= nV) throw Error("edge vertex id out of range");
+                ctx->hE[2 * size_t(i) + k] = v;
+            }
+        for (int i = 0; i < nF; i++)
+            for (int k = 0; k < 3; k++) {
+                const int v = F[i + size_t(ldF) * k];
+                if (v < 0 || v >= nV) throw Error("face vertex id out of range");
+                ctx->hF[3 * size_t(i) + k] = v;
+            }
+        // faces_to_edges (:510-543)
+        std::unordered_map<uint64_t, int> edge_of;
+        edge_of.reserve(size_t(nE) * 2);
+        auto ekey = [](int a, int b) { return (uint64_t(uint32_t(std::min(a, b))) << 32) | uint32_t(std::max(a, b)); };
+        for (int i = 0; i < nE; i++) edge_of.emplace(ekey(ctx->hE[2 * size_t(i)], ctx->hE[2 * size_t(i) + 1]), i);
+        ctx->hF2E.resize(3 * size_t(nF));
+        for (int i = 0; i < nF; i++)
+            for (int k = 0; k < 3; k++) {
+                auto it = edge_of.find(ekey(ctx->hF[3 * size_t(i) + k], ctx->hF[3 * size_t(i) + (k + 1) % 3]));
+                if (it == edge_of.end()) throw Error("Unable to find edge!");
+                ctx->hF2E[3 * size_t(i) + k] = it->second;
+            }
+        // codimensional vertices / edges (:145-183)
+        std::vector<char> cv(nV, 1), ce(nE, 1);
+        for (int v : ctx->hE) cv[v] = 0;
+        for (int e : ctx->hF2E) ce[e] = 0;
+        ctx->codimV.clear(), ctx->codimE.clear();
+        for (int i = 0; i < nV; i++)
+            if (cv[i]) ctx->codimV.push_back(i);
+        for (int i = 0; i < nE; i++)
+            if (ce[i]) ctx->codimE.push_back(i);
+        // vertex / edge areas (:309-374)
+        auto P = [&](int v, int k) { return ctx->rest[3 * size_t(v) + k]; };
+        auto elen = [&](int i) {
+            const int a = ctx->hE[2 * size_t(i)], b = ctx->hE[2 * size_t(i) + 1];
+            double s = 0;
+            for (int k = 0; k < 3; k++) s += (P(a, k) - P(b, k)) * (P(a, k) - P(b, k));
+            return std::sqrt(s);
+        };
+        std::vector<double> vea(nV, -1.0), vfa(nV, -1.0);
+        for (int i = 0; i < nE; i++) {
+            const double len = elen(i);
+            for (int k = 0; k < 2; k++) {
+                double& a = vea[ctx->hE[2 * size_t(i) + k]];
+                a = std::max(a, 0.0) + 0.5 * len;
+            }
+        }
+        ctx->eArea.assign(nE, -1.0);
+        for (int i = 0; i < nF; i++) {
+            const int a = ctx->hF[3 * size_t(i)], b = ctx->hF[3 * size_t(i) + 1], c = ctx->hF[3 * size_t(i) + 2];
+            const double u[3] = { P(b, 0) - P(a, 0), P(b, 1) - P(a, 1), P(b, 2) - P(a, 2) };
+            const double v[3] = { P(c, 0) - P(a, 0), P(c, 1) - P(a, 1), P(c, 2) - P(a, 2) };
+            const double n[3] = { u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0] };
+            const double area = 0.5 * std::sqrt(n[0] * n[0] + (n[1] * n[1] + n[2] * n[2]));
+            for (int k = 0; k < 3; k++) {
+                double& va = vfa[ctx->hF[3 * size_t(i) + k]];
+                va = std::max(va, 0.0) + area / 3.0;
+                double& ea = ctx->eArea[ctx->hF2E[3 * size_t(i) + k]];
+                ea = std::max(ea, 0.0) + area / 3.0;
+            }
+        }
+        ctx->vArea.resize(nV);
+        for (int i = 0; i < nV; i++) ctx->vArea[i] = vfa[i] < 0 ? (vea[i] < 0 ? 1.0 : vea[i]) : vfa[i];
+        for (int i = 0; i < nE; i++)
+            if (ctx->eArea[i] < 0) ctx->eArea[i] = elen(i);
+        // device mirrors
+        std::vector<int2> e2(nE);
+        for (int i = 0; i < nE; i++) e2[i] = make_int2(ctx->hE[2 * size_t(i)], ctx->hE[2 * size_t(i) + 1]);
+        std::vector<int4> f4(nF), fe4(nF);
+        for (int i = 0; i < nF; i++) {
+            f4[i] = make_int4(ctx->hF[3 * size_t(i)], ctx->hF[3 * size_t(i) + 1], ctx->hF[3 * size_t(i) + 2], 0);
+            fe4[i] = make_int4(ctx->hF2E[3 * size_t(i)], ctx->hF2E[3 * size_t(i) + 1], ctx->hF2E[3 * size_t(i) + 2], 0);
+        }
+        std::vector<double4> r4(nV);
+        for (int i = 0; i < nV; i++) r4[i] = make_double4(P(i, 0), P(i, 1), P(i, 2), 0.0);
+        upload(ctx, ctx->dE, e2);
+        upload(ctx, ctx->dF, f4);
+        upload(ctx, ctx->dF2E, fe4);
+        upload(ctx, ctx->dRest, r4);
+        upload(ctx, ctx->dVArea, ctx->vArea);
+        upload(ctx, ctx->dEArea, ctx->eArea);
+        upload(ctx, ctx->dCodimV, ctx->codimV);
+        upload(ctx, ctx->dCodimE, ctx->codimE);
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
+        ctx->built = false;
+        ctx->coll_valid = false;
+        for (auto& c : ctx->cand) c.count = 0;
+        for (auto& c : ctx->coll) c.count = 0;
+        for (auto& c : ctx->detected) c.count = 0;
+    });
+}
+int ipcb_mesh_num_codim_vertices(ipcb_ctx* ctx, int32_t* n)
+{
+    *n = int32_t(ctx->codimV.size());
+    return 0;
+}
+int ipcb_mesh_num_codim_edges(ipcb_ctx* ctx, int32_t* n)
+{
+    *n = int32_t(ctx->codimE.size());
+    return 0;
+}
+int ipcb_mesh_faces_to_edges(ipcb_ctx* ctx, int32_t* f2e)
+{
+    for (int i = 0; i < ctx->nF; i++)
+        for (int k = 0; k < 3; k++) f2e[i + size_t(ctx->nF) * k] = ctx->hF2E[3 * size_t(i) + k];
+    return 0;
+}
+int ipcb_mesh_areas(ipcb_ctx* ctx, double* va, double* ea)
+{
+    std::copy(ctx->vArea.begin(), ctx->vArea.end(), va);
+    std::copy(ctx->eArea.begin(), ctx->eArea.end(), ea);
+    return 0;
+}
+
+// ---- BroadPhase
+int ipcb_broad_build_static(ipcb_ctx* ctx, const double* V, int32_t ld, double r, int32_t boxes)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (boxes != IPCB_BOXES_FLOAT) throw Error("the CUDA broad phase implements the LBVH float-box predicate only");
+        stage_positions(ctx, V, ld, false);
+        broad_build(ctx, false, r);
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int ipcb_broad_build_swept(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double r, int32_t boxes)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (boxes != IPCB_BOXES_FLOAT) throw Error("the CUDA broad phase implements the LBVH float-box predicate only");
+        stage_positions(ctx, V0, ld, false);
+        stage_positions(ctx, V1, ld, true);
+        broad_build(ctx, true, r);
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int ipcb_broad_detect(ipcb_ctx* ctx, int32_t kind, int64_t* count)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (kind < 0 || kind > 5) throw Error("bad candidate kind");
+        broad_detect(ctx, kind, ctx->detected[kind]);
+        *count = ctx->detected[kind].count;
+    });
+}
+static void fetch_pairs(ipcb_ctx* ctx, PairList& pl, int32_t* pairs)
+{
+    if (pl.count == 0) return;
+    sort_pairs(ctx, pl);
+    IPCB_CUDA(cudaMemcpyAsync(pairs, pl.pairs.p, sizeof(int2) * pl.count, cudaMemcpyDeviceToHost, ctx->stream));
+    IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+int ipcb_broad_fetch(ipcb_ctx* ctx, int32_t kind, int32_t* pairs)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (kind < 0 || kind > 5) throw Error("bad candidate kind");
+        fetch_pairs(ctx, ctx->detected[kind], pairs);
+    });
+}
+int ipcb_broad_vertex_boxes(ipcb_ctx* ctx, void* boxes)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (!ctx->built) throw Error("broad phase not built");
+        IPCB_CUDA(cudaMemcpyAsync(boxes, ctx->vset.box.p, sizeof(FBox) * ctx->nV, cudaMemcpyDeviceToHost, ctx->stream));
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+// ---- Candidates
+int ipcb_candidates_build_static(ipcb_ctx* ctx, const double* V, int32_t ld, double r, int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        stage_positions(ctx, V, ld, false);
+        candidates_build(ctx, false, r);
+        fill_counts(ctx->cand, counts);
+    });
+}
+int ipcb_candidates_build_swept(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double r, int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        stage_positions(ctx, V0, ld, false);
+        stage_positions(ctx, V1, ld, true);
+        candidates_build(ctx, true, r);
+        fill_counts(ctx->cand, counts);
+    });
+}
+int ipcb_candidates_build_swept_dev(ipcb_ctx* ctx, const double* dV0, const double* dV1, int32_t ld, double r, int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        convert_positions(ctx, dV0, ld, ctx->X0);
+        convert_positions(ctx, dV1, ld, ctx->X1);
+        candidates_build(ctx, true, r);
+        fill_counts(ctx->cand, counts);
+    });
+}
+int ipcb_candidates_fetch(ipcb_ctx* ctx, int32_t kind, int32_t* pairs)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (kind < 0 || kind > 3) throw Error("bad candidate kind");
+        fetch_pairs(ctx, ctx->cand[kind], pairs);
+    });
+}
+int ipcb_candidates_set(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_t* pairs)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (kind < 0 || kind > 3) throw Error("bad candidate kind");
+        const int limit = kind == IPCB_VV ? ctx->nV : (kind == IPCB_FV ? ctx->nF : ctx->nE);
+        const int limit2 = kind == IPCB_EE ? ctx->nE : ctx->nV;
+        for (int64_t i = 0; i < count; i++)
+            if (pairs[2 * i] < 0 || pairs[2 * i] >= limit || pairs[2 * i + 1] < 0 || pairs[2 * i + 1] >= limit2)
+                throw Error("candidate index out of range");
+        PairList& pl = ctx->cand[kind];
+        pl.pairs.reserve(std::max<int64_t>(count, 1));
+        if (count) IPCB_CUDA(cudaMemcpyAsync(pl.pairs.p, pairs, sizeof(int2) * count, cudaMemcpyHostToDevice, ctx->stream));
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        pl.count = count;
+        pl.sorted = false;
+    });
+}
+
+// ---- NormalCollisions::build
+int ipcb_collisions_build_from_candidates_dev(ipcb_ctx* ctx, const double* dV, int32_t ld, double dhat, double dmin, int32_t flags,
+                                              int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        convert_positions(ctx, dV, ld, ctx->X0);
+        collisions_build(ctx, dhat, dmin, flags);
+        coll_counts(ctx, counts);
+    });
+}
+int ipcb_collisions_build_dev(ipcb_ctx* ctx, const double* dV, int32_t ld, double dhat, double dmin, int32_t flags, int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        convert_positions(ctx, dV, ld, ctx->X0);
+        candidates_build(ctx, false, 0.5 * (dhat + dmin)); // normal_collisions.cpp:30
+        collisions_build(ctx, dhat, dmin, flags);
+        coll_counts(ctx, counts);
+    });
+}
+int ipcb_collisions_build_from_candidates(ipcb_ctx* ctx, const double* V, int32_t ld, double dhat, double dmin, int32_t flags,
+                                          int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        stage_positions(ctx, V, ld, false);
+        collisions_build(ctx, dhat, dmin, flags);
+        coll_counts(ctx, counts);
+    });
+}
+int ipcb_collisions_build(ipcb_ctx* ctx, const double* V, int32_t ld, double dhat, double dmin, int32_t flags, int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        stage_positions(ctx, V, ld, false);
+        candidates_build(ctx, false, 0.5 * (dhat + dmin));
+        collisions_build(ctx, dhat, dmin, flags);
+        coll_counts(ctx, counts);
+    });
+}
+int ipcb_collisions_fetch(ipcb_ctx* ctx, int32_t kind, int32_t* ids, double* weight, double* eps_x, uint8_t* dtype)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (kind < 0 || kind > 3) throw Error("bad collision kind");
+        require_collisions(ctx);
+        const CollisionSet& cs = ctx->coll[kind];
+        const size_t n = size_t(cs.count);
+        if (n == 0) return;
+        cudaStream_t s = ctx->stream;
+        if (ids) IPCB_CUDA(cudaMemcpyAsync(ids, cs.ids.p, sizeof(int2) * n, cudaMemcpyDeviceToHost, s));
+        if (weight) IPCB_CUDA(cudaMemcpyAsync(weight, cs.w.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+        if (kind == IPCB_EE) {
+            if (eps_x) IPCB_CUDA(cudaMemcpyAsync(eps_x, cs.eps.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+            if (dtype) IPCB_CUDA(cudaMemcpyAsync(dtype, cs.dtype.p, n, cudaMemcpyDeviceToHost, s));
+        } else {
+            if (eps_x) std::fill(eps_x, eps_x + n, 0.0);
+            if (dtype) std::fill(dtype, dtype + n, uint8_t(0));
+        }
+        IPCB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+int ipcb_collisions_min_distance(ipcb_ctx* ctx, const double* V, int32_t ld, double* out)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        require_collisions(ctx);
+        stage_positions(ctx, V, ld, false);
+        *out = collisions_min_distance(ctx);
+    });
+}
+
+// ---- BarrierPotential
+int ipcb_barrier_energy_dev(ipcb_ctx* ctx, const double* dV, int32_t ld, const ipcb_barrier_params* bp, double* d_energy)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        require_collisions(ctx);
+        convert_positions(ctx, dV, ld, ctx->X0);
+        barrier_energy(ctx, *bp, d_energy);
+    });
+}
+int ipcb_barrier_energy(ipcb_ctx* ctx, const double* V, int32_t ld, const ipcb_barrier_params* bp, double* energy)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        require_collisions(ctx);
+        stage_positions(ctx, V, ld, false);
+        double* d_out = reinterpret_cast<double*>(ctx->dCounters.p + 12);
+        barrier_energy(ctx, *bp, d_out);
+        IPCB_CUDA(cudaMemcpyAsync(energy, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int ipcb_barrier_gradient_dev(ipcb_ctx* ctx, const double* dV, int32_t ld, const ipcb_barrier_params* bp, double* d_grad)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        require_collisions(ctx);
+        convert_positions(ctx, dV, ld, ctx->X0);
+        barrier_gradient(ctx, *bp, d_grad);
+    });
+}
+int ipcb_barrier_gradient(ipcb_ctx* ctx, const double* V, int32_t ld, const ipcb_barrier_params* bp, double* grad)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        require_collisions(ctx);
+        stage_positions(ctx, V, ld, false);
+        ctx->dGrad.reserve(3 * size_t(ctx->nV) + 1);
+        barrier_gradient(ctx, *bp, ctx->dGrad.p);
+        IPCB_CUDA(cudaMemcpyAsync(grad, ctx->dGrad.p, sizeof(double) * 3 * size_t(ctx->nV), cudaMemcpyDeviceToHost, ctx->stream));
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int ipcb_barrier_hessian_dev(ipcb_ctx* ctx, const double* dV, int32_t ld, const ipcb_barrier_params* bp, int32_t psd_mode, int64_t* nnz)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        require_collisions(ctx);
+        if (psd_mode < 0 || psd_mode > 2) throw Error("Invalid type of PSD projection!");
+        convert_positions(ctx, dV, ld, ctx->X0);
+        barrier_hessian(ctx, *bp, psd_mode);
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *nnz = ctx->nnz;
+    });
+}
+int ipcb_barrier_hessian(ipcb_ctx* ctx, const double* V, int32_t ld, const ipcb_barrier_params* bp, int32_t psd_mode, int64_t* nnz)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        require_collisions(ctx);
+        if (psd_mode < 0 || psd_mode > 2) throw Error("Invalid type of PSD projection!");
+        stage_positions(ctx, V, ld, false);
+        barrier_hessian(ctx, *bp, psd_mode);
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *nnz = ctx->nnz;
+    });
+}
+int ipcb_barrier_hessian_dev_ptrs(ipcb_ctx* ctx, const int32_t** d_outer, const int32_t** d_inner, const double** d_values)
+{
+    *d_outer = ctx->outer.p;
+    *d_inner = ctx->inner.p;
+    *d_values = ctx->vals.p;
+    return 0;
+}
+int ipcb_barrier_hessian_fetch(ipcb_ctx* ctx, int32_t* outer, int32_t* inner, double* values)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        cudaStream_t s = ctx->stream;
+        IPCB_CUDA(cudaMemcpyAsync(outer, ctx->outer.p, sizeof(int) * (3 * size_t(ctx->nV) + 1), cudaMemcpyDeviceToHost, s));
+        if (ctx->nnz) {
+            IPCB_CUDA(cudaMemcpyAsync(inner, ctx->inner.p, sizeof(int) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+            IPCB_CUDA(cudaMemcpyAsync(values, ctx->vals.p, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
+        }
+        IPCB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+// ---- CCD
+int ipcb_ccd_stepsize_from_candidates_dev(ipcb_ctx* ctx, const double* dV0, const double* dV1, int32_t ld, double min_distance,
+                                          const ipcb_ccd_params* ccd, double* d_step)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        convert_positions(ctx, dV0, ld, ctx->X0);
+        convert_positions(ctx, dV1, ld, ctx->X1);
+        ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_step);
+    });
+}
+int ipcb_ccd_stepsize_dev(ipcb_ctx* ctx, const double* dV0, const double* dV1, int32_t ld, double min_distance, const ipcb_ccd_params* ccd,
+                          double* d_step)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        convert_positions(ctx, dV0, ld, ctx->X0);
+        convert_positions(ctx, dV1, ld, ctx->X1);
+        candidates_build(ctx, true, 0.5 * min_distance); // ipc.cpp:95-96
+        ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_step);
+    });
+}
+int ipcb_ccd_stepsize_from_candidates(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double min_distance,
+                                      const ipcb_ccd_params* ccd, double* step)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        stage_positions(ctx, V0, ld, false);
+        stage_positions(ctx, V1, ld, true);
+        double* d_out = reinterpret_cast<double*>(ctx->dCounters.p + 13);
+        ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_out);
+        IPCB_CUDA(cudaMemcpyAsync(step, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int ipcb_ccd_stepsize(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double min_distance, const ipcb_ccd_params* ccd,
+                      double* step)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        stage_positions(ctx, V0, ld, false);
+        stage_positions(ctx, V1, ld, true);
+        candidates_build(ctx, true, 0.5 * min_distance);
+        double* d_out = reinterpret_cast<double*>(ctx->dCounters.p + 13);
+        ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_out);
+        IPCB_CUDA(cudaMemcpyAsync(step, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int ipcb_ccd_narrow_phase(ipcb_ctx* ctx, int32_t kind, int64_t n, const double* x_t0, const double* x_t1, double min_distance, double tmax,
+                          const ipcb_ccd_params* ccd, uint8_t* hit, double* toi)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (kind < 0 || kind > 3) throw Error("bad candidate kind");
+        if (!(tmax >= 0 && tmax <= 1)) throw Error("tmax must be in [0, 1]");
+        ccd_narrow_phase(ctx, kind, n, x_t0, x_t1, min_distance, tmax, resolve_ccd(ccd), hit, toi);
+    });
+}
+
+} // extern "C"

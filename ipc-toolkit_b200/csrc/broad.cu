@@ -1,0 +1,632 @@
+// broad.cu — CUDA broad phase behind ipc::BroadPhase.
+//
+// Replaces (reference src/ipc/): broad_phase/aabb.cpp:35-126 (boxes with
+// conservative nextafter inflation), broad_phase/lbvh.cpp:29-41 (outward
+// rounding to float), :134-330 (Morton + hierarchy build), :348-797
+// (traversal + candidate emission), broad_phase/broad_phase.cpp:12-202 and
+// candidates/candidates.cpp:43-222 (Candidates::build orchestration).
+//
+// Design (B200-first, not the reference's CPU layout):
+//  * positions are converted once per call to one 32-byte double4 per vertex;
+//  * the tree is a Karras radix tree over 63-bit Morton keys (sorted with
+//    cub::DeviceRadixSort, plumbing), refit bottom-up with arrival counters;
+//    one internal node = one 64-byte fetch holding BOTH child boxes, so leaves
+//    are never fetched during traversal;
+//  * traversal is one thread per Morton-ordered query leaf, warp-synchronous,
+//    with hits staged in a per-warp shared-memory queue and flushed with ONE
+//    global atomic per ~100 pairs (warp-aggregated compaction) and coalesced
+//    int2 stores;
+//  * output capacity is learned from the previous step; on overflow the kernel
+//    keeps counting and the pass is repeated once with a larger buffer.
+// The candidate SET is the tree-independent predicate
+//   { (i,j) : fbox_i ∩ fbox_j ≠ ∅ (closed) ∧ no shared vertex }
+// exactly like the reference's default LBVH (SURVEY §7 hard part 1).
+#include "ctx.cuh"
+#include <cub/device/device_radix_sort.cuh>
+#include <cfloat>
+
+namespace ipcb {
+
+// ---------------------------------------------------------------------------
+// positions
+__global__ void k_to_aos(int n, const double* __restrict__ V, int ld, double4* __restrict__ X)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    X[i] = make_double4(V[i], V[i + (size_t)ld], V[i + 2 * (size_t)ld], 0.0);
+}
+
+void upload_positions(ipcb_ctx* ctx, const double* hV, int ld, Buf<double>& stage)
+{
+    stage.reserve(3 * size_t(ctx->nV));
+    // copy the three columns into a compact nV x 3 column-major staging buffer (ld may exceed nV)
+    for (int k = 0; k < 3; k++)
+        IPCB_CUDA(cudaMemcpyAsync(stage.p + size_t(k) * ctx->nV, hV + size_t(k) * ld, sizeof(double) * ctx->nV,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+}
+
+void convert_positions(ipcb_ctx* ctx, const double* dV, int ld, Buf<double4>& X)
+{
+    X.reserve(ctx->nV);
+    if (ctx->nV == 0) return;
+    k_to_aos<<<grid_for(ctx->nV, 256), 256, 0, ctx->stream>>>(ctx->nV, dV, ld, X.p);
+    ctx->launches++;
+}
+
+// ---------------------------------------------------------------------------
+// boxes
+__device__ inline float round_down(double v) { return nextafterf(__double2float_rn(v), -INFINITY); }
+__device__ inline float round_up(double v) { return nextafterf(__double2float_rn(v), INFINITY); }
+
+__device__ inline void atomic_min_f(float* addr, float v)
+{
+    if (v >= 0)
+        atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else
+        atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+__device__ inline void atomic_max_f(float* addr, float v)
+{
+    if (v >= 0)
+        atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else
+        atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+__global__ void k_scene_init(float* scene)
+{
+    if (threadIdx.x < 3) scene[threadIdx.x] = INFINITY;
+    else if (threadIdx.x < 6) scene[threadIdx.x] = -INFINITY;
+}
+
+// aabb.cpp:35-87 + lbvh.cpp:29-41; also reduces the scene box (broad_phase.cpp:93-125)
+__global__ void k_vertex_boxes(int n, const double4* __restrict__ X0, const double4* __restrict__ X1, double r,
+                               FBox* __restrict__ box, int4* __restrict__ prim, float* scene)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+    if (i < n) {
+        const double4 p = X0[i];
+        const double c[3] = { p.x, p.y, p.z };
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lo[k] = round_down(nextafter(c[k] - r, -INFINITY));
+            hi[k] = round_up(nextafter(c[k] + r, INFINITY));
+        }
+        if (X1) {
+            const double4 q = X1[i];
+            const double e[3] = { q.x, q.y, q.z };
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                lo[k] = fminf(lo[k], round_down(nextafter(e[k] - r, -INFINITY)));
+                hi[k] = fmaxf(hi[k], round_up(nextafter(e[k] + r, INFINITY)));
+            }
+        }
+        FBox b;
+#pragma unroll
+        for (int k = 0; k < 3; k++) b.lo[k] = lo[k], b.hi[k] = hi[k];
+        box[i] = b;
+        prim[i] = make_int4(i, -1, -1, i);
+    }
+    // block reduction of the scene bounds
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (lo[k] <= hi[k]) {
+                atomic_min_f(scene + k, lo[k]);
+                atomic_max_f(scene + 3 + k, hi[k]);
+            }
+        }
+    }
+}
+
+// aabb.cpp:89-126: edge / face box = union of its vertex boxes (float rounding
+// is monotone, so rounding commutes with min / max)
+__global__ void k_edge_boxes(int n, const int2* __restrict__ E, const FBox* __restrict__ vb, FBox* __restrict__ box,
+                             int4* __restrict__ prim)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 e = E[i];
+    const FBox a = vb[e.x], b = vb[e.y];
+    FBox o;
+#pragma unroll
+    for (int k = 0; k < 3; k++) o.lo[k] = fminf(a.lo[k], b.lo[k]), o.hi[k] = fmaxf(a.hi[k], b.hi[k]);
+    box[i] = o;
+    prim[i] = make_int4(e.x, e.y, -1, i);
+}
+__global__ void k_face_boxes(int n, const int4* __restrict__ F, const FBox* __restrict__ vb, FBox* __restrict__ box,
+                             int4* __restrict__ prim)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 f = F[i];
+    const FBox a = vb[f.x], b = vb[f.y], c = vb[f.z];
+    FBox o;
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        o.lo[k] = fminf(fminf(a.lo[k], b.lo[k]), c.lo[k]), o.hi[k] = fmaxf(fmaxf(a.hi[k], b.hi[k]), c.hi[k]);
+    box[i] = o;
+    prim[i] = make_int4(f.x, f.y, f.z, i);
+}
+// gather a subset (codimensional vertices / edges) of a PrimSet
+__global__ void k_gather_set(int n, const int* __restrict__ ids, const FBox* __restrict__ box, const int4* __restrict__ prim,
+                             FBox* __restrict__ obox, int4* __restrict__ oprim)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    obox[i] = box[ids[i]];
+    oprim[i] = prim[ids[i]];
+}
+
+// ---------------------------------------------------------------------------
+// Morton keys (math/morton.hpp:23-63, lbvh.cpp:150-168)
+__device__ inline unsigned long long expand21(unsigned long long v)
+{
+    v = (v | v << 32) & 0x1F00000000FFFFull;
+    v = (v | v << 16) & 0x1F0000FF0000FFull;
+    v = (v | v << 8) & 0x100F00F00F00F00Full;
+    v = (v | v << 4) & 0x10C30C30C30C30C3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+__global__ void k_morton(int n, const FBox* __restrict__ box, const float* __restrict__ scene,
+                         unsigned long long* __restrict__ key, int* __restrict__ ord)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const FBox b = box[i];
+    unsigned long long code = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double w = double(scene[3 + k]) - double(scene[k]);
+        double m = w > 0 ? (0.5 * (double(b.lo[k]) + double(b.hi[k])) - double(scene[k])) / w : 0.0;
+        m = fmin(fmax(m * 2097152.0, 0.0), 2097151.0);
+        code |= expand21((unsigned long long)m) << (2 - k);
+    }
+    key[i] = code;
+    ord[i] = i;
+}
+__global__ void k_apply_order(int n, const int* __restrict__ ord, const FBox* __restrict__ box, const int4* __restrict__ prim,
+                              FBox* __restrict__ sbox, int4* __restrict__ sprim)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = ord[i];
+    sbox[i] = box[j];
+    sprim[i] = prim[j];
+}
+
+// ---------------------------------------------------------------------------
+// Karras radix tree over the sorted keys; duplicates are broken by position
+// (lbvh.cpp:104-131 uses the same fallback)
+__device__ inline int delta(const unsigned long long* __restrict__ key, int n, int i, unsigned long long ki, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long kj = key[j];
+    if (ki == kj) return 64 + __clz(i ^ j);
+    return __clzll(ki ^ kj);
+}
+__global__ void k_karras(int n, const unsigned long long* __restrict__ key, Node* __restrict__ nodes, int* __restrict__ parent,
+                         int* __restrict__ flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const unsigned long long ki = key[i];
+    const int d = delta(key, n, i, ki, i + 1) > delta(key, n, i, ki, i - 1) ? 1 : -1;
+    const int dmin = delta(key, n, i, ki, i - d);
+    int lmax = 2;
+    while (delta(key, n, i, ki, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(key, n, i, ki, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(key, n, i, ki, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(key, n, i, ki, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int left = (lo == gamma) ? ~gamma : gamma;
+    const int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    nodes[i].child[0] = left;
+    nodes[i].child[1] = right;
+    nodes[i].split = gamma;
+    nodes[i].last = hi;
+    parent[left < 0 ? (n - 1 + ~left) : left] = i;
+    parent[right < 0 ? (n - 1 + ~right) : right] = i;
+    flag[i] = 0;
+    if (i == 0) parent[0] = -1;
+}
+
+// bottom-up refit: the second thread to arrive at a node computes its child boxes
+__global__ void k_refit(int n, const FBox* __restrict__ sbox, Node* nodes, const int* __restrict__ parent, int* flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int node = parent[n - 1 + i];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(flag + node, 1) == 0) return;
+        Node* nd = nodes + node;
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            const int ch = nd->child[c];
+            if (ch < 0) {
+                const FBox b = sbox[~ch];
+#pragma unroll
+                for (int k = 0; k < 3; k++) nd->lo[c][k] = b.lo[k], nd->hi[c][k] = b.hi[k];
+            } else {
+                const volatile Node* cn = nodes + ch;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    nd->lo[c][k] = fminf(cn->lo[0][k], cn->lo[1][k]);
+                    nd->hi[c][k] = fmaxf(cn->hi[0][k], cn->hi[1][k]);
+                }
+            }
+        }
+        node = parent[node];
+    }
+}
+
+static void sort_keys(ipcb_ctx* ctx, Tree& t, int n)
+{
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 63, ctx->stream);
+    t.tmp.reserve(bytes);
+    cub::DeviceRadixSort::SortPairs(t.tmp.p, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 63, ctx->stream);
+    ctx->launches += 9; // onesweep: histogram + exclusive sum + 7 passes of 8+ bits (approximate)
+}
+
+// Morton-sort a PrimSet; with_nodes additionally builds the hierarchy
+static void build_tree(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, bool with_nodes)
+{
+    const int n = ps.n;
+    t.n = n;
+    t.has_nodes = false;
+    if (n == 0) return;
+    cudaStream_t s = ctx->stream;
+    t.key.reserve(n), t.key_sorted.reserve(n), t.ord.reserve(n), t.ord_sorted.reserve(n);
+    t.sbox.reserve(n), t.sprim.reserve(n);
+    k_morton<<<grid_for(n, 256), 256, 0, s>>>(n, ps.box.p, ctx->scene.p, t.key.p, t.ord.p);
+    sort_keys(ctx, t, n);
+    k_apply_order<<<grid_for(n, 256), 256, 0, s>>>(n, t.ord_sorted.p, ps.box.p, ps.prim.p, t.sbox.p, t.sprim.p);
+    ctx->launches += 2;
+    if (!with_nodes || n < 2) {
+        t.has_nodes = with_nodes;
+        return;
+    }
+    t.nodes.reserve(n - 1), t.parent.reserve(2 * size_t(n) - 1), t.flag.reserve(n - 1);
+    k_karras<<<grid_for(n - 1, 256), 256, 0, s>>>(n, t.key_sorted.p, t.nodes.p, t.parent.p, t.flag.p);
+    k_refit<<<grid_for(n, 256), 256, 0, s>>>(n, t.sbox.p, t.nodes.p, t.parent.p, t.flag.p);
+    ctx->launches += 2;
+    t.has_nodes = true;
+}
+
+void broad_build(ipcb_ctx* ctx, bool swept, double r)
+{
+    Stage st(ctx, "broad_build");
+    cudaStream_t s = ctx->stream;
+    const int nV = ctx->nV, nE = ctx->nE, nF = ctx->nF;
+    ctx->scene.reserve(8);
+    k_scene_init<<<1, 32, 0, s>>>(ctx->scene.p);
+    ctx->vset.n = nV, ctx->eset.n = nE, ctx->fset.n = nF;
+    ctx->vset.box.reserve(nV), ctx->vset.prim.reserve(nV);
+    ctx->eset.box.reserve(nE), ctx->eset.prim.reserve(nE);
+    ctx->fset.box.reserve(nF), ctx->fset.prim.reserve(nF);
+    if (nV)
+        k_vertex_boxes<<<grid_for(nV, 256), 256, 0, s>>>(nV, ctx->X0.p, swept ? ctx->X1.p : nullptr, r, ctx->vset.box.p,
+                                                        ctx->vset.prim.p, ctx->scene.p);
+    if (nE) k_edge_boxes<<<grid_for(nE, 256), 256, 0, s>>>(nE, ctx->dE.p, ctx->vset.box.p, ctx->eset.box.p, ctx->eset.prim.p);
+    if (nF) k_face_boxes<<<grid_for(nF, 256), 256, 0, s>>>(nF, ctx->dF.p, ctx->vset.box.p, ctx->fset.box.p, ctx->fset.prim.p);
+    ctx->launches += 4;
+    ctx->vtree_ok = ctx->etree_ok = ctx->ftree_ok = false;
+    ctx->vtree.n = ctx->etree.n = ctx->ftree.n = 0;
+    ctx->vtree.has_nodes = ctx->etree.has_nodes = ctx->ftree.has_nodes = false;
+    ctx->built = true;
+    ctx->swept = swept;
+    IPCB_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------
+// traversal
+constexpr int TRAV_BLOCK = 128;
+constexpr int STAGE_CAP = 160; // per-warp staging slots; flushed when > STAGE_CAP - 64
+
+__device__ inline bool shares_vertex(int4 a, int4 b)
+{
+    // lbvh.cpp:801-873 with can_vertices_collide == true; -1 entries are padding
+    bool s = a.x == b.x || (b.y >= 0 && a.x == b.y) || (b.z >= 0 && a.x == b.z);
+    if (a.y >= 0) s |= a.y == b.x || (b.y >= 0 && a.y == b.y) || (b.z >= 0 && a.y == b.z);
+    if (a.z >= 0) s |= a.z == b.x || (b.y >= 0 && a.z == b.y) || (b.z >= 0 && a.z == b.z);
+    return s;
+}
+
+// MODE 0: emit (query, target); 1: emit (target, query); 2: self, emit (min, max)
+template <int MODE>
+__global__ void __launch_bounds__(TRAV_BLOCK)
+    k_traverse(int q_begin, int q_end, const FBox* __restrict__ qbox, const int4* __restrict__ qprim,
+               const Node* __restrict__ nodes, int n_target, const FBox* __restrict__ tbox, const int4* __restrict__ tprim,
+               int2* __restrict__ out, unsigned long long* counter, unsigned long long capacity, int check_shared)
+{
+    __shared__ int2 stage[TRAV_BLOCK / 32][STAGE_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = qi < q_end;
+    FBox q;
+    int4 qp = make_int4(-1, -1, -1, -1);
+    if (active) {
+        q = qbox[qi];
+        qp = qprim[qi];
+    }
+    int stack[96];
+    int sp = 0;
+    int node = 0;
+    int nstaged = 0;
+    int single = -1; // n_target == 1: the only leaf
+    if (n_target == 1) {
+        if (active && MODE != 2) {
+            const FBox b = tbox[0];
+            if (q.lo[0] <= b.hi[0] && b.lo[0] <= q.hi[0] && q.lo[1] <= b.hi[1] && b.lo[1] <= q.hi[1] && q.lo[2] <= b.hi[2]
+                && b.lo[2] <= q.hi[2])
+                single = 0;
+        }
+    }
+    bool walking = active && n_target > 1;
+    while (__any_sync(0xffffffffu, walking || single >= 0)) {
+        int hit0 = single, hit1 = -1;
+        single = -1;
+        if (walking) {
+            const float4* np = reinterpret_cast<const float4*>(nodes + node);
+            const float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
+            const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
+            // layout: lo[0] = a.xyz, lo[1] = (a.w, b.x, b.y), hi[0] = (b.z, b.w, c.x), hi[1] = c.yzw
+            bool ol = q.lo[0] <= b.z && a.x <= q.hi[0] && q.lo[1] <= b.w && a.y <= q.hi[1] && q.lo[2] <= c.x && a.z <= q.hi[2];
+            bool orr = q.lo[0] <= c.y && a.w <= q.hi[0] && q.lo[1] <= c.z && b.x <= q.hi[1] && q.lo[2] <= c.w && b.y <= q.hi[2];
+            if (MODE == 2) { // only leaves after the query in Morton order (lbvh.cpp:415-424)
+                ol = ol && d.z > qi;
+                orr = orr && d.w > qi;
+            }
+            if (ol && d.x < 0) hit0 = ~d.x;
+            if (orr && d.y < 0) hit1 = ~d.y;
+            const bool tl = ol && d.x >= 0, tr = orr && d.y >= 0;
+            if (tl) {
+                node = d.x;
+                if (tr) stack[sp++] = d.y;
+            } else if (tr) {
+                node = d.y;
+            } else if (sp > 0) {
+                node = stack[--sp];
+            } else {
+                walking = false;
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int hit = h == 0 ? hit0 : hit1;
+            bool emit = false;
+            int2 pr = make_int2(0, 0);
+            if (hit >= 0) {
+                const int4 tp = __ldg(tprim + hit);
+                if (!check_shared || !shares_vertex(qp, tp)) {
+                    emit = true;
+                    if (MODE == 0) pr = make_int2(qp.w, tp.w);
+                    else if (MODE == 1) pr = make_int2(tp.w, qp.w);
+                    else pr = make_int2(min(qp.w, tp.w), max(qp.w, tp.w));
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, emit);
+            if (m) {
+                if (emit) stage[warp][nstaged + __popc(m & ((1u << lane) - 1))] = pr;
+                nstaged += __popc(m);
+            }
+        }
+        if (nstaged > STAGE_CAP - 64) {
+            __syncwarp();
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(counter, (unsigned long long)nstaged);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (int k = lane; k < nstaged; k += 32)
+                if (base + k < capacity) out[base + k] = stage[warp][k];
+            nstaged = 0;
+            __syncwarp();
+        }
+    }
+    if (nstaged > 0) {
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)nstaged);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int k = lane; k < nstaged; k += 32)
+            if (base + k < capacity) out[base + k] = stage[warp][k];
+    }
+}
+
+// run one detection: queries (sorted view) against a tree
+static void run_traverse(ipcb_ctx* ctx, const Tree& q, const Tree& t, int mode, bool check_shared, PairList& out, bool shard)
+{
+    out.count = 0;
+    out.sorted = false;
+    if (q.n == 0 || t.n == 0 || (mode == 2 && t.n < 2)) return;
+    cudaStream_t s = ctx->stream;
+    int q_begin = 0, q_end = q.n;
+    if (shard && ctx->shard_world > 1) { // contiguous Morton range of query leaves per rank
+        q_begin = int((int64_t(q.n) * ctx->shard_rank) / ctx->shard_world);
+        q_end = int((int64_t(q.n) * (ctx->shard_rank + 1)) / ctx->shard_world);
+    }
+    const int nq = q_end - q_begin;
+    if (nq <= 0) return;
+    if (out.pairs.cap == 0) out.pairs.reserve(size_t(nq) * 8 + 1024);
+    for (int attempt = 0; attempt < 3; attempt++) {
+        IPCB_CUDA(cudaMemsetAsync(ctx->dCounters.p, 0, sizeof(unsigned long long), s));
+        const unsigned long long cap = out.pairs.cap;
+        const unsigned grid = grid_for(nq, TRAV_BLOCK);
+        const Node* nodes = t.nodes.p;
+        if (mode == 0)
+            k_traverse<0><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q.sbox.p, q.sprim.p, nodes, t.n, t.sbox.p, t.sprim.p, out.pairs.p,
+                                                      ctx->dCounters.p, cap, check_shared);
+        else if (mode == 1)
+            k_traverse<1><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q.sbox.p, q.sprim.p, nodes, t.n, t.sbox.p, t.sprim.p, out.pairs.p,
+                                                      ctx->dCounters.p, cap, check_shared);
+        else
+            k_traverse<2><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q.sbox.p, q.sprim.p, nodes, t.n, t.sbox.p, t.sprim.p, out.pairs.p,
+                                                      ctx->dCounters.p, cap, check_shared);
+        ctx->launches++;
+        IPCB_CUDA(cudaGetLastError());
+        IPCB_CUDA(cudaMemcpyAsync(ctx->pinned.p, ctx->dCounters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        IPCB_CUDA(cudaStreamSynchronize(s));
+        const unsigned long long found = (unsigned long long)ctx->pinned.p[0];
+        if (found <= cap) {
+            out.count = int64_t(found);
+            return;
+        }
+        out.pairs.reserve(size_t(found) + size_t(found) / 8); // overflow: grow and repeat the pass
+    }
+    throw Error("broad phase: candidate buffer overflow persisted");
+}
+
+static Tree& ensure_tree(ipcb_ctx* ctx, int which)
+{
+    if (which == 0) {
+        if (!ctx->vtree_ok) build_tree(ctx, ctx->vset, ctx->vtree, true), ctx->vtree_ok = true;
+        return ctx->vtree;
+    }
+    if (which == 1) {
+        if (!ctx->etree_ok) build_tree(ctx, ctx->eset, ctx->etree, true), ctx->etree_ok = true;
+        return ctx->etree;
+    }
+    if (!ctx->ftree_ok) build_tree(ctx, ctx->fset, ctx->ftree, true), ctx->ftree_ok = true;
+    return ctx->ftree;
+}
+
+// broad_phase.hpp:71-97 — which BVH is walked by which leaves follows lbvh.cpp:692-797
+void broad_detect(ipcb_ctx* ctx, int kind, PairList& out)
+{
+    if (!ctx->built) throw Error("broad phase not built");
+    Stage st(ctx, "broad_detect");
+    switch (kind) {
+    case IPCB_VV: {
+        Tree& v = ensure_tree(ctx, 0);
+        run_traverse(ctx, v, v, 2, true, out, true);
+        break;
+    }
+    case IPCB_EV: { // edges walk the vertex BVH
+        Tree& e = ensure_tree(ctx, 1);
+        Tree& v = ensure_tree(ctx, 0);
+        run_traverse(ctx, e, v, 0, true, out, true);
+        break;
+    }
+    case IPCB_EE: {
+        Tree& e = ensure_tree(ctx, 1);
+        run_traverse(ctx, e, e, 2, true, out, true);
+        break;
+    }
+    case IPCB_FV: { // vertices walk the face BVH, emitted as (face, vertex)
+        Tree& v = ensure_tree(ctx, 0);
+        Tree& f = ensure_tree(ctx, 2);
+        run_traverse(ctx, v, f, 1, true, out, true);
+        break;
+    }
+    case IPCB_EF: { // faces walk the edge BVH, emitted as (edge, face)
+        Tree& f = ensure_tree(ctx, 2);
+        Tree& e = ensure_tree(ctx, 1);
+        run_traverse(ctx, f, e, 1, true, out, true);
+        break;
+    }
+    case IPCB_FF: {
+        Tree& f = ensure_tree(ctx, 2);
+        run_traverse(ctx, f, f, 2, true, out, true);
+        break;
+    }
+    default: throw Error("bad candidate kind");
+    }
+}
+
+// sort pairs lexicographically (canonical order for fetch / parity checks)
+__global__ void k_pairs_to_keys(int64_t n, const int2* __restrict__ p, unsigned long long* __restrict__ k)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) k[i] = ((unsigned long long)(unsigned)p[i].x << 32) | (unsigned)p[i].y;
+}
+__global__ void k_keys_to_pairs(int64_t n, const unsigned long long* __restrict__ k, int2* __restrict__ p)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = make_int2(int(k[i] >> 32), int(k[i] & 0xffffffffu));
+}
+void sort_pairs(ipcb_ctx* ctx, PairList& pl)
+{
+    if (pl.sorted || pl.count < 2) {
+        pl.sorted = true;
+        return;
+    }
+    const int64_t n = pl.count;
+    ctx->hkey.reserve(n), ctx->hkey_sorted.reserve(n);
+    cudaStream_t s = ctx->stream;
+    k_pairs_to_keys<<<grid_for(n, 256), 256, 0, s>>>(n, pl.pairs.p, ctx->hkey.p);
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, bytes, ctx->hkey.p, ctx->hkey_sorted.p, n, 0, 64, s);
+    ctx->cubtmp.reserve(bytes);
+    cub::DeviceRadixSort::SortKeys(ctx->cubtmp.p, bytes, ctx->hkey.p, ctx->hkey_sorted.p, n, 0, 64, s);
+    k_keys_to_pairs<<<grid_for(n, 256), 256, 0, s>>>(n, ctx->hkey_sorted.p, pl.pairs.p);
+    ctx->launches += 11;
+    pl.sorted = true;
+}
+
+// Candidates::build, 3D (candidates.cpp:43-222): EE + FV on the whole mesh,
+// VV between codim vertices, EV between codim edges and codim vertices
+void candidates_build(ipcb_ctx* ctx, bool swept, double r)
+{
+    broad_build(ctx, swept, r);
+    {
+        Stage st(ctx, "lbvh_build");
+        if (ctx->nE >= 2) ensure_tree(ctx, 1);
+        if (ctx->nF && ctx->nV) {
+            ensure_tree(ctx, 2);
+            // the vertex queries only need the Morton order, not a hierarchy
+            if (!ctx->vtree_ok) build_tree(ctx, ctx->vset, ctx->vtree, false);
+        }
+    }
+    for (auto& c : ctx->cand) c.count = 0, c.sorted = false;
+    {
+        Stage st(ctx, "traverse_ee");
+        if (ctx->nE >= 2) run_traverse(ctx, ctx->etree, ctx->etree, 2, true, ctx->cand[IPCB_EE], true);
+    }
+    {
+        Stage st(ctx, "traverse_fv");
+        if (ctx->nF && ctx->nV) run_traverse(ctx, ctx->vtree, ctx->ftree, 1, true, ctx->cand[IPCB_FV], true);
+    }
+    const int ncv = int(ctx->codimV.size()), nce = int(ctx->codimE.size());
+    if (ncv) {
+        Stage st(ctx, "codim");
+        cudaStream_t s = ctx->stream;
+        ctx->cvset.n = ncv;
+        ctx->cvset.box.reserve(ncv), ctx->cvset.prim.reserve(ncv);
+        k_gather_set<<<grid_for(ncv, 256), 256, 0, s>>>(ncv, ctx->dCodimV.p, ctx->vset.box.p, ctx->vset.prim.p, ctx->cvset.box.p,
+                                                      ctx->cvset.prim.p);
+        ctx->launches++;
+        build_tree(ctx, ctx->cvset, ctx->cvtree, true);
+        if (ncv >= 2 && ctx->shard_rank == 0) // tiny sets are not sharded: rank 0 owns them
+            run_traverse(ctx, ctx->cvtree, ctx->cvtree, 2, false, ctx->cand[IPCB_VV], false);
+        if (nce) {
+            ctx->ceset.n = nce;
+            ctx->ceset.box.reserve(nce), ctx->ceset.prim.reserve(nce);
+            k_gather_set<<<grid_for(nce, 256), 256, 0, s>>>(nce, ctx->dCodimE.p, ctx->eset.box.p, ctx->eset.prim.p, ctx->ceset.box.p,
+                                                          ctx->ceset.prim.p);
+            ctx->launches++;
+            build_tree(ctx, ctx->ceset, ctx->cetree, false);
+            if (ctx->shard_rank == 0) run_traverse(ctx, ctx->cetree, ctx->cvtree, 0, false, ctx->cand[IPCB_EV], false);
+        }
+    }
+}
+
+} // namespace ipcb

@@ -1,0 +1,199 @@
+// ctx.cuh — the library context: host mesh tables, device mirrors, resident
+// broad-phase trees, candidate and collision sets, Hessian CSR.
+//
+// Data layout in HBM (all struct-of-arrays unless noted):
+//   X0/X1      double4 per vertex (x,y,z,pad): ONE 32-byte sector per gather
+//   boxes      6 x float per primitive (outward-rounded, lbvh.cpp:29-41)
+//   prims      int4 per primitive: vertex ids (-1 padded) + primitive id
+//   tree nodes 64 B per internal node: both child boxes + child links + range
+//   pairs      int2 per candidate
+//   collisions int2 ids + double weight (+ double eps_x + uint8 dtype for EE)
+#pragma once
+#include "common.cuh"
+#include <array>
+#include <chrono>
+#include <map>
+
+namespace ipcb {
+
+struct alignas(8) FBox {
+    float lo[3], hi[3];
+};
+
+// internal LBVH node; children: >= 0 internal node index, < 0 leaf ~sorted_position
+struct alignas(64) Node {
+    float lo[2][3], hi[2][3]; // child boxes (0 = left, 1 = right)
+    int child[2];
+    int split; // last sorted leaf of the left child
+    int last;  // last sorted leaf of the right child (= of this node)
+};
+static_assert(sizeof(Node) == 64, "one node = one 64-byte fetch");
+
+struct PrimSet {
+    int n = 0;
+    Buf<FBox> box;
+    Buf<int4> prim;
+};
+
+// Morton-sorted view of a PrimSet (+ hierarchy when built as a tree)
+struct Tree {
+    int n = 0;
+    bool has_nodes = false;
+    Buf<unsigned long long> key, key_sorted;
+    Buf<int> ord, ord_sorted;
+    Buf<FBox> sbox;
+    Buf<int4> sprim;
+    Buf<Node> nodes;
+    Buf<int> parent; // [0,n-1) internal nodes, [n-1,2n-1) leaves
+    Buf<int> flag;
+    Buf<char> tmp;
+};
+
+struct PairList {
+    Buf<int2> pairs;
+    int64_t count = 0;
+    bool sorted = false;
+};
+
+struct CollisionSet {
+    // build streams (unsorted, duplicates)
+    Buf<unsigned long long> key_raw, key_sorted;
+    Buf<double> w_raw;
+    Buf<double> eps_raw;
+    Buf<unsigned char> dt_raw;
+    Buf<int> idx_raw, idx_sorted;
+    // final, sorted by key, merged
+    Buf<int2> ids;
+    Buf<double> w, eps;
+    Buf<unsigned char> dtype;
+    Buf<int> head, pos;
+    Buf<double> wsum;
+    int64_t count = 0;
+};
+
+struct StageTimer {
+    std::vector<std::pair<std::string, float>> stages;
+};
+
+} // namespace ipcb
+
+struct ipcb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int64_t launches = 0;
+    int shard_rank = 0, shard_world = 1;
+
+    // ---- host mesh (collision_mesh.cpp:15-127)
+    int nV = 0, nE = 0, nF = 0;
+    std::vector<double> rest; // 3 per vertex
+    std::vector<int32_t> hE, hF, hF2E;
+    std::vector<int32_t> codimV, codimE;
+    std::vector<double> vArea, eArea;
+    // ---- device mesh
+    ipcb::Buf<int2> dE;
+    ipcb::Buf<int4> dF;   // f0,f1,f2,pad
+    ipcb::Buf<int4> dF2E; // e0,e1,e2,pad
+    ipcb::Buf<double4> dRest;
+    ipcb::Buf<double> dVArea, dEArea;
+    ipcb::Buf<int> dCodimV, dCodimE;
+
+    // ---- positions
+    ipcb::Buf<double> stageA, stageB; // col-major staging for host entry points
+    ipcb::Buf<double4> X0, X1;
+
+    // ---- broad phase
+    bool built = false;
+    bool swept = false;
+    ipcb::PrimSet vset, eset, fset, cvset, ceset;
+    ipcb::Tree vtree, etree, ftree, cvtree, cetree;
+    bool vtree_ok = false, etree_ok = false, ftree_ok = false;
+    ipcb::Buf<float> scene; // 6 floats: min xyz, max xyz
+    ipcb::PairList detected[6];
+
+    // ---- candidates / collisions
+    ipcb::PairList cand[4];
+    ipcb::CollisionSet coll[4];
+    double dmin = 0;
+    bool coll_valid = false;
+
+    // ---- potential
+    ipcb::Buf<double> dScalar; // small device scalars (energy, toi, ...)
+    ipcb::Buf<double> dGrad;
+    // hessian assembly
+    ipcb::Buf<unsigned long long> hkey, hkey_sorted;
+    ipcb::Buf<int> hidx, hidx_sorted;
+    ipcb::Buf<double> hval;             // 9 doubles per emitted block
+    ipcb::Buf<unsigned short> hmask;    // 9-bit non-zero mask per emitted block
+    ipcb::Buf<int> hhead, hpos, hcolptr, hcnt, hscan;
+    ipcb::Buf<double> ublk;             // unique blocks (9 doubles)
+    ipcb::Buf<unsigned short> umask;
+    ipcb::Buf<unsigned long long> ukey;
+    ipcb::Buf<int> outer, inner;
+    ipcb::Buf<double> vals;
+    int64_t nnz = 0;
+    ipcb::Buf<char> cubtmp;
+
+    // ---- ccd
+    ipcb::Buf<char> ccd_work;
+
+    // ---- counters read back through pinned memory
+    ipcb::Pinned pinned;
+    ipcb::Buf<unsigned long long> dCounters; // 16 device counters
+
+    // ---- per-stage timing of the last API call
+    std::vector<std::pair<std::string, float>> stage_ms;
+    std::vector<std::string> stage_names_keepalive;
+};
+
+namespace ipcb {
+
+// RAII stage timer using CUDA events on the context's stream
+struct Stage {
+    ipcb_ctx* ctx;
+    const char* name;
+    cudaEvent_t a, b;
+    Stage(ipcb_ctx* c, const char* n) : ctx(c), name(n)
+    {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, ctx->stream);
+    }
+    ~Stage()
+    {
+        cudaEventRecord(b, ctx->stream);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        ctx->stage_ms.emplace_back(name, ms);
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+    }
+};
+
+// positions
+void upload_positions(ipcb_ctx* ctx, const double* hV, int ld, Buf<double>& stage);
+void convert_positions(ipcb_ctx* ctx, const double* dV, int ld, Buf<double4>& X);
+
+// broad phase (broad.cu)
+void broad_build(ipcb_ctx* ctx, bool swept, double inflation_radius);
+void broad_detect(ipcb_ctx* ctx, int kind, PairList& out);
+void candidates_build(ipcb_ctx* ctx, bool swept, double inflation_radius);
+void sort_pairs(ipcb_ctx* ctx, PairList& pl);
+
+// collisions (collisions.cu)
+void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags);
+double collisions_min_distance(ipcb_ctx* ctx);
+
+// potential (potential.cu)
+void barrier_energy(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_out);
+void barrier_gradient(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_grad);
+void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode);
+
+// ccd (ccd.cu)
+void ccd_stepsize(ipcb_ctx* ctx, double min_distance, const ipcb_ccd_params& p, double* d_out);
+void ccd_narrow_phase(ipcb_ctx* ctx, int kind, int64_t n, const double* h_t0, const double* h_t1, double min_distance, double tmax,
+                      const ipcb_ccd_params& p, uint8_t* h_hit, double* h_toi);
+
+ipcb_ccd_params resolve_ccd(const ipcb_ccd_params* p);
+
+} // namespace ipcb

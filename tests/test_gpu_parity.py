@@ -1,0 +1,202 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on
+identical seeded inputs.  Bars (BASELINE.json north_star): candidate and
+collision sets bit-exact after canonical sort; Hessian sparsity identical;
+energy / gradient / Hessian values within 1e-10 relative; CCD step never larger
+than the oracle's by more than the tolerance."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10  # north_star: values within 1e-10 relative
+
+
+def _scene(scenes, name):
+    return {
+        "c1": lambda: scenes.cloth_on_sphere(64, 32),
+        "drape": lambda: scenes.cloth_on_sphere(48, 24, drape=True),
+        "stack": lambda: scenes.cloth_stack(3, 30),
+        "stack_tight": lambda: scenes.cloth_stack(4, 20, gap=0.2),
+        "soup": lambda: scenes.random_soup(150, seed=7),
+        "sheets": lambda: scenes.perturbed_sheets(3, 16),
+    }[name]()
+
+
+SCENES = ["c1", "drape", "stack", "stack_tight", "soup", "sheets"]
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    n = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / n if n > 0 else np.linalg.norm(a)
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_vertex_boxes_bit_exact(cuda, oracle, scenes, name):
+    V0, V1, E, F, P = _scene(scenes, name)
+    for swept in (False, True):
+        res = []
+        for api in (cuda, oracle):
+            mesh = api.CollisionMesh(V0, E, F)
+            bp = api.BroadPhase(mesh)
+            bp.build(V0, V1 if swept else None, inflation_radius=0.5 * P["dhat"])
+            res.append(bp.vertex_boxes())
+        assert res[0].dtype == np.float32 and np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("swept", [False, True])
+def test_broad_phase_all_kinds(cuda, oracle, scenes, name, swept):
+    V0, V1, E, F, P = _scene(scenes, name)
+    if swept and name == "sheets":
+        V1 = V0 + 0.2 * (V1 - V0)  # keep the 6-kind brute-force comparison small
+    got, want = [], []
+    for api, out in ((cuda, got), (oracle, want)):
+        mesh = api.CollisionMesh(V0, E, F)
+        if api is oracle:
+            oracle.set_broad_method(mesh, 1)  # brute force over the float-box predicate
+        bp = api.BroadPhase(mesh)
+        bp.build(V0, V1 if swept else None, inflation_radius=0.5 * P["dhat"])
+        for fn in ("vertex_vertex", "edge_vertex", "edge_edge", "face_vertex", "edge_face", "face_face"):
+            out.append(getattr(bp, "detect_%s_candidates" % fn)())
+    for kind, (a, b) in enumerate(zip(got, want)):
+        assert a.shape == b.shape, "kind %d: %d vs %d candidates" % (kind, len(a), len(b))
+        assert np.array_equal(a, b), "kind %d candidate sets differ" % kind
+        assert len(np.unique(a, axis=0)) == len(a), "duplicate candidates"  # test_lbvh.cpp:142-149
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_collision_set_and_potential(cuda, oracle, scenes, name):
+    V0, V1, E, F, P = _scene(scenes, name)
+    dhat = P["dhat"]
+    for area in (False, True):
+        res = {}
+        for key, api in (("cuda", cuda), ("oracle", oracle)):
+            mesh = api.CollisionMesh(V0, E, F)
+            c = api.NormalCollisions()
+            c.set_use_area_weighting(area)
+            c.build(mesh, V0, dhat)
+            sets = [getattr(c, k + "_collisions") for k in ("vv", "ev", "ee", "fv")]
+            B = api.BarrierPotential(dhat, 1.0, use_physical_barrier=area)
+            X = V0 + 0.02 * dhat * np.sin(np.arange(V0.size).reshape(V0.shape))  # evaluate off the build point
+            res[key] = dict(sets=sets, e=B(c, mesh, X), g=B.gradient(c, mesh, X),
+                            h0=B.hessian(c, mesh, X), h1=B.hessian(c, mesh, X, api.PSDProjectionMethod.CLAMP),
+                            h2=B.hessian(c, mesh, X, api.PSDProjectionMethod.ABS), dmin=c.compute_minimum_distance(mesh, X))
+        a, b = res["cuda"], res["oracle"]
+        assert sum(len(s.ids) for s in b["sets"]) > 0
+        for sa, sb in zip(a["sets"], b["sets"]):
+            assert np.array_equal(sa.ids, sb.ids)  # bit-exact collision set (canonical order)
+            assert np.array_equal(sa.dtype, sb.dtype)
+            assert np.array_equal(sa.eps_x, sb.eps_x)
+            assert relerr(sa.weight, sb.weight) <= 1e-14
+        assert abs(a["e"] - b["e"]) <= RTOL * abs(b["e"])
+        assert relerr(a["g"], b["g"]) <= RTOL
+        assert abs(a["dmin"] - b["dmin"]) <= 1e-14 * b["dmin"]
+        for h in ("h0", "h1", "h2"):
+            A, Bm = a[h], b[h]
+            assert np.array_equal(A.indptr, Bm.indptr), h + ": outer index arrays differ"
+            assert np.array_equal(A.indices, Bm.indices), h + ": sparsity pattern differs"
+            assert relerr(A.data, Bm.data) <= RTOL, h
+        # projected Hessians are PSD and symmetric
+        H = a["h1"]
+        assert abs(H - H.T).max() <= 1e-12 * abs(H).max()
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_step_size(cuda, oracle, scenes, name):
+    V0, V1, E, F, P = _scene(scenes, name)
+    for md in (0.0, 1e-4 * P["dhat"]):
+        steps = {}
+        for key, api in (("cuda", cuda), ("oracle", oracle)):
+            mesh = api.CollisionMesh(V0, E, F)
+            steps[key] = (api.compute_collision_free_stepsize(mesh, V0, V1, md),
+                          api.compute_collision_free_stepsize(mesh, V0, V1, md, narrow_phase_ccd=api.AdditiveCCD()))
+        (ti_g, ac_g), (ti_o, ac_o) = steps["cuda"], steps["oracle"]
+        assert 0 <= ti_g <= 1 and 0 <= ac_g <= 1
+        # Tight Inclusion: the queue finds the earliest terminal box: never later than the sequential
+        # search, and within the time tolerance of it
+        assert ti_g <= ti_o + 1e-12
+        assert ti_g >= ti_o - 1e-3 * max(ti_o, 1e-3) - 1e-6, (ti_g, ti_o)
+        # Additive CCD is the same arithmetic; the shared-bound pruning can only change which query stops first
+        assert abs(ac_g - ac_o) <= 1e-9 * max(ac_o, 1e-12), (ac_g, ac_o)
+        # advancing by the returned step must be intersection free w.r.t. the oracle's check
+        if ti_g < 1:
+            mesh = oracle.CollisionMesh(V0, E, F)
+            assert oracle.is_step_collision_free(mesh, V0, V0 + 0.999 * ti_g * (V1 - V0), md)
+
+
+def test_codim_known_answers(cuda):
+    """collisions/test_normal_collisions.cpp:14-107 and :109-209 of the reference, through the CUDA path"""
+    V = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]], float)
+    V -= V.mean(0)
+    mesh = cuda.CollisionMesh(V)
+    assert mesh.num_codim_vertices() == 8
+    c = cuda.NormalCollisions()
+    c.build(mesh, V, 0.25, 0.8)
+    assert c.counts() == [12, 0, 0, 0]
+    B = cuda.BarrierPotential(0.25, 1.0)
+    assert B(c, mesh, V) > 0
+    f = -B.gradient(c, mesh, V).reshape(-1, 3)
+    assert np.allclose(f / np.linalg.norm(f, axis=1, keepdims=True), V / np.linalg.norm(V, axis=1, keepdims=True))
+    V1 = V.copy()
+    V1[:, 1] *= 0.5
+    cand = cuda.Candidates()
+    cand.build(mesh, V, V1, 0.4)
+    assert cand.size() == len(cand.vv_candidates) > 0
+    assert not cand.is_step_collision_free(mesh, V, V1, 0.8)
+    assert cand.compute_collision_free_stepsize(mesh, V, V1, 0.8) == pytest.approx((1 - (0.8 + 1e-4)) / 2 / 0.25, rel=1.2e-5)
+
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 0, -1], [-1, 0, 0], [0, 0, 1], [0, 1, 0], [0, 2, 0], [0, 3, 0]], float)
+    E = np.array([[0, 1], [0, 2], [0, 3], [0, 4]])
+    mesh = cuda.CollisionMesh(V, E)
+    assert (mesh.num_codim_vertices(), mesh.num_codim_edges()) == (3, 4)
+    V1 = V.copy()
+    V1[5:, 1] -= 4
+    cand = cuda.Candidates()
+    cand.build(mesh, V, V1, 1e-3)
+    assert [len(cand.vv_candidates), len(cand.ev_candidates), len(cand.ee_candidates), len(cand.fv_candidates)] == [3, 12, 0, 0]
+    assert cand.compute_collision_free_stepsize(mesh, V, V1, 2e-3) == pytest.approx((1 - (2e-3 + 1e-4)) / 4, rel=1.2e-5)
+    c = cuda.NormalCollisions()
+    c.build(mesh, V, 0.25, 0.8)
+    assert c.counts() == [2, 4, 0, 0]
+
+
+def test_narrow_phase_matches_oracle(cuda, oracle):
+    rng = np.random.default_rng(5)
+    n = 400
+    for kind in (0, 1, 2, 3):
+        a = rng.uniform(-1, 1, (n, 4, 3))
+        b = a + rng.normal(0, 0.6, (n, 4, 3))
+        for ccd in ("ti", "accd"):
+            hg, tg = cuda.narrow_phase_ccd(kind, a, b, 1e-3, 1.0, cuda.AdditiveCCD() if ccd == "accd" else None)
+            ho, to = oracle.narrow_phase_ccd(kind, a, b, 1e-3, 1.0, oracle.AdditiveCCD() if ccd == "accd" else None)
+            assert np.array_equal(hg, ho), (kind, ccd, np.flatnonzero(hg != ho)[:5])
+            assert hg.sum() > 0
+            if ccd == "accd":
+                assert np.allclose(tg[hg], to[ho], rtol=1e-9, atol=0)
+            else:
+                assert np.all(tg[hg] <= to[ho] + 1e-12)
+                assert np.all(tg[hg] >= to[ho] - 2e-3)
+
+
+def test_errors_are_reported(cuda):
+    V = np.zeros((3, 3))
+    with pytest.raises(RuntimeError, match="Unable to find edge!"):
+        cuda.CollisionMesh(V, np.array([[0, 1]]), np.array([[0, 1, 2]]))  # collision_mesh.cpp:537
+    mesh = cuda.CollisionMesh(np.eye(3))
+    with pytest.raises(RuntimeError):
+        cuda.BarrierPotential(1e-3)(cuda.NormalCollisions(), mesh, V)  # stale / unbuilt collision handle
+
+
+def test_empty_inputs(cuda):
+    V = np.array([[0.0, 0, 0], [1, 0, 0], [0, 1, 0]])
+    mesh = cuda.CollisionMesh(V, np.array([[0, 1], [1, 2], [0, 2]]), np.array([[0, 1, 2]]))
+    c = cuda.NormalCollisions()
+    c.build(mesh, V, 1e-3)
+    assert c.empty()
+    B = cuda.BarrierPotential(1e-3)
+    assert B(c, mesh, V) == 0.0
+    assert not B.gradient(c, mesh, V).any()
+    H = B.hessian(c, mesh, V)
+    assert H.shape == (9, 9) and H.nnz == 0  # potential.cpp:107-109
+    assert cuda.compute_collision_free_stepsize(mesh, V, V + 1.0) == 1.0  # candidates.cpp:263-265
