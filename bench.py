@@ -1,0 +1,346 @@
+"""bench.py — ms per contact step (NormalCollisions::build + barrier E / grad / Hessian(CLAMP) +
+compute_collision_free_stepsize) on the BASELINE.json workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c3|c2|c1|c5]
+
+One JSON line on stdout (rank 0).  `value` = whole-job ms per step with inputs resident in HBM,
+timed with CUDA events on the library's own stream, max over ranks; `e2e` = the same step through the
+host-buffer C ABI (pinned host inputs, host results); `roofline` = the dominant kernel against the
+measured HBM copy bandwidth; `cpu_baseline` = the CPU restatement on a bounded sample of the workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ms per contact step (build+barrier E/grad/Hess+CCD)"
+
+WORKLOADS = {
+    # name: (description, generator kwargs, bounded CPU sample kwargs, sample scale = full tris / sample tris)
+    "c1": ("C1 64x64 cloth over a 32x32 UV sphere (~10K tris), dhat=1e-3", dict(kind="sphere", n=64, res=32, drape=False), None),
+    "c2": ("C2 256x256 cloth draped on a 50K-tri sphere (~180K tris), dhat=1e-3", dict(kind="sphere", n=256, res=160, drape=True), None),
+    "c3": ("C3 8 stacked 250x250 cloth layers (1.0M tris), gap 0.5*dhat, dense edge-edge contact", dict(kind="stack", layers=8, n=250, gap=0.5),
+           dict(kind="stack", layers=3, n=100, gap=0.5, h=1.0 / 250)),
+    "c5": ("C5 16-layer compressed stack (2.0M tris), gap 0.2*dhat, PSD=CLAMP", dict(kind="stack", layers=16, n=250, gap=0.2),
+           dict(kind="stack", layers=3, n=100, gap=0.2, h=1.0 / 250)),
+}
+
+
+def make_scene(scenes, spec):
+    if spec["kind"] == "sphere":
+        return scenes.cloth_on_sphere(spec["n"], spec["res"], drape=spec["drape"])
+    return scenes.cloth_stack(spec["layers"], spec["n"], gap=spec["gap"], h=spec.get("h"))
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks and throttle reasons while the timed region runs"""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def cpu_step(api, mesh, V0, V1, dhat):
+    """one contact step through the oracle's (reference-equivalent) CPU path"""
+    c = api.NormalCollisions()
+    c.build(mesh, V0, dhat)
+    B = api.BarrierPotential(dhat, 1.0)
+    e = B(c, mesh, V0)
+    g = B.gradient(c, mesh, V0)
+    H = B.hessian(c, mesh, V0, api.PSDProjectionMethod.CLAMP)
+    step = api.compute_collision_free_stepsize(mesh, V0, V1)
+    return e, g, H, step, c.counts()
+
+
+def run_reference(args, desc, full_spec, sample_spec):
+    """--impl reference: the CPU restatement of the reference path (the upstream library cannot be built
+    here) with all host threads, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("ipcb_scenes", os.path.join(ROOT, "ipc-toolkit_b200", "scenes.py"))
+    scenes = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(scenes)
+    api = pyoracle.load(fast=True)
+    use = sample_spec or full_spec
+    V0, V1, E, F, P = make_scene(scenes, use)
+    full_tris = make_tris(full_spec)
+    scale = full_tris / F.shape[0]
+    mesh = api.CollisionMesh(V0, E, F)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        out = cpu_step(api, mesh, V0, V1, P["dhat"])
+        dt = (time.perf_counter() - t) * 1e3
+        if it >= args.warmup:
+            times.append(dt)
+    ms = float(np.mean(times)) * scale
+    cores = api.num_threads()
+    sample = "%d of %d triangles of the workload (same generator), ms scaled by %.3f" % (F.shape[0], full_tris, scale)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "triangles": full_tris},
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "collisions_in_sample": out[4],
+    }))
+
+
+def make_tris(spec):
+    if spec["kind"] == "sphere":
+        return 2 * spec["n"] ** 2 + 2 * spec["res"] * (spec["res"] - 1)
+    return spec["layers"] * 2 * spec["n"] ** 2
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    desc, full_spec, sample_spec = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, desc, full_spec, sample_spec)
+
+    import torch
+    import ipctk_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    api = ipctk_b200.library()
+    lib = api.lib
+    scenes = ipctk_b200._pkg.scenes
+    abi = ipctk_b200._pkg._abi
+    V0, V1, E, F, P = make_scene(scenes, full_spec)
+    dhat = P["dhat"]
+    nV = V0.shape[0]
+    mesh = api.CollisionMesh(V0, E, F, device=local)
+    ctx = mesh._ctx
+    lib.check(lib.ctx_set_shard(ctx, rank, world))
+    stream = torch.cuda.ExternalStream(lib.ctx_stream(ctx), device=torch.device("cuda", local))
+
+    # ---- device-resident inputs (column-major N x 3 like Eigen)
+    dV0 = torch.from_numpy(np.asfortranarray(V0).T.copy()).cuda()  # 3 x N contiguous == N x 3 column-major
+    dV1 = torch.from_numpy(np.asfortranarray(V1).T.copy()).cuda()
+    d_energy = torch.zeros(1, dtype=torch.float64, device="cuda")
+    d_grad = torch.zeros(3 * nV, dtype=torch.float64, device="cuda")
+    d_step = torch.zeros(1, dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    bp = abi.BarrierParams(dhat, 1.0, 0)
+    ccd = abi.CcdParams(0, 0.0, 0, 0.0)
+    counts = (C.c_int64 * 4)()
+    nnz = C.c_int64()
+    info = {}
+    stage_acc = {}
+
+    def collect_stages():
+        names = (C.c_char_p * 32)()
+        ms = (C.c_float * 32)()
+        n = lib.ctx_stage_times(ctx, 32, names, ms)
+        for i in range(n):
+            stage_acc.setdefault(names[i].decode(), []).append(ms[i])
+
+    def device_step(record=False):
+        p0, p1 = C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr())
+        lib.check(lib.collisions_build_dev(ctx, p0, nV, dhat, 0.0, 0, counts))
+        if record:
+            collect_stages()
+        info["collisions"] = list(counts)
+        lib.check(lib.barrier_energy_dev(ctx, p0, nV, C.byref(bp), C.c_void_p(d_energy.data_ptr())))
+        if record:
+            collect_stages()
+        lib.check(lib.barrier_gradient_dev(ctx, p0, nV, C.byref(bp), C.c_void_p(d_grad.data_ptr())))
+        if record:
+            collect_stages()
+        lib.check(lib.barrier_hessian_dev(ctx, p0, nV, C.byref(bp), 1, C.byref(nnz)))
+        if record:
+            collect_stages()
+        info["nnz"] = nnz.value
+        lib.check(lib.ccd_stepsize_dev(ctx, p0, p1, nV, 0.0, C.byref(ccd), C.c_void_p(d_step.data_ptr())))
+        if record:
+            collect_stages()
+        if dist is not None:  # sum / sum / min all-reduces over NVLink; the Hessian stays per rank
+            with torch.cuda.stream(stream):
+                dist.all_reduce(d_energy)
+                dist.all_reduce(d_grad)
+                dist.all_reduce(d_step, op=dist.ReduceOp.MIN)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        total = 0.0
+        for _ in range(steps):
+            flush.fill_(1)  # evict L2 between timed iterations
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            fn()
+            b.record(stream)
+            b.synchronize()
+            total += a.elapsed_time(b)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t = torch.tensor([total], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+        return float(t.item()) / steps
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = C.c_int64()
+    lib.ctx_launch_count(ctx, C.byref(l0))
+    ms_dev = timed(device_step, args.steps, args.warmup)
+    l1 = C.c_int64()
+    lib.ctx_launch_count(ctx, C.byref(l1))
+    launches = (l1.value - l0.value) // (args.steps + args.warmup) * args.steps
+    device_step(record=True)  # one extra, untimed pass to read the per-stage device times
+
+    # ---- end to end through the host-buffer C ABI (pinned inputs, host results)
+    hV0 = torch.from_numpy(np.asfortranarray(V0).T.copy()).pin_memory()
+    hV1 = torch.from_numpy(np.asfortranarray(V1).T.copy()).pin_memory()
+    h_grad = torch.zeros(3 * nV, dtype=torch.float64).pin_memory()
+    hv0p, hv1p = C.c_void_p(hV0.data_ptr()), C.c_void_p(hV1.data_ptr())
+    e2e_bytes = {"h2d": 0, "d2h": 0}
+    hbuf = {}
+
+    def host_step():
+        e, st = C.c_double(), C.c_double()
+        lib.check(lib.collisions_build(ctx, hv0p, nV, dhat, 0.0, 0, counts))
+        lib.check(lib.barrier_energy(ctx, hv0p, nV, C.byref(bp), C.byref(e)))
+        lib.check(lib.barrier_gradient(ctx, hv0p, nV, C.byref(bp), C.c_void_p(h_grad.data_ptr())))
+        lib.check(lib.barrier_hessian(ctx, hv0p, nV, C.byref(bp), 1, C.byref(nnz)))
+        n = nnz.value
+        if hbuf.get("n", -1) < n:
+            hbuf["outer"] = torch.zeros(3 * nV + 1, dtype=torch.int32).pin_memory()
+            hbuf["inner"] = torch.zeros(int(n * 1.2) + 1, dtype=torch.int32).pin_memory()
+            hbuf["vals"] = torch.zeros(int(n * 1.2) + 1, dtype=torch.float64).pin_memory()
+            hbuf["n"] = int(n * 1.2)
+        lib.check(lib.barrier_hessian_fetch(ctx, C.c_void_p(hbuf["outer"].data_ptr()), C.c_void_p(hbuf["inner"].data_ptr()),
+                                            C.c_void_p(hbuf["vals"].data_ptr())))
+        lib.check(lib.ccd_stepsize(ctx, hv0p, hv1p, nV, 0.0, C.byref(ccd), C.byref(st)))
+        e2e_bytes["h2d"] = 24 * nV * 4 + 24 * nV * 2  # V uploaded by build / energy / gradient / hessian + (V0, V1) by ccd
+        e2e_bytes["d2h"] = 8 + 24 * nV + 4 * (3 * nV + 1) + 12 * n + 8
+        info["step"], info["energy"] = st.value, e.value
+
+    ms_e2e = None
+    if world == 1:
+        ms_e2e = timed(host_step, max(2, args.steps // 2), 1)
+    sampler.stop_flag = True
+
+    # ---- roofline of the dominant stage (algorithmic bytes: DESIGN.md "Kernels and rooflines")
+    stages = {k: float(np.mean(v)) for k, v in stage_acc.items()}
+    peak, peak_kind = load_peaks()
+    ncoll = info.get("collisions", [0, 0, 0, 0])
+    nblk = 4 * ncoll[0] + 9 * ncoll[1] + 16 * (ncoll[2] + ncoll[3])
+    # hessian_local: per collision ids+record (24 B) + stencil gather (32 B per vertex) in, per block 8 B key + 72 B values + 2 B mask out
+    alg_bytes = sum(c * (24 + 32 * n) for c, n in zip(ncoll, (2, 3, 4, 4))) + nblk * 82
+    dom_ms = stages.get("hessian_local")
+    roof = None
+    if dom_ms:
+        ach = alg_bytes / (dom_ms * 1e-3) / 1e9
+        roof = {"kernel": "k_hessian_local", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_kind, "algorithmic_bytes": alg_bytes, "kernel_ms": dom_ms,
+                "note": "FP64-bound in practice (Jacobi PSD projection); see profiles/ and DESIGN.md"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle
+
+        oapi = pyoracle.load(fast=True)
+        use = sample_spec or full_spec
+        sV0, sV1, sE, sF, sP = make_scene(scenes, use)
+        scale = F.shape[0] / sF.shape[0]
+        omesh = oapi.CollisionMesh(sV0, sE, sF)
+        t = time.perf_counter()
+        cpu_step(oapi, omesh, sV0, sV1, sP["dhat"])
+        cpu_ms = (time.perf_counter() - t) * 1e3 * scale
+        cpu = {"value": cpu_ms, "unit": "ms", "cores": oapi.num_threads(), "kind": "port",
+               "sample": "%d of %d triangles (same generator), one step, ms scaled by %.3f" % (sF.shape[0], F.shape[0], scale)}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": ms_dev, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": desc, "triangles": int(F.shape[0]), "vertices": int(nV), "edges": int(E.shape[0]), "dhat": dhat,
+                       "psd": "CLAMP", "ccd": "TightInclusion", "l2": "flushed between timed steps (256 MB write)",
+                       "parallelism": "candidate shards by Morton range of query leaves" if world > 1 else "single GPU"},
+            "e2e": None if ms_e2e is None else {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": e2e_bytes["h2d"],
+                                                "d2h_bytes_per_step": e2e_bytes["d2h"]},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "stages_ms": stages,
+            "counts": {"collisions_rank0": ncoll, "hessian_nnz_rank0": info.get("nnz"), "step": info.get("step"),
+                       "energy": info.get("energy")},
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -560,8 +560,10 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     k_block_heads<<<grid_for(nblk, 256), 256, 0, s>>>(nblk, ctx->hkey_sorted.p, ctx->hhead.p);
     cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, b2, ctx->hhead.p, ctx->hpos.p, nblk, s);
     IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[8], ctx->hpos.p + (nblk - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[10], ctx->hhead.p + (nblk - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
     IPCB_CUDA(cudaStreamSynchronize(s));
-    const int nU = *reinterpret_cast<int*>(&ctx->pinned.p[8]) + 1; // the last element always belongs to the last run
+    // number of runs = heads before the last element + (1 if the last element starts a run)
+    const int nU = *reinterpret_cast<int*>(&ctx->pinned.p[8]) + *reinterpret_cast<int*>(&ctx->pinned.p[10]);
     ctx->ukey.reserve(nU), ctx->ublk.reserve(9 * size_t(nU)), ctx->umask.reserve(nU);
     k_block_reduce<<<grid_for(nblk, 256), 256, 0, s>>>(nblk, ctx->hkey_sorted.p, ctx->hidx_sorted.p, ctx->hhead.p, ctx->hpos.p, ctx->hval.p,
                                                        ctx->hmask.p, ctx->ukey.p, ctx->ublk.p, ctx->umask.p);

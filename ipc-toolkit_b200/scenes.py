@@ -75,14 +75,15 @@ def cloth_on_sphere(n_cloth=64, sphere_res=32, dhat=1e-3, seed=1, drape=False, o
     return V0, V1, _edges(F), F, {"dhat": dhat, "n_cloth_vertices": Vc.shape[0]}
 
 
-def cloth_stack(layers=8, n=250, dhat=1e-3, gap=0.5, seed=3):
+def cloth_stack(layers=8, n=250, dhat=1e-3, gap=0.5, seed=3, h=None):
     """C3 / C5: `layers` stacked n x n cloth sheets, gap*dhat apart, each rotated by a distinct small
-    angle so that edges cross (dense edge-edge contact)"""
+    angle so that edges cross (dense edge-edge contact).  `h` fixes the cell size (default 1/n, i.e. a
+    unit sheet); a smaller n with the same h is a crop of the same workload (bounded CPU samples)."""
     rng = np.random.default_rng(seed)
-    h = 1.0 / n
+    h = 1.0 / n if h is None else h
     parts = []
     for k in range(layers):
-        V, F = grid_sheet(n, n, 1.0)
+        V, F = grid_sheet(n, n, n * h)
         ang = 0.05 + 0.11 * k
         c, s = np.cos(ang), np.sin(ang)
         V[:, :2] = V[:, :2] @ np.array([[c, -s], [s, c]]).T
@@ -93,8 +94,8 @@ def cloth_stack(layers=8, n=250, dhat=1e-3, gap=0.5, seed=3):
     V0, F = _merge(parts)
     V1 = V0.copy()
     nv = parts[0][0].shape[0]
-    for k in range(layers):  # squeeze the stack: every layer moves towards the middle
-        V1[k * nv:(k + 1) * nv, 2] -= (k - 0.5 * (layers - 1)) * 0.8 * gap * dhat
+    for k in range(layers):  # squeeze the stack past contact: neighbouring layers meet at t ~ 0.77
+        V1[k * nv:(k + 1) * nv, 2] -= (k - 0.5 * (layers - 1)) * 1.3 * gap * dhat
     return V0, V1, _edges(F), F, {"dhat": dhat, "layers": layers}
 
 
