@@ -255,6 +255,8 @@ def main():
     lib.ctx_launch_count(ctx, C.byref(l1))
     launches = (l1.value - l0.value) // (args.steps + args.warmup) * args.steps
     device_step(record=True)  # one extra, untimed pass to read the per-stage device times
+    lib.check(lib.candidates_build_swept_dev(ctx, C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr()), nV, 0.0, counts))
+    info["ccd_candidates"] = list(counts)
 
     # ---- end to end through the host-buffer C ABI (pinned inputs, host results)
     hV0 = torch.from_numpy(np.asfortranarray(V0).T.copy()).pin_memory()
@@ -334,7 +336,8 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
             "stages_ms": stages,
-            "counts": {"collisions_rank0": ncoll, "hessian_nnz_rank0": info.get("nnz"), "step": info.get("step"),
+            "counts": {"collisions_rank0": ncoll, "ccd_candidates_rank0": info.get("ccd_candidates"),
+                       "hessian_nnz_rank0": info.get("nnz"), "step": info.get("step"),
                        "energy": info.get("energy")},
         }
         print(json.dumps(out))

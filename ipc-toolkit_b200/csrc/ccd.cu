@@ -7,20 +7,25 @@
 // Tight-Inclusion root finder itself (third-party ticcd v1.0.6, not in the
 // reference tree) is re-designed for the GPU from the published algorithm:
 //
-//   * level 0: one thread per candidate gathers its 8 points, evaluates the
-//     initial distance, tolerances and the floating-point filter, and tests the
-//     root box [0,1]^3; only survivors get a query record and a queue unit;
-//   * a GLOBAL interval-subdivision queue: every unit is (query, dyadic t/u/v
-//     box); one kernel launch processes a whole level of all live queries, tests
-//     the 8-corner co-domain box against the eps-cube, records terminal boxes
-//     with atomicMin on the query's TOI bit pattern, and pushes split children
-//     with warp-aggregated atomics.  The earliest TOI over all terminal boxes is
-//     exactly what the sequential breadth-first search returns (it returns the
-//     first terminal box in (level, t) order), see DESIGN.md;
-//   * cross-query pruning with a global bound mirrors the reference's atomic
-//     earliest_toi (candidates.cpp:267-286);
-//   * the rare queries whose TOI is below SMALL_TOI are re-run with the
-//     reference's no-zero-TOI refinement (tight_inclusion_ccd.cpp:59-72).
+//   * one thread per candidate gathers its 8 points (one 32-byte sector per
+//     vertex), evaluates the initial distance, the domain tolerances and the
+//     floating-point filter, and tests the root box [0,1]^3 — most candidates
+//     end here;
+//   * survivors refine IN REGISTERS: an earliest-time-first depth-first
+//     subdivision over dyadic (t,u,v) boxes with a small per-thread stack.  The
+//     result is the minimum lower time bound over all terminal boxes, which is
+//     what the sequential breadth-first search of the library returns (it
+//     returns the first terminal box in (level, t) order);
+//   * like the reference's `std::atomic<double> earliest_toi`
+//     (candidates.cpp:267-286) a global bound holds the minimum of the FINAL
+//     times of impact published so far; every thread re-reads it while refining,
+//     so late queries only search [0, bound];
+//   * a query that exceeds its in-register unit budget spills its stack into a
+//     GLOBAL interval-subdivision queue that is processed level by level by all
+//     SMs (warp-aggregated atomic pushes), so a pathological query is refined by
+//     thousands of threads instead of stalling one warp;
+//   * queries whose TOI is below SMALL_TOI are re-run with the reference's
+//     no-zero-TOI refinement (tight_inclusion_ccd.cpp:59-72 + ticcd's loop).
 #include "ctx.cuh"
 #include "geom.cuh"
 
@@ -52,7 +57,6 @@ struct QuerySource {
     const double* raw0;
     const double* raw1;
 };
-__device__ inline d3 ldp(const double4* X, int i) { return load_vertex(X, i); }
 // stencil at t0 / t1; returns number of points (2, 3, 4)
 __device__ inline int load_query(const QuerySource& q, int64_t i, d3* a, d3* b)
 {
@@ -72,7 +76,7 @@ __device__ inline int load_query(const QuerySource& q, int64_t i, d3* a, d3* b)
             const int4 f = __ldg(q.F + c.x);
             vid[0] = c.y, vid[1] = f.x, vid[2] = f.y, vid[3] = f.z;
         }
-        for (int k = 0; k < n; k++) a[k] = ldp(q.X0, vid[k]), b[k] = ldp(q.X1, vid[k]);
+        for (int k = 0; k < n; k++) a[k] = load_vertex(q.X0, vid[k]), b[k] = load_vertex(q.X1, vid[k]);
     } else {
         for (int k = 0; k < n; k++) {
             a[k] = { q.raw0[12 * i + 3 * k], q.raw0[12 * i + 3 * k + 1], q.raw0[12 * i + 3 * k + 2] };
@@ -94,13 +98,16 @@ __device__ inline void atomic_min_double(unsigned long long* addr, double v) // 
 {
     atomicMin(addr, (unsigned long long)__double_as_longlong(v));
 }
-__device__ inline double load_bound(const unsigned long long* addr)
+__host__ __device__ inline double load_bound(const unsigned long long* addr)
 {
-    return __longlong_as_double((long long)*reinterpret_cast<const volatile unsigned long long*>(addr));
+    const unsigned long long bits = *reinterpret_cast<const volatile unsigned long long*>(addr);
+    double v;
+    memcpy(&v, &bits, sizeof v);
+    return v;
 }
 
 struct CcdOut {
-    unsigned long long* bound; // global earliest TOI (bit pattern), or nullptr
+    unsigned long long* bound; // global earliest FINAL time of impact (bit pattern), or nullptr
     unsigned char* hit;        // per query, or nullptr
     double* toi;               // per query, or nullptr
 };
@@ -175,28 +182,36 @@ __global__ void __launch_bounds__(128)
 
 // ===========================================================================
 // Tight Inclusion
-struct TIQuery {
-    double s[12], e[12]; // the 4 points handed to the root finder at t = 0 / t = 1
-    double tol[3];       // domain tolerances (t, u, v)
-    double err[3];       // floating-point filter per coordinate
-    double ms;           // minimum separation of the current run
-    double co_tol;       // co-domain tolerance (delta)
+constexpr double SMALL_TOI = 1e-6; // tight_inclusion_ccd.hpp:19
+
+struct TIParams { // parameters of one root-finder run
+    double tol[3]; // domain tolerances (t, u, v)
+    double err[3]; // floating-point filter per coordinate
+    double ms;     // minimum separation
+    double co_tol; // co-domain tolerance (delta)
     double tmax;
-    double d0;           // initial distance
+};
+struct TIQuery { // a spilled query (global queue)
+    double s[12], e[12];
+    TIParams P;
     int is_vf;
     int pad;
-    long long src; // index of the originating candidate / query
+    long long src;
+};
+struct TIBox { // dyadic box: [n / 2^k, (n+1) / 2^k] per dimension
+    unsigned tn, un, vn;
+    unsigned char tk, uk, vk, pad;
 };
 struct TIUnit {
     int q;
-    unsigned tn, un, vn; // dyadic numerators
-    unsigned char tk, uk, vk, pad;
+    TIBox b;
 };
 
-__device__ inline double linf3(d3 a) { return fmax(fmax(fabs(a.x), fabs(a.y)), fabs(a.z)); }
-__device__ inline d3 getp(const double* p, int k) { return { p[3 * k], p[3 * k + 1], p[3 * k + 2] }; }
+__host__ __device__ inline double linf3(d3 a) { return fmax(fmax(fabs(a.x), fabs(a.y)), fabs(a.z)); }
+__host__ __device__ inline d3 getp(const double* p, int k) { return { p[3 * k], p[3 * k + 1], p[3 * k + 2] }; }
 
-__device__ inline void ti_tolerances(const double* s, const double* e, int is_vf, double co_tol, double* tol)
+// domain tolerances from the co-domain tolerance: delta / (3 * max edge length of the swept primitive)
+__host__ __device__ inline void ti_tolerances(const double* s, const double* e, int is_vf, double co_tol, double* tol)
 {
     d3 p000, p001, p011, p010, p100, p101, p111, p110;
     const d3 s0 = getp(s, 0), s1 = getp(s, 1), s2 = getp(s, 2), s3 = getp(s, 3);
@@ -215,7 +230,7 @@ __device__ inline void ti_tolerances(const double* s, const double* e, int is_vf
     tol[1] = co_tol / e0l;
     tol[2] = co_tol / e1l;
 }
-__device__ inline void ti_error(const double* s, const double* e, int is_vf, bool using_ms, double* err)
+__host__ __device__ inline void ti_error(const double* s, const double* e, int is_vf, bool using_ms, double* err)
 {
     const double filter = using_ms ? (is_vf ? 7.549516567451064e-15 : 7.105427357601002e-15)
                                    : (is_vf ? 6.661338147750939e-15 : 6.217248937900877e-15);
@@ -226,26 +241,27 @@ __device__ inline void ti_error(const double* s, const double* e, int is_vf, boo
         err[c] = filter * delta * delta * delta;
     }
 }
-// co-domain box of the root function over a (t,u,v) box vs the eps-cube
-__device__ inline bool ti_inclusion(const TIQuery& Q, const double* tt, const double* uu, const double* vv, bool& box_in,
-                                    double* true_tol)
+// co-domain box of the (multilinear) root function over a (t,u,v) box against the eps-cube
+__host__ __device__ inline bool ti_inclusion(const double* s, const double* e, int is_vf, const TIParams& P, const double* tt, const double* uu,
+                                    const double* vv, bool& box_in, double* true_tol)
 {
     box_in = true;
+#pragma unroll
     for (int c = 0; c < 3; c++) {
         double vmin = INFINITY, vmax = -INFINITY;
 #pragma unroll
         for (int a = 0; a < 2; a++) {
             const double t = tt[a];
-            const double p0 = (Q.e[c] - Q.s[c]) * t + Q.s[c];
-            const double p1 = (Q.e[3 + c] - Q.s[3 + c]) * t + Q.s[3 + c];
-            const double p2 = (Q.e[6 + c] - Q.s[6 + c]) * t + Q.s[6 + c];
-            const double p3 = (Q.e[9 + c] - Q.s[9 + c]) * t + Q.s[9 + c];
+            const double p0 = (e[c] - s[c]) * t + s[c];
+            const double p1 = (e[3 + c] - s[3 + c]) * t + s[3 + c];
+            const double p2 = (e[6 + c] - s[6 + c]) * t + s[6 + c];
+            const double p3 = (e[9 + c] - s[9 + c]) * t + s[9 + c];
 #pragma unroll
             for (int b = 0; b < 2; b++)
 #pragma unroll
                 for (int d = 0; d < 2; d++) {
                     double val;
-                    if (Q.is_vf) {
+                    if (is_vf) {
                         const double pt = (p2 - p1) * uu[b] + (p3 - p1) * vv[d] + p1;
                         val = p0 - pt;
                     } else {
@@ -257,7 +273,7 @@ __device__ inline bool ti_inclusion(const TIQuery& Q, const double* tt, const do
                     vmax = fmax(vmax, val);
                 }
         }
-        const double lim = Q.err[c] + Q.ms;
+        const double lim = P.err[c] + P.ms;
         true_tol[c] = vmax - vmin;
         if (vmin > lim || vmax < -lim) return false;
         if (vmin < -lim || vmax > lim) box_in = false;
@@ -265,11 +281,113 @@ __device__ inline bool ti_inclusion(const TIQuery& Q, const double* tt, const do
     return true;
 }
 
+__host__ __device__ inline void box_bounds(const TIBox& b, double* tt, double* uu, double* vv)
+{
+    tt[0] = ldexp(double(b.tn), -int(b.tk)), tt[1] = ldexp(double(b.tn + 1), -int(b.tk));
+    uu[0] = ldexp(double(b.un), -int(b.uk)), uu[1] = ldexp(double(b.un + 1), -int(b.uk));
+    vv[0] = ldexp(double(b.vn), -int(b.vk)), vv[1] = ldexp(double(b.vn + 1), -int(b.vk));
+}
+
+// One subdivision step on a live box.  Returns 0: rejected, 1: terminal (its lower time bound is
+// a time of impact), 2: split into nchild children (earliest first).
+__host__ __device__ inline int ti_step(const double* s, const double* e, int is_vf, const TIParams& P, const TIBox& b, const double* tt,
+                              const double* uu, const double* vv, TIBox* child, int& nchild)
+{
+    bool box_in;
+    double true_tol[3];
+    nchild = 0;
+    if (!ti_inclusion(s, e, is_vf, P, tt, uu, vv, box_in, true_tol)) return 0;
+    const double w[3] = { tt[1] - tt[0], uu[1] - uu[0], vv[1] - vv[0] };
+    const bool tol_cond = true_tol[0] <= P.co_tol && true_tol[1] <= P.co_tol && true_tol[2] <= P.co_tol;
+    const bool cond1 = w[0] <= P.tol[0] && w[1] <= P.tol[1] && w[2] <= P.tol[2];
+    if (cond1 || tol_cond || box_in) return 1;
+    int split = 0;
+    double bestv = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double r = w[k] > P.tol[k] ? w[k] / P.tol[k] : -INFINITY;
+        if (r > bestv) bestv = r, split = k; // first maximum wins
+    }
+    const int kk = split == 0 ? b.tk : (split == 1 ? b.uk : b.vk);
+    if (kk >= 30) return 1; // bisection depth exhausted: stop conservatively
+    TIBox c0 = b, c1 = b;
+    if (split == 0) {
+        c0.tn = 2 * b.tn, c1.tn = 2 * b.tn + 1, c0.tk = c1.tk = b.tk + 1;
+        child[nchild++] = c0; // the first half always overlaps [0, tmax]
+        if (P.tmax == 1.0 || ldexp(double(c1.tn), -int(c1.tk)) <= P.tmax) child[nchild++] = c1;
+    } else if (split == 1) {
+        c0.un = 2 * b.un, c1.un = 2 * b.un + 1, c0.uk = c1.uk = b.uk + 1;
+        child[nchild++] = c0;
+        if (!is_vf || ldexp(double(c1.un), -int(c1.uk)) + vv[0] <= 1.0) child[nchild++] = c1; // u + v <= 1
+    } else {
+        c0.vn = 2 * b.vn, c1.vn = 2 * b.vn + 1, c0.vk = c1.vk = b.vk + 1;
+        child[nchild++] = c0;
+        if (!is_vf || ldexp(double(c1.vn), -int(c1.vk)) + uu[0] <= 1.0) child[nchild++] = c1;
+    }
+    return 2;
+}
+
+// Level-0 culling, consistent with the root finder: returns true when NO box inside
+// [0,tmax] x [0,1]^2 can ever be reported.
+//  (1) the co-domain box of the root clipped to the search window misses the eps-cube (every
+//      sub-box's co-domain box is contained in it);
+//  (2) a separating direction n: n.F is multilinear in (t,u,v), so it is bounded by its 8 corner
+//      values; if all of them exceed ||n||_1 (ms + err + delta) in magnitude with one sign, no
+//      point of the window has |F_c| <= ms + err_c + delta for all c, and a terminal box (co-domain
+//      width <= delta, or inside the cube) cannot exist.
+__host__ __device__ inline bool ti_cull(const double* s, const double* e, int is_vf, const TIParams& P, double tmax)
+{
+    const double tt[2] = { 0.0, tmax }, unit[2] = { 0.0, 1.0 };
+    bool box_in;
+    double tw[3];
+    if (!ti_inclusion(s, e, is_vf, P, tt, unit, unit, box_in, tw)) return true;
+    // corner values of F at t = 0 and t = tmax
+    d3 Fc[8];
+    d3 p0[4], p1[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        p0[k] = getp(s, k);
+        const d3 ek = getp(e, k);
+        p1[k] = { (ek.x - p0[k].x) * tmax + p0[k].x, (ek.y - p0[k].y) * tmax + p0[k].y, (ek.z - p0[k].z) * tmax + p0[k].z };
+    }
+    if (is_vf) { // p - {t0, t1, t2, t1 + t2 - t0}: the root finder's (u,v) domain is the parallelogram
+        Fc[0] = p0[0] - p0[1], Fc[1] = p0[0] - p0[2], Fc[2] = p0[0] - p0[3], Fc[3] = p0[0] - (p0[2] + p0[3] - p0[1]);
+        Fc[4] = p1[0] - p1[1], Fc[5] = p1[0] - p1[2], Fc[6] = p1[0] - p1[3], Fc[7] = p1[0] - (p1[2] + p1[3] - p1[1]);
+    } else {
+        Fc[0] = p0[0] - p0[2], Fc[1] = p0[0] - p0[3], Fc[2] = p0[1] - p0[2], Fc[3] = p0[1] - p0[3];
+        Fc[4] = p1[0] - p1[2], Fc[5] = p1[0] - p1[3], Fc[6] = p1[1] - p1[2], Fc[7] = p1[1] - p1[3];
+    }
+    const double margin = (fmax(fmax(P.err[0], P.err[1]), P.err[2]) + P.ms + P.co_tol) * (1.0 + 1e-9);
+    d3 axes[4];
+    int na;
+    if (is_vf) {
+        const d3 n = cross(p0[2] - p0[1], p0[3] - p0[1]);
+        axes[0] = n, axes[1] = cross(p0[2] - p0[1], n), axes[2] = cross(p0[3] - p0[2], n), axes[3] = cross(p0[1] - p0[3], n);
+        na = 4;
+    } else {
+        const d3 ua = p0[1] - p0[0], ub = p0[3] - p0[2], n = cross(ua, ub);
+        axes[0] = n, axes[1] = cross(ua, n), axes[2] = cross(ub, n);
+        na = 3;
+    }
+    for (int a = 0; a < na; a++) {
+        const d3 n = axes[a];
+        const double l1 = (fabs(n.x) + fabs(n.y) + fabs(n.z)) * margin;
+        double mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const double v = dot(n, Fc[k]);
+            mn = fmin(mn, v), mx = fmax(mx, v);
+        }
+        if (mn > l1 || mx < -l1) return true;
+    }
+    return false;
+}
+
 struct TIQueue {
     TIQuery* queries;
-    unsigned long long* qtoi; // per query earliest terminal t (bit pattern), +inf when none
-    int* qflags;              // per query: bit0 = excluded from the global bound
-    unsigned long long* nq;   // survivor counter
+    unsigned long long* qtoi; // per spilled query: earliest terminal t so far (bit pattern)
+    int* qflags;              // bit1: in the no-zero-toi refinement; bit2: finished
+    unsigned long long* nq;
     unsigned long long qcap;
     TIUnit* in;
     TIUnit* outq;
@@ -277,14 +395,44 @@ struct TIQueue {
     unsigned long long ucap;
 };
 
-// warp-aggregated slot reservation
+constexpr int DFS_STACK = 96;
+
+// Earliest-first depth-first refinement in registers.  Returns true when the search finished;
+// false when the unit budget was exhausted (stack[0..sp) then holds the unexplored boxes).
+__host__ __device__ inline bool ti_dfs(const double* s, const double* e, int is_vf, TIParams& P, const unsigned long long* bound, int budget,
+                              TIBox* stack, int& sp, double& best)
+{
+    int iter = 0;
+    while (sp > 0) {
+        const TIBox b = stack[--sp];
+        double tt[2], uu[2], vv[2];
+        box_bounds(b, tt, uu, vv);
+        if (tt[0] >= best) continue; // TOI_SKIP pruning of the sequential search
+        if (bound && (iter & 3) == 0) P.tmax = fmin(P.tmax, load_bound(bound));
+        if (tt[0] > P.tmax) continue;
+        if (++iter > budget || sp + 2 > DFS_STACK) {
+            stack[sp++] = b;
+            return false;
+        }
+        TIBox child[2];
+        int nchild;
+        const int r = ti_step(s, e, is_vf, P, b, tt, uu, vv, child, nchild);
+        if (r == 1) best = fmin(best, tt[0]);
+        else if (r == 2) {
+            if (nchild == 2) stack[sp++] = child[1];
+            stack[sp++] = child[0]; // earliest / first half on top
+        }
+    }
+    return true;
+}
+
+// warp-aggregated slot reservation (count slots per wanting lane)
 __device__ inline unsigned long long warp_reserve(unsigned long long* counter, bool want, int count)
 {
     const unsigned m = __ballot_sync(0xffffffffu, want);
     if (m == 0) return 0;
     const int lane = threadIdx.x & 31;
-    // every wanting lane asks for `count` slots (count is 1 or 2); prefix over lanes
-    int mine = want ? count : 0;
+    const int mine = want ? count : 0;
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -298,13 +446,19 @@ __device__ inline unsigned long long warp_reserve(unsigned long long* counter, b
     return base + (incl - mine);
 }
 
-// level 0 (tight_inclusion_ccd.cpp:222-336 + ccd_strategy :33-58 up to the first root-finder call)
+// tight_inclusion_ccd.cpp:222-336 + ccd_strategy :33-75, one thread per query
 __global__ void __launch_bounds__(128)
-    k_ti_level0(QuerySource q, double min_distance, double tmax, double tolerance, double rescale, TIQueue Z, CcdOut out)
+    k_ti_query(QuerySource q, double min_distance, double tmax_in, double tolerance, double rescale, int budget, TIQueue Z, CcdOut out)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    bool survive = false;
-    TIQuery Q;
+    bool spill = false;
+    double s[12], e[12];
+    TIParams P;
+    TIBox stack[DFS_STACK];
+    int sp = 0;
+    int is_vf = 0;
+    int spill_flags = 0;
+    double best = INFINITY;
     if (i < q.n) {
         d3 a[4], b[4];
         const int n = load_query(q, i, a, b);
@@ -325,192 +479,172 @@ __global__ void __launch_bounds__(128)
                 s4[0] = s4[1] = a[0], s4[2] = a[1], s4[3] = a[2];
                 e4[0] = e4[1] = b[0], e4[2] = b[1], e4[3] = b[2];
             } else {
+#pragma unroll
                 for (int k = 0; k < 4; k++) s4[k] = a[k], e4[k] = b[k];
             }
+#pragma unroll
             for (int k = 0; k < 4; k++) {
-                Q.s[3 * k] = s4[k].x, Q.s[3 * k + 1] = s4[k].y, Q.s[3 * k + 2] = s4[k].z;
-                Q.e[3 * k] = e4[k].x, Q.e[3 * k + 1] = e4[k].y, Q.e[3 * k + 2] = e4[k].z;
+                s[3 * k] = s4[k].x, s[3 * k + 1] = s4[k].y, s[3 * k + 2] = s4[k].z;
+                e[3 * k] = e4[k].x, e[3 * k + 1] = e4[k].y, e[3 * k + 2] = e4[k].z;
             }
-            Q.is_vf = q.kind == IPCB_FV;
-            Q.d0 = d0;
-            Q.tmax = tmax;
-            Q.src = i;
-            Q.pad = 0;
-            double med = (1.0 - rescale) * (d0 - min_distance); // min effective distance (:45-49)
+            is_vf = q.kind == IPCB_FV;
+            // the search window is fixed when the query starts, like `tmax = earliest_toi.load()` (candidates.cpp:270)
+            const double tmax0 = out.bound ? fmin(tmax_in, load_bound(out.bound)) : tmax_in;
+            double med = (1.0 - rescale) * (d0 - min_distance); // minimum effective distance (:45-49)
             med = fmin(med, 1e-4);
             med += min_distance;
-            Q.ms = med;
-            Q.co_tol = fmin(0.5 * d0, tolerance); // adjusted tolerance (:245-246)
-            ti_tolerances(Q.s, Q.e, Q.is_vf, Q.co_tol, Q.tol);
-            ti_error(Q.s, Q.e, Q.is_vf, Q.ms > 0, Q.err);
-            const double unit[2] = { 0.0, 1.0 };
-            bool box_in;
-            double tt[3];
-            survive = ti_inclusion(Q, unit, unit, unit, box_in, tt);
-            if (!survive) report(out, i, false, 0.0);
+            P.ms = med;
+            P.co_tol = fmin(0.5 * d0, tolerance); // adjusted tolerance (:245-246)
+            P.tmax = tmax0;
+            ti_tolerances(s, e, is_vf, P.co_tol, P.tol);
+            ti_error(s, e, is_vf, P.ms > 0, P.err);
+            // ---- first query: minimum effective distance, no_zero_toi = false
+            bool done = true;
+            if (!ti_cull(s, e, is_vf, P, tmax0)) {
+                stack[0] = TIBox { 0, 0, 0, 0, 0, 0, 0 };
+                sp = 1;
+                done = ti_dfs(s, e, is_vf, P, out.bound, budget, stack, sp, best);
+            }
+            if (!done) {
+                spill = true;
+            } else if (best < SMALL_TOI) {
+                // ---- second query: ms = min_distance, no_zero_toi = true, shrinking until toi != 0
+                P.ms = min_distance;
+                P.tmax = tmax0;
+                ti_error(s, e, is_vf, P.ms > 0, P.err);
+                for (int round = 0; round < 200; round++) {
+                    best = INFINITY;
+                    stack[0] = TIBox { 0, 0, 0, 0, 0, 0, 0 };
+                    sp = 1;
+                    done = ti_dfs(s, e, is_vf, P, nullptr, budget, stack, sp, best);
+                    if (!done) {
+                        spill = true;
+                        spill_flags = 2;
+                        break;
+                    }
+                    if (best == 0.0 && P.co_tol > 1e-300) {
+                        if (10 * P.co_tol < P.ms) {
+                            P.ms *= 0.5;
+                        } else {
+                            P.co_tol *= 0.5;
+                            ti_tolerances(s, e, is_vf, P.co_tol, P.tol);
+                        }
+                    } else {
+                        break;
+                    }
+                }
+                if (!spill) report(out, i, best < INFINITY, best * rescale);
+            } else {
+                report(out, i, best < INFINITY, best);
+            }
         }
     }
-    const unsigned long long slot = warp_reserve(Z.nq, survive, 1);
-    if (survive) {
-        if (slot < Z.qcap) {
-            Z.queries[slot] = Q;
-            Z.qtoi[slot] = 0x7ff0000000000000ull;
-            Z.qflags[slot] = 0;
+    // ---- spill path: hand the unexplored boxes to the global queue
+    const unsigned long long slot = warp_reserve(Z.nq, spill, 1);
+    const bool slot_ok = spill && slot < Z.qcap;
+    const unsigned long long ubase = warp_reserve(Z.nout, slot_ok, sp);
+    if (spill) {
+        if (slot_ok && ubase + sp <= Z.ucap) {
+            TIQuery& Q = Z.queries[slot];
+#pragma unroll
+            for (int k = 0; k < 12; k++) Q.s[k] = s[k], Q.e[k] = e[k];
+            Q.P = P;
+            Q.is_vf = is_vf;
+            Q.pad = 0;
+            Q.src = i;
+            Z.qtoi[slot] = (unsigned long long)__double_as_longlong(best);
+            Z.qflags[slot] = spill_flags;
+            for (int k = 0; k < sp; k++) Z.outq[ubase + k] = TIUnit { int(slot), stack[k] };
         }
-        // slot >= qcap is detected on the host (counter > capacity) and the pass is repeated
+        // a failed reservation is detected on the host (counter > capacity): the pass is repeated with room
     }
 }
 
-// push the root unit of every query whose flags match (need_mask == 0: any) and avoid exclude_mask
-__global__ void k_ti_push_roots(int nq, const int* __restrict__ qflags, int need_mask, int exclude_mask, TIUnit* units,
-                                unsigned long long* count)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool want = i < nq;
-    if (want) {
-        const int f = qflags[i];
-        want = (need_mask == 0 || (f & need_mask)) && !(f & exclude_mask);
-    }
-    const unsigned long long slot = warp_reserve(count, want, 1);
-    if (want) units[slot] = TIUnit { i, 0, 0, 0, 0, 0, 0, 0 };
-}
-
-constexpr double SMALL_TOI = 1e-6;
-
+// one level of the global queue
 __global__ void __launch_bounds__(128)
-    k_ti_level(TIQueue Z, unsigned long long nin, unsigned long long* bound, int use_bound, int force_terminal)
+    k_ti_level(TIQueue Z, unsigned long long nin, const unsigned long long* bound, int force_terminal, int last_attempt)
 {
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     int nchild = 0;
-    TIUnit child[2];
+    TIBox child[2];
+    int qid = 0;
+    double t0 = 0;
     if (i < nin) {
         const TIUnit u = Z.in[i];
+        qid = u.q;
         const TIQuery& Q = Z.queries[u.q];
-        const double tt[2] = { ldexp(double(u.tn), -int(u.tk)), ldexp(double(u.tn + 1), -int(u.tk)) };
-        const double uu[2] = { ldexp(double(u.un), -int(u.uk)), ldexp(double(u.un + 1), -int(u.uk)) };
-        const double vv[2] = { ldexp(double(u.vn), -int(u.vk)), ldexp(double(u.vn + 1), -int(u.vk)) };
+        double tt[2], uu[2], vv[2];
+        box_bounds(u.b, tt, uu, vv);
+        t0 = tt[0];
         const double best_q = __longlong_as_double((long long)*reinterpret_cast<volatile unsigned long long*>(Z.qtoi + u.q));
-        bool live = tt[0] < best_q; // TOI_SKIP pruning of the sequential search
-        if (live && use_bound && !(Z.qflags[u.q] & 1)) live = tt[0] < load_bound(bound);
+        bool live = tt[0] < best_q && tt[0] <= Q.P.tmax;
+        // first-query units may also use the fresher global bound; refinement units keep their window
+        if (live && bound && !(Z.qflags[u.q] & 2)) live = tt[0] <= load_bound(bound);
         if (live) {
-            bool box_in;
-            double true_tol[3];
-            if (ti_inclusion(Q, tt, uu, vv, box_in, true_tol)) {
-                const double w[3] = { tt[1] - tt[0], uu[1] - uu[0], vv[1] - vv[0] };
-                const bool tol_cond = true_tol[0] <= Q.co_tol && true_tol[1] <= Q.co_tol && true_tol[2] <= Q.co_tol;
-                const bool cond1 = w[0] <= Q.tol[0] && w[1] <= Q.tol[1] && w[2] <= Q.tol[2];
-                bool terminal = cond1 || tol_cond || box_in || force_terminal;
-                int split = 0;
-                if (!terminal) {
-                    double bestv = -INFINITY;
-                    for (int k = 0; k < 3; k++) {
-                        const double r = w[k] > Q.tol[k] ? w[k] / Q.tol[k] : -INFINITY;
-                        if (r > bestv) bestv = r, split = k;
-                    }
-                    const int kk = split == 0 ? u.tk : (split == 1 ? u.uk : u.vk);
-                    if (kk >= 30) terminal = true; // bisection depth exhausted: stop conservatively
-                }
-                if (terminal) {
-                    atomic_min_double(Z.qtoi + u.q, tt[0]);
-                    if (use_bound && !(Z.qflags[u.q] & 1) && tt[0] >= SMALL_TOI) atomic_min_double(bound, tt[0]);
-                } else {
-                    TIUnit c0 = u, c1 = u;
-                    if (split == 0) {
-                        c0.tn = 2 * u.tn, c1.tn = 2 * u.tn + 1, c0.tk = c1.tk = u.tk + 1;
-                        child[nchild++] = c0; // first half always overlaps [0, tmax]
-                        const double mid = ldexp(double(c1.tn), -int(c1.tk));
-                        if (Q.tmax == 1.0 || mid <= Q.tmax) child[nchild++] = c1;
-                    } else if (split == 1) {
-                        c0.un = 2 * u.un, c1.un = 2 * u.un + 1, c0.uk = c1.uk = u.uk + 1;
-                        child[nchild++] = c0;
-                        const double mid = ldexp(double(c1.un), -int(c1.uk));
-                        if (!Q.is_vf || mid + vv[0] <= 1.0) child[nchild++] = c1; // u + v <= 1
-                    } else {
-                        c0.vn = 2 * u.vn, c1.vn = 2 * u.vn + 1, c0.vk = c1.vk = u.vk + 1;
-                        child[nchild++] = c0;
-                        const double mid = ldexp(double(c1.vn), -int(c1.vk));
-                        if (!Q.is_vf || mid + uu[0] <= 1.0) child[nchild++] = c1;
-                    }
-                    // (the first half satisfies u + v <= 1 whenever its parent did)
-                }
-            }
+            int r = ti_step(Q.s, Q.e, Q.is_vf, Q.P, u.b, tt, uu, vv, child, nchild);
+            if (r == 2 && force_terminal) r = 1, nchild = 0;
+            if (r == 1) atomic_min_double(Z.qtoi + u.q, tt[0]);
         }
     }
     const unsigned long long slot = warp_reserve(Z.nout, nchild > 0, nchild);
     if (nchild > 0) {
         if (slot + nchild <= Z.ucap) {
-            for (int k = 0; k < nchild; k++) Z.outq[slot + k] = child[k];
-        } else {
-            // queue full: stop refining this box conservatively (its lower time bound is a valid TOI)
-            const TIUnit u = Z.in[i];
-            const double t0 = ldexp(double(u.tn), -int(u.tk));
-            atomic_min_double(Z.qtoi + u.q, t0);
+            for (int k = 0; k < nchild; k++) Z.outq[slot + k] = TIUnit { qid, child[k] };
+        } else if (last_attempt) {
+            atomic_min_double(Z.qtoi + qid, t0); // queue still full after growing: stop refining this box conservatively
         }
+        // otherwise the host grows the queue and runs this level again (nothing may be recorded here)
     }
 }
 
-// after a run: classify queries. mode 0 (after phase 1): flag queries with toi < SMALL_TOI for the
-// no-zero-toi refinement (bit 1 = active, bit 0 = excluded from bound) and set their refinement
-// parameters; others report.  mode 1 (refinement round): queries with toi == 0 shrink ms / tolerance
-// and stay active; the rest report toi * rescale (tight_inclusion_ccd.cpp:59-72 and the ticcd
-// no_zero_toi loop).
-__global__ void k_ti_finalize(int nq, TIQueue Z, int mode, double min_distance, double rescale, CcdOut out, unsigned long long* nactive)
+// after the queue drained: queries of the first run with toi < SMALL_TOI enter the refinement (flags
+// bit1) with ms = min_distance; refinement queries with toi == 0 shrink ms / tolerance and stay
+// active; everything else reports its final time of impact.
+__global__ void k_ti_finalize(int nq, TIQueue Z, double min_distance, double rescale, CcdOut out, unsigned long long* nactive)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
+    const int flags = Z.qflags[i];
+    if (flags & 4) return;
     TIQuery& Q = Z.queries[i];
     const double toi = __longlong_as_double((long long)Z.qtoi[i]);
     const bool hit = toi < INFINITY;
-    int flags = Z.qflags[i];
-    if (mode == 0) {
-        if (flags & 4) return; // already finished in an earlier pass
+    if (!(flags & 2)) {
         if (hit && toi < SMALL_TOI) {
-            Q.ms = min_distance;
-            ti_error(Q.s, Q.e, Q.is_vf, Q.ms > 0, Q.err);
+            Q.P.ms = min_distance;
+            ti_error(Q.s, Q.e, Q.is_vf, Q.P.ms > 0, Q.P.err);
             Z.qtoi[i] = 0x7ff0000000000000ull;
-            Z.qflags[i] = 1 | 2;
+            Z.qflags[i] = 2;
             atomicAdd(nactive, 1ull);
         } else {
             report(out, Q.src, hit, toi);
-            Z.qflags[i] = flags | 4;
+            Z.qflags[i] = 4;
         }
     } else {
-        if (!(flags & 2)) return;
-        if (hit && toi == 0.0 && Q.co_tol > 1e-300) {
-            if (10 * Q.co_tol < Q.ms) {
-                Q.ms *= 0.5;
+        if (hit && toi == 0.0 && Q.P.co_tol > 1e-300) {
+            if (10 * Q.P.co_tol < Q.P.ms) {
+                Q.P.ms *= 0.5;
             } else {
-                Q.co_tol *= 0.5;
-                ti_tolerances(Q.s, Q.e, Q.is_vf, Q.co_tol, Q.tol);
+                Q.P.co_tol *= 0.5;
+                ti_tolerances(Q.s, Q.e, Q.is_vf, Q.P.co_tol, Q.P.tol);
             }
             Z.qtoi[i] = 0x7ff0000000000000ull;
             atomicAdd(nactive, 1ull);
         } else {
             report(out, Q.src, hit, toi * rescale);
-            Z.qflags[i] = (flags & ~2) | 4;
+            Z.qflags[i] = 4;
         }
     }
 }
-
-// redo pass: forget the phase-1 result of every non-refined query
-__global__ void k_ti_reset(int nq, const int* __restrict__ qflags, unsigned long long* qtoi)
+// root units for the queries that (re)start a refinement round
+__global__ void k_ti_push_roots(int nq, const int* __restrict__ qflags, TIUnit* units, unsigned long long* count)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nq && !(qflags[i] & 1)) qtoi[i] = 0x7ff0000000000000ull;
+    const bool want = i < nq && (qflags[i] & 2) && !(qflags[i] & 4);
+    const unsigned long long slot = warp_reserve(count, want, 1);
+    if (want) units[slot] = TIUnit { i, TIBox { 0, 0, 0, 0, 0, 0, 0 } };
 }
-__global__ void k_ti_report_plain(int nq, TIQueue Z, CcdOut out)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq || (Z.qflags[i] & 1)) return;
-    const double toi = __longlong_as_double((long long)Z.qtoi[i]);
-    report(out, Z.queries[i].src, toi < INFINITY, toi);
-}
-__global__ void k_set_bits(unsigned long long* dst, const unsigned long long* src, double cap)
-{
-    // dst = min(*src, cap) as a non-negative double bit pattern
-    const double v = src ? fmin(__longlong_as_double((long long)*src), cap) : cap;
-    *dst = (unsigned long long)__double_as_longlong(v);
-}
+__global__ void k_set_bits(unsigned long long* dst, double v) { *dst = (unsigned long long)__double_as_longlong(v); }
 
 struct TIWork {
     Buf<TIQuery> queries;
@@ -526,37 +660,45 @@ static unsigned long long read_counter(ipcb_ctx* ctx, const unsigned long long* 
     IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
     return (unsigned long long)ctx->pinned.p[0];
 }
-static double bits_to_double(unsigned long long b)
-{
-    double d;
-    memcpy(&d, &b, sizeof d);
-    return d;
-}
 
-// run the queue to exhaustion starting from `nunits` units in W.ua
-static void ti_run_levels(ipcb_ctx* ctx, TIWork& W, TIQueue Z, unsigned long long nunits, unsigned long long* prune)
+// drain the global queue: `nunits` units are in W.ua.  When a level produces more children than the
+// output buffer holds, the buffer is grown and the level is simply run again (a level only reads its
+// input and does atomicMin on the per-query times, so it is idempotent).
+static void ti_run_levels(ipcb_ctx* ctx, TIWork& W, TIQueue Z, unsigned long long nunits, const unsigned long long* bound)
 {
     cudaStream_t s = ctx->stream;
     unsigned long long* cnt = ctx->dCounters.p + 2;
-    TIUnit* in = W.ua.p;
-    TIUnit* outq = W.ub.p;
+    Buf<TIUnit>* in = &W.ua;
+    Buf<TIUnit>* outq = &W.ub;
     for (int level = 0; nunits > 0; level++) {
-        IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
-        Z.in = in, Z.outq = outq, Z.nout = cnt;
-        k_ti_level<<<grid_for(nunits, 128), 128, 0, s>>>(Z, nunits, prune, prune ? 1 : 0, level >= 100 ? 1 : 0);
-        ctx->launches++;
-        IPCB_CUDA(cudaGetLastError());
-        nunits = std::min(read_counter(ctx, cnt), Z.ucap);
+        for (int attempt = 0;; attempt++) {
+            IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
+            Z.in = in->p, Z.outq = outq->p, Z.nout = cnt, Z.ucap = outq->cap;
+            k_ti_level<<<grid_for(nunits, 128), 128, 0, s>>>(Z, nunits, bound, level >= 120 ? 1 : 0, attempt >= 3 ? 1 : 0);
+            ctx->launches++;
+            IPCB_CUDA(cudaGetLastError());
+            const unsigned long long produced = read_counter(ctx, cnt);
+            if (produced <= outq->cap || attempt >= 3) {
+                nunits = std::min<unsigned long long>(produced, outq->cap);
+                break;
+            }
+            outq->reserve(size_t(produced) + size_t(produced) / 2); // contents need not be preserved
+        }
         std::swap(in, outq);
     }
 }
 
-// Tight-Inclusion CCD over one query source.  out.bound != nullptr selects step-size mode: *out.bound
-// only ever receives FINAL times of impact; a separate pruning bound (seeded from it) is tightened
-// by phase-1 terminal boxes.  Because a query that is later refined (toi < SMALL_TOI) may have
-// tightened the pruning bound with a non-final value, the result is accepted only if it is <= the
-// final pruning bound; otherwise the non-refined queries are searched once more against the (valid)
-// result itself.
+static int g_budget = 0;
+static int dfs_budget()
+{
+    if (g_budget == 0) {
+        const char* e = getenv("IPCB_TI_BUDGET"); // in-register units per query before spilling to the global queue
+        g_budget = e ? std::max(1, atoi(e)) : 2048;
+    }
+    return g_budget;
+}
+
+// Tight-Inclusion CCD over one query source
 static void ti_run(ipcb_ctx* ctx, const QuerySource& src, double min_distance, double tmax, const ipcb_ccd_params& p, CcdOut out)
 {
     if (src.n == 0) return;
@@ -567,64 +709,40 @@ static void ti_run(ipcb_ctx* ctx, const QuerySource& src, double min_distance, d
     unsigned long long* nq_d = ctx->dCounters.p + 1;
     unsigned long long* cnt = ctx->dCounters.p + 2;
     unsigned long long* nactive_d = ctx->dCounters.p + 3;
-    unsigned long long* prune_d = ctx->dCounters.p + 4;
-    const bool step_mode = out.bound != nullptr;
-    size_t qcap = std::max<size_t>(W.queries.cap, std::max<size_t>(4096, size_t(src.n) / 16));
-    unsigned long long nq = 0;
+    size_t qcap = std::max<size_t>(W.queries.cap, 1024);
+    size_t ucap = std::max<size_t>(W.ua.cap, size_t(1) << 16);
+    unsigned long long nq = 0, nunits = 0;
     for (int attempt = 0;; attempt++) {
         W.queries.reserve(qcap), W.qtoi.reserve(qcap), W.qflags.reserve(qcap);
+        W.ua.reserve(ucap), W.ub.reserve(ucap);
         qcap = std::min(W.queries.cap, std::min(W.qtoi.cap, W.qflags.cap));
-        IPCB_CUDA(cudaMemsetAsync(nq_d, 0, sizeof(unsigned long long), s));
-        TIQueue Z0 { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, nullptr, nullptr, 0 };
-        k_ti_level0<<<grid_for(src.n, 128), 128, 0, s>>>(src, min_distance, tmax, p.tolerance, p.conservative_rescaling, Z0, out);
+        ucap = std::min(W.ua.cap, W.ub.cap);
+        IPCB_CUDA(cudaMemsetAsync(nq_d, 0, 2 * sizeof(unsigned long long), s)); // nq and the unit counter
+        TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, W.ua.p, cnt, (unsigned long long)ucap };
+        k_ti_query<<<grid_for(src.n, 128), 128, 0, s>>>(src, min_distance, tmax, p.tolerance, p.conservative_rescaling, dfs_budget(), Z, out);
         ctx->launches++;
         IPCB_CUDA(cudaGetLastError());
         nq = read_counter(ctx, nq_d);
-        if (nq <= qcap) break;
-        if (attempt > 2) throw Error("ccd: query buffer overflow persisted");
-        qcap = nq + nq / 8; // level-0 reports are idempotent, so the pass can simply be repeated with room
+        nunits = read_counter(ctx, cnt);
+        if (nq <= qcap && nunits <= ucap) break;
+        if (attempt > 3) throw Error("ccd: spill buffers overflow persisted");
+        // reports are idempotent (atomicMin / identical values), so the pass can simply be repeated with room
+        qcap = std::max<size_t>(qcap, nq + nq / 4);
+        ucap = std::max<size_t>(ucap, size_t(DFS_STACK) * (nq + nq / 4));
     }
     if (nq == 0) return;
-    const size_t want_u = std::max<size_t>(W.ua.cap, std::max<size_t>(1 << 16, 8 * size_t(nq)));
-    W.ua.reserve(want_u), W.ub.reserve(want_u);
-    TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, nullptr, nullptr,
-                (unsigned long long)std::min(W.ua.cap, W.ub.cap) };
-    auto push_roots = [&](int need_mask, int exclude_mask) {
-        IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
-        k_ti_push_roots<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), W.qflags.p, need_mask, exclude_mask, W.ua.p, cnt);
-        ctx->launches++;
-        return read_counter(ctx, cnt);
-    };
-    // ---- phase 1: minimum effective distance, no_zero_toi = false (tight_inclusion_ccd.cpp:45-52)
-    if (step_mode) {
-        k_set_bits<<<1, 1, 0, s>>>(prune_d, out.bound, tmax);
-        ctx->launches++;
-    }
-    ti_run_levels(ctx, W, Z, push_roots(0, 0), step_mode ? prune_d : nullptr);
-    IPCB_CUDA(cudaMemsetAsync(nactive_d, 0, sizeof(unsigned long long), s));
-    k_ti_finalize<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), Z, 0, min_distance, p.conservative_rescaling, out, nactive_d);
-    ctx->launches++;
-    unsigned long long nactive = read_counter(ctx, nactive_d);
-    const bool refined = nactive > 0;
-    // ---- phase 2: no-zero-toi refinement rounds (ms = min_distance; :59-72 + ticcd's shrink loop)
-    for (int round = 0; nactive > 0 && round < 100; round++) {
-        ti_run_levels(ctx, W, Z, push_roots(2, 0), nullptr);
+    // ---- spilled queries: global interval-subdivision queue
+    TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, nullptr, nullptr, (unsigned long long)ucap };
+    ti_run_levels(ctx, W, Z, nunits, out.bound);
+    for (int round = 0; round < 250; round++) {
         IPCB_CUDA(cudaMemsetAsync(nactive_d, 0, sizeof(unsigned long long), s));
-        k_ti_finalize<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), Z, 1, min_distance, p.conservative_rescaling, out, nactive_d);
+        k_ti_finalize<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), Z, min_distance, p.conservative_rescaling, out, nactive_d);
         ctx->launches++;
-        nactive = read_counter(ctx, nactive_d);
-    }
-    if (step_mode && refined) {
-        const double result = bits_to_double(read_counter(ctx, out.bound));
-        const double pruned = bits_to_double(read_counter(ctx, prune_d));
-        if (result > pruned) { // pruning bound was tightened by a value that did not stay final
-            k_ti_reset<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), W.qflags.p, W.qtoi.p);
-            k_set_bits<<<1, 1, 0, s>>>(prune_d, out.bound, tmax);
-            ctx->launches += 2;
-            ti_run_levels(ctx, W, Z, push_roots(0, 1), prune_d);
-            k_ti_report_plain<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), Z, out);
-            ctx->launches++;
-        }
+        if (read_counter(ctx, nactive_d) == 0) break;
+        IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
+        k_ti_push_roots<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), W.qflags.p, W.ua.p, cnt);
+        ctx->launches++;
+        ti_run_levels(ctx, W, Z, read_counter(ctx, cnt), nullptr);
     }
 }
 
@@ -653,10 +771,10 @@ void ccd_stepsize(ipcb_ctx* ctx, double min_distance, const ipcb_ccd_params& p, 
     Stage st(ctx, "ccd_narrow");
     cudaStream_t s = ctx->stream;
     unsigned long long* bound = ctx->dCounters.p + 8;
-    k_set_bits<<<1, 1, 0, s>>>(bound, nullptr, 1.0);
+    k_set_bits<<<1, 1, 0, s>>>(bound, 1.0);
     ctx->launches++;
     CcdOut out { bound, nullptr, nullptr };
-    // the cheap kinds first: their hits tighten the bound for the big EE / FV sets
+    // the small kinds first: their hits tighten the bound for the big EE / FV sets
     for (int kind : { IPCB_VV, IPCB_EV, IPCB_FV, IPCB_EE }) run_ccd(ctx, cand_source(ctx, kind), min_distance, 1.0, p, out);
     IPCB_CUDA(cudaMemcpyAsync(d_out, bound, sizeof(double), cudaMemcpyDeviceToDevice, s));
 }

@@ -1,0 +1,272 @@
+// hessian_fast.cuh — PSD-projected local barrier Hessians in an analytic subspace.
+//
+// A squared distance is phi(x) = min_theta |r(x,theta)|^2 with r = sum_i c_i x_i the vector between
+// the closest points (c = barycentric coefficients, summing to zero) and theta the p <= 2 closest-point
+// parameters.  With tau_j = dr/dtheta_j (edge directions) and e_j = d tau_j / dx (a +-1 pattern over
+// the points), implicit differentiation of the minimiser gives
+//
+//     grad phi = 2 c (x) r ,     Hess phi = 2 (c c^T) (x) I3  -  2 A G^-1 A^T ,
+//     a_j = c (x) tau_j + e_j (x) r ,   G_jk = tau_j . tau_k ,
+//
+// so the local matrix  w [ f'' grad grad^T + f' Hess ]  (normal_potential.cpp:196-204) lives in the
+// span of the 3 + p ORTHONORMAL vectors  c^ (x) e_x, c^ (x) e_y, c^ (x) e_z, eps_1 (x) r^, eps_2 (x) r^
+// (eps_j: the e_j made orthonormal and orthogonal to c^).  Projecting the (3+p) x (3+p) coordinate
+// matrix to the PSD cone projects the full 6/9/12-dimensional matrix exactly (project_to_psd,
+// utils/eigen_ext.tpp:56-108), and a 3x3 / 4x4 / 5x5 cyclic Jacobi fits in registers.
+// Edge-edge collisions with an ACTIVE mollifier have extra terms and take the general path.
+#pragma once
+#include "geom.cuh"
+
+namespace ipcb {
+
+// cyclic Jacobi, fully unrolled: A symmetric (upper triangle used), V eigenvectors in columns
+template <int N> __device__ __forceinline__ void jacobi_reg(double (&A)[N][N], double (&V)[N][N])
+{
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < N; j++) V[i][j] = i == j ? 1.0 : 0.0;
+    double tot = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = i; j < N; j++) tot = fma(A[i][j], A[i][j], tot);
+    const double stop = tot * 1e-33;
+#pragma unroll 1
+    for (int sweep = 0; sweep < 30; sweep++) {
+        double off = 0;
+#pragma unroll
+        for (int p = 0; p < N; p++)
+#pragma unroll
+            for (int q = p + 1; q < N; q++) off = fma(A[p][q], A[p][q], off);
+        if (off <= stop) break;
+#pragma unroll
+        for (int p = 0; p < N - 1; p++) {
+#pragma unroll
+            for (int q = p + 1; q < N; q++) {
+                const double apq = A[p][q];
+                if (apq != 0.0) {
+                    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+                    const double c = rsqrt(fma(t, t, 1.0)), s = t * c;
+                    A[p][p] = fma(-t, apq, A[p][p]);
+                    A[q][q] = fma(t, apq, A[q][q]);
+                    A[p][q] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < N; k++) {
+                        if (k != p && k != q) {
+                            double& akp = k < p ? A[k][p] : A[p][k];
+                            double& akq = k < q ? A[k][q] : A[q][k];
+                            const double x = akp, y = akq;
+                            akp = fma(c, x, -s * y);
+                            akq = fma(s, x, c * y);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < N; k++) {
+                        const double x = V[k][p], y = V[k][q];
+                        V[k][p] = fma(c, x, -s * y);
+                        V[k][q] = fma(s, x, c * y);
+                    }
+                }
+            }
+        }
+    }
+}
+
+struct FastGeom {
+    d3 r;         // closest-point vector
+    double cv[4]; // barycentric coefficients over the primitive's points
+    d3 tau[2];    // dr/dtheta_j
+    double ev[2][4];
+    double g11, g12, g22; // G = tau_j . tau_k
+};
+
+// closest-point data of a sub-primitive over points y[0..np)
+__device__ __forceinline__ int fast_geometry(int prim, const d3* y, FastGeom& g)
+{
+#pragma unroll
+    for (int k = 0; k < 4; k++) g.cv[k] = 0, g.ev[0][k] = 0, g.ev[1][k] = 0;
+    g.g11 = g.g22 = 1.0, g.g12 = 0.0;
+    g.tau[0] = g.tau[1] = d3 { 0, 0, 0 };
+    if (prim == 0) { // point - point
+        g.r = y[0] - y[1];
+        g.cv[0] = 1, g.cv[1] = -1;
+        return 0;
+    }
+    if (prim == 1) { // point y0 - line (y1, y2)
+        const d3 tl = y[2] - y[1], q = y[0] - y[1];
+        const double ll = dot(tl, tl), lam = dot(q, tl) / ll;
+        g.r = q - lam * tl;
+        g.cv[0] = 1, g.cv[1] = lam - 1, g.cv[2] = -lam;
+        g.tau[0] = -1.0 * tl;
+        g.ev[0][1] = 1, g.ev[0][2] = -1;
+        g.g11 = ll;
+        return 1;
+    }
+    if (prim == 2) { // point y0 - plane (y1, y2, y3)
+        const d3 ta = y[2] - y[1], tb = y[3] - y[1], q = y[0] - y[1];
+        const double a = dot(ta, ta), b = dot(ta, tb), c = dot(tb, tb), b1 = dot(q, ta), b2 = dot(q, tb);
+        const double det = a * c - b * b;
+        const double la = (c * b1 - b * b2) / det, lb = (a * b2 - b * b1) / det;
+        g.r = q - la * ta - lb * tb;
+        g.cv[0] = 1, g.cv[1] = la + lb - 1, g.cv[2] = -la, g.cv[3] = -lb;
+        g.tau[0] = -1.0 * ta, g.tau[1] = -1.0 * tb;
+        g.ev[0][1] = 1, g.ev[0][2] = -1;
+        g.ev[1][1] = 1, g.ev[1][3] = -1;
+        g.g11 = a, g.g12 = b, g.g22 = c;
+        return 2;
+    }
+    // line (y0, y1) - line (y2, y3)
+    const d3 u = y[1] - y[0], v = y[3] - y[2], w0 = y[0] - y[2];
+    const double a = dot(u, u), b = -dot(u, v), c = dot(v, v), b1 = -dot(w0, u), b2 = dot(w0, v);
+    const double det = a * c - b * b;
+    const double s = (c * b1 - b * b2) / det, t = (a * b2 - b * b1) / det;
+    g.r = w0 + s * u - t * v;
+    g.cv[0] = 1 - s, g.cv[1] = s, g.cv[2] = -(1 - t), g.cv[3] = -t;
+    g.tau[0] = u, g.tau[1] = -1.0 * v;
+    g.ev[0][0] = -1, g.ev[0][1] = 1;
+    g.ev[1][2] = 1, g.ev[1][3] = -1;
+    g.g11 = a, g.g12 = b, g.g22 = c;
+    return 2;
+}
+
+// Projected local matrix for a primitive with P parameters over np points.
+// emit(a, b, blk) receives every 3x3 block (row-major) for a,b < np.
+template <int P, typename Emit>
+__device__ __forceinline__ void fast_projected_blocks(const FastGeom& g, int np, double wf1, double wf2, int mode, const Emit& emit)
+{
+    constexpr int N = 3 + P;
+    const d3 r = g.r;
+    const double d = sqrt(dot(r, r));
+    const d3 rh = { r.x / d, r.y / d, r.z / d };
+    double cn2 = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) cn2 = fma(g.cv[k], g.cv[k], cn2);
+    const double cn = sqrt(cn2);
+    double ch[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) ch[k] = g.cv[k] / cn;
+    // orthonormal eps_j (orthogonal to ch) and the coordinates of a_j
+    double eps[2][4];
+    double tvec[2][3], bvec[2][2];
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) eps[j][k] = 0;
+        tvec[j][0] = tvec[j][1] = tvec[j][2] = 0, bvec[j][0] = bvec[j][1] = 0;
+    }
+    if (P >= 1) {
+        double al = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) al = fma(g.ev[0][k], ch[k], al);
+        double nn = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            eps[0][k] = g.ev[0][k] - al * ch[k];
+            nn = fma(eps[0][k], eps[0][k], nn);
+        }
+        const double n1 = sqrt(nn);
+#pragma unroll
+        for (int k = 0; k < 4; k++) eps[0][k] /= n1;
+        tvec[0][0] = fma(cn, g.tau[0].x, al * r.x), tvec[0][1] = fma(cn, g.tau[0].y, al * r.y), tvec[0][2] = fma(cn, g.tau[0].z, al * r.z);
+        bvec[0][0] = d * n1;
+    }
+    if (P >= 2) {
+        double al = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) al = fma(g.ev[1][k], ch[k], al);
+        double w2[4], beta = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            w2[k] = g.ev[1][k] - al * ch[k];
+            beta = fma(w2[k], eps[0][k], beta);
+        }
+        double nn = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            w2[k] -= beta * eps[0][k];
+            nn = fma(w2[k], w2[k], nn);
+        }
+        const double gam = sqrt(nn);
+#pragma unroll
+        for (int k = 0; k < 4; k++) eps[1][k] = w2[k] / gam;
+        tvec[1][0] = fma(cn, g.tau[1].x, al * r.x), tvec[1][1] = fma(cn, g.tau[1].y, al * r.y), tvec[1][2] = fma(cn, g.tau[1].z, al * r.z);
+        bvec[1][0] = d * beta, bvec[1][1] = d * gam;
+    }
+    // G^-1
+    double gi[2][2] = { { 0, 0 }, { 0, 0 } };
+    if (P == 1) gi[0][0] = 1.0 / g.g11;
+    if (P == 2) {
+        const double det = g.g11 * g.g22 - g.g12 * g.g12;
+        gi[0][0] = g.g22 / det, gi[1][1] = g.g11 / det, gi[0][1] = gi[1][0] = -g.g12 / det;
+    }
+    // coordinate matrix M = 4 w f'' cn^2 [r;0][r;0]^T + 2 w f' cn^2 diag(I3, 0) - 2 w f' A~ G^-1 A~^T
+    double M[N][N], V[N][N];
+    const double rr[3] = { r.x, r.y, r.z };
+    double at[2][N]; // a~_j
+#pragma unroll
+    for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int i = 0; i < N; i++) at[j][i] = i < 3 ? tvec[j][i] : bvec[j][i - 3];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = i; j < N; j++) {
+            double v = 0;
+            if (i < 3 && j < 3) v = 4.0 * wf2 * cn2 * rr[i] * rr[j] + (i == j ? 2.0 * wf1 * cn2 : 0.0);
+            double k2 = 0;
+#pragma unroll
+            for (int a = 0; a < P; a++)
+#pragma unroll
+                for (int b = 0; b < P; b++) k2 = fma(gi[a][b] * at[a][i], at[b][j], k2);
+            M[i][j] = v - 2.0 * wf1 * k2;
+        }
+    jacobi_reg<N>(M, V);
+    double lam[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        lam[i] = M[i][i];
+        if (lam[i] < 0.0) lam[i] = mode == IPCB_PSD_CLAMP ? 0.0 : -lam[i];
+    }
+    // M+ = V diag(lam) V^T
+    double Mp[N][N];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = i; j < N; j++) {
+            double acc = 0;
+#pragma unroll
+            for (int k = 0; k < N; k++) acc = fma(V[i][k] * lam[k], V[j][k], acc);
+            Mp[i][j] = Mp[j][i] = acc;
+        }
+    // expand: block(a,b) = ch_a ch_b Mp_TT + ch_a u_b r^T-like terms (see header)
+    const double rhv[3] = { rh.x, rh.y, rh.z };
+    for (int a = 0; a < np; a++) {
+        double ua[3] = { 0, 0, 0 };
+#pragma unroll
+        for (int k = 0; k < P; k++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) ua[c] = fma(eps[k][a], Mp[3 + k][c], ua[c]);
+        for (int b = 0; b < np; b++) {
+            double ub[3] = { 0, 0, 0 }, sab = 0;
+#pragma unroll
+            for (int k = 0; k < P; k++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) ub[c] = fma(eps[k][b], Mp[c][3 + k], ub[c]);
+#pragma unroll
+                for (int l = 0; l < P; l++) sab = fma(eps[k][a] * eps[l][b], Mp[3 + k][3 + l], sab);
+            }
+            const double cab = ch[a] * ch[b];
+            double blk[9];
+#pragma unroll
+            for (int rr_ = 0; rr_ < 3; rr_++)
+#pragma unroll
+                for (int c = 0; c < 3; c++)
+                    blk[3 * rr_ + c] = cab * Mp[rr_][c] + ch[a] * ub[rr_] * rhv[c] + ch[b] * rhv[rr_] * ua[c] + sab * rhv[rr_] * rhv[c];
+            emit(a, b, blk);
+        }
+    }
+}
+
+} // namespace ipcb

@@ -25,6 +25,7 @@
 //    exactly non-zero value there (duplicates summed, never pruned).
 #include "ctx.cuh"
 #include "geom.cuh"
+#include "hessian_fast.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -267,8 +268,10 @@ template <int NR> __device__ inline void jacobi(double* A, double* V)
     }
 }
 
-// H: NP x NP blocks (stride 4 blocks per block-row, 9 doubles per block, row-major)
-template <int NP> __device__ inline void project_psd(double* H, int mode)
+// H: 4 x 4 blocks (9 doubles per block, row-major); the projection acts on the NP stencil points
+// pt[0..NP) that the local matrix really involves — all other rows / columns are exactly zero and
+// must stay exactly zero (they are not entries of the reference's sparse matrix)
+template <int NP> __device__ inline void project_psd(double* H, int mode, const int* pt)
 {
     constexpr int M = NP - 1, NR = 3 * M;
     double S[NR * NR], V[NR * NR];
@@ -282,7 +285,7 @@ template <int NP> __device__ inline void project_psd(double* H, int mode)
                         const double hia = Helmert<NP>::at(i, a);
                         if (hia == 0.0) continue;
                         double row = 0;
-                        for (int j = 0; j < NP; j++) row = fma(Helmert<NP>::at(j, b), H[(i * 4 + j) * 9 + 3 * r + c], row);
+                        for (int j = 0; j < NP; j++) row = fma(Helmert<NP>::at(j, b), H[(pt[i] * 4 + pt[j]) * 9 + 3 * r + c], row);
                         acc = fma(hia, row, acc);
                     }
                     S[(3 * a + r) * NR + 3 * b + c] = acc;
@@ -323,20 +326,22 @@ template <int NP> __device__ inline void project_psd(double* H, int mode)
                         for (int b = 0; b < M; b++) row = fma(Helmert<NP>::at(j, b), S[(3 * a + r) * NR + 3 * b + c], row);
                         acc = fma(hia, row, acc);
                     }
-                    H[(i * 4 + j) * 9 + 3 * r + c] = acc;
+                    H[(pt[i] * 4 + pt[j]) * 9 + 3 * r + c] = acc;
                 }
 }
 
 // ---------------------------------------------------------------------------
 // local Hessians -> vertex blocks (potential.cpp:96-154, normal_potential.cpp:172-232)
+// `list` (optional): indices of the collisions to process (the ones the fast path handed over)
 template <int KIND>
 __global__ void __launch_bounds__(128)
     k_hessian_local(CollView c, MeshView m, BarrierDev B, int psd_mode, int64_t block_offset, unsigned long long* __restrict__ hkey,
-                    double* __restrict__ hval, unsigned short* __restrict__ hmask)
+                    double* __restrict__ hval, unsigned short* __restrict__ hmask, const int* __restrict__ list, int64_t nlist)
 {
     constexpr int NP = KIND == IPCB_VV ? 2 : (KIND == IPCB_EV ? 3 : 4);
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= c.n) return;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (tid >= (list ? nlist : c.n)) return;
+    const int64_t i = list ? list[tid] : tid;
     int vid[4];
     d3 x[4];
     load_stencil(KIND, c.ids[i], m, vid, x);
@@ -390,7 +395,26 @@ __global__ void __launch_bounds__(128)
                         }
         }
     }
-    if (project) project_psd<NP>(D.H, psd_mode);
+    if (project) {
+        const int all[4] = { 0, 1, 2, 3 };
+        if (KIND == IPCB_EE) {
+            // an edge-edge collision whose distance type is a vertex-vertex / vertex-edge pair and whose
+            // mollifier is inactive only involves 2 / 3 of its 4 points: the other points' rows are
+            // exactly zero, span an invariant subspace of the projection and must stay exactly zero
+            int pt[4], np = 0;
+            for (int p = 0; p < 4; p++) {
+                bool any = false;
+                for (int q = 0; q < 4; q++)
+                    for (int k = 0; k < 9; k++) any |= D.H[(p * 4 + q) * 9 + k] != 0.0 || D.H[(q * 4 + p) * 9 + k] != 0.0;
+                if (any) pt[np++] = p;
+            }
+            if (np == 4) project_psd<4>(D.H, psd_mode, pt);
+            else if (np == 3) project_psd<3>(D.H, psd_mode, pt);
+            else if (np == 2) project_psd<2>(D.H, psd_mode, pt);
+        } else {
+            project_psd<NP>(D.H, psd_mode, all);
+        }
+    }
     // emit NP*NP vertex blocks keyed (column vertex, row vertex)
     const int64_t base = block_offset + i * (NP * NP);
     for (int bi = 0; bi < NP; bi++)
@@ -405,6 +429,70 @@ __global__ void __launch_bounds__(128)
             }
             hmask[e] = mask;
         }
+}
+
+// PSD-projected local Hessians through the analytic 3+p dimensional subspace (hessian_fast.cuh).
+// Edge-edge collisions whose mollifier is active at X are appended to `slow` for the general kernel.
+template <int KIND>
+__global__ void __launch_bounds__(128)
+    k_hessian_fast(CollView c, MeshView m, BarrierDev B, int psd_mode, int64_t block_offset, unsigned long long* __restrict__ hkey,
+                   double* __restrict__ hval, unsigned short* __restrict__ hmask, int* __restrict__ slow, unsigned long long* slow_count)
+{
+    constexpr int NP = KIND == IPCB_VV ? 2 : (KIND == IPCB_EV ? 3 : 4);
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool is_slow = false;
+    if (i < c.n) {
+        int vid[4];
+        d3 x[4];
+        load_stencil(KIND, c.ids[i], m, vid, x);
+        const Sub sb = collision_sub(KIND, KIND == IPCB_EE ? c.dt[i] : 0);
+        if (KIND == IPCB_EE) is_slow = sqn(cross(x[1] - x[0], x[3] - x[2])) < c.eps[i]; // mollifier active
+        if (!is_slow) {
+            const int np = sb.prim == 0 ? 2 : (sb.prim == 1 ? 3 : 4);
+            const int pi[4] = { sb.i0, sb.i1, sb.i2, sb.i3 };
+            d3 y[4];
+            for (int k = 0; k < np; k++) y[k] = x[pi[k]];
+            FastGeom g;
+            fast_geometry(sb.prim, y, g);
+            const double d2 = sub_value(sb, x); // the same value the energy / gradient use
+            const double w = c.w[i];
+            const double wf1 = w * B.df(d2), wf2 = w * B.ddf(d2);
+            const int64_t base = block_offset + i * (NP * NP);
+            // keys (and zero blocks for the stencil points the primitive does not involve)
+            bool used[4] = { false, false, false, false };
+            for (int k = 0; k < np; k++) used[pi[k]] = true;
+            for (int bi = 0; bi < NP; bi++)
+                for (int bj = 0; bj < NP; bj++) {
+                    const int64_t e = base + bi * NP + bj;
+                    hkey[e] = ((unsigned long long)(unsigned)vid[bj] << 32) | (unsigned)vid[bi];
+                    if (!(used[bi] && used[bj])) {
+                        for (int k = 0; k < 9; k++) hval[e * 9 + k] = 0.0;
+                        hmask[e] = 0;
+                    }
+                }
+            auto emit = [&](int a, int b, const double* blk) {
+                const int64_t e = base + pi[a] * NP + pi[b];
+                unsigned short mask = 0;
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    hval[e * 9 + k] = blk[k];
+                    mask |= (blk[k] != 0.0) << k;
+                }
+                hmask[e] = mask;
+            };
+            if (sb.prim == 0) fast_projected_blocks<0>(g, np, wf1, wf2, psd_mode, emit);
+            else if (sb.prim == 1) fast_projected_blocks<1>(g, np, wf1, wf2, psd_mode, emit);
+            else fast_projected_blocks<2>(g, np, wf1, wf2, psd_mode, emit);
+        }
+    }
+    const unsigned mball = __ballot_sync(0xffffffffu, is_slow);
+    if (mball) {
+        const int lane = threadIdx.x & 31;
+        unsigned long long basep = 0;
+        if (lane == __ffs(mball) - 1) basep = atomicAdd(slow_count, (unsigned long long)__popc(mball));
+        basep = __shfl_sync(0xffffffffu, basep, __ffs(mball) - 1);
+        if (is_slow) slow[basep + __popc(mball & ((1u << lane) - 1))] = int(i);
+    }
 }
 
 __global__ void k_iota_h(int64_t n, int* __restrict__ idx)
@@ -531,19 +619,37 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
         ctx->hkey.reserve(nblk), ctx->hkey_sorted.reserve(nblk), ctx->hidx.reserve(nblk), ctx->hidx_sorted.reserve(nblk);
         ctx->hval.reserve(9 * size_t(nblk)), ctx->hmask.reserve(nblk);
         const MeshView m = mesh_view(ctx);
-        if (ctx->coll[0].count)
-            k_hessian_local<IPCB_VV><<<grid_for(ctx->coll[0].count, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, offs[0], ctx->hkey.p,
-                                                                                        ctx->hval.p, ctx->hmask.p);
-        if (ctx->coll[1].count)
-            k_hessian_local<IPCB_EV><<<grid_for(ctx->coll[1].count, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, offs[1], ctx->hkey.p,
-                                                                                        ctx->hval.p, ctx->hmask.p);
-        if (ctx->coll[2].count)
-            k_hessian_local<IPCB_EE><<<grid_for(ctx->coll[2].count, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, offs[2], ctx->hkey.p,
-                                                                                        ctx->hval.p, ctx->hmask.p);
-        if (ctx->coll[3].count)
-            k_hessian_local<IPCB_FV><<<grid_for(ctx->coll[3].count, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, offs[3], ctx->hkey.p,
-                                                                                        ctx->hval.p, ctx->hmask.p);
-        ctx->launches += 4;
+        unsigned long long* hk = ctx->hkey.p;
+        double* hv = ctx->hval.p;
+        unsigned short* hm = ctx->hmask.p;
+        const int64_t n0 = ctx->coll[0].count, n1 = ctx->coll[1].count, n2 = ctx->coll[2].count, n3 = ctx->coll[3].count;
+        static const bool force_general = getenv("IPCB_HESSIAN_GENERAL") != nullptr; // A/B switch for tests and profiles
+        if (psd_mode == IPCB_PSD_NONE || force_general) {
+            if (n0) k_hessian_local<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, offs[0], hk, hv, hm, nullptr, 0);
+            if (n1) k_hessian_local<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, offs[1], hk, hv, hm, nullptr, 0);
+            if (n2) k_hessian_local<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, offs[2], hk, hv, hm, nullptr, 0);
+            if (n3) k_hessian_local<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, offs[3], hk, hv, hm, nullptr, 0);
+            ctx->launches += 4;
+        } else {
+            unsigned long long* slow_count = ctx->dCounters.p + 5;
+            ctx->hhead.reserve(std::max<int64_t>(n2, 1)); // scratch: the slow list (not yet needed by the assembly)
+            IPCB_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(unsigned long long), s));
+            if (n0) k_hessian_fast<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, offs[0], hk, hv, hm, ctx->hhead.p, slow_count);
+            if (n1) k_hessian_fast<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, offs[1], hk, hv, hm, ctx->hhead.p, slow_count);
+            if (n3) k_hessian_fast<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, offs[3], hk, hv, hm, ctx->hhead.p, slow_count);
+            if (n2) {
+                k_hessian_fast<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, offs[2], hk, hv, hm, ctx->hhead.p, slow_count);
+                IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[11], slow_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+                IPCB_CUDA(cudaStreamSynchronize(s));
+                const int64_t nslow = ctx->pinned.p[11];
+                if (nslow) {
+                    // the list lives in hhead, which the assembly overwrites later: process it now
+                    k_hessian_local<IPCB_EE><<<grid_for(nslow, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, offs[2], hk, hv, hm, ctx->hhead.p, nslow);
+                    ctx->launches++;
+                }
+            }
+            ctx->launches += 4;
+        }
         IPCB_CUDA(cudaGetLastError());
     }
     Stage st(ctx, "hessian_assemble");

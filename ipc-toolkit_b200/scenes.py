@@ -112,7 +112,7 @@ def perturbed_sheets(layers=4, n=64, spacing=2.0, disp=5.0, seed=4):
         parts.append((V, F))
     V0, F = _merge(parts)
     V1 = V0 + rng.uniform(-1, 1, V0.shape) * disp * h
-    return V0, V1, _edges(F), F, {"dhat": 1e-3}
+    return V0, V1, _edges(F), F, {"dhat": 0.6 * spacing * h}
 
 
 def random_soup(n_tris=200, seed=0, scale=0.15):
