@@ -145,6 +145,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ncu-step", action="store_true",
+                    help="profiling aid: warm up, then run ONE device step between cudaProfilerStart/Stop and exit "
+                         "(use with ncu --profile-from-start off); prints no bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     desc, full_spec, sample_spec = WORKLOADS[args.workload]
@@ -244,6 +247,18 @@ def main():
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
         return float(t.item()) / steps
+
+    if args.ncu_step:
+        for _ in range(args.warmup):
+            device_step()
+        torch.cuda.synchronize()
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        device_step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
 
     sampler = ClockSampler(local)
     if rank == 0:

@@ -119,15 +119,19 @@ struct ipcb_ctx {
     // ---- potential
     ipcb::Buf<double> dScalar; // small device scalars (energy, toi, ...)
     ipcb::Buf<double> dGrad;
-    // hessian assembly
-    ipcb::Buf<unsigned long long> hkey, hkey_sorted;
-    ipcb::Buf<int> hidx, hidx_sorted;
-    ipcb::Buf<double> hval;             // 9 doubles per emitted block
-    ipcb::Buf<unsigned short> hmask;    // 9-bit non-zero mask per emitted block
-    ipcb::Buf<int> hhead, hpos, hcolptr, hcnt, hscan;
-    ipcb::Buf<double> ublk;             // unique blocks (9 doubles)
-    ipcb::Buf<unsigned short> umask;
-    ipcb::Buf<unsigned long long> ukey;
+    // hessian assembly (potential.cu): per-collision records, vertex incidences, per-column sorted items
+    ipcb::Buf<unsigned long long> hkey, hkey_sorted; // incidence keys (vertex << 32 | collision * 4 + point); also pair sorting
+    ipcb::Buf<int4> hvid;                            // stencil vertex ids per collision (-1 padded)
+    ipcb::Buf<unsigned short> hmask;                 // 16 x 9-bit non-zero masks per collision (slot = col point * 4 + row point)
+    ipcb::Buf<double> hblk;                          // 16 x 9 doubles per collision
+    ipcb::Buf<int> hslow;                            // edge-edge collisions handed to the general kernel
+    ipcb::Buf<int> hcolinc, hcolR, hitemoff;         // per column vertex: first incidence, #items, first item
+    ipcb::Buf<unsigned> hsref;                       // per item, column-major then row-sorted: block slot | head flag
+    ipcb::Buf<int> hcnt;                             // entries per scalar column
+    ipcb::Buf<int> hbig;                             // columns too large for one warp's shared memory
+    ipcb::Buf<char> hscratch;                        // global sort scratch for huge columns
+    size_t hscratch_items = 0;
+    bool hess_attr_set = false;
     ipcb::Buf<int> outer, inner;
     ipcb::Buf<double> vals;
     int64_t nnz = 0;

@@ -436,6 +436,60 @@ __device__ inline double sub_deriv(const Sub& s, const d3* x, LocalDeriv& L)
     default: return ll_deriv(x, s.i0, s.i1, s.i2, s.i3, L);
     }
 }
+// ---- gradient-only forms (registers only) ---------------------------------------
+// Same closed forms as the *_deriv functions above without the Hessian blocks.  gp[k] receives the
+// gradient w.r.t. the primitive's k-th ARGUMENT point (y[0..np)); returns the squared distance.
+__device__ __forceinline__ void cross_sq_grad(d3 a, d3 b, d3 c /* = a x b */, d3& ga, d3& gb)
+{
+    ga = 2.0 * cross(b, c);
+    gb = 2.0 * cross(c, a);
+}
+__device__ __forceinline__ void triple_grad(d3 q, d3 u, d3 v, d3& gq, d3& gu, d3& gv)
+{
+    const d3 n = cross(u, v);
+    const double s = dot(q, n), M = sqn(n);
+    d3 gMu, gMv;
+    cross_sq_grad(u, v, n, gMu, gMv);
+    const double iM = 1.0 / M, c1 = 2.0 * s * iM, c2 = s * s * iM * iM;
+    const d3 gsu = cross(v, q), gsv = cross(q, u);
+    gq = c1 * n;
+    gu = { c1 * gsu.x - c2 * gMu.x, c1 * gsu.y - c2 * gMu.y, c1 * gsu.z - c2 * gMu.z };
+    gv = { c1 * gsv.x - c2 * gMv.x, c1 * gsv.y - c2 * gMv.y, c1 * gsv.z - c2 * gMv.z };
+}
+// prim: 0 PP (y0,y1), 1 PL (p, e0, e1), 2 plane (p, t0, t1, t2), 3 LL (a0, a1, b0, b1)
+__device__ __forceinline__ void prim_grad(int prim, const d3* y, d3* gp)
+{
+    const d3 zero = { 0, 0, 0 };
+    gp[0] = gp[1] = gp[2] = gp[3] = zero;
+    if (prim == 0) {
+        const d3 r = y[1] - y[0];
+        gp[1] = 2.0 * r;
+        gp[0] = zero - gp[1];
+    } else if (prim == 1) {
+        const d3 a = y[1] - y[0], b = y[2] - y[0], c = cross(a, b), e = y[2] - y[1];
+        const double N = sqn(c), Lq = sqn(e);
+        d3 ga, gb;
+        cross_sq_grad(a, b, c, ga, gb);
+        const double iL = 1.0 / Lq, NL2 = N * iL * iL;
+        const d3 gL0 = -2.0 * e, gL1 = 2.0 * e;
+        gp[1] = { iL * ga.x - NL2 * gL0.x, iL * ga.y - NL2 * gL0.y, iL * ga.z - NL2 * gL0.z };
+        gp[2] = { iL * gb.x - NL2 * gL1.x, iL * gb.y - NL2 * gL1.y, iL * gb.z - NL2 * gL1.z };
+        gp[0] = (zero - gp[1]) - gp[2];
+    } else if (prim == 2) {
+        d3 gq, gu, gv;
+        triple_grad(y[0] - y[1], y[2] - y[1], y[3] - y[1], gq, gu, gv);
+        gp[0] = gq, gp[2] = gu, gp[3] = gv;
+        gp[1] = ((zero - gq) - gu) - gv;
+    } else {
+        d3 gq, gu, gv; // q = b0 - a0, u = a1 - a0, v = b1 - b0
+        triple_grad(y[2] - y[0], y[1] - y[0], y[3] - y[2], gq, gu, gv);
+        gp[0] = (zero - gq) - gu;
+        gp[1] = gu;
+        gp[2] = gq - gv;
+        gp[3] = gv;
+    }
+}
+
 // s = |(ea1-ea0) x (eb1-eb0)|^2 on stencil points 0..3
 __device__ inline double cross_sqnorm_deriv(const d3* x, LocalDeriv& L)
 {

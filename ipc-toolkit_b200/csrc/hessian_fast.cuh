@@ -131,66 +131,69 @@ __device__ __forceinline__ int fast_geometry(int prim, const d3* y, FastGeom& g)
     return 2;
 }
 
-// Projected local matrix for a primitive with P parameters over np points.
-// emit(a, b, blk) receives every 3x3 block (row-major) for a,b < np.
-template <int P, typename Emit>
-__device__ __forceinline__ void fast_projected_blocks(const FastGeom& g, int np, double wf1, double wf2, int mode, const Emit& emit)
+// Projected coordinate matrix and basis of a primitive with P parameters.
+template <int P> struct FastProj {
+    double Mp[3 + P][3 + P]; // PSD-projected coordinate matrix
+    double eps[2][4];        // orthonormal eps_j over the primitive's points
+    double ch[4];            // c / |c|
+    double rh[3];            // r / |r|
+};
+
+template <int P> __device__ __forceinline__ void fast_project(const FastGeom& g, double wf1, double wf2, int mode, FastProj<P>& pr)
 {
     constexpr int N = 3 + P;
     const d3 r = g.r;
     const double d = sqrt(dot(r, r));
-    const d3 rh = { r.x / d, r.y / d, r.z / d };
+    pr.rh[0] = r.x / d, pr.rh[1] = r.y / d, pr.rh[2] = r.z / d;
     double cn2 = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) cn2 = fma(g.cv[k], g.cv[k], cn2);
     const double cn = sqrt(cn2);
-    double ch[4];
 #pragma unroll
-    for (int k = 0; k < 4; k++) ch[k] = g.cv[k] / cn;
+    for (int k = 0; k < 4; k++) pr.ch[k] = g.cv[k] / cn;
     // orthonormal eps_j (orthogonal to ch) and the coordinates of a_j
-    double eps[2][4];
     double tvec[2][3], bvec[2][2];
 #pragma unroll
     for (int j = 0; j < 2; j++) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) eps[j][k] = 0;
+        for (int k = 0; k < 4; k++) pr.eps[j][k] = 0;
         tvec[j][0] = tvec[j][1] = tvec[j][2] = 0, bvec[j][0] = bvec[j][1] = 0;
     }
     if (P >= 1) {
         double al = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) al = fma(g.ev[0][k], ch[k], al);
+        for (int k = 0; k < 4; k++) al = fma(g.ev[0][k], pr.ch[k], al);
         double nn = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            eps[0][k] = g.ev[0][k] - al * ch[k];
-            nn = fma(eps[0][k], eps[0][k], nn);
+            pr.eps[0][k] = g.ev[0][k] - al * pr.ch[k];
+            nn = fma(pr.eps[0][k], pr.eps[0][k], nn);
         }
         const double n1 = sqrt(nn);
 #pragma unroll
-        for (int k = 0; k < 4; k++) eps[0][k] /= n1;
+        for (int k = 0; k < 4; k++) pr.eps[0][k] /= n1;
         tvec[0][0] = fma(cn, g.tau[0].x, al * r.x), tvec[0][1] = fma(cn, g.tau[0].y, al * r.y), tvec[0][2] = fma(cn, g.tau[0].z, al * r.z);
         bvec[0][0] = d * n1;
     }
     if (P >= 2) {
         double al = 0;
 #pragma unroll
-        for (int k = 0; k < 4; k++) al = fma(g.ev[1][k], ch[k], al);
+        for (int k = 0; k < 4; k++) al = fma(g.ev[1][k], pr.ch[k], al);
         double w2[4], beta = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            w2[k] = g.ev[1][k] - al * ch[k];
-            beta = fma(w2[k], eps[0][k], beta);
+            w2[k] = g.ev[1][k] - al * pr.ch[k];
+            beta = fma(w2[k], pr.eps[0][k], beta);
         }
         double nn = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            w2[k] -= beta * eps[0][k];
+            w2[k] -= beta * pr.eps[0][k];
             nn = fma(w2[k], w2[k], nn);
         }
         const double gam = sqrt(nn);
 #pragma unroll
-        for (int k = 0; k < 4; k++) eps[1][k] = w2[k] / gam;
+        for (int k = 0; k < 4; k++) pr.eps[1][k] = w2[k] / gam;
         tvec[1][0] = fma(cn, g.tau[1].x, al * r.x), tvec[1][1] = fma(cn, g.tau[1].y, al * r.y), tvec[1][2] = fma(cn, g.tau[1].z, al * r.z);
         bvec[1][0] = d * beta, bvec[1][1] = d * gam;
     }
@@ -230,7 +233,6 @@ __device__ __forceinline__ void fast_projected_blocks(const FastGeom& g, int np,
         if (lam[i] < 0.0) lam[i] = mode == IPCB_PSD_CLAMP ? 0.0 : -lam[i];
     }
     // M+ = V diag(lam) V^T
-    double Mp[N][N];
 #pragma unroll
     for (int i = 0; i < N; i++)
 #pragma unroll
@@ -238,35 +240,31 @@ __device__ __forceinline__ void fast_projected_blocks(const FastGeom& g, int np,
             double acc = 0;
 #pragma unroll
             for (int k = 0; k < N; k++) acc = fma(V[i][k] * lam[k], V[j][k], acc);
-            Mp[i][j] = Mp[j][i] = acc;
+            pr.Mp[i][j] = pr.Mp[j][i] = acc;
         }
-    // expand: block(a,b) = ch_a ch_b Mp_TT + ch_a u_b r^T-like terms (see header)
-    const double rhv[3] = { rh.x, rh.y, rh.z };
-    for (int a = 0; a < np; a++) {
-        double ua[3] = { 0, 0, 0 };
+}
+
+// 3x3 block (rows of point a, columns of point b; row-major) of the projected local matrix:
+//   ch_a ch_b Mp_TT + ch_a (r^ (x) u_b) ... (see header)
+template <int P> __device__ __forceinline__ void fast_block(const FastProj<P>& pr, int a, int b, double* blk)
+{
+    double ua[3] = { 0, 0, 0 }, ub[3] = { 0, 0, 0 }, sab = 0;
 #pragma unroll
-        for (int k = 0; k < P; k++)
+    for (int k = 0; k < P; k++) {
 #pragma unroll
-            for (int c = 0; c < 3; c++) ua[c] = fma(eps[k][a], Mp[3 + k][c], ua[c]);
-        for (int b = 0; b < np; b++) {
-            double ub[3] = { 0, 0, 0 }, sab = 0;
-#pragma unroll
-            for (int k = 0; k < P; k++) {
-#pragma unroll
-                for (int c = 0; c < 3; c++) ub[c] = fma(eps[k][b], Mp[c][3 + k], ub[c]);
-#pragma unroll
-                for (int l = 0; l < P; l++) sab = fma(eps[k][a] * eps[l][b], Mp[3 + k][3 + l], sab);
-            }
-            const double cab = ch[a] * ch[b];
-            double blk[9];
-#pragma unroll
-            for (int rr_ = 0; rr_ < 3; rr_++)
-#pragma unroll
-                for (int c = 0; c < 3; c++)
-                    blk[3 * rr_ + c] = cab * Mp[rr_][c] + ch[a] * ub[rr_] * rhv[c] + ch[b] * rhv[rr_] * ua[c] + sab * rhv[rr_] * rhv[c];
-            emit(a, b, blk);
+        for (int c = 0; c < 3; c++) {
+            ua[c] = fma(pr.eps[k][a], pr.Mp[3 + k][c], ua[c]);
+            ub[c] = fma(pr.eps[k][b], pr.Mp[c][3 + k], ub[c]);
         }
+#pragma unroll
+        for (int l = 0; l < P; l++) sab = fma(pr.eps[k][a] * pr.eps[l][b], pr.Mp[3 + k][3 + l], sab);
     }
+    const double cab = pr.ch[a] * pr.ch[b];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            blk[3 * r + c] = cab * pr.Mp[r][c] + pr.ch[a] * ub[r] * pr.rh[c] + pr.ch[b] * pr.rh[r] * ua[c] + sab * pr.rh[r] * pr.rh[c];
 }
 
 } // namespace ipcb

@@ -162,44 +162,68 @@ void barrier_energy(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_out)
 
 // ---------------------------------------------------------------------------
 // gradient (potential.cpp:58-94, normal_potential.cpp:137-170, local_to_global.hpp:21-45)
-__global__ void __launch_bounds__(128) k_gradient(CollView c, MeshView m, BarrierDev B, double* __restrict__ grad)
+// One thread per collision, registers only: the distance gradient comes from the gradient-only closed
+// forms (geom.cuh prim_grad), the stencil is resolved at compile time for VV / EV / FV and through
+// the distance type for EE.
+template <int KIND> __global__ void __launch_bounds__(256) k_gradient(CollView c, MeshView m, BarrierDev B, double* __restrict__ grad)
 {
+    constexpr int NP = KIND == IPCB_VV ? 2 : (KIND == IPCB_EV ? 3 : 4);
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= c.n) return;
     int vid[4];
     d3 x[4];
-    const int n = load_stencil(c.kind, c.ids[i], m, vid, x);
+    load_stencil(KIND, c.ids[i], m, vid, x);
     const double w = c.w[i];
-    LocalDeriv D;
-    zero_local(D);
-    double mol = 1.0, s = 0.0, eps = 0.0;
-    if (c.kind == IPCB_EE) {
-        eps = c.eps[i];
-        s = sqn(cross(x[1] - x[0], x[3] - x[2]));
-        mol = moll(s, eps);
-        if (mol <= 0) return; // gradient is exactly zero (normal_potential.cpp:143-147)
-    }
-    const double d = sub_deriv(collision_sub(c.kind, c.kind == IPCB_EE ? c.dt[i] : 0), x, D);
-    const double gf = B.df(d);
-    double g[12];
-    if (c.kind != IPCB_EE) {
-        for (int k = 0; k < 3 * n; k++) g[k] = (w * gf) * D.g[k];
+    d3 G[4];
+    if (KIND != IPCB_EE) {
+        // VV: PP(0,1); EV: PL(0,1,2); FV: plane(0,1,2,3) — argument order == stencil order
+        const int prim = KIND == IPCB_VV ? 0 : (KIND == IPCB_EV ? 1 : 2);
+        const double d = sub_value(collision_sub(KIND, 0), x);
+        prim_grad(prim, x, G);
+        const double sc = w * B.df(d);
+#pragma unroll
+        for (int a = 0; a < NP; a++) G[a] = sc * G[a];
     } else {
-        const double f = B.f(d);
-        for (int k = 0; k < 12; k++) g[k] = (w * mol * gf) * D.g[k];
-        if (s < eps) {
-            // second use of the local container for the mollifier's cross-norm derivative
-            zero_local(D);
-            cross_sqnorm_deriv(x, D);
-            const double dm = moll_d(s, eps);
-            for (int k = 0; k < 12; k++) g[k] = (w * f) * (dm * D.g[k]) + g[k];
+        const double eps = c.eps[i];
+        const double s = sqn(cross(x[1] - x[0], x[3] - x[2]));
+        const double mol = moll(s, eps);
+        if (mol <= 0) return; // gradient is exactly zero (normal_potential.cpp:143-147)
+        const Sub sb = sub_edge_edge(c.dt[i]);
+        const double d = sub_value(sb, x);
+        const int pi[4] = { sb.i0, sb.i1, sb.i2, sb.i3 };
+        const int np = sb.prim == 0 ? 2 : (sb.prim == 1 ? 3 : 4);
+        d3 y[4], gp[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int p = pi[k];
+            y[k] = p == 0 ? x[0] : (p == 1 ? x[1] : (p == 2 ? x[2] : x[3]));
+        }
+        prim_grad(sb.prim, y, gp);
+        const double sc = w * mol * B.df(d);
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            d3 acc = { 0, 0, 0 };
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (k < np && pi[k] == a) acc = acc + gp[k];
+            G[a] = sc * acc;
+        }
+        if (s < eps) { // + (w f) m'(s) grad s
+            const d3 u = x[1] - x[0], v = x[3] - x[2];
+            d3 gu, gv;
+            cross_sq_grad(u, v, cross(u, v), gu, gv);
+            const double wf = w * B.f(d), dm = moll_d(s, eps);
+            const d3 mu = wf * (dm * gu), mv = wf * (dm * gv);
+            G[0] = G[0] - mu, G[1] = G[1] + mu, G[2] = G[2] - mv, G[3] = G[3] + mv;
         }
     }
-    for (int a = 0; a < n; a++)
-        for (int k = 0; k < 3; k++) {
-            const double v = g[3 * a + k];
-            if (v != 0.0) atomicAdd(grad + 3 * (size_t)vid[a] + k, v);
-        }
+#pragma unroll
+    for (int a = 0; a < NP; a++) {
+        double* g = grad + 3 * (size_t)vid[a];
+        if (G[a].x != 0.0) atomicAdd(g, G[a].x);
+        if (G[a].y != 0.0) atomicAdd(g + 1, G[a].y);
+        if (G[a].z != 0.0) atomicAdd(g + 2, G[a].z);
+    }
 }
 
 void barrier_gradient(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_grad)
@@ -208,11 +232,12 @@ void barrier_gradient(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_gr
     cudaStream_t s = ctx->stream;
     const BarrierDev B = make_barrier(bp, ctx->dmin);
     IPCB_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(double) * 3 * size_t(ctx->nV), s));
-    for (int k = 0; k < 4; k++) {
-        if (!ctx->coll[k].count) continue;
-        k_gradient<<<grid_for(ctx->coll[k].count, 128), 128, 0, s>>>(view(ctx, k), mesh_view(ctx), B, d_grad);
-        ctx->launches++;
-    }
+    const MeshView m = mesh_view(ctx);
+    const int64_t n0 = ctx->coll[0].count, n1 = ctx->coll[1].count, n2 = ctx->coll[2].count, n3 = ctx->coll[3].count;
+    if (n0) k_gradient<IPCB_VV><<<grid_for(n0, 256), 256, 0, s>>>(view(ctx, 0), m, B, d_grad), ctx->launches++;
+    if (n1) k_gradient<IPCB_EV><<<grid_for(n1, 256), 256, 0, s>>>(view(ctx, 1), m, B, d_grad), ctx->launches++;
+    if (n2) k_gradient<IPCB_EE><<<grid_for(n2, 256), 256, 0, s>>>(view(ctx, 2), m, B, d_grad), ctx->launches++;
+    if (n3) k_gradient<IPCB_FV><<<grid_for(n3, 256), 256, 0, s>>>(view(ctx, 3), m, B, d_grad), ctx->launches++;
     IPCB_CUDA(cudaGetLastError());
 }
 
@@ -333,10 +358,29 @@ template <int NP> __device__ inline void project_psd(double* H, int mode, const 
 // ---------------------------------------------------------------------------
 // local Hessians -> vertex blocks (potential.cpp:96-154, normal_potential.cpp:172-232)
 // `list` (optional): indices of the collisions to process (the ones the fast path handed over)
+// Output of the local kernels: one record per collision, addressed by the GLOBAL collision index
+// gi (VV first, then EV, EE, FV).  Block slot (a, b) = a * 4 + b holds the 3x3 block whose COLUMNS
+// belong to stencil point a and whose ROWS belong to point b (row-major), i.e. what the column of
+// vertex vid[a] needs in compressed-column order.
+struct HessOut {
+    int4* vid;               // stencil vertex ids, -1 padded
+    unsigned short* mask;    // 16 per collision: 9-bit exact-non-zero mask per slot
+    double* blk;             // 16 x 9 per collision
+    unsigned long long* inc; // incidences: (vertex << 32) | (gi * 4 + a), NP per collision
+};
+constexpr int HSLOTS = 16;
+
+template <int NP> __device__ inline void write_record(const HessOut& out, int64_t gi, int64_t inc_base, const int* vid)
+{
+    out.vid[gi] = make_int4(vid[0], vid[1], NP > 2 ? vid[2] : -1, NP > 3 ? vid[3] : -1);
+#pragma unroll
+    for (int a = 0; a < NP; a++) out.inc[inc_base + a] = ((unsigned long long)(unsigned)vid[a] << 32) | (unsigned long long)(gi * 4 + a);
+}
+
 template <int KIND>
 __global__ void __launch_bounds__(128)
-    k_hessian_local(CollView c, MeshView m, BarrierDev B, int psd_mode, int64_t block_offset, unsigned long long* __restrict__ hkey,
-                    double* __restrict__ hval, unsigned short* __restrict__ hmask, const int* __restrict__ list, int64_t nlist)
+    k_hessian_local(CollView c, MeshView m, BarrierDev B, int psd_mode, int64_t gi0, int64_t inc0, HessOut out, const int* __restrict__ list,
+                    int64_t nlist)
 {
     constexpr int NP = KIND == IPCB_VV ? 2 : (KIND == IPCB_EV ? 3 : 4);
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -415,180 +459,410 @@ __global__ void __launch_bounds__(128)
             project_psd<NP>(D.H, psd_mode, all);
         }
     }
-    // emit NP*NP vertex blocks keyed (column vertex, row vertex)
-    const int64_t base = block_offset + i * (NP * NP);
+    // emit the NP x NP vertex blocks: slot (column point bj, row point bi)
+    const int64_t gi = gi0 + i;
+    if (!list) write_record<NP>(out, gi, inc0 + i * NP, vid); // listed collisions already have their record
+    unsigned short masks[HSLOTS];
+#pragma unroll
+    for (int k = 0; k < HSLOTS; k++) masks[k] = 0;
     for (int bi = 0; bi < NP; bi++)
         for (int bj = 0; bj < NP; bj++) {
-            const int64_t e = base + bi * NP + bj;
-            hkey[e] = ((unsigned long long)(unsigned)vid[bj] << 32) | (unsigned)vid[bi];
+            const int slot = bj * 4 + bi;
             unsigned short mask = 0;
             for (int k = 0; k < 9; k++) {
                 const double v = D.H[(bi * 4 + bj) * 9 + k];
-                hval[e * 9 + k] = v;
+                out.blk[(gi * HSLOTS + slot) * 9 + k] = v;
                 mask |= (v != 0.0) << k; // exact zeros are not entries (local_to_global.hpp:290-291)
             }
-            hmask[e] = mask;
+            masks[slot] = mask;
         }
+    for (int k = 0; k < HSLOTS; k++) out.mask[gi * HSLOTS + k] = masks[k];
 }
 
 // PSD-projected local Hessians through the analytic 3+p dimensional subspace (hessian_fast.cuh).
-// Edge-edge collisions whose mollifier is active at X are appended to `slow` for the general kernel.
+// Edge-edge collisions whose mollifier is active at X (or whose distance type is not edge-edge) are
+// appended to `slow` for the general kernel.
+//
+// Stores: a thread owns one collision = 1152 contiguous bytes of blocks.  Writing them from
+// registers would make every 8-byte store of a warp hit 32 different sectors; instead each block
+// row (NP blocks = NP*72 contiguous bytes per collision) is staged in shared memory (odd stride:
+// conflict-free) and written out by the whole warp with consecutive lanes on consecutive addresses.
 template <int KIND>
 __global__ void __launch_bounds__(128)
-    k_hessian_fast(CollView c, MeshView m, BarrierDev B, int psd_mode, int64_t block_offset, unsigned long long* __restrict__ hkey,
-                   double* __restrict__ hval, unsigned short* __restrict__ hmask, int* __restrict__ slow, unsigned long long* slow_count)
+    k_hessian_fast(CollView c, MeshView m, BarrierDev B, int psd_mode, int64_t gi0, int64_t inc0, HessOut out, int* __restrict__ slow,
+                   unsigned long long* slow_count)
 {
     constexpr int NP = KIND == IPCB_VV ? 2 : (KIND == IPCB_EV ? 3 : 4);
+    constexpr int P = KIND == IPCB_VV ? 0 : (KIND == IPCB_EV ? 1 : 2);
+    constexpr int PRIM = KIND == IPCB_VV ? 0 : (KIND == IPCB_EV ? 1 : (KIND == IPCB_FV ? 2 : 3));
+    constexpr int ROW = NP * 9, PAD = ROW | 1;
+    __shared__ double stage[4][32][PAD];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool valid = i < c.n;
     bool is_slow = false;
-    if (i < c.n) {
+    FastProj<P> pr;
+    if (valid) {
         int vid[4];
         d3 x[4];
         load_stencil(KIND, c.ids[i], m, vid, x);
-        const Sub sb = collision_sub(KIND, KIND == IPCB_EE ? c.dt[i] : 0);
-        if (KIND == IPCB_EE) is_slow = sqn(cross(x[1] - x[0], x[3] - x[2])) < c.eps[i]; // mollifier active
+        write_record<NP>(out, gi0 + i, inc0 + i * NP, vid);
+        if (KIND == IPCB_EE) is_slow = c.dt[i] != EE_AB || sqn(cross(x[1] - x[0], x[3] - x[2])) < c.eps[i];
         if (!is_slow) {
-            const int np = sb.prim == 0 ? 2 : (sb.prim == 1 ? 3 : 4);
-            const int pi[4] = { sb.i0, sb.i1, sb.i2, sb.i3 };
-            d3 y[4];
-            for (int k = 0; k < np; k++) y[k] = x[pi[k]];
             FastGeom g;
-            fast_geometry(sb.prim, y, g);
-            const double d2 = sub_value(sb, x); // the same value the energy / gradient use
+            fast_geometry(PRIM, x, g);
+            const double d2 = sub_value(collision_sub(KIND, EE_AB), x); // the same value the energy / gradient use
             const double w = c.w[i];
-            const double wf1 = w * B.df(d2), wf2 = w * B.ddf(d2);
-            const int64_t base = block_offset + i * (NP * NP);
-            // keys (and zero blocks for the stencil points the primitive does not involve)
-            bool used[4] = { false, false, false, false };
-            for (int k = 0; k < np; k++) used[pi[k]] = true;
-            for (int bi = 0; bi < NP; bi++)
-                for (int bj = 0; bj < NP; bj++) {
-                    const int64_t e = base + bi * NP + bj;
-                    hkey[e] = ((unsigned long long)(unsigned)vid[bj] << 32) | (unsigned)vid[bi];
-                    if (!(used[bi] && used[bj])) {
-                        for (int k = 0; k < 9; k++) hval[e * 9 + k] = 0.0;
-                        hmask[e] = 0;
-                    }
-                }
-            auto emit = [&](int a, int b, const double* blk) {
-                const int64_t e = base + pi[a] * NP + pi[b];
-                unsigned short mask = 0;
-#pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    hval[e * 9 + k] = blk[k];
-                    mask |= (blk[k] != 0.0) << k;
-                }
-                hmask[e] = mask;
-            };
-            if (sb.prim == 0) fast_projected_blocks<0>(g, np, wf1, wf2, psd_mode, emit);
-            else if (sb.prim == 1) fast_projected_blocks<1>(g, np, wf1, wf2, psd_mode, emit);
-            else fast_projected_blocks<2>(g, np, wf1, wf2, psd_mode, emit);
+            fast_project<P>(g, w * B.df(d2), w * B.ddf(d2), psd_mode, pr);
         }
     }
-    const unsigned mball = __ballot_sync(0xffffffffu, is_slow);
-    if (mball) {
-        const int lane = threadIdx.x & 31;
+    const bool emit = valid && !is_slow;
+    const unsigned emask = __ballot_sync(0xffffffffu, emit);
+    const unsigned smask = __ballot_sync(0xffffffffu, is_slow);
+    if (smask) {
         unsigned long long basep = 0;
-        if (lane == __ffs(mball) - 1) basep = atomicAdd(slow_count, (unsigned long long)__popc(mball));
-        basep = __shfl_sync(0xffffffffu, basep, __ffs(mball) - 1);
-        if (is_slow) slow[basep + __popc(mball & ((1u << lane) - 1))] = int(i);
+        if (lane == __ffs(smask) - 1) basep = atomicAdd(slow_count, (unsigned long long)__popc(smask));
+        basep = __shfl_sync(0xffffffffu, basep, __ffs(smask) - 1);
+        if (is_slow) slow[basep + __popc(smask & ((1u << lane) - 1))] = int(i);
+    }
+    if (emask == 0) return;
+    const int64_t gw = gi0 + (i - lane); // global index of lane 0's collision
+    unsigned mpack[HSLOTS / 2];
+#pragma unroll
+    for (int k = 0; k < HSLOTS / 2; k++) mpack[k] = 0;
+#pragma unroll
+    for (int a = 0; a < NP; a++) { // column point
+        if (emit) {
+#pragma unroll
+            for (int b = 0; b < NP; b++) { // row point
+                double blk[9];
+                fast_block<P>(pr, b, a, blk);
+                unsigned mask = 0;
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    stage[warp][lane][b * 9 + k] = blk[k];
+                    mask |= (blk[k] != 0.0) << k;
+                }
+                const int slot = a * 4 + b;
+                mpack[slot >> 1] |= mask << (16 * (slot & 1));
+            }
+        }
+        __syncwarp();
+        for (int f = lane; f < 32 * ROW; f += 32) {
+            const int cl = f / ROW, j = f - cl * ROW;
+            if ((emask >> cl) & 1u) out.blk[(gw + cl) * (HSLOTS * 9) + a * 36 + j] = stage[warp][cl][j];
+        }
+        __syncwarp();
+    }
+    if (emit) {
+        uint4* mp = reinterpret_cast<uint4*>(out.mask + (gi0 + i) * HSLOTS);
+        mp[0] = make_uint4(mpack[0], mpack[1], mpack[2], mpack[3]);
+        mp[1] = make_uint4(mpack[4], mpack[5], mpack[6], mpack[7]);
     }
 }
 
-__global__ void k_iota_h(int64_t n, int* __restrict__ idx)
+// ---------------------------------------------------------------------------
+// Assembly into compressed columns (== compressed rows of the symmetric matrix), replacing
+// local_hessian_to_global_triplets + setFromTriplets (local_to_global.hpp:263-305, potential.cpp:218).
+//
+// The reference sorts 144 scalar triplets per collision globally.  Here only the (vertex, collision)
+// INCIDENCES are sorted globally (4 per collision, radix sort on the vertex bits); everything else
+// happens per column vertex inside one warp: the column's row blocks are sorted by row vertex in
+// shared memory (bitonic), runs of equal row vertex become one unique block whose pattern is the
+// OR of the exact-non-zero masks (pass 1: counts), and after one prefix sum over the scalar
+// columns the blocks are gathered (72 contiguous bytes each), run-summed with a segmented warp
+// scan and written straight into inner / values (pass 2).  Summation order is fixed by the sort.
+constexpr unsigned HEAD_BIT = 0x80000000u;
+constexpr int WARP_CAP = 512;  // items a warp sorts in shared memory
+constexpr int CTA_CAP = 8192;  // items a block sorts in shared memory; beyond: global scratch
+
+__device__ inline int lower_bound_hi(const unsigned long long* __restrict__ key, int lo, int hi, unsigned v)
 {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) idx[i] = int(i);
-}
-__global__ void k_block_heads(int64_t n, const unsigned long long* __restrict__ key, int* __restrict__ head)
-{
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < n) head[i] = (i == 0 || key[i] != key[i - 1]) ? 1 : 0;
-}
-// sum every run of equal keys into one unique block (setFromTriplets sums duplicates)
-__global__ void k_block_reduce(int64_t n, const unsigned long long* __restrict__ key, const int* __restrict__ idx,
-                               const int* __restrict__ head, const int* __restrict__ upos, const double* __restrict__ hval,
-                               const unsigned short* __restrict__ hmask, unsigned long long* __restrict__ ukey,
-                               double* __restrict__ ublk, unsigned short* __restrict__ umask)
-{
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n || !head[i]) return;
-    const unsigned long long k = key[i];
-    double acc[9] = { 0, 0, 0, 0, 0, 0, 0, 0, 0 };
-    unsigned short mask = 0;
-    for (int64_t j = i; j < n && key[j] == k; j++) {
-        const int e = idx[j];
-        mask |= hmask[e];
-#pragma unroll
-        for (int q = 0; q < 9; q++) acc[q] += hval[(size_t)e * 9 + q];
-    }
-    const int u = upos[i];
-    ukey[u] = k;
-    umask[u] = mask;
-#pragma unroll
-    for (int q = 0; q < 9; q++) ublk[(size_t)u * 9 + q] = acc[q];
-}
-// colptr[v] = first unique block whose column vertex is >= v  (v in 0..nV)
-__global__ void k_colptr(int nV, int nU, const unsigned long long* __restrict__ ukey, int* __restrict__ colptr)
-{
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v > nV) return;
-    const unsigned long long target = (unsigned long long)(unsigned)v << 32;
-    int lo = 0, hi = nU;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (ukey[mid] < target) lo = mid + 1;
+        if (unsigned(key[mid] >> 32) < v) lo = mid + 1;
         else hi = mid;
     }
-    colptr[v] = lo;
+    return lo;
 }
-// per unique block and scalar column l: number of entries, stored l-major inside its block column
-__global__ void k_block_counts(int nU, const unsigned long long* __restrict__ ukey, const unsigned short* __restrict__ umask,
-                               const int* __restrict__ colptr, int* __restrict__ cnt)
+__device__ inline int lower_bound_lo(const unsigned long long* __restrict__ key, int lo, int hi, unsigned v)
 {
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= nU) return;
-    const int vj = int(ukey[u] >> 32);
-    const int s = colptr[vj], nb = colptr[vj + 1] - s;
-    const unsigned m = umask[u];
-#pragma unroll
-    for (int l = 0; l < 3; l++) cnt[3 * (size_t)s + l * nb + (u - s)] = __popc(m & (0x49u << l));
-}
-__global__ void k_fill_csc(int nU, const unsigned long long* __restrict__ ukey, const unsigned short* __restrict__ umask,
-                           const double* __restrict__ ublk, const int* __restrict__ colptr, const int* __restrict__ scan,
-                           int* __restrict__ inner, double* __restrict__ vals)
-{
-    const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= nU) return;
-    const unsigned long long k = ukey[u];
-    const int vj = int(k >> 32), vi = int(k & 0xffffffffu);
-    const int s = colptr[vj], nb = colptr[vj + 1] - s;
-    const unsigned m = umask[u];
-#pragma unroll
-    for (int l = 0; l < 3; l++) {
-        int p = scan[3 * (size_t)s + l * nb + (u - s)];
-#pragma unroll
-        for (int r = 0; r < 3; r++) {
-            if (m & (1u << (3 * r + l))) {
-                inner[p] = 3 * vi + r;
-                vals[p] = ublk[(size_t)u * 9 + 3 * r + l];
-                p++;
-            }
-        }
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (unsigned(key[mid]) < v) lo = mid + 1;
+        else hi = mid;
     }
+    return lo;
 }
-__global__ void k_outer(int nV, const int* __restrict__ colptr, const int* __restrict__ scan, int* __restrict__ outer)
+// per column vertex: first incidence and number of row-block items (2 / 3 / 4 per VV / EV / other incidence)
+__global__ void k_col_ranges(int nV, int nInc, const unsigned long long* __restrict__ inc, unsigned ref_ev, unsigned ref_ee,
+                             int* __restrict__ colinc, int* __restrict__ colR)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v > nV) return;
-    if (v == nV) {
-        outer[3 * (size_t)nV] = scan[3 * (size_t)colptr[nV]];
+    const int s = lower_bound_hi(inc, 0, nInc, unsigned(v));
+    colinc[v] = s;
+    int R = 0;
+    if (v < nV) {
+        const int e = lower_bound_hi(inc, s, nInc, unsigned(v) + 1u);
+        const int b1 = lower_bound_lo(inc, s, e, ref_ev), b2 = lower_bound_lo(inc, b1, e, ref_ee);
+        R = 2 * (b1 - s) + 3 * (b2 - b1) + 4 * (e - b2);
+    }
+    colR[v] = R;
+}
+
+template <int NT> __device__ inline void group_sync()
+{
+    if (NT == 32) __syncwarp();
+    else __syncthreads();
+}
+// bitonic sort of n (power of two) keys by NT cooperating threads
+template <int NT> __device__ inline void bitonic_sort(unsigned long long* keys, int n, int t)
+{
+    for (int k = 2; k <= n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int q = t; q < (n >> 1); q += NT) {
+                const int i = ((q & ~(j - 1)) << 1) | (q & (j - 1)); // index with bit j clear
+                const int p = i | j;
+                const unsigned long long a = keys[i], b = keys[p];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) keys[i] = b, keys[p] = a;
+            }
+            group_sync<NT>();
+        }
+}
+
+struct SymArgs {
+    int nV;
+    const unsigned long long* inc;
+    const int* colinc;
+    const int* colR;
+    const int* itemoff;
+    const int4* vid;
+    const unsigned short* mask;
+    unsigned ref_ev, ref_ee;
+    unsigned* sref;
+    int* cnt;
+};
+
+// Pass 1 for one column by NT threads (t = thread rank).  keys / refs / masks: room for npow2 / R / R.
+template <int NT>
+__device__ inline void column_symbolic(const SymArgs& A, int v, int t, unsigned long long* keys, unsigned* refs, unsigned short* masks,
+                                       int* red /* 3 ints per warp of the group, shared */)
+{
+    const int s = A.colinc[v], e = A.colinc[v + 1], R = A.colR[v];
+    int npow2 = 1;
+    while (npow2 < R) npow2 <<= 1;
+    // item slots: incidences are ordered VV, EV, then 4-point kinds
+    const int b1 = lower_bound_lo(A.inc, s, e, A.ref_ev), b2 = lower_bound_lo(A.inc, b1, e, A.ref_ee);
+    for (int q = s + t; q < e; q += NT) {
+        const unsigned ref = unsigned(A.inc[q]); // gi * 4 + a
+        const unsigned gi = ref >> 2, a = ref & 3u;
+        int np, slot0;
+        if (q < b1) np = 2, slot0 = 2 * (q - s);
+        else if (q < b2) np = 3, slot0 = 2 * (b1 - s) + 3 * (q - b1);
+        else np = 4, slot0 = 2 * (b1 - s) + 3 * (b2 - b1) + 4 * (q - b2);
+        const int4 vv = A.vid[gi];
+        const uint2 mm = *reinterpret_cast<const uint2*>(A.mask + size_t(gi) * HSLOTS + a * 4);
+        const int vi[4] = { vv.x, vv.y, vv.z, vv.w };
+        const unsigned short mk[4] = { (unsigned short)(mm.x & 0xffffu), (unsigned short)(mm.x >> 16), (unsigned short)(mm.y & 0xffffu),
+                                       (unsigned short)(mm.y >> 16) };
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (b < np) {
+                const int slot = slot0 + b;
+                keys[slot] = ((unsigned long long)(unsigned)vi[b] << 32) | unsigned(slot);
+                refs[slot] = gi * HSLOTS + a * 4 + b;
+                masks[slot] = mk[b];
+            }
+    }
+    for (int q = R + t; q < npow2; q += NT) keys[q] = ~0ull;
+    group_sync<NT>();
+    bitonic_sort<NT>(keys, npow2, t);
+    // heads, pattern counts, sorted block references
+    unsigned* sref = A.sref + A.itemoff[v];
+    int c0 = 0, c1 = 0, c2 = 0;
+    for (int q = t; q < R; q += NT) {
+        const unsigned long long k = keys[q];
+        const unsigned row = unsigned(k >> 32);
+        const bool head = q == 0 || unsigned(keys[q - 1] >> 32) != row;
+        sref[q] = refs[unsigned(k)] | (head ? HEAD_BIT : 0u);
+        if (head) {
+            unsigned mk = 0;
+            for (int j = q; j < R && unsigned(keys[j] >> 32) == row; j++) mk |= masks[unsigned(keys[j])];
+            c0 += __popc(mk & 0x49u), c1 += __popc(mk & 0x92u), c2 += __popc(mk & 0x124u);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    if (NT == 32) {
+        if (t == 0) A.cnt[3 * size_t(v)] = c0, A.cnt[3 * size_t(v) + 1] = c1, A.cnt[3 * size_t(v) + 2] = c2;
+    } else {
+        if ((t & 31) == 0) red[3 * (t >> 5)] = c0, red[3 * (t >> 5) + 1] = c1, red[3 * (t >> 5) + 2] = c2;
+        __syncthreads();
+        if (t < 3) {
+            int sum = 0;
+            for (int w = 0; w < NT / 32; w++) sum += red[3 * w + t];
+            A.cnt[3 * size_t(v) + t] = sum;
+        }
+        __syncthreads();
+    }
+}
+
+constexpr int SYM_WARPS = 4;
+__global__ void __launch_bounds__(32 * SYM_WARPS) k_hess_symbolic(SymArgs A, int warp_cap, int* __restrict__ big, unsigned long long* nbig)
+{
+    __shared__ unsigned long long keys[SYM_WARPS][WARP_CAP];
+    __shared__ unsigned refs[SYM_WARPS][WARP_CAP];
+    __shared__ unsigned short masks[SYM_WARPS][WARP_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v = blockIdx.x * SYM_WARPS + warp;
+    if (v > A.nV) return;
+    if (v == A.nV) { // closing entry of the count array
+        if (lane == 0) A.cnt[3 * size_t(v)] = 0;
         return;
     }
-    const int s = colptr[v], nb = colptr[v + 1] - s;
-#pragma unroll
-    for (int l = 0; l < 3; l++) outer[3 * (size_t)v + l] = scan[3 * (size_t)s + l * nb];
+    const int R = A.colR[v];
+    if (R == 0) {
+        if (lane < 3) A.cnt[3 * size_t(v) + lane] = 0;
+        return;
+    }
+    if (R > warp_cap) { // handed to the block-per-column kernel
+        if (lane == 0) big[atomicAdd(nbig, 1ull)] = v;
+        return;
+    }
+    column_symbolic<32>(A, v, lane, keys[warp], refs[warp], masks[warp], nullptr);
 }
+
+constexpr int BIG_THREADS = 256;
+constexpr size_t BIG_SMEM = size_t(CTA_CAP) * (8 + 4 + 2);
+// columns with more than WARP_CAP items: one block per column, looping over the list; columns beyond
+// CTA_CAP sort in a per-block global scratch region (need[0] reports the size required if it is too small)
+__global__ void __launch_bounds__(BIG_THREADS)
+    k_hess_symbolic_big(SymArgs A, int cta_cap, const int* __restrict__ big, const unsigned long long* nbig, char* scratch,
+                        unsigned long long scratch_items, unsigned long long* need)
+{
+    extern __shared__ __align__(16) char smem[];
+    __shared__ int red[3 * BIG_THREADS / 32];
+    const unsigned long long n = *nbig;
+    for (unsigned long long idx = blockIdx.x; idx < n; idx += gridDim.x) {
+        const int v = big[idx];
+        const int R = A.colR[v];
+        int npow2 = 1;
+        while (npow2 < R) npow2 <<= 1;
+        char* base = smem;
+        size_t cap = CTA_CAP;
+        if (R > cta_cap) {
+            if ((unsigned long long)npow2 > scratch_items) {
+                if (threadIdx.x == 0) atomicMax(need, (unsigned long long)npow2);
+                continue; // the host grows the scratch and repeats the assembly
+            }
+            base = scratch + size_t(blockIdx.x) * scratch_items * 14;
+            cap = scratch_items;
+        }
+        unsigned long long* keys = reinterpret_cast<unsigned long long*>(base);
+        unsigned* refs = reinterpret_cast<unsigned*>(base + cap * 8);
+        unsigned short* masks = reinterpret_cast<unsigned short*>(base + cap * 12);
+        column_symbolic<BIG_THREADS>(A, v, threadIdx.x, keys, refs, masks, red);
+        __syncthreads();
+    }
+}
+
+// Pass 2: one warp per column streams its sorted items in chunks of 32
+__global__ void __launch_bounds__(32 * SYM_WARPS)
+    k_hess_numeric(int nV, const int* __restrict__ colR, const int* __restrict__ itemoff, const unsigned* __restrict__ sref,
+                   const int4* __restrict__ vid, const double* __restrict__ blk, const int* __restrict__ outer, int* __restrict__ inner,
+                   double* __restrict__ vals)
+{
+    const int lane = threadIdx.x & 31;
+    const int v = blockIdx.x * SYM_WARPS + (threadIdx.x >> 5);
+    if (v >= nV) return;
+    const int R = colR[v];
+    if (R == 0) return;
+    const unsigned* refs = sref + itemoff[v];
+    int base0 = outer[3 * size_t(v)], base1 = outer[3 * size_t(v) + 1], base2 = outer[3 * size_t(v) + 2];
+    double carry[9];
+    unsigned carry_mask = 0;
+#pragma unroll
+    for (int k = 0; k < 9; k++) carry[k] = 0;
+    for (int q0 = 0; q0 < R; q0 += 32) {
+        const int q = q0 + lane;
+        const bool in = q < R;
+        unsigned ref = 0;
+        bool head = false;
+        double val[9];
+        unsigned mk = 0;
+        if (in) {
+            const unsigned r = refs[q];
+            head = (r & HEAD_BIT) != 0;
+            ref = r & ~HEAD_BIT;
+            const double* bp = blk + size_t(ref) * 9;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                val[k] = __ldg(bp + k);
+                mk |= (val[k] != 0.0) << k;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 9; k++) val[k] = 0;
+        }
+        // the next item's head flag decides where a run ends
+        const unsigned next_ref = (q + 1 < R) ? refs[q + 1] : HEAD_BIT;
+        const bool tail = in && (next_ref & HEAD_BIT) != 0;
+        // segmented inclusive scan (sum of values, OR of masks) in item order; heads start segments
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        // distance to the start of this lane's segment within the chunk (lane + 1 if it began before the chunk)
+        const unsigned below = heads & (0xffffffffu >> (31 - lane));
+        const int seg_start = below ? 31 - __clz(below) : -1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const bool take = lane - o >= seg_start && lane - o >= 0;
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+                const double up = __shfl_up_sync(0xffffffffu, val[k], o);
+                if (take) val[k] += up;
+            }
+            const unsigned um = __shfl_up_sync(0xffffffffu, mk, o);
+            if (take) mk |= um;
+        }
+        if (seg_start < 0) { // the run began in an earlier chunk
+#pragma unroll
+            for (int k = 0; k < 9; k++) val[k] = carry[k] + val[k];
+            mk |= carry_mask;
+        }
+        // entries of the finished runs
+        const int n0 = tail ? __popc(mk & 0x49u) : 0, n1 = tail ? __popc(mk & 0x92u) : 0, n2 = tail ? __popc(mk & 0x124u) : 0;
+        int p0 = n0, p1 = n1, p2 = n2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u0 = __shfl_up_sync(0xffffffffu, p0, o), u1 = __shfl_up_sync(0xffffffffu, p1, o), u2 = __shfl_up_sync(0xffffffffu, p2, o);
+            if (lane >= o) p0 += u0, p1 += u1, p2 += u2;
+        }
+        if (tail) {
+            const int4 vv = vid[ref >> 4];
+            const int b = ref & 3u;
+            const int row = 3 * (b == 0 ? vv.x : (b == 1 ? vv.y : (b == 2 ? vv.z : vv.w)));
+            int w0 = base0 + p0 - n0, w1 = base1 + p1 - n1, w2 = base2 + p2 - n2;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                if (mk & (1u << (3 * r))) inner[w0] = row + r, vals[w0] = val[3 * r], w0++;
+                if (mk & (1u << (3 * r + 1))) inner[w1] = row + r, vals[w1] = val[3 * r + 1], w1++;
+                if (mk & (1u << (3 * r + 2))) inner[w2] = row + r, vals[w2] = val[3 * r + 2], w2++;
+            }
+        }
+        base0 += __shfl_sync(0xffffffffu, p0, 31), base1 += __shfl_sync(0xffffffffu, p1, 31), base2 += __shfl_sync(0xffffffffu, p2, 31);
+        // carry the open run of lane 31 into the next chunk
+        const bool open = !__shfl_sync(0xffffffffu, (int)tail, 31);
+#pragma unroll
+        for (int k = 0; k < 9; k++) carry[k] = open ? __shfl_sync(0xffffffffu, val[k], 31) : 0.0;
+        carry_mask = open ? __shfl_sync(0xffffffffu, mk, 31) : 0u;
+    }
+}
+
 __global__ void k_zero_int(int64_t n, int* p)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -600,97 +874,111 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     cudaStream_t s = ctx->stream;
     const BarrierDev B = make_barrier(bp, ctx->dmin);
     const int nV = ctx->nV;
-    const int np2[4] = { 4, 9, 16, 16 };
-    int64_t nblk = 0, offs[4];
-    for (int k = 0; k < 4; k++) {
-        offs[k] = nblk;
-        nblk += ctx->coll[k].count * np2[k];
-    }
+    const int64_t n0 = ctx->coll[0].count, n1 = ctx->coll[1].count, n2 = ctx->coll[2].count, n3 = ctx->coll[3].count;
+    const int64_t ncoll = n0 + n1 + n2 + n3;
+    const int64_t gi0[4] = { 0, n0, n0 + n1, n0 + n1 + n2 };
+    const int64_t inc0[4] = { 0, 2 * n0, 2 * n0 + 3 * n1, 2 * n0 + 3 * n1 + 4 * n2 };
+    const int64_t ninc = 2 * n0 + 3 * n1 + 4 * (n2 + n3);
+    const int64_t nitems = 4 * n0 + 9 * n1 + 16 * (n2 + n3);
     ctx->outer.reserve(3 * size_t(nV) + 1);
     ctx->nnz = 0;
-    if (nblk == 0) { // empty ndof x ndof matrix (potential.cpp:107-109)
+    if (ncoll == 0) { // empty ndof x ndof matrix (potential.cpp:107-109)
         k_zero_int<<<grid_for(3 * size_t(nV) + 1, 256), 256, 0, s>>>(3 * int64_t(nV) + 1, ctx->outer.p);
         ctx->launches++;
         return;
     }
-    if (nblk > 0x7fffffffll) throw Error("Hessian has more than 2^31 local blocks; shard the collision set");
+    if (ncoll >= (int64_t(1) << 27) || nitems > 0x7fffffffll)
+        throw Error("Hessian: more than 2^27 collisions / 2^31 local blocks on one device; shard the collision set");
     {
         Stage st(ctx, "hessian_local");
-        ctx->hkey.reserve(nblk), ctx->hkey_sorted.reserve(nblk), ctx->hidx.reserve(nblk), ctx->hidx_sorted.reserve(nblk);
-        ctx->hval.reserve(9 * size_t(nblk)), ctx->hmask.reserve(nblk);
+        ctx->hvid.reserve(ncoll), ctx->hmask.reserve(size_t(ncoll) * HSLOTS), ctx->hblk.reserve(size_t(ncoll) * HSLOTS * 9);
+        ctx->hkey.reserve(ninc), ctx->hkey_sorted.reserve(ninc);
+        const HessOut out { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p, ctx->hkey.p };
         const MeshView m = mesh_view(ctx);
-        unsigned long long* hk = ctx->hkey.p;
-        double* hv = ctx->hval.p;
-        unsigned short* hm = ctx->hmask.p;
-        const int64_t n0 = ctx->coll[0].count, n1 = ctx->coll[1].count, n2 = ctx->coll[2].count, n3 = ctx->coll[3].count;
         static const bool force_general = getenv("IPCB_HESSIAN_GENERAL") != nullptr; // A/B switch for tests and profiles
         if (psd_mode == IPCB_PSD_NONE || force_general) {
-            if (n0) k_hessian_local<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, offs[0], hk, hv, hm, nullptr, 0);
-            if (n1) k_hessian_local<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, offs[1], hk, hv, hm, nullptr, 0);
-            if (n2) k_hessian_local<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, offs[2], hk, hv, hm, nullptr, 0);
-            if (n3) k_hessian_local<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, offs[3], hk, hv, hm, nullptr, 0);
-            ctx->launches += 4;
+            if (n0) k_hessian_local<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, nullptr, 0), ctx->launches++;
+            if (n1) k_hessian_local<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, nullptr, 0), ctx->launches++;
+            if (n2) k_hessian_local<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, nullptr, 0), ctx->launches++;
+            if (n3) k_hessian_local<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, nullptr, 0), ctx->launches++;
         } else {
             unsigned long long* slow_count = ctx->dCounters.p + 5;
-            ctx->hhead.reserve(std::max<int64_t>(n2, 1)); // scratch: the slow list (not yet needed by the assembly)
+            ctx->hslow.reserve(std::max<int64_t>(n2, 1));
             IPCB_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(unsigned long long), s));
-            if (n0) k_hessian_fast<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, offs[0], hk, hv, hm, ctx->hhead.p, slow_count);
-            if (n1) k_hessian_fast<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, offs[1], hk, hv, hm, ctx->hhead.p, slow_count);
-            if (n3) k_hessian_fast<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, offs[3], hk, hv, hm, ctx->hhead.p, slow_count);
+            if (n0) k_hessian_fast<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, ctx->hslow.p, slow_count), ctx->launches++;
+            if (n1) k_hessian_fast<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, ctx->hslow.p, slow_count), ctx->launches++;
+            if (n3) k_hessian_fast<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count), ctx->launches++;
             if (n2) {
-                k_hessian_fast<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, offs[2], hk, hv, hm, ctx->hhead.p, slow_count);
+                k_hessian_fast<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, slow_count);
+                ctx->launches++;
                 IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[11], slow_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
                 IPCB_CUDA(cudaStreamSynchronize(s));
                 const int64_t nslow = ctx->pinned.p[11];
                 if (nslow) {
-                    // the list lives in hhead, which the assembly overwrites later: process it now
-                    k_hessian_local<IPCB_EE><<<grid_for(nslow, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, offs[2], hk, hv, hm, ctx->hhead.p, nslow);
+                    k_hessian_local<IPCB_EE><<<grid_for(nslow, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, nslow);
                     ctx->launches++;
                 }
             }
-            ctx->launches += 4;
         }
         IPCB_CUDA(cudaGetLastError());
     }
     Stage st(ctx, "hessian_assemble");
-    int vbits = 0;
-    while ((1ll << vbits) < std::max(nV, 2)) vbits++;
-    k_iota_h<<<grid_for(nblk, 256), 256, 0, s>>>(nblk, ctx->hidx.p);
-    ctx->hhead.reserve(nblk), ctx->hpos.reserve(nblk + 1);
-    size_t b1 = 0, b2 = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b1, ctx->hkey.p, ctx->hkey_sorted.p, ctx->hidx.p, ctx->hidx_sorted.p, nblk, 0, 32 + vbits, s);
-    cub::DeviceScan::ExclusiveSum(nullptr, b2, ctx->hhead.p, ctx->hpos.p, nblk, s);
-    ctx->cubtmp.reserve(std::max(b1, b2) + 1024);
-    cub::DeviceRadixSort::SortPairs(ctx->cubtmp.p, b1, ctx->hkey.p, ctx->hkey_sorted.p, ctx->hidx.p, ctx->hidx_sorted.p, nblk, 0, 32 + vbits,
-                                    s);
-    k_block_heads<<<grid_for(nblk, 256), 256, 0, s>>>(nblk, ctx->hkey_sorted.p, ctx->hhead.p);
-    cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, b2, ctx->hhead.p, ctx->hpos.p, nblk, s);
-    IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[8], ctx->hpos.p + (nblk - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
-    IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[10], ctx->hhead.p + (nblk - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
-    IPCB_CUDA(cudaStreamSynchronize(s));
-    // number of runs = heads before the last element + (1 if the last element starts a run)
-    const int nU = *reinterpret_cast<int*>(&ctx->pinned.p[8]) + *reinterpret_cast<int*>(&ctx->pinned.p[10]);
-    ctx->ukey.reserve(nU), ctx->ublk.reserve(9 * size_t(nU)), ctx->umask.reserve(nU);
-    k_block_reduce<<<grid_for(nblk, 256), 256, 0, s>>>(nblk, ctx->hkey_sorted.p, ctx->hidx_sorted.p, ctx->hhead.p, ctx->hpos.p, ctx->hval.p,
-                                                       ctx->hmask.p, ctx->ukey.p, ctx->ublk.p, ctx->umask.p);
-    ctx->hcolptr.reserve(size_t(nV) + 2);
-    k_colptr<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, nU, ctx->ukey.p, ctx->hcolptr.p);
-    const size_t ncnt = 3 * size_t(nU) + 1;
-    ctx->hcnt.reserve(ncnt), ctx->hscan.reserve(ncnt);
-    k_zero_int<<<grid_for(ncnt, 256), 256, 0, s>>>(int64_t(ncnt), ctx->hcnt.p);
-    k_block_counts<<<grid_for(nU, 256), 256, 0, s>>>(nU, ctx->ukey.p, ctx->umask.p, ctx->hcolptr.p, ctx->hcnt.p);
-    size_t b3 = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, b3, ctx->hcnt.p, ctx->hscan.p, int(ncnt), s);
-    ctx->cubtmp.reserve(b3);
-    cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, b3, ctx->hcnt.p, ctx->hscan.p, int(ncnt), s);
-    IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[9], ctx->hscan.p + (ncnt - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
-    IPCB_CUDA(cudaStreamSynchronize(s));
+    int vbits = 1;
+    while ((1ll << vbits) < nV) vbits++;
+    // 1. incidences grouped by vertex (stable: each column keeps the collision order)
+    size_t b1 = 0, b2 = 0, b3 = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, b1, ctx->hkey.p, ctx->hkey_sorted.p, ninc, 32, 32 + vbits, s);
+    ctx->hcolinc.reserve(size_t(nV) + 2), ctx->hcolR.reserve(size_t(nV) + 2), ctx->hitemoff.reserve(size_t(nV) + 2);
+    ctx->hcnt.reserve(3 * size_t(nV) + 1);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, ctx->hcolR.p, ctx->hitemoff.p, nV + 1, s);
+    cub::DeviceScan::ExclusiveSum(nullptr, b3, ctx->hcnt.p, ctx->outer.p, 3 * nV + 1, s);
+    ctx->cubtmp.reserve(std::max(b1, std::max(b2, b3)) + 1024);
+    cub::DeviceRadixSort::SortKeys(ctx->cubtmp.p, b1, ctx->hkey.p, ctx->hkey_sorted.p, ninc, 32, 32 + vbits, s);
+    ctx->launches += 2 + (vbits + 7) / 8;
+    // 2. column ranges and item offsets
+    const unsigned ref_ev = unsigned(gi0[1] * 4), ref_ee = unsigned(gi0[2] * 4);
+    k_col_ranges<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, int(ninc), ctx->hkey_sorted.p, ref_ev, ref_ee, ctx->hcolinc.p, ctx->hcolR.p);
+    cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, b2, ctx->hcolR.p, ctx->hitemoff.p, nV + 1, s);
+    ctx->launches += 3;
+    // 3. pass 1: per-column sort by row vertex, pattern counts
+    ctx->hsref.reserve(nitems);
+    ctx->hbig.reserve(size_t(nV) + 1);
+    unsigned long long* nbig = ctx->dCounters.p + 6;
+    unsigned long long* need = ctx->dCounters.p + 7;
+    const SymArgs A { nV, ctx->hkey_sorted.p, ctx->hcolinc.p, ctx->hcolR.p, ctx->hitemoff.p, ctx->hvid.p, ctx->hmask.p, ref_ev, ref_ee,
+                      ctx->hsref.p, ctx->hcnt.p };
+    if (!ctx->hess_attr_set) { // per device
+        IPCB_CUDA(cudaFuncSetAttribute(k_hess_symbolic_big, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BIG_SMEM)));
+        ctx->hess_attr_set = true;
+    }
+    const int big_grid = NUM_SMS;
+    // test hooks: lower the hand-over thresholds so that small scenes exercise the block / global-scratch paths
+    int warp_cap = WARP_CAP, cta_cap = CTA_CAP;
+    if (const char* e = getenv("IPCB_HESS_WARP_CAP")) warp_cap = std::min(WARP_CAP, std::max(1, atoi(e)));
+    if (const char* e = getenv("IPCB_HESS_CTA_CAP")) cta_cap = std::min(CTA_CAP, std::max(1, atoi(e)));
+    for (int attempt = 0;; attempt++) {
+        IPCB_CUDA(cudaMemsetAsync(nbig, 0, 2 * sizeof(unsigned long long), s));
+        k_hess_symbolic<<<grid_for(size_t(nV) + 1, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(A, warp_cap, ctx->hbig.p, nbig);
+        k_hess_symbolic_big<<<big_grid, BIG_THREADS, BIG_SMEM, s>>>(A, cta_cap, ctx->hbig.p, nbig, ctx->hscratch.p, ctx->hscratch_items, need);
+        ctx->launches += 2;
+        // 4. scalar column pointers, nnz
+        cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, b3, ctx->hcnt.p, ctx->outer.p, 3 * nV + 1, s);
+        ctx->launches += 2;
+        IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[9], ctx->outer.p + 3 * size_t(nV), sizeof(int), cudaMemcpyDeviceToHost, s));
+        IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[10], need, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        IPCB_CUDA(cudaStreamSynchronize(s));
+        const size_t want = size_t(ctx->pinned.p[10]);
+        if (want == 0) break;
+        if (attempt > 0) throw Error("Hessian: sort scratch for a huge column could not be provided");
+        ctx->hscratch.reserve(want * 14 * size_t(big_grid)); // a vertex with more than CTA_CAP row blocks: sort in global memory
+        ctx->hscratch_items = want;
+    }
     ctx->nnz = *reinterpret_cast<int*>(&ctx->pinned.p[9]);
-    ctx->inner.reserve(ctx->nnz), ctx->vals.reserve(ctx->nnz);
-    k_fill_csc<<<grid_for(nU, 256), 256, 0, s>>>(nU, ctx->ukey.p, ctx->umask.p, ctx->ublk.p, ctx->hcolptr.p, ctx->hscan.p, ctx->inner.p,
-                                                 ctx->vals.p);
-    k_outer<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, ctx->hcolptr.p, ctx->hscan.p, ctx->outer.p);
-    ctx->launches += 9 + 12;
+    ctx->inner.reserve(std::max<int64_t>(ctx->nnz, 1)), ctx->vals.reserve(std::max<int64_t>(ctx->nnz, 1));
+    // 5. pass 2: gather, run-sum, write compressed columns
+    k_hess_numeric<<<grid_for(nV, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hvid.p, ctx->hblk.p,
+                                                                       ctx->outer.p, ctx->inner.p, ctx->vals.p);
+    ctx->launches++;
     IPCB_CUDA(cudaGetLastError());
 }
 

@@ -115,6 +115,19 @@ def perturbed_sheets(layers=4, n=64, spacing=2.0, disp=5.0, seed=4):
     return V0, V1, _edges(F), F, {"dhat": 0.6 * spacing * h}
 
 
+def dense_sheet(n=16, dhat_cells=3.0, seed=6):
+    """one jittered n x n sheet whose dhat spans `dhat_cells` cells: every vertex is in contact with
+    hundreds of primitives of its own sheet (stress for per-vertex work such as Hessian columns with
+    thousands of row blocks)"""
+    rng = np.random.default_rng(seed)
+    h = 1.0 / n
+    V, F = grid_sheet(n, n, 1.0)
+    V[:, :2] += rng.uniform(-0.2, 0.2, (V.shape[0], 2)) * h
+    V[:, 2] = rng.uniform(-0.3, 0.3, V.shape[0]) * h
+    V1 = V + rng.normal(0, 0.3, V.shape) * h
+    return V, V1, _edges(F), F, {"dhat": dhat_cells * h}
+
+
 def random_soup(n_tris=200, seed=0, scale=0.15):
     """small random triangle soup (every triangle has its own 3 vertices) — dense, irregular contact"""
     rng = np.random.default_rng(seed)

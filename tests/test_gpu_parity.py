@@ -19,6 +19,9 @@ def _scene(scenes, name):
         "stack_tight": lambda: scenes.cloth_stack(4, 20, gap=0.2),
         "soup": lambda: scenes.random_soup(150, seed=7),
         "sheets": lambda: scenes.perturbed_sheets(3, 16),
+        # Hessian columns with thousands of row blocks: block-per-column sort in shared memory / in global scratch
+        "dense3": lambda: scenes.dense_sheet(16, 3.0),
+        "dense6": lambda: scenes.dense_sheet(14, 6.0),
     }[name]()
 
 
@@ -65,7 +68,7 @@ def test_broad_phase_all_kinds(cuda, oracle, scenes, name, swept):
         assert len(np.unique(a, axis=0)) == len(a), "duplicate candidates"  # test_lbvh.cpp:142-149
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", SCENES + ["dense3", "dense6"])
 def test_collision_set_and_potential(cuda, oracle, scenes, name):
     V0, V1, E, F, P = _scene(scenes, name)
     dhat = P["dhat"]
@@ -128,6 +131,25 @@ def test_step_size(cuda, oracle, scenes, name):
             assert oracle.is_step_collision_free(mesh, V0, V0 + 0.999 * ti_g * (V1 - V0), md)
 
 
+@pytest.mark.parametrize("caps", [(64, 8192), (32, 128)])
+def test_hessian_big_column_paths(cuda, oracle, scenes, caps, monkeypatch):
+    """columns beyond one warp's shared memory go to the block-per-column kernel, columns beyond a block's shared
+    memory sort in global scratch: force both hand-overs on a small scene and compare with the oracle"""
+    V0, V1, E, F, P = scenes.dense_sheet(14, 6.0)
+    monkeypatch.setenv("IPCB_HESS_WARP_CAP", str(caps[0]))
+    monkeypatch.setenv("IPCB_HESS_CTA_CAP", str(caps[1]))
+    res = []
+    for api in (cuda, oracle):
+        mesh = api.CollisionMesh(V0, E, F)
+        c = api.NormalCollisions()
+        c.build(mesh, V0, P["dhat"])
+        B = api.BarrierPotential(P["dhat"], 1.0)
+        res.append([B.hessian(c, mesh, V0, m) for m in (api.PSDProjectionMethod.NONE, api.PSDProjectionMethod.CLAMP)])
+    for A, Bm in zip(*res):
+        assert np.array_equal(A.indptr, Bm.indptr) and np.array_equal(A.indices, Bm.indices)
+        assert relerr(A.data, Bm.data) <= RTOL
+
+
 def test_codim_known_answers(cuda):
     """collisions/test_normal_collisions.cpp:14-107 and :109-209 of the reference, through the CUDA path"""
     V = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]], float)
@@ -168,7 +190,7 @@ def test_narrow_phase_matches_oracle(cuda, oracle):
     rng = np.random.default_rng(5)
     for kind in (0, 1, 2, 3):
         n = 400 if kind >= 2 else 60
-        a = rng.uniform(-1, 1, (n, 4, 3))
+        a = rng.uniform(-1, 1, (n, 4, 3)) * (1.0 if kind >= 2 else 0.4)  # points / point-edge pairs need to start closer to meet
         b = a + rng.normal(0, 0.6, (n, 4, 3))
         # point-point / point-edge only meet with a real thickness; a coarser tolerance keeps the
         # sequential oracle fast there (the work grows with min_distance / tolerance)
