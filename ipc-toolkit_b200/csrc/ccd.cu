@@ -327,37 +327,11 @@ __host__ __device__ inline int ti_step(const double* s, const double* e, int is_
     return 2;
 }
 
-// Level-0 culling, consistent with the root finder: returns true when NO box inside
-// [0,tmax] x [0,1]^2 can ever be reported.
-//  (1) the co-domain box of the root clipped to the search window misses the eps-cube (every
-//      sub-box's co-domain box is contained in it);
-//  (2) a separating direction n: n.F is multilinear in (t,u,v), so it is bounded by its 8 corner
-//      values; if all of them exceed ||n||_1 (ms + err + delta) in magnitude with one sign, no
-//      point of the window has |F_c| <= ms + err_c + delta for all c, and a terminal box (co-domain
-//      width <= delta, or inside the cube) cannot exist.
-__host__ __device__ inline bool ti_cull(const double* s, const double* e, int is_vf, const TIParams& P, double tmax)
+// separating direction test over the window [0, tmax] x [0,1]^2 with a uniform margin (see ti_cull (2)).
+// n.F at the 8 corners of the window only needs the projections of the 4 points at t = 0 and t = tmax:
+// edge-edge corners are a_i - b_j, vertex-face corners p - {t0, t1, t2, t1 + t2 - t0}.
+__host__ __device__ inline bool ti_separated(const d3* p0, const d3* e4, int is_vf, double tmax, double margin)
 {
-    const double tt[2] = { 0.0, tmax }, unit[2] = { 0.0, 1.0 };
-    bool box_in;
-    double tw[3];
-    if (!ti_inclusion(s, e, is_vf, P, tt, unit, unit, box_in, tw)) return true;
-    // corner values of F at t = 0 and t = tmax
-    d3 Fc[8];
-    d3 p0[4], p1[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        p0[k] = getp(s, k);
-        const d3 ek = getp(e, k);
-        p1[k] = { (ek.x - p0[k].x) * tmax + p0[k].x, (ek.y - p0[k].y) * tmax + p0[k].y, (ek.z - p0[k].z) * tmax + p0[k].z };
-    }
-    if (is_vf) { // p - {t0, t1, t2, t1 + t2 - t0}: the root finder's (u,v) domain is the parallelogram
-        Fc[0] = p0[0] - p0[1], Fc[1] = p0[0] - p0[2], Fc[2] = p0[0] - p0[3], Fc[3] = p0[0] - (p0[2] + p0[3] - p0[1]);
-        Fc[4] = p1[0] - p1[1], Fc[5] = p1[0] - p1[2], Fc[6] = p1[0] - p1[3], Fc[7] = p1[0] - (p1[2] + p1[3] - p1[1]);
-    } else {
-        Fc[0] = p0[0] - p0[2], Fc[1] = p0[0] - p0[3], Fc[2] = p0[1] - p0[2], Fc[3] = p0[1] - p0[3];
-        Fc[4] = p1[0] - p1[2], Fc[5] = p1[0] - p1[3], Fc[6] = p1[1] - p1[2], Fc[7] = p1[1] - p1[3];
-    }
-    const double margin = (fmax(fmax(P.err[0], P.err[1]), P.err[2]) + P.ms + P.co_tol) * (1.0 + 1e-9);
     d3 axes[4];
     int na;
     if (is_vf) {
@@ -374,13 +348,48 @@ __host__ __device__ inline bool ti_cull(const double* s, const double* e, int is
         const double l1 = (fabs(n.x) + fabs(n.y) + fabs(n.z)) * margin;
         double mn = INFINITY, mx = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const double v = dot(n, Fc[k]);
-            mn = fmin(mn, v), mx = fmax(mx, v);
+        for (int t = 0; t < 2; t++) {
+            double pr[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const double d0 = dot(n, p0[k]);
+                pr[k] = t == 0 ? d0 : (dot(n, e4[k]) - d0) * tmax + d0;
+            }
+            double lo, hi;
+            if (is_vf) {
+                const double q = pr[2] + pr[3] - pr[1];
+                lo = pr[0] - fmax(fmax(pr[1], pr[2]), fmax(pr[3], q));
+                hi = pr[0] - fmin(fmin(pr[1], pr[2]), fmin(pr[3], q));
+            } else {
+                lo = fmin(pr[0], pr[1]) - fmax(pr[2], pr[3]);
+                hi = fmax(pr[0], pr[1]) - fmin(pr[2], pr[3]);
+            }
+            mn = fmin(mn, lo), mx = fmax(mx, hi);
         }
         if (mn > l1 || mx < -l1) return true;
     }
     return false;
+}
+
+// Level-0 culling, consistent with the root finder: returns true when NO box inside
+// [0,tmax] x [0,1]^2 can ever be reported.
+//  (1) the co-domain box of the root clipped to the search window misses the eps-cube (every
+//      sub-box's co-domain box is contained in it);
+//  (2) a separating direction n: n.F is multilinear in (t,u,v), so it is bounded by its 8 corner
+//      values; if all of them exceed ||n||_1 (ms + err + delta) in magnitude with one sign, no
+//      point of the window has |F_c| <= ms + err_c + delta for all c, and a terminal box (co-domain
+//      width <= delta, or inside the cube) cannot exist.
+__host__ __device__ inline bool ti_cull(const double* s, const double* e, int is_vf, const TIParams& P, double tmax)
+{
+    const double tt[2] = { 0.0, tmax }, unit[2] = { 0.0, 1.0 };
+    bool box_in;
+    double tw[3];
+    if (!ti_inclusion(s, e, is_vf, P, tt, unit, unit, box_in, tw)) return true;
+    d3 p0[4], e4[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) p0[k] = getp(s, k), e4[k] = getp(e, k);
+    const double margin = (fmax(fmax(P.err[0], P.err[1]), P.err[2]) + P.ms + P.co_tol) * (1.0 + 1e-9);
+    return ti_separated(p0, e4, is_vf, tmax, margin);
 }
 
 struct TIQueue {
@@ -446,11 +455,55 @@ __device__ inline unsigned long long warp_reserve(unsigned long long* counter, b
     return base + (incl - mine);
 }
 
+// Pre-filter, one thread per candidate with few registers (high occupancy; the positions are L2
+// resident): a candidate whose swept stencil is separated along one of the primitive's own
+// directions by more than the LARGEST margin any root-finder run on it could use
+//   err (floating-point filter, ms > 0 variant) + min_distance + 1e-4 (cap of the minimum effective
+//   distance, tight_inclusion_ccd.cpp:48) + tolerance (>= the adjusted co-domain tolerance)
+// can neither start closer than min_distance nor produce a terminal box (see ti_cull), so it is
+// dropped here; survivors are compacted into `list` for the full per-query kernel.
+__global__ void __launch_bounds__(256, 3)
+    k_ti_filter(QuerySource q, double min_distance, double tmax_in, double tolerance, CcdOut out, int* __restrict__ list,
+                unsigned long long* nlist)
+{
+    const unsigned long long* bound = out.bound;
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    bool keep = false;
+    if (i < q.n) {
+        keep = true;
+        if (q.kind >= IPCB_EE) { // point-point / point-edge queries are few (codimensional): always kept
+            d3 a[4], b[4];
+            load_query(q, i, a, b);
+            double mx = 1.0;
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                mx = fmax(mx, fmax(fmax(fmax(fabs(a[k].x), fabs(a[k].y)), fabs(a[k].z)), fmax(fmax(fabs(b[k].x), fabs(b[k].y)), fabs(b[k].z))));
+            const int is_vf = q.kind == IPCB_FV;
+            const double err = (is_vf ? 7.549516567451064e-15 : 7.105427357601002e-15) * mx * mx * mx;
+            const double margin = (err + min_distance + 1e-4 + tolerance) * (1.0 + 1e-9);
+            const double tmax = bound ? fmin(tmax_in, load_bound(bound)) : tmax_in;
+            keep = !ti_separated(a, b, is_vf, tmax, margin);
+            if (!keep) report(out, i, false, 0.0);
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(nlist, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (keep) list[base + __popc(m & ((1u << lane) - 1))] = int(i);
+    }
+}
+
 // tight_inclusion_ccd.cpp:222-336 + ccd_strategy :33-75, one thread per query
 __global__ void __launch_bounds__(128)
-    k_ti_query(QuerySource q, double min_distance, double tmax_in, double tolerance, double rescale, int budget, TIQueue Z, CcdOut out)
+    k_ti_query(QuerySource q, const int* __restrict__ list, int64_t nlist, double min_distance, double tmax_in, double tolerance, double rescale,
+               int budget, TIQueue Z, CcdOut out)
 {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool active = tid < nlist;
+    const int64_t i = active ? list[tid] : 0;
     bool spill = false;
     double s[12], e[12];
     TIParams P;
@@ -459,7 +512,7 @@ __global__ void __launch_bounds__(128)
     int is_vf = 0;
     int spill_flags = 0;
     double best = INFINITY;
-    if (i < q.n) {
+    if (active) {
         d3 a[4], b[4];
         const int n = load_query(q, i, a, b);
         const double d0 = sqrt(auto_distance(q.kind, a));
@@ -651,6 +704,7 @@ struct TIWork {
     Buf<unsigned long long> qtoi;
     Buf<int> qflags;
     Buf<TIUnit> ua, ub;
+    Buf<int> list; // candidates that survive the pre-filter
 };
 static std::map<ipcb_ctx*, TIWork*> g_work; // one per context
 
@@ -712,6 +766,14 @@ static void ti_run(ipcb_ctx* ctx, const QuerySource& src, double min_distance, d
     size_t qcap = std::max<size_t>(W.queries.cap, 1024);
     size_t ucap = std::max<size_t>(W.ua.cap, size_t(1) << 16);
     unsigned long long nq = 0, nunits = 0;
+    // ---- pre-filter: most broad-phase candidates are separated along one of their own directions
+    if (src.n > 0x7fffffffll) throw Error("ccd: more than 2^31 candidates of one kind");
+    W.list.reserve(src.n);
+    IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
+    k_ti_filter<<<grid_for(src.n, 256), 256, 0, s>>>(src, min_distance, tmax, p.tolerance, out, W.list.p, cnt);
+    ctx->launches++;
+    const int64_t nlist = int64_t(read_counter(ctx, cnt));
+    if (nlist == 0) return;
     for (int attempt = 0;; attempt++) {
         W.queries.reserve(qcap), W.qtoi.reserve(qcap), W.qflags.reserve(qcap);
         W.ua.reserve(ucap), W.ub.reserve(ucap);
@@ -719,7 +781,8 @@ static void ti_run(ipcb_ctx* ctx, const QuerySource& src, double min_distance, d
         ucap = std::min(W.ua.cap, W.ub.cap);
         IPCB_CUDA(cudaMemsetAsync(nq_d, 0, 2 * sizeof(unsigned long long), s)); // nq and the unit counter
         TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, W.ua.p, cnt, (unsigned long long)ucap };
-        k_ti_query<<<grid_for(src.n, 128), 128, 0, s>>>(src, min_distance, tmax, p.tolerance, p.conservative_rescaling, dfs_budget(), Z, out);
+        k_ti_query<<<grid_for(nlist, 128), 128, 0, s>>>(src, W.list.p, nlist, min_distance, tmax, p.tolerance, p.conservative_rescaling,
+                                                        dfs_budget(), Z, out);
         ctx->launches++;
         IPCB_CUDA(cudaGetLastError());
         nq = read_counter(ctx, nq_d);

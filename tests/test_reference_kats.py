@@ -1,0 +1,380 @@
+"""Pins the CPU oracle against the reference's own known-answer / property tests, transcribed in
+tests/kats.py with the reference file:line of every case.  CPU only; the GPU versions of the same vectors are in
+tests/test_gpu_kats.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import kats
+
+
+def _p(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def dtype_of(o, kind, pts):
+    a, p = _p(np.concatenate([np.asarray(x, float) for x in pts]))
+    return o.cdll.ipco_unit_distance_type(kind, p)
+
+
+def distance(o, kind, pts, dtype=-1, derivs=False):
+    a, p = _p(np.concatenate([np.asarray(x, float) for x in pts] + [np.zeros(12 - 3 * len(pts))]))
+    val = C.c_double()
+    g, gp = _p(np.zeros(12))
+    h, hp = _p(np.zeros(144))
+    rc = o.cdll.ipco_unit_distance(kind, p, dtype, C.byref(val), gp, hp)
+    assert rc == 0
+    return (val.value, g, h.reshape(12, 12).T) if derivs else val.value
+
+
+# ---- distance types -------------------------------------------------------------------------------
+def test_point_edge_distance_type(oracle):
+    for p, e0, e1, ok in kats.point_edge_type_cases():
+        assert dtype_of(oracle, 1, (p, e0, e1)) in ok
+
+
+def test_point_triangle_distance_type(oracle):
+    for p, t0, t1, t2, expected in kats.point_triangle_type_cases():
+        assert dtype_of(oracle, 3, (p, t0, t1, t2)) == expected, (p, expected)
+
+
+def test_edge_edge_distance_type_and_distance(oracle):
+    for gen in (kats.edge_edge_not_ea_eb_cases, kats.edge_edge_ea_eb_cases, kats.edge_edge_parallel_cases):
+        for a0, a1, b0, b1, ok, d2 in gen():
+            if ok is not None:
+                assert dtype_of(oracle, 2, (a0, a1, b0, b1)) in ok
+            d = distance(oracle, 2, (a0, a1, b0, b1))
+            assert d == pytest.approx(d2, abs=1e-12, rel=1e-9)
+            if ok is None:  # test_edge_edge.cpp:206-211: AUTO is never larger than any explicit vertex / edge type
+                for t in range(8):
+                    assert d <= distance(oracle, 2, (a0, a1, b0, b1), t) * (1 + 1e-9) + 1e-15
+
+
+def test_edge_edge_coplanar_regression(oracle):
+    for a0, a1, b0, b1, required, expected in kats.edge_edge_coplanar_regression():
+        t = dtype_of(oracle, 2, (a0, a1, b0, b1))
+        assert t != kats.EA_EB
+        if required is not None:
+            assert t == required
+        d = distance(oracle, 2, (a0, a1, b0, b1))
+        assert d > 0 and np.isfinite(d)
+        if expected is not None:
+            assert d == pytest.approx(expected, abs=1e-10)
+
+
+# ---- distances -----------------------------------------------------------------------------------
+def test_point_triangle_distance(oracle):
+    for p, t0, t1, t2, cp in kats.point_triangle_distance_cases():
+        assert distance(oracle, 3, (p, t0, t1, t2)) == pytest.approx(float(np.sum((p - cp) ** 2)), abs=1e-12, rel=1e-12)
+
+
+def test_edge_edge_distance(oracle):
+    for e00, e01, e10, e11, d2 in kats.edge_edge_distance_grid() + kats.edge_edge_degenerate_cases():
+        assert distance(oracle, 2, (e00, e01, e10, e11)) == pytest.approx(d2, abs=1e-12, rel=1e-12)
+
+
+def _fd_grad(f, x, h=1e-7):
+    g = np.zeros_like(x)
+    for i in range(x.size):
+        e = np.zeros_like(x)
+        e[i] = h * max(1.0, abs(x[i]))
+        g[i] = (f(x + e) - f(x - e)) / (2 * e[i])
+    return g
+
+
+def test_distance_derivatives_match_finite_differences(oracle):
+    """the reference checks every gradient / Hessian against finite differences (distance/test_*.cpp "gradient"/"hessian"
+    cases); same check on random stencils for every kind and every explicit distance type"""
+    rng = np.random.default_rng(3)
+    for kind, npts, ntypes in ((0, 2, 1), (1, 3, 3), (2, 4, 9), (3, 4, 7)):
+        for t in range(ntypes):
+            for _ in range(3):
+                x = rng.uniform(-1, 1, 3 * npts)
+                dt = -1 if kind == 0 else t
+                val, g, H = distance(oracle, kind, x.reshape(-1, 3), dt, derivs=True)
+                f = lambda y: distance(oracle, kind, y.reshape(-1, 3), dt)
+                fg = _fd_grad(f, x)
+                assert np.allclose(g[: 3 * npts], fg, rtol=1e-5, atol=1e-6)
+                fH = np.array([_fd_grad(lambda y, i=i: distance(oracle, kind, y.reshape(-1, 3), dt, derivs=True)[1][i], x) for i in range(3 * npts)])
+                assert np.allclose(H[: 3 * npts, : 3 * npts], fH, rtol=1e-4, atol=1e-5)
+
+
+# ---- mollifier, barrier, PSD, Morton -----------------------------------------------------------------------
+def test_edge_edge_mollifier(oracle):
+    """distance/test_edge_edge_mollifier.cpp:18-292"""
+    cd = oracle.cdll
+    perp = np.array([[-1.0, 0, 0], [1, 0, 0], [0, -1, 0], [0, 1, 0]])
+    almost = np.array([[-1.0, 0, 0], [1, 0, 0], [-1, 1e-9, 0], [1, -1e-9, 0]])
+    rest = np.array([[0.0, 0, 0], [1, 0, 0], [0, 0, 0], [0, 1, 0]])
+
+    def moll(x, eps):
+        a, p = _p(x)
+        out, op = _p(np.zeros(2))
+        g, gp = _p(np.zeros(12))
+        h, hp = _p(np.zeros(144))
+        cd.ipco_unit_mollifier(p, eps, op, gp, hp)
+        return out[0], out[1], g, h.reshape(12, 12).T
+
+    assert moll(perp, 1.0)[0] == pytest.approx(16)  # cross squared norm, :22-27
+    assert moll(almost, 1.0)[0] == pytest.approx(0, abs=1e-9)
+    for edges in (perp, almost):
+        a, p = _p(edges)
+        assert cd.ipco_unit_mollifier_threshold(p) == pytest.approx(0.016)  # :255-260
+    eps_x = cd.ipco_unit_mollifier_threshold(_p(rest)[1])
+    for edges in (perp, almost):
+        s, m, g, H = moll(edges, eps_x)
+        assert 0 <= m <= 1
+        x = edges.ravel()
+        fg = _fd_grad(lambda y: moll(y.reshape(4, 3), eps_x)[1], x)
+        assert np.allclose(g, fg, rtol=1e-5, atol=1e-6 * max(1, np.abs(fg).max()))
+        fH = np.array([_fd_grad(lambda y, i=i: moll(y.reshape(4, 3), eps_x)[2][i], x) for i in range(12)])
+        assert np.allclose(H, fH, rtol=1e-4, atol=1e-5 * max(1, np.abs(fH).max()))
+    # scalar mollifier (:82-160) through a perpendicular pair scaled so that its cross norm equals x
+    for rel_x in (0, 0.5, 1, 2):
+        for eps in (1e-3, 1e-1, 1, 2):
+            x = rel_x * eps
+            L = np.sqrt(np.sqrt(x)) if x > 0 else 0.0  # |u x v|^2 = L^4 for perpendicular edges of length L
+            e = np.array([[0.0, 0, 0], [L, 0, 0], [0, 0, 1], [0, L, 1]])
+            s, m, _, _ = moll(e, eps)
+            assert s == pytest.approx(x, rel=1e-12, abs=1e-300)
+            assert 0 <= m <= 1
+            if x > eps:
+                assert m == 1
+            else:
+                assert m == pytest.approx((-x / eps + 2) * (x / eps))
+
+
+def test_barrier_derivatives(oracle):
+    """barrier/test_barrier.cpp:398-462 (ClampedLogBarrier section) + :11-43 of barrier.cpp"""
+    cd = oracle.cdll
+
+    def b(d, dhat):
+        out, op = _p(np.zeros(3))
+        cd.ipco_unit_barrier(d, dhat, op)
+        return out
+
+    for use_sqr in (False, True):
+        for e in range(-2 if use_sqr else -5, 0):
+            dhat = 10.0 ** e
+            for d in np.arange(0.5 * dhat, 0.9 * dhat, (0.9 - 0.5) / 10.0 * dhat)[:10]:
+                dd, hh = (d * d, dhat * dhat) if use_sqr else (d, dhat)
+                h = 1e-7 * dd
+                f0, f1, f2 = b(dd, hh)
+                assert f1 == pytest.approx((b(dd + h, hh)[0] - b(dd - h, hh)[0]) / (2 * h), rel=1e-5)
+                assert f2 == pytest.approx((b(dd + h, hh)[1] - b(dd - h, hh)[1]) / (2 * h), rel=1e-5)
+    assert b(1.0, 1.0)[0] == 0 and b(2.0, 1.0).tolist() == [0, 0, 0] and np.isinf(b(0.0, 1.0)[0])
+
+
+def test_project_to_psd(oracle):
+    """utils/test_utils.cpp:27-48"""
+    cd = oracle.cdll
+
+    def psd(A, mode):
+        a, p = _p(np.array(A, float).T.copy())
+        assert cd.ipco_unit_project_to_psd(a.shape[0], p, mode) == 0
+        return a.T
+
+    I3 = np.eye(3)
+    assert np.allclose(psd(I3, 1), I3) and np.allclose(psd(I3, 2), I3)
+    assert np.allclose(psd(-I3, 1), 0)
+    A = [[2, 1], [1, 2]]
+    assert np.allclose(psd(A, 1), A) and np.allclose(psd(A, 2), A)
+    assert np.allclose(psd([[1, 2], [2, 1]], 1), 1.5 * np.ones((2, 2)))  # eigenvalues -1, 3
+    assert np.allclose(psd([[1, 2], [2, 1]], 2), [[2, 1], [1, 2]])
+    rng = np.random.default_rng(0)
+    for n in (6, 9, 12):
+        M = rng.normal(size=(n, n))
+        M = M + M.T
+        w, V = np.linalg.eigh(M)
+        assert np.allclose(psd(M, 1), (V * np.maximum(w, 0)) @ V.T, atol=1e-12)
+        assert np.allclose(psd(M, 2), (V * np.abs(w)) @ V.T, atol=1e-12)
+
+
+def test_morton_code(oracle):
+    """math/morton.hpp:23-63 compiled standalone from the reference tree gives 0x5600000000000000"""
+    assert oracle.cdll.ipco_unit_morton_3D(0.5, 0.25, 0.75) == 0x5600000000000000
+
+
+# ---- broad phase, collisions, potential, step size (shared with the GPU tests) --------------------------------------
+def check_broad_phase_kats(api):
+    """broad_phase/test_broad_phase.cpp:116-137 (2D embedded at z = 0), :207-231/:246-253 (crossing edges), :273-294
+    (100 chained boxes -> 99 vertex-vertex candidates)"""
+    V0 = np.array([[1.11111, 0.5, 0], [1.11111, 0.75, 0], [1, 0.5, 0], [1, 0.75, 0]])
+    V1 = V0.copy()
+    V1[:2, 0] = 0.888889
+    E = np.array([[1, 0], [2, 3]])
+    mesh = api.CollisionMesh(V0, E)
+    cand = api.Candidates()
+    cand.build(mesh, V0, V1, 0.0)
+    assert len(cand.ee_candidates) == 1  # the two edges sweep through each other
+    assert not cand.is_step_collision_free(mesh, V0, V1)
+
+    V0 = np.array([[-1.0, -1, 0], [1, -1, 0], [0, 1, 1], [0, 1, -1]])
+    U = np.zeros_like(V0)
+    U[:2, 1], U[2:, 1] = 2, -2
+    E = np.array([[0, 1], [2, 3]])
+    mesh = api.CollisionMesh(V0, E)
+    cand = api.Candidates()
+    cand.build(mesh, V0, V0 + U, 0.0)
+    assert [tuple(c) for c in cand.ee_candidates] == [(0, 1)]
+    toi = cand.compute_collision_free_stepsize(mesh, V0, V0 + U)
+    assert 0.4 < toi <= 0.5  # the edges meet at t = 0.5
+
+    Vc = np.zeros((100, 3))
+    Vc[:, 0] = 0.6 * np.arange(100) + 0.5
+    mesh = api.CollisionMesh(Vc)
+    cand = api.Candidates()
+    cand.build(mesh, Vc, None, 0.5)
+    assert len(cand.vv_candidates) == 99 and cand.size() == 99
+
+
+def check_codim_kats(api):
+    """collisions/test_normal_collisions.cpp:14-107 and :109-209"""
+    V = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]], float)
+    V -= V.mean(0)
+    mesh = api.CollisionMesh(V)
+    assert (mesh.num_vertices(), mesh.num_codim_vertices(), mesh.num_edges(), mesh.num_faces()) == (8, 8, 0, 0)
+    for area in (False, True):
+        for physical in (False, True):
+            c = api.NormalCollisions()
+            c.set_use_area_weighting(area)
+            c.build(mesh, V, 0.25, 0.8)
+            assert c.counts() == [12, 0, 0, 0]
+            B = api.BarrierPotential(0.25, 1.0, physical)
+            assert B(c, mesh, V) > 0
+            f = -B.gradient(c, mesh, V).reshape(-1, 3)
+            assert np.allclose(f / np.linalg.norm(f, axis=1, keepdims=True), V / np.linalg.norm(V, axis=1, keepdims=True))
+    V1 = V.copy()
+    V1[:, 1] *= 0.5
+    cand = api.Candidates()
+    cand.build(mesh, V, V1, 0.4)
+    assert cand.size() == len(cand.vv_candidates) > 0
+    assert not cand.is_step_collision_free(mesh, V, V1, 0.8)
+    assert cand.compute_collision_free_stepsize(mesh, V, V1, 0.8) == pytest.approx((1 - (0.8 + 1e-4)) / 2 / 0.25, rel=1.2e-5)
+
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 0, -1], [-1, 0, 0], [0, 0, 1], [0, 1, 0], [0, 2, 0], [0, 3, 0]], float)
+    E = np.array([[0, 1], [0, 2], [0, 3], [0, 4]])
+    mesh = api.CollisionMesh(V, E)
+    assert (mesh.num_codim_vertices(), mesh.num_codim_edges(), mesh.num_edges(), mesh.num_faces()) == (3, 4, 4, 0)
+    V1 = V.copy()
+    V1[5:, 1] -= 4
+    cand = api.Candidates()
+    cand.build(mesh, V, V1, 1e-3)
+    assert [len(cand.vv_candidates), len(cand.ev_candidates), len(cand.ee_candidates), len(cand.fv_candidates)] == [3, 12, 0, 0]
+    assert not cand.is_step_collision_free(mesh, V, V1, 2e-3)
+    assert cand.compute_collision_free_stepsize(mesh, V, V1, 2e-3) == pytest.approx((1 - (2e-3 + 1e-4)) / 4, rel=1.2e-5)
+    for area in (False, True):
+        c = api.NormalCollisions()
+        c.set_use_area_weighting(area)
+        c.build(mesh, V, 0.25, 0.8)
+        assert c.counts() == [2, 4, 0, 0]
+        assert api.BarrierPotential(0.25, 1.0)(c, mesh, V) > 0
+
+
+def check_barrier_potential_scenes(api):
+    """potential/test_barrier_potential.cpp:133-245: collisions exist and the gradient / Hessian match finite differences
+    of the potential on the SAME collision set"""
+    for name, (V, E, F, dhat) in kats.barrier_potential_scenes().items():
+        if E is None:
+            E = api_edges(F)
+        mesh = api.CollisionMesh(V, E, F)
+        for area in (False, True):
+            for physical in (False, True):
+                c = api.NormalCollisions()
+                c.set_use_area_weighting(area)
+                c.build(mesh, V, dhat)
+                assert not c.empty(), name
+                B = api.BarrierPotential(dhat, 1.0, physical)
+                g = B.gradient(c, mesh, V)
+                H = B.hessian(c, mesh, V).toarray()
+                x = V.ravel().copy()
+                h = 1e-9
+                fg = np.zeros_like(x)
+                fH = np.zeros((x.size, x.size))
+                for i in range(x.size):
+                    e = np.zeros_like(x)
+                    e[i] = h
+                    fg[i] = (B(c, mesh, (x + e).reshape(V.shape)) - B(c, mesh, (x - e).reshape(V.shape))) / (2 * h)
+                    fH[:, i] = (B.gradient(c, mesh, (x + e).reshape(V.shape)) - B.gradient(c, mesh, (x - e).reshape(V.shape))) / (2 * h)
+                assert np.allclose(g, fg, rtol=2e-4, atol=1e-6 * np.abs(fg).max()), name
+                assert np.allclose(H, fH, rtol=2e-3, atol=1e-5 * np.abs(fH).max()), name
+                assert np.allclose(H, H.T, atol=1e-12 * np.abs(H).max())
+                Hp = B.hessian(c, mesh, V, 1).toarray()
+                assert np.linalg.eigvalsh(0.5 * (Hp + Hp.T)).min() >= -1e-9 * np.abs(Hp).max()
+
+
+def api_edges(F):
+    e = np.concatenate([F[:, [0, 1]], F[:, [1, 2]], F[:, [2, 0]]]).astype(np.int64)
+    e.sort(axis=1)
+    return np.unique(e, axis=0).astype(np.int32)
+
+
+def check_readme_quick_start(api):
+    """README.md:51-88"""
+    V, E, F, V1, dhat = kats.readme_quick_start()
+    mesh = api.CollisionMesh(V, E, F)
+    c = api.NormalCollisions()
+    c.build(mesh, V, dhat)
+    assert c.size() > 0  # "the two triangles are within dhat, so collisions are active"
+    B = api.BarrierPotential(dhat, 1e3)
+    assert B(c, mesh, V) > 0
+    assert np.abs(B.gradient(c, mesh, V)).max() > 0
+    H = B.hessian(c, mesh, V)
+    assert H.shape == (18, 18) and H.nnz > 0
+    step = api.compute_collision_free_stepsize(mesh, V, V1)
+    assert 0.3 < step <= 0.5  # triangle 2 reaches triangle 1 at t = 0.5
+
+
+def check_ccd_kats(api):
+    """ccd/test_edge_edge_ccd.cpp, test_point_triangle_ccd.cpp, test_point_edge_ccd.cpp, test_point_point_ccd.cpp"""
+    for kind, cases in ((2, kats.edge_edge_ccd_cases()), (3, kats.point_triangle_ccd_cases())):
+        groups = {}
+        for c in cases:
+            groups.setdefault((c["tol"], c["max_iter"], c["tmax"]), []).append(c)
+        for (tol, max_iter, tmax), cs in groups.items():
+            t0, t1 = np.stack([c["t0"] for c in cs]), np.stack([c["t1"] for c in cs])
+            for ccd in (api.TightInclusionCCD(tol, max_iter), api.AdditiveCCD()):
+                hit, toi = api.narrow_phase_ccd(kind, t0, t1, 0.0, tmax, ccd)
+                for c, h, t in zip(cs, hit, toi):
+                    if c["conservative"]:
+                        assert h or not c["expected"], (c["name"], type(ccd).__name__)
+                    else:
+                        assert h == c["expected"], (c["name"], type(ccd).__name__, c["tol"])
+                    if h:
+                        assert 0 <= t <= tmax
+    pe = kats.point_edge_ccd_cases()
+    t0, t1 = np.stack([c["t0"] for c in pe]), np.stack([c["t1"] for c in pe])
+    for ccd in (api.TightInclusionCCD(), api.AdditiveCCD(-1, 0.999)):
+        hit, toi = api.narrow_phase_ccd(1, t0, t1, 0.0, 1.0, ccd)
+        for c, h, t in zip(pe, hit, toi):
+            assert h == c["expected"], (c["name"], type(ccd).__name__)
+            if h:
+                # the reference asserts toi <= expected (conservative); the lower bound only guards against a trivial 0
+                assert t <= c["toi"] + 1e-9 and t >= 0.9 * c["toi"], (c["name"], t)
+    pp = kats.point_point_ccd_cases()
+    for md in pp["min_distances"]:
+        for ccd in (api.TightInclusionCCD(), api.AdditiveCCD(-1, 0.999)):
+            hit, toi = api.narrow_phase_ccd(0, pp["t0"][None], pp["t1"][None], md, 1.0, ccd)
+            assert hit[0] and toi[0] == pytest.approx(pp["toi"], abs=pp["margin"] + md)
+
+
+def test_broad_phase_kats(oracle):
+    check_broad_phase_kats(oracle)
+
+
+def test_codim_kats(oracle):
+    check_codim_kats(oracle)
+
+
+def test_barrier_potential_scenes(oracle):
+    check_barrier_potential_scenes(oracle)
+
+
+def test_readme_quick_start(oracle):
+    check_readme_quick_start(oracle)
+
+
+def test_ccd_kats(oracle):
+    check_ccd_kats(oracle)
