@@ -463,13 +463,15 @@ __device__ inline unsigned long long warp_reserve(unsigned long long* counter, b
 // can neither start closer than min_distance nor produce a terminal box (see ti_cull), so it is
 // dropped here; survivors are compacted into `list` for the full per-query kernel.
 __global__ void __launch_bounds__(256, 3)
-    k_ti_filter(QuerySource q, double min_distance, double tmax_in, double tolerance, CcdOut out, int* __restrict__ list,
-                unsigned long long* nlist)
+    k_ti_filter(QuerySource q, int sel_mode, int sel_mod, double min_distance, double tmax_in, double tolerance, CcdOut out,
+                int* __restrict__ list, unsigned long long* nlist)
 {
     const unsigned long long* bound = out.bound;
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // sel_mode 0: every candidate; 1: the sample i % sel_mod == 0 (thread t -> i = t * sel_mod); 2: the rest
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (sel_mode == 1) i *= sel_mod;
     bool keep = false;
-    if (i < q.n) {
+    if (i < q.n && !(sel_mode == 2 && i % sel_mod == 0)) {
         keep = true;
         if (q.kind >= IPCB_EE) { // point-point / point-edge queries are few (codimensional): always kept
             d3 a[4], b[4];
@@ -496,61 +498,86 @@ __global__ void __launch_bounds__(256, 3)
     }
 }
 
-// tight_inclusion_ccd.cpp:222-336 + ccd_strategy :33-75, one thread per query
+// Query set-up shared by the per-thread and the per-warp search (tight_inclusion_ccd.cpp:222-336 and
+// ccd_strategy :33-75).  Returns false when the query is already answered (and reported).
+__device__ inline bool ti_setup(const QuerySource& q, int64_t i, double min_distance, double tmax_in, double tolerance, double rescale,
+                                const CcdOut& out, double* s, double* e, TIParams& P, int& is_vf, double& tmax0)
+{
+    d3 a[4], b[4];
+    const int n = load_query(q, i, a, b);
+    const double d0 = sqrt(auto_distance(q.kind, a));
+    bool moving = false;
+    for (int k = 0; k < n; k++) moving |= !same(a[k], b[k]);
+    if (d0 <= min_distance) { // check_initial_distance: toi = 0 (also the no-motion answer)
+        report(out, i, true, 0.0);
+        return false;
+    }
+    if (!moving) {
+        report(out, i, false, 0.0);
+        return false;
+    }
+    // points handed to the root finder: VV / EV are degenerate edge-edge queries (:104,:177)
+    d3 s4[4], e4[4];
+    if (q.kind == IPCB_VV) {
+        s4[0] = s4[1] = a[0], s4[2] = s4[3] = a[1];
+        e4[0] = e4[1] = b[0], e4[2] = e4[3] = b[1];
+    } else if (q.kind == IPCB_EV) {
+        s4[0] = s4[1] = a[0], s4[2] = a[1], s4[3] = a[2];
+        e4[0] = e4[1] = b[0], e4[2] = b[1], e4[3] = b[2];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) s4[k] = a[k], e4[k] = b[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        s[3 * k] = s4[k].x, s[3 * k + 1] = s4[k].y, s[3 * k + 2] = s4[k].z;
+        e[3 * k] = e4[k].x, e[3 * k + 1] = e4[k].y, e[3 * k + 2] = e4[k].z;
+    }
+    is_vf = q.kind == IPCB_FV;
+    // the search window is fixed when the query starts, like `tmax = earliest_toi.load()` (candidates.cpp:270)
+    tmax0 = out.bound ? fmin(tmax_in, load_bound(out.bound)) : tmax_in;
+    double med = (1.0 - rescale) * (d0 - min_distance); // minimum effective distance (:45-49)
+    med = fmin(med, 1e-4);
+    med += min_distance;
+    P.ms = med;
+    P.co_tol = fmin(0.5 * d0, tolerance); // adjusted tolerance (:245-246)
+    P.tmax = tmax0;
+    ti_tolerances(s, e, is_vf, P.co_tol, P.tol);
+    ti_error(s, e, is_vf, P.ms > 0, P.err);
+    return true;
+}
+// no-zero-toi refinement step (ticcd's loop behind tight_inclusion_ccd.cpp:59-72): returns true when another round is needed
+__device__ inline bool ti_shrink(const double* s, const double* e, int is_vf, TIParams& P, double best)
+{
+    if (!(best == 0.0 && P.co_tol > 1e-300)) return false;
+    if (10 * P.co_tol < P.ms) {
+        P.ms *= 0.5;
+    } else {
+        P.co_tol *= 0.5;
+        ti_tolerances(s, e, is_vf, P.co_tol, P.tol);
+    }
+    return true;
+}
+
+// Stage 2, one thread per pre-filtered query: exact level-0 cull, then a short in-register depth-first search.
+// A query that needs more than `budget` boxes in any run is deferred to the warp-cooperative kernel.
 __global__ void __launch_bounds__(128)
     k_ti_query(QuerySource q, const int* __restrict__ list, int64_t nlist, double min_distance, double tmax_in, double tolerance, double rescale,
-               int budget, TIQueue Z, CcdOut out)
+               int budget, int* __restrict__ hard, unsigned long long* nhard, CcdOut out)
 {
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool active = tid < nlist;
     const int64_t i = active ? list[tid] : 0;
-    bool spill = false;
-    double s[12], e[12];
-    TIParams P;
-    TIBox stack[DFS_STACK];
-    int sp = 0;
-    int is_vf = 0;
-    int spill_flags = 0;
-    double best = INFINITY;
+    bool defer = false;
     if (active) {
-        d3 a[4], b[4];
-        const int n = load_query(q, i, a, b);
-        const double d0 = sqrt(auto_distance(q.kind, a));
-        bool moving = false;
-        for (int k = 0; k < n; k++) moving |= !same(a[k], b[k]);
-        if (d0 <= min_distance) { // check_initial_distance: toi = 0 (also the no-motion answer)
-            report(out, i, true, 0.0);
-        } else if (!moving) {
-            report(out, i, false, 0.0);
-        } else {
-            // points handed to the root finder: VV / EV are degenerate edge-edge queries (:104,:177)
-            d3 s4[4], e4[4];
-            if (q.kind == IPCB_VV) {
-                s4[0] = s4[1] = a[0], s4[2] = s4[3] = a[1];
-                e4[0] = e4[1] = b[0], e4[2] = e4[3] = b[1];
-            } else if (q.kind == IPCB_EV) {
-                s4[0] = s4[1] = a[0], s4[2] = a[1], s4[3] = a[2];
-                e4[0] = e4[1] = b[0], e4[2] = b[1], e4[3] = b[2];
-            } else {
-#pragma unroll
-                for (int k = 0; k < 4; k++) s4[k] = a[k], e4[k] = b[k];
-            }
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                s[3 * k] = s4[k].x, s[3 * k + 1] = s4[k].y, s[3 * k + 2] = s4[k].z;
-                e[3 * k] = e4[k].x, e[3 * k + 1] = e4[k].y, e[3 * k + 2] = e4[k].z;
-            }
-            is_vf = q.kind == IPCB_FV;
-            // the search window is fixed when the query starts, like `tmax = earliest_toi.load()` (candidates.cpp:270)
-            const double tmax0 = out.bound ? fmin(tmax_in, load_bound(out.bound)) : tmax_in;
-            double med = (1.0 - rescale) * (d0 - min_distance); // minimum effective distance (:45-49)
-            med = fmin(med, 1e-4);
-            med += min_distance;
-            P.ms = med;
-            P.co_tol = fmin(0.5 * d0, tolerance); // adjusted tolerance (:245-246)
-            P.tmax = tmax0;
-            ti_tolerances(s, e, is_vf, P.co_tol, P.tol);
-            ti_error(s, e, is_vf, P.ms > 0, P.err);
+        double s[12], e[12];
+        TIParams P;
+        int is_vf;
+        double tmax0;
+        if (ti_setup(q, i, min_distance, tmax_in, tolerance, rescale, out, s, e, P, is_vf, tmax0)) {
+            TIBox stack[DFS_STACK];
+            int sp = 0;
+            double best = INFINITY;
             // ---- first query: minimum effective distance, no_zero_toi = false
             bool done = true;
             if (!ti_cull(s, e, is_vf, P, tmax0)) {
@@ -559,7 +586,7 @@ __global__ void __launch_bounds__(128)
                 done = ti_dfs(s, e, is_vf, P, out.bound, budget, stack, sp, best);
             }
             if (!done) {
-                spill = true;
+                defer = true;
             } else if (best < SMALL_TOI) {
                 // ---- second query: ms = min_distance, no_zero_toi = true, shrinking until toi != 0
                 P.ms = min_distance;
@@ -569,45 +596,123 @@ __global__ void __launch_bounds__(128)
                     best = INFINITY;
                     stack[0] = TIBox { 0, 0, 0, 0, 0, 0, 0 };
                     sp = 1;
-                    done = ti_dfs(s, e, is_vf, P, nullptr, budget, stack, sp, best);
-                    if (!done) {
-                        spill = true;
-                        spill_flags = 2;
+                    if (!ti_dfs(s, e, is_vf, P, nullptr, budget, stack, sp, best)) {
+                        defer = true;
                         break;
                     }
-                    if (best == 0.0 && P.co_tol > 1e-300) {
-                        if (10 * P.co_tol < P.ms) {
-                            P.ms *= 0.5;
-                        } else {
-                            P.co_tol *= 0.5;
-                            ti_tolerances(s, e, is_vf, P.co_tol, P.tol);
-                        }
-                    } else {
-                        break;
-                    }
+                    if (!ti_shrink(s, e, is_vf, P, best)) break;
                 }
-                if (!spill) report(out, i, best < INFINITY, best * rescale);
+                if (!defer) report(out, i, best < INFINITY, best * rescale);
             } else {
                 report(out, i, best < INFINITY, best);
             }
         }
     }
-    // ---- spill path: hand the unexplored boxes to the global queue
-    const unsigned long long slot = warp_reserve(Z.nq, spill, 1);
-    const bool slot_ok = spill && slot < Z.qcap;
-    const unsigned long long ubase = warp_reserve(Z.nout, slot_ok, sp);
-    if (spill) {
-        if (slot_ok && ubase + sp <= Z.ucap) {
+    const unsigned long long slot = warp_reserve(nhard, defer, 1);
+    if (defer) hard[slot] = int(i);
+}
+
+// Stage 3, one WARP per hard query: the 32 lanes pop up to 32 boxes from a shared-memory stack, evaluate them in
+// parallel and push the children (earliest first on top), sharing the best terminal time.  The result (minimum
+// lower time bound over all terminal boxes not pruned by it) does not depend on the evaluation order.  If the
+// stack overflows, the query is handed to the global level-synchronous queue.
+constexpr int WSTACK = 1024;
+__device__ inline bool ti_warp_search(const double* s, const double* e, int is_vf, TIParams& P, const unsigned long long* bound, TIBox* stk,
+                                      int cap, double& best, int lane)
+{
+    int sp = 1;
+    if (lane == 0) stk[0] = TIBox { 0, 0, 0, 0, 0, 0, 0 };
+    __syncwarp();
+    best = INFINITY;
+    while (sp > 0) {
+        const int n = min(sp, 32);
+        const bool have = lane < n;
+        TIBox b = TIBox { 0, 0, 0, 0, 0, 0, 0 };
+        if (have) b = stk[sp - 1 - lane];
+        sp -= n;
+        __syncwarp();
+        if (bound) P.tmax = fmin(P.tmax, load_bound(bound));
+        int r = 0, nchild = 0;
+        TIBox child[2];
+        double t0 = INFINITY;
+        if (have) {
+            double tt[2], uu[2], vv[2];
+            box_bounds(b, tt, uu, vv);
+            if (tt[0] < best && tt[0] <= P.tmax) {
+                r = ti_step(s, e, is_vf, P, b, tt, uu, vv, child, nchild);
+                if (r == 1) t0 = tt[0];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t0 = fmin(t0, __shfl_xor_sync(0xffffffffu, t0, o));
+        best = fmin(best, t0);
+        const int mine = r == 2 ? nchild : 0;
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (sp + total > cap) return false;
+        // lane 0 held the top of the stack: its children go back on top
+        const int off = sp + (total - incl);
+        if (mine == 2) stk[off] = child[1], stk[off + 1] = child[0];
+        else if (mine == 1) stk[off] = child[0];
+        sp += total;
+        __syncwarp();
+    }
+    return true;
+}
+
+constexpr int WARP_SEARCH_WARPS = 2;
+__global__ void __launch_bounds__(32 * WARP_SEARCH_WARPS)
+    k_ti_warp(QuerySource q, const int* __restrict__ hard, int64_t nhard, double min_distance, double tmax_in, double tolerance, double rescale,
+              int cap, TIQueue Z, CcdOut out)
+{
+    __shared__ TIBox stk[WARP_SEARCH_WARPS][WSTACK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t w = blockIdx.x * int64_t(WARP_SEARCH_WARPS) + warp;
+    if (w >= nhard) return;
+    const int64_t i = hard[w];
+    double s[12], e[12];
+    TIParams P;
+    int is_vf;
+    double tmax0;
+    // every lane computes the same set-up (an early answer is reported by all lanes with identical values)
+    if (!ti_setup(q, i, min_distance, tmax_in, tolerance, rescale, out, s, e, P, is_vf, tmax0)) return;
+    double best = INFINITY;
+    int flags = 0;
+    bool ok = true;
+    if (!ti_cull(s, e, is_vf, P, tmax0)) ok = ti_warp_search(s, e, is_vf, P, out.bound, stk[warp], cap, best, lane);
+    if (ok && best < SMALL_TOI) {
+        P.ms = min_distance;
+        P.tmax = tmax0;
+        ti_error(s, e, is_vf, P.ms > 0, P.err);
+        flags = 2;
+        for (int round = 0; round < 200; round++) {
+            ok = ti_warp_search(s, e, is_vf, P, nullptr, stk[warp], cap, best, lane);
+            if (!ok || !ti_shrink(s, e, is_vf, P, best)) break;
+        }
+        if (ok && lane == 0) report(out, i, best < INFINITY, best * rescale);
+    } else if (ok) {
+        if (lane == 0) report(out, i, best < INFINITY, best);
+    }
+    if (!ok && lane == 0) { // stack overflow: restart this run from its root in the global queue
+        const unsigned long long slot = atomicAdd(Z.nq, 1ull);
+        const unsigned long long u = atomicAdd(Z.nout, 1ull);
+        if (slot < Z.qcap && u < Z.ucap) {
             TIQuery& Q = Z.queries[slot];
 #pragma unroll
             for (int k = 0; k < 12; k++) Q.s[k] = s[k], Q.e[k] = e[k];
+            if (flags == 0) P.tmax = tmax0;
             Q.P = P;
             Q.is_vf = is_vf;
             Q.pad = 0;
             Q.src = i;
-            Z.qtoi[slot] = (unsigned long long)__double_as_longlong(best);
-            Z.qflags[slot] = spill_flags;
-            for (int k = 0; k < sp; k++) Z.outq[ubase + k] = TIUnit { int(slot), stack[k] };
+            Z.qtoi[slot] = 0x7ff0000000000000ull;
+            Z.qflags[slot] = flags;
+            Z.outq[u] = TIUnit { int(slot), TIBox { 0, 0, 0, 0, 0, 0, 0 } };
         }
         // a failed reservation is detected on the host (counter > capacity): the pass is repeated with room
     }
@@ -705,6 +810,7 @@ struct TIWork {
     Buf<int> qflags;
     Buf<TIUnit> ua, ub;
     Buf<int> list; // candidates that survive the pre-filter
+    Buf<int> hard; // queries deferred to the warp-cooperative search
 };
 static std::map<ipcb_ctx*, TIWork*> g_work; // one per context
 
@@ -742,14 +848,18 @@ static void ti_run_levels(ipcb_ctx* ctx, TIWork& W, TIQueue Z, unsigned long lon
     }
 }
 
-static int g_budget = 0;
+// in-register boxes per query before it is deferred to the warp-cooperative search, and the shared-memory
+// stack capacity per warp before a query goes to the global queue (the environment variables are test hooks
+// that force the later stages on small inputs)
 static int dfs_budget()
 {
-    if (g_budget == 0) {
-        const char* e = getenv("IPCB_TI_BUDGET"); // in-register units per query before spilling to the global queue
-        g_budget = e ? std::max(1, atoi(e)) : 2048;
-    }
-    return g_budget;
+    const char* e = getenv("IPCB_TI_BUDGET");
+    return e ? std::max(1, atoi(e)) : 96;
+}
+static int warp_stack_cap()
+{
+    const char* e = getenv("IPCB_TI_WSTACK");
+    return e ? std::min(WSTACK, std::max(2, atoi(e))) : WSTACK;
 }
 
 // Tight-Inclusion CCD over one query source
@@ -766,46 +876,71 @@ static void ti_run(ipcb_ctx* ctx, const QuerySource& src, double min_distance, d
     size_t qcap = std::max<size_t>(W.queries.cap, 1024);
     size_t ucap = std::max<size_t>(W.ua.cap, size_t(1) << 16);
     unsigned long long nq = 0, nunits = 0;
-    // ---- pre-filter: most broad-phase candidates are separated along one of their own directions
     if (src.n > 0x7fffffffll) throw Error("ccd: more than 2^31 candidates of one kind");
     W.list.reserve(src.n);
-    IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
-    k_ti_filter<<<grid_for(src.n, 256), 256, 0, s>>>(src, min_distance, tmax, p.tolerance, out, W.list.p, cnt);
-    ctx->launches++;
-    const int64_t nlist = int64_t(read_counter(ctx, cnt));
-    if (nlist == 0) return;
-    for (int attempt = 0;; attempt++) {
-        W.queries.reserve(qcap), W.qtoi.reserve(qcap), W.qflags.reserve(qcap);
-        W.ua.reserve(ucap), W.ub.reserve(ucap);
-        qcap = std::min(W.queries.cap, std::min(W.qtoi.cap, W.qflags.cap));
-        ucap = std::min(W.ua.cap, W.ub.cap);
-        IPCB_CUDA(cudaMemsetAsync(nq_d, 0, 2 * sizeof(unsigned long long), s)); // nq and the unit counter
-        TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, W.ua.p, cnt, (unsigned long long)ucap };
-        k_ti_query<<<grid_for(nlist, 128), 128, 0, s>>>(src, W.list.p, nlist, min_distance, tmax, p.tolerance, p.conservative_rescaling,
-                                                        dfs_budget(), Z, out);
+    // one phase = pre-filter (most broad-phase candidates are separated along one of their own directions
+    // inside the current search window) + per-query search of the survivors + the spill queue
+    auto phase = [&](int sel_mode, int sel_mod) {
+        const int64_t nthreads = sel_mode == 1 ? (src.n + sel_mod - 1) / sel_mod : src.n;
+        IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
+        k_ti_filter<<<grid_for(nthreads, 256), 256, 0, s>>>(src, sel_mode, sel_mod, min_distance, tmax, p.tolerance, out, W.list.p, cnt);
+        ctx->launches++;
+        const int64_t nlist = int64_t(read_counter(ctx, cnt));
+        if (nlist == 0) return;
+        // ---- stage 2: per-thread search with a small budget; the rest is deferred
+        W.hard.reserve(nlist);
+        IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
+        k_ti_query<<<grid_for(nlist, 128), 128, 0, s>>>(src, W.list.p, nlist, min_distance, tmax, p.tolerance, p.conservative_rescaling, dfs_budget(),
+                                                        W.hard.p, cnt, out);
         ctx->launches++;
         IPCB_CUDA(cudaGetLastError());
-        nq = read_counter(ctx, nq_d);
-        nunits = read_counter(ctx, cnt);
-        if (nq <= qcap && nunits <= ucap) break;
-        if (attempt > 3) throw Error("ccd: spill buffers overflow persisted");
-        // reports are idempotent (atomicMin / identical values), so the pass can simply be repeated with room
-        qcap = std::max<size_t>(qcap, nq + nq / 4);
-        ucap = std::max<size_t>(ucap, size_t(DFS_STACK) * (nq + nq / 4));
-    }
-    if (nq == 0) return;
-    // ---- spilled queries: global interval-subdivision queue
-    TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, nullptr, nullptr, (unsigned long long)ucap };
-    ti_run_levels(ctx, W, Z, nunits, out.bound);
-    for (int round = 0; round < 250; round++) {
-        IPCB_CUDA(cudaMemsetAsync(nactive_d, 0, sizeof(unsigned long long), s));
-        k_ti_finalize<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), Z, min_distance, p.conservative_rescaling, out, nactive_d);
-        ctx->launches++;
-        if (read_counter(ctx, nactive_d) == 0) break;
-        IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
-        k_ti_push_roots<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), W.qflags.p, W.ua.p, cnt);
-        ctx->launches++;
-        ti_run_levels(ctx, W, Z, read_counter(ctx, cnt), nullptr);
+        const int64_t nhard = int64_t(read_counter(ctx, cnt));
+        if (nhard == 0) return;
+        // ---- stage 3: one warp per hard query; shared-memory stack overflows go to the global queue
+        for (int attempt = 0;; attempt++) {
+            W.queries.reserve(qcap), W.qtoi.reserve(qcap), W.qflags.reserve(qcap);
+            W.ua.reserve(ucap), W.ub.reserve(ucap);
+            qcap = std::min(W.queries.cap, std::min(W.qtoi.cap, W.qflags.cap));
+            ucap = std::min(W.ua.cap, W.ub.cap);
+            IPCB_CUDA(cudaMemsetAsync(nq_d, 0, 2 * sizeof(unsigned long long), s)); // nq and the unit counter
+            TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, W.ua.p, cnt, (unsigned long long)ucap };
+            k_ti_warp<<<grid_for(nhard, WARP_SEARCH_WARPS), 32 * WARP_SEARCH_WARPS, 0, s>>>(src, W.hard.p, nhard, min_distance, tmax, p.tolerance, p.conservative_rescaling,
+                                                                                          warp_stack_cap(), Z, out);
+            ctx->launches++;
+            IPCB_CUDA(cudaGetLastError());
+            nq = read_counter(ctx, nq_d);
+            nunits = read_counter(ctx, cnt);
+            if (nq <= qcap && nunits <= ucap) break;
+            if (attempt > 3) throw Error("ccd: spill buffers overflow persisted");
+            // reports are idempotent (atomicMin / identical values), so the pass can simply be repeated with room
+            qcap = std::max<size_t>(qcap, nq + nq / 4);
+            ucap = std::max<size_t>(ucap, nq + nq / 4);
+        }
+        if (nq == 0) return;
+        // ---- spilled queries: global interval-subdivision queue
+        TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, nullptr, nullptr, (unsigned long long)ucap };
+        ti_run_levels(ctx, W, Z, nunits, out.bound);
+        for (int round = 0; round < 250; round++) {
+            IPCB_CUDA(cudaMemsetAsync(nactive_d, 0, sizeof(unsigned long long), s));
+            k_ti_finalize<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), Z, min_distance, p.conservative_rescaling, out, nactive_d);
+            ctx->launches++;
+            if (read_counter(ctx, nactive_d) == 0) break;
+            IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
+            k_ti_push_roots<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), W.qflags.p, W.ua.p, cnt);
+            ctx->launches++;
+            ti_run_levels(ctx, W, Z, read_counter(ctx, cnt), nullptr);
+        }
+    };
+    // With a shared bound (step-size search) a strided SAMPLE of the candidates goes first: its earliest time
+    // of impact shrinks the search window, so the pre-filter of the remaining candidates (the same
+    // std::atomic<double> earliest_toi idea as candidates.cpp:267-286, applied before any root finding)
+    // discards almost everything that cannot beat it.
+    constexpr int SAMPLE = 64;
+    if (out.bound && src.n >= 16 * 1024 * SAMPLE / 8) {
+        phase(1, SAMPLE);
+        phase(2, SAMPLE);
+    } else {
+        phase(0, 1);
     }
 }
 

@@ -212,6 +212,28 @@ def test_narrow_phase_matches_oracle(cuda, oracle):
                 assert np.mean(np.abs(tg[hg] - to[ho]) <= 1e-12) > 0.9
 
 
+@pytest.mark.parametrize("hooks", [{"IPCB_TI_BUDGET": "1"}, {"IPCB_TI_BUDGET": "1", "IPCB_TI_WSTACK": "8"}])
+def test_ccd_later_stages(cuda, oracle, scenes, hooks, monkeypatch):
+    """force every search into the warp-cooperative kernel (budget 1) and, with a tiny shared-memory stack, on into
+    the global level-synchronous queue: the answers must not depend on which stage finishes a query"""
+    rng = np.random.default_rng(9)
+    a = rng.uniform(-1, 1, (300, 4, 3))
+    b = a + rng.normal(0, 0.6, (300, 4, 3))
+    V0, V1, E, F, P = scenes.cloth_stack(3, 30)
+    ref_hits = {k: cuda.narrow_phase_ccd(k, a, b, 1e-3, 1.0) for k in (2, 3)}
+    mesh = cuda.CollisionMesh(V0, E, F)
+    ref_step = cuda.compute_collision_free_stepsize(mesh, V0, V1)
+    for k, v in hooks.items():
+        monkeypatch.setenv(k, v)
+    for k in (2, 3):
+        hit, toi = cuda.narrow_phase_ccd(k, a, b, 1e-3, 1.0)
+        assert np.array_equal(hit, ref_hits[k][0]) and hit.sum() > 0
+        assert np.array_equal(toi[hit], ref_hits[k][1][hit])  # order-independent minimum: bit-identical
+        ho, to = oracle.narrow_phase_ccd(k, a, b, 1e-3, 1.0)
+        assert np.array_equal(hit, ho)
+    assert cuda.compute_collision_free_stepsize(mesh, V0, V1) == ref_step
+
+
 def test_errors_are_reported(cuda):
     V = np.zeros((3, 3))
     with pytest.raises(RuntimeError, match="Unable to find edge!"):
