@@ -126,7 +126,9 @@ struct ipcb_ctx {
     ipcb::Buf<double> hblk;                          // 16 x 9 doubles per collision
     ipcb::Buf<int> hslow;                            // edge-edge collisions handed to the general kernel
     ipcb::Buf<int> hcolinc, hcolR, hitemoff;         // per column vertex: first incidence, #items, first item
-    ipcb::Buf<unsigned> hsref;                       // per item, column-major then row-sorted: block slot | head flag
+    ipcb::Buf<unsigned> hsref;                       // per item, grouped by column then by row vertex: block slot
+    ipcb::Buf<int2> hudesc;                          // per unique block: (first item within its column, row vertex)
+    ipcb::Buf<int> hcolU;                            // unique blocks per column
     ipcb::Buf<int> hcnt;                             // entries per scalar column
     ipcb::Buf<int> hbig;                             // columns too large for one warp's shared memory
     ipcb::Buf<char> hscratch;                        // global sort scratch for huge columns

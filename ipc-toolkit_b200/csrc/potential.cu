@@ -572,7 +572,6 @@ __global__ void __launch_bounds__(128)
 // OR of the exact-non-zero masks (pass 1: counts), and after one prefix sum over the scalar
 // columns the blocks are gathered (72 contiguous bytes each), run-summed with a segmented warp
 // scan and written straight into inner / values (pass 2).  Summation order is fixed by the sort.
-constexpr unsigned HEAD_BIT = 0x80000000u;
 constexpr int WARP_CAP = 512;  // items a warp sorts in shared memory
 constexpr int CTA_CAP = 8192;  // items a block sorts in shared memory; beyond: global scratch
 
@@ -641,56 +640,82 @@ struct SymArgs {
     const int4* vid;
     const unsigned short* mask;
     unsigned ref_ev, ref_ee;
-    unsigned* sref;
-    int* cnt;
+    unsigned* sref; // per item (grouped by unique block): block slot gi * 16 + a * 4 + b
+    int2* udesc;    // per unique block of a column, at itemoff[v] + u: (first item within the column, row vertex)
+    int* colU;      // unique blocks per column
+    int* cnt;       // entries per scalar column
 };
 
-// Pass 1 for one column by NT threads (t = thread rank).  keys / refs / masks: room for npow2 / R / R.
+// one incidence = one collision seen from one of its stencil points: its row blocks
+struct IncItems {
+    unsigned gi, a;
+    int np;
+    int vi[4];
+    unsigned short mk[4];
+};
+__device__ inline IncItems load_incidence(const SymArgs& A, int q, int b1, int b2)
+{
+    IncItems it;
+    const unsigned ref = unsigned(A.inc[q]); // gi * 4 + a
+    it.gi = ref >> 2, it.a = ref & 3u;
+    it.np = q < b1 ? 2 : (q < b2 ? 3 : 4); // incidences are ordered VV, EV, then the 4-point kinds
+    const int4 vv = A.vid[it.gi];
+    const uint2 mm = *reinterpret_cast<const uint2*>(A.mask + size_t(it.gi) * HSLOTS + it.a * 4);
+    it.vi[0] = vv.x, it.vi[1] = vv.y, it.vi[2] = vv.z, it.vi[3] = vv.w;
+    it.mk[0] = (unsigned short)(mm.x & 0xffffu), it.mk[1] = (unsigned short)(mm.x >> 16);
+    it.mk[2] = (unsigned short)(mm.y & 0xffffu), it.mk[3] = (unsigned short)(mm.y >> 16);
+    return it;
+}
+
+// ---- pass 1, general path: sort all row blocks of the column (NT cooperating threads) ---------------------------------
+// keys / refs / masks: room for npow2 / R / R entries; scan: NT ints (shared)
 template <int NT>
-__device__ inline void column_symbolic(const SymArgs& A, int v, int t, unsigned long long* keys, unsigned* refs, unsigned short* masks,
-                                       int* red /* 3 ints per warp of the group, shared */)
+__device__ inline void column_symbolic_sort(const SymArgs& A, int v, int t, unsigned long long* keys, unsigned* refs, unsigned short* masks,
+                                            int* scan)
 {
     const int s = A.colinc[v], e = A.colinc[v + 1], R = A.colR[v];
     int npow2 = 1;
     while (npow2 < R) npow2 <<= 1;
-    // item slots: incidences are ordered VV, EV, then 4-point kinds
     const int b1 = lower_bound_lo(A.inc, s, e, A.ref_ev), b2 = lower_bound_lo(A.inc, b1, e, A.ref_ee);
     for (int q = s + t; q < e; q += NT) {
-        const unsigned ref = unsigned(A.inc[q]); // gi * 4 + a
-        const unsigned gi = ref >> 2, a = ref & 3u;
-        int np, slot0;
-        if (q < b1) np = 2, slot0 = 2 * (q - s);
-        else if (q < b2) np = 3, slot0 = 2 * (b1 - s) + 3 * (q - b1);
-        else np = 4, slot0 = 2 * (b1 - s) + 3 * (b2 - b1) + 4 * (q - b2);
-        const int4 vv = A.vid[gi];
-        const uint2 mm = *reinterpret_cast<const uint2*>(A.mask + size_t(gi) * HSLOTS + a * 4);
-        const int vi[4] = { vv.x, vv.y, vv.z, vv.w };
-        const unsigned short mk[4] = { (unsigned short)(mm.x & 0xffffu), (unsigned short)(mm.x >> 16), (unsigned short)(mm.y & 0xffffu),
-                                       (unsigned short)(mm.y >> 16) };
+        const IncItems it = load_incidence(A, q, b1, b2);
+        const int slot0 = q < b1 ? 2 * (q - s) : (q < b2 ? 2 * (b1 - s) + 3 * (q - b1) : 2 * (b1 - s) + 3 * (b2 - b1) + 4 * (q - b2));
 #pragma unroll
         for (int b = 0; b < 4; b++)
-            if (b < np) {
+            if (b < it.np) {
                 const int slot = slot0 + b;
-                keys[slot] = ((unsigned long long)(unsigned)vi[b] << 32) | unsigned(slot);
-                refs[slot] = gi * HSLOTS + a * 4 + b;
-                masks[slot] = mk[b];
+                keys[slot] = ((unsigned long long)(unsigned)it.vi[b] << 32) | unsigned(slot);
+                refs[slot] = it.gi * HSLOTS + it.a * 4 + b;
+                masks[slot] = it.mk[b];
             }
     }
     for (int q = R + t; q < npow2; q += NT) keys[q] = ~0ull;
     group_sync<NT>();
     bitonic_sort<NT>(keys, npow2, t);
-    // heads, pattern counts, sorted block references
-    unsigned* sref = A.sref + A.itemoff[v];
+    // unique blocks: thread t owns the contiguous items [lo, hi)
+    const int L = (R + NT - 1) / NT, lo = min(R, t * L), hi = min(R, lo + L);
+    int heads = 0;
+    for (int q = lo; q < hi; q++) heads += q == 0 || unsigned(keys[q] >> 32) != unsigned(keys[q - 1] >> 32);
+    scan[t] = heads;
+    group_sync<NT>();
+    int u = 0, total = 0;
+    for (int k = 0; k < NT; k++) {
+        const int c = scan[k];
+        u += k < t ? c : 0;
+        total += c;
+    }
+    const int ioff = A.itemoff[v];
     int c0 = 0, c1 = 0, c2 = 0;
-    for (int q = t; q < R; q += NT) {
+    for (int q = lo; q < hi; q++) {
         const unsigned long long k = keys[q];
         const unsigned row = unsigned(k >> 32);
-        const bool head = q == 0 || unsigned(keys[q - 1] >> 32) != row;
-        sref[q] = refs[unsigned(k)] | (head ? HEAD_BIT : 0u);
-        if (head) {
+        A.sref[ioff + q] = refs[unsigned(k)];
+        if (q == 0 || unsigned(keys[q - 1] >> 32) != row) {
             unsigned mk = 0;
             for (int j = q; j < R && unsigned(keys[j] >> 32) == row; j++) mk |= masks[unsigned(keys[j])];
             c0 += __popc(mk & 0x49u), c1 += __popc(mk & 0x92u), c2 += __popc(mk & 0x124u);
+            A.udesc[ioff + u] = make_int2(q, int(row));
+            u++;
         }
     }
 #pragma unroll
@@ -700,25 +725,144 @@ __device__ inline void column_symbolic(const SymArgs& A, int v, int t, unsigned 
         c2 += __shfl_xor_sync(0xffffffffu, c2, o);
     }
     if (NT == 32) {
-        if (t == 0) A.cnt[3 * size_t(v)] = c0, A.cnt[3 * size_t(v) + 1] = c1, A.cnt[3 * size_t(v) + 2] = c2;
+        if (t == 0) A.cnt[3 * size_t(v)] = c0, A.cnt[3 * size_t(v) + 1] = c1, A.cnt[3 * size_t(v) + 2] = c2, A.colU[v] = total;
     } else {
-        if ((t & 31) == 0) red[3 * (t >> 5)] = c0, red[3 * (t >> 5) + 1] = c1, red[3 * (t >> 5) + 2] = c2;
-        __syncthreads();
+        group_sync<NT>(); // scan[] is reused for the block reduction
+        if ((t & 31) == 0) scan[3 * (t >> 5)] = c0, scan[3 * (t >> 5) + 1] = c1, scan[3 * (t >> 5) + 2] = c2;
+        group_sync<NT>();
         if (t < 3) {
             int sum = 0;
-            for (int w = 0; w < NT / 32; w++) sum += red[3 * w + t];
+            for (int w = 0; w < NT / 32; w++) sum += scan[3 * w + t];
             A.cnt[3 * size_t(v) + t] = sum;
         }
-        __syncthreads();
+        if (t == 0) A.colU[v] = total;
+        group_sync<NT>();
     }
 }
 
-constexpr int SYM_WARPS = 4;
-__global__ void __launch_bounds__(32 * SYM_WARPS) k_hess_symbolic(SymArgs A, int warp_cap, int* __restrict__ big, unsigned long long* nbig)
+// ---- pass 1, fast path (one warp): de-duplicate the row vertices in a shared-memory hash table, sort only the
+// unique ones, then place the items with a stable counting sort (deterministic order inside every run) ----------------
+constexpr int HT = 128; // hash slots per warp
+struct HashSmem {
+    int key[HT];
+    unsigned msk[HT];
+    int cnt[HT];
+    int base[HT];
+    unsigned long long ukey[HT];
+};
+__device__ inline int hash_slot(int vi) { return int((unsigned(vi) * 2654435761u) >> 25); } // 7 bits
+
+// returns false when the column has more unique row vertices than the table holds
+__device__ inline bool column_symbolic_hash(const SymArgs& A, int v, int lane, HashSmem& H)
 {
-    __shared__ unsigned long long keys[SYM_WARPS][WARP_CAP];
-    __shared__ unsigned refs[SYM_WARPS][WARP_CAP];
-    __shared__ unsigned short masks[SYM_WARPS][WARP_CAP];
+    const int s = A.colinc[v], e = A.colinc[v + 1], R = A.colR[v];
+    const int b1 = lower_bound_lo(A.inc, s, e, A.ref_ev), b2 = lower_bound_lo(A.inc, b1, e, A.ref_ee);
+    for (int k = lane; k < HT; k += 32) H.key[k] = -1, H.msk[k] = 0, H.cnt[k] = 0;
+    __syncwarp();
+    // A. insert every row vertex; OR the patterns, count the items
+    bool overflow = false;
+    for (int q = s + lane; q < e; q += 32) {
+        const IncItems it = load_incidence(A, q, b1, b2);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (b < it.np) {
+                int h = hash_slot(it.vi[b]), probe = 0;
+                for (; probe < HT; probe++) {
+                    const int old = atomicCAS(&H.key[h], -1, it.vi[b]);
+                    if (old == -1 || old == it.vi[b]) break;
+                    h = (h + 1) & (HT - 1);
+                }
+                if (probe == HT) overflow = true;
+                else atomicOr(&H.msk[h], unsigned(it.mk[b])), atomicAdd(&H.cnt[h], 1);
+            }
+    }
+    if (__any_sync(0xffffffffu, overflow)) return false;
+    __syncwarp();
+    // B. unique row vertices, sorted
+    int U = 0;
+    for (int k0 = 0; k0 < HT; k0 += 32) {
+        const int k = k0 + lane;
+        const bool occ = H.key[k] != -1;
+        const unsigned m = __ballot_sync(0xffffffffu, occ);
+        if (occ) H.ukey[U + __popc(m & ((1u << lane) - 1))] = ((unsigned long long)(unsigned)H.key[k] << 32) | unsigned(k);
+        U += __popc(m);
+    }
+    int npow2 = 1;
+    while (npow2 < U) npow2 <<= 1;
+    for (int k = U + lane; k < npow2; k += 32) H.ukey[k] = ~0ull;
+    __syncwarp();
+    bitonic_sort<32>(H.ukey, npow2, lane);
+    // C. run starts, descriptors, pattern counts
+    const int ioff = A.itemoff[v];
+    int c0 = 0, c1 = 0, c2 = 0, run = 0;
+    for (int u0 = 0; u0 < U; u0 += 32) {
+        const int u = u0 + lane;
+        int slot = 0, c = 0;
+        if (u < U) slot = int(unsigned(H.ukey[u])), c = H.cnt[slot];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += up;
+        }
+        if (u < U) {
+            const int start = run + incl - c;
+            H.base[slot] = start;
+            A.udesc[ioff + u] = make_int2(start, int(unsigned(H.ukey[u] >> 32)));
+            const unsigned mk = H.msk[slot];
+            c0 += __popc(mk & 0x49u), c1 += __popc(mk & 0x92u), c2 += __popc(mk & 0x124u);
+        }
+        run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    if (lane == 0) A.cnt[3 * size_t(v)] = c0, A.cnt[3 * size_t(v) + 1] = c1, A.cnt[3 * size_t(v) + 2] = c2, A.colU[v] = U;
+    __syncwarp();
+    // D. stable placement: chunks of 32 incidences in order, point by point; items of a chunk that fall into the
+    // same run are ranked by lane
+    for (int q0 = s; q0 < e; q0 += 32) {
+        const int q = q0 + lane;
+        IncItems it;
+        it.np = 0;
+        if (q < e) it = load_incidence(A, q, b1, b2);
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const bool valid = b < it.np;
+            const unsigned vm = __ballot_sync(0xffffffffu, valid);
+            if (valid) {
+                int h = hash_slot(it.vi[b]);
+                while (H.key[h] != it.vi[b]) h = (h + 1) & (HT - 1);
+                const unsigned peers = __match_any_sync(vm, h);
+                const int rank = __popc(peers & ((1u << lane) - 1));
+                const int pos = H.base[h];
+                __syncwarp(vm);
+                if (rank == 0) H.base[h] = pos + __popc(peers);
+                A.sref[ioff + pos + rank] = it.gi * HSLOTS + it.a * 4 + b;
+            }
+            __syncwarp();
+        }
+    }
+    (void)R;
+    return true;
+}
+
+constexpr int SYM_WARPS = 4;
+union WarpSmem {
+    HashSmem h;
+    struct {
+        unsigned long long keys[WARP_CAP];
+        unsigned refs[WARP_CAP];
+        unsigned short masks[WARP_CAP];
+        int scan[32];
+    } srt;
+};
+__global__ void __launch_bounds__(32 * SYM_WARPS) k_hess_symbolic(SymArgs A, int warp_cap, int use_hash, int* __restrict__ big, unsigned long long* nbig)
+{
+    __shared__ WarpSmem sm[SYM_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int v = blockIdx.x * SYM_WARPS + warp;
     if (v > A.nV) return;
@@ -729,25 +873,28 @@ __global__ void __launch_bounds__(32 * SYM_WARPS) k_hess_symbolic(SymArgs A, int
     const int R = A.colR[v];
     if (R == 0) {
         if (lane < 3) A.cnt[3 * size_t(v) + lane] = 0;
+        if (lane == 0) A.colU[v] = 0;
         return;
     }
+    if (use_hash && column_symbolic_hash(A, v, lane, sm[warp].h)) return;
+    __syncwarp();
     if (R > warp_cap) { // handed to the block-per-column kernel
         if (lane == 0) big[atomicAdd(nbig, 1ull)] = v;
         return;
     }
-    column_symbolic<32>(A, v, lane, keys[warp], refs[warp], masks[warp], nullptr);
+    column_symbolic_sort<32>(A, v, lane, sm[warp].srt.keys, sm[warp].srt.refs, sm[warp].srt.masks, sm[warp].srt.scan);
 }
 
 constexpr int BIG_THREADS = 256;
 constexpr size_t BIG_SMEM = size_t(CTA_CAP) * (8 + 4 + 2);
-// columns with more than WARP_CAP items: one block per column, looping over the list; columns beyond
-// CTA_CAP sort in a per-block global scratch region (need[0] reports the size required if it is too small)
+// columns the warp kernel could not take: one block per column, looping over the list; columns beyond CTA_CAP
+// sort in a per-block global scratch region (need[0] reports the size required if it is too small)
 __global__ void __launch_bounds__(BIG_THREADS)
     k_hess_symbolic_big(SymArgs A, int cta_cap, const int* __restrict__ big, const unsigned long long* nbig, char* scratch,
                         unsigned long long scratch_items, unsigned long long* need)
 {
     extern __shared__ __align__(16) char smem[];
-    __shared__ int red[3 * BIG_THREADS / 32];
+    __shared__ int scan[BIG_THREADS];
     const unsigned long long n = *nbig;
     for (unsigned long long idx = blockIdx.x; idx < n; idx += gridDim.x) {
         const int v = big[idx];
@@ -767,99 +914,66 @@ __global__ void __launch_bounds__(BIG_THREADS)
         unsigned long long* keys = reinterpret_cast<unsigned long long*>(base);
         unsigned* refs = reinterpret_cast<unsigned*>(base + cap * 8);
         unsigned short* masks = reinterpret_cast<unsigned short*>(base + cap * 12);
-        column_symbolic<BIG_THREADS>(A, v, threadIdx.x, keys, refs, masks, red);
+        column_symbolic_sort<BIG_THREADS>(A, v, threadIdx.x, keys, refs, masks, scan);
         __syncthreads();
     }
 }
 
-// Pass 2: one warp per column streams its sorted items in chunks of 32
+// ---- pass 2: one warp per column; 9 lanes per unique block (one per entry of the 3x3 block), three blocks at a time.
+// A lane walks its block's run in the fixed item order, adding entry k of every gathered block (the 9 lanes of a
+// group read 72 contiguous bytes) and noting whether any addend was non-zero: that IS the reference's pattern
+// (local_to_global.hpp:290-291).  Positions inside the three scalar columns follow from one ballot.
 __global__ void __launch_bounds__(32 * SYM_WARPS)
-    k_hess_numeric(int nV, const int* __restrict__ colR, const int* __restrict__ itemoff, const unsigned* __restrict__ sref,
-                   const int4* __restrict__ vid, const double* __restrict__ blk, const int* __restrict__ outer, int* __restrict__ inner,
-                   double* __restrict__ vals)
+    k_hess_numeric(int nV, const int* __restrict__ colR, const int* __restrict__ colU, const int* __restrict__ itemoff,
+                   const unsigned* __restrict__ sref, const int2* __restrict__ udesc, const double* __restrict__ blk,
+                   const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals)
 {
     const int lane = threadIdx.x & 31;
     const int v = blockIdx.x * SYM_WARPS + (threadIdx.x >> 5);
     if (v >= nV) return;
-    const int R = colR[v];
-    if (R == 0) return;
-    const unsigned* refs = sref + itemoff[v];
-    int base0 = outer[3 * size_t(v)], base1 = outer[3 * size_t(v) + 1], base2 = outer[3 * size_t(v) + 2];
-    double carry[9];
-    unsigned carry_mask = 0;
+    const int U = colU[v];
+    if (U == 0) return;
+    const int R = colR[v], ioff = itemoff[v];
+    const int g = lane / 9, k = lane - 9 * g, l = k % 3, r = k / 3;
+    const unsigned colmask = 0x1249249u << l; // lanes of the same scalar column
+    int base = g < 3 ? outer[3 * size_t(v) + l] : 0;
+    for (int u0 = 0; u0 < U; u0 += 3) {
+        const int u = u0 + g;
+        const bool valid = g < 3 && u < U;
+        int start = 0, len = 0, row = 0;
+        if (valid) {
+            const int2 d = udesc[ioff + u];
+            start = d.x, row = d.y;
+            len = (u + 1 < U ? udesc[ioff + u + 1].x : R) - start;
+        }
+        int maxlen = len;
 #pragma unroll
-    for (int k = 0; k < 9; k++) carry[k] = 0;
-    for (int q0 = 0; q0 < R; q0 += 32) {
-        const int q = q0 + lane;
-        const bool in = q < R;
-        unsigned ref = 0;
-        bool head = false;
-        double val[9];
-        unsigned mk = 0;
-        if (in) {
-            const unsigned r = refs[q];
-            head = (r & HEAD_BIT) != 0;
-            ref = r & ~HEAD_BIT;
-            const double* bp = blk + size_t(ref) * 9;
+        for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
+        const unsigned* rp = sref + ioff + start;
+        double acc = 0.0;
+        bool nz = false;
+        for (int j = 0; j < maxlen; j += 4) {
+            double val[4];
 #pragma unroll
-            for (int k = 0; k < 9; k++) {
-                val[k] = __ldg(bp + k);
-                mk |= (val[k] != 0.0) << k;
+            for (int x = 0; x < 4; x++) {
+                val[x] = 0.0;
+                if (j + x < len) val[x] = __ldg(blk + size_t(rp[j + x]) * 9 + k);
             }
-        } else {
 #pragma unroll
-            for (int k = 0; k < 9; k++) val[k] = 0;
+            for (int x = 0; x < 4; x++)
+                if (j + x < len) {
+                    acc += val[x];
+                    nz |= val[x] != 0.0;
+                }
         }
-        // the next item's head flag decides where a run ends
-        const unsigned next_ref = (q + 1 < R) ? refs[q + 1] : HEAD_BIT;
-        const bool tail = in && (next_ref & HEAD_BIT) != 0;
-        // segmented inclusive scan (sum of values, OR of masks) in item order; heads start segments
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        // distance to the start of this lane's segment within the chunk (lane + 1 if it began before the chunk)
-        const unsigned below = heads & (0xffffffffu >> (31 - lane));
-        const int seg_start = below ? 31 - __clz(below) : -1;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const bool take = lane - o >= seg_start && lane - o >= 0;
-#pragma unroll
-            for (int k = 0; k < 9; k++) {
-                const double up = __shfl_up_sync(0xffffffffu, val[k], o);
-                if (take) val[k] += up;
-            }
-            const unsigned um = __shfl_up_sync(0xffffffffu, mk, o);
-            if (take) mk |= um;
+        const bool present = valid && nz;
+        const unsigned pm = __ballot_sync(0xffffffffu, present) & colmask;
+        if (present) {
+            const int p = base + __popc(pm & ((1u << lane) - 1));
+            inner[p] = 3 * row + r;
+            vals[p] = acc;
         }
-        if (seg_start < 0) { // the run began in an earlier chunk
-#pragma unroll
-            for (int k = 0; k < 9; k++) val[k] = carry[k] + val[k];
-            mk |= carry_mask;
-        }
-        // entries of the finished runs
-        const int n0 = tail ? __popc(mk & 0x49u) : 0, n1 = tail ? __popc(mk & 0x92u) : 0, n2 = tail ? __popc(mk & 0x124u) : 0;
-        int p0 = n0, p1 = n1, p2 = n2;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u0 = __shfl_up_sync(0xffffffffu, p0, o), u1 = __shfl_up_sync(0xffffffffu, p1, o), u2 = __shfl_up_sync(0xffffffffu, p2, o);
-            if (lane >= o) p0 += u0, p1 += u1, p2 += u2;
-        }
-        if (tail) {
-            const int4 vv = vid[ref >> 4];
-            const int b = ref & 3u;
-            const int row = 3 * (b == 0 ? vv.x : (b == 1 ? vv.y : (b == 2 ? vv.z : vv.w)));
-            int w0 = base0 + p0 - n0, w1 = base1 + p1 - n1, w2 = base2 + p2 - n2;
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                if (mk & (1u << (3 * r))) inner[w0] = row + r, vals[w0] = val[3 * r], w0++;
-                if (mk & (1u << (3 * r + 1))) inner[w1] = row + r, vals[w1] = val[3 * r + 1], w1++;
-                if (mk & (1u << (3 * r + 2))) inner[w2] = row + r, vals[w2] = val[3 * r + 2], w2++;
-            }
-        }
-        base0 += __shfl_sync(0xffffffffu, p0, 31), base1 += __shfl_sync(0xffffffffu, p1, 31), base2 += __shfl_sync(0xffffffffu, p2, 31);
-        // carry the open run of lane 31 into the next chunk
-        const bool open = !__shfl_sync(0xffffffffu, (int)tail, 31);
-#pragma unroll
-        for (int k = 0; k < 9; k++) carry[k] = open ? __shfl_sync(0xffffffffu, val[k], 31) : 0.0;
-        carry_mask = open ? __shfl_sync(0xffffffffu, mk, 31) : 0u;
+        base += __popc(pm);
     }
 }
 
@@ -945,8 +1059,9 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     ctx->hbig.reserve(size_t(nV) + 1);
     unsigned long long* nbig = ctx->dCounters.p + 6;
     unsigned long long* need = ctx->dCounters.p + 7;
+    ctx->hudesc.reserve(nitems), ctx->hcolU.reserve(size_t(nV) + 1);
     const SymArgs A { nV, ctx->hkey_sorted.p, ctx->hcolinc.p, ctx->hcolR.p, ctx->hitemoff.p, ctx->hvid.p, ctx->hmask.p, ref_ev, ref_ee,
-                      ctx->hsref.p, ctx->hcnt.p };
+                      ctx->hsref.p, ctx->hudesc.p, ctx->hcolU.p, ctx->hcnt.p };
     if (!ctx->hess_attr_set) { // per device
         IPCB_CUDA(cudaFuncSetAttribute(k_hess_symbolic_big, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BIG_SMEM)));
         ctx->hess_attr_set = true;
@@ -956,9 +1071,10 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     int warp_cap = WARP_CAP, cta_cap = CTA_CAP;
     if (const char* e = getenv("IPCB_HESS_WARP_CAP")) warp_cap = std::min(WARP_CAP, std::max(1, atoi(e)));
     if (const char* e = getenv("IPCB_HESS_CTA_CAP")) cta_cap = std::min(CTA_CAP, std::max(1, atoi(e)));
+    const int use_hash = getenv("IPCB_HESS_NO_HASH") ? 0 : 1;
     for (int attempt = 0;; attempt++) {
         IPCB_CUDA(cudaMemsetAsync(nbig, 0, 2 * sizeof(unsigned long long), s));
-        k_hess_symbolic<<<grid_for(size_t(nV) + 1, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(A, warp_cap, ctx->hbig.p, nbig);
+        k_hess_symbolic<<<grid_for(size_t(nV) + 1, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(A, warp_cap, use_hash, ctx->hbig.p, nbig);
         k_hess_symbolic_big<<<big_grid, BIG_THREADS, BIG_SMEM, s>>>(A, cta_cap, ctx->hbig.p, nbig, ctx->hscratch.p, ctx->hscratch_items, need);
         ctx->launches += 2;
         // 4. scalar column pointers, nnz
@@ -976,8 +1092,8 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     ctx->nnz = *reinterpret_cast<int*>(&ctx->pinned.p[9]);
     ctx->inner.reserve(std::max<int64_t>(ctx->nnz, 1)), ctx->vals.reserve(std::max<int64_t>(ctx->nnz, 1));
     // 5. pass 2: gather, run-sum, write compressed columns
-    k_hess_numeric<<<grid_for(nV, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hvid.p, ctx->hblk.p,
-                                                                       ctx->outer.p, ctx->inner.p, ctx->vals.p);
+    k_hess_numeric<<<grid_for(nV, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p,
+                                                                       ctx->hblk.p, ctx->outer.p, ctx->inner.p, ctx->vals.p);
     ctx->launches++;
     IPCB_CUDA(cudaGetLastError());
 }

@@ -131,13 +131,18 @@ def test_step_size(cuda, oracle, scenes, name):
             assert oracle.is_step_collision_free(mesh, V0, V0 + 0.999 * ti_g * (V1 - V0), md)
 
 
-@pytest.mark.parametrize("caps", [(64, 8192), (32, 128)])
-def test_hessian_big_column_paths(cuda, oracle, scenes, caps, monkeypatch):
-    """columns beyond one warp's shared memory go to the block-per-column kernel, columns beyond a block's shared
-    memory sort in global scratch: force both hand-overs on a small scene and compare with the oracle"""
+@pytest.mark.parametrize("hooks", [
+    {},  # hash path with fall-back to the sort path for columns with more than 128 unique row vertices
+    {"IPCB_HESS_NO_HASH": "1"},  # warp sort path, block path for columns beyond 512 row blocks
+    {"IPCB_HESS_NO_HASH": "1", "IPCB_HESS_WARP_CAP": "64"},  # most columns on the block-per-column kernel
+    {"IPCB_HESS_NO_HASH": "1", "IPCB_HESS_WARP_CAP": "32", "IPCB_HESS_CTA_CAP": "128"},  # ... sorting in global scratch
+])
+def test_hessian_column_paths(cuda, oracle, scenes, hooks, monkeypatch):
+    """Hessian assembly: every per-column path (hash de-duplication in one warp, warp sort, block-per-column sort in
+    shared memory, block sort in global scratch) must produce the oracle's matrix"""
     V0, V1, E, F, P = scenes.dense_sheet(14, 6.0)
-    monkeypatch.setenv("IPCB_HESS_WARP_CAP", str(caps[0]))
-    monkeypatch.setenv("IPCB_HESS_CTA_CAP", str(caps[1]))
+    for k, v in hooks.items():
+        monkeypatch.setenv(k, v)
     res = []
     for api in (cuda, oracle):
         mesh = api.CollisionMesh(V0, E, F)
