@@ -178,9 +178,10 @@ __device__ inline unsigned long long expand21(unsigned long long v)
     v = (v | v << 2) & 0x1249249249249249ull;
     return v;
 }
-__global__ void k_morton(int n, const FBox* __restrict__ box, const float* __restrict__ scene,
+__global__ void k_morton(int n, int bits, const FBox* __restrict__ box, const float* __restrict__ scene,
                          unsigned long long* __restrict__ key, int* __restrict__ ord)
 {
+    const double cells = double(1u << bits);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const FBox b = box[i];
@@ -189,7 +190,7 @@ __global__ void k_morton(int n, const FBox* __restrict__ box, const float* __res
     for (int k = 0; k < 3; k++) {
         const double w = double(scene[3 + k]) - double(scene[k]);
         double m = w > 0 ? (0.5 * (double(b.lo[k]) + double(b.hi[k])) - double(scene[k])) / w : 0.0;
-        m = fmin(fmax(m * 2097152.0, 0.0), 2097151.0);
+        m = fmin(fmax(m * cells, 0.0), cells - 1.0);
         code |= expand21((unsigned long long)m) << (2 - k);
     }
     key[i] = code;
@@ -279,13 +280,18 @@ __global__ void k_refit(int n, const FBox* __restrict__ sbox, Node* nodes, const
     }
 }
 
-static void sort_keys(ipcb_ctx* ctx, Tree& t, int n)
+// Morton resolution per axis.  The candidate SET does not depend on the tree (SURVEY §7 hard part 1), only the
+// traversal cost does, so the keys only need enough cells to separate neighbouring primitives: 10 bits per axis
+// (4 radix passes) up to 4M primitives, 13 (5 passes) up to 64M, the reference's 21 (8 passes) beyond.
+static int morton_bits(int n) { return n <= (1 << 22) ? 10 : (n <= (1 << 26) ? 13 : 21); }
+
+static void sort_keys(ipcb_ctx* ctx, Tree& t, int n, int bits)
 {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 63, ctx->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 3 * bits, ctx->stream);
     t.tmp.reserve(bytes);
-    cub::DeviceRadixSort::SortPairs(t.tmp.p, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 63, ctx->stream);
-    ctx->launches += 9; // onesweep: histogram + exclusive sum + 7 passes of 8+ bits (approximate)
+    cub::DeviceRadixSort::SortPairs(t.tmp.p, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 3 * bits, ctx->stream);
+    ctx->launches += 2 + (3 * bits + 7) / 8; // onesweep: histogram + exclusive sum + one pass per 8 bits
 }
 
 // Morton-sort a PrimSet; with_nodes additionally builds the hierarchy
@@ -298,8 +304,9 @@ static void build_tree(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, bool with_node
     cudaStream_t s = ctx->stream;
     t.key.reserve(n), t.key_sorted.reserve(n), t.ord.reserve(n), t.ord_sorted.reserve(n);
     t.sbox.reserve(n), t.sprim.reserve(n);
-    k_morton<<<grid_for(n, 256), 256, 0, s>>>(n, ps.box.p, ctx->scene.p, t.key.p, t.ord.p);
-    sort_keys(ctx, t, n);
+    const int bits = morton_bits(n);
+    k_morton<<<grid_for(n, 256), 256, 0, s>>>(n, bits, ps.box.p, ctx->scene.p, t.key.p, t.ord.p);
+    sort_keys(ctx, t, n, bits);
     k_apply_order<<<grid_for(n, 256), 256, 0, s>>>(n, t.ord_sorted.p, ps.box.p, ps.prim.p, t.sbox.p, t.sprim.p);
     ctx->launches += 2;
     if (!with_nodes || n < 2) {

@@ -32,6 +32,8 @@ template <int N> __device__ __forceinline__ void jacobi_reg(double (&A)[N][N], d
 #pragma unroll
         for (int j = i; j < N; j++) tot = fma(A[i][j], A[i][j], tot);
     const double stop = tot * 1e-33;
+    // an entry whose square is below stop / #pairs cannot keep the sweep loop alive: rotating it away is wasted work
+    const double skip = stop / double(N * (N - 1) / 2);
 #pragma unroll 1
     for (int sweep = 0; sweep < 30; sweep++) {
         double off = 0;
@@ -45,7 +47,7 @@ template <int N> __device__ __forceinline__ void jacobi_reg(double (&A)[N][N], d
 #pragma unroll
             for (int q = p + 1; q < N; q++) {
                 const double apq = A[p][q];
-                if (apq != 0.0) {
+                if (apq * apq > skip) {
                     const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
                     const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
                     const double c = rsqrt(fma(t, t, 1.0)), s = t * c;

@@ -923,6 +923,26 @@ __global__ void __launch_bounds__(BIG_THREADS)
 // A lane walks its block's run in the fixed item order, adding entry k of every gathered block (the 9 lanes of a
 // group read 72 contiguous bytes) and noting whether any addend was non-zero: that IS the reference's pattern
 // (local_to_global.hpp:290-291).  Positions inside the three scalar columns follow from one ballot.
+// The loads form a dependent chain (descriptor -> block references -> blocks); it is software-pipelined: while the
+// blocks of one group of runs are in flight, the descriptors and references of the next group are fetched.
+constexpr int NUM_BATCH = 8; // block references fetched ahead per run
+struct RunRefs {
+    int start, len, row;
+    unsigned ref[NUM_BATCH];
+};
+__device__ __forceinline__ RunRefs load_run(const int2* __restrict__ ud, const unsigned* __restrict__ sr, int u, int U, int R, bool lane_ok)
+{
+    RunRefs rr;
+    rr.start = 0, rr.len = 0, rr.row = 0;
+    if (lane_ok && u < U) {
+        const int2 d = ud[u];
+        rr.start = d.x, rr.row = d.y;
+        rr.len = (u + 1 < U ? ud[u + 1].x : R) - d.x;
+    }
+#pragma unroll
+    for (int x = 0; x < NUM_BATCH; x++) rr.ref[x] = x < rr.len ? sr[rr.start + x] : 0u;
+    return rr;
+}
 __global__ void __launch_bounds__(32 * SYM_WARPS)
     k_hess_numeric(int nV, const int* __restrict__ colR, const int* __restrict__ colU, const int* __restrict__ itemoff,
                    const unsigned* __restrict__ sref, const int2* __restrict__ udesc, const double* __restrict__ blk,
@@ -935,45 +955,42 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
     if (U == 0) return;
     const int R = colR[v], ioff = itemoff[v];
     const int g = lane / 9, k = lane - 9 * g, l = k % 3, r = k / 3;
+    const bool lane_ok = g < 3;
     const unsigned colmask = 0x1249249u << l; // lanes of the same scalar column
-    int base = g < 3 ? outer[3 * size_t(v) + l] : 0;
+    const int2* ud = udesc + ioff;
+    const unsigned* sr = sref + ioff;
+    int base = lane_ok ? outer[3 * size_t(v) + l] : 0;
+    RunRefs cur = load_run(ud, sr, g, U, R, lane_ok);
     for (int u0 = 0; u0 < U; u0 += 3) {
-        const int u = u0 + g;
-        const bool valid = g < 3 && u < U;
-        int start = 0, len = 0, row = 0;
-        if (valid) {
-            const int2 d = udesc[ioff + u];
-            start = d.x, row = d.y;
-            len = (u + 1 < U ? udesc[ioff + u + 1].x : R) - start;
-        }
-        int maxlen = len;
+        double val[NUM_BATCH];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, o));
-        const unsigned* rp = sref + ioff + start;
+        for (int x = 0; x < NUM_BATCH; x++) {
+            val[x] = 0.0;
+            if (x < cur.len) val[x] = __ldg(blk + size_t(cur.ref[x]) * 9 + k);
+        }
+        const RunRefs nxt = load_run(ud, sr, u0 + 3 + g, U, R, lane_ok); // overlaps with the block loads above
         double acc = 0.0;
         bool nz = false;
-        for (int j = 0; j < maxlen; j += 4) {
-            double val[4];
 #pragma unroll
-            for (int x = 0; x < 4; x++) {
-                val[x] = 0.0;
-                if (j + x < len) val[x] = __ldg(blk + size_t(rp[j + x]) * 9 + k);
+        for (int x = 0; x < NUM_BATCH; x++)
+            if (x < cur.len) {
+                acc += val[x];
+                nz |= val[x] != 0.0;
             }
-#pragma unroll
-            for (int x = 0; x < 4; x++)
-                if (j + x < len) {
-                    acc += val[x];
-                    nz |= val[x] != 0.0;
-                }
+        for (int j = NUM_BATCH; j < cur.len; j++) { // long runs: the remainder, in order
+            const double w = __ldg(blk + size_t(sr[cur.start + j]) * 9 + k);
+            acc += w;
+            nz |= w != 0.0;
         }
-        const bool present = valid && nz;
+        const bool present = cur.len > 0 && nz;
         const unsigned pm = __ballot_sync(0xffffffffu, present) & colmask;
         if (present) {
             const int p = base + __popc(pm & ((1u << lane) - 1));
-            inner[p] = 3 * row + r;
+            inner[p] = 3 * cur.row + r;
             vals[p] = acc;
         }
         base += __popc(pm);
+        cur = nxt;
     }
 }
 
