@@ -418,6 +418,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK)
                 walking = false;
             }
         }
+        if (!__any_sync(0xffffffffu, hit0 >= 0 || hit1 >= 0)) continue; // most visited nodes are inner nodes of inner nodes
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const int hit = h == 0 ? hit0 : hit1;

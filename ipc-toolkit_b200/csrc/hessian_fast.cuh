@@ -19,7 +19,44 @@
 
 namespace ipcb {
 
-// cyclic Jacobi, fully unrolled: A symmetric (upper triangle used), V eigenvectors in columns
+// Jacobi rotation parameters for the pivot (app, apq, aqq): t = tan(phi) of the smaller rotation angle.
+// With d = aqq - app and h = 2 apq:  t = h / (d + sign(d) sqrt(d^2 + h^2))  — one square root and one division.
+__device__ __forceinline__ void jacobi_params(double app, double apq, double aqq, double& t, double& c, double& s)
+{
+    const double d = aqq - app, h = 2.0 * apq;
+    t = h / (d + copysign(sqrt(fma(d, d, h * h)), d));
+    c = rsqrt(fma(t, t, 1.0));
+    s = t * c;
+}
+// apply the rotation in the (p, q) plane to A (upper triangle) and accumulate it into V
+template <int N> __device__ __forceinline__ void jacobi_apply(double (&A)[N][N], double (&V)[N][N], int p, int q, double t, double c, double s)
+{
+    const double apq = A[p][q];
+    A[p][p] = fma(-t, apq, A[p][p]);
+    A[q][q] = fma(t, apq, A[q][q]);
+    A[p][q] = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        if (k != p && k != q) {
+            double& akp = k < p ? A[k][p] : A[p][k];
+            double& akq = k < q ? A[k][q] : A[q][k];
+            const double x = akp, y = akq;
+            akp = fma(c, x, -s * y);
+            akq = fma(s, x, c * y);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        const double x = V[k][p], y = V[k][q];
+        V[k][p] = fma(c, x, -s * y);
+        V[k][q] = fma(s, x, c * y);
+    }
+}
+
+// Jacobi eigen-solver, fully unrolled in registers: A symmetric (upper triangle used), V eigenvectors in columns.
+// Parallel (round-robin) ordering: the pivots of one round are disjoint, so their parameters (the serial part:
+// a square root, a division and a reciprocal square root each) are independent instruction chains that the
+// scheduler overlaps; rotations on disjoint planes commute, so they are applied one after the other.
 template <int N> __device__ __forceinline__ void jacobi_reg(double (&A)[N][N], double (&V)[N][N])
 {
 #pragma unroll
@@ -34,6 +71,7 @@ template <int N> __device__ __forceinline__ void jacobi_reg(double (&A)[N][N], d
     const double stop = tot * 1e-33;
     // an entry whose square is below stop / #pairs cannot keep the sweep loop alive: rotating it away is wasted work
     const double skip = stop / double(N * (N - 1) / 2);
+    constexpr int M = (N % 2) ? N : N - 1; // rounds per sweep
 #pragma unroll 1
     for (int sweep = 0; sweep < 30; sweep++) {
         double off = 0;
@@ -43,35 +81,27 @@ template <int N> __device__ __forceinline__ void jacobi_reg(double (&A)[N][N], d
             for (int q = p + 1; q < N; q++) off = fma(A[p][q], A[p][q], off);
         if (off <= stop) break;
 #pragma unroll
-        for (int p = 0; p < N - 1; p++) {
+        for (int r = 0; r < M; r++) {
+            // pairs of round r: i + j = r (mod M) among 0..M-1; for even N the index N-1 meets the one left over
+            double t[N / 2], c[N / 2], s[N / 2];
+            bool on[N / 2];
+            int pp[N / 2], qq[N / 2];
+            int np = 0;
 #pragma unroll
-            for (int q = p + 1; q < N; q++) {
-                const double apq = A[p][q];
-                if (apq * apq > skip) {
-                    const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-                    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
-                    const double c = rsqrt(fma(t, t, 1.0)), s = t * c;
-                    A[p][p] = fma(-t, apq, A[p][p]);
-                    A[q][q] = fma(t, apq, A[q][q]);
-                    A[p][q] = 0.0;
-#pragma unroll
-                    for (int k = 0; k < N; k++) {
-                        if (k != p && k != q) {
-                            double& akp = k < p ? A[k][p] : A[p][k];
-                            double& akq = k < q ? A[k][q] : A[q][k];
-                            const double x = akp, y = akq;
-                            akp = fma(c, x, -s * y);
-                            akq = fma(s, x, c * y);
-                        }
-                    }
-#pragma unroll
-                    for (int k = 0; k < N; k++) {
-                        const double x = V[k][p], y = V[k][q];
-                        V[k][p] = fma(c, x, -s * y);
-                        V[k][q] = fma(s, x, c * y);
-                    }
-                }
+            for (int i = 0; i < M; i++) {
+                const int j = ((r - i) % M + M) % M;
+                if (i < j) pp[np] = i, qq[np] = j, np++;
+                else if (i == j && N % 2 == 0) pp[np] = i, qq[np] = N - 1, np++;
             }
+#pragma unroll
+            for (int k = 0; k < N / 2; k++) {
+                const double apq = A[pp[k]][qq[k]];
+                on[k] = apq * apq > skip;
+                if (on[k]) jacobi_params(A[pp[k]][pp[k]], apq, A[qq[k]][qq[k]], t[k], c[k], s[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < N / 2; k++)
+                if (on[k]) jacobi_apply<N>(A, V, pp[k], qq[k], t[k], c[k], s[k]);
         }
     }
 }

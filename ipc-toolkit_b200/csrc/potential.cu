@@ -548,9 +548,16 @@ __global__ void __launch_bounds__(128)
             }
         }
         __syncwarp();
-        for (int f = lane; f < 32 * ROW; f += 32) {
-            const int cl = f / ROW, j = f - cl * ROW;
-            if ((emask >> cl) & 1u) out.blk[(gw + cl) * (HSLOTS * 9) + a * 36 + j] = stage[warp][cl][j];
+        {
+            int cl = 0, j = lane; // flat index lane + 32 * it over the warp's 32 x ROW staged doubles, without a division
+            while (j >= ROW) j -= ROW, cl++;
+            double* dst = out.blk + gw * (HSLOTS * 9) + a * 36;
+#pragma unroll 4
+            for (int it = 0; it < ROW; it++) {
+                if ((emask >> cl) & 1u) dst[size_t(cl) * (HSLOTS * 9) + j] = stage[warp][cl][j];
+                j += 32;
+                while (j >= ROW) j -= ROW, cl++;
+            }
         }
         __syncwarp();
     }
