@@ -269,7 +269,9 @@ def main():
     l1 = C.c_int64()
     lib.ctx_launch_count(ctx, C.byref(l1))
     launches = (l1.value - l0.value) // (args.steps + args.warmup) * args.steps
+    lib.ctx_enable_stage_timing(ctx, 1)
     device_step(record=True)  # one extra, untimed pass to read the per-stage device times
+    lib.ctx_enable_stage_timing(ctx, 0)
     lib.check(lib.candidates_build_swept_dev(ctx, C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr()), nV, 0.0, counts))
     info["ccd_candidates"] = list(counts)
 
@@ -306,7 +308,7 @@ def main():
     sampler.stop_flag = True
 
     # ---- roofline of the dominant stage (algorithmic bytes: DESIGN.md "Kernels and rooflines")
-    stages = {k: float(np.mean(v)) for k, v in stage_acc.items()}
+    stages = {k: float(np.sum(v)) for k, v in stage_acc.items()}  # one recorded step: stages that run twice (static + swept) add up
     peak, peak_kind = load_peaks()
     ncoll = info.get("collisions", [0, 0, 0, 0])
     nblk = 4 * ncoll[0] + 9 * ncoll[1] + 16 * (ncoll[2] + ncoll[3])

@@ -206,7 +206,10 @@ int IPCB_FN(ccd_stepsize_from_candidates_dev)(ipcb_ctx* ctx, const double* dV0, 
 int IPCB_FN(ctx_set_shard)(ipcb_ctx* ctx, int32_t rank, int32_t world);
 /* number of kernels this context has launched so far (bench.py gpu_launches) */
 int IPCB_FN(ctx_launch_count)(ipcb_ctx* ctx, int64_t* n);
-/* per-stage device time of the last call in ms, by stage name; returns the number of stages filled */
+/* per-stage device time of the last call in ms, by stage name; returns the number of stages filled.
+ * Stage timing synchronises the stream at every stage boundary, so it is OFF by default: switch it on
+ * with ctx_enable_stage_timing(ctx, 1) for a profiling pass (bench.py does, outside its timed region). */
+int IPCB_FN(ctx_enable_stage_timing)(ipcb_ctx* ctx, int32_t on);
 int IPCB_FN(ctx_stage_times)(ipcb_ctx* ctx, int32_t max_stages, const char** names, float* ms);
 #endif
 

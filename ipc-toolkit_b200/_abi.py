@@ -65,6 +65,7 @@ DEVICE_API = {
     "ccd_stepsize_from_candidates_dev": (C.c_int, [P, P, P, c_i32, c_f64, C.POINTER(CcdParams), P]),
     "ctx_set_shard": (C.c_int, [P, c_i32, c_i32]),
     "ctx_launch_count": (C.c_int, [P, C.POINTER(c_i64)]),
+    "ctx_enable_stage_timing": (C.c_int, [P, c_i32]),
     "ctx_stage_times": (C.c_int, [P, c_i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
 }
 

@@ -81,6 +81,13 @@ int ipcb_ctx_create(int device, ipcb_ctx** out)
         ipcb_ctx* ctx = new ipcb_ctx();
         ctx->device = device;
         IPCB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        const bool single_stream = getenv("IPCB_SINGLE_STREAM") != nullptr; // A/B switch: no intra-call concurrency
+        for (int k = 0; k < ipcb_ctx::NAUX; k++) {
+            if (single_stream) ctx->aux[k] = ctx->stream;
+            else IPCB_CUDA(cudaStreamCreateWithFlags(&ctx->aux[k], cudaStreamNonBlocking));
+            IPCB_CUDA(cudaEventCreateWithFlags(&ctx->ev_join[k], cudaEventDisableTiming));
+        }
+        IPCB_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
         ctx->pinned.init(32);
         ctx->dCounters.reserve(32);
         IPCB_CUDA(cudaMemsetAsync(ctx->dCounters.p, 0, 32 * sizeof(unsigned long long), ctx->stream));
@@ -93,6 +100,12 @@ void ipcb_ctx_destroy(ipcb_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < ipcb_ctx::NAUX; k++) {
+        cudaStreamSynchronize(ctx->aux[k]);
+        if (ctx->aux[k] != ctx->stream) cudaStreamDestroy(ctx->aux[k]);
+        cudaEventDestroy(ctx->ev_join[k]);
+    }
+    cudaEventDestroy(ctx->ev_fork);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -109,6 +122,11 @@ int ipcb_ctx_set_shard(ipcb_ctx* ctx, int32_t rank, int32_t world)
 int ipcb_ctx_launch_count(ipcb_ctx* ctx, int64_t* n)
 {
     *n = ctx->launches;
+    return 0;
+}
+int ipcb_ctx_enable_stage_timing(ipcb_ctx* ctx, int32_t on)
+{
+    ctx->timing = on != 0;
     return 0;
 }
 int ipcb_ctx_stage_times(ipcb_ctx* ctx, int32_t max_stages, const char** names, float* ms)

@@ -285,28 +285,28 @@ __global__ void k_refit(int n, const FBox* __restrict__ sbox, Node* nodes, const
 // (4 radix passes) up to 4M primitives, 13 (5 passes) up to 64M, the reference's 21 (8 passes) beyond.
 static int morton_bits(int n) { return n <= (1 << 22) ? 10 : (n <= (1 << 26) ? 13 : 21); }
 
-static void sort_keys(ipcb_ctx* ctx, Tree& t, int n, int bits)
+static void sort_keys(ipcb_ctx* ctx, Tree& t, int n, int bits, cudaStream_t s)
 {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 3 * bits, ctx->stream);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 3 * bits, s);
     t.tmp.reserve(bytes);
-    cub::DeviceRadixSort::SortPairs(t.tmp.p, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 3 * bits, ctx->stream);
+    cub::DeviceRadixSort::SortPairs(t.tmp.p, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 3 * bits, s);
     ctx->launches += 2 + (3 * bits + 7) / 8; // onesweep: histogram + exclusive sum + one pass per 8 bits
 }
 
 // Morton-sort a PrimSet; with_nodes additionally builds the hierarchy
-static void build_tree(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, bool with_nodes)
+static void build_tree(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, bool with_nodes, cudaStream_t s = nullptr)
 {
     const int n = ps.n;
     t.n = n;
     t.has_nodes = false;
     if (n == 0) return;
-    cudaStream_t s = ctx->stream;
+    if (!s) s = ctx->stream;
     t.key.reserve(n), t.key_sorted.reserve(n), t.ord.reserve(n), t.ord_sorted.reserve(n);
     t.sbox.reserve(n), t.sprim.reserve(n);
     const int bits = morton_bits(n);
     k_morton<<<grid_for(n, 256), 256, 0, s>>>(n, bits, ps.box.p, ctx->scene.p, t.key.p, t.ord.p);
-    sort_keys(ctx, t, n, bits);
+    sort_keys(ctx, t, n, bits, s);
     k_apply_order<<<grid_for(n, 256), 256, 0, s>>>(n, t.ord_sorted.p, ps.box.p, ps.prim.p, t.sbox.p, t.sprim.p);
     ctx->launches += 2;
     if (!with_nodes || n < 2) {
@@ -350,17 +350,27 @@ void broad_build(ipcb_ctx* ctx, bool swept, double r)
 constexpr int TRAV_BLOCK = 128;
 constexpr int STAGE_CAP = 160; // per-warp staging slots; flushed when > STAGE_CAP - 64
 
-__device__ inline bool shares_vertex(int4 a, int4 b)
+// lbvh.cpp:801-873 with can_vertices_collide == true; QN / TN = vertices of the query / target primitive
+template <int QN, int TN> __device__ __forceinline__ bool shares_vertex(int4 a, int4 b)
 {
-    // lbvh.cpp:801-873 with can_vertices_collide == true; -1 entries are padding
-    bool s = a.x == b.x || (b.y >= 0 && a.x == b.y) || (b.z >= 0 && a.x == b.z);
-    if (a.y >= 0) s |= a.y == b.x || (b.y >= 0 && a.y == b.y) || (b.z >= 0 && a.y == b.z);
-    if (a.z >= 0) s |= a.z == b.x || (b.y >= 0 && a.z == b.y) || (b.z >= 0 && a.z == b.z);
+    bool s = a.x == b.x;
+    if (TN > 1) s |= a.x == b.y;
+    if (TN > 2) s |= a.x == b.z;
+    if (QN > 1) {
+        s |= a.y == b.x;
+        if (TN > 1) s |= a.y == b.y;
+        if (TN > 2) s |= a.y == b.z;
+    }
+    if (QN > 2) {
+        s |= a.z == b.x;
+        if (TN > 1) s |= a.z == b.y;
+        if (TN > 2) s |= a.z == b.z;
+    }
     return s;
 }
 
 // MODE 0: emit (query, target); 1: emit (target, query); 2: self, emit (min, max)
-template <int MODE>
+template <int MODE, int QN, int TN>
 __global__ void __launch_bounds__(TRAV_BLOCK)
     k_traverse(int q_begin, int q_end, const FBox* __restrict__ qbox, const int4* __restrict__ qprim,
                const Node* __restrict__ nodes, int n_target, const FBox* __restrict__ tbox, const int4* __restrict__ tprim,
@@ -390,13 +400,52 @@ __global__ void __launch_bounds__(TRAV_BLOCK)
         }
     }
     bool walking = active && n_target > 1;
-    while (__any_sync(0xffffffffu, walking || single >= 0)) {
-        int hit0 = single, hit1 = -1;
-        single = -1;
+    // Leaf hits need the target primitive's vertex ids (shared-vertex rejection, primitive id): a dependent
+    // scattered load.  It is software-pipelined: the ids of the hits found at one node are requested right away
+    // and consumed one iteration later, after the NEXT node's fetch has been issued, so the two latencies overlap.
+    int pend0 = single, pend1 = -1;
+    int4 tp0 = make_int4(0, 0, 0, 0), tp1 = tp0;
+    if (pend0 >= 0) tp0 = __ldg(tprim + pend0);
+    while (__any_sync(0xffffffffu, walking || pend0 >= 0 || pend1 >= 0)) {
+        float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+        int4 d = make_int4(0, 0, 0, 0);
         if (walking) {
             const float4* np = reinterpret_cast<const float4*>(nodes + node);
-            const float4 a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
-            const int4 d = __ldg(reinterpret_cast<const int4*>(np + 3));
+            a = __ldg(np), b = __ldg(np + 1), c = __ldg(np + 2);
+            d = __ldg(reinterpret_cast<const int4*>(np + 3));
+        }
+        if (__any_sync(0xffffffffu, pend0 >= 0 || pend1 >= 0)) { // most visited nodes have no leaf children that overlap
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int hit = h == 0 ? pend0 : pend1;
+                const int4 tp = h == 0 ? tp0 : tp1;
+                bool emit = false;
+                int2 pr = make_int2(0, 0);
+                if (hit >= 0 && (!check_shared || !shares_vertex<QN, TN>(qp, tp))) {
+                    emit = true;
+                    if (MODE == 0) pr = make_int2(qp.w, tp.w);
+                    else if (MODE == 1) pr = make_int2(tp.w, qp.w);
+                    else pr = make_int2(min(qp.w, tp.w), max(qp.w, tp.w));
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, emit);
+                if (m) {
+                    if (emit) stage[warp][nstaged + __popc(m & ((1u << lane) - 1))] = pr;
+                    nstaged += __popc(m);
+                }
+            }
+            if (nstaged > STAGE_CAP - 64) {
+                __syncwarp();
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(counter, (unsigned long long)nstaged);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (int k = lane; k < nstaged; k += 32)
+                    if (base + k < capacity) out[base + k] = stage[warp][k];
+                nstaged = 0;
+                __syncwarp();
+            }
+        }
+        pend0 = pend1 = -1;
+        if (walking) {
             // layout: lo[0] = a.xyz, lo[1] = (a.w, b.x, b.y), hi[0] = (b.z, b.w, c.x), hi[1] = c.yzw
             bool ol = q.lo[0] <= b.z && a.x <= q.hi[0] && q.lo[1] <= b.w && a.y <= q.hi[1] && q.lo[2] <= c.x && a.z <= q.hi[2];
             bool orr = q.lo[0] <= c.y && a.w <= q.hi[0] && q.lo[1] <= c.z && b.x <= q.hi[1] && q.lo[2] <= c.w && b.y <= q.hi[2];
@@ -404,8 +453,8 @@ __global__ void __launch_bounds__(TRAV_BLOCK)
                 ol = ol && d.z > qi;
                 orr = orr && d.w > qi;
             }
-            if (ol && d.x < 0) hit0 = ~d.x;
-            if (orr && d.y < 0) hit1 = ~d.y;
+            if (ol && d.x < 0) pend0 = ~d.x, tp0 = __ldg(tprim + pend0);
+            if (orr && d.y < 0) pend1 = ~d.y, tp1 = __ldg(tprim + pend1);
             const bool tl = ol && d.x >= 0, tr = orr && d.y >= 0;
             if (tl) {
                 node = d.x;
@@ -418,37 +467,6 @@ __global__ void __launch_bounds__(TRAV_BLOCK)
                 walking = false;
             }
         }
-        if (!__any_sync(0xffffffffu, hit0 >= 0 || hit1 >= 0)) continue; // most visited nodes are inner nodes of inner nodes
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int hit = h == 0 ? hit0 : hit1;
-            bool emit = false;
-            int2 pr = make_int2(0, 0);
-            if (hit >= 0) {
-                const int4 tp = __ldg(tprim + hit);
-                if (!check_shared || !shares_vertex(qp, tp)) {
-                    emit = true;
-                    if (MODE == 0) pr = make_int2(qp.w, tp.w);
-                    else if (MODE == 1) pr = make_int2(tp.w, qp.w);
-                    else pr = make_int2(min(qp.w, tp.w), max(qp.w, tp.w));
-                }
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, emit);
-            if (m) {
-                if (emit) stage[warp][nstaged + __popc(m & ((1u << lane) - 1))] = pr;
-                nstaged += __popc(m);
-            }
-        }
-        if (nstaged > STAGE_CAP - 64) {
-            __syncwarp();
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(counter, (unsigned long long)nstaged);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            for (int k = lane; k < nstaged; k += 32)
-                if (base + k < capacity) out[base + k] = stage[warp][k];
-            nstaged = 0;
-            __syncwarp();
-        }
     }
     if (nstaged > 0) {
         __syncwarp();
@@ -460,47 +478,82 @@ __global__ void __launch_bounds__(TRAV_BLOCK)
     }
 }
 
-// run one detection: queries (sorted view) against a tree
-static void run_traverse(ipcb_ctx* ctx, const Tree& q, const Tree& t, int mode, bool check_shared, PairList& out, bool shard)
-{
-    out.count = 0;
-    out.sorted = false;
-    if (q.n == 0 || t.n == 0 || (mode == 2 && t.n < 2)) return;
-    cudaStream_t s = ctx->stream;
-    int q_begin = 0, q_end = q.n;
-    if (shard && ctx->shard_world > 1) { // contiguous Morton range of query leaves per rank
-        q_begin = int((int64_t(q.n) * ctx->shard_rank) / ctx->shard_world);
-        q_end = int((int64_t(q.n) * (ctx->shard_rank + 1)) / ctx->shard_world);
+// one detection: queries (sorted view) against a tree.  launch() enqueues the kernel and the read-back of the
+// pair count on the job's stream; finish() waits for it and, if the output buffer was too small, grows it and
+// repeats the pass.  Two jobs on different streams / counter slots run concurrently.
+struct TraverseJob {
+    ipcb_ctx* ctx;
+    const Tree* q;
+    const Tree* t;
+    int mode, qn, tn;
+    bool check_shared;
+    PairList* out;
+    cudaStream_t s;
+    int slot; // device counter / pinned slot (0 or 1)
+    int q_begin = 0, q_end = 0;
+    bool live = false;
+
+    void launch(bool shard)
+    {
+        out->count = 0;
+        out->sorted = false;
+        live = false;
+        if (q->n == 0 || t->n == 0 || (mode == 2 && t->n < 2)) return;
+        q_begin = 0, q_end = q->n;
+        if (shard && ctx->shard_world > 1) { // contiguous Morton range of query leaves per rank
+            q_begin = int((int64_t(q->n) * ctx->shard_rank) / ctx->shard_world);
+            q_end = int((int64_t(q->n) * (ctx->shard_rank + 1)) / ctx->shard_world);
+        }
+        if (q_end - q_begin <= 0) return;
+        if (out->pairs.cap == 0) out->pairs.reserve(size_t(q_end - q_begin) * 8 + 1024);
+        live = true;
+        enqueue();
     }
-    const int nq = q_end - q_begin;
-    if (nq <= 0) return;
-    if (out.pairs.cap == 0) out.pairs.reserve(size_t(nq) * 8 + 1024);
-    for (int attempt = 0; attempt < 3; attempt++) {
-        IPCB_CUDA(cudaMemsetAsync(ctx->dCounters.p, 0, sizeof(unsigned long long), s));
-        const unsigned long long cap = out.pairs.cap;
-        const unsigned grid = grid_for(nq, TRAV_BLOCK);
-        const Node* nodes = t.nodes.p;
-        if (mode == 0)
-            k_traverse<0><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q.sbox.p, q.sprim.p, nodes, t.n, t.sbox.p, t.sprim.p, out.pairs.p,
-                                                      ctx->dCounters.p, cap, check_shared);
-        else if (mode == 1)
-            k_traverse<1><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q.sbox.p, q.sprim.p, nodes, t.n, t.sbox.p, t.sprim.p, out.pairs.p,
-                                                      ctx->dCounters.p, cap, check_shared);
-        else
-            k_traverse<2><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q.sbox.p, q.sprim.p, nodes, t.n, t.sbox.p, t.sprim.p, out.pairs.p,
-                                                      ctx->dCounters.p, cap, check_shared);
+    void enqueue()
+    {
+        unsigned long long* counter = ctx->dCounters.p + 16 + slot;
+        IPCB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
+        const unsigned long long cap = out->pairs.cap;
+        const unsigned grid = grid_for(q_end - q_begin, TRAV_BLOCK);
+#define IPCB_TRAVERSE(M, QN, TN)                                                                                                    \
+    k_traverse<M, QN, TN><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes.p, t->n, t->sbox.p, t->sprim.p, \
+                                                      out->pairs.p, counter, cap, check_shared)
+        switch (mode * 100 + qn * 10 + tn) {
+        case 211: IPCB_TRAVERSE(2, 1, 1); break; // vertex - vertex
+        case 21: IPCB_TRAVERSE(0, 2, 1); break;  // edges walk the vertex tree
+        case 222: IPCB_TRAVERSE(2, 2, 2); break; // edge - edge
+        case 113: IPCB_TRAVERSE(1, 1, 3); break; // vertices walk the face tree
+        case 132: IPCB_TRAVERSE(1, 3, 2); break; // faces walk the edge tree
+        case 233: IPCB_TRAVERSE(2, 3, 3); break; // face - face
+        default: throw Error("broad phase: unsupported traversal");
+        }
+#undef IPCB_TRAVERSE
         ctx->launches++;
         IPCB_CUDA(cudaGetLastError());
-        IPCB_CUDA(cudaMemcpyAsync(ctx->pinned.p, ctx->dCounters.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-        IPCB_CUDA(cudaStreamSynchronize(s));
-        const unsigned long long found = (unsigned long long)ctx->pinned.p[0];
-        if (found <= cap) {
-            out.count = int64_t(found);
-            return;
-        }
-        out.pairs.reserve(size_t(found) + size_t(found) / 8); // overflow: grow and repeat the pass
+        IPCB_CUDA(cudaMemcpyAsync(ctx->pinned.p + 16 + slot, counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     }
-    throw Error("broad phase: candidate buffer overflow persisted");
+    void finish()
+    {
+        if (!live) return;
+        for (int attempt = 0; attempt < 3; attempt++) {
+            IPCB_CUDA(cudaStreamSynchronize(s));
+            const unsigned long long found = (unsigned long long)ctx->pinned.p[16 + slot];
+            if (found <= out->pairs.cap) {
+                out->count = int64_t(found);
+                return;
+            }
+            out->pairs.reserve(size_t(found) + size_t(found) / 8); // overflow: grow and repeat the pass
+            enqueue();
+        }
+        throw Error("broad phase: candidate buffer overflow persisted");
+    }
+};
+
+static void run_traverse(ipcb_ctx* ctx, const Tree& q, const Tree& t, int mode, int qn, int tn, bool check_shared, PairList& out, bool shard)
+{
+    TraverseJob job { ctx, &q, &t, mode, qn, tn, check_shared, &out, ctx->stream, 0 };
+    job.launch(shard);
+    job.finish();
 }
 
 static Tree& ensure_tree(ipcb_ctx* ctx, int which)
@@ -525,35 +578,35 @@ void broad_detect(ipcb_ctx* ctx, int kind, PairList& out)
     switch (kind) {
     case IPCB_VV: {
         Tree& v = ensure_tree(ctx, 0);
-        run_traverse(ctx, v, v, 2, true, out, true);
+        run_traverse(ctx, v, v, 2, 1, 1, true, out, true);
         break;
     }
     case IPCB_EV: { // edges walk the vertex BVH
         Tree& e = ensure_tree(ctx, 1);
         Tree& v = ensure_tree(ctx, 0);
-        run_traverse(ctx, e, v, 0, true, out, true);
+        run_traverse(ctx, e, v, 0, 2, 1, true, out, true);
         break;
     }
     case IPCB_EE: {
         Tree& e = ensure_tree(ctx, 1);
-        run_traverse(ctx, e, e, 2, true, out, true);
+        run_traverse(ctx, e, e, 2, 2, 2, true, out, true);
         break;
     }
     case IPCB_FV: { // vertices walk the face BVH, emitted as (face, vertex)
         Tree& v = ensure_tree(ctx, 0);
         Tree& f = ensure_tree(ctx, 2);
-        run_traverse(ctx, v, f, 1, true, out, true);
+        run_traverse(ctx, v, f, 1, 1, 3, true, out, true);
         break;
     }
     case IPCB_EF: { // faces walk the edge BVH, emitted as (edge, face)
         Tree& f = ensure_tree(ctx, 2);
         Tree& e = ensure_tree(ctx, 1);
-        run_traverse(ctx, f, e, 1, true, out, true);
+        run_traverse(ctx, f, e, 1, 3, 2, true, out, true);
         break;
     }
     case IPCB_FF: {
         Tree& f = ensure_tree(ctx, 2);
-        run_traverse(ctx, f, f, 2, true, out, true);
+        run_traverse(ctx, f, f, 2, 3, 3, true, out, true);
         break;
     }
     default: throw Error("bad candidate kind");
@@ -595,23 +648,32 @@ void sort_pairs(ipcb_ctx* ctx, PairList& pl)
 void candidates_build(ipcb_ctx* ctx, bool swept, double r)
 {
     broad_build(ctx, swept, r);
-    {
-        Stage st(ctx, "lbvh_build");
-        if (ctx->nE >= 2) ensure_tree(ctx, 1);
-        if (ctx->nF && ctx->nV) {
-            ensure_tree(ctx, 2);
-            // the vertex queries only need the Morton order, not a hierarchy
-            if (!ctx->vtree_ok) build_tree(ctx, ctx->vset, ctx->vtree, false);
-        }
-    }
     for (auto& c : ctx->cand) c.count = 0, c.sorted = false;
     {
-        Stage st(ctx, "traverse_ee");
-        if (ctx->nE >= 2) run_traverse(ctx, ctx->etree, ctx->etree, 2, true, ctx->cand[IPCB_EE], true);
-    }
-    {
-        Stage st(ctx, "traverse_fv");
-        if (ctx->nF && ctx->nV) run_traverse(ctx, ctx->vtree, ctx->ftree, 1, true, ctx->cand[IPCB_FV], true);
+        // The edge tree + edge-edge traversal and the face tree + face-vertex traversal are independent: they run on
+        // two auxiliary streams (the small sort / hierarchy kernels of one chain fill the tails of the other); the
+        // vertex queries only need the Morton order, not a hierarchy (main stream).
+        Stage st(ctx, "lbvh_build+traverse");
+        const bool do_ee = ctx->nE >= 2, do_fv = ctx->nF && ctx->nV;
+        ctx->fork();
+        TraverseJob ee { ctx, &ctx->etree, &ctx->etree, 2, 2, 2, true, &ctx->cand[IPCB_EE], ctx->aux[0], 0 };
+        TraverseJob fv { ctx, &ctx->vtree, &ctx->ftree, 1, 1, 3, true, &ctx->cand[IPCB_FV], ctx->aux[1], 1 };
+        if (do_ee) {
+            if (!ctx->etree_ok) build_tree(ctx, ctx->eset, ctx->etree, true, ctx->aux[0]), ctx->etree_ok = true;
+            ee.launch(true);
+        }
+        if (do_fv) {
+            if (!ctx->ftree_ok) build_tree(ctx, ctx->fset, ctx->ftree, true, ctx->aux[1]), ctx->ftree_ok = true;
+            if (!ctx->vtree_ok) build_tree(ctx, ctx->vset, ctx->vtree, false, ctx->aux[2]);
+            ctx->join(2); // not needed by the main stream itself, but keeps every later main-stream consumer ordered
+            IPCB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->aux[2]));
+            IPCB_CUDA(cudaStreamWaitEvent(ctx->aux[1], ctx->ev_fork, 0)); // the vertex order feeds the face-vertex traversal
+            fv.launch(true);
+        }
+        ee.finish();
+        fv.finish();
+        ctx->join(0);
+        ctx->join(1);
     }
     const int ncv = int(ctx->codimV.size()), nce = int(ctx->codimE.size());
     if (ncv) {
@@ -624,7 +686,7 @@ void candidates_build(ipcb_ctx* ctx, bool swept, double r)
         ctx->launches++;
         build_tree(ctx, ctx->cvset, ctx->cvtree, true);
         if (ncv >= 2 && ctx->shard_rank == 0) // tiny sets are not sharded: rank 0 owns them
-            run_traverse(ctx, ctx->cvtree, ctx->cvtree, 2, false, ctx->cand[IPCB_VV], false);
+            run_traverse(ctx, ctx->cvtree, ctx->cvtree, 2, 1, 1, false, ctx->cand[IPCB_VV], false);
         if (nce) {
             ctx->ceset.n = nce;
             ctx->ceset.box.reserve(nce), ctx->ceset.prim.reserve(nce);
@@ -632,7 +694,7 @@ void candidates_build(ipcb_ctx* ctx, bool swept, double r)
                                                           ctx->ceset.prim.p);
             ctx->launches++;
             build_tree(ctx, ctx->ceset, ctx->cetree, false);
-            if (ctx->shard_rank == 0) run_traverse(ctx, ctx->cetree, ctx->cvtree, 0, false, ctx->cand[IPCB_EV], false);
+            if (ctx->shard_rank == 0) run_traverse(ctx, ctx->cetree, ctx->cvtree, 0, 2, 1, false, ctx->cand[IPCB_EV], false);
         }
     }
 }

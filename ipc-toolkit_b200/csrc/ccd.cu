@@ -935,10 +935,13 @@ static void ti_run(ipcb_ctx* ctx, const QuerySource& src, double min_distance, d
     // of impact shrinks the search window, so the pre-filter of the remaining candidates (the same
     // std::atomic<double> earliest_toi idea as candidates.cpp:267-286, applied before any root finding)
     // discards almost everything that cannot beat it.
-    constexpr int SAMPLE = 64;
-    if (out.bound && src.n >= 16 * 1024 * SAMPLE / 8) {
-        phase(1, SAMPLE);
-        phase(2, SAMPLE);
+    // The sample only has to be large enough to fill the GPU once (a fixed count, not a fixed fraction).
+    int64_t target = 65536;
+    if (const char* e = getenv("IPCB_TI_SAMPLE")) target = std::max(1, atoi(e));
+    const int stride = int(std::min<int64_t>(src.n / target, 1 << 20));
+    if (out.bound && stride >= 4) {
+        phase(1, stride);
+        phase(2, stride);
     } else {
         phase(0, 1);
     }

@@ -188,44 +188,46 @@ __global__ void k_emit_collisions(int64_t n, const unsigned long long* __restric
     }
 }
 
-static int key_bits(const ipcb_ctx* ctx)
+// Keys are (id0 << 32 | id1) with id0, id1 below these bounds per kind: the radix sort only has to look at
+// the low bits of id1 and of id0 (two bit ranges would need two sorts; one range from 0 to 32 + bits(id0) with
+// id1 < 2^32 is what cub offers, so the saving comes from the id0 bits only)
+static int key_bits(const ipcb_ctx* ctx, int kind)
 {
-    int m = std::max(std::max(ctx->nV, ctx->nE), std::max(ctx->nF, 2));
-    int b = 0;
+    const int m = kind == IPCB_VV ? ctx->nV : (kind == IPCB_FV ? ctx->nF : ctx->nE);
+    int b = 1;
     while ((1ll << b) < m) b++;
     return 32 + b;
 }
 
-static void merge_stream(ipcb_ctx* ctx, int kind, int64_t n)
+// enqueue the merge of one stream on `s`: sort by key, run heads + weight sums, scan, emit; the count is read back
+// into pinned slots 20 + 2 * kind (pos of the last record) and 21 + 2 * kind (its head flag)
+static void merge_stream_enqueue(ipcb_ctx* ctx, int kind, int64_t n, cudaStream_t s)
 {
     CollisionSet& cs = ctx->coll[kind];
     cs.count = 0;
     if (n == 0) return;
-    cudaStream_t s = ctx->stream;
     cs.idx_raw.reserve(n), cs.idx_sorted.reserve(n), cs.key_sorted.reserve(n), cs.head.reserve(n), cs.pos.reserve(n + 1);
     Buf<double>& wsum = cs.wsum;
     wsum.reserve(n);
     k_iota<<<grid_for(n, 256), 256, 0, s>>>(n, cs.idx_raw.p);
     size_t bytes = 0, bytes2 = 0;
-    const int bits = key_bits(ctx);
+    const int bits = key_bits(ctx, kind);
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, cs.key_raw.p, cs.key_sorted.p, cs.idx_raw.p, cs.idx_sorted.p, n, 0, bits, s);
     cub::DeviceScan::ExclusiveSum(nullptr, bytes2, cs.head.p, cs.pos.p, n, s);
-    ctx->cubtmp.reserve(std::max(bytes, bytes2));
-    cub::DeviceRadixSort::SortPairs(ctx->cubtmp.p, bytes, cs.key_raw.p, cs.key_sorted.p, cs.idx_raw.p, cs.idx_sorted.p, n, 0, bits, s);
+    cs.cubtmp.reserve(std::max(bytes, bytes2));
+    cub::DeviceRadixSort::SortPairs(cs.cubtmp.p, bytes, cs.key_raw.p, cs.key_sorted.p, cs.idx_raw.p, cs.idx_sorted.p, n, 0, bits, s);
     const int merge = kind != IPCB_FV; // fv collisions are appended, never merged (builder.cpp:659-661)
     k_runs<<<grid_for(n, 256), 256, 0, s>>>(n, cs.key_sorted.p, cs.idx_sorted.p, cs.w_raw.p, merge, cs.head.p, wsum.p);
-    cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, bytes2, cs.head.p, cs.pos.p, n, s);
+    cub::DeviceScan::ExclusiveSum(cs.cubtmp.p, bytes2, cs.head.p, cs.pos.p, n, s);
     cs.ids.reserve(n), cs.w.reserve(n);
     if (kind == IPCB_EE) cs.eps.reserve(n), cs.dtype.reserve(n);
     k_emit_collisions<<<grid_for(n, 256), 256, 0, s>>>(n, cs.key_sorted.p, cs.idx_sorted.p, cs.head.p, cs.pos.p, wsum.p,
                                                        kind == IPCB_EE ? cs.eps_raw.p : nullptr, cs.dt_raw.p, cs.ids.p, cs.w.p,
                                                        cs.eps.p, cs.dtype.p);
-    ctx->launches += 12;
+    ctx->launches += 5 + (bits + 7) / 8 + 4;
     // count = pos[n-1] + head[n-1]
-    IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[8], cs.pos.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
-    IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[9], cs.head.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
-    IPCB_CUDA(cudaStreamSynchronize(s));
-    cs.count = int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[8])) + int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[9]));
+    IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[20 + 2 * kind], cs.pos.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[21 + 2 * kind], cs.head.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
 }
 
 void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
@@ -257,6 +259,7 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
             a.out[k] = { cs.key_raw.p, cs.w_raw.p, k == IPCB_EE ? cs.eps_raw.p : nullptr, k == IPCB_EE ? cs.dt_raw.p : nullptr,
                          ctx->dCounters.p + 1 + k };
         }
+        ctx->fork(); // the face-vertex candidates are classified concurrently with the edge-edge ones
         for (int k = 0; k < 4; k++) {
             a.cand = ctx->cand[k].pairs.p;
             a.n = ctx->cand[k].count;
@@ -265,16 +268,26 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
             if (k == IPCB_VV) k_classify<IPCB_VV><<<grid, 256, 0, s>>>(a);
             if (k == IPCB_EV) k_classify<IPCB_EV><<<grid, 256, 0, s>>>(a);
             if (k == IPCB_EE) k_classify<IPCB_EE><<<grid, 256, 0, s>>>(a);
-            if (k == IPCB_FV) k_classify<IPCB_FV><<<grid, 256, 0, s>>>(a);
+            if (k == IPCB_FV) k_classify<IPCB_FV><<<grid, 256, 0, ctx->aux[0]>>>(a);
             ctx->launches++;
         }
+        ctx->join(0);
         IPCB_CUDA(cudaGetLastError());
         IPCB_CUDA(cudaMemcpyAsync(ctx->pinned.p, ctx->dCounters.p + 1, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         IPCB_CUDA(cudaStreamSynchronize(s));
     }
     const int64_t raw[4] = { ctx->pinned.p[0], ctx->pinned.p[1], ctx->pinned.p[2], ctx->pinned.p[3] };
     Stage st(ctx, "merge_collisions");
-    for (int k = 0; k < 4; k++) merge_stream(ctx, k, raw[k]);
+    // the four streams are merged concurrently (their sorts are small and latency-bound): EE on the main stream
+    cudaStream_t where[4] = { ctx->aux[0], ctx->aux[1], s, ctx->aux[2] };
+    ctx->fork();
+    for (int k = 0; k < 4; k++) merge_stream_enqueue(ctx, k, raw[k], where[k]);
+    for (int k = 0; k < 4; k++) {
+        if (raw[k] == 0) continue;
+        IPCB_CUDA(cudaStreamSynchronize(where[k]));
+        ctx->coll[k].count = int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[20 + 2 * k])) + int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[21 + 2 * k]));
+    }
+    for (int k = 0; k < ipcb_ctx::NAUX; k++) ctx->join(k);
 }
 
 // ---- compute_minimum_distance (normal_collisions.cpp:209-233) ----------------------

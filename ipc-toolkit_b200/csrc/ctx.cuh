@@ -68,6 +68,7 @@ struct CollisionSet {
     Buf<unsigned char> dtype;
     Buf<int> head, pos;
     Buf<double> wsum;
+    Buf<char> cubtmp; // per stream: the four merges run concurrently
     int64_t count = 0;
 };
 
@@ -80,8 +81,24 @@ struct StageTimer {
 struct ipcb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    // auxiliary streams for independent work inside one call (tree builds, traversals, per-kind kernels);
+    // fork() makes them wait for `stream`, join(k) makes `stream` wait for aux[k]
+    static constexpr int NAUX = 3;
+    cudaStream_t aux[NAUX] = { nullptr, nullptr, nullptr };
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = { nullptr, nullptr, nullptr };
+    void fork()
+    {
+        cudaEventRecord(ev_fork, stream);
+        for (int k = 0; k < NAUX; k++) cudaStreamWaitEvent(aux[k], ev_fork, 0);
+    }
+    void join(int k)
+    {
+        cudaEventRecord(ev_join[k], aux[k]);
+        cudaStreamWaitEvent(stream, ev_join[k], 0);
+    }
     int64_t launches = 0;
     int shard_rank = 0, shard_world = 1;
+    bool timing = false; // per-stage CUDA-event timing (synchronises at every stage boundary)
 
     // ---- host mesh (collision_mesh.cpp:15-127)
     int nV = 0, nE = 0, nF = 0;
@@ -153,19 +170,21 @@ struct ipcb_ctx {
 
 namespace ipcb {
 
-// RAII stage timer using CUDA events on the context's stream
+// RAII stage timer using CUDA events on the context's stream; a no-op unless ctx->timing is set
 struct Stage {
     ipcb_ctx* ctx;
     const char* name;
-    cudaEvent_t a, b;
+    cudaEvent_t a = nullptr, b = nullptr;
     Stage(ipcb_ctx* c, const char* n) : ctx(c), name(n)
     {
+        if (!ctx->timing) return;
         cudaEventCreate(&a);
         cudaEventCreate(&b);
         cudaEventRecord(a, ctx->stream);
     }
     ~Stage()
     {
+        if (!a) return;
         cudaEventRecord(b, ctx->stream);
         cudaEventSynchronize(b);
         float ms = 0;

@@ -1043,9 +1043,11 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
             unsigned long long* slow_count = ctx->dCounters.p + 5;
             ctx->hslow.reserve(std::max<int64_t>(n2, 1));
             IPCB_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(unsigned long long), s));
-            if (n0) k_hessian_fast<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, ctx->hslow.p, slow_count), ctx->launches++;
-            if (n1) k_hessian_fast<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, ctx->hslow.p, slow_count), ctx->launches++;
-            if (n3) k_hessian_fast<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count), ctx->launches++;
+            // the four kinds write disjoint records: the small ones run beside the edge-edge kernel
+            ctx->fork();
+            if (n0) k_hessian_fast<IPCB_VV><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, ctx->hslow.p, slow_count), ctx->launches++;
+            if (n1) k_hessian_fast<IPCB_EV><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, ctx->hslow.p, slow_count), ctx->launches++;
+            if (n3) k_hessian_fast<IPCB_FV><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count), ctx->launches++;
             if (n2) {
                 k_hessian_fast<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, slow_count);
                 ctx->launches++;
@@ -1057,6 +1059,8 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
                     ctx->launches++;
                 }
             }
+            ctx->join(0);
+            ctx->join(1);
         }
         IPCB_CUDA(cudaGetLastError());
     }
