@@ -57,6 +57,30 @@ struct QuerySource {
     const double* raw0;
     const double* raw1;
 };
+// several kinds behind one concatenated index space [off[k], off[k+1]) (the step-size search looks at the
+// face-vertex and edge-edge candidates in the same launches)
+struct MultiSource {
+    int nk;
+    int kind[4];
+    long long off[5];
+    const int2* cand[4];
+    const int2* E;
+    const int4* F;
+    const double4* X0;
+    const double4* X1;
+    const double* raw0;
+    const double* raw1;
+};
+__device__ inline QuerySource locate(const MultiSource& m, long long g, int64_t& i)
+{
+    int k = 0;
+#pragma unroll
+    for (int j = 1; j < 4; j++)
+        if (j < m.nk && g >= m.off[j]) k = j;
+    i = g - m.off[k];
+    return QuerySource { m.kind[k], m.off[k + 1] - m.off[k], m.cand[k], m.E, m.F, m.X0, m.X1, m.raw0, m.raw1 };
+}
+
 // stencil at t0 / t1; returns number of points (2, 3, 4)
 __device__ inline int load_query(const QuerySource& q, int64_t i, d3* a, d3* b)
 {
@@ -241,6 +265,7 @@ __host__ __device__ inline void ti_error(const double* s, const double* e, int i
         err[c] = filter * delta * delta * delta;
     }
 }
+// co-domain box of the (multilinear) root function over a (t,u,v) box against the eps-cube
 // co-domain box of the (multilinear) root function over a (t,u,v) box against the eps-cube
 __host__ __device__ inline bool ti_inclusion(const double* s, const double* e, int is_vf, const TIParams& P, const double* tt, const double* uu,
                                     const double* vv, bool& box_in, double* true_tol)
@@ -463,15 +488,16 @@ __device__ inline unsigned long long warp_reserve(unsigned long long* counter, b
 // can neither start closer than min_distance nor produce a terminal box (see ti_cull), so it is
 // dropped here; survivors are compacted into `list` for the full per-query kernel.
 __global__ void __launch_bounds__(256, 3)
-    k_ti_filter(QuerySource q, int sel_mode, int sel_mod, double min_distance, double tmax_in, double tolerance, CcdOut out,
+    k_ti_filter(MultiSource ms, int stride, int prev_stride, double min_distance, double tmax_in, double tolerance, CcdOut out,
                 int* __restrict__ list, unsigned long long* nlist)
 {
     const unsigned long long* bound = out.bound;
-    // sel_mode 0: every candidate; 1: the sample i % sel_mod == 0 (thread t -> i = t * sel_mod); 2: the rest
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (sel_mode == 1) i *= sel_mod;
+    // thread t looks at candidate g = t * stride, unless an earlier (coarser) phase already did: g % prev_stride == 0
+    const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * stride;
     bool keep = false;
-    if (i < q.n && !(sel_mode == 2 && i % sel_mod == 0)) {
+    if (g < ms.off[ms.nk] && !(prev_stride > 0 && g % prev_stride == 0)) {
+        int64_t i;
+        const QuerySource q = locate(ms, g, i);
         keep = true;
         if (q.kind >= IPCB_EE) { // point-point / point-edge queries are few (codimensional): always kept
             d3 a[4], b[4];
@@ -494,7 +520,7 @@ __global__ void __launch_bounds__(256, 3)
         unsigned long long base = 0;
         if (lane == __ffs(m) - 1) base = atomicAdd(nlist, (unsigned long long)__popc(m));
         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (keep) list[base + __popc(m & ((1u << lane) - 1))] = int(i);
+        if (keep) list[base + __popc(m & ((1u << lane) - 1))] = int(g);
     }
 }
 
@@ -559,68 +585,82 @@ __device__ inline bool ti_shrink(const double* s, const double* e, int is_vf, TI
     return true;
 }
 
-// Stage 2, one thread per pre-filtered query: exact level-0 cull, then a short in-register depth-first search.
-// A query that needs more than `budget` boxes in any run is deferred to the warp-cooperative kernel.
+// Stage 2, one THREAD per pre-filtered query (persistent grid, the list length is read on the device): exact set-up
+// and level-0 cull, then a short earliest-first depth-first search in registers.  It answers most queries with
+// thousands of them in flight; a query that needs more than `budget` boxes in any run is deferred to the
+// warp-cooperative kernel.
 __global__ void __launch_bounds__(128)
-    k_ti_query(QuerySource q, const int* __restrict__ list, int64_t nlist, double min_distance, double tmax_in, double tolerance, double rescale,
-               int budget, int* __restrict__ hard, unsigned long long* nhard, CcdOut out)
+    k_ti_query(MultiSource ms, const int* __restrict__ list, const unsigned long long* __restrict__ nlist, unsigned long long* next,
+               double min_distance, double tmax_in, double tolerance, double rescale, int budget, int* __restrict__ hard,
+               unsigned long long* nhard, CcdOut out)
 {
-    const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const bool active = tid < nlist;
-    const int64_t i = active ? list[tid] : 0;
-    bool defer = false;
-    if (active) {
-        double s[12], e[12];
-        TIParams P;
-        int is_vf;
-        double tmax0;
-        if (ti_setup(q, i, min_distance, tmax_in, tolerance, rescale, out, s, e, P, is_vf, tmax0)) {
-            TIBox stack[DFS_STACK];
-            int sp = 0;
-            double best = INFINITY;
-            // ---- first query: minimum effective distance, no_zero_toi = false
-            bool done = true;
-            if (!ti_cull(s, e, is_vf, P, tmax0)) {
-                stack[0] = TIBox { 0, 0, 0, 0, 0, 0, 0 };
-                sp = 1;
-                done = ti_dfs(s, e, is_vf, P, out.bound, budget, stack, sp, best);
-            }
-            if (!done) {
-                defer = true;
-            } else if (best < SMALL_TOI) {
-                // ---- second query: ms = min_distance, no_zero_toi = true, shrinking until toi != 0
-                P.ms = min_distance;
-                P.tmax = tmax0;
-                ti_error(s, e, is_vf, P.ms > 0, P.err);
-                for (int round = 0; round < 200; round++) {
-                    best = INFINITY;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n = *nlist;
+    for (;;) {
+        unsigned long long w0 = 0;
+        if (lane == 0) w0 = atomicAdd(next, 32ull);
+        w0 = __shfl_sync(0xffffffffu, w0, 0);
+        if (w0 >= n) return;
+        const unsigned long long w = w0 + lane;
+        bool defer = false;
+        int g = 0;
+        if (w < n) {
+            g = list[w];
+            int64_t i;
+            const QuerySource q = locate(ms, g, i);
+            double s[12], e[12];
+            TIParams P;
+            int is_vf;
+            double tmax0;
+            if (ti_setup(q, i, min_distance, tmax_in, tolerance, rescale, out, s, e, P, is_vf, tmax0)) {
+                TIBox stack[DFS_STACK];
+                int sp = 0;
+                double best = INFINITY;
+                // ---- first query: minimum effective distance, no_zero_toi = false
+                bool done = true;
+                if (!ti_cull(s, e, is_vf, P, tmax0)) {
                     stack[0] = TIBox { 0, 0, 0, 0, 0, 0, 0 };
                     sp = 1;
-                    if (!ti_dfs(s, e, is_vf, P, nullptr, budget, stack, sp, best)) {
-                        defer = true;
-                        break;
-                    }
-                    if (!ti_shrink(s, e, is_vf, P, best)) break;
+                    done = ti_dfs(s, e, is_vf, P, out.bound, budget, stack, sp, best);
                 }
-                if (!defer) report(out, i, best < INFINITY, best * rescale);
-            } else {
-                report(out, i, best < INFINITY, best);
+                if (!done) {
+                    defer = true;
+                } else if (best < SMALL_TOI) {
+                    // ---- second query: ms = min_distance, no_zero_toi = true, shrinking until toi != 0
+                    P.ms = min_distance;
+                    P.tmax = tmax0;
+                    ti_error(s, e, is_vf, P.ms > 0, P.err);
+                    for (int round = 0; round < 200; round++) {
+                        best = INFINITY;
+                        stack[0] = TIBox { 0, 0, 0, 0, 0, 0, 0 };
+                        sp = 1;
+                        if (!ti_dfs(s, e, is_vf, P, nullptr, budget, stack, sp, best)) {
+                            defer = true;
+                            break;
+                        }
+                        if (!ti_shrink(s, e, is_vf, P, best)) break;
+                    }
+                    if (!defer) report(out, i, best < INFINITY, best * rescale);
+                } else {
+                    report(out, i, best < INFINITY, best);
+                }
             }
         }
+        const unsigned long long slot = warp_reserve(nhard, defer, 1);
+        if (defer) hard[slot] = g;
     }
-    const unsigned long long slot = warp_reserve(nhard, defer, 1);
-    if (defer) hard[slot] = int(i);
 }
 
-// Stage 3, one WARP per hard query: the 32 lanes pop up to 32 boxes from a shared-memory stack, evaluate them in
+// One WARP per surviving query: the 32 lanes pop up to 32 boxes from a shared-memory stack, evaluate them in
 // parallel and push the children (earliest first on top), sharing the best terminal time.  The result (minimum
 // lower time bound over all terminal boxes not pruned by it) does not depend on the evaluation order.  If the
 // stack overflows, the query is handed to the global level-synchronous queue.
 constexpr int WSTACK = 1024;
+__device__ unsigned long long g_dbg[8]; // diagnostics: [0] warp searches, [1] warp iterations, [2] max iterations of one search
 __device__ inline bool ti_warp_search(const double* s, const double* e, int is_vf, TIParams& P, const unsigned long long* bound, TIBox* stk,
                                       int cap, double& best, int lane)
 {
-    int sp = 1;
+    int sp = 1, iters = 0;
     if (lane == 0) stk[0] = TIBox { 0, 0, 0, 0, 0, 0, 0 };
     __syncwarp();
     best = INFINITY;
@@ -661,60 +701,71 @@ __device__ inline bool ti_warp_search(const double* s, const double* e, int is_v
         else if (mine == 1) stk[off] = child[0];
         sp += total;
         __syncwarp();
+        iters++;
     }
+    if (lane == 0) atomicAdd(&g_dbg[0], 1ull), atomicAdd(&g_dbg[1], (unsigned long long)iters), atomicMax(&g_dbg[2], (unsigned long long)iters);
     return true;
 }
 
 constexpr int WARP_SEARCH_WARPS = 2;
-__global__ void __launch_bounds__(32 * WARP_SEARCH_WARPS)
-    k_ti_warp(QuerySource q, const int* __restrict__ hard, int64_t nhard, double min_distance, double tmax_in, double tolerance, double rescale,
-              int cap, TIQueue Z, CcdOut out)
+// Persistent grid: every warp draws the next entry of the survivor list from a device counter until the list (whose
+// length the pre-filter left in *nlist) is exhausted — no host round trip between the filter and the search.
+__global__ void __launch_bounds__(32 * WARP_SEARCH_WARPS, 5)
+    k_ti_warp(MultiSource ms, const int* __restrict__ list, const unsigned long long* __restrict__ nlist, unsigned long long* next,
+              double min_distance, double tmax_in, double tolerance, double rescale, int cap, TIQueue Z, CcdOut out)
 {
     __shared__ TIBox stk[WARP_SEARCH_WARPS][WSTACK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t w = blockIdx.x * int64_t(WARP_SEARCH_WARPS) + warp;
-    if (w >= nhard) return;
-    const int64_t i = hard[w];
-    double s[12], e[12];
-    TIParams P;
-    int is_vf;
-    double tmax0;
-    // every lane computes the same set-up (an early answer is reported by all lanes with identical values)
-    if (!ti_setup(q, i, min_distance, tmax_in, tolerance, rescale, out, s, e, P, is_vf, tmax0)) return;
-    double best = INFINITY;
-    int flags = 0;
-    bool ok = true;
-    if (!ti_cull(s, e, is_vf, P, tmax0)) ok = ti_warp_search(s, e, is_vf, P, out.bound, stk[warp], cap, best, lane);
-    if (ok && best < SMALL_TOI) {
-        P.ms = min_distance;
-        P.tmax = tmax0;
-        ti_error(s, e, is_vf, P.ms > 0, P.err);
-        flags = 2;
-        for (int round = 0; round < 200; round++) {
-            ok = ti_warp_search(s, e, is_vf, P, nullptr, stk[warp], cap, best, lane);
-            if (!ok || !ti_shrink(s, e, is_vf, P, best)) break;
+    const unsigned long long n = *nlist;
+    for (;;) {
+        unsigned long long w = 0;
+        if (lane == 0) w = atomicAdd(next, 1ull);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n) return;
+        int64_t i;
+        const QuerySource q = locate(ms, list[w], i);
+        double s[12], e[12];
+        TIParams P;
+        int is_vf;
+        double tmax0;
+        // every lane computes the same set-up (an early answer is reported by all lanes with identical values)
+        if (!ti_setup(q, i, min_distance, tmax_in, tolerance, rescale, out, s, e, P, is_vf, tmax0)) continue;
+        double best = INFINITY;
+        int flags = 0;
+        bool ok = true;
+        if (!ti_cull(s, e, is_vf, P, tmax0)) ok = ti_warp_search(s, e, is_vf, P, out.bound, stk[warp], cap, best, lane);
+        if (ok && best < SMALL_TOI) {
+            P.ms = min_distance;
+            P.tmax = tmax0;
+            ti_error(s, e, is_vf, P.ms > 0, P.err);
+            flags = 2;
+            for (int round = 0; round < 200; round++) {
+                ok = ti_warp_search(s, e, is_vf, P, nullptr, stk[warp], cap, best, lane);
+                if (!ok || !ti_shrink(s, e, is_vf, P, best)) break;
+            }
+            if (ok && lane == 0) report(out, i, best < INFINITY, best * rescale);
+        } else if (ok) {
+            if (lane == 0) report(out, i, best < INFINITY, best);
         }
-        if (ok && lane == 0) report(out, i, best < INFINITY, best * rescale);
-    } else if (ok) {
-        if (lane == 0) report(out, i, best < INFINITY, best);
-    }
-    if (!ok && lane == 0) { // stack overflow: restart this run from its root in the global queue
-        const unsigned long long slot = atomicAdd(Z.nq, 1ull);
-        const unsigned long long u = atomicAdd(Z.nout, 1ull);
-        if (slot < Z.qcap && u < Z.ucap) {
-            TIQuery& Q = Z.queries[slot];
+        if (!ok && lane == 0) { // stack overflow: restart this run from its root in the global queue
+            const unsigned long long slot = atomicAdd(Z.nq, 1ull);
+            const unsigned long long u = atomicAdd(Z.nout, 1ull);
+            if (slot < Z.qcap && u < Z.ucap) {
+                TIQuery& Q = Z.queries[slot];
 #pragma unroll
-            for (int k = 0; k < 12; k++) Q.s[k] = s[k], Q.e[k] = e[k];
-            if (flags == 0) P.tmax = tmax0;
-            Q.P = P;
-            Q.is_vf = is_vf;
-            Q.pad = 0;
-            Q.src = i;
-            Z.qtoi[slot] = 0x7ff0000000000000ull;
-            Z.qflags[slot] = flags;
-            Z.outq[u] = TIUnit { int(slot), TIBox { 0, 0, 0, 0, 0, 0, 0 } };
+                for (int k = 0; k < 12; k++) Q.s[k] = s[k], Q.e[k] = e[k];
+                if (flags == 0) P.tmax = tmax0;
+                Q.P = P;
+                Q.is_vf = is_vf;
+                Q.pad = 0;
+                Q.src = i;
+                Z.qtoi[slot] = 0x7ff0000000000000ull;
+                Z.qflags[slot] = flags;
+                Z.outq[u] = TIUnit { int(slot), TIBox { 0, 0, 0, 0, 0, 0, 0 } };
+            }
+            // a failed reservation is detected on the host (counter > capacity): the whole search is repeated with room
         }
-        // a failed reservation is detected on the host (counter > capacity): the pass is repeated with room
+        __syncwarp();
     }
 }
 
@@ -848,9 +899,9 @@ static void ti_run_levels(ipcb_ctx* ctx, TIWork& W, TIQueue Z, unsigned long lon
     }
 }
 
-// in-register boxes per query before it is deferred to the warp-cooperative search, and the shared-memory
-// stack capacity per warp before a query goes to the global queue (the environment variables are test hooks
-// that force the later stages on small inputs)
+// in-register boxes per query before it is deferred to the warp-cooperative search, and the shared-memory stack
+// capacity per warp before a query goes to the global queue (the environment variables are test hooks that force
+// the later stages on small inputs)
 static int dfs_budget()
 {
     const char* e = getenv("IPCB_TI_BUDGET");
@@ -862,88 +913,113 @@ static int warp_stack_cap()
     return e ? std::min(WSTACK, std::max(2, atoi(e))) : WSTACK;
 }
 
-// Tight-Inclusion CCD over one query source
-static void ti_run(ipcb_ctx* ctx, const QuerySource& src, double min_distance, double tmax, const ipcb_ccd_params& p, CcdOut out)
+// Tight-Inclusion CCD over a (multi-kind) query source.
+//   phase = pre-filter (most broad-phase candidates are separated along one of their own directions inside the
+//   current search window) -> survivor list -> warp-cooperative search (persistent grid, device-side list length).
+// With a shared bound (step-size search) strided SAMPLES of the candidates are probed first: the earliest time of
+// impact they find shrinks the window of the final pass over all candidates — the std::atomic<double> earliest_toi
+// idea of candidates.cpp:267-286 applied before any root finding — so the pre-filter of the bulk discards almost
+// everything that cannot beat the bound.
+// Nothing is read back until the end; stack overflows (rare) are collected in the global queue and drained last.
+static void ti_run(ipcb_ctx* ctx, const MultiSource& ms, double min_distance, double tmax, const ipcb_ccd_params& p, CcdOut out)
 {
-    if (src.n == 0) return;
+    const int64_t total = ms.off[ms.nk];
+    if (total == 0) return;
+    if (total > 0x7fffffffll) throw Error("ccd: more than 2^31 candidates in one search");
     cudaStream_t s = ctx->stream;
     TIWork*& wp = g_work[ctx];
     if (!wp) wp = new TIWork();
     TIWork& W = *wp;
     unsigned long long* nq_d = ctx->dCounters.p + 1;
-    unsigned long long* cnt = ctx->dCounters.p + 2;
+    unsigned long long* cnt = ctx->dCounters.p + 2; // units in the global queue (directly after nq_d)
     unsigned long long* nactive_d = ctx->dCounters.p + 3;
+    unsigned long long* nlist_d = ctx->dCounters.p + 9; // survivor count, its work counter, deferred count, its work counter
+    unsigned long long* next_d = ctx->dCounters.p + 10;
+    unsigned long long* nhard_d = ctx->dCounters.p + 11;
+    unsigned long long* next2_d = ctx->dCounters.p + 12;
     size_t qcap = std::max<size_t>(W.queries.cap, 1024);
     size_t ucap = std::max<size_t>(W.ua.cap, size_t(1) << 16);
+    W.list.reserve(total), W.hard.reserve(total);
+    // strided samples, coarse to fine (default: one sample of ~64K candidates, then everything else; IPCB_TI_GROWTH
+    // inserts intermediate samples)
+    int64_t sample = 65536;
+    int growth = 1 << 20;
+    if (const char* e = getenv("IPCB_TI_SAMPLE")) sample = std::max(1, atoi(e));
+    if (const char* e = getenv("IPCB_TI_GROWTH")) growth = std::max(2, atoi(e));
+    int strides[8], nphase = 0;
+    if (out.bound && total / sample >= 4) {
+        // a candidate that two phases both look at (strides that do not divide each other) is simply searched twice
+        for (int64_t st = std::min<int64_t>(total / sample, 1 << 24); st > 1 && nphase < 7; st /= growth) strides[nphase++] = int(st);
+    }
+    strides[nphase++] = 1;
     unsigned long long nq = 0, nunits = 0;
-    if (src.n > 0x7fffffffll) throw Error("ccd: more than 2^31 candidates of one kind");
-    W.list.reserve(src.n);
-    // one phase = pre-filter (most broad-phase candidates are separated along one of their own directions
-    // inside the current search window) + per-query search of the survivors + the spill queue
-    auto phase = [&](int sel_mode, int sel_mod) {
-        const int64_t nthreads = sel_mode == 1 ? (src.n + sel_mod - 1) / sel_mod : src.n;
-        IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
-        k_ti_filter<<<grid_for(nthreads, 256), 256, 0, s>>>(src, sel_mode, sel_mod, min_distance, tmax, p.tolerance, out, W.list.p, cnt);
-        ctx->launches++;
-        const int64_t nlist = int64_t(read_counter(ctx, cnt));
-        if (nlist == 0) return;
-        // ---- stage 2: per-thread search with a small budget; the rest is deferred
-        W.hard.reserve(nlist);
-        IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
-        k_ti_query<<<grid_for(nlist, 128), 128, 0, s>>>(src, W.list.p, nlist, min_distance, tmax, p.tolerance, p.conservative_rescaling, dfs_budget(),
-                                                        W.hard.p, cnt, out);
-        ctx->launches++;
+    for (int attempt = 0;; attempt++) {
+        W.queries.reserve(qcap), W.qtoi.reserve(qcap), W.qflags.reserve(qcap);
+        W.ua.reserve(ucap), W.ub.reserve(ucap);
+        qcap = std::min(W.queries.cap, std::min(W.qtoi.cap, W.qflags.cap));
+        ucap = std::min(W.ua.cap, W.ub.cap);
+        IPCB_CUDA(cudaMemsetAsync(nq_d, 0, 2 * sizeof(unsigned long long), s)); // nq and the unit counter
+        TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, W.ua.p, cnt, (unsigned long long)ucap };
+        // probe = true: a sample phase.  Its only purpose is a good bound, so queries that need more than the
+        // in-register budget are NOT pursued (an expensive search above the final step size is wasted work, and a
+        // single pathological one can cost milliseconds): every sampled candidate is looked at again by the final
+        // phase, then inside a tight window.
+        auto phase = [&](int st, bool probe) {
+            IPCB_CUDA(cudaMemsetAsync(nlist_d, 0, 4 * sizeof(unsigned long long), s)); // list lengths and work counters
+            k_ti_filter<<<grid_for((total + st - 1) / st, 256), 256, 0, s>>>(ms, st, 0, min_distance, tmax, p.tolerance, out, W.list.p, nlist_d);
+            k_ti_query<<<NUM_SMS * 2, 128, 0, s>>>(ms, W.list.p, nlist_d, next_d, min_distance, tmax, p.tolerance, p.conservative_rescaling,
+                                                   dfs_budget(), W.hard.p, nhard_d, out);
+            ctx->launches += 2;
+            if (!probe) {
+                k_ti_warp<<<NUM_SMS * 5, 32 * WARP_SEARCH_WARPS, 0, s>>>(ms, W.hard.p, nhard_d, next2_d, min_distance, tmax, p.tolerance,
+                                                                        p.conservative_rescaling, warp_stack_cap(), Z, out);
+                ctx->launches++;
+            }
+            static const bool debug = getenv("IPCB_DEBUG") != nullptr;
+            if (debug) { // per-phase survivor count and time (synchronises; diagnostics only)
+                const auto t0 = std::chrono::steady_clock::now();
+                const unsigned long long nl = read_counter(ctx, nlist_d);
+                const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                double b = 0;
+                if (out.bound) {
+                    const unsigned long long bits = read_counter(ctx, out.bound);
+                    memcpy(&b, &bits, sizeof b);
+                }
+                unsigned long long dbg[8];
+                cudaMemcpyFromSymbol(dbg, g_dbg, sizeof dbg);
+                const unsigned long long zero[8] = { 0 };
+                cudaMemcpyToSymbol(g_dbg, zero, sizeof zero);
+                fprintf(stderr, "[ipcb]   phase stride %d: %llu survivors, %llu deferred, bound %.6f, waited %.3f ms; warp searches %llu, iterations %llu, max %llu\n",
+                        st, nl, read_counter(ctx, nhard_d), b, ms, dbg[0], dbg[1], dbg[2]);
+            }
+        };
+        for (int k = 0; k < nphase; k++) phase(strides[k], k + 1 < nphase);
         IPCB_CUDA(cudaGetLastError());
-        const int64_t nhard = int64_t(read_counter(ctx, cnt));
-        if (nhard == 0) return;
-        // ---- stage 3: one warp per hard query; shared-memory stack overflows go to the global queue
-        for (int attempt = 0;; attempt++) {
-            W.queries.reserve(qcap), W.qtoi.reserve(qcap), W.qflags.reserve(qcap);
-            W.ua.reserve(ucap), W.ub.reserve(ucap);
-            qcap = std::min(W.queries.cap, std::min(W.qtoi.cap, W.qflags.cap));
-            ucap = std::min(W.ua.cap, W.ub.cap);
-            IPCB_CUDA(cudaMemsetAsync(nq_d, 0, 2 * sizeof(unsigned long long), s)); // nq and the unit counter
-            TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, W.ua.p, cnt, (unsigned long long)ucap };
-            k_ti_warp<<<grid_for(nhard, WARP_SEARCH_WARPS), 32 * WARP_SEARCH_WARPS, 0, s>>>(src, W.hard.p, nhard, min_distance, tmax, p.tolerance, p.conservative_rescaling,
-                                                                                          warp_stack_cap(), Z, out);
-            ctx->launches++;
-            IPCB_CUDA(cudaGetLastError());
-            nq = read_counter(ctx, nq_d);
-            nunits = read_counter(ctx, cnt);
-            if (nq <= qcap && nunits <= ucap) break;
-            if (attempt > 3) throw Error("ccd: spill buffers overflow persisted");
-            // reports are idempotent (atomicMin / identical values), so the pass can simply be repeated with room
-            qcap = std::max<size_t>(qcap, nq + nq / 4);
-            ucap = std::max<size_t>(ucap, nq + nq / 4);
-        }
-        if (nq == 0) return;
-        // ---- spilled queries: global interval-subdivision queue
-        TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, nullptr, nullptr, (unsigned long long)ucap };
-        ti_run_levels(ctx, W, Z, nunits, out.bound);
-        for (int round = 0; round < 250; round++) {
-            IPCB_CUDA(cudaMemsetAsync(nactive_d, 0, sizeof(unsigned long long), s));
-            k_ti_finalize<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), Z, min_distance, p.conservative_rescaling, out, nactive_d);
-            ctx->launches++;
-            if (read_counter(ctx, nactive_d) == 0) break;
-            IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
-            k_ti_push_roots<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), W.qflags.p, W.ua.p, cnt);
-            ctx->launches++;
-            ti_run_levels(ctx, W, Z, read_counter(ctx, cnt), nullptr);
-        }
-    };
-    // With a shared bound (step-size search) a strided SAMPLE of the candidates goes first: its earliest time
-    // of impact shrinks the search window, so the pre-filter of the remaining candidates (the same
-    // std::atomic<double> earliest_toi idea as candidates.cpp:267-286, applied before any root finding)
-    // discards almost everything that cannot beat it.
-    // The sample only has to be large enough to fill the GPU once (a fixed count, not a fixed fraction).
-    int64_t target = 65536;
-    if (const char* e = getenv("IPCB_TI_SAMPLE")) target = std::max(1, atoi(e));
-    const int stride = int(std::min<int64_t>(src.n / target, 1 << 20));
-    if (out.bound && stride >= 4) {
-        phase(1, stride);
-        phase(2, stride);
-    } else {
-        phase(0, 1);
+        nq = read_counter(ctx, nq_d);
+        nunits = nq ? read_counter(ctx, cnt) : 0;
+        static const bool debug = getenv("IPCB_DEBUG") != nullptr;
+        if (debug)
+            fprintf(stderr, "[ipcb] ti_run: %lld candidates, stride %d, attempt %d: %llu queries / %llu units in the global queue (cap %zu / %zu)\n",
+                    (long long)total, strides[0], attempt, nq, nunits, qcap, ucap);
+        if (nq <= qcap && nunits <= ucap) break;
+        if (attempt > 3) throw Error("ccd: spill buffers overflow persisted");
+        // reports are idempotent (atomicMin / identical values), so the search can simply be repeated with room
+        qcap = std::max<size_t>(qcap, nq + nq / 4);
+        ucap = std::max<size_t>(ucap, nq + nq / 4);
+    }
+    if (nq == 0) return;
+    // ---- queries whose shared-memory stack overflowed: global level-synchronous queue
+    TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, nullptr, nullptr, (unsigned long long)ucap };
+    ti_run_levels(ctx, W, Z, nunits, out.bound);
+    for (int round = 0; round < 250; round++) {
+        IPCB_CUDA(cudaMemsetAsync(nactive_d, 0, sizeof(unsigned long long), s));
+        k_ti_finalize<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), Z, min_distance, p.conservative_rescaling, out, nactive_d);
+        ctx->launches++;
+        if (read_counter(ctx, nactive_d) == 0) break;
+        IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
+        k_ti_push_roots<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), W.qflags.p, W.ua.p, cnt);
+        ctx->launches++;
+        ti_run_levels(ctx, W, Z, read_counter(ctx, cnt), nullptr);
     }
 }
 
@@ -952,17 +1028,19 @@ static QuerySource cand_source(ipcb_ctx* ctx, int kind)
     return { kind, ctx->cand[kind].count, ctx->cand[kind].pairs.p, ctx->dE.p, ctx->dF.p, ctx->X0.p, ctx->X1.p, nullptr, nullptr };
 }
 
-static void run_ccd(ipcb_ctx* ctx, const QuerySource& src, double min_distance, double tmax, const ipcb_ccd_params& p, CcdOut out)
+static MultiSource multi_source(ipcb_ctx* ctx, std::initializer_list<int> kinds)
 {
-    if (src.n == 0) return;
-    if (p.kind == IPCB_CCD_ADDITIVE) {
-        k_additive<<<grid_for(src.n, 128), 128, 0, ctx->stream>>>(src, min_distance, tmax, (long long)p.max_iterations,
-                                                                 p.conservative_rescaling, out);
-        ctx->launches++;
-        IPCB_CUDA(cudaGetLastError());
-    } else {
-        ti_run(ctx, src, min_distance, tmax, p, out);
+    MultiSource m {};
+    m.E = ctx->dE.p, m.F = ctx->dF.p, m.X0 = ctx->X0.p, m.X1 = ctx->X1.p;
+    m.off[0] = 0;
+    for (int kind : kinds) {
+        if (ctx->cand[kind].count == 0) continue;
+        m.kind[m.nk] = kind;
+        m.cand[m.nk] = ctx->cand[kind].pairs.p;
+        m.off[m.nk + 1] = m.off[m.nk] + ctx->cand[kind].count;
+        m.nk++;
     }
+    return m;
 }
 
 // Candidates::compute_collision_free_stepsize (candidates.cpp:252-292): earliest TOI over the
@@ -975,8 +1053,19 @@ void ccd_stepsize(ipcb_ctx* ctx, double min_distance, const ipcb_ccd_params& p, 
     k_set_bits<<<1, 1, 0, s>>>(bound, 1.0);
     ctx->launches++;
     CcdOut out { bound, nullptr, nullptr };
-    // the small kinds first: their hits tighten the bound for the big EE / FV sets
-    for (int kind : { IPCB_VV, IPCB_EV, IPCB_FV, IPCB_EE }) run_ccd(ctx, cand_source(ctx, kind), min_distance, 1.0, p, out);
+    if (p.kind == IPCB_CCD_ADDITIVE) {
+        for (int kind : { IPCB_VV, IPCB_EV, IPCB_FV, IPCB_EE }) {
+            const QuerySource src = cand_source(ctx, kind);
+            if (src.n == 0) continue;
+            k_additive<<<grid_for(src.n, 128), 128, 0, s>>>(src, min_distance, 1.0, (long long)p.max_iterations, p.conservative_rescaling, out);
+            ctx->launches++;
+        }
+        IPCB_CUDA(cudaGetLastError());
+    } else {
+        // the few codimensional point-point / point-edge candidates first, then faces and edges together
+        ti_run(ctx, multi_source(ctx, { IPCB_VV, IPCB_EV }), min_distance, 1.0, p, out);
+        ti_run(ctx, multi_source(ctx, { IPCB_FV, IPCB_EE }), min_distance, 1.0, p, out);
+    }
     IPCB_CUDA(cudaMemcpyAsync(d_out, bound, sizeof(double), cudaMemcpyDeviceToDevice, s));
 }
 
@@ -991,9 +1080,17 @@ void ccd_narrow_phase(ipcb_ctx* ctx, int kind, int64_t n, const double* h_t0, co
     IPCB_CUDA(cudaMemcpyAsync(a.p, h_t0, sizeof(double) * 12 * n, cudaMemcpyHostToDevice, s));
     IPCB_CUDA(cudaMemcpyAsync(b.p, h_t1, sizeof(double) * 12 * n, cudaMemcpyHostToDevice, s));
     IPCB_CUDA(cudaMemsetAsync(hit.p, 0, n, s));
-    QuerySource src { kind, n, nullptr, nullptr, nullptr, nullptr, nullptr, a.p, b.p };
     CcdOut out { nullptr, hit.p, toi.p };
-    run_ccd(ctx, src, min_distance, tmax, p, out);
+    if (p.kind == IPCB_CCD_ADDITIVE) {
+        const QuerySource src { kind, n, nullptr, nullptr, nullptr, nullptr, nullptr, a.p, b.p };
+        k_additive<<<grid_for(n, 128), 128, 0, s>>>(src, min_distance, tmax, (long long)p.max_iterations, p.conservative_rescaling, out);
+        ctx->launches++;
+        IPCB_CUDA(cudaGetLastError());
+    } else {
+        MultiSource m {};
+        m.nk = 1, m.kind[0] = kind, m.off[0] = 0, m.off[1] = n, m.raw0 = a.p, m.raw1 = b.p;
+        ti_run(ctx, m, min_distance, tmax, p, out);
+    }
     IPCB_CUDA(cudaMemcpyAsync(h_hit, hit.p, n, cudaMemcpyDeviceToHost, s));
     IPCB_CUDA(cudaMemcpyAsync(h_toi, toi.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     IPCB_CUDA(cudaStreamSynchronize(s));

@@ -217,10 +217,12 @@ def test_narrow_phase_matches_oracle(cuda, oracle):
                 assert np.mean(np.abs(tg[hg] - to[ho]) <= 1e-12) > 0.9
 
 
-@pytest.mark.parametrize("hooks", [{"IPCB_TI_BUDGET": "1"}, {"IPCB_TI_BUDGET": "1", "IPCB_TI_WSTACK": "8"}])
+@pytest.mark.parametrize("hooks", [{"IPCB_TI_BUDGET": "1"}, {"IPCB_TI_BUDGET": "1", "IPCB_TI_WSTACK": "8"},
+                                   {"IPCB_TI_SAMPLE": "16", "IPCB_TI_GROWTH": "4"}])
 def test_ccd_later_stages(cuda, oracle, scenes, hooks, monkeypatch):
     """force every search into the warp-cooperative kernel (budget 1) and, with a tiny shared-memory stack, on into
-    the global level-synchronous queue: the answers must not depend on which stage finishes a query"""
+    the global level-synchronous queue; with a tiny first sample the nested strided phases run on a small scene:
+    the answers must not depend on which stage finishes a query"""
     rng = np.random.default_rng(9)
     a = rng.uniform(-1, 1, (300, 4, 3))
     b = a + rng.normal(0, 0.6, (300, 4, 3))
