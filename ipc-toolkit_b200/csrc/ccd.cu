@@ -421,6 +421,7 @@ struct TIQueue {
     TIQuery* queries;
     unsigned long long* qtoi; // per spilled query: earliest terminal t so far (bit pattern)
     int* qflags;              // bit1: in the no-zero-toi refinement; bit2: finished
+    unsigned long long* qcount; // boxes evaluated for the query in its current run (effort cap)
     unsigned long long* nq;
     unsigned long long qcap;
     TIUnit* in;
@@ -444,6 +445,7 @@ __host__ __device__ inline bool ti_dfs(const double* s, const double* e, int is_
         if (tt[0] >= best) continue; // TOI_SKIP pruning of the sequential search
         if (bound && (iter & 3) == 0) P.tmax = fmin(P.tmax, load_bound(bound));
         if (tt[0] > P.tmax) continue;
+        tt[1] = fmin(tt[1], fmin(best, P.tmax)); // only impacts before the best one so far (and inside the window) matter
         if (++iter > budget || sp + 2 > DFS_STACK) {
             stack[sp++] = b;
             return false;
@@ -658,7 +660,7 @@ __global__ void __launch_bounds__(128)
 constexpr int WSTACK = 1024;
 __device__ unsigned long long g_dbg[8]; // diagnostics: [0] warp searches, [1] warp iterations, [2] max iterations of one search
 __device__ inline bool ti_warp_search(const double* s, const double* e, int is_vf, TIParams& P, const unsigned long long* bound, TIBox* stk,
-                                      int cap, double& best, int lane)
+                                      int cap, long long max_boxes, double& best, int lane)
 {
     int sp = 1, iters = 0;
     if (lane == 0) stk[0] = TIBox { 0, 0, 0, 0, 0, 0, 0 };
@@ -679,6 +681,7 @@ __device__ inline bool ti_warp_search(const double* s, const double* e, int is_v
             double tt[2], uu[2], vv[2];
             box_bounds(b, tt, uu, vv);
             if (tt[0] < best && tt[0] <= P.tmax) {
+                tt[1] = fmin(tt[1], fmin(best, P.tmax)); // only impacts before the best one so far (and inside the window) matter
                 r = ti_step(s, e, is_vf, P, b, tt, uu, vv, child, nchild);
                 if (r == 1) t0 = tt[0];
             }
@@ -702,6 +705,19 @@ __device__ inline bool ti_warp_search(const double* s, const double* e, int is_v
         sp += total;
         __syncwarp();
         iters++;
+        if (max_boxes >= 0 && (long long)iters * 32 >= max_boxes) {
+            // effort cap (max_iterations of the reference's root finder): stop refining and answer with the earliest
+            // time any unexplored box could still hold an impact — conservative, like ticcd when it runs out of iterations
+            double tmin = INFINITY;
+            for (int k = lane; k < sp; k += 32) {
+                const TIBox& u = stk[k];
+                tmin = fmin(tmin, ldexp(double(u.tn), -int(u.tk)));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tmin = fmin(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+            if (tmin <= P.tmax) best = fmin(best, tmin);
+            break;
+        }
     }
     if (lane == 0) atomicAdd(&g_dbg[0], 1ull), atomicAdd(&g_dbg[1], (unsigned long long)iters), atomicMax(&g_dbg[2], (unsigned long long)iters);
     return true;
@@ -712,7 +728,7 @@ constexpr int WARP_SEARCH_WARPS = 2;
 // length the pre-filter left in *nlist) is exhausted — no host round trip between the filter and the search.
 __global__ void __launch_bounds__(32 * WARP_SEARCH_WARPS, 5)
     k_ti_warp(MultiSource ms, const int* __restrict__ list, const unsigned long long* __restrict__ nlist, unsigned long long* next,
-              double min_distance, double tmax_in, double tolerance, double rescale, int cap, TIQueue Z, CcdOut out)
+              double min_distance, double tmax_in, double tolerance, double rescale, int cap, long long max_boxes, TIQueue Z, CcdOut out)
 {
     __shared__ TIBox stk[WARP_SEARCH_WARPS][WSTACK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -733,14 +749,14 @@ __global__ void __launch_bounds__(32 * WARP_SEARCH_WARPS, 5)
         double best = INFINITY;
         int flags = 0;
         bool ok = true;
-        if (!ti_cull(s, e, is_vf, P, tmax0)) ok = ti_warp_search(s, e, is_vf, P, out.bound, stk[warp], cap, best, lane);
+        if (!ti_cull(s, e, is_vf, P, tmax0)) ok = ti_warp_search(s, e, is_vf, P, out.bound, stk[warp], cap, max_boxes, best, lane);
         if (ok && best < SMALL_TOI) {
             P.ms = min_distance;
             P.tmax = tmax0;
             ti_error(s, e, is_vf, P.ms > 0, P.err);
             flags = 2;
             for (int round = 0; round < 200; round++) {
-                ok = ti_warp_search(s, e, is_vf, P, nullptr, stk[warp], cap, best, lane);
+                ok = ti_warp_search(s, e, is_vf, P, nullptr, stk[warp], cap, max_boxes, best, lane);
                 if (!ok || !ti_shrink(s, e, is_vf, P, best)) break;
             }
             if (ok && lane == 0) report(out, i, best < INFINITY, best * rescale);
@@ -761,6 +777,7 @@ __global__ void __launch_bounds__(32 * WARP_SEARCH_WARPS, 5)
                 Q.src = i;
                 Z.qtoi[slot] = 0x7ff0000000000000ull;
                 Z.qflags[slot] = flags;
+                Z.qcount[slot] = 0;
                 Z.outq[u] = TIUnit { int(slot), TIBox { 0, 0, 0, 0, 0, 0, 0 } };
             }
             // a failed reservation is detected on the host (counter > capacity): the whole search is repeated with room
@@ -771,7 +788,7 @@ __global__ void __launch_bounds__(32 * WARP_SEARCH_WARPS, 5)
 
 // one level of the global queue
 __global__ void __launch_bounds__(128)
-    k_ti_level(TIQueue Z, unsigned long long nin, const unsigned long long* bound, int force_terminal, int last_attempt)
+    k_ti_level(TIQueue Z, unsigned long long nin, const unsigned long long* bound, long long max_boxes, int force_terminal, int last_attempt)
 {
     const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     int nchild = 0;
@@ -790,7 +807,11 @@ __global__ void __launch_bounds__(128)
         // first-query units may also use the fresher global bound; refinement units keep their window
         if (live && bound && !(Z.qflags[u.q] & 2)) live = tt[0] <= load_bound(bound);
         if (live) {
+            tt[1] = fmin(tt[1], fmin(best_q, Q.P.tmax));
             int r = ti_step(Q.s, Q.e, Q.is_vf, Q.P, u.b, tt, uu, vv, child, nchild);
+            // effort cap per query (the reference root finder's max_iterations): further boxes are not refined, their
+            // lower time bound is taken as a possible impact (conservative)
+            if (r == 2 && max_boxes >= 0 && (long long)atomicAdd(Z.qcount + u.q, 1ull) >= max_boxes) r = 1, nchild = 0;
             if (r == 2 && force_terminal) r = 1, nchild = 0;
             if (r == 1) atomic_min_double(Z.qtoi + u.q, tt[0]);
         }
@@ -824,6 +845,7 @@ __global__ void k_ti_finalize(int nq, TIQueue Z, double min_distance, double res
             ti_error(Q.s, Q.e, Q.is_vf, Q.P.ms > 0, Q.P.err);
             Z.qtoi[i] = 0x7ff0000000000000ull;
             Z.qflags[i] = 2;
+            Z.qcount[i] = 0;
             atomicAdd(nactive, 1ull);
         } else {
             report(out, Q.src, hit, toi);
@@ -838,6 +860,7 @@ __global__ void k_ti_finalize(int nq, TIQueue Z, double min_distance, double res
                 ti_tolerances(Q.s, Q.e, Q.is_vf, Q.P.co_tol, Q.P.tol);
             }
             Z.qtoi[i] = 0x7ff0000000000000ull;
+            Z.qcount[i] = 0;
             atomicAdd(nactive, 1ull);
         } else {
             report(out, Q.src, hit, toi * rescale);
@@ -859,6 +882,7 @@ struct TIWork {
     Buf<TIQuery> queries;
     Buf<unsigned long long> qtoi;
     Buf<int> qflags;
+    Buf<unsigned long long> qcount;
     Buf<TIUnit> ua, ub;
     Buf<int> list; // candidates that survive the pre-filter
     Buf<int> hard; // queries deferred to the warp-cooperative search
@@ -875,7 +899,7 @@ static unsigned long long read_counter(ipcb_ctx* ctx, const unsigned long long* 
 // drain the global queue: `nunits` units are in W.ua.  When a level produces more children than the
 // output buffer holds, the buffer is grown and the level is simply run again (a level only reads its
 // input and does atomicMin on the per-query times, so it is idempotent).
-static void ti_run_levels(ipcb_ctx* ctx, TIWork& W, TIQueue Z, unsigned long long nunits, const unsigned long long* bound)
+static void ti_run_levels(ipcb_ctx* ctx, TIWork& W, TIQueue Z, unsigned long long nunits, const unsigned long long* bound, long long max_boxes)
 {
     cudaStream_t s = ctx->stream;
     unsigned long long* cnt = ctx->dCounters.p + 2;
@@ -885,7 +909,7 @@ static void ti_run_levels(ipcb_ctx* ctx, TIWork& W, TIQueue Z, unsigned long lon
         for (int attempt = 0;; attempt++) {
             IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
             Z.in = in->p, Z.outq = outq->p, Z.nout = cnt, Z.ucap = outq->cap;
-            k_ti_level<<<grid_for(nunits, 128), 128, 0, s>>>(Z, nunits, bound, level >= 120 ? 1 : 0, attempt >= 3 ? 1 : 0);
+            k_ti_level<<<grid_for(nunits, 128), 128, 0, s>>>(Z, nunits, bound, max_boxes, level >= 120 ? 1 : 0, attempt >= 3 ? 1 : 0);
             ctx->launches++;
             IPCB_CUDA(cudaGetLastError());
             const unsigned long long produced = read_counter(ctx, cnt);
@@ -954,12 +978,12 @@ static void ti_run(ipcb_ctx* ctx, const MultiSource& ms, double min_distance, do
     strides[nphase++] = 1;
     unsigned long long nq = 0, nunits = 0;
     for (int attempt = 0;; attempt++) {
-        W.queries.reserve(qcap), W.qtoi.reserve(qcap), W.qflags.reserve(qcap);
+        W.queries.reserve(qcap), W.qtoi.reserve(qcap), W.qflags.reserve(qcap), W.qcount.reserve(qcap);
         W.ua.reserve(ucap), W.ub.reserve(ucap);
-        qcap = std::min(W.queries.cap, std::min(W.qtoi.cap, W.qflags.cap));
+        qcap = std::min(std::min(W.queries.cap, W.qcount.cap), std::min(W.qtoi.cap, W.qflags.cap));
         ucap = std::min(W.ua.cap, W.ub.cap);
         IPCB_CUDA(cudaMemsetAsync(nq_d, 0, 2 * sizeof(unsigned long long), s)); // nq and the unit counter
-        TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, W.ua.p, cnt, (unsigned long long)ucap };
+        TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, W.qcount.p, nq_d, (unsigned long long)qcap, nullptr, W.ua.p, cnt, (unsigned long long)ucap };
         // probe = true: a sample phase.  Its only purpose is a good bound, so queries that need more than the
         // in-register budget are NOT pursued (an expensive search above the final step size is wasted work, and a
         // single pathological one can cost milliseconds): every sampled candidate is looked at again by the final
@@ -972,7 +996,7 @@ static void ti_run(ipcb_ctx* ctx, const MultiSource& ms, double min_distance, do
             ctx->launches += 2;
             if (!probe) {
                 k_ti_warp<<<NUM_SMS * 5, 32 * WARP_SEARCH_WARPS, 0, s>>>(ms, W.hard.p, nhard_d, next2_d, min_distance, tmax, p.tolerance,
-                                                                        p.conservative_rescaling, warp_stack_cap(), Z, out);
+                                                                        p.conservative_rescaling, warp_stack_cap(), (long long)p.max_iterations, Z, out);
                 ctx->launches++;
             }
             static const bool debug = getenv("IPCB_DEBUG") != nullptr;
@@ -1009,8 +1033,8 @@ static void ti_run(ipcb_ctx* ctx, const MultiSource& ms, double min_distance, do
     }
     if (nq == 0) return;
     // ---- queries whose shared-memory stack overflowed: global level-synchronous queue
-    TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, nq_d, (unsigned long long)qcap, nullptr, nullptr, nullptr, (unsigned long long)ucap };
-    ti_run_levels(ctx, W, Z, nunits, out.bound);
+    TIQueue Z { W.queries.p, W.qtoi.p, W.qflags.p, W.qcount.p, nq_d, (unsigned long long)qcap, nullptr, nullptr, nullptr, (unsigned long long)ucap };
+    ti_run_levels(ctx, W, Z, nunits, out.bound, (long long)p.max_iterations);
     for (int round = 0; round < 250; round++) {
         IPCB_CUDA(cudaMemsetAsync(nactive_d, 0, sizeof(unsigned long long), s));
         k_ti_finalize<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), Z, min_distance, p.conservative_rescaling, out, nactive_d);
@@ -1019,7 +1043,7 @@ static void ti_run(ipcb_ctx* ctx, const MultiSource& ms, double min_distance, do
         IPCB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), s));
         k_ti_push_roots<<<grid_for(nq, 128), 128, 0, s>>>(int(nq), W.qflags.p, W.ua.p, cnt);
         ctx->launches++;
-        ti_run_levels(ctx, W, Z, read_counter(ctx, cnt), nullptr);
+        ti_run_levels(ctx, W, Z, read_counter(ctx, cnt), nullptr, (long long)p.max_iterations);
     }
 }
 
