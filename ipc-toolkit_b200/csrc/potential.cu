@@ -28,6 +28,7 @@
 #include "hessian_fast.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <memory>
 
 namespace ipcb {
 
@@ -1064,7 +1065,8 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
         }
         IPCB_CUDA(cudaGetLastError());
     }
-    Stage st(ctx, "hessian_assemble");
+    // stage timers (only when ctx->timing is on): the three kernels of the assembly are timed one by one
+    std::unique_ptr<Stage> st(new Stage(ctx, "hess_incidences"));
     int vbits = 1;
     while ((1ll << vbits) < nV) vbits++;
     // 1. incidences grouped by vertex (stable: each column keeps the collision order)
@@ -1082,6 +1084,8 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     k_col_ranges<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, int(ninc), ctx->hkey_sorted.p, ref_ev, ref_ee, ctx->hcolinc.p, ctx->hcolR.p);
     cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, b2, ctx->hcolR.p, ctx->hitemoff.p, nV + 1, s);
     ctx->launches += 3;
+    st.reset();
+    st.reset(new Stage(ctx, "hess_symbolic"));
     // 3. pass 1: per-column sort by row vertex, pattern counts
     ctx->hsref.reserve(nitems);
     ctx->hbig.reserve(size_t(nV) + 1);
@@ -1119,6 +1123,8 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     }
     ctx->nnz = *reinterpret_cast<int*>(&ctx->pinned.p[9]);
     ctx->inner.reserve(std::max<int64_t>(ctx->nnz, 1)), ctx->vals.reserve(std::max<int64_t>(ctx->nnz, 1));
+    st.reset();
+    st.reset(new Stage(ctx, "hess_numeric"));
     // 5. pass 2: gather, run-sum, write compressed columns
     k_hess_numeric<<<grid_for(nV, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p,
                                                                        ctx->hblk.p, ctx->outer.p, ctx->inner.p, ctx->vals.p);

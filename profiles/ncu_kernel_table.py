@@ -1,4 +1,5 @@
-"""Per-kernel table from an `ncu --set full` report:  python profiles/ncu_kernel_table.py gpurun_out/prof.ncu-rep"""
+"""Per-kernel table from an `ncu --set full` report (or its `--page raw --csv` export):
+    python profiles/ncu_kernel_table.py gpurun_out/prof.ncu-rep"""
 import csv
 import io
 import subprocess
@@ -14,7 +15,10 @@ WANT = [
 
 
 def main(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):  # already exported with `ncu -i report --page raw --csv`
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = [(hdr.index(k) if k in hdr else -1, n, w) for k, n, w in WANT]
