@@ -186,6 +186,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     api = ipctk_b200.library()
     lib = api.lib
@@ -323,9 +324,33 @@ def main():
         e2e_bytes["d2h"] = 8 + 24 * nV + 4 * (3 * nV + 1) + 12 * n + 8
         info["step"], info["energy"] = st.value, e.value
 
-    ms_e2e = None
-    if world == 1:
-        ms_e2e = timed(host_step, max(2, args.steps // 2), 1)
+    h_small = torch.zeros(2, dtype=torch.float64).pin_memory()
+
+    def sharded_host_step():
+        """N > 1: pinned host positions in, host results out around the sharded device step (the all-reduces need
+        device buffers): H2D of V0 / V1, the device step with its NCCL all-reduces, D2H of energy, gradient, step size
+        and of this rank's Hessian CSR"""
+        with torch.cuda.stream(stream):
+            dV0.copy_(hV0, non_blocking=True)
+            dV1.copy_(hV1, non_blocking=True)
+        device_step()
+        with torch.cuda.stream(stream):
+            h_grad.copy_(d_grad, non_blocking=True)
+            h_small[0:1].copy_(d_energy, non_blocking=True)
+            h_small[1:2].copy_(d_step, non_blocking=True)
+        n = nnz.value
+        if hbuf.get("n", -1) < n:
+            hbuf["outer"] = torch.zeros(3 * nV + 1, dtype=torch.int32).pin_memory()
+            hbuf["inner"] = torch.zeros(int(n * 1.2) + 1, dtype=torch.int32).pin_memory()
+            hbuf["vals"] = torch.zeros(int(n * 1.2) + 1, dtype=torch.float64).pin_memory()
+            hbuf["n"] = int(n * 1.2)
+        lib.check(lib.barrier_hessian_fetch(ctx, C.c_void_p(hbuf["outer"].data_ptr()), C.c_void_p(hbuf["inner"].data_ptr()),
+                                            C.c_void_p(hbuf["vals"].data_ptr())))
+        e2e_bytes["h2d"] = 24 * nV * 2
+        e2e_bytes["d2h"] = 8 + 24 * nV + 4 * (3 * nV + 1) + 12 * n + 8
+        info["step"], info["energy"] = float(h_small[1]), float(h_small[0])
+
+    ms_e2e = timed(host_step if world == 1 else sharded_host_step, max(2, args.steps // 2), 1)
     sampler.stop_flag = True
 
     # ---- rooflines (algorithmic bytes per launch: DESIGN.md §4, SURVEY §8d), kernel times = CUDA-event stage times
@@ -404,6 +429,12 @@ def main():
         print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
+    # The library's stream (wrapped as a torch ExternalStream) dies with the mesh; pinned / device tensors that were
+    # last used on it must not outlive it.  Leave without running destructors in an arbitrary order.
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == "__main__":
