@@ -178,7 +178,7 @@ __device__ inline unsigned long long expand21(unsigned long long v)
     v = (v | v << 2) & 0x1249249249249249ull;
     return v;
 }
-__global__ void k_morton(int n, int bits, const FBox* __restrict__ box, const float* __restrict__ scene,
+__global__ void k_morton(int n, int bits, int uniform, const FBox* __restrict__ box, const float* __restrict__ scene,
                          unsigned long long* __restrict__ key, int* __restrict__ ord)
 {
     const double cells = double(1u << bits);
@@ -186,9 +186,14 @@ __global__ void k_morton(int n, int bits, const FBox* __restrict__ box, const fl
     if (i >= n) return;
     const FBox b = box[i];
     unsigned long long code = 0;
+    // ONE cell size for the three axes (the largest scene extent), unlike the reference's per-axis normalisation
+    // (lbvh.cpp:152-166): in a flat scene (stacked cloth) the short axis then only contributes its low bits, the
+    // upper levels of the tree split along the long axes and node boxes stay close to cubes.  The candidate set
+    // does not depend on the tree; `uniform` = 0 restores the per-axis cells.
+    const double wmax = fmax(fmax(double(scene[3]) - double(scene[0]), double(scene[4]) - double(scene[1])), double(scene[5]) - double(scene[2]));
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const double w = double(scene[3 + k]) - double(scene[k]);
+        const double w = uniform ? wmax : double(scene[3 + k]) - double(scene[k]);
         double m = w > 0 ? (0.5 * (double(b.lo[k]) + double(b.hi[k])) - double(scene[k])) / w : 0.0;
         m = fmin(fmax(m * cells, 0.0), cells - 1.0);
         code |= expand21((unsigned long long)m) << (2 - k);
@@ -305,7 +310,7 @@ static void build_tree(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, bool with_node
     t.key.reserve(n), t.key_sorted.reserve(n), t.ord.reserve(n), t.ord_sorted.reserve(n);
     t.sbox.reserve(n), t.sprim.reserve(n);
     const int bits = morton_bits(n);
-    k_morton<<<grid_for(n, 256), 256, 0, s>>>(n, bits, ps.box.p, ctx->scene.p, t.key.p, t.ord.p);
+    k_morton<<<grid_for(n, 256), 256, 0, s>>>(n, bits, getenv("IPCB_MORTON_PER_AXIS") ? 0 : 1, ps.box.p, ctx->scene.p, t.key.p, t.ord.p);
     sort_keys(ctx, t, n, bits, s);
     k_apply_order<<<grid_for(n, 256), 256, 0, s>>>(n, t.ord_sorted.p, ps.box.p, ps.prim.p, t.sbox.p, t.sprim.p);
     ctx->launches += 2;
