@@ -166,6 +166,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--workload", default="c3")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--additive-hessian", action="store_true",
+                    help="N > 1: keep every rank's potential on its own collision shard (Hessian = additive contribution) "
+                         "instead of the all-gathered set with row-block Hessians")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: warm up, then run ONE device step between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench line")
@@ -221,30 +224,19 @@ def main():
         for i in range(n):
             stage_acc.setdefault(names[i].decode(), []).append(ms[i])
 
+    # the step itself lives in the package (ipc-toolkit_b200/sharded.py) so that the tests exercise the same code:
+    # N = 1: the five library calls; N > 1: sharded broad phase, all-gather + merge of the collision records,
+    # energy / gradient by collision range, Hessian by balanced row block, all-reduces
+    sharded = __import__("importlib").import_module("ipc_toolkit_b200.sharded")
+    stepper = sharded.DeviceShardedStep(api, mesh, rank, world, dist, torch, stream, row_block=not args.additive_hessian)
+
     def device_step(record=False):
-        p0, p1 = C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr())
-        lib.check(lib.collisions_build_dev(ctx, p0, nV, dhat, 0.0, 0, counts))
-        if record:
-            collect_stages()
-        info["collisions"] = list(counts)
-        lib.check(lib.barrier_energy_dev(ctx, p0, nV, C.byref(bp), C.c_void_p(d_energy.data_ptr())))
-        if record:
-            collect_stages()
-        lib.check(lib.barrier_gradient_dev(ctx, p0, nV, C.byref(bp), C.c_void_p(d_grad.data_ptr())))
-        if record:
-            collect_stages()
-        lib.check(lib.barrier_hessian_dev(ctx, p0, nV, C.byref(bp), 1, C.byref(nnz)))
-        if record:
-            collect_stages()
-        info["nnz"] = nnz.value
-        lib.check(lib.ccd_stepsize_dev(ctx, p0, p1, nV, 0.0, C.byref(ccd), C.c_void_p(d_step.data_ptr())))
-        if record:
-            collect_stages()
-        if dist is not None:  # sum / sum / min all-reduces over NVLink; the Hessian stays per rank
-            with torch.cuda.stream(stream):
-                dist.all_reduce(d_energy)
-                dist.all_reduce(d_grad)
-                dist.all_reduce(d_step, op=dist.ReduceOp.MIN)
+        stepper.after = collect_stages if record else None
+        info["nnz"] = stepper.step(dV0, dV1, d_energy, d_grad, d_step, dhat, bp, ccd)
+        info["collisions"] = list(stepper.counts)
+        info["shard_collisions"] = list(stepper.shard_counts)
+        info["rows"] = list(stepper.rows)
+        nnz.value = info["nnz"]
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -413,7 +405,11 @@ def main():
             "data": "synthetic",
             "config": {"workload": desc, "triangles": int(F.shape[0]), "vertices": int(nV), "edges": int(E.shape[0]), "dhat": dhat,
                        "psd": "CLAMP", "ccd": "TightInclusion", "l2": "flushed between timed steps (256 MB write)",
-                       "parallelism": "candidate shards by Morton range of query leaves" if world > 1 else "single GPU"},
+                       "parallelism": ("single GPU" if world == 1 else
+                                       "candidate shards by Morton range of query leaves; " +
+                                       ("Hessian as additive rank contributions" if args.additive_hessian else
+                                        "collision records all-gathered + merged, energy/gradient by collision range, "
+                                        "Hessian by balanced row block (no collective)"))},
             "e2e": None if ms_e2e is None else {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": e2e_bytes["h2d"],
                                                 "d2h_bytes_per_step": e2e_bytes["d2h"]},
             "gpu_launches": int(launches),
@@ -422,7 +418,8 @@ def main():
             "rooflines": rooflines,
             "cpu_baseline": cpu,
             "stages_ms": stages,
-            "counts": {"collisions_rank0": ncoll, "ccd_candidates_rank0": info.get("ccd_candidates"),
+            "counts": {"collisions_rank0": ncoll, "shard_collisions_rank0": info.get("shard_collisions"),
+                       "hessian_rows_rank0": info.get("rows"), "ccd_candidates_rank0": info.get("ccd_candidates"),
                        "hessian_nnz_rank0": info.get("nnz"), "step": info.get("step"),
                        "energy": info.get("energy")},
         }

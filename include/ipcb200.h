@@ -144,6 +144,30 @@ int IPCB_FN(collisions_fetch)(ipcb_ctx* ctx, int32_t kind, int32_t* ids, double*
                               uint8_t* dtype);
 /* compute_minimum_distance (normal_collisions.cpp:209-233): min squared distance, +inf if empty */
 int IPCB_FN(collisions_min_distance)(ipcb_ctx* ctx, const double* V, int32_t ld, double* min_dist_sqr);
+/* The reference's collision containers are public data (normal_collisions.hpp:177-189: vv_collisions ..
+ * fv_collisions) and NormalCollisions::build fills them by merging per-thread builders
+ * (NormalCollisionsBuilder::merge, builder.cpp:547-689: equal collisions are united and their weights
+ * added, weight == 0 dropped).  These three calls expose exactly that step: start an empty set, append the
+ * records of any number of builders (= of the other ranks of a sharded build), merge.  The merged set
+ * becomes the context's resident set, in canonical order (sorted ids), as after collisions_build.
+ * Records: ids count x 2 row-major (as collisions_fetch returns them), weight, and for EE eps_x and dtype. */
+int IPCB_FN(collisions_clear)(ipcb_ctx* ctx);
+int IPCB_FN(collisions_append)(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_t* ids, const double* weight,
+                               const double* eps_x, const uint8_t* dtype);
+int IPCB_FN(collisions_merge)(ipcb_ctx* ctx, double dmin, int64_t counts[4]);
+/* Sharding of the potential over ranks, for contexts that all hold the SAME collision set:
+ *  - collision range: energy and gradient only visit the slice [rank*n/world, (rank+1)*n/world) of every
+ *    kind's collisions (the results need a sum all-reduce);
+ *  - row block: the Hessian is assembled only for the DOF rows (== columns, the matrix is symmetric) of the
+ *    vertices [v_begin, v_end); local Hessians are computed for every collision touching such a vertex and
+ *    only the owned rows are kept, so the rank matrices tile the global matrix without any exchange.
+ *    outer keeps its global length 3nV+1 (empty outside the block).  v_end < 0 selects all vertices. */
+int IPCB_FN(ctx_set_collision_range)(ipcb_ctx* ctx, int32_t rank, int32_t world);
+int IPCB_FN(ctx_set_row_block)(ipcb_ctx* ctx, int32_t v_begin, int32_t v_end);
+/* Row-block boundaries that balance the Hessian work: bounds[0..world] ascending with bounds[0] = 0,
+ * bounds[world] = nV, such that every block holds about the same number of 3x3 block contributions of
+ * the resident collision set (deterministic: identical on every rank holding the same set). */
+int IPCB_FN(hessian_balanced_row_blocks)(ipcb_ctx* ctx, int32_t world, int32_t* bounds /* world + 1 */);
 
 /* ---- BarrierPotential (potentials/potential.cpp:36-222) ----------------- */
 int IPCB_FN(barrier_energy)(ipcb_ctx* ctx, const double* V, int32_t ld, const ipcb_barrier_params* bp, double* energy);
@@ -183,6 +207,13 @@ int IPCB_FN(collisions_build_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, d
                                   int32_t flags, int64_t counts[4]);
 int IPCB_FN(collisions_build_from_candidates_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, double dhat,
                                                   double dmin, int32_t flags, int64_t counts[4]);
+/* device pointers to the resident collision set of one kind (ids: int32 count x 2; eps_x / dtype NULL unless EE);
+ * valid until the next collision build / merge on this context */
+int IPCB_FN(collisions_dev_ptrs)(ipcb_ctx* ctx, int32_t kind, int64_t* count, const int32_t** d_ids, const double** d_weight,
+                                 const double** d_eps_x, const uint8_t** d_dtype);
+/* collisions_append with DEVICE arrays (e.g. the all-gathered records of the other ranks) */
+int IPCB_FN(collisions_append_dev)(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_t* d_ids, const double* d_weight,
+                                   const double* d_eps_x, const uint8_t* d_dtype);
 int IPCB_FN(barrier_energy_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, const ipcb_barrier_params* bp,
                                 double* d_energy /* device, 1 double */);
 int IPCB_FN(barrier_gradient_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, const ipcb_barrier_params* bp,
@@ -192,6 +223,13 @@ int IPCB_FN(barrier_hessian_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, co
 /* device pointers to the resident CSR of the last barrier_hessian (valid until the next one) */
 int IPCB_FN(barrier_hessian_dev_ptrs)(ipcb_ctx* ctx, const int32_t** d_outer, const int32_t** d_inner,
                                       const double** d_values);
+/* The rank-to-rank exchange format of a sharded build: all records of the resident set in ONE device buffer,
+ * so that one all-gather moves them.  Layout for counts n[VV..FV], every array 8-byte aligned, in this order:
+ *   ids_vv (8 n0) | w_vv (8 n0) | ids_ev | w_ev | ids_ee | w_ee | eps_ee (8 n2) | ids_fv | w_fv | dtype_ee (n2, padded to 8)
+ * = 16 (n0 + n1 + n3) + 24 n2 + pad8(n2) bytes.  pack copies on the context's stream and does not synchronise;
+ * append_packed is collisions_append_dev for each kind of one packed buffer. */
+int IPCB_FN(collisions_pack_dev)(ipcb_ctx* ctx, void* d_buffer, int64_t capacity_bytes, int64_t* bytes);
+int IPCB_FN(collisions_append_packed_dev)(ipcb_ctx* ctx, const void* d_buffer, const int64_t counts[4]);
 int IPCB_FN(candidates_build_swept_dev)(ipcb_ctx* ctx, const double* dV0, const double* dV1, int32_t ld,
                                         double inflation_radius, int64_t counts[4]);
 int IPCB_FN(ccd_stepsize_dev)(ipcb_ctx* ctx, const double* dV0, const double* dV1, int32_t ld, double min_distance,

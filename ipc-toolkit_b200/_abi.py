@@ -43,6 +43,12 @@ HOST_API = {
     "collisions_build_from_candidates": (C.c_int, [P, P, c_i32, c_f64, c_f64, c_i32, C.POINTER(c_i64)]),
     "collisions_fetch": (C.c_int, [P, c_i32, P, P, P, P]),
     "collisions_min_distance": (C.c_int, [P, P, c_i32, C.POINTER(c_f64)]),
+    "collisions_clear": (C.c_int, [P]),
+    "collisions_append": (C.c_int, [P, c_i32, c_i64, P, P, P, P]),
+    "collisions_merge": (C.c_int, [P, c_f64, C.POINTER(c_i64)]),
+    "ctx_set_collision_range": (C.c_int, [P, c_i32, c_i32]),
+    "ctx_set_row_block": (C.c_int, [P, c_i32, c_i32]),
+    "hessian_balanced_row_blocks": (C.c_int, [P, c_i32, P]),
     "barrier_energy": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), C.POINTER(c_f64)]),
     "barrier_gradient": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), P]),
     "barrier_hessian": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), c_i32, C.POINTER(c_i64)]),
@@ -60,6 +66,10 @@ DEVICE_API = {
     "barrier_gradient_dev": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), P]),
     "barrier_hessian_dev": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), c_i32, C.POINTER(c_i64)]),
     "barrier_hessian_dev_ptrs": (C.c_int, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
+    "collisions_dev_ptrs": (C.c_int, [P, c_i32, C.POINTER(c_i64), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
+    "collisions_append_dev": (C.c_int, [P, c_i32, c_i64, P, P, P, P]),
+    "collisions_pack_dev": (C.c_int, [P, P, c_i64, C.POINTER(c_i64)]),
+    "collisions_append_packed_dev": (C.c_int, [P, P, C.POINTER(c_i64)]),
     "candidates_build_swept_dev": (C.c_int, [P, P, P, c_i32, c_f64, C.POINTER(c_i64)]),
     "ccd_stepsize_dev": (C.c_int, [P, P, P, c_i32, c_f64, C.POINTER(CcdParams), P]),
     "ccd_stepsize_from_candidates_dev": (C.c_int, [P, P, P, c_i32, c_f64, C.POINTER(CcdParams), P]),

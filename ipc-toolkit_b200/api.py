@@ -152,6 +152,18 @@ def make_api(lib):
         def edge_areas(self):
             return self._areas()[1]
 
+        # ---- sharding of the potential over ranks holding the same collision set (include/ipcb200.h)
+        def set_collision_range(self, rank, world):
+            lib.check(lib.ctx_set_collision_range(self._ctx, rank, world))
+
+        def set_row_block(self, v_begin=0, v_end=-1):
+            lib.check(lib.ctx_set_row_block(self._ctx, v_begin, v_end))
+
+        def balanced_row_blocks(self, world):
+            bounds = np.zeros(world + 1, np.int32)
+            lib.check(lib.hessian_balanced_row_blocks(self._ctx, world, bounds.ctypes.data_as(C.c_void_p)))
+            return bounds
+
         def _areas(self):
             va = np.zeros(self.num_vertices())
             ea = np.zeros(self.num_edges())
@@ -317,6 +329,30 @@ def make_api(lib):
                 v, p, ld = _f64(V)
                 lib.check(lib.collisions_build(mesh._ctx, p, ld, dhat, dmin, flags, counts))
                 mesh._cand_gen += 1  # the resident candidates were rebuilt too
+            self._bind(mesh, counts, dmin)
+
+        def assign(self, mesh, builders, dmin=0.0):
+            """Fill the set from the records of several builders and merge them like
+            NormalCollisionsBuilder::merge (builder.cpp:547-689: equal collisions united, weights added,
+            weight == 0 dropped).  `builders`: iterable of 4-tuples (vv, ev, ee, fv) of record namespaces as the
+            *_collisions properties return them (ids, weight, eps_x, dtype) — e.g. the sets of the other ranks."""
+            lib.check(lib.collisions_clear(mesh._ctx))
+            for kinds in builders:
+                for kind, rec in enumerate(kinds):
+                    if rec is None:
+                        continue
+                    ids = np.ascontiguousarray(rec.ids, np.int32).reshape(-1, 2)
+                    w = np.ascontiguousarray(rec.weight, np.float64)
+                    eps = np.ascontiguousarray(rec.eps_x, np.float64)
+                    dt = np.ascontiguousarray(rec.dtype, np.uint8)
+                    lib.check(lib.collisions_append(mesh._ctx, kind, ids.shape[0], ids.ctypes.data_as(C.c_void_p),
+                                                    w.ctypes.data_as(C.c_void_p), eps.ctypes.data_as(C.c_void_p),
+                                                    dt.ctypes.data_as(C.c_void_p)))
+            counts = (C.c_int64 * 4)()
+            lib.check(lib.collisions_merge(mesh._ctx, dmin, counts))
+            self._bind(mesh, counts, dmin)
+
+        def _bind(self, mesh, counts, dmin):
             self.mesh = mesh
             mesh._coll_gen += 1
             self._gen = mesh._coll_gen

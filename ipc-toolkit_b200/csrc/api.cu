@@ -119,6 +119,30 @@ int ipcb_ctx_set_shard(ipcb_ctx* ctx, int32_t rank, int32_t world)
         ctx->shard_world = world;
     });
 }
+int ipcb_ctx_set_collision_range(ipcb_ctx* ctx, int32_t rank, int32_t world)
+{
+    return guarded([&] {
+        if (world < 1 || rank < 0 || rank >= world) throw Error("bad collision range");
+        ctx->coll_rank = rank;
+        ctx->coll_world = world;
+    });
+}
+int ipcb_ctx_set_row_block(ipcb_ctx* ctx, int32_t v_begin, int32_t v_end)
+{
+    return guarded([&] {
+        if (v_end >= 0 && (v_begin < 0 || v_begin > v_end)) throw Error("bad row block");
+        ctx->row_lo = v_end < 0 ? 0 : v_begin;
+        ctx->row_hi = v_end < 0 ? -1 : v_end;
+    });
+}
+int ipcb_hessian_balanced_row_blocks(ipcb_ctx* ctx, int32_t world, int32_t* bounds)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        require_collisions(ctx);
+        hessian_balanced_row_blocks(ctx, world, bounds);
+    });
+}
 int ipcb_ctx_launch_count(ipcb_ctx* ctx, int64_t* n)
 {
     *n = ctx->launches;
@@ -444,6 +468,132 @@ int ipcb_collisions_fetch(ipcb_ctx* ctx, int32_t kind, int32_t* ids, double* wei
             if (dtype) std::fill(dtype, dtype + n, uint8_t(0));
         }
         IPCB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+int ipcb_collisions_clear(ipcb_ctx* ctx)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        collisions_clear(ctx);
+    });
+}
+static void check_collision_kind(int32_t kind, int64_t count)
+{
+    if (kind < 0 || kind > 3) throw Error("bad collision kind");
+    if (count < 0) throw Error("negative collision count");
+}
+int ipcb_collisions_append_dev(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_t* d_ids, const double* d_weight,
+                               const double* d_eps_x, const uint8_t* d_dtype)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        check_collision_kind(kind, count);
+        collisions_append_dev(ctx, kind, count, d_ids, d_weight, d_eps_x, d_dtype);
+    });
+}
+int ipcb_collisions_append(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_t* ids, const double* weight, const double* eps_x,
+                           const uint8_t* dtype)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        check_collision_kind(kind, count);
+        if (count == 0) return;
+        const int limit = kind == IPCB_VV ? ctx->nV : (kind == IPCB_FV ? ctx->nF : ctx->nE);
+        const int limit2 = kind == IPCB_EE ? ctx->nE : ctx->nV;
+        for (int64_t i = 0; i < count; i++)
+            if (ids[2 * i] < 0 || ids[2 * i] >= limit || ids[2 * i + 1] < 0 || ids[2 * i + 1] >= limit2)
+                throw Error("collision index out of range");
+        if (kind == IPCB_EE && (!eps_x || !dtype)) throw Error("edge-edge collision records need eps_x and dtype");
+        // stage through device scratch (the Hessian key buffers are free between assemblies)
+        cudaStream_t s = ctx->stream;
+        const size_t n = size_t(count);
+        ctx->hkey.reserve(n), ctx->hkey_sorted.reserve(n), ctx->stageA.reserve(n), ctx->stageB.reserve(n);
+        IPCB_CUDA(cudaMemcpyAsync(ctx->hkey.p, ids, sizeof(int2) * n, cudaMemcpyHostToDevice, s));
+        IPCB_CUDA(cudaMemcpyAsync(ctx->stageA.p, weight, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        if (kind == IPCB_EE) {
+            IPCB_CUDA(cudaMemcpyAsync(ctx->stageB.p, eps_x, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+            IPCB_CUDA(cudaMemcpyAsync(ctx->hkey_sorted.p, dtype, n, cudaMemcpyHostToDevice, s));
+        }
+        collisions_append_dev(ctx, kind, count, reinterpret_cast<const int32_t*>(ctx->hkey.p), ctx->stageA.p, ctx->stageB.p,
+                              reinterpret_cast<const uint8_t*>(ctx->hkey_sorted.p));
+        IPCB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+int ipcb_collisions_merge(ipcb_ctx* ctx, double dmin, int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        collisions_merge(ctx, dmin);
+        coll_counts(ctx, counts);
+    });
+}
+int ipcb_collisions_dev_ptrs(ipcb_ctx* ctx, int32_t kind, int64_t* count, const int32_t** d_ids, const double** d_weight,
+                             const double** d_eps_x, const uint8_t** d_dtype)
+{
+    return guarded([&] {
+        if (kind < 0 || kind > 3) throw Error("bad collision kind");
+        require_collisions(ctx);
+        const CollisionSet& cs = ctx->coll[kind];
+        *count = cs.count;
+        *d_ids = reinterpret_cast<const int32_t*>(cs.ids.p);
+        *d_weight = cs.w.p;
+        *d_eps_x = kind == IPCB_EE ? cs.eps.p : nullptr;
+        *d_dtype = kind == IPCB_EE ? cs.dtype.p : nullptr;
+    });
+}
+namespace {
+struct PackedLayout {
+    int64_t ids[4], w[4], eps, dt, bytes;
+};
+PackedLayout packed_layout(const int64_t n[4])
+{
+    PackedLayout L;
+    int64_t off = 0;
+    for (int k = 0; k < 4; k++) {
+        L.ids[k] = off, off += 8 * n[k];
+        L.w[k] = off, off += 8 * n[k];
+        if (k == IPCB_EE) L.eps = off, off += 8 * n[k];
+    }
+    L.dt = off, off += (n[IPCB_EE] + 7) / 8 * 8;
+    L.bytes = off;
+    return L;
+}
+} // namespace
+int ipcb_collisions_pack_dev(ipcb_ctx* ctx, void* d_buffer, int64_t capacity_bytes, int64_t* bytes)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        require_collisions(ctx);
+        int64_t n[4];
+        coll_counts(ctx, n);
+        const PackedLayout L = packed_layout(n);
+        *bytes = L.bytes;
+        if (L.bytes > capacity_bytes) throw Error("collisions_pack_dev: buffer too small");
+        char* out = static_cast<char*>(d_buffer);
+        cudaStream_t s = ctx->stream;
+        for (int k = 0; k < 4; k++) {
+            if (n[k] == 0) continue;
+            const CollisionSet& cs = ctx->coll[k];
+            IPCB_CUDA(cudaMemcpyAsync(out + L.ids[k], cs.ids.p, 8 * n[k], cudaMemcpyDeviceToDevice, s));
+            IPCB_CUDA(cudaMemcpyAsync(out + L.w[k], cs.w.p, 8 * n[k], cudaMemcpyDeviceToDevice, s));
+            if (k == IPCB_EE) {
+                IPCB_CUDA(cudaMemcpyAsync(out + L.eps, cs.eps.p, 8 * n[k], cudaMemcpyDeviceToDevice, s));
+                IPCB_CUDA(cudaMemcpyAsync(out + L.dt, cs.dtype.p, n[k], cudaMemcpyDeviceToDevice, s));
+            }
+        }
+    });
+}
+int ipcb_collisions_append_packed_dev(ipcb_ctx* ctx, const void* d_buffer, const int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        for (int k = 0; k < 4; k++) check_collision_kind(k, counts[k]);
+        const PackedLayout L = packed_layout(counts);
+        const char* in = static_cast<const char*>(d_buffer);
+        for (int k = 0; k < 4; k++)
+            collisions_append_dev(ctx, k, counts[k], reinterpret_cast<const int32_t*>(in + L.ids[k]),
+                                  reinterpret_cast<const double*>(in + L.w[k]), reinterpret_cast<const double*>(in + L.eps),
+                                  reinterpret_cast<const uint8_t*>(in + L.dt));
     });
 }
 int ipcb_collisions_min_distance(ipcb_ctx* ctx, const double* V, int32_t ld, double* out)

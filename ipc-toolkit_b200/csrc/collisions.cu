@@ -230,6 +230,8 @@ static void merge_stream_enqueue(ipcb_ctx* ctx, int kind, int64_t n, cudaStream_
     IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[21 + 2 * kind], cs.head.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
 }
 
+static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4]);
+
 void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
 {
     cudaStream_t s = ctx->stream;
@@ -277,6 +279,12 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
         IPCB_CUDA(cudaStreamSynchronize(s));
     }
     const int64_t raw[4] = { ctx->pinned.p[0], ctx->pinned.p[1], ctx->pinned.p[2], ctx->pinned.p[3] };
+    merge_streams(ctx, raw);
+}
+
+static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4])
+{
+    cudaStream_t s = ctx->stream;
     Stage st(ctx, "merge_collisions");
     // the four streams are merged concurrently (their sorts are small and latency-bound): EE on the main stream
     cudaStream_t where[4] = { ctx->aux[0], ctx->aux[1], s, ctx->aux[2] };
@@ -288,6 +296,52 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
         ctx->coll[k].count = int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[20 + 2 * k])) + int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[21 + 2 * k]));
     }
     for (int k = 0; k < ipcb_ctx::NAUX; k++) ctx->join(k);
+}
+
+// ---- public containers + NormalCollisionsBuilder::merge (normal_collisions.hpp:177-189, builder.cpp:547-689) -------
+// collisions_clear / collisions_append / collisions_merge: records of several builders (the ranks of a sharded
+// build) are appended to the raw streams as (key, weight[, eps, dtype]) and merged by the same sort + run-merge
+// that finishes collisions_build.
+__global__ void k_ids_to_keys(int64_t n, const int2* __restrict__ ids, int unordered, unsigned long long* __restrict__ key)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = ids[i];
+    key[i] = unordered ? mkkey(min(c.x, c.y), max(c.x, c.y)) : mkkey(c.x, c.y);
+}
+void collisions_clear(ipcb_ctx* ctx)
+{
+    for (auto& c : ctx->coll) c.count = 0, c.raw_count = 0;
+    ctx->coll_valid = false;
+}
+void collisions_append_dev(ipcb_ctx* ctx, int kind, int64_t n, const int32_t* d_ids, const double* d_w, const double* d_eps,
+                           const uint8_t* d_dt)
+{
+    if (n == 0) return;
+    cudaStream_t s = ctx->stream;
+    CollisionSet& cs = ctx->coll[kind];
+    const size_t have = size_t(cs.raw_count), want = have + size_t(n);
+    if (want > 0x7fffffffull) throw Error("more than 2^31 collision records of one kind");
+    cs.key_raw.reserve_keep(want, have, s), cs.w_raw.reserve_keep(want, have, s);
+    if (kind == IPCB_EE) cs.eps_raw.reserve_keep(want, have, s), cs.dt_raw.reserve_keep(want, have, s);
+    k_ids_to_keys<<<grid_for(n, 256), 256, 0, s>>>(n, reinterpret_cast<const int2*>(d_ids), kind == IPCB_VV || kind == IPCB_EE, cs.key_raw.p + have);
+    ctx->launches++;
+    IPCB_CUDA(cudaMemcpyAsync(cs.w_raw.p + have, d_w, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+    if (kind == IPCB_EE) {
+        if (!d_eps || !d_dt) throw Error("edge-edge collision records need eps_x and dtype");
+        IPCB_CUDA(cudaMemcpyAsync(cs.eps_raw.p + have, d_eps, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        IPCB_CUDA(cudaMemcpyAsync(cs.dt_raw.p + have, d_dt, n, cudaMemcpyDeviceToDevice, s));
+    }
+    IPCB_CUDA(cudaGetLastError());
+    cs.raw_count = int64_t(want);
+}
+void collisions_merge(ipcb_ctx* ctx, double dmin)
+{
+    ctx->dmin = dmin;
+    ctx->coll_valid = true;
+    const int64_t raw[4] = { ctx->coll[0].raw_count, ctx->coll[1].raw_count, ctx->coll[2].raw_count, ctx->coll[3].raw_count };
+    for (auto& c : ctx->coll) c.count = 0, c.raw_count = 0;
+    merge_streams(ctx, raw);
 }
 
 // ---- compute_minimum_distance (normal_collisions.cpp:209-233) ----------------------

@@ -70,6 +70,7 @@ struct CollisionSet {
     Buf<double> wsum;
     Buf<char> cubtmp; // per stream: the four merges run concurrently
     int64_t count = 0;
+    int64_t raw_count = 0; // records appended through collisions_append since the last collisions_clear
 };
 
 struct StageTimer {
@@ -98,6 +99,8 @@ struct ipcb_ctx {
     }
     int64_t launches = 0;
     int shard_rank = 0, shard_world = 1;
+    int coll_rank = 0, coll_world = 1; // energy / gradient: slice of every kind's collisions
+    int row_lo = 0, row_hi = -1;       // Hessian: owned vertex range (row_hi < 0: all)
     bool timing = false; // per-stage CUDA-event timing (synchronises at every stage boundary)
 
     // ---- host mesh (collision_mesh.cpp:15-127)
@@ -207,12 +210,17 @@ void sort_pairs(ipcb_ctx* ctx, PairList& pl);
 
 // collisions (collisions.cu)
 void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags);
+void collisions_clear(ipcb_ctx* ctx);
+void collisions_append_dev(ipcb_ctx* ctx, int kind, int64_t n, const int32_t* d_ids, const double* d_w, const double* d_eps,
+                           const uint8_t* d_dt);
+void collisions_merge(ipcb_ctx* ctx, double dmin);
 double collisions_min_distance(ipcb_ctx* ctx);
 
 // potential (potential.cu)
 void barrier_energy(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_out);
 void barrier_gradient(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_grad);
 void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode);
+void hessian_balanced_row_blocks(ipcb_ctx* ctx, int world, int32_t* bounds);
 
 // ccd (ccd.cu)
 void ccd_stepsize(ipcb_ctx* ctx, double min_distance, const ipcb_ccd_params& p, double* d_out);

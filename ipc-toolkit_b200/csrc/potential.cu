@@ -138,6 +138,17 @@ static CollView view(const ipcb_ctx* ctx, int k)
     const CollisionSet& cs = ctx->coll[k];
     return { k, cs.count, cs.ids.p, cs.w.p, cs.eps.p, cs.dtype.p };
 }
+// energy / gradient on a rank of a sharded potential: the slice [rank*n/world, (rank+1)*n/world) of the kind
+static CollView view_slice(const ipcb_ctx* ctx, int k)
+{
+    CollView c = view(ctx, k);
+    if (ctx->coll_world > 1) {
+        const int64_t lo = c.n * ctx->coll_rank / ctx->coll_world, hi = c.n * (ctx->coll_rank + 1) / ctx->coll_world;
+        c.ids += lo, c.w += lo, c.n = hi - lo;
+        if (k == IPCB_EE) c.eps += lo, c.dt += lo;
+    }
+    return c;
+}
 static MeshView mesh_view(const ipcb_ctx* ctx) { return { ctx->dE.p, ctx->dF.p, ctx->X0.p }; }
 
 void barrier_energy(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_out)
@@ -146,13 +157,14 @@ void barrier_energy(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_out)
     cudaStream_t s = ctx->stream;
     const BarrierDev B = make_barrier(bp, ctx->dmin);
     size_t nblocks = 0;
-    for (int k = 0; k < 4; k++) nblocks += grid_for(ctx->coll[k].count, EBLOCK);
+    for (int k = 0; k < 4; k++) nblocks += grid_for(view_slice(ctx, k).n, EBLOCK);
     ctx->dScalar.reserve(nblocks + 16);
     size_t off = 0;
     for (int k = 0; k < 4; k++) {
-        const unsigned g = grid_for(ctx->coll[k].count, EBLOCK);
+        const CollView c = view_slice(ctx, k);
+        const unsigned g = grid_for(c.n, EBLOCK);
         if (!g) continue;
-        k_energy<<<g, EBLOCK, 0, s>>>(view(ctx, k), mesh_view(ctx), B, ctx->dScalar.p + off);
+        k_energy<<<g, EBLOCK, 0, s>>>(c, mesh_view(ctx), B, ctx->dScalar.p + off);
         off += g;
         ctx->launches++;
     }
@@ -234,11 +246,11 @@ void barrier_gradient(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_gr
     const BarrierDev B = make_barrier(bp, ctx->dmin);
     IPCB_CUDA(cudaMemsetAsync(d_grad, 0, sizeof(double) * 3 * size_t(ctx->nV), s));
     const MeshView m = mesh_view(ctx);
-    const int64_t n0 = ctx->coll[0].count, n1 = ctx->coll[1].count, n2 = ctx->coll[2].count, n3 = ctx->coll[3].count;
-    if (n0) k_gradient<IPCB_VV><<<grid_for(n0, 256), 256, 0, s>>>(view(ctx, 0), m, B, d_grad), ctx->launches++;
-    if (n1) k_gradient<IPCB_EV><<<grid_for(n1, 256), 256, 0, s>>>(view(ctx, 1), m, B, d_grad), ctx->launches++;
-    if (n2) k_gradient<IPCB_EE><<<grid_for(n2, 256), 256, 0, s>>>(view(ctx, 2), m, B, d_grad), ctx->launches++;
-    if (n3) k_gradient<IPCB_FV><<<grid_for(n3, 256), 256, 0, s>>>(view(ctx, 3), m, B, d_grad), ctx->launches++;
+    const CollView c0 = view_slice(ctx, 0), c1 = view_slice(ctx, 1), c2 = view_slice(ctx, 2), c3 = view_slice(ctx, 3);
+    if (c0.n) k_gradient<IPCB_VV><<<grid_for(c0.n, 256), 256, 0, s>>>(c0, m, B, d_grad), ctx->launches++;
+    if (c1.n) k_gradient<IPCB_EV><<<grid_for(c1.n, 256), 256, 0, s>>>(c1, m, B, d_grad), ctx->launches++;
+    if (c2.n) k_gradient<IPCB_EE><<<grid_for(c2.n, 256), 256, 0, s>>>(c2, m, B, d_grad), ctx->launches++;
+    if (c3.n) k_gradient<IPCB_FV><<<grid_for(c3.n, 256), 256, 0, s>>>(c3, m, B, d_grad), ctx->launches++;
     IPCB_CUDA(cudaGetLastError());
 }
 
@@ -368,14 +380,23 @@ struct HessOut {
     unsigned short* mask;    // 16 per collision: 9-bit exact-non-zero mask per slot
     double* blk;             // 16 x 9 per collision
     unsigned long long* inc; // incidences: (vertex << 32) | (gi * 4 + a), NP per collision
+    int v_lo, v_hi;          // owned vertex range (row block of a sharded Hessian); incidences of other
+    int v_none;              // vertices get the vertex key v_none (= nV: sorted behind every column)
 };
 constexpr int HSLOTS = 16;
 
-template <int NP> __device__ inline void write_record(const HessOut& out, int64_t gi, int64_t inc_base, const int* vid)
+// returns the mask of the stencil points whose vertex this rank owns
+template <int NP> __device__ inline unsigned write_record(const HessOut& out, int64_t gi, int64_t inc_base, const int* vid)
 {
     out.vid[gi] = make_int4(vid[0], vid[1], NP > 2 ? vid[2] : -1, NP > 3 ? vid[3] : -1);
+    unsigned own = 0;
 #pragma unroll
-    for (int a = 0; a < NP; a++) out.inc[inc_base + a] = ((unsigned long long)(unsigned)vid[a] << 32) | (unsigned long long)(gi * 4 + a);
+    for (int a = 0; a < NP; a++) {
+        const bool mine = vid[a] >= out.v_lo && vid[a] < out.v_hi;
+        own |= unsigned(mine) << a;
+        out.inc[inc_base + a] = ((unsigned long long)(unsigned)(mine ? vid[a] : out.v_none) << 32) | (unsigned long long)(gi * 4 + a);
+    }
+    return own;
 }
 
 template <int KIND>
@@ -390,6 +411,8 @@ __global__ void __launch_bounds__(128)
     int vid[4];
     d3 x[4];
     load_stencil(KIND, c.ids[i], m, vid, x);
+    // listed collisions already have their record; a collision without an owned vertex contributes nothing
+    if (!list && write_record<NP>(out, gi0 + i, inc0 + i * NP, vid) == 0) return;
     const double w = c.w[i];
     LocalDeriv D;
     zero_local(D);
@@ -462,7 +485,6 @@ __global__ void __launch_bounds__(128)
     }
     // emit the NP x NP vertex blocks: slot (column point bj, row point bi)
     const int64_t gi = gi0 + i;
-    if (!list) write_record<NP>(out, gi, inc0 + i * NP, vid); // listed collisions already have their record
     unsigned short masks[HSLOTS];
 #pragma unroll
     for (int k = 0; k < HSLOTS; k++) masks[k] = 0;
@@ -502,14 +524,15 @@ __global__ void __launch_bounds__(128)
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool valid = i < c.n;
     bool is_slow = false;
+    unsigned own = 0; // stencil points whose vertex (column) this rank owns
     FastProj<P> pr;
     if (valid) {
         int vid[4];
         d3 x[4];
         load_stencil(KIND, c.ids[i], m, vid, x);
-        write_record<NP>(out, gi0 + i, inc0 + i * NP, vid);
-        if (KIND == IPCB_EE) is_slow = c.dt[i] != EE_AB || sqn(cross(x[1] - x[0], x[3] - x[2])) < c.eps[i];
-        if (!is_slow) {
+        own = write_record<NP>(out, gi0 + i, inc0 + i * NP, vid);
+        if (KIND == IPCB_EE) is_slow = own != 0 && (c.dt[i] != EE_AB || sqn(cross(x[1] - x[0], x[3] - x[2])) < c.eps[i]);
+        if (!is_slow && own != 0) {
             FastGeom g;
             fast_geometry(PRIM, x, g);
             const double d2 = sub_value(collision_sub(KIND, EE_AB), x); // the same value the energy / gradient use
@@ -517,8 +540,8 @@ __global__ void __launch_bounds__(128)
             fast_project<P>(g, w * B.df(d2), w * B.ddf(d2), psd_mode, pr);
         }
     }
-    const bool emit = valid && !is_slow;
-    const unsigned emask = __ballot_sync(0xffffffffu, emit);
+    const bool emit = valid && !is_slow && own != 0;
+    const unsigned emask_any = __ballot_sync(0xffffffffu, emit);
     const unsigned smask = __ballot_sync(0xffffffffu, is_slow);
     if (smask) {
         unsigned long long basep = 0;
@@ -526,14 +549,17 @@ __global__ void __launch_bounds__(128)
         basep = __shfl_sync(0xffffffffu, basep, __ffs(smask) - 1);
         if (is_slow) slow[basep + __popc(smask & ((1u << lane) - 1))] = int(i);
     }
-    if (emask == 0) return;
+    if (emask_any == 0) return;
     const int64_t gw = gi0 + (i - lane); // global index of lane 0's collision
     unsigned mpack[HSLOTS / 2];
 #pragma unroll
     for (int k = 0; k < HSLOTS / 2; k++) mpack[k] = 0;
 #pragma unroll
     for (int a = 0; a < NP; a++) { // column point
-        if (emit) {
+        const bool emit_a = emit && ((own >> a) & 1u);
+        const unsigned emask = __ballot_sync(0xffffffffu, emit_a);
+        if (emask == 0) continue;
+        if (emit_a) {
 #pragma unroll
             for (int b = 0; b < NP; b++) { // row point
                 double blk[9];
@@ -1002,6 +1028,70 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
     }
 }
 
+// ---- balanced row blocks of a sharded Hessian: per vertex, the number of 3x3 blocks its column receives ----------
+template <int KIND> __global__ void k_vertex_load(CollView c, MeshView m, int* __restrict__ load)
+{
+    constexpr int NP = KIND == IPCB_VV ? 2 : (KIND == IPCB_EV ? 3 : 4);
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    const int2 id = c.ids[i];
+    int vid[4];
+    if (KIND == IPCB_VV) {
+        vid[0] = id.x, vid[1] = id.y;
+    } else if (KIND == IPCB_EV) {
+        const int2 e = __ldg(m.E + id.x);
+        vid[0] = id.y, vid[1] = e.x, vid[2] = e.y;
+    } else if (KIND == IPCB_EE) {
+        const int2 ea = __ldg(m.E + id.x), eb = __ldg(m.E + id.y);
+        vid[0] = ea.x, vid[1] = ea.y, vid[2] = eb.x, vid[3] = eb.y;
+    } else {
+        const int4 f = __ldg(m.F + id.x);
+        vid[0] = id.y, vid[1] = f.x, vid[2] = f.y, vid[3] = f.z;
+    }
+#pragma unroll
+    for (int a = 0; a < NP; a++) atomicAdd(load + vid[a], NP);
+}
+// bounds[r] = first vertex whose exclusive prefix load reaches r * total / world
+__global__ void k_balance_bounds(int nV, const int* __restrict__ prefix, int world, int* __restrict__ bounds)
+{
+    const int r = threadIdx.x;
+    if (r > world) return;
+    const long long total = prefix[nV];
+    const long long want = total * r / world;
+    int lo = 0, hi = nV;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] < want) lo = mid + 1;
+        else hi = mid;
+    }
+    bounds[r] = r == 0 ? 0 : (r == world ? nV : lo);
+}
+void hessian_balanced_row_blocks(ipcb_ctx* ctx, int world, int32_t* bounds)
+{
+    cudaStream_t s = ctx->stream;
+    const int nV = ctx->nV;
+    if (world < 1 || world > 1024) throw Error("bad world size");
+    ctx->hcolR.reserve(size_t(nV) + 2), ctx->hitemoff.reserve(size_t(nV) + 2 + 1032);
+    IPCB_CUDA(cudaMemsetAsync(ctx->hcolR.p, 0, sizeof(int) * (size_t(nV) + 1), s));
+    const MeshView m = mesh_view(ctx);
+    const int64_t n0 = ctx->coll[0].count, n1 = ctx->coll[1].count, n2 = ctx->coll[2].count, n3 = ctx->coll[3].count;
+    if (n0) k_vertex_load<IPCB_VV><<<grid_for(n0, 256), 256, 0, s>>>(view(ctx, 0), m, ctx->hcolR.p), ctx->launches++;
+    if (n1) k_vertex_load<IPCB_EV><<<grid_for(n1, 256), 256, 0, s>>>(view(ctx, 1), m, ctx->hcolR.p), ctx->launches++;
+    if (n2) k_vertex_load<IPCB_EE><<<grid_for(n2, 256), 256, 0, s>>>(view(ctx, 2), m, ctx->hcolR.p), ctx->launches++;
+    if (n3) k_vertex_load<IPCB_FV><<<grid_for(n3, 256), 256, 0, s>>>(view(ctx, 3), m, ctx->hcolR.p), ctx->launches++;
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, ctx->hcolR.p, ctx->hitemoff.p, nV + 1, s);
+    ctx->cubtmp.reserve(bytes + 1024);
+    cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, bytes, ctx->hcolR.p, ctx->hitemoff.p, nV + 1, s);
+    int* d_bounds = ctx->hitemoff.p + nV + 2;
+    k_balance_bounds<<<1, 1024, 0, s>>>(nV, ctx->hitemoff.p, world, d_bounds);
+    ctx->launches += 3;
+    IPCB_CUDA(cudaGetLastError());
+    IPCB_CUDA(cudaMemcpyAsync(bounds, d_bounds, sizeof(int) * (world + 1), cudaMemcpyDeviceToHost, s));
+    IPCB_CUDA(cudaStreamSynchronize(s));
+    for (int r = 1; r <= world; r++) bounds[r] = std::max(bounds[r], bounds[r - 1]);
+}
+
 __global__ void k_zero_int(int64_t n, int* p)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -1032,7 +1122,8 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
         Stage st(ctx, "hessian_local");
         ctx->hvid.reserve(ncoll), ctx->hmask.reserve(size_t(ncoll) * HSLOTS), ctx->hblk.reserve(size_t(ncoll) * HSLOTS * 9);
         ctx->hkey.reserve(ninc), ctx->hkey_sorted.reserve(ninc);
-        const HessOut out { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p, ctx->hkey.p };
+        const int v_lo = ctx->row_hi < 0 ? 0 : std::max(0, ctx->row_lo), v_hi = ctx->row_hi < 0 ? nV : std::min(nV, ctx->row_hi);
+        const HessOut out { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p, ctx->hkey.p, v_lo, v_hi, nV };
         const MeshView m = mesh_view(ctx);
         static const bool force_general = getenv("IPCB_HESSIAN_GENERAL") != nullptr; // A/B switch for tests and profiles
         if (psd_mode == IPCB_PSD_NONE || force_general) {
@@ -1068,7 +1159,7 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     // stage timers (only when ctx->timing is on): the three kernels of the assembly are timed one by one
     std::unique_ptr<Stage> st(new Stage(ctx, "hess_incidences"));
     int vbits = 1;
-    while ((1ll << vbits) < nV) vbits++;
+    while ((1ll << vbits) <= nV) vbits++; // the value nV marks incidences of vertices outside the rank's row block
     // 1. incidences grouped by vertex (stable: each column keeps the collision order)
     size_t b1 = 0, b2 = 0, b3 = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, b1, ctx->hkey.p, ctx->hkey_sorted.p, ninc, 32, 32 + vbits, s);

@@ -1,20 +1,36 @@
-"""Multi-GPU contact step: one process per GPU, every rank holds the whole mesh and the positions,
-works on a disjoint shard of the broad-phase candidates, and the results combine with three all-reduces
-(energy: sum, gradient: sum, step size: min).  The Hessian stays the rank's additive contribution.
+"""Multi-GPU contact step: one process per GPU, every rank holds the whole mesh and the positions.
 
-`ShardedContactStep` is host-side plumbing over the API classes of `api.py` and `torch.distributed`; it runs
-unchanged on NCCL (CUDA tensors, product library) and on gloo (CPU tensors; used by the world-size-2 tests with
-the candidate shard selected through the public Candidates container instead of the device-side Morton range).
+1. Broad phase + classification are sharded: rank r traverses only its Morton range of query leaves
+   (`ipcb_ctx_set_shard`), so the ranks produce disjoint candidate shards with no exchange.
+2. The per-rank collision sets are the reference's per-thread builders at rank granularity: ONE all-gather of the
+   packed records (16-24 B each) and `NormalCollisionsBuilder::merge` on every rank (`collisions_append*` +
+   `collisions_merge`) leave the full, canonical `NormalCollisions` on every rank — what the API returns anyway.
+3. The potential is sharded over that common set: energy and gradient by collision range (sum all-reduces), the
+   Hessian by row block — rank r assembles the DOF rows of its vertex range from every collision touching them and
+   keeps only those rows, so the rank matrices tile the global CSR and need no collective.  Row-block boundaries are
+   chosen to balance the number of 3x3 block contributions (`hessian_balanced_row_blocks`, identical on all ranks).
+4. The step size is the min all-reduce of the per-shard earliest times of impact.
+
+`ShardedContactStep` is the host-side form over the API classes of `api.py` and `torch.distributed` (works on gloo
+with any library exporting the host ABI: the world-size-2 CPU tests drive it through the oracle, with the candidate
+shard selected through the public Candidates container instead of the device-side Morton range).
+`DeviceShardedStep` is the device-resident form used by `bench.py` and the NCCL test: device positions in, device
+energy / gradient / step size out, nothing staged through the host except four counts per rank.
 """
+import ctypes as C
+
 import numpy as np
 
 
 class ShardedContactStep:
-    def __init__(self, api, mesh, rank, world, dist=None, device=None, native=True):
+    def __init__(self, api, mesh, rank, world, dist=None, device=None, native=True, row_block=True):
         """native=True: the library shards the query leaves itself (ipcb_ctx_set_shard, product only);
         native=False: candidates are built in full and rank r keeps the slice [r*n/world, (r+1)*n/world) of every
-        kind through Candidates.set (works with any library that exports the host ABI)."""
+        kind through Candidates.set (works with any library that exports the host ABI).
+        row_block=False keeps the simpler combination: every rank's potential over its own collision shard, the
+        Hessian as the rank's additive contribution (sum over ranks == global matrix)."""
         self.api, self.mesh, self.rank, self.world, self.dist, self.device, self.native = api, mesh, rank, world, dist, device, native
+        self.row_block = row_block and world > 1 and dist is not None
         if native:
             api.lib.check(api.lib.ctx_set_shard(mesh._ctx, rank, world))
 
@@ -41,6 +57,18 @@ class ShardedContactStep:
         self.dist.all_reduce(t, op=op)
         return t.cpu().numpy().reshape(np.shape(array))
 
+    def _gather_collisions(self, coll, dmin):
+        """all ranks' records -> the merged, canonical set on every rank"""
+        mine = (coll.vv_collisions, coll.ev_collisions, coll.ee_collisions, coll.fv_collisions)
+        parts = [None] * self.world
+        self.dist.all_gather_object(parts, [(r.ids, r.weight, r.eps_x, r.dtype) for r in mine])
+        import types
+
+        builders = [[types.SimpleNamespace(ids=k[0], weight=k[1], eps_x=k[2], dtype=k[3]) for k in p] for p in parts]
+        full = self.api.NormalCollisions()
+        full.assign(self.mesh, builders, dmin)
+        return full
+
     def step(self, V0, V1, dhat, stiffness=1.0, psd=None, dmin=0.0, min_distance=0.0, ccd=None):
         api = self.api
         cand = api.Candidates()
@@ -48,10 +76,21 @@ class ShardedContactStep:
         cand = self._shard_candidates(cand)
         coll = api.NormalCollisions()
         coll.build(cand, self.mesh, V0, dhat, dmin)
+        shard_counts = coll.counts()
+        rows = None
+        if self.row_block:
+            coll = self._gather_collisions(coll, dmin)
+            bounds = self.mesh.balanced_row_blocks(self.world)
+            rows = (int(bounds[self.rank]), int(bounds[self.rank + 1]))
+            self.mesh.set_collision_range(self.rank, self.world)
+            self.mesh.set_row_block(*rows)
         B = api.BarrierPotential(dhat, stiffness)
         energy = B(coll, self.mesh, V0)
         grad = B.gradient(coll, self.mesh, V0)
         H = B.hessian(coll, self.mesh, V0, api.PSDProjectionMethod.CLAMP if psd is None else psd)
+        if self.row_block:
+            self.mesh.set_collision_range(0, 1)
+            self.mesh.set_row_block()
         swept = api.Candidates()
         swept.build(self.mesh, V0, V1, 0.5 * min_distance)
         swept = self._shard_candidates(swept)
@@ -61,4 +100,98 @@ class ShardedContactStep:
             energy = float(self._allreduce(np.array([energy]), SUM)[0])
             grad = self._allreduce(grad, SUM)
             step = float(self._allreduce(np.array([step]), MIN)[0])
-        return dict(energy=energy, gradient=grad, hessian_local=H, step=step, collisions=coll.counts())
+        return dict(energy=energy, gradient=grad, hessian_local=H, rows=rows, step=step, shard_collisions=shard_counts,
+                    collisions=coll.counts())
+
+
+def packed_bytes(counts):
+    """size of the exchange buffer of include/ipcb200.h (collisions_pack_dev) for counts [VV, EV, EE, FV]"""
+    n0, n1, n2, n3 = (int(c) for c in counts)
+    return 16 * (n0 + n1 + n3) + 24 * n2 + (n2 + 7) // 8 * 8
+
+
+class DeviceShardedStep:
+    """The sharded contact step with device-resident inputs and outputs (product library + NCCL).
+
+    dV0 / dV1: torch CUDA tensors holding N x 3 column-major positions; d_energy (1), d_grad (3N), d_step (1): torch CUDA
+    float64 outputs.  All library calls and collectives are enqueued on the context's stream."""
+
+    def __init__(self, api, mesh, rank, world, dist, torch, stream, row_block=True):
+        self.api, self.lib, self.mesh, self.ctx = api, api.lib, mesh, mesh._ctx
+        self.rank, self.world, self.dist, self.torch, self.stream = rank, world, dist, torch, stream
+        self.row_block = row_block and world > 1
+        self.lib.check(self.lib.ctx_set_shard(self.ctx, rank, world))
+        self.counts = (C.c_int64 * 4)()
+        self.nnz = C.c_int64()
+        self.send = self.recv = None
+        self.cap = 0
+        self.d_counts = torch.zeros(4, dtype=torch.int64, device="cuda")
+        self.d_counts_all = torch.zeros(4 * world, dtype=torch.int64, device="cuda")
+        self.h_counts = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self.rows = (0, mesh.num_vertices())
+        self.shard_counts = [0, 0, 0, 0]
+        self.after = None  # optional callback after every library call (bench.py collects stage times)
+
+    def _done(self):
+        if self.after is not None:
+            self.after()
+
+    def exchange_collisions(self, dmin):
+        torch, lib, dist = self.torch, self.lib, self.dist
+        self.shard_counts = list(self.counts)
+        # 1. counts of every rank (the only host round trip of the exchange)
+        self.h_counts.copy_(torch.tensor(self.shard_counts, dtype=torch.int64))
+        with torch.cuda.stream(self.stream):
+            self.d_counts.copy_(self.h_counts, non_blocking=True)
+            dist.all_gather_into_tensor(self.d_counts_all, self.d_counts)
+            all_counts = self.d_counts_all.cpu().view(self.world, 4).tolist()
+        need = max(packed_bytes(c) for c in all_counts)
+        if need > self.cap:
+            self.cap = int(need * 1.25) + 1024
+            self.cap -= self.cap % 16
+            self.send = torch.empty(self.cap, dtype=torch.uint8, device="cuda")
+            self.recv = torch.empty(self.cap * self.world, dtype=torch.uint8, device="cuda")
+        # 2. one all-gather of the packed records (only the used prefix of every slot travels)
+        used = (need + 15) // 16 * 16
+        nbytes = C.c_int64()
+        lib.check(lib.collisions_pack_dev(self.ctx, C.c_void_p(self.send.data_ptr()), self.cap, C.byref(nbytes)))
+        recv = self.recv[:used * self.world]
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(recv, self.send[:used])
+        # 3. NormalCollisionsBuilder::merge over the ranks' records
+        lib.check(lib.collisions_clear(self.ctx))
+        for r in range(self.world):
+            c = (C.c_int64 * 4)(*all_counts[r])
+            lib.check(lib.collisions_append_packed_dev(self.ctx, C.c_void_p(recv.data_ptr() + r * used), c))
+        lib.check(lib.collisions_merge(self.ctx, dmin, self.counts))
+        self._done()
+        # 4. balanced row blocks for the Hessian, collision ranges for energy / gradient
+        bounds = self.mesh.balanced_row_blocks(self.world)
+        self.rows = (int(bounds[self.rank]), int(bounds[self.rank + 1]))
+
+    def step(self, dV0, dV1, d_energy, d_grad, d_step, dhat, bp, ccd, dmin=0.0, min_distance=0.0, psd=1):
+        torch, lib, dist, ctx = self.torch, self.lib, self.dist, self.ctx
+        nV = self.mesh.num_vertices()
+        p0, p1 = C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr())
+        lib.check(lib.collisions_build_dev(ctx, p0, nV, dhat, dmin, 0, self.counts))
+        self._done()
+        if self.row_block:
+            self.exchange_collisions(dmin)
+            lib.check(lib.ctx_set_collision_range(ctx, self.rank, self.world))
+            lib.check(lib.ctx_set_row_block(ctx, *self.rows))
+        else:
+            self.shard_counts = list(self.counts)
+        lib.check(lib.barrier_energy_dev(ctx, p0, nV, C.byref(bp), C.c_void_p(d_energy.data_ptr())))
+        self._done()
+        lib.check(lib.barrier_gradient_dev(ctx, p0, nV, C.byref(bp), C.c_void_p(d_grad.data_ptr())))
+        self._done()
+        lib.check(lib.barrier_hessian_dev(ctx, p0, nV, C.byref(bp), psd, C.byref(self.nnz)))
+        self._done()
+        lib.check(lib.ccd_stepsize_dev(ctx, p0, p1, nV, min_distance, C.byref(ccd), C.c_void_p(d_step.data_ptr())))
+        self._done()
+        if self.world > 1:  # sum / sum / min all-reduces over NVLink; the Hessian needs no collective
+            with torch.cuda.stream(self.stream):
+                dist.all_reduce(d_energy)
+                dist.all_reduce(d_grad)
+                dist.all_reduce(d_step, op=dist.ReduceOp.MIN)
+        return self.nnz.value

@@ -81,7 +81,10 @@ struct ipcb_ctx {
     // candidates + collisions
     std::vector<Pair> cand[4];
     std::vector<Coll> coll[4];
+    std::vector<Coll> appended[4]; // collisions_append since the last collisions_clear
     double dmin = 0;
+    int coll_rank = 0, coll_world = 1; // energy / gradient: slice of every kind's collisions
+    int row_lo = 0, row_hi = -1;       // Hessian: owned vertex range (row_hi < 0: all)
     // hessian
     std::vector<int32_t> outer, inner;
     std::vector<double> vals;
@@ -427,6 +430,29 @@ int stencil_ids(const ipcb_ctx* ctx, int kind, int a, int b, int32_t ids[4])
     }
 }
 
+// NormalCollisionsBuilder::merge (builder.cpp:604-689): records of all builders united, equal collisions
+// merged with weight accumulation, weight == 0 dropped; canonical order = sorted by (a, b, dtype)
+void merge_collisions(ipcb_ctx* ctx, int k, std::vector<Coll>& all)
+{
+    __gnu_parallel::stable_sort(all.begin(), all.end(), [](const Coll& x, const Coll& y) {
+        if (x.a != y.a) return x.a < y.a;
+        if (x.b != y.b) return x.b < y.b;
+        return x.dtype < y.dtype;
+    });
+    std::vector<Coll>& out = ctx->coll[k];
+    out.clear();
+    for (const Coll& c : all) {
+        if (k != IPCB_FV && !out.empty() && out.back().a == c.a && out.back().b == c.b && out.back().dtype == c.dtype) {
+            out.back().w += c.w;
+        } else {
+            out.push_back(c);
+        }
+    }
+    if (k != IPCB_FV) {
+        out.erase(std::remove_if(out.begin(), out.end(), [](const Coll& c) { return c.w == 0; }), out.end());
+    }
+}
+
 // NormalCollisions::build(candidates, ...) — normal_collisions.cpp:38-158 with
 // the IPC set type, builder.cpp:26-336 (classification + reduction) and
 // :547-689 (merge with weight accumulation, weight == 0 dropped)
@@ -511,27 +537,10 @@ void collisions_build(ipcb_ctx* ctx, const std::vector<V3>& V, double dhat, doub
         default: loc[IPCB_FV][t].push_back({ fi, vi, w, 0, 0 }); break;
         }
     }
-    // merge (builder.cpp:604-689); canonical order = sorted by (a, b, dtype)
     for (int k = 0; k < 4; k++) {
         std::vector<Coll> all;
         for (auto& l : loc[k]) all.insert(all.end(), l.begin(), l.end());
-        __gnu_parallel::stable_sort(all.begin(), all.end(), [](const Coll& x, const Coll& y) {
-            if (x.a != y.a) return x.a < y.a;
-            if (x.b != y.b) return x.b < y.b;
-            return x.dtype < y.dtype;
-        });
-        std::vector<Coll>& out = ctx->coll[k];
-        out.clear();
-        for (const Coll& c : all) {
-            if (k != IPCB_FV && !out.empty() && out.back().a == c.a && out.back().b == c.b && out.back().dtype == c.dtype) {
-                out.back().w += c.w;
-            } else {
-                out.push_back(c);
-            }
-        }
-        if (k != IPCB_FV) {
-            out.erase(std::remove_if(out.begin(), out.end(), [](const Coll& c) { return c.w == 0; }), out.end());
-        }
+        merge_collisions(ctx, k, all);
     }
     ctx->dmin = dmin; // normal_collisions.cpp:154-157
 }
@@ -960,6 +969,66 @@ int ipco_collisions_fetch(ipcb_ctx* ctx, int32_t kind, int32_t* ids, double* wei
     }
     return 0;
 }
+int ipco_collisions_clear(ipcb_ctx* ctx)
+{
+    for (int k = 0; k < 4; k++) ctx->coll[k].clear(), ctx->appended[k].clear();
+    return 0;
+}
+int ipco_collisions_append(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_t* ids, const double* weight, const double* eps_x,
+                           const uint8_t* dtype)
+{
+    if (kind < 0 || kind > 3) return fail("bad collision kind");
+    if (kind == IPCB_EE && count > 0 && (!eps_x || !dtype)) return fail("edge-edge collision records need eps_x and dtype");
+    for (int64_t i = 0; i < count; i++) {
+        int32_t a = ids[2 * i], b = ids[2 * i + 1];
+        if (kind == IPCB_VV || kind == IPCB_EE)
+            if (a > b) std::swap(a, b);
+        ctx->appended[kind].push_back({ a, b, weight[i], kind == IPCB_EE ? eps_x[i] : 0.0, kind == IPCB_EE ? dtype[i] : uint8_t(0) });
+    }
+    return 0;
+}
+int ipco_collisions_merge(ipcb_ctx* ctx, double dmin, int64_t counts[4])
+{
+    for (int k = 0; k < 4; k++) {
+        merge_collisions(ctx, k, ctx->appended[k]);
+        ctx->appended[k].clear();
+    }
+    ctx->dmin = dmin;
+    coll_counts(ctx, counts);
+    return 0;
+}
+int ipco_ctx_set_collision_range(ipcb_ctx* ctx, int32_t rank, int32_t world)
+{
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad collision range");
+    ctx->coll_rank = rank, ctx->coll_world = world;
+    return 0;
+}
+int ipco_ctx_set_row_block(ipcb_ctx* ctx, int32_t v_begin, int32_t v_end)
+{
+    if (v_end >= 0 && (v_begin < 0 || v_begin > v_end)) return fail("bad row block");
+    ctx->row_lo = v_end < 0 ? 0 : v_begin, ctx->row_hi = v_end < 0 ? -1 : v_end;
+    return 0;
+}
+// same rule as the product: per vertex the number of 3x3 blocks its column receives, boundaries at r * total / world
+int ipco_hessian_balanced_row_blocks(ipcb_ctx* ctx, int32_t world, int32_t* bounds)
+{
+    if (world < 1) return fail("bad world size");
+    std::vector<long long> prefix(size_t(ctx->nV) + 1, 0);
+    for (int k = 0; k < 4; k++)
+        for (const Coll& c : ctx->coll[k]) {
+            int32_t ids[4];
+            const int n = stencil_ids(ctx, k, c.a, c.b, ids);
+            for (int j = 0; j < n; j++) prefix[size_t(ids[j]) + 1] += n;
+        }
+    for (int v = 0; v < ctx->nV; v++) prefix[v + 1] += prefix[v];
+    const long long total = prefix[ctx->nV];
+    for (int r = 0; r <= world; r++) {
+        const long long want = total * r / world;
+        bounds[r] = r == 0 ? 0 : (r == world ? ctx->nV : int32_t(std::lower_bound(prefix.begin(), prefix.begin() + ctx->nV, want) - prefix.begin()));
+    }
+    for (int r = 1; r <= world; r++) bounds[r] = std::max(bounds[r], bounds[r - 1]);
+    return 0;
+}
 int ipco_collisions_min_distance(ipcb_ctx* ctx, const double* Vp, int32_t ld, double* out)
 {
     const auto V = load_vertices(ctx->nV, Vp, ld);
@@ -984,8 +1053,9 @@ int ipco_barrier_energy(ipcb_ctx* ctx, const double* Vp, int32_t ld, const ipcb_
     for (int k = 0; k < 4; k++) {
         const auto& cs = ctx->coll[k];
         double sum = 0;
+        const size_t lo = cs.size() * size_t(ctx->coll_rank) / size_t(ctx->coll_world), hi = cs.size() * size_t(ctx->coll_rank + 1) / size_t(ctx->coll_world);
 #pragma omp parallel for reduction(+ : sum) schedule(static)
-        for (size_t i = 0; i < cs.size(); i++) {
+        for (size_t i = lo; i < hi; i++) {
             int32_t ids[4];
             const int n = stencil_ids(ctx, k, cs[i].a, cs[i].b, ids);
             V3 x[4];
@@ -1007,8 +1077,9 @@ int ipco_barrier_gradient(ipcb_ctx* ctx, const double* Vp, int32_t ld, const ipc
     std::vector<std::vector<double>> loc(nt); // tbb::combinable<VectorXd> (potential.cpp:74-94)
     for (int k = 0; k < 4; k++) {
         const auto& cs = ctx->coll[k];
+        const size_t lo = cs.size() * size_t(ctx->coll_rank) / size_t(ctx->coll_world), hi = cs.size() * size_t(ctx->coll_rank + 1) / size_t(ctx->coll_world);
 #pragma omp parallel for schedule(static)
-        for (size_t i = 0; i < cs.size(); i++) {
+        for (size_t i = lo; i < hi; i++) {
             auto& mine = loc[omp_get_thread_num()];
             if (mine.empty()) mine.assign(ndof, 0.0);
             int32_t ids[4];
@@ -1038,6 +1109,7 @@ int ipco_barrier_hessian(ipcb_ctx* ctx, const double* Vp, int32_t ld, const ipcb
         double val;
     };
     const int nt = omp_get_max_threads();
+    const int row_lo = ctx->row_hi < 0 ? 0 : ctx->row_lo, row_hi = ctx->row_hi < 0 ? ctx->nV : ctx->row_hi;
     std::vector<std::vector<Trip>> loc(nt);
     for (int k = 0; k < 4; k++) {
         const auto& cs = ctx->coll[k];
@@ -1048,16 +1120,21 @@ int ipco_barrier_hessian(ipcb_ctx* ctx, const double* Vp, int32_t ld, const ipcb
             const int n = stencil_ids(ctx, k, cs[i].a, cs[i].b, ids);
             V3 x[4];
             for (int j = 0; j < n; j++) x[j] = V[ids[j]];
+            bool any_owned = false;
+            for (int j = 0; j < n; j++) any_owned |= ids[j] >= row_lo && ids[j] < row_hi;
+            if (!any_owned) continue; // row block of a sharded Hessian: this collision touches no owned vertex
             double H[144];
             collision_hessian(k, cs[i], x, B, ctx->dmin, psd_mode, H);
             // utils/local_to_global.hpp:263-305: exact zeros are skipped
             for (int a = 0; a < n; a++)
-                for (int b = 0; b < n; b++)
+                for (int b = 0; b < n; b++) {
+                    if (ids[b] < row_lo || ids[b] >= row_hi) continue; // columns (== rows) of other ranks
                     for (int r = 0; r < 3; r++)
                         for (int c = 0; c < 3; c++) {
                             const double val = H[(3 * a + r) + 12 * (3 * b + c)];
                             if (val != 0) mine.push_back({ 3 * ids[b] + c, 3 * ids[a] + r, val });
                         }
+                }
         }
     }
     std::vector<Trip> all;

@@ -262,3 +262,77 @@ def test_empty_inputs(cuda):
     H = B.hessian(c, mesh, V)
     assert H.shape == (9, 9) and H.nnz == 0  # potential.cpp:107-109
     assert cuda.compute_collision_free_stepsize(mesh, V, V + 1.0) == 1.0  # candidates.cpp:263-265
+
+
+@pytest.mark.parametrize("name", ["stack", "drape", "dense3"])
+def test_collision_merge_and_sharded_potential(cuda, oracle, scenes, name):
+    """NormalCollisionsBuilder::merge over several builders (collisions_clear / append / merge) and the sharded
+    potential (collision ranges for energy / gradient, row blocks for the Hessian) against the oracle: merging the
+    records of two overlapping halves restores the set with accumulated weights; the range / block results of three
+    pretend ranks tile the single-context results."""
+    import types
+
+    V0, V1, E, F, P = _scene(scenes, name)
+    dhat = P["dhat"]
+    X = V0 + 0.02 * dhat * np.sin(np.arange(V0.size).reshape(V0.shape))
+    world = 3
+    out = {}
+    for key, api in (("cuda", cuda), ("oracle", oracle)):
+        mesh = api.CollisionMesh(V0, E, F)
+        c = api.NormalCollisions()
+        c.build(mesh, V0, dhat)
+        full = [getattr(c, k + "_collisions") for k in ("vv", "ev", "ee", "fv")]
+        B = api.BarrierPotential(dhat, 1.0)
+        ref = dict(e=B(c, mesh, X), g=B.gradient(c, mesh, X), h=B.hessian(c, mesh, X, api.PSDProjectionMethod.CLAMP))
+
+        def part(rec, sl, kind):  # VV / EV / EE records of the overlap appear in both builders; FV ones are never merged
+            return types.SimpleNamespace(ids=rec.ids[sl], weight=rec.weight[sl], eps_x=rec.eps_x[sl], dtype=rec.dtype[sl])
+
+        builders = []
+        for b in range(2):
+            kinds = []
+            for kind, rec in enumerate(full):
+                n = len(rec.ids)
+                lo, hi = (0, (2 * n) // 3) if b == 0 else (n // 3, n)
+                if kind == 3:
+                    lo, hi = (0, n // 2) if b == 0 else (n // 2, n)
+                kinds.append(part(rec, slice(lo, hi), kind))
+            builders.append(kinds[::1])
+        builders.reverse()  # order of the builders must not matter
+        m = api.NormalCollisions()
+        m.assign(mesh, builders, 0.0)
+        merged = [getattr(m, k + "_collisions") for k in ("vv", "ev", "ee", "fv")]
+        for kind, (a, b) in enumerate(zip(merged, full)):
+            assert np.array_equal(a.ids, b.ids) and np.array_equal(a.dtype, b.dtype) and np.array_equal(a.eps_x, b.eps_x)
+            n = len(b.ids)
+            expect = b.weight.copy()
+            if kind != 3:
+                expect[n // 3:(2 * n) // 3] *= 2  # the overlap was contributed by both builders
+            assert np.array_equal(a.weight, expect)
+        # back to unit weights, then the sharded potential
+        m.assign(mesh, [full], 0.0)
+        bounds = mesh.balanced_row_blocks(world)
+        e, g, tiles = 0.0, 0.0, []
+        for r in range(world):
+            mesh.set_collision_range(r, world)
+            mesh.set_row_block(int(bounds[r]), int(bounds[r + 1]))
+            e += B(m, mesh, X)
+            g = g + B.gradient(m, mesh, X)
+            tiles.append(B.hessian(m, mesh, X, api.PSDProjectionMethod.CLAMP))
+        mesh.set_collision_range(0, 1)
+        mesh.set_row_block()
+        assert abs(e - ref["e"]) <= 1e-12 * abs(ref["e"]) and relerr(g, ref["g"]) <= 1e-12
+        H = ref["h"].tocsc()
+        for r, T in enumerate(tiles):
+            lo, hi = 3 * int(bounds[r]), 3 * int(bounds[r + 1])
+            T = T.tocsc()
+            assert T[:, :lo].nnz == 0 and T[:, hi:].nnz == 0
+            A, Bm = T[:, lo:hi], H[:, lo:hi]
+            assert np.array_equal(A.indptr, Bm.indptr) and np.array_equal(A.indices, Bm.indices)
+            assert relerr(A.data, Bm.data) <= 1e-13
+        assert sum(T.nnz for T in tiles) == H.nnz
+        out[key] = dict(bounds=bounds, merged=merged, tiles=tiles)
+    assert np.array_equal(out["cuda"]["bounds"], out["oracle"]["bounds"])
+    assert out["cuda"]["bounds"][0] == 0 and out["cuda"]["bounds"][-1] == V0.shape[0]
+    for a, b in zip(out["cuda"]["tiles"], out["oracle"]["tiles"]):
+        assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) and relerr(a.data, b.data) <= RTOL

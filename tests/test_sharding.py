@@ -1,7 +1,10 @@
 """Multi-GPU host logic on CPU: two gloo ranks, each working on its shard of the candidates through
-the oracle library, must reproduce the single-rank energy / gradient / step size after the all-reduces, and the sum
-of the rank Hessians must equal the single-rank Hessian (same pattern, values to 1e-10).  The GPU variant runs the
-same class on NCCL with the device-side Morton-range shard (`-m gpu`, needs 2 GPUs)."""
+the oracle library, must reproduce the single-rank energy / gradient / step size after the all-reduces.
+row_block mode: the ranks' collision records are all-gathered and merged (every rank then holds exactly the
+single-rank set), energy / gradient run on collision ranges and every rank assembles only its row block of the
+Hessian: the blocks must tile the single-rank matrix (pattern identical, values to 1e-10).  additive mode: the sum
+of the rank Hessians must equal the single-rank Hessian.  The GPU variants run the same classes on NCCL with the
+device-side Morton-range shard (`-m gpu`, need 2 GPUs), and the device-resident step `bench.py` uses."""
 import os
 import socket
 import sys
@@ -20,7 +23,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, backend, queue):
+def _worker(rank, world, port, backend, row_block, queue):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -47,9 +50,10 @@ def _worker(rank, world, port, backend, queue):
             api = pyoracle.load()
             api.set_num_threads(2)
             mesh = api.CollisionMesh(V0, E, F)
-        out = sharded.ShardedContactStep(api, mesh, rank, world, dist=dist, device=device, native=backend == "nccl").step(
-            V0, V1, P["dhat"])
+        out = sharded.ShardedContactStep(api, mesh, rank, world, dist=dist, device=device, native=backend == "nccl",
+                                         row_block=row_block).step(V0, V1, P["dhat"])
         H = out["hessian_local"].toarray()
+        Hmine = H.copy()
         t = torch.from_numpy(H)
         if device is not None:
             t = t.to(device)
@@ -59,8 +63,18 @@ def _worker(rank, world, port, backend, queue):
         one = sharded.ShardedContactStep(api, mesh1, 0, 1, native=backend == "nccl").step(V0, V1, P["dhat"])
         H1 = one["hessian_local"].toarray()
         Hs = t.cpu().numpy()
+        tiles = None
+        if row_block:  # the rank's matrix is exactly the single-rank matrix restricted to its columns (== rows)
+            lo, hi = out["rows"]
+            mask = np.zeros(H1.shape[1], bool)
+            mask[3 * lo:3 * hi] = True
+            inside = H1[:, mask]
+            tiles = dict(rows=(lo, hi), outside_empty=not Hmine[:, ~mask].any(),
+                         pattern=bool(np.array_equal(Hmine[:, mask] != 0, inside != 0)),
+                         err=float(np.linalg.norm(Hmine[:, mask] - inside) / max(np.linalg.norm(inside), 1e-300)),
+                         same_set=out["collisions"] == one["collisions"])
         res = dict(
-            rank=rank, shard_collisions=out["collisions"], all_collisions=one["collisions"],
+            rank=rank, shard_collisions=out["shard_collisions"], all_collisions=one["collisions"], tiles=tiles,
             energy=abs(out["energy"] - one["energy"]) / abs(one["energy"]),
             grad=np.linalg.norm(out["gradient"] - one["gradient"]) / np.linalg.norm(one["gradient"]),
             step=(out["step"], one["step"]),
@@ -73,13 +87,13 @@ def _worker(rank, world, port, backend, queue):
         queue.put(dict(rank=rank, error=traceback.format_exc() + repr(e)))
 
 
-def _run(backend, world=2):
+def _run(backend, world=2, row_block=True):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, row_block, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=600) for _ in procs]
@@ -100,16 +114,112 @@ def _check(results):
         assert r["energy"] <= 1e-12 and r["grad"] <= 1e-12
         assert r["step"][0] == pytest.approx(r["step"][1], rel=1e-3, abs=1e-6)
         assert r["hess"] <= 1e-10 and r["pattern"]
+        if r["tiles"] is not None:
+            t = r["tiles"]
+            assert t["same_set"] and t["outside_empty"] and t["pattern"] and t["err"] <= 1e-10, t
+    if results[0]["tiles"] is not None:  # the row blocks partition the vertices
+        rows = [r["tiles"]["rows"] for r in results]
+        assert rows[0][0] == 0 and all(rows[k][1] == rows[k + 1][0] for k in range(len(rows) - 1))
+        assert all(hi > lo for lo, hi in rows)
 
 
-def test_two_rank_contact_step_gloo(oracle):  # the fixture builds the oracle before the ranks race for it
-    _check(_run("gloo"))
+@pytest.mark.parametrize("row_block", [True, False], ids=["row_block", "additive"])
+def test_two_rank_contact_step_gloo(oracle, row_block):  # the fixture builds the oracle before the ranks race for it
+    _check(_run("gloo", row_block=row_block))
 
 
 @pytest.mark.gpu
-def test_two_rank_contact_step_nccl(cuda):
+@pytest.mark.parametrize("row_block", [True, False], ids=["row_block", "additive"])
+def test_two_rank_contact_step_nccl(cuda, row_block):
     import torch
 
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
-    _check(_run("nccl"))
+    _check(_run("nccl", row_block=row_block))
+
+
+def _device_worker(rank, world, port, queue):
+    """the device-resident sharded step of bench.py (DeviceShardedStep) against the single-context step on the same GPU"""
+    try:
+        import ctypes as C
+
+        sys.path.insert(0, ROOT)
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        import scipy.sparse as sp
+        import torch
+        import torch.distributed as dist
+
+        import ipctk_b200
+
+        scenes, abi = ipctk_b200._pkg.scenes, ipctk_b200._pkg._abi
+        sharded = __import__("importlib").import_module("ipc_toolkit_b200.sharded")
+        torch.cuda.set_device(rank)
+        device = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+        api = ipctk_b200.library()
+        lib = api.lib
+        V0, V1, E, F, P = scenes.cloth_stack(4, 40)
+        nV = V0.shape[0]
+        dV0 = torch.from_numpy(np.asfortranarray(V0).T.copy()).cuda()
+        dV1 = torch.from_numpy(np.asfortranarray(V1).T.copy()).cuda()
+        bp, ccd = abi.BarrierParams(P["dhat"], 1.0, 0), abi.CcdParams(0, 0.0, 0, 0.0)
+
+        def run(r, w, d):
+            mesh = api.CollisionMesh(V0, E, F, device=rank)
+            stream = torch.cuda.ExternalStream(lib.ctx_stream(mesh._ctx), device=device)
+            st = sharded.DeviceShardedStep(api, mesh, r, w, d, torch, stream)
+            e, g, s = (torch.zeros(n, dtype=torch.float64, device="cuda") for n in (1, 3 * nV, 1))
+            for _ in range(2):  # twice: buffers are reused across steps
+                nnz = st.step(dV0, dV1, e, g, s, P["dhat"], bp, ccd)
+            torch.cuda.synchronize()
+            outer, inner, vals = np.zeros(3 * nV + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
+            lib.check(lib.barrier_hessian_fetch(mesh._ctx, outer.ctypes.data_as(C.c_void_p), inner.ctypes.data_as(C.c_void_p),
+                                                vals.ctypes.data_as(C.c_void_p)))
+            H = sp.csc_matrix((vals, inner, outer), shape=(3 * nV, 3 * nV))
+            return dict(e=float(e.item()), g=g.cpu().numpy(), s=float(s.item()), H=H, rows=st.rows, counts=list(st.counts),
+                        shard=list(st.shard_counts))
+
+        out = run(rank, world, dist)
+        one = run(0, 1, None)
+        lo, hi = 3 * out["rows"][0], 3 * out["rows"][1]
+        A, B = out["H"][:, lo:hi], one["H"][:, lo:hi]
+        res = dict(rank=rank, rows=out["rows"], same_set=out["counts"] == one["counts"], shard=out["shard"],
+                   energy=abs(out["e"] - one["e"]) / abs(one["e"]), grad=float(np.linalg.norm(out["g"] - one["g"]) / np.linalg.norm(one["g"])),
+                   step=(out["s"], one["s"]), outside=int(out["H"][:, :lo].nnz + out["H"][:, hi:].nnz),
+                   pattern=bool(np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)),
+                   hess=float(np.linalg.norm(A.data - B.data) / np.linalg.norm(B.data)) if A.nnz == B.nnz else 1.0, nnz=int(A.nnz),
+                   nnz_all=int(one["H"].nnz))
+        dist.destroy_process_group()
+        queue.put(res)
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        queue.put(dict(rank=rank, error=traceback.format_exc() + repr(e)))
+
+
+@pytest.mark.gpu
+def test_device_sharded_step_nccl(cuda):
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_device_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r["rank"])
+    for p in procs:
+        p.join(60)
+    for r in results:
+        assert "error" not in r, r.get("error")
+        assert r["same_set"] and r["outside"] == 0 and r["pattern"] and r["hess"] <= 1e-10, r
+        assert r["energy"] <= 1e-12 and r["grad"] <= 1e-12
+        assert r["step"][0] == pytest.approx(r["step"][1], rel=1e-3, abs=1e-6)
+        assert sum(r["shard"]) > 0
+    rows = [r["rows"] for r in results]
+    assert rows[0][0] == 0 and all(rows[k][1] == rows[k + 1][0] for k in range(world - 1))
+    assert sum(r["nnz"] for r in results) == results[0]["nnz_all"]  # the row blocks tile the matrix
