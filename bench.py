@@ -189,7 +189,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p")  # NCCL logs (its version banner) stay out of stdout: one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     api = ipctk_b200.library()
     lib = api.lib

@@ -52,7 +52,7 @@ def _worker(rank, world, port, backend, row_block, queue):
             mesh = api.CollisionMesh(V0, E, F)
         out = sharded.ShardedContactStep(api, mesh, rank, world, dist=dist, device=device, native=backend == "nccl",
                                          row_block=row_block).step(V0, V1, P["dhat"])
-        H = out["hessian_local"].toarray()
+        H = np.ascontiguousarray(out["hessian_local"].toarray())
         Hmine = H.copy()
         t = torch.from_numpy(H)
         if device is not None:
@@ -96,11 +96,29 @@ def _run(backend, world=2, row_block=True):
     procs = [ctx.Process(target=_worker, args=(r, world, port, backend, row_block, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=600) for _ in procs]
+    return _collect(q, procs)
+
+
+def _collect(q, procs, timeout=240):
+    """results of all ranks; a rank that failed (its peers then wait in a collective forever) fails the test at once"""
+    import queue as queue_mod
+
+    results, error = [], None
+    try:
+        for _ in procs:
+            r = q.get(timeout=timeout)
+            if "error" in r:
+                error = r["error"]
+                break
+            results.append(r)
+    except queue_mod.Empty:
+        error = "timeout waiting for the ranks"
     for p in procs:
-        p.join(60)
-    for r in results:
-        assert "error" not in r, r.get("error")
+        if error is None:
+            p.join(60)
+        if p.is_alive():
+            p.kill()
+    assert error is None, error
     return sorted(results, key=lambda r: r["rank"])
 
 
@@ -164,8 +182,11 @@ def _device_worker(rank, world, port, queue):
         dV1 = torch.from_numpy(np.asfortranarray(V1).T.copy()).cuda()
         bp, ccd = abi.BarrierParams(P["dhat"], 1.0, 0), abi.CcdParams(0, 0.0, 0, 0.0)
 
+        keep = []  # contexts (and their streams) must outlive every tensor used on them
+
         def run(r, w, d):
             mesh = api.CollisionMesh(V0, E, F, device=rank)
+            keep.append(mesh)
             stream = torch.cuda.ExternalStream(lib.ctx_stream(mesh._ctx), device=device)
             st = sharded.DeviceShardedStep(api, mesh, r, w, d, torch, stream)
             e, g, s = (torch.zeros(n, dtype=torch.float64, device="cuda") for n in (1, 3 * nV, 1))
@@ -189,12 +210,16 @@ def _device_worker(rank, world, port, queue):
                    pattern=bool(np.array_equal(A.indptr, B.indptr) and np.array_equal(A.indices, B.indices)),
                    hess=float(np.linalg.norm(A.data - B.data) / np.linalg.norm(B.data)) if A.nnz == B.nnz else 1.0, nnz=int(A.nnz),
                    nnz_all=int(one["H"].nnz))
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
         queue.put(res)
     except Exception as e:  # pragma: no cover
         import traceback
 
         queue.put(dict(rank=rank, error=traceback.format_exc() + repr(e)))
+    # like bench.py: the library's streams are wrapped as torch ExternalStreams; leave without running destructors
+    queue.close()
+    queue.join_thread()
+    os._exit(0)
 
 
 @pytest.mark.gpu
@@ -211,11 +236,8 @@ def test_device_sharded_step_nccl(cuda):
     procs = [ctx.Process(target=_device_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = sorted([q.get(timeout=600) for _ in procs], key=lambda r: r["rank"])
-    for p in procs:
-        p.join(60)
+    results = _collect(q, procs)
     for r in results:
-        assert "error" not in r, r.get("error")
         assert r["same_set"] and r["outside"] == 0 and r["pattern"] and r["hess"] <= 1e-10, r
         assert r["energy"] <= 1e-12 and r["grad"] <= 1e-12
         assert r["step"][0] == pytest.approx(r["step"][1], rel=1e-3, abs=1e-6)
