@@ -144,6 +144,8 @@ struct ipcb_ctx {
     ipcb::Buf<int4> hvid;                            // stencil vertex ids per collision (-1 padded)
     ipcb::Buf<unsigned short> hmask;                 // 16 x 9-bit non-zero masks per collision (slot = col point * 4 + row point)
     ipcb::Buf<double> hblk;                          // 16 x 9 doubles per collision
+    ipcb::Buf<unsigned char> hflag;                  // row block: does the collision touch an owned vertex
+    ipcb::Buf<int> hsel;                             // row block: per kind, the collisions that do (ascending)
     ipcb::Buf<int> hslow;                            // edge-edge collisions handed to the general kernel
     ipcb::Buf<int> hcolinc, hcolR, hitemoff;         // per column vertex: first incidence, #items, first item
     ipcb::Buf<unsigned> hsref;                       // per item, grouped by column then by row vertex: block slot

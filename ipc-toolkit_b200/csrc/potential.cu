@@ -28,6 +28,8 @@
 #include "hessian_fast.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
 #include <memory>
 
 namespace ipcb {
@@ -402,17 +404,18 @@ template <int NP> __device__ inline unsigned write_record(const HessOut& out, in
 template <int KIND>
 __global__ void __launch_bounds__(128)
     k_hessian_local(CollView c, MeshView m, BarrierDev B, int psd_mode, int64_t gi0, int64_t inc0, HessOut out, const int* __restrict__ list,
-                    int64_t nlist)
+                    int64_t nlist, const int* __restrict__ sel, int64_t nsel)
 {
     constexpr int NP = KIND == IPCB_VV ? 2 : (KIND == IPCB_EV ? 3 : 4);
     const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (tid >= (list ? nlist : c.n)) return;
-    const int64_t i = list ? list[tid] : tid;
+    if (tid >= (list ? nlist : nsel)) return;
+    const int64_t t = list ? list[tid] : tid; // record index within the kind
+    const int64_t i = sel ? sel[t] : t;       // collision index within the kind
     int vid[4];
     d3 x[4];
     load_stencil(KIND, c.ids[i], m, vid, x);
     // listed collisions already have their record; a collision without an owned vertex contributes nothing
-    if (!list && write_record<NP>(out, gi0 + i, inc0 + i * NP, vid) == 0) return;
+    if (!list && write_record<NP>(out, gi0 + t, inc0 + t * NP, vid) == 0) return;
     const double w = c.w[i];
     LocalDeriv D;
     zero_local(D);
@@ -484,7 +487,7 @@ __global__ void __launch_bounds__(128)
         }
     }
     // emit the NP x NP vertex blocks: slot (column point bj, row point bi)
-    const int64_t gi = gi0 + i;
+    const int64_t gi = gi0 + t;
     unsigned short masks[HSLOTS];
 #pragma unroll
     for (int k = 0; k < HSLOTS; k++) masks[k] = 0;
@@ -513,7 +516,7 @@ __global__ void __launch_bounds__(128)
 template <int KIND>
 __global__ void __launch_bounds__(128)
     k_hessian_fast(CollView c, MeshView m, BarrierDev B, int psd_mode, int64_t gi0, int64_t inc0, HessOut out, int* __restrict__ slow,
-                   unsigned long long* slow_count)
+                   unsigned long long* slow_count, const int* __restrict__ sel, int64_t nsel)
 {
     constexpr int NP = KIND == IPCB_VV ? 2 : (KIND == IPCB_EV ? 3 : 4);
     constexpr int P = KIND == IPCB_VV ? 0 : (KIND == IPCB_EV ? 1 : 2);
@@ -521,8 +524,10 @@ __global__ void __launch_bounds__(128)
     constexpr int ROW = NP * 9, PAD = ROW | 1;
     __shared__ double stage[4][32][PAD];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const bool valid = i < c.n;
+    // t = record index within the kind; i = collision index (sel: the collisions touching the rank's row block)
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool valid = t < nsel;
+    const int64_t i = valid && sel ? sel[t] : t;
     bool is_slow = false;
     unsigned own = 0; // stencil points whose vertex (column) this rank owns
     FastProj<P> pr;
@@ -530,7 +535,7 @@ __global__ void __launch_bounds__(128)
         int vid[4];
         d3 x[4];
         load_stencil(KIND, c.ids[i], m, vid, x);
-        own = write_record<NP>(out, gi0 + i, inc0 + i * NP, vid);
+        own = write_record<NP>(out, gi0 + t, inc0 + t * NP, vid);
         if (KIND == IPCB_EE) is_slow = own != 0 && (c.dt[i] != EE_AB || sqn(cross(x[1] - x[0], x[3] - x[2])) < c.eps[i]);
         if (!is_slow && own != 0) {
             FastGeom g;
@@ -547,10 +552,10 @@ __global__ void __launch_bounds__(128)
         unsigned long long basep = 0;
         if (lane == __ffs(smask) - 1) basep = atomicAdd(slow_count, (unsigned long long)__popc(smask));
         basep = __shfl_sync(0xffffffffu, basep, __ffs(smask) - 1);
-        if (is_slow) slow[basep + __popc(smask & ((1u << lane) - 1))] = int(i);
+        if (is_slow) slow[basep + __popc(smask & ((1u << lane) - 1))] = int(t);
     }
     if (emask_any == 0) return;
-    const int64_t gw = gi0 + (i - lane); // global index of lane 0's collision
+    const int64_t gw = gi0 + (t - lane); // record index of lane 0's collision
     unsigned mpack[HSLOTS / 2];
 #pragma unroll
     for (int k = 0; k < HSLOTS / 2; k++) mpack[k] = 0;
@@ -589,7 +594,7 @@ __global__ void __launch_bounds__(128)
         __syncwarp();
     }
     if (emit) {
-        uint4* mp = reinterpret_cast<uint4*>(out.mask + (gi0 + i) * HSLOTS);
+        uint4* mp = reinterpret_cast<uint4*>(out.mask + (gi0 + t) * HSLOTS);
         mp[0] = make_uint4(mpack[0], mpack[1], mpack[2], mpack[3]);
         mp[1] = make_uint4(mpack[4], mpack[5], mpack[6], mpack[7]);
     }
@@ -1028,6 +1033,38 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
     }
 }
 
+// ---- row block of a sharded Hessian: which collisions touch an owned vertex ---------------------------------------
+__device__ inline int stencil_ids_only(int kind, int2 id, const MeshView& m, int* vid)
+{
+    if (kind == IPCB_VV) {
+        vid[0] = id.x, vid[1] = id.y;
+        return 2;
+    }
+    if (kind == IPCB_EV) {
+        const int2 e = __ldg(m.E + id.x);
+        vid[0] = id.y, vid[1] = e.x, vid[2] = e.y;
+        return 3;
+    }
+    if (kind == IPCB_EE) {
+        const int2 ea = __ldg(m.E + id.x), eb = __ldg(m.E + id.y);
+        vid[0] = ea.x, vid[1] = ea.y, vid[2] = eb.x, vid[3] = eb.y;
+        return 4;
+    }
+    const int4 f = __ldg(m.F + id.x);
+    vid[0] = id.y, vid[1] = f.x, vid[2] = f.y, vid[3] = f.z;
+    return 4;
+}
+__global__ void k_touch_flags(CollView c, MeshView m, int v_lo, int v_hi, unsigned char* __restrict__ flag)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= c.n) return;
+    int vid[4];
+    const int n = stencil_ids_only(c.kind, c.ids[i], m, vid);
+    bool any = false;
+    for (int a = 0; a < n; a++) any |= vid[a] >= v_lo && vid[a] < v_hi;
+    flag[i] = any;
+}
+
 // ---- balanced row blocks of a sharded Hessian: per vertex, the number of 3x3 blocks its column receives ----------
 template <int KIND> __global__ void k_vertex_load(CollView c, MeshView m, int* __restrict__ load)
 {
@@ -1103,14 +1140,49 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     cudaStream_t s = ctx->stream;
     const BarrierDev B = make_barrier(bp, ctx->dmin);
     const int nV = ctx->nV;
-    const int64_t n0 = ctx->coll[0].count, n1 = ctx->coll[1].count, n2 = ctx->coll[2].count, n3 = ctx->coll[3].count;
+    const int v_lo = ctx->row_hi < 0 ? 0 : std::max(0, ctx->row_lo), v_hi = ctx->row_hi < 0 ? nV : std::min(nV, ctx->row_hi);
+    const MeshView m = mesh_view(ctx);
+    // n_k: records of kind k = all its collisions, or (row block of a sharded Hessian) the ones touching an owned vertex
+    int64_t nk[4] = { ctx->coll[0].count, ctx->coll[1].count, ctx->coll[2].count, ctx->coll[3].count };
+    const int* sel[4] = { nullptr, nullptr, nullptr, nullptr };
+    ctx->outer.reserve(3 * size_t(nV) + 1);
+    ctx->nnz = 0;
+    if ((v_lo > 0 || v_hi < nV) && nk[0] + nk[1] + nk[2] + nk[3] > 0) {
+        Stage st(ctx, "hess_select");
+        const int64_t all = nk[0] + nk[1] + nk[2] + nk[3];
+        ctx->hflag.reserve(all), ctx->hsel.reserve(all);
+        cudaStream_t where[4] = { ctx->aux[0], ctx->aux[1], s, ctx->aux[2] };
+        unsigned long long* d_cnt = ctx->dCounters.p + 24;
+        IPCB_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), s));
+        ctx->fork();
+        int64_t off = 0;
+        for (int k = 0; k < 4; k++) {
+            if (nk[k] == 0) continue;
+            unsigned char* flag = ctx->hflag.p + off;
+            int* list = ctx->hsel.p + off;
+            sel[k] = list;
+            off += nk[k];
+            k_touch_flags<<<grid_for(nk[k], 256), 256, 0, where[k]>>>(view(ctx, k), m, v_lo, v_hi, flag);
+            size_t bytes = 0;
+            cub::CountingInputIterator<int> iota(0);
+            int* d_num = reinterpret_cast<int*>(d_cnt + k);
+            cub::DeviceSelect::Flagged(nullptr, bytes, iota, flag, list, d_num, int(nk[k]), where[k]);
+            ctx->coll[k].cubtmp.reserve(bytes + 256);
+            cub::DeviceSelect::Flagged(ctx->coll[k].cubtmp.p, bytes, iota, flag, list, d_num, int(nk[k]), where[k]);
+            ctx->launches += 3;
+        }
+        for (int k = 0; k < ipcb_ctx::NAUX; k++) ctx->join(k);
+        IPCB_CUDA(cudaGetLastError());
+        IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[28], d_cnt, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        IPCB_CUDA(cudaStreamSynchronize(s));
+        for (int k = 0; k < 4; k++) nk[k] = nk[k] ? int64_t(ctx->pinned.p[28 + k] & 0xffffffffll) : 0;
+    }
+    const int64_t n0 = nk[0], n1 = nk[1], n2 = nk[2], n3 = nk[3];
     const int64_t ncoll = n0 + n1 + n2 + n3;
     const int64_t gi0[4] = { 0, n0, n0 + n1, n0 + n1 + n2 };
     const int64_t inc0[4] = { 0, 2 * n0, 2 * n0 + 3 * n1, 2 * n0 + 3 * n1 + 4 * n2 };
     const int64_t ninc = 2 * n0 + 3 * n1 + 4 * (n2 + n3);
     const int64_t nitems = 4 * n0 + 9 * n1 + 16 * (n2 + n3);
-    ctx->outer.reserve(3 * size_t(nV) + 1);
-    ctx->nnz = 0;
     if (ncoll == 0) { // empty ndof x ndof matrix (potential.cpp:107-109)
         k_zero_int<<<grid_for(3 * size_t(nV) + 1, 256), 256, 0, s>>>(3 * int64_t(nV) + 1, ctx->outer.p);
         ctx->launches++;
@@ -1122,32 +1194,30 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
         Stage st(ctx, "hessian_local");
         ctx->hvid.reserve(ncoll), ctx->hmask.reserve(size_t(ncoll) * HSLOTS), ctx->hblk.reserve(size_t(ncoll) * HSLOTS * 9);
         ctx->hkey.reserve(ninc), ctx->hkey_sorted.reserve(ninc);
-        const int v_lo = ctx->row_hi < 0 ? 0 : std::max(0, ctx->row_lo), v_hi = ctx->row_hi < 0 ? nV : std::min(nV, ctx->row_hi);
         const HessOut out { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p, ctx->hkey.p, v_lo, v_hi, nV };
-        const MeshView m = mesh_view(ctx);
         static const bool force_general = getenv("IPCB_HESSIAN_GENERAL") != nullptr; // A/B switch for tests and profiles
         if (psd_mode == IPCB_PSD_NONE || force_general) {
-            if (n0) k_hessian_local<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, nullptr, 0), ctx->launches++;
-            if (n1) k_hessian_local<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, nullptr, 0), ctx->launches++;
-            if (n2) k_hessian_local<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, nullptr, 0), ctx->launches++;
-            if (n3) k_hessian_local<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, nullptr, 0), ctx->launches++;
+            if (n0) k_hessian_local<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, nullptr, 0, sel[0], n0), ctx->launches++;
+            if (n1) k_hessian_local<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, nullptr, 0, sel[1], n1), ctx->launches++;
+            if (n2) k_hessian_local<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, nullptr, 0, sel[2], n2), ctx->launches++;
+            if (n3) k_hessian_local<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, nullptr, 0, sel[3], n3), ctx->launches++;
         } else {
             unsigned long long* slow_count = ctx->dCounters.p + 5;
             ctx->hslow.reserve(std::max<int64_t>(n2, 1));
             IPCB_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(unsigned long long), s));
             // the four kinds write disjoint records: the small ones run beside the edge-edge kernel
             ctx->fork();
-            if (n0) k_hessian_fast<IPCB_VV><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, ctx->hslow.p, slow_count), ctx->launches++;
-            if (n1) k_hessian_fast<IPCB_EV><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, ctx->hslow.p, slow_count), ctx->launches++;
-            if (n3) k_hessian_fast<IPCB_FV><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count), ctx->launches++;
+            if (n0) k_hessian_fast<IPCB_VV><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, ctx->hslow.p, slow_count, sel[0], n0), ctx->launches++;
+            if (n1) k_hessian_fast<IPCB_EV><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, ctx->hslow.p, slow_count, sel[1], n1), ctx->launches++;
+            if (n3) k_hessian_fast<IPCB_FV><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
             if (n2) {
-                k_hessian_fast<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, slow_count);
+                k_hessian_fast<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, slow_count, sel[2], n2);
                 ctx->launches++;
                 IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[11], slow_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
                 IPCB_CUDA(cudaStreamSynchronize(s));
                 const int64_t nslow = ctx->pinned.p[11];
                 if (nslow) {
-                    k_hessian_local<IPCB_EE><<<grid_for(nslow, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, nslow);
+                    k_hessian_local<IPCB_EE><<<grid_for(nslow, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, nslow, sel[2], n2);
                     ctx->launches++;
                 }
             }
