@@ -186,11 +186,16 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist = None
+    json_fd = None
     if world > 1:
         import torch.distributed as dist
 
         os.environ.setdefault("NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p")  # NCCL logs (its version banner) stay out of stdout: one JSON line
+        # NCCL prints its version banner on stdout: point fd 1 at stderr for the run and keep the real stdout for the
+        # ONE JSON line
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     api = ipctk_b200.library()
     lib = api.lib
@@ -424,7 +429,11 @@ def main():
                        "hessian_nnz_rank0": info.get("nnz"), "step": info.get("step"),
                        "energy": info.get("energy")},
         }
-        print(json.dumps(out))
+        line = json.dumps(out) + "\n"
+        if json_fd is None:
+            sys.stdout.write(line)
+        else:
+            os.write(json_fd, line.encode())
     if dist is not None:
         dist.destroy_process_group()
     # The library's stream (wrapped as a torch ExternalStream) dies with the mesh; pinned / device tensors that were

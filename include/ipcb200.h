@@ -65,6 +65,12 @@ enum { IPCB_BOXES_FLOAT = 0, IPCB_BOXES_DOUBLE = 1 };
 /* flags for collisions_build (collisions/normal/normal_collisions.hpp:191-194) */
 enum { IPCB_USE_AREA_WEIGHTING = 1 };
 
+/* flags for collisions_merge: the appended builders worked on DISJOINT candidate shards (the ranks of a sharded
+ * build), so their edge-edge and face-vertex records are unique across builders and only vertex-vertex /
+ * edge-vertex records need uniting.  The result is the same set; the product then skips the global sort of the
+ * EE / FV records until somebody asks for them in canonical order (collisions_fetch, collisions_dev_ptrs). */
+enum { IPCB_MERGE_DISJOINT_SHARDS = 1 };
+
 /* CCD parameters; defaults are the reference's (tight_inclusion_ccd.hpp:11-19,
  * additive_ccd.hpp:21-26).  A value <= 0 for tolerance / conservative_rescaling
  * or == 0 for max_iterations selects the default of `kind`. */
@@ -154,7 +160,7 @@ int IPCB_FN(collisions_min_distance)(ipcb_ctx* ctx, const double* V, int32_t ld,
 int IPCB_FN(collisions_clear)(ipcb_ctx* ctx);
 int IPCB_FN(collisions_append)(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_t* ids, const double* weight,
                                const double* eps_x, const uint8_t* dtype);
-int IPCB_FN(collisions_merge)(ipcb_ctx* ctx, double dmin, int64_t counts[4]);
+int IPCB_FN(collisions_merge)(ipcb_ctx* ctx, double dmin, int32_t flags, int64_t counts[4]);
 /* Sharding of the potential over ranks, for contexts that all hold the SAME collision set:
  *  - collision range: energy and gradient only visit the slice [rank*n/world, (rank+1)*n/world) of every
  *    kind's collisions (the results need a sum all-reduce);

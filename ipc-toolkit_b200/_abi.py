@@ -45,7 +45,7 @@ HOST_API = {
     "collisions_min_distance": (C.c_int, [P, P, c_i32, C.POINTER(c_f64)]),
     "collisions_clear": (C.c_int, [P]),
     "collisions_append": (C.c_int, [P, c_i32, c_i64, P, P, P, P]),
-    "collisions_merge": (C.c_int, [P, c_f64, C.POINTER(c_i64)]),
+    "collisions_merge": (C.c_int, [P, c_f64, c_i32, C.POINTER(c_i64)]),
     "ctx_set_collision_range": (C.c_int, [P, c_i32, c_i32]),
     "ctx_set_row_block": (C.c_int, [P, c_i32, c_i32]),
     "hessian_balanced_row_blocks": (C.c_int, [P, c_i32, P]),

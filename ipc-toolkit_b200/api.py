@@ -331,11 +331,12 @@ def make_api(lib):
                 mesh._cand_gen += 1  # the resident candidates were rebuilt too
             self._bind(mesh, counts, dmin)
 
-        def assign(self, mesh, builders, dmin=0.0):
+        def assign(self, mesh, builders, dmin=0.0, disjoint_shards=False):
             """Fill the set from the records of several builders and merge them like
             NormalCollisionsBuilder::merge (builder.cpp:547-689: equal collisions united, weights added,
             weight == 0 dropped).  `builders`: iterable of 4-tuples (vv, ev, ee, fv) of record namespaces as the
-            *_collisions properties return them (ids, weight, eps_x, dtype) — e.g. the sets of the other ranks."""
+            *_collisions properties return them (ids, weight, eps_x, dtype) — e.g. the sets of the other ranks.
+            disjoint_shards=True promises that the builders worked on disjoint candidate shards (IPCB_MERGE_DISJOINT_SHARDS)."""
             lib.check(lib.collisions_clear(mesh._ctx))
             for kinds in builders:
                 for kind, rec in enumerate(kinds):
@@ -349,7 +350,7 @@ def make_api(lib):
                                                     w.ctypes.data_as(C.c_void_p), eps.ctypes.data_as(C.c_void_p),
                                                     dt.ctypes.data_as(C.c_void_p)))
             counts = (C.c_int64 * 4)()
-            lib.check(lib.collisions_merge(mesh._ctx, dmin, counts))
+            lib.check(lib.collisions_merge(mesh._ctx, dmin, 1 if disjoint_shards else 0, counts))
             self._bind(mesh, counts, dmin)
 
         def _bind(self, mesh, counts, dmin):

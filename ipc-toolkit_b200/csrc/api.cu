@@ -454,6 +454,7 @@ int ipcb_collisions_fetch(ipcb_ctx* ctx, int32_t kind, int32_t* ids, double* wei
         begin_call(ctx);
         if (kind < 0 || kind > 3) throw Error("bad collision kind");
         require_collisions(ctx);
+        collisions_sort(ctx, kind);
         const CollisionSet& cs = ctx->coll[kind];
         const size_t n = size_t(cs.count);
         if (n == 0) return;
@@ -519,11 +520,11 @@ int ipcb_collisions_append(ipcb_ctx* ctx, int32_t kind, int64_t count, const int
         IPCB_CUDA(cudaStreamSynchronize(s));
     });
 }
-int ipcb_collisions_merge(ipcb_ctx* ctx, double dmin, int64_t counts[4])
+int ipcb_collisions_merge(ipcb_ctx* ctx, double dmin, int32_t flags, int64_t counts[4])
 {
     return guarded([&] {
         begin_call(ctx);
-        collisions_merge(ctx, dmin);
+        collisions_merge(ctx, dmin, flags);
         coll_counts(ctx, counts);
     });
 }
@@ -533,6 +534,8 @@ int ipcb_collisions_dev_ptrs(ipcb_ctx* ctx, int32_t kind, int64_t* count, const 
     return guarded([&] {
         if (kind < 0 || kind > 3) throw Error("bad collision kind");
         require_collisions(ctx);
+        begin_call(ctx);
+        collisions_sort(ctx, kind);
         const CollisionSet& cs = ctx->coll[kind];
         *count = cs.count;
         *d_ids = reinterpret_cast<const int32_t*>(cs.ids.p);
@@ -589,11 +592,7 @@ int ipcb_collisions_append_packed_dev(ipcb_ctx* ctx, const void* d_buffer, const
         begin_call(ctx);
         for (int k = 0; k < 4; k++) check_collision_kind(k, counts[k]);
         const PackedLayout L = packed_layout(counts);
-        const char* in = static_cast<const char*>(d_buffer);
-        for (int k = 0; k < 4; k++)
-            collisions_append_dev(ctx, k, counts[k], reinterpret_cast<const int32_t*>(in + L.ids[k]),
-                                  reinterpret_cast<const double*>(in + L.w[k]), reinterpret_cast<const double*>(in + L.eps),
-                                  reinterpret_cast<const uint8_t*>(in + L.dt));
+        collisions_append_packed_dev(ctx, d_buffer, counts, L.ids, L.w, L.eps, L.dt);
     });
 }
 int ipcb_collisions_min_distance(ipcb_ctx* ctx, const double* V, int32_t ld, double* out)

@@ -45,6 +45,14 @@ struct ClassifyArgs {
 __device__ inline d3 ld3(const double4* X, int i) { return load_vertex(X, i); }
 __device__ inline unsigned long long mkkey(int a, int b) { return ((unsigned long long)(unsigned)a << 32) | (unsigned)b; }
 
+__global__ void k_ids_to_keys(int64_t n, const int2* __restrict__ ids, int unordered, unsigned long long* __restrict__ key)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = ids[i];
+    key[i] = unordered ? mkkey(min(c.x, c.y), max(c.x, c.y)) : mkkey(c.x, c.y);
+}
+
 // warp-aggregated append of one record per participating lane
 __device__ inline void append(const StreamOut& o, bool pred, unsigned long long key, double w, double eps, unsigned char dt)
 {
@@ -230,7 +238,7 @@ static void merge_stream_enqueue(ipcb_ctx* ctx, int kind, int64_t n, cudaStream_
     IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[21 + 2 * kind], cs.head.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
 }
 
-static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4]);
+static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4], bool disjoint = false);
 
 void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
 {
@@ -282,33 +290,135 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
     merge_streams(ctx, raw);
 }
 
-static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4])
+// records -> final arrays without sorting or merging (every record is kept)
+__global__ void k_keep_all(int64_t n, const unsigned long long* __restrict__ key, const double* __restrict__ w_raw,
+                           const double* __restrict__ eps_raw, const unsigned char* __restrict__ dt_raw, int2* __restrict__ ids,
+                           double* __restrict__ w, double* __restrict__ eps, unsigned char* __restrict__ dt)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = key[i];
+    ids[i] = make_int2(int(k >> 32), int(k & 0xffffffffu));
+    w[i] = w_raw[i];
+    if (eps_raw) eps[i] = eps_raw[i], dt[i] = dt_raw[i];
+}
+
+// disjoint: the builders come from disjoint candidate shards, so edge-edge and face-vertex records are unique across
+// builders and only VV / EV records need uniting: EE / FV are concatenated in builder order (each builder's records
+// are sorted; the canonical global order is restored on demand by collisions_sort)
+static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4], bool disjoint)
 {
     cudaStream_t s = ctx->stream;
     Stage st(ctx, "merge_collisions");
     // the four streams are merged concurrently (their sorts are small and latency-bound): EE on the main stream
     cudaStream_t where[4] = { ctx->aux[0], ctx->aux[1], s, ctx->aux[2] };
     ctx->fork();
-    for (int k = 0; k < 4; k++) merge_stream_enqueue(ctx, k, raw[k], where[k]);
     for (int k = 0; k < 4; k++) {
-        if (raw[k] == 0) continue;
+        CollisionSet& cs = ctx->coll[k];
+        cs.sorted = true;
+        if (disjoint && (k == IPCB_EE || k == IPCB_FV)) {
+            const int64_t n = raw[k];
+            cs.count = n;
+            cs.sorted = false;
+            if (n == 0) continue;
+            cs.ids.reserve(n), cs.w.reserve(n);
+            if (k == IPCB_EE) cs.eps.reserve(n), cs.dtype.reserve(n);
+            k_keep_all<<<grid_for(n, 256), 256, 0, where[k]>>>(n, cs.key_raw.p, cs.w_raw.p, k == IPCB_EE ? cs.eps_raw.p : nullptr, cs.dt_raw.p,
+                                                             cs.ids.p, cs.w.p, cs.eps.p, cs.dtype.p);
+            ctx->launches++;
+        } else {
+            merge_stream_enqueue(ctx, k, raw[k], where[k]);
+        }
+    }
+    for (int k = 0; k < 4; k++) {
+        if (raw[k] == 0 || !ctx->coll[k].sorted) continue;
         IPCB_CUDA(cudaStreamSynchronize(where[k]));
         ctx->coll[k].count = int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[20 + 2 * k])) + int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[21 + 2 * k]));
     }
     for (int k = 0; k < ipcb_ctx::NAUX; k++) ctx->join(k);
+    IPCB_CUDA(cudaGetLastError());
+}
+
+// canonical order (sorted ids) of a kind that was concatenated by a disjoint merge: its own records go through the
+// regular sort + run merge once (nothing is united: edge-edge / face-vertex records of disjoint shards are unique)
+void collisions_sort(ipcb_ctx* ctx, int kind)
+{
+    CollisionSet& cs = ctx->coll[kind];
+    if (cs.sorted || cs.count == 0) {
+        cs.sorted = true;
+        return;
+    }
+    cudaStream_t s = ctx->stream;
+    const int64_t n = cs.count;
+    cs.key_raw.reserve(n), cs.w_raw.reserve(n);
+    if (kind == IPCB_EE) cs.eps_raw.reserve(n), cs.dt_raw.reserve(n);
+    k_ids_to_keys<<<grid_for(n, 256), 256, 0, s>>>(n, cs.ids.p, kind == IPCB_VV || kind == IPCB_EE, cs.key_raw.p);
+    IPCB_CUDA(cudaMemcpyAsync(cs.w_raw.p, cs.w.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+    if (kind == IPCB_EE) {
+        IPCB_CUDA(cudaMemcpyAsync(cs.eps_raw.p, cs.eps.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        IPCB_CUDA(cudaMemcpyAsync(cs.dt_raw.p, cs.dtype.p, n, cudaMemcpyDeviceToDevice, s));
+    }
+    ctx->launches++;
+    merge_stream_enqueue(ctx, kind, n, s);
+    IPCB_CUDA(cudaStreamSynchronize(s));
+    cs.count = int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[20 + 2 * kind])) + int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[21 + 2 * kind]));
+    cs.sorted = true;
 }
 
 // ---- public containers + NormalCollisionsBuilder::merge (normal_collisions.hpp:177-189, builder.cpp:547-689) -------
 // collisions_clear / collisions_append / collisions_merge: records of several builders (the ranks of a sharded
 // build) are appended to the raw streams as (key, weight[, eps, dtype]) and merged by the same sort + run-merge
 // that finishes collisions_build.
-__global__ void k_ids_to_keys(int64_t n, const int2* __restrict__ ids, int unordered, unsigned long long* __restrict__ key)
+// one launch appends all four kinds of a packed buffer (include/ipcb200.h: collisions_pack_dev layout)
+struct UnpackArgs {
+    const char* in;
+    int64_t n[4], first[4]; // records per kind, first thread of the kind
+    int64_t ids[4], w[4], eps, dt; // byte offsets inside the buffer
+    unsigned long long* key[4];
+    double* wout[4];
+    double* eps_out;
+    unsigned char* dt_out;
+};
+__global__ void k_unpack(UnpackArgs a, int64_t total)
 {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int2 c = ids[i];
-    key[i] = unordered ? mkkey(min(c.x, c.y), max(c.x, c.y)) : mkkey(c.x, c.y);
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int k = t >= a.first[3] ? 3 : (t >= a.first[2] ? 2 : (t >= a.first[1] ? 1 : 0));
+    const int64_t i = t - a.first[k];
+    const int2 c = reinterpret_cast<const int2*>(a.in + a.ids[k])[i];
+    a.key[k][i] = (k == IPCB_VV || k == IPCB_EE) ? mkkey(min(c.x, c.y), max(c.x, c.y)) : mkkey(c.x, c.y);
+    a.wout[k][i] = reinterpret_cast<const double*>(a.in + a.w[k])[i];
+    if (k == IPCB_EE) {
+        a.eps_out[i] = reinterpret_cast<const double*>(a.in + a.eps)[i];
+        a.dt_out[i] = reinterpret_cast<const unsigned char*>(a.in + a.dt)[i];
+    }
 }
+void collisions_append_packed_dev(ipcb_ctx* ctx, const void* d_buffer, const int64_t n[4], const int64_t ids_off[4], const int64_t w_off[4],
+                                  int64_t eps_off, int64_t dt_off)
+{
+    cudaStream_t s = ctx->stream;
+    UnpackArgs a;
+    a.in = static_cast<const char*>(d_buffer);
+    int64_t total = 0;
+    for (int k = 0; k < 4; k++) {
+        CollisionSet& cs = ctx->coll[k];
+        const size_t have = size_t(cs.raw_count), want = have + size_t(n[k]);
+        if (want > 0x7fffffffull) throw Error("more than 2^31 collision records of one kind");
+        cs.key_raw.reserve_keep(want, have, s), cs.w_raw.reserve_keep(want, have, s);
+        if (k == IPCB_EE) cs.eps_raw.reserve_keep(want, have, s), cs.dt_raw.reserve_keep(want, have, s);
+        a.n[k] = n[k], a.first[k] = total, a.ids[k] = ids_off[k], a.w[k] = w_off[k];
+        a.key[k] = cs.key_raw.p + have, a.wout[k] = cs.w_raw.p + have;
+        if (k == IPCB_EE) a.eps_out = cs.eps_raw.p + have, a.dt_out = cs.dt_raw.p + have;
+        total += n[k];
+        cs.raw_count = int64_t(want);
+    }
+    a.eps = eps_off, a.dt = dt_off;
+    if (total == 0) return;
+    k_unpack<<<grid_for(total, 256), 256, 0, s>>>(a, total);
+    ctx->launches++;
+    IPCB_CUDA(cudaGetLastError());
+}
+
 void collisions_clear(ipcb_ctx* ctx)
 {
     for (auto& c : ctx->coll) c.count = 0, c.raw_count = 0;
@@ -335,13 +445,13 @@ void collisions_append_dev(ipcb_ctx* ctx, int kind, int64_t n, const int32_t* d_
     IPCB_CUDA(cudaGetLastError());
     cs.raw_count = int64_t(want);
 }
-void collisions_merge(ipcb_ctx* ctx, double dmin)
+void collisions_merge(ipcb_ctx* ctx, double dmin, int flags)
 {
     ctx->dmin = dmin;
     ctx->coll_valid = true;
     const int64_t raw[4] = { ctx->coll[0].raw_count, ctx->coll[1].raw_count, ctx->coll[2].raw_count, ctx->coll[3].raw_count };
     for (auto& c : ctx->coll) c.count = 0, c.raw_count = 0;
-    merge_streams(ctx, raw);
+    merge_streams(ctx, raw, (flags & IPCB_MERGE_DISJOINT_SHARDS) != 0);
 }
 
 // ---- compute_minimum_distance (normal_collisions.cpp:209-233) ----------------------

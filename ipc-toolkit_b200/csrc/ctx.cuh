@@ -70,6 +70,7 @@ struct CollisionSet {
     Buf<double> wsum;
     Buf<char> cubtmp; // per stream: the four merges run concurrently
     int64_t count = 0;
+    bool sorted = true;    // false after a disjoint merge concatenated the builders' records (collisions_sort restores it)
     int64_t raw_count = 0; // records appended through collisions_append since the last collisions_clear
 };
 
@@ -215,7 +216,10 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags);
 void collisions_clear(ipcb_ctx* ctx);
 void collisions_append_dev(ipcb_ctx* ctx, int kind, int64_t n, const int32_t* d_ids, const double* d_w, const double* d_eps,
                            const uint8_t* d_dt);
-void collisions_merge(ipcb_ctx* ctx, double dmin);
+void collisions_append_packed_dev(ipcb_ctx* ctx, const void* d_buffer, const int64_t n[4], const int64_t ids_off[4], const int64_t w_off[4],
+                                  int64_t eps_off, int64_t dt_off);
+void collisions_merge(ipcb_ctx* ctx, double dmin, int flags);
+void collisions_sort(ipcb_ctx* ctx, int kind);
 double collisions_min_distance(ipcb_ctx* ctx);
 
 // potential (potential.cu)

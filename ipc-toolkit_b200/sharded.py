@@ -66,7 +66,7 @@ class ShardedContactStep:
 
         builders = [[types.SimpleNamespace(ids=k[0], weight=k[1], eps_x=k[2], dtype=k[3]) for k in p] for p in parts]
         full = self.api.NormalCollisions()
-        full.assign(self.mesh, builders, dmin)
+        full.assign(self.mesh, builders, dmin, disjoint_shards=True)
         return full
 
     def step(self, V0, V1, dhat, stiffness=1.0, psd=None, dmin=0.0, min_distance=0.0, ccd=None):
@@ -131,41 +131,49 @@ class DeviceShardedStep:
         self.rows = (0, mesh.num_vertices())
         self.shard_counts = [0, 0, 0, 0]
         self.after = None  # optional callback after every library call (bench.py collects stage times)
+        if self.row_block:
+            self.side = torch.cuda.Stream()
+            self.ev_packed, self.ev_gathered = torch.cuda.Event(), torch.cuda.Event()
 
     def _done(self):
         if self.after is not None:
             self.after()
 
-    def exchange_collisions(self, dmin):
+    def start_exchange(self):
+        """counts of every rank (the only host round trip), pack, and ONE all-gather of the packed records on a side
+        stream: it overlaps with whatever the caller enqueues next on the context's stream (the CCD stage)"""
         torch, lib, dist = self.torch, self.lib, self.dist
         self.shard_counts = list(self.counts)
-        # 1. counts of every rank (the only host round trip of the exchange)
         self.h_counts.copy_(torch.tensor(self.shard_counts, dtype=torch.int64))
         with torch.cuda.stream(self.stream):
             self.d_counts.copy_(self.h_counts, non_blocking=True)
             dist.all_gather_into_tensor(self.d_counts_all, self.d_counts)
-            all_counts = self.d_counts_all.cpu().view(self.world, 4).tolist()
-        need = max(packed_bytes(c) for c in all_counts)
+            self.all_counts = self.d_counts_all.cpu().view(self.world, 4).tolist()
+        need = max(packed_bytes(c) for c in self.all_counts)
         if need > self.cap:
             self.cap = int(need * 1.25) + 1024
             self.cap -= self.cap % 16
             self.send = torch.empty(self.cap, dtype=torch.uint8, device="cuda")
             self.recv = torch.empty(self.cap * self.world, dtype=torch.uint8, device="cuda")
-        # 2. one all-gather of the packed records (only the used prefix of every slot travels)
-        used = (need + 15) // 16 * 16
+        self.used = (need + 15) // 16 * 16  # only the used prefix of every slot travels
         nbytes = C.c_int64()
         lib.check(lib.collisions_pack_dev(self.ctx, C.c_void_p(self.send.data_ptr()), self.cap, C.byref(nbytes)))
-        recv = self.recv[:used * self.world]
-        with torch.cuda.stream(self.stream):
-            dist.all_gather_into_tensor(recv, self.send[:used])
-        # 3. NormalCollisionsBuilder::merge over the ranks' records
+        self.ev_packed.record(self.stream)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_packed)
+            dist.all_gather_into_tensor(self.recv[:self.used * self.world], self.send[:self.used])
+            self.ev_gathered.record(self.side)
+
+    def finish_exchange(self, dmin):
+        """NormalCollisionsBuilder::merge over the ranks' records, then the balanced row blocks"""
+        lib = self.lib
+        self.stream.wait_event(self.ev_gathered)
         lib.check(lib.collisions_clear(self.ctx))
         for r in range(self.world):
-            c = (C.c_int64 * 4)(*all_counts[r])
-            lib.check(lib.collisions_append_packed_dev(self.ctx, C.c_void_p(recv.data_ptr() + r * used), c))
-        lib.check(lib.collisions_merge(self.ctx, dmin, self.counts))
+            c = (C.c_int64 * 4)(*self.all_counts[r])
+            lib.check(lib.collisions_append_packed_dev(self.ctx, C.c_void_p(self.recv.data_ptr() + r * self.used), c))
+        lib.check(lib.collisions_merge(self.ctx, dmin, 1, self.counts))  # 1 = IPCB_MERGE_DISJOINT_SHARDS
         self._done()
-        # 4. balanced row blocks for the Hessian, collision ranges for energy / gradient
         bounds = self.mesh.balanced_row_blocks(self.world)
         self.rows = (int(bounds[self.rank]), int(bounds[self.rank + 1]))
 
@@ -176,18 +184,21 @@ class DeviceShardedStep:
         lib.check(lib.collisions_build_dev(ctx, p0, nV, dhat, dmin, 0, self.counts))
         self._done()
         if self.row_block:
-            self.exchange_collisions(dmin)
-            lib.check(lib.ctx_set_collision_range(ctx, self.rank, self.world))
-            lib.check(lib.ctx_set_row_block(ctx, *self.rows))
+            self.start_exchange()
         else:
             self.shard_counts = list(self.counts)
+        # the step size does not depend on the collision set: it runs while the records travel
+        lib.check(lib.ccd_stepsize_dev(ctx, p0, p1, nV, min_distance, C.byref(ccd), C.c_void_p(d_step.data_ptr())))
+        self._done()
+        if self.row_block:
+            self.finish_exchange(dmin)
+            lib.check(lib.ctx_set_collision_range(ctx, self.rank, self.world))
+            lib.check(lib.ctx_set_row_block(ctx, *self.rows))
         lib.check(lib.barrier_energy_dev(ctx, p0, nV, C.byref(bp), C.c_void_p(d_energy.data_ptr())))
         self._done()
         lib.check(lib.barrier_gradient_dev(ctx, p0, nV, C.byref(bp), C.c_void_p(d_grad.data_ptr())))
         self._done()
         lib.check(lib.barrier_hessian_dev(ctx, p0, nV, C.byref(bp), psd, C.byref(self.nnz)))
-        self._done()
-        lib.check(lib.ccd_stepsize_dev(ctx, p0, p1, nV, min_distance, C.byref(ccd), C.c_void_p(d_step.data_ptr())))
         self._done()
         if self.world > 1:  # sum / sum / min all-reduces over NVLink; the Hessian needs no collective
             with torch.cuda.stream(self.stream):

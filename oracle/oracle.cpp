@@ -987,7 +987,7 @@ int ipco_collisions_append(ipcb_ctx* ctx, int32_t kind, int64_t count, const int
     }
     return 0;
 }
-int ipco_collisions_merge(ipcb_ctx* ctx, double dmin, int64_t counts[4])
+int ipco_collisions_merge(ipcb_ctx* ctx, double dmin, int32_t /* flags: a hint, the set is the same */, int64_t counts[4])
 {
     for (int k = 0; k < 4; k++) {
         merge_collisions(ctx, k, ctx->appended[k]);

@@ -309,7 +309,16 @@ def test_collision_merge_and_sharded_potential(cuda, oracle, scenes, name):
             if kind != 3:
                 expect[n // 3:(2 * n) // 3] *= 2  # the overlap was contributed by both builders
             assert np.array_equal(a.weight, expect)
-        # back to unit weights, then the sharded potential
+        # disjoint shards (IPCB_MERGE_DISJOINT_SHARDS): EE / FV records are concatenated, VV / EV united; the canonical
+        # order comes back when the records are fetched
+        halves = [[part(rec, slice(b, None, 2), kind) for kind, rec in enumerate(full)] for b in (1, 0)]
+        m.assign(mesh, halves, 0.0, disjoint_shards=True)
+        e_concat = B(m, mesh, X)
+        assert abs(e_concat - ref["e"]) <= 1e-12 * abs(ref["e"])
+        for a, b in zip([getattr(m, k + "_collisions") for k in ("vv", "ev", "ee", "fv")], full):
+            assert np.array_equal(a.ids, b.ids) and np.array_equal(a.dtype, b.dtype) and np.array_equal(a.eps_x, b.eps_x)
+            assert np.array_equal(a.weight, b.weight)
+        # back to one builder, then the sharded potential
         m.assign(mesh, [full], 0.0)
         bounds = mesh.balanced_row_blocks(world)
         e, g, tiles = 0.0, 0.0, []
