@@ -247,6 +247,22 @@ public:
         check(ipcb_collisions_min_distance(mesh.ctx(), vertices.data, vertices.ld, &d));
         return d;
     }
+    /// Fill the set from the records of several builders and merge them like NormalCollisionsBuilder::merge
+    /// (normal_collisions_builder.cpp:547-689): equal collisions united, weights added, weight == 0 dropped.
+    /// `builders[b][kind]`; disjoint_shards promises builders over disjoint candidate shards (ranks of a sharded build).
+    void assign(const CollisionMesh& mesh, const std::vector<std::array<Records, 4>>& builders, double dmin = 0, bool disjoint_shards = false)
+    {
+        check(ipcb_collisions_clear(mesh.ctx()));
+        for (const auto& b : builders)
+            for (int kind = 0; kind < 4; kind++) {
+                const Records& r = b[kind];
+                if (r.ids.empty()) continue;
+                check(ipcb_collisions_append(mesh.ctx(), kind, int64_t(r.ids.size()), r.ids[0].data(), r.weight.data(),
+                                             kind == IPCB_EE ? r.eps_x.data() : nullptr, kind == IPCB_EE ? r.dtype.data() : nullptr));
+            }
+        check(ipcb_collisions_merge(mesh.ctx(), dmin, disjoint_shards ? IPCB_MERGE_DISJOINT_SHARDS : 0, m_counts));
+        m_mesh = &mesh;
+    }
 
 private:
     const CollisionMesh* m_mesh = nullptr;

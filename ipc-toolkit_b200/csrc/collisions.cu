@@ -71,7 +71,9 @@ __device__ inline void append(const StreamOut& o, bool pred, unsigned long long 
     }
 }
 
-template <int KIND> __global__ void __launch_bounds__(256) k_classify(ClassifyArgs a)
+// MINB: resident blocks per SM the register allocation aims for (4 = 64 registers, 50 % occupancy: the kernel waits on
+// vertex gathers, more warps hide more latency; a handful of spilled bytes for EE / FV)
+template <int KIND, int MINB> __global__ void __launch_bounds__(256, MINB) k_classify(ClassifyArgs a)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     // 0 = nothing, 1 = VV, 2 = EV, 3 = own kind (EE / FV)
@@ -275,10 +277,13 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
             a.n = ctx->cand[k].count;
             if (a.n == 0) continue;
             const unsigned grid = grid_for(a.n, 256);
-            if (k == IPCB_VV) k_classify<IPCB_VV><<<grid, 256, 0, s>>>(a);
-            if (k == IPCB_EV) k_classify<IPCB_EV><<<grid, 256, 0, s>>>(a);
-            if (k == IPCB_EE) k_classify<IPCB_EE><<<grid, 256, 0, s>>>(a);
-            if (k == IPCB_FV) k_classify<IPCB_FV><<<grid, 256, 0, ctx->aux[0]>>>(a);
+            static const bool sparse = getenv("IPCB_CLASSIFY_SPARSE") != nullptr; // A/B switch: 3 resident blocks, no spill
+            if (k == IPCB_VV) k_classify<IPCB_VV, 4><<<grid, 256, 0, s>>>(a);
+            if (k == IPCB_EV) k_classify<IPCB_EV, 4><<<grid, 256, 0, s>>>(a);
+            if (k == IPCB_EE && sparse) k_classify<IPCB_EE, 3><<<grid, 256, 0, s>>>(a);
+            else if (k == IPCB_EE) k_classify<IPCB_EE, 4><<<grid, 256, 0, s>>>(a);
+            if (k == IPCB_FV && sparse) k_classify<IPCB_FV, 3><<<grid, 256, 0, ctx->aux[0]>>>(a);
+            else if (k == IPCB_FV) k_classify<IPCB_FV, 4><<<grid, 256, 0, ctx->aux[0]>>>(a);
             ctx->launches++;
         }
         ctx->join(0);

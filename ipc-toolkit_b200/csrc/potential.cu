@@ -513,8 +513,8 @@ __global__ void __launch_bounds__(128)
 // registers would make every 8-byte store of a warp hit 32 different sectors; instead each block
 // row (NP blocks = NP*72 contiguous bytes per collision) is staged in shared memory (odd stride:
 // conflict-free) and written out by the whole warp with consecutive lanes on consecutive addresses.
-template <int KIND>
-__global__ void __launch_bounds__(128)
+template <int KIND, int MINB>
+__global__ void __launch_bounds__(128, MINB)
     k_hessian_fast(CollView c, MeshView m, BarrierDev B, int psd_mode, int64_t gi0, int64_t inc0, HessOut out, int* __restrict__ slow,
                    unsigned long long* slow_count, const int* __restrict__ sel, int64_t nsel)
 {
@@ -1207,11 +1207,14 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
             IPCB_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(unsigned long long), s));
             // the four kinds write disjoint records: the small ones run beside the edge-edge kernel
             ctx->fork();
-            if (n0) k_hessian_fast<IPCB_VV><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, ctx->hslow.p, slow_count, sel[0], n0), ctx->launches++;
-            if (n1) k_hessian_fast<IPCB_EV><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, ctx->hslow.p, slow_count, sel[1], n1), ctx->launches++;
-            if (n3) k_hessian_fast<IPCB_FV><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
+            static const bool dense = getenv("IPCB_HFAST_SPARSE") == nullptr; // 4 resident blocks per SM (small spill) for the 4-point kinds; A/B switch
+            if (n0) k_hessian_fast<IPCB_VV, 1><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, ctx->hslow.p, slow_count, sel[0], n0), ctx->launches++;
+            if (n1) k_hessian_fast<IPCB_EV, 1><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, ctx->hslow.p, slow_count, sel[1], n1), ctx->launches++;
+            if (n3 && dense) k_hessian_fast<IPCB_FV, 4><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
+            else if (n3) k_hessian_fast<IPCB_FV, 3><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
             if (n2) {
-                k_hessian_fast<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, slow_count, sel[2], n2);
+                if (dense) k_hessian_fast<IPCB_EE, 4><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, slow_count, sel[2], n2);
+                else k_hessian_fast<IPCB_EE, 3><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, slow_count, sel[2], n2);
                 ctx->launches++;
                 IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[11], slow_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
                 IPCB_CUDA(cudaStreamSynchronize(s));
