@@ -1208,8 +1208,8 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
             // the four kinds write disjoint records: the small ones run beside the edge-edge kernel
             ctx->fork();
             static const bool dense = getenv("IPCB_HFAST_SPARSE") == nullptr; // 4 resident blocks per SM (small spill) for the 4-point kinds; A/B switch
-            if (n0) k_hessian_fast<IPCB_VV, 1><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, ctx->hslow.p, slow_count, sel[0], n0), ctx->launches++;
-            if (n1) k_hessian_fast<IPCB_EV, 1><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, ctx->hslow.p, slow_count, sel[1], n1), ctx->launches++;
+            if (n0) k_hessian_fast<IPCB_VV, 4><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, ctx->hslow.p, slow_count, sel[0], n0), ctx->launches++;
+            if (n1) k_hessian_fast<IPCB_EV, 4><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, ctx->hslow.p, slow_count, sel[1], n1), ctx->launches++;
             if (n3 && dense) k_hessian_fast<IPCB_FV, 4><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
             else if (n3) k_hessian_fast<IPCB_FV, 3><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
             if (n2) {
