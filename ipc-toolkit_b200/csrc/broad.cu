@@ -285,6 +285,159 @@ __global__ void k_refit(int n, const FBox* __restrict__ sbox, Node* nodes, const
     }
 }
 
+// ---------------------------------------------------------------------------
+// Node boxes WITHOUT a bottom-up pass.  A Karras node knows the range of sorted leaves below each child, so a child
+// box is a range union over the sorted leaf boxes: a three-level range-min/max structure answers it with a handful
+// of independent loads, and every node is finished by the thread that built it (no parent links, no arrival
+// counters, no dependent chain of tree depth).  Unions are min / max, hence exactly the boxes the bottom-up refit
+// (lbvh.cpp:262-330) produces.
+//   level A: blocks of 32 leaves        — per leaf the union from its block's start (preA) and to its block's end (sufA)
+//   level B: super-blocks of 32 blocks  — the same over the block totals (preB / sufB per block)
+//   level C: sparse table over the super-block totals (built by one CTA)
+struct Rmq {
+    const FBox* sbox;
+    FBox *preA, *sufA, *blk, *preB, *sufB, *table;
+    int n, nb, ns, levels;
+};
+__device__ inline FBox box_union(const FBox& a, const FBox& b)
+{
+    FBox r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) r.lo[k] = fminf(a.lo[k], b.lo[k]), r.hi[k] = fmaxf(a.hi[k], b.hi[k]);
+    return r;
+}
+__device__ inline FBox box_empty()
+{
+    FBox r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) r.lo[k] = INFINITY, r.hi[k] = -INFINITY;
+    return r;
+}
+__device__ inline FBox box_shfl_up(const FBox& b, int o)
+{
+    FBox r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) r.lo[k] = __shfl_up_sync(0xffffffffu, b.lo[k], o), r.hi[k] = __shfl_up_sync(0xffffffffu, b.hi[k], o);
+    return r;
+}
+__device__ inline FBox box_shfl_down(const FBox& b, int o)
+{
+    FBox r;
+#pragma unroll
+    for (int k = 0; k < 3; k++) r.lo[k] = __shfl_down_sync(0xffffffffu, b.lo[k], o), r.hi[k] = __shfl_down_sync(0xffffffffu, b.hi[k], o);
+    return r;
+}
+// inclusive prefix / suffix unions over the 32 lanes of a warp
+__device__ inline void warp_scan_boxes(const FBox& b, int lane, FBox& pre, FBox& suf)
+{
+    pre = b, suf = b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const FBox up = box_shfl_up(pre, o), dn = box_shfl_down(suf, o);
+        if (lane >= o) pre = box_union(pre, up);
+        if (lane + o < 32) suf = box_union(suf, dn);
+    }
+}
+// apply_order fused with level A: one warp per block of 32 sorted leaves
+__global__ void __launch_bounds__(256) k_apply_order_scan(int n, const int* __restrict__ ord, const FBox* __restrict__ box,
+                                                          const int4* __restrict__ prim, FBox* __restrict__ sbox, int4* __restrict__ sprim, Rmq q)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    FBox b = box_empty();
+    if (i < n) {
+        const int j = ord[i];
+        b = box[j];
+        sbox[i] = b;
+        sprim[i] = prim[j];
+    }
+    FBox pre, suf;
+    warp_scan_boxes(b, lane, pre, suf);
+    if (i < n) q.preA[i] = pre, q.sufA[i] = suf;
+    if (lane == 31 && (i >> 5) < q.nb) q.blk[i >> 5] = pre;
+}
+// level B: one warp per super-block of 32 blocks
+__global__ void __launch_bounds__(256) k_rmq_super(Rmq q)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const FBox v = b < q.nb ? q.blk[b] : box_empty();
+    FBox pre, suf;
+    warp_scan_boxes(v, lane, pre, suf);
+    if (b < q.nb) q.preB[b] = pre, q.sufB[b] = suf;
+    if (lane == 31 && (b >> 5) < q.ns) q.table[b >> 5] = pre;
+}
+// level C: sparse table over the super-block totals, one CTA
+__global__ void __launch_bounds__(1024) k_rmq_table(Rmq q)
+{
+    for (int l = 1; l <= q.levels; l++) {
+        __syncthreads();
+        const int half = 1 << (l - 1);
+        const FBox* src = q.table + size_t(l - 1) * q.ns;
+        FBox* dst = q.table + size_t(l) * q.ns;
+        for (int s = threadIdx.x; s + 2 * half <= q.ns; s += blockDim.x) dst[s] = box_union(src[s], src[s + half]);
+    }
+}
+// union of the sorted leaf boxes i..j (inclusive)
+__device__ inline FBox range_box(const Rmq& q, int i, int j)
+{
+    const int bi = i >> 5, bj = j >> 5;
+    if (bi == bj) {
+        if ((i & 31) == 0) return q.preA[j];
+        if ((j & 31) == 31 || j == q.n - 1) return q.sufA[i];
+        FBox r = q.sbox[i];
+        for (int k = i + 1; k <= j; k++) r = box_union(r, q.sbox[k]);
+        return r;
+    }
+    FBox r = box_union(q.sufA[i], q.preA[j]);
+    const int b0 = bi + 1, b1 = bj - 1;
+    if (b0 > b1) return r;
+    const int s0 = b0 >> 5, s1 = b1 >> 5;
+    if (s0 == s1) {
+        if ((b0 & 31) == 0) return box_union(r, q.preB[b1]);
+        if ((b1 & 31) == 31 || b1 == q.nb - 1) return box_union(r, q.sufB[b0]);
+        for (int b = b0; b <= b1; b++) r = box_union(r, q.blk[b]);
+        return r;
+    }
+    r = box_union(r, box_union(q.sufB[b0], q.preB[b1]));
+    const int t0 = s0 + 1, t1 = s1 - 1;
+    if (t0 > t1) return r;
+    const int l = 31 - __clz(t1 - t0 + 1);
+    const FBox* tab = q.table + size_t(l) * q.ns;
+    return box_union(r, box_union(tab[t0], tab[t1 - (1 << l) + 1]));
+}
+// Karras node + both child boxes in one go
+__global__ void k_karras_boxes(int n, const unsigned long long* __restrict__ key, Node* __restrict__ nodes, Rmq q)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const unsigned long long ki = key[i];
+    const int d = delta(key, n, i, ki, i + 1) > delta(key, n, i, ki, i - 1) ? 1 : -1;
+    const int dmin = delta(key, n, i, ki, i - d);
+    int lmax = 2;
+    while (delta(key, n, i, ki, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(key, n, i, ki, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(key, n, i, ki, j);
+    int s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(key, n, i, ki, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const FBox L = lo == gamma ? q.sbox[lo] : range_box(q, lo, gamma);
+    const FBox R = hi == gamma + 1 ? q.sbox[hi] : range_box(q, gamma + 1, hi);
+    Node nd;
+#pragma unroll
+    for (int k = 0; k < 3; k++) nd.lo[0][k] = L.lo[k], nd.hi[0][k] = L.hi[k], nd.lo[1][k] = R.lo[k], nd.hi[1][k] = R.hi[k];
+    nd.child[0] = (lo == gamma) ? ~gamma : gamma;
+    nd.child[1] = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    nd.split = gamma;
+    nd.last = hi;
+    nodes[i] = nd;
+}
+
 // Morton resolution per axis.  The candidate SET does not depend on the tree (SURVEY §7 hard part 1), only the
 // traversal cost does, so the keys only need enough cells to separate neighbouring primitives: 10 bits per axis
 // (4 radix passes) up to 4M primitives, 13 (5 passes) up to 64M, the reference's 21 (8 passes) beyond.
@@ -312,16 +465,36 @@ static void build_tree(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, bool with_node
     const int bits = morton_bits(n);
     k_morton<<<grid_for(n, 256), 256, 0, s>>>(n, bits, getenv("IPCB_MORTON_PER_AXIS") ? 0 : 1, ps.box.p, ctx->scene.p, t.key.p, t.ord.p);
     sort_keys(ctx, t, n, bits, s);
-    k_apply_order<<<grid_for(n, 256), 256, 0, s>>>(n, t.ord_sorted.p, ps.box.p, ps.prim.p, t.sbox.p, t.sprim.p);
-    ctx->launches += 2;
-    if (!with_nodes || n < 2) {
-        t.has_nodes = with_nodes;
+    const bool bottom_up = getenv("IPCB_REFIT_BOTTOM_UP") != nullptr; // A/B + test hook: the arrival-counter refit
+    if (!with_nodes || n < 2 || bottom_up) {
+        k_apply_order<<<grid_for(n, 256), 256, 0, s>>>(n, t.ord_sorted.p, ps.box.p, ps.prim.p, t.sbox.p, t.sprim.p);
+        ctx->launches += 2;
+        if (!with_nodes || n < 2) {
+            t.has_nodes = with_nodes;
+            return;
+        }
+        t.nodes.reserve(n - 1), t.parent.reserve(2 * size_t(n) - 1), t.flag.reserve(n - 1);
+        k_karras<<<grid_for(n - 1, 256), 256, 0, s>>>(n, t.key_sorted.p, t.nodes.p, t.parent.p, t.flag.p);
+        k_refit<<<grid_for(n, 256), 256, 0, s>>>(n, t.sbox.p, t.nodes.p, t.parent.p, t.flag.p);
+        ctx->launches += 2;
+        t.has_nodes = true;
         return;
     }
-    t.nodes.reserve(n - 1), t.parent.reserve(2 * size_t(n) - 1), t.flag.reserve(n - 1);
-    k_karras<<<grid_for(n - 1, 256), 256, 0, s>>>(n, t.key_sorted.p, t.nodes.p, t.parent.p, t.flag.p);
-    k_refit<<<grid_for(n, 256), 256, 0, s>>>(n, t.sbox.p, t.nodes.p, t.parent.p, t.flag.p);
-    ctx->launches += 2;
+    // range-query node boxes: apply_order + level A, level B, level C, then every node in one pass
+    Rmq q;
+    q.n = n, q.nb = (n + 31) / 32, q.ns = (q.nb + 31) / 32;
+    q.levels = 0;
+    while ((2 << q.levels) <= q.ns) q.levels++;
+    const size_t total = 2 * size_t(n) + 3 * size_t(q.nb) + size_t(q.levels + 1) * q.ns;
+    t.rmq.reserve(total);
+    q.sbox = t.sbox.p;
+    q.preA = t.rmq.p, q.sufA = q.preA + n, q.blk = q.sufA + n, q.preB = q.blk + q.nb, q.sufB = q.preB + q.nb, q.table = q.sufB + q.nb;
+    t.nodes.reserve(n - 1);
+    k_apply_order_scan<<<grid_for(size_t(q.nb) * 32, 256), 256, 0, s>>>(n, t.ord_sorted.p, ps.box.p, ps.prim.p, t.sbox.p, t.sprim.p, q);
+    k_rmq_super<<<grid_for(size_t(q.ns) * 32, 256), 256, 0, s>>>(q);
+    if (q.levels > 0) k_rmq_table<<<1, 1024, 0, s>>>(q);
+    k_karras_boxes<<<grid_for(n - 1, 256), 256, 0, s>>>(n, t.key_sorted.p, t.nodes.p, q);
+    ctx->launches += 5;
     t.has_nodes = true;
 }
 

@@ -44,7 +44,8 @@ struct Tree {
     Buf<FBox> sbox;
     Buf<int4> sprim;
     Buf<Node> nodes;
-    Buf<int> parent; // [0,n-1) internal nodes, [n-1,2n-1) leaves
+    Buf<FBox> rmq;   // range-union tables over the sorted leaf boxes (node boxes without a bottom-up pass)
+    Buf<int> parent; // [0,n-1) internal nodes, [n-1,2n-1) leaves (bottom-up refit only)
     Buf<int> flag;
     Buf<char> tmp;
 };

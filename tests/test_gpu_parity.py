@@ -49,7 +49,12 @@ def test_vertex_boxes_bit_exact(cuda, oracle, scenes, name):
 
 @pytest.mark.parametrize("name", SCENES)
 @pytest.mark.parametrize("swept", [False, True])
-def test_broad_phase_all_kinds(cuda, oracle, scenes, name, swept):
+@pytest.mark.parametrize("refit", ["range_query", "bottom_up"])
+def test_broad_phase_all_kinds(cuda, oracle, scenes, name, swept, refit, monkeypatch):
+    if refit == "bottom_up":  # node boxes by the arrival-counter refit instead of range queries over the sorted leaves
+        if name not in ("stack", "soup"):
+            pytest.skip("the alternative refit is covered on two scenes")
+        monkeypatch.setenv("IPCB_REFIT_BOTTOM_UP", "1")
     V0, V1, E, F, P = _scene(scenes, name)
     if swept and name == "sheets":
         V1 = V0 + 0.2 * (V1 - V0)  # keep the 6-kind brute-force comparison small
