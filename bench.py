@@ -295,6 +295,28 @@ def main():
     lib.check(lib.candidates_build_swept_dev(ctx, C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr()), nV, 0.0, counts))
     info["ccd_candidates"] = list(counts)
 
+    # ---- the line-search inner loop of the reference's solver example (python/examples/solver.py:
+    # 95-116) from RESIDENT candidates: swept candidates with inflation dhat built once, then per line-search point
+    # NormalCollisions::build(candidates, mesh, X, dhat) + the barrier energy — no broad phase inside the loop
+    line_search = None
+    if world == 1:
+        p0, p1 = C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr())
+        lib.check(lib.candidates_build_swept_dev(ctx, p0, p1, nV, dhat, counts))
+        ls_cand = list(counts)
+        lib.check(lib.ccd_stepsize_from_candidates_dev(ctx, p0, p1, nV, 0.0, C.byref(ccd), C.c_void_p(d_step.data_ptr())))
+        torch.cuda.synchronize()
+        alpha = float(d_step.item())
+        dX = (dV0 + 0.5 * alpha * (dV1 - dV0)).contiguous()
+        ls_counts = (C.c_int64 * 4)()
+
+        def rebuild():
+            lib.check(lib.collisions_build_from_candidates_dev(ctx, C.c_void_p(dX.data_ptr()), nV, dhat, 0.0, 0, ls_counts))
+            lib.check(lib.barrier_energy_dev(ctx, C.c_void_p(dX.data_ptr()), nV, C.byref(bp), C.c_void_p(d_energy.data_ptr())))
+
+        ls_ms = timed(rebuild, max(3, args.steps // 2), 2)
+        line_search = {"ms_per_rebuild": ls_ms, "what": "collisions_build_from_candidates_dev + barrier_energy_dev at x0 + alpha/2 dx",
+                       "resident_candidates": ls_cand, "collisions": list(ls_counts), "alpha": alpha}
+
     # ---- end to end through the host-buffer C ABI (pinned inputs, host results)
     hV0 = torch.from_numpy(np.asfortranarray(V0).T.copy()).pin_memory()
     hV1 = torch.from_numpy(np.asfortranarray(V1).T.copy()).pin_memory()
@@ -426,6 +448,7 @@ def main():
             "rooflines": rooflines,
             "cpu_baseline": cpu,
             "stages_ms": stages,
+            "line_search_rebuild": line_search,
             "counts": {"collisions_rank0": ncoll, "shard_collisions_rank0": info.get("shard_collisions"),
                        "hessian_rows_rank0": info.get("rows"), "ccd_candidates_rank0": info.get("ccd_candidates"),
                        "hessian_nnz_rank0": info.get("nnz"), "step": info.get("step"),

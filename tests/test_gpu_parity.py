@@ -350,3 +350,47 @@ def test_collision_merge_and_sharded_potential(cuda, oracle, scenes, name):
     assert out["cuda"]["bounds"][0] == 0 and out["cuda"]["bounds"][-1] == V0.shape[0]
     for a, b in zip(out["cuda"]["tiles"], out["oracle"]["tiles"]):
         assert np.array_equal(a.indptr, b.indptr) and np.array_equal(a.indices, b.indices) and relerr(a.data, b.data) <= RTOL
+
+
+@pytest.mark.parametrize("name", ["stack", "drape", "sheets"])
+def test_line_search_rebuild_from_resident_candidates(cuda, oracle, scenes, name):
+    """SURVEY §8f rank 2 — the caller loop of the reference's solver example (python/examples/solver.py:95-116):
+    candidates built ONCE over the swept step with inflation dhat, the collision-free step size from them, then
+    NormalCollisions::build(candidates, mesh, X, dhat) + the barrier energy at several line-search points, all from the
+    resident candidate set (no broad phase in the loop).  Sets bit-exact, energies / minimum distances to 1e-10."""
+    V0, V1, E, F, P = _scene(scenes, name)
+    dhat = P["dhat"]
+    state = {}
+    for key, api in (("cuda", cuda), ("oracle", oracle)):
+        mesh = api.CollisionMesh(V0, E, F)
+        cand = api.Candidates()
+        cand.build(mesh, V0, V1, dhat)
+        alpha = cand.compute_collision_free_stepsize(mesh, V0, V1)
+        state[key] = dict(api=api, mesh=mesh, cand=cand, alpha=alpha, n=[len(cand.vv_candidates), len(cand.ev_candidates),
+                                                                        len(cand.ee_candidates), len(cand.fv_candidates)],
+                          ee=cand.ee_candidates.copy(), fv=cand.fv_candidates.copy())
+    a, b = state["cuda"], state["oracle"]
+    assert a["n"] == b["n"] and np.array_equal(a["ee"], b["ee"]) and np.array_equal(a["fv"], b["fv"])
+    assert a["alpha"] <= b["alpha"] + 1e-3 * b["alpha"] + 1e-6 and a["alpha"] >= b["alpha"] - 1e-3 * b["alpha"] - 1e-6
+    alpha = min(a["alpha"], b["alpha"])
+    B = {k: s["api"].BarrierPotential(dhat, 1.0) for k, s in state.items()}
+    energies = []
+    for it in range(4):  # backtracking: alpha, alpha / 2, ...
+        X = V0 + alpha * 0.5 ** it * (V1 - V0)
+        res = {}
+        for key, s in state.items():
+            c = s["api"].NormalCollisions()
+            c.build(s["cand"], s["mesh"], X, dhat)
+            sets = [getattr(c, k + "_collisions") for k in ("vv", "ev", "ee", "fv")]
+            res[key] = dict(sets=sets, e=B[key](c, s["mesh"], X), d=c.compute_minimum_distance(s["mesh"], X),
+                            g=B[key].gradient(c, s["mesh"], X))
+        for sa, sb in zip(res["cuda"]["sets"], res["oracle"]["sets"]):
+            assert np.array_equal(sa.ids, sb.ids) and np.array_equal(sa.dtype, sb.dtype) and relerr(sa.weight, sb.weight) <= 1e-14
+        assert abs(res["cuda"]["e"] - res["oracle"]["e"]) <= RTOL * abs(res["oracle"]["e"])
+        assert relerr(res["cuda"]["g"], res["oracle"]["g"]) <= RTOL
+        if np.isfinite(res["oracle"]["d"]):
+            assert abs(res["cuda"]["d"] - res["oracle"]["d"]) <= 1e-12 * res["oracle"]["d"]
+        else:
+            assert not np.isfinite(res["cuda"]["d"])
+        energies.append(res["cuda"]["e"])
+    assert any(e > 0 for e in energies)
