@@ -147,10 +147,29 @@ template <int KIND, int MINB> __global__ void __launch_bounds__(256, MINB) k_cla
             }
         }
     }
-    append(a.out[IPCB_VV], dest == 1, key, w, 0, 0);
-    if (KIND != IPCB_VV) append(a.out[IPCB_EV], dest == 2, key, w, 0, 0);
-    if (KIND == IPCB_EE) append(a.out[IPCB_EE], dest == 3, key, w, eps, dt);
-    if (KIND == IPCB_FV) append(a.out[IPCB_FV], dest == 3, key, w, 0, 0);
+    // warp-aggregated append to the (up to) three destination streams with ONE atomic round trip: lanes 0..2 reserve
+    // the ranges of destinations 1..3 in the same instruction, instead of three dependent reserve-then-store rounds
+    const int lane = threadIdx.x & 31;
+    const unsigned m1 = __ballot_sync(0xffffffffu, dest == 1), m2 = __ballot_sync(0xffffffffu, dest == 2),
+                   m3 = __ballot_sync(0xffffffffu, dest == 3);
+    if ((m1 | m2 | m3) == 0) return;
+    constexpr int OWN = KIND == IPCB_EE ? IPCB_EE : IPCB_FV; // stream of destination 3 (unused for VV / EV candidates)
+    unsigned long long base = 0;
+    {
+        const unsigned mine = lane == 0 ? m1 : (lane == 1 ? m2 : m3);
+        unsigned long long* counter = lane == 0 ? a.out[IPCB_VV].counter : (lane == 1 ? a.out[IPCB_EV].counter : a.out[OWN].counter);
+        if (lane < 3 && mine) base = atomicAdd(counter, (unsigned long long)__popc(mine));
+    }
+    const unsigned long long b1 = __shfl_sync(0xffffffffu, base, 0), b2 = __shfl_sync(0xffffffffu, base, 1),
+                             b3 = __shfl_sync(0xffffffffu, base, 2);
+    if (dest == 0) return;
+    const unsigned below = (1u << lane) - 1;
+    const unsigned long long p = dest == 1 ? b1 + __popc(m1 & below) : (dest == 2 ? b2 + __popc(m2 & below) : b3 + __popc(m3 & below));
+    unsigned long long* okey = dest == 1 ? a.out[IPCB_VV].key : (dest == 2 ? a.out[IPCB_EV].key : a.out[OWN].key);
+    double* ow = dest == 1 ? a.out[IPCB_VV].w : (dest == 2 ? a.out[IPCB_EV].w : a.out[OWN].w);
+    okey[p] = key;
+    ow[p] = w;
+    if (KIND == IPCB_EE && dest == 3) a.out[IPCB_EE].eps[p] = eps, a.out[IPCB_EE].dt[p] = dt;
 }
 
 // ---- merge: sorted keys -> unique records with accumulated weights ---------------

@@ -149,6 +149,7 @@ struct ipcb_ctx {
     ipcb::Buf<unsigned char> hflag;                  // row block: does the collision touch an owned vertex
     ipcb::Buf<int> hsel;                             // row block: per kind, the collisions that do (ascending)
     ipcb::Buf<int> hslow;                            // edge-edge collisions handed to the general kernel
+    ipcb::Buf<int2> hcolb;                           // per column vertex: first EV incidence, first 4-point incidence
     ipcb::Buf<int> hcolinc, hcolR, hitemoff;         // per column vertex: first incidence, #items, first item
     ipcb::Buf<unsigned> hsref;                       // per item, grouped by column then by row vertex: block slot
     ipcb::Buf<int2> hudesc;                          // per unique block: (first item within its column, row vertex)

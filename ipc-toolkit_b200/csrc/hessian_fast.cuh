@@ -19,14 +19,19 @@
 
 namespace ipcb {
 
-// Jacobi rotation parameters for the pivot (app, apq, aqq): t = tan(phi) of the smaller rotation angle.
-// With d = aqq - app and h = 2 apq:  t = h / (d + sign(d) sqrt(d^2 + h^2))  — one square root and one division.
+// Jacobi rotation parameters for the pivot (app, apq, aqq): the smaller rotation angle phi with tan(2 phi) = h / d,
+// d = aqq - app, h = 2 apq.  Half-angle form with two reciprocal square roots and neither a division nor a square
+// root (FP64 div / sqrt are ~20-instruction sequences each, rsqrt about half of that):
+//   cos(2 phi) = |d| / sqrt(d^2 + h^2),  c = cos(phi) = sqrt((1 + cos 2phi) / 2),  s = sin(2 phi) / (2 c),  t = s / c.
 __device__ __forceinline__ void jacobi_params(double app, double apq, double aqq, double& t, double& c, double& s)
 {
     const double d = aqq - app, h = 2.0 * apq;
-    t = h / (d + copysign(sqrt(fma(d, d, h * h)), d));
-    c = rsqrt(fma(t, t, 1.0));
-    s = t * c;
+    const double rq = rsqrt(fma(d, d, h * h));
+    const double c2 = fma(0.5 * fabs(d), rq, 0.5); // cos^2(phi) in [1/2, 1]
+    const double rc = rsqrt(c2);                   // 1 / cos(phi)
+    c = c2 * rc;
+    s = copysign(0.5 * h * rq, d * h) * rc;        // sign(d) * h carries the sign of tan(2 phi)
+    t = s * rc;
 }
 // apply the rotation in the (p, q) plane to A (upper triangle) and accumulate it into V
 template <int N> __device__ __forceinline__ void jacobi_apply(double (&A)[N][N], double (&V)[N][N], int p, int q, double t, double c, double s)

@@ -633,8 +633,10 @@ __device__ inline int lower_bound_lo(const unsigned long long* __restrict__ key,
     return lo;
 }
 // per column vertex: first incidence and number of row-block items (2 / 3 / 4 per VV / EV / other incidence)
+// colb[v] = (b1, b2): first edge-vertex incidence and first 4-point incidence of the column (incidences are ordered
+// VV, EV, then the 4-point kinds) — computed once here instead of by every lane of the column's warp
 __global__ void k_col_ranges(int nV, int nInc, const unsigned long long* __restrict__ inc, unsigned ref_ev, unsigned ref_ee,
-                             int* __restrict__ colinc, int* __restrict__ colR)
+                             int* __restrict__ colinc, int* __restrict__ colR, int2* __restrict__ colb)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v > nV) return;
@@ -645,6 +647,7 @@ __global__ void k_col_ranges(int nV, int nInc, const unsigned long long* __restr
         const int e = lower_bound_hi(inc, s, nInc, unsigned(v) + 1u);
         const int b1 = lower_bound_lo(inc, s, e, ref_ev), b2 = lower_bound_lo(inc, b1, e, ref_ee);
         R = 2 * (b1 - s) + 3 * (b2 - b1) + 4 * (e - b2);
+        colb[v] = make_int2(b1, b2);
     }
     colR[v] = R;
 }
@@ -676,6 +679,7 @@ struct SymArgs {
     const int* colinc;
     const int* colR;
     const int* itemoff;
+    const int2* colb;
     const int4* vid;
     const unsigned short* mask;
     unsigned ref_ev, ref_ee;
@@ -715,7 +719,8 @@ __device__ inline void column_symbolic_sort(const SymArgs& A, int v, int t, unsi
     const int s = A.colinc[v], e = A.colinc[v + 1], R = A.colR[v];
     int npow2 = 1;
     while (npow2 < R) npow2 <<= 1;
-    const int b1 = lower_bound_lo(A.inc, s, e, A.ref_ev), b2 = lower_bound_lo(A.inc, b1, e, A.ref_ee);
+    const int2 bb = A.colb[v];
+    const int b1 = bb.x, b2 = bb.y;
     for (int q = s + t; q < e; q += NT) {
         const IncItems it = load_incidence(A, q, b1, b2);
         const int slot0 = q < b1 ? 2 * (q - s) : (q < b2 ? 2 * (b1 - s) + 3 * (q - b1) : 2 * (b1 - s) + 3 * (b2 - b1) + 4 * (q - b2));
@@ -795,13 +800,19 @@ __device__ inline int hash_slot(int vi) { return int((unsigned(vi) * 2654435761u
 __device__ inline bool column_symbolic_hash(const SymArgs& A, int v, int lane, HashSmem& H)
 {
     const int s = A.colinc[v], e = A.colinc[v + 1], R = A.colR[v];
-    const int b1 = lower_bound_lo(A.inc, s, e, A.ref_ev), b2 = lower_bound_lo(A.inc, b1, e, A.ref_ee);
+    const int2 bb = A.colb[v];
+    const int b1 = bb.x, b2 = bb.y;
     for (int k = lane; k < HT; k += 32) H.key[k] = -1, H.msk[k] = 0, H.cnt[k] = 0;
     __syncwarp();
-    // A. insert every row vertex; OR the patterns, count the items
+    // A. insert every row vertex; OR the patterns, count the items.  The first two incidences of every lane stay in
+    // registers for the placement pass (a column has ~46 incidences on the dense scenes: no second gather)
     bool overflow = false;
+    IncItems keep0, keep1;
+    keep0.np = keep1.np = 0;
     for (int q = s + lane; q < e; q += 32) {
         const IncItems it = load_incidence(A, q, b1, b2);
+        if (q < s + 32) keep0 = it;
+        else if (q < s + 64) keep1 = it;
 #pragma unroll
         for (int b = 0; b < 4; b++)
             if (b < it.np) {
@@ -867,7 +878,7 @@ __device__ inline bool column_symbolic_hash(const SymArgs& A, int v, int lane, H
         const int q = q0 + lane;
         IncItems it;
         it.np = 0;
-        if (q < e) it = load_incidence(A, q, b1, b2);
+        if (q < e) it = q0 == s ? keep0 : (q0 == s + 32 ? keep1 : load_incidence(A, q, b1, b2));
 #pragma unroll
         for (int b = 0; b < 4; b++) {
             const bool valid = b < it.np;
@@ -964,14 +975,14 @@ __global__ void __launch_bounds__(BIG_THREADS)
 // (local_to_global.hpp:290-291).  Positions inside the three scalar columns follow from one ballot.
 // The loads form a dependent chain (descriptor -> block references -> blocks); it is software-pipelined: while the
 // blocks of one group of runs are in flight, the descriptors and references of the next group are fetched.
-constexpr int NUM_BATCH = 8; // block references fetched ahead per run
-struct RunRefs {
+// NUM_BATCH: block references fetched ahead per run (12 by default; IPCB_NUM_BATCH=8 / 16 select the other variants)
+template <int NUM_BATCH> struct RunRefs {
     int start, len, row;
     unsigned ref[NUM_BATCH];
 };
-__device__ __forceinline__ RunRefs load_run(const int2* __restrict__ ud, const unsigned* __restrict__ sr, int u, int U, int R, bool lane_ok)
+template <int NUM_BATCH> __device__ __forceinline__ RunRefs<NUM_BATCH> load_run(const int2* __restrict__ ud, const unsigned* __restrict__ sr, int u, int U, int R, bool lane_ok)
 {
-    RunRefs rr;
+    RunRefs<NUM_BATCH> rr;
     rr.start = 0, rr.len = 0, rr.row = 0;
     if (lane_ok && u < U) {
         const int2 d = ud[u];
@@ -982,6 +993,7 @@ __device__ __forceinline__ RunRefs load_run(const int2* __restrict__ ud, const u
     for (int x = 0; x < NUM_BATCH; x++) rr.ref[x] = x < rr.len ? sr[rr.start + x] : 0u;
     return rr;
 }
+template <int NUM_BATCH>
 __global__ void __launch_bounds__(32 * SYM_WARPS)
     k_hess_numeric(int nV, const int* __restrict__ colR, const int* __restrict__ colU, const int* __restrict__ itemoff,
                    const unsigned* __restrict__ sref, const int2* __restrict__ udesc, const double* __restrict__ blk,
@@ -999,7 +1011,7 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
     const int2* ud = udesc + ioff;
     const unsigned* sr = sref + ioff;
     int base = lane_ok ? outer[3 * size_t(v) + l] : 0;
-    RunRefs cur = load_run(ud, sr, g, U, R, lane_ok);
+    RunRefs<NUM_BATCH> cur = load_run<NUM_BATCH>(ud, sr, g, U, R, lane_ok);
     for (int u0 = 0; u0 < U; u0 += 3) {
         double val[NUM_BATCH];
 #pragma unroll
@@ -1007,7 +1019,7 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
             val[x] = 0.0;
             if (x < cur.len) val[x] = __ldg(blk + size_t(cur.ref[x]) * 9 + k);
         }
-        const RunRefs nxt = load_run(ud, sr, u0 + 3 + g, U, R, lane_ok); // overlaps with the block loads above
+        const RunRefs<NUM_BATCH> nxt = load_run<NUM_BATCH>(ud, sr, u0 + 3 + g, U, R, lane_ok); // overlaps with the block loads above
         double acc = 0.0;
         bool nz = false;
 #pragma unroll
@@ -1016,7 +1028,9 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
                 acc += val[x];
                 nz |= val[x] != 0.0;
             }
-        for (int j = NUM_BATCH; j < cur.len; j++) { // long runs: the remainder, in order
+        // long runs: the remainder, in order (a batched remainder — NUM_BATCH more loads in flight — measured SLOWER:
+        // 3.2 vs 2.4 ms on C3; most remainders are one or two blocks and the predicated batch costs more than it hides)
+        for (int j = NUM_BATCH; j < cur.len; j++) {
             const double w = __ldg(blk + size_t(sr[cur.start + j]) * 9 + k);
             acc += w;
             nz |= w != 0.0;
@@ -1245,7 +1259,9 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     ctx->launches += 2 + (vbits + 7) / 8;
     // 2. column ranges and item offsets
     const unsigned ref_ev = unsigned(gi0[1] * 4), ref_ee = unsigned(gi0[2] * 4);
-    k_col_ranges<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, int(ninc), ctx->hkey_sorted.p, ref_ev, ref_ee, ctx->hcolinc.p, ctx->hcolR.p);
+    ctx->hcolb.reserve(size_t(nV) + 1);
+    k_col_ranges<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, int(ninc), ctx->hkey_sorted.p, ref_ev, ref_ee, ctx->hcolinc.p, ctx->hcolR.p,
+                                                            ctx->hcolb.p);
     cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, b2, ctx->hcolR.p, ctx->hitemoff.p, nV + 1, s);
     ctx->launches += 3;
     st.reset();
@@ -1256,7 +1272,7 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     unsigned long long* nbig = ctx->dCounters.p + 6;
     unsigned long long* need = ctx->dCounters.p + 7;
     ctx->hudesc.reserve(nitems), ctx->hcolU.reserve(size_t(nV) + 1);
-    const SymArgs A { nV, ctx->hkey_sorted.p, ctx->hcolinc.p, ctx->hcolR.p, ctx->hitemoff.p, ctx->hvid.p, ctx->hmask.p, ref_ev, ref_ee,
+    const SymArgs A { nV, ctx->hkey_sorted.p, ctx->hcolinc.p, ctx->hcolR.p, ctx->hitemoff.p, ctx->hcolb.p, ctx->hvid.p, ctx->hmask.p, ref_ev, ref_ee,
                       ctx->hsref.p, ctx->hudesc.p, ctx->hcolU.p, ctx->hcnt.p };
     if (!ctx->hess_attr_set) { // per device
         IPCB_CUDA(cudaFuncSetAttribute(k_hess_symbolic_big, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BIG_SMEM)));
@@ -1290,8 +1306,18 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     st.reset();
     st.reset(new Stage(ctx, "hess_numeric"));
     // 5. pass 2: gather, run-sum, write compressed columns
-    k_hess_numeric<<<grid_for(nV, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p,
-                                                                       ctx->hblk.p, ctx->outer.p, ctx->inner.p, ctx->vals.p);
+    const char* nb_env = getenv("IPCB_NUM_BATCH");
+    const int nb = nb_env ? atoi(nb_env) : 12; // measured on C3: 2.43 ms (8), 2.24 ms (12)
+    const unsigned ngrid = grid_for(nV, SYM_WARPS);
+    if (nb == 16)
+        k_hess_numeric<16><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,
+                                                           ctx->outer.p, ctx->inner.p, ctx->vals.p);
+    else if (nb == 12)
+        k_hess_numeric<12><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,
+                                                           ctx->outer.p, ctx->inner.p, ctx->vals.p);
+    else
+        k_hess_numeric<8><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,
+                                                          ctx->outer.p, ctx->inner.p, ctx->vals.p);
     ctx->launches++;
     IPCB_CUDA(cudaGetLastError());
 }
