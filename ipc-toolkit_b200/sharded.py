@@ -156,6 +156,9 @@ class DeviceShardedStep:
             self.send = torch.empty(self.cap, dtype=torch.uint8, device="cuda")
             self.recv = torch.empty(self.cap * self.world, dtype=torch.uint8, device="cuda")
         self.used = (need + 15) // 16 * 16  # only the used prefix of every slot travels
+        if self.used == 0:  # no rank found a collision (all ranks see the same `need`): nothing to move
+            self.ev_gathered.record(self.stream)
+            return
         nbytes = C.c_int64()
         lib.check(lib.collisions_pack_dev(self.ctx, C.c_void_p(self.send.data_ptr()), self.cap, C.byref(nbytes)))
         self.ev_packed.record(self.stream)
@@ -170,6 +173,8 @@ class DeviceShardedStep:
         self.stream.wait_event(self.ev_gathered)
         lib.check(lib.collisions_clear(self.ctx))
         for r in range(self.world):
+            if sum(self.all_counts[r]) == 0:
+                continue
             c = (C.c_int64 * 4)(*self.all_counts[r])
             lib.check(lib.collisions_append_packed_dev(self.ctx, C.c_void_p(self.recv.data_ptr() + r * self.used), c))
         lib.check(lib.collisions_merge(self.ctx, dmin, 1, self.counts))  # 1 = IPCB_MERGE_DISJOINT_SHARDS
