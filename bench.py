@@ -398,6 +398,11 @@ def main():
 
     # local Hessians: per collision 24 B record + 32 B per stencil point in; 16 B ids + 32 B masks + 8 B per incidence +
     # 72 B per 3x3 block out
+    if world > 1 and not args.additive_hessian:
+        # row-block mode: every rank holds the FULL set (ncoll) and assembles its row block, i.e. about 1 / world of
+        # the items and of the block rows; rank 0's share is what its kernels moved (ncu traffic is a single-GPU capture)
+        ncoll = [c / world for c in ncoll]
+        nitems, ninc, traffic = nitems / world, ninc / world, None
     hl_bytes = sum(c * (24 + 32 * n + 16 + 32 + 8 * n + 72 * n * n) for c, n in zip(ncoll, npts))
     # numeric pass: 4 B reference + 72 B block per item in, 8 B per unique block (~nnz / 9), 12 B per entry out
     hn_bytes = nitems * 76 + nnz_ * 12 + (nnz_ // 9) * 8
@@ -406,7 +411,7 @@ def main():
     rooflines = [r for r in (
         roof("k_hessian_fast<VV|EV|EE|FV> (4 concurrent launches)", "hessian_local", hl_bytes,
              ["k_hessian_fast<0", "k_hessian_fast<1", "k_hessian_fast<2", "k_hessian_fast<3"],
-             "FP64-pipe bound (register Jacobi PSD projection, ~42% FP64 pipe at 18% occupancy); stores coalesced through shared memory"),
+             "FP64-pipe bound (register Jacobi PSD projection, ~44% FP64 pipe at 25% occupancy, 128 registers); stores coalesced through shared memory"),
         roof("k_hess_numeric", "hess_numeric", hn_bytes, ["k_hess_numeric"], "HBM gather of 72-byte blocks, software-pipelined"),
         roof("k_hess_symbolic", "hess_symbolic", hs_bytes, ["k_hess_symbolic"], "shared-memory hash + sort per column; instruction / latency bound"),
     ) if r]
@@ -449,7 +454,7 @@ def main():
             "cpu_baseline": cpu,
             "stages_ms": stages,
             "line_search_rebuild": line_search,
-            "counts": {"collisions_rank0": ncoll, "shard_collisions_rank0": info.get("shard_collisions"),
+            "counts": {"collisions_rank0": info.get("collisions"), "shard_collisions_rank0": info.get("shard_collisions"),
                        "hessian_rows_rank0": info.get("rows"), "ccd_candidates_rank0": info.get("ccd_candidates"),
                        "hessian_nnz_rank0": info.get("nnz"), "step": info.get("step"),
                        "energy": info.get("energy")},
