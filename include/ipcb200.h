@@ -62,8 +62,11 @@ enum { IPCB_CCD_TIGHT_INCLUSION = 0, IPCB_CCD_ADDITIVE = 1 };
  * HashGrid double boxes (broad_phase/aabb.cpp:29-33).  Cross-check switch. */
 enum { IPCB_BOXES_FLOAT = 0, IPCB_BOXES_DOUBLE = 1 };
 
-/* flags for collisions_build (collisions/normal/normal_collisions.hpp:191-194) */
-enum { IPCB_USE_AREA_WEIGHTING = 1 };
+/* flags for collisions_build (collisions/normal/normal_collisions.hpp:191-194: use_area_weighting; :29-39
+ * CollisionSetType).  IPCB_SET_IMPROVED_MAX_APPROX selects CollisionSetType::IMPROVED_MAX_APPROX (the negative /
+ * positive correction collisions of normal_collisions.cpp:84-128); the CPU restatement implements it, the CUDA library
+ * does not yet and fails loudly when asked. */
+enum { IPCB_USE_AREA_WEIGHTING = 1, IPCB_SET_IMPROVED_MAX_APPROX = 2 };
 
 /* flags for collisions_merge: the appended builders worked on DISJOINT candidate shards (the ranks of a sharded
  * build), so their edge-edge and face-vertex records are unique across builders and only vertex-vertex /

@@ -301,7 +301,13 @@ def make_api(lib):
             return self.compute_collision_free_stepsize(mesh, vertices_t0, vertices_t1, min_distance, narrow_phase_ccd) >= 1.0
 
     class NormalCollisions:
-        """ipc::NormalCollisions — collisions/normal/normal_collisions.cpp:20-158 (IPC set type)"""
+        """ipc::NormalCollisions — collisions/normal/normal_collisions.cpp:20-158 (IPC set type; IMPROVED_MAX_APPROX is
+        restated in the CPU checker only, the CUDA library raises for it)"""
+
+        class CollisionSetType(enum.IntEnum):  # normal_collisions.hpp:29-39
+            IPC = 0
+            IMPROVED_MAX_APPROX = 1
+            OGC = 2
 
         def __init__(self):
             self.mesh = None
@@ -309,14 +315,23 @@ def make_api(lib):
             self._counts = [0, 0, 0, 0]
             self._host = {}
             self.use_area_weighting = False
+            self.collision_set_type = NormalCollisions.CollisionSetType.IPC
 
         def set_use_area_weighting(self, v):
             self.use_area_weighting = bool(v)
 
+        def set_collision_set_type(self, t):
+            self.collision_set_type = NormalCollisions.CollisionSetType(t)
+
+        def _flags(self):
+            if self.collision_set_type == NormalCollisions.CollisionSetType.OGC:
+                raise NotImplementedError("CollisionSetType.OGC is outside this path (DESIGN.md §7)")
+            return (1 if self.use_area_weighting else 0) | (2 if self.collision_set_type else 0)
+
         def build(self, *args, **kw):
             """build(mesh, V, dhat, dmin=0, broad_phase=None) or build(candidates, mesh, V, dhat, dmin=0)"""
             counts = (C.c_int64 * 4)()
-            flags = 1 if self.use_area_weighting else 0
+            flags = self._flags()
             if isinstance(args[0], Candidates):
                 cand, mesh, V, dhat = args[:4]
                 dmin = args[4] if len(args) > 4 else kw.get("dmin", 0.0)

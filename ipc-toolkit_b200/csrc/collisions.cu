@@ -263,6 +263,8 @@ static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4], bool disjoint = f
 
 void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
 {
+    if (flags & IPCB_SET_IMPROVED_MAX_APPROX)
+        throw Error("CollisionSetType::IMPROVED_MAX_APPROX is not implemented in the CUDA library yet (IPC set type only)");
     cudaStream_t s = ctx->stream;
     int64_t total = 0;
     for (auto& c : ctx->cand) total += c.count;

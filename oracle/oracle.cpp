@@ -72,6 +72,10 @@ struct ipcb_ctx {
     std::vector<int32_t> E, F, F2E; // row-major nE x 2, nF x 3, nF x 3
     std::vector<int32_t> codim_vertices, codim_edges;
     std::vector<double> vertex_areas, edge_areas;
+    // adjacencies (collision_mesh.cpp:247-307), sorted: vertex -> vertices, vertex -> edges, edge -> opposite vertices
+    // of its faces; is_vertex_on_boundary
+    std::vector<std::vector<int32_t>> vv_adj, ve_adj, ev_adj;
+    std::vector<char> on_boundary;
     // broad phase
     int boxes_mode = IPCB_BOXES_FLOAT;
     bool built = false;
@@ -434,15 +438,22 @@ int stencil_ids(const ipcb_ctx* ctx, int kind, int a, int b, int32_t ids[4])
 // merged with weight accumulation, weight == 0 dropped; canonical order = sorted by (a, b, dtype)
 void merge_collisions(ipcb_ctx* ctx, int k, std::vector<Coll>& all)
 {
-    __gnu_parallel::stable_sort(all.begin(), all.end(), [](const Coll& x, const Coll& y) {
-        if (x.a != y.a) return x.a < y.a;
-        if (x.b != y.b) return x.b < y.b;
-        return x.dtype < y.dtype;
+    // edge-edge collisions are equal when their UNORDERED edge pair and their distance type agree
+    // (collisions/normal/edge_edge.cpp:123-142); the stored orientation (the distance type refers to it) is kept.
+    // With the IPC set type the first edge id is always the smaller one, so this is the plain (a, b, dtype) order.
+    const bool unordered = k == IPCB_EE;
+    auto lo = [unordered](const Coll& c) { return unordered ? std::min(c.a, c.b) : c.a; };
+    auto hi = [unordered](const Coll& c) { return unordered ? std::max(c.a, c.b) : c.b; };
+    __gnu_parallel::stable_sort(all.begin(), all.end(), [&](const Coll& x, const Coll& y) {
+        if (lo(x) != lo(y)) return lo(x) < lo(y);
+        if (hi(x) != hi(y)) return hi(x) < hi(y);
+        if (x.dtype != y.dtype) return x.dtype < y.dtype;
+        return x.a < y.a;
     });
     std::vector<Coll>& out = ctx->coll[k];
     out.clear();
     for (const Coll& c : all) {
-        if (k != IPCB_FV && !out.empty() && out.back().a == c.a && out.back().b == c.b && out.back().dtype == c.dtype) {
+        if (k != IPCB_FV && !out.empty() && lo(out.back()) == lo(c) && hi(out.back()) == hi(c) && out.back().dtype == c.dtype) {
             out.back().w += c.w;
         } else {
             out.push_back(c);
@@ -450,6 +461,132 @@ void merge_collisions(ipcb_ctx* ctx, int k, std::vector<Coll>& all)
     }
     if (k != IPCB_FV) {
         out.erase(std::remove_if(out.begin(), out.end(), [](const Coll& c) { return c.w == 0; }), out.end());
+    }
+}
+
+// CollisionSetType::IMPROVED_MAX_APPROX (normal_collisions.cpp:84-128): after the IPC passes, sub-element candidates
+// are derived from the element candidates (candidates.cpp:584-695: active vertex-vertex / edge-vertex pairs of every
+// edge-vertex / edge-edge / face-vertex candidate, duplicates removed) and each adds a NEGATIVE or POSITIVE correction
+// collision whose weight counts how often the IPC passes over-counted the pair (builder.cpp:340-543).
+template <typename Active>
+void improved_max_approx_corrections(ipcb_ctx* ctx, const std::vector<V3>& V, bool area, const Active& is_active, std::vector<std::vector<Coll>> (&loc)[4])
+{
+    const int32_t* E = ctx->E.data();
+    const int32_t* F = ctx->F.data();
+    auto contains = [](const std::vector<int32_t>& sorted, int32_t v) { return std::binary_search(sorted.begin(), sorted.end(), v); };
+    auto add_vv = [&](int vi, int vj, double w) { loc[IPCB_VV][0].push_back({ std::min(vi, vj), std::max(vi, vj), w, 0, 0 }); };
+    auto add_ev = [&](int ei, int vi, double w) { loc[IPCB_EV][0].push_back({ ei, vi, w, 0, 0 }); };
+    // add_edge_vertex_collision(mesh, candidate, dtype, weight) :108-138: reduced to the closest feature
+    auto add_ev_typed = [&](int ei, int vi, PE dtype, double w) {
+        if (dtype == PE_P_E0) add_vv(vi, E[2 * ei], w);
+        else if (dtype == PE_P_E1) add_vv(vi, E[2 * ei + 1], w);
+        else add_ev(ei, vi, w);
+    };
+    auto unique_unordered = [](std::vector<Pair>& p) { // VertexVertexCandidate: order and equality ignore orientation
+        for (auto& q : p)
+            if (q[0] > q[1]) std::swap(q[0], q[1]);
+        std::sort(p.begin(), p.end());
+        p.erase(std::unique(p.begin(), p.end()), p.end());
+    };
+    auto unique_ordered = [](std::vector<Pair>& p) {
+        std::sort(p.begin(), p.end());
+        p.erase(std::unique(p.begin(), p.end()), p.end());
+    };
+
+    // ---- edge-vertex candidates -> vertex-vertex (:584-622), negative corrections (builder.cpp:340-383)
+    if (!ctx->cand[IPCB_EV].empty()) {
+        std::vector<Pair> vv;
+        for (const Pair& c : ctx->cand[IPCB_EV])
+            for (int j = 0; j < 2; j++) {
+                const int vi = c[1], vj = E[2 * c[0] + j];
+                if (is_active(point_point_distance(V[vi], V[vj]))) vv.push_back({ vi, vj });
+            }
+        unique_unordered(vv);
+        for (const Pair& c : vv) {
+            double w = 0;
+            auto add_weight = [&](int vi, int vj) {
+                const auto& inc = ctx->vv_adj[vj];
+                const int amt = int(inc.size()) - int(contains(inc, vi));
+                if (amt > 1) w += (1 - amt) * (area ? 0.5 * ctx->vertex_areas[vi] : 1.0); // / 2: double counting
+            };
+            add_weight(c[0], c[1]);
+            add_weight(c[1], c[0]);
+            if (w != 0) add_vv(c[0], c[1], w);
+        }
+    }
+    // ---- edge-edge candidates -> edge-vertex (:666-695), negative corrections (builder.cpp:457-543)
+    if (!ctx->cand[IPCB_EE].empty()) {
+        std::vector<Pair> ev;
+        for (const Pair& c : ctx->cand[IPCB_EE])
+            for (int i = 0; i < 2; i++) {
+                const int ei = c[i], ej = c[1 - i];
+                for (int j = 0; j < 2; j++) {
+                    const int vj = E[2 * ej + j];
+                    const V3 p = V[vj], e0 = V[E[2 * ei]], e1 = V[E[2 * ei + 1]];
+                    if (is_active(point_edge_distance(p, e0, e1, point_edge_distance_type(p, e0, e1)))) ev.push_back({ ei, vj });
+                }
+            }
+        unique_ordered(ev);
+        for (const Pair& c : ev) {
+            const int ea = c[0], p = c[1];
+            const int ea0 = E[2 * ea], ea1 = E[2 * ea + 1];
+            const double w = area ? -0.25 * ctx->edge_areas[ea] : -1.0; // / 4: double counting and PT + EE
+            const PE dtype = point_edge_distance_type(V[p], V[ea0], V[ea1]);
+            int nonmollified = 0;
+            for (const int32_t eb : ctx->ve_adj[p]) {
+                const int eb0 = E[2 * eb], eb1 = E[2 * eb + 1];
+                const int q = p == eb0 ? eb1 : eb0;
+                if (q == ea0 || q == ea1) continue;
+                const double eps_x = edge_edge_mollifier_threshold(ctx->rest[ea0], ctx->rest[ea1], ctx->rest[eb0], ctx->rest[eb1]);
+                if (edge_edge_cross_squarednorm(V[ea0], V[ea1], V[eb0], V[eb1]) >= eps_x) {
+                    nonmollified++;
+                    continue;
+                }
+                // a mollified edge-edge collision with the point-edge type lifted to the edge pair (ea, eb)
+                EE ee;
+                if (dtype == PE_P_E0) ee = p == eb0 ? EE_EA0_EB0 : EE_EA0_EB1;
+                else if (dtype == PE_P_E1) ee = p == eb0 ? EE_EA1_EB0 : EE_EA1_EB1;
+                else ee = p == eb0 ? EE_EA_EB0 : EE_EA_EB1;
+                loc[IPCB_EE][0].push_back({ ea, eb, w, eps_x, uint8_t(ee) });
+            }
+            if (nonmollified == 1) continue; // (rho - 1) = 0
+            add_ev_typed(ea, p, dtype, (nonmollified - 1) * w);
+        }
+    }
+    // ---- face-vertex candidates -> edge-vertex (:640-664) negative, -> vertex-vertex (:624-638) positive
+    if (!ctx->cand[IPCB_FV].empty()) {
+        std::vector<Pair> ev, vv;
+        for (const Pair& c : ctx->cand[IPCB_FV]) {
+            const int fi = c[0], vi = c[1];
+            for (int j = 0; j < 3; j++) {
+                const int ei = ctx->F2E[3 * fi + j];
+                const V3 p = V[vi], e0 = V[E[2 * ei]], e1 = V[E[2 * ei + 1]];
+                if (is_active(point_edge_distance(p, e0, e1, point_edge_distance_type(p, e0, e1)))) ev.push_back({ ei, vi });
+                const int vj = F[3 * fi + j];
+                if (is_active(point_point_distance(V[vi], V[vj]))) vv.push_back({ vi, vj });
+            }
+        }
+        unique_ordered(ev);
+        unique_unordered(vv);
+        for (const Pair& c : ev) { // builder.cpp:421-455
+            const int ei = c[0], vi = c[1];
+            const auto& inc = ctx->ev_adj[ei];
+            const int amt = int(inc.size()) - int(contains(inc, vi));
+            if (amt > 1) {
+                const double w = (1 - amt) * (area ? 0.25 * ctx->vertex_areas[vi] : 1.0);
+                add_ev_typed(ei, vi, point_edge_distance_type(V[vi], V[E[2 * ei]], V[E[2 * ei + 1]]), w);
+            }
+        }
+        for (const Pair& c : vv) { // builder.cpp:385-419
+            double w = 0;
+            auto add_weight = [&](int vi, int vj) {
+                if (ctx->on_boundary[vj] || contains(ctx->vv_adj[vj], vi)) return; // boundary and incident vertices are skipped
+                w += area ? 0.25 * ctx->vertex_areas[vi] : 1.0;
+            };
+            add_weight(c[0], c[1]);
+            add_weight(c[1], c[0]);
+            if (w != 0) add_vv(c[0], c[1], w);
+        }
     }
 }
 
@@ -537,6 +674,7 @@ void collisions_build(ipcb_ctx* ctx, const std::vector<V3>& V, double dhat, doub
         default: loc[IPCB_FV][t].push_back({ fi, vi, w, 0, 0 }); break;
         }
     }
+    if (flags & IPCB_SET_IMPROVED_MAX_APPROX) improved_max_approx_corrections(ctx, V, area, is_active, loc);
     for (int k = 0; k < 4; k++) {
         std::vector<Coll> all;
         for (auto& l : loc[k]) all.insert(all.end(), l.begin(), l.end());
@@ -840,6 +978,25 @@ int ipco_mesh_set(ipcb_ctx* ctx, int32_t nV, const double* rest, int32_t ld_rest
     for (int i = 0; i < nV; i++) ctx->vertex_areas[i] = vfa[i] < 0 ? (vea[i] < 0 ? 1.0 : vea[i]) : vfa[i];
     for (int i = 0; i < nE; i++)
         if (ctx->edge_areas[i] < 0) ctx->edge_areas[i] = edge_len(i);
+    // init_adjacencies (collision_mesh.cpp:247-307)
+    auto dedupe = [](std::vector<std::vector<int32_t>>& v) {
+        for (auto& a : v) {
+            std::sort(a.begin(), a.end());
+            a.erase(std::unique(a.begin(), a.end()), a.end());
+        }
+    };
+    ctx->vv_adj.assign(nV, {}), ctx->ve_adj.assign(nV, {}), ctx->ev_adj.assign(nE, {});
+    for (int i = 0; i < nE; i++) {
+        const int32_t a = ctx->E[2 * i], b = ctx->E[2 * i + 1];
+        ctx->vv_adj[a].push_back(b), ctx->vv_adj[b].push_back(a);
+        ctx->ve_adj[a].push_back(i), ctx->ve_adj[b].push_back(i);
+    }
+    for (int i = 0; i < nF; i++)
+        for (int j = 0; j < 3; j++) ctx->ev_adj[ctx->F2E[3 * i + j]].push_back(ctx->F[3 * i + (j + 2) % 3]);
+    dedupe(ctx->vv_adj), dedupe(ctx->ve_adj), dedupe(ctx->ev_adj);
+    ctx->on_boundary.assign(nV, 1); // 3D: a vertex of an edge shared by two triangles is not on the boundary (:283-292)
+    for (int i = 0; i < nE; i++)
+        if (ctx->ev_adj[i].size() >= 2) ctx->on_boundary[ctx->E[2 * i]] = ctx->on_boundary[ctx->E[2 * i + 1]] = 0;
     ctx->built = false;
     for (auto& c : ctx->cand) c.clear();
     for (auto& c : ctx->coll) c.clear();
@@ -981,8 +1138,7 @@ int ipco_collisions_append(ipcb_ctx* ctx, int32_t kind, int64_t count, const int
     if (kind == IPCB_EE && count > 0 && (!eps_x || !dtype)) return fail("edge-edge collision records need eps_x and dtype");
     for (int64_t i = 0; i < count; i++) {
         int32_t a = ids[2 * i], b = ids[2 * i + 1];
-        if (kind == IPCB_VV || kind == IPCB_EE)
-            if (a > b) std::swap(a, b);
+        if (kind == IPCB_VV && a > b) std::swap(a, b); // an edge-edge record keeps its orientation: its dtype refers to it
         ctx->appended[kind].push_back({ a, b, weight[i], kind == IPCB_EE ? eps_x[i] : 0.0, kind == IPCB_EE ? dtype[i] : uint8_t(0) });
     }
     return 0;

@@ -398,3 +398,20 @@ def test_line_search_rebuild_from_resident_candidates(cuda, oracle, scenes, name
             assert not np.isfinite(res["cuda"]["d"])
         energies.append(res["cuda"]["e"])
     assert any(e > 0 for e in energies)
+
+
+def test_unsupported_set_types_fail_loudly(cuda, scenes):
+    """CollisionSetType::IMPROVED_MAX_APPROX is restated in the CPU checker only so far: the CUDA library must refuse it
+    instead of silently building the IPC set; OGC is outside the path"""
+    V0, V1, E, F, P = _scene(scenes, "stack")
+    mesh = cuda.CollisionMesh(V0, E, F)
+    c = cuda.NormalCollisions()
+    c.set_collision_set_type(cuda.NormalCollisions.CollisionSetType.IMPROVED_MAX_APPROX)
+    with pytest.raises(RuntimeError, match="IMPROVED_MAX_APPROX"):
+        c.build(mesh, V0, P["dhat"])
+    c.set_collision_set_type(cuda.NormalCollisions.CollisionSetType.OGC)
+    with pytest.raises(NotImplementedError):
+        c.build(mesh, V0, P["dhat"])
+    c.set_collision_set_type(cuda.NormalCollisions.CollisionSetType.IPC)
+    c.build(mesh, V0, P["dhat"])
+    assert sum(c.counts()) > 0

@@ -378,3 +378,113 @@ def test_readme_quick_start(oracle):
 
 def test_ccd_kats(oracle):
     check_ccd_kats(oracle)
+
+
+# ---- CollisionSetType::IMPROVED_MAX_APPROX: restated in the oracle only so far ----------------------
+def _fan(k=6, apex=0.3):
+    """a cone of k triangles around the raised vertex 0 (interior: every spoke is shared by two triangles; the apex and
+    the spokes are convex, so their closest-point regions have a finite size and no test point sits on a type
+    boundary) + one free point"""
+    ang = 2 * np.pi * np.arange(k) / k
+    V = np.vstack([[0, 0, apex], np.c_[np.cos(ang), np.sin(ang), np.zeros(k)], [0, 0, 0]])
+    F = np.array([[0, 1 + i, 1 + (i + 1) % k] for i in range(k)], np.int32)
+    return V, F
+
+
+def test_improved_max_approx_counts_and_weights(oracle):
+    """collisions/test_normal_collisions.cpp:69-107,170-209 (12 vertex-vertex collisions on the cube for every set type;
+    6 + 1 collisions, 2 + 1 of them vertex-vertex, on the edge-vertex scene) and the defining property of the
+    convergent formulation (normal_collisions_builder.cpp:340-543): a point above an interior VERTEX of valence k is
+    counted k times by the IPC set (once per incident face) and once after the corrections (k - k + 1); above the
+    middle of an interior EDGE twice by IPC and once after the corrections (2 - 1)."""
+    T = oracle.NormalCollisions.CollisionSetType
+
+    def build(mesh, V, dhat, dmin, t, area=False):
+        c = oracle.NormalCollisions()
+        c.set_use_area_weighting(area)
+        c.set_collision_set_type(t)
+        c.build(mesh, V, dhat, dmin)
+        return c
+
+    V = np.array([[0, 0, 0], [0, 0, 1], [0, 1, 0], [0, 1, 1], [1, 0, 0], [1, 0, 1], [1, 1, 0], [1, 1, 1]], float)
+    V -= V.mean(0)
+    mesh = oracle.CollisionMesh(V)
+    for area in (False, True):
+        assert build(mesh, V, 0.25, 0.8, T.IMPROVED_MAX_APPROX, area).counts() == [12, 0, 0, 0]
+
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 0, -1], [-1, 0, 0], [0, 0, 1], [0, 1, 0], [0, 2, 0], [0, 3, 0]], float)
+    E = np.array([[0, 1], [0, 2], [0, 3], [0, 4]])
+    mesh = oracle.CollisionMesh(V, E)
+    for area in (False, True):
+        c = build(mesh, V, 0.25, 0.8, T.IMPROVED_MAX_APPROX, area)
+        assert c.counts() == [3, 4, 0, 0]
+        assert oracle.BarrierPotential(0.25, 1.0)(c, mesh, V) > 0
+        extra = dict(zip(map(tuple, c.vv_collisions.ids), c.vv_collisions.weight))[(0, 5)]
+        assert extra == (1 - 4) * (0.5 * mesh.vertex_areas()[5] if area else 1.0)  # 4 incident edges at vertex 0
+
+    k, dhat = 6, 0.1
+    V, F = _fan(k)
+    E = oracle.edges_from_faces(F)
+    p = k + 1
+    mesh = oracle.CollisionMesh(V, E, F)
+    # above the interior vertex
+    B = oracle.BarrierPotential(dhat, 1.0)
+
+    def summary(X, t):  # (counts, records, energy) of one build; a handle is valid until the next build on its mesh
+        c = build(mesh, X, dhat, 0.0, t)
+        recs = {n: (getattr(c, n + "_collisions").ids.tolist(), getattr(c, n + "_collisions").weight.tolist()) for n in ("vv", "ev", "ee", "fv")}
+        return c.counts(), recs, B(c, mesh, X)
+
+    def normal(f):
+        n = np.cross(V[f[1]] - V[f[0]], V[f[2]] - V[f[0]])
+        return n / np.linalg.norm(n)
+
+    X = V.copy()
+    X[p] = V[0] + [0.004 * dhat, 0.002 * dhat, 0.5 * dhat]  # in the apex's region, slightly off the axis
+    (n_ipc, r_ipc, e_ipc), (n_imp, r_imp, e_imp) = summary(X, T.IPC), summary(X, T.IMPROVED_MAX_APPROX)
+    assert n_ipc == [1, 0, 0, 0] and r_ipc["vv"] == ([[0, p]], [float(k)])
+    assert n_imp == [1, 0, 0, 0] and r_imp["vv"] == ([[0, p]], [1.0])
+    assert e_ipc == pytest.approx(k * e_imp, rel=1e-14)
+    # above the middle of an interior edge (spoke 0-1)
+    ridge = normal(F[0]) + normal(F[k - 1])  # spoke 0-1 is shared by the first and the last triangle
+    X[p] = 0.5 * (V[0] + V[1]) + 0.5 * dhat * ridge / np.linalg.norm(ridge) + [0, 0.003 * dhat, 0]
+    (n_ipc, r_ipc, _), (n_imp, r_imp, _) = summary(X, T.IPC), summary(X, T.IMPROVED_MAX_APPROX)
+    assert n_ipc == [0, 1, 0, 0] and r_ipc["ev"][1] == [2.0]
+    assert n_imp == [0, 1, 0, 0] and r_imp["ev"][1] == [1.0] and r_imp["ev"][0] == r_ipc["ev"][0]
+    # above the inside of a face: nothing to correct
+    X[p] = V[F[0]].mean(0) + 0.5 * dhat * normal(F[0])
+    assert summary(X, T.IPC)[0] == summary(X, T.IMPROVED_MAX_APPROX)[0] == [0, 0, 0, 1]
+
+
+def test_improved_max_approx_derivatives(oracle, scenes):
+    """potential/test_barrier_potential.cpp:34,126 run their finite-difference checks for IMPROVED_MAX_APPROX too: negative
+    weights and mollified edge-edge collisions with vertex / edge distance types go through the same potential"""
+    T = oracle.NormalCollisions.CollisionSetType
+    V0, V1, E, F, P = scenes.dense_sheet(6, 1.5)  # dhat spans 1.5 cells: vertex / edge proximity everywhere
+    dhat = P["dhat"]
+    mesh = oracle.CollisionMesh(V0, E, F)
+    for area in (False, True):
+        ipc = oracle.NormalCollisions()
+        ipc.set_use_area_weighting(area)
+        ipc.build(mesh, V0, dhat)
+        n_ipc = ipc.counts()
+        c = oracle.NormalCollisions()
+        c.set_use_area_weighting(area)
+        c.set_collision_set_type(T.IMPROVED_MAX_APPROX)
+        c.build(mesh, V0, dhat)
+        assert sum(c.counts()) > 0 and c.counts() != n_ipc  # corrections were added
+        assert (c.ee_collisions.dtype != 8).any()  # mollified edge-edge corrections with vertex / edge distance types
+        w = np.concatenate([getattr(c, k + "_collisions").weight for k in ("vv", "ev", "ee", "fv")])
+        assert (w < 0).any() and (w > 0).any()
+        B = oracle.BarrierPotential(dhat, 1.0, use_physical_barrier=area)
+        g = B.gradient(c, mesh, V0)
+        H = B.hessian(c, mesh, V0)
+        rng = np.random.default_rng(5)
+        p = rng.standard_normal(V0.shape)
+        eps = 1e-6 * dhat
+        fd_e = (B(c, mesh, V0 + eps * p) - B(c, mesh, V0 - eps * p)) / (2 * eps)
+        fd_g = (B.gradient(c, mesh, V0 + eps * p) - B.gradient(c, mesh, V0 - eps * p)) / (2 * eps)
+        assert fd_e == pytest.approx(g @ p.ravel(), rel=1e-5)
+        assert np.linalg.norm(fd_g - H @ p.ravel()) <= 1e-5 * np.linalg.norm(fd_g)
+        Hp = B.hessian(c, mesh, V0, oracle.PSDProjectionMethod.CLAMP).toarray()
+        assert np.linalg.eigvalsh(0.5 * (Hp + Hp.T)).min() >= -1e-9 * np.abs(Hp).max()
