@@ -245,3 +245,51 @@ def test_device_sharded_step_nccl(cuda):
     rows = [r["rows"] for r in results]
     assert rows[0][0] == 0 and all(rows[k][1] == rows[k + 1][0] for k in range(world - 1))
     assert sum(r["nnz"] for r in results) == results[0]["nnz_all"]  # the row blocks tile the matrix
+
+
+def _empty_worker(rank, world, port, queue):
+    """no rank finds a collision: the exchange, the merge, the balanced row blocks and the potential must cope with empty
+    sets (energy 0, zero gradient, empty Hessian) while the step size still comes from the swept candidates"""
+    try:
+        sys.path.insert(0, ROOT)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        import torch.distributed as dist
+
+        import ipctk_b200
+
+        scenes = ipctk_b200._pkg.scenes
+        sharded = __import__("importlib").import_module("ipc_toolkit_b200.sharded")
+        V0, V1, E, F, P = scenes.cloth_stack(2, 6, gap=50.0)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import pyoracle
+
+        api = pyoracle.load()
+        api.set_num_threads(2)
+        out = sharded.ShardedContactStep(api, api.CollisionMesh(V0, E, F), rank, world, dist=dist, native=False).step(V0, V1, P["dhat"])
+        one = sharded.ShardedContactStep(api, api.CollisionMesh(V0, E, F), 0, 1, native=False).step(V0, V1, P["dhat"])
+        res = dict(rank=rank, collisions=out["collisions"], energy=out["energy"], grad=float(np.abs(out["gradient"]).max()),
+                   nnz=int(out["hessian_local"].nnz), rows=out["rows"], step=(out["step"], one["step"]))
+        dist.destroy_process_group()
+        queue.put(res)
+    except Exception as e:  # pragma: no cover
+        import traceback
+
+        queue.put(dict(rank=rank, error=traceback.format_exc() + repr(e)))
+
+
+def test_two_rank_step_without_collisions_gloo(oracle):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_empty_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = _collect(q, procs)
+    for r in results:
+        assert r["collisions"] == [0, 0, 0, 0] and r["energy"] == 0.0 and r["grad"] == 0.0 and r["nnz"] == 0
+        assert 0 < r["step"][0] < 1 and r["step"][0] == pytest.approx(r["step"][1], rel=1e-3, abs=1e-6)
+    rows = [r["rows"] for r in results]
+    assert rows[0][0] == 0 and rows[0][1] == rows[1][0]
