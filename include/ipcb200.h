@@ -64,8 +64,8 @@ enum { IPCB_BOXES_FLOAT = 0, IPCB_BOXES_DOUBLE = 1 };
 
 /* flags for collisions_build (collisions/normal/normal_collisions.hpp:191-194: use_area_weighting; :29-39
  * CollisionSetType).  IPCB_SET_IMPROVED_MAX_APPROX selects CollisionSetType::IMPROVED_MAX_APPROX (the negative /
- * positive correction collisions of normal_collisions.cpp:84-128); the CPU restatement implements it, the CUDA library
- * does not yet and fails loudly when asked. */
+ * positive correction collisions of normal_collisions.cpp:84-128, normal_collisions_builder.cpp:340-543).  Not
+ * available on a sharded context (ctx_set_shard with world > 1): the call fails. */
 enum { IPCB_USE_AREA_WEIGHTING = 1, IPCB_SET_IMPROVED_MAX_APPROX = 2 };
 
 /* flags for collisions_merge: the appended builders worked on DISJOINT candidate shards (the ranks of a sharded

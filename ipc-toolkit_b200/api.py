@@ -301,8 +301,7 @@ def make_api(lib):
             return self.compute_collision_free_stepsize(mesh, vertices_t0, vertices_t1, min_distance, narrow_phase_ccd) >= 1.0
 
     class NormalCollisions:
-        """ipc::NormalCollisions — collisions/normal/normal_collisions.cpp:20-158 (IPC set type; IMPROVED_MAX_APPROX is
-        restated in the CPU checker only, the CUDA library raises for it)"""
+        """ipc::NormalCollisions — collisions/normal/normal_collisions.cpp:20-158 (IPC and IMPROVED_MAX_APPROX set types)"""
 
         class CollisionSetType(enum.IntEnum):  # normal_collisions.hpp:29-39
             IPC = 0

@@ -266,6 +266,7 @@ int ipcb_mesh_set(ipcb_ctx* ctx, int32_t nV, const double* rest, int32_t ld_rest
         IPCB_CUDA(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
         ctx->built = false;
         ctx->coll_valid = false;
+        ctx->adj_ready = false;
         for (auto& c : ctx->cand) c.count = 0;
         for (auto& c : ctx->coll) c.count = 0;
         for (auto& c : ctx->detected) c.count = 0;

@@ -15,8 +15,10 @@
 // output order canonical: sorted by (id0, id1).
 #include "ctx.cuh"
 #include "geom.cuh"
+#include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
 
 namespace ipcb {
 
@@ -259,12 +261,14 @@ static void merge_stream_enqueue(ipcb_ctx* ctx, int kind, int64_t n, cudaStream_
     IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[21 + 2 * kind], cs.head.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
 }
 
-static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4], bool disjoint = false);
+static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4], bool disjoint = false, bool typed_ee = false);
+static void improved_max_approx_corrections(ipcb_ctx* ctx, double offset_sqr, bool area, int64_t raw[4]);
 
 void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
 {
-    if (flags & IPCB_SET_IMPROVED_MAX_APPROX)
-        throw Error("CollisionSetType::IMPROVED_MAX_APPROX is not implemented in the CUDA library yet (IPC set type only)");
+    const bool improved = (flags & IPCB_SET_IMPROVED_MAX_APPROX) != 0;
+    if (improved && ctx->shard_world > 1) // the corrections need every candidate of a sub-element pair on one rank
+        throw Error("CollisionSetType::IMPROVED_MAX_APPROX is not available on a sharded context (IPC set type only)");
     cudaStream_t s = ctx->stream;
     int64_t total = 0;
     for (auto& c : ctx->cand) total += c.count;
@@ -312,8 +316,9 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
         IPCB_CUDA(cudaMemcpyAsync(ctx->pinned.p, ctx->dCounters.p + 1, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         IPCB_CUDA(cudaStreamSynchronize(s));
     }
-    const int64_t raw[4] = { ctx->pinned.p[0], ctx->pinned.p[1], ctx->pinned.p[2], ctx->pinned.p[3] };
-    merge_streams(ctx, raw);
+    int64_t raw[4] = { ctx->pinned.p[0], ctx->pinned.p[1], ctx->pinned.p[2], ctx->pinned.p[3] };
+    if (improved) improved_max_approx_corrections(ctx, (dmin + dhat) * (dmin + dhat), (flags & IPCB_USE_AREA_WEIGHTING) != 0, raw);
+    merge_streams(ctx, raw, false, improved);
 }
 
 // records -> final arrays without sorting or merging (every record is kept)
@@ -332,7 +337,8 @@ __global__ void k_keep_all(int64_t n, const unsigned long long* __restrict__ key
 // disjoint: the builders come from disjoint candidate shards, so edge-edge and face-vertex records are unique across
 // builders and only VV / EV records need uniting: EE / FV are concatenated in builder order (each builder's records
 // are sorted; the canonical global order is restored on demand by collisions_sort)
-static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4], bool disjoint)
+static void merge_ee_typed_enqueue(ipcb_ctx* ctx, int64_t n, cudaStream_t s);
+static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4], bool disjoint, bool typed_ee)
 {
     cudaStream_t s = ctx->stream;
     Stage st(ctx, "merge_collisions");
@@ -352,6 +358,8 @@ static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4], bool disjoint)
             k_keep_all<<<grid_for(n, 256), 256, 0, where[k]>>>(n, cs.key_raw.p, cs.w_raw.p, k == IPCB_EE ? cs.eps_raw.p : nullptr, cs.dt_raw.p,
                                                              cs.ids.p, cs.w.p, cs.eps.p, cs.dtype.p);
             ctx->launches++;
+        } else if (typed_ee && k == IPCB_EE) {
+            merge_ee_typed_enqueue(ctx, raw[k], where[k]);
         } else {
             merge_stream_enqueue(ctx, k, raw[k], where[k]);
         }
@@ -531,6 +539,402 @@ double collisions_min_distance(ipcb_ctx* ctx)
     double d;
     memcpy(&d, &bits, sizeof d);
     return d;
+}
+
+
+// =====================================================================================================================
+// CollisionSetType::IMPROVED_MAX_APPROX (normal_collisions.cpp:84-128).  After the IPC classification pass:
+//  1. sub-element candidates are derived from the element candidates (candidates.cpp:584-695): the ACTIVE
+//     vertex-vertex / edge-vertex pairs of every edge-vertex, edge-edge and face-vertex candidate — emitted as 64-bit
+//     keys, radix-sorted and made unique (the reference sorts and std::unique's them);
+//  2. one thread per unique pair appends its NEGATIVE / POSITIVE correction records to the same raw streams the
+//     classification filled (builder.cpp:340-543), reading the mesh adjacencies as CSR;
+//  3. the usual merge follows; edge-edge records are merged on (unordered edge pair, distance type) and keep their
+//     orientation (collisions/normal/edge_edge.cpp:123-142): correction collisions carry vertex / edge distance types
+//     and are not (min, max)-ordered.
+struct AdjView {
+    const int *vv_off, *vv, *ve_off, *ve, *ev_off, *ev;
+    const unsigned char* boundary;
+};
+__device__ inline bool csr_contains(const int* __restrict__ off, const int* __restrict__ val, int row, int x)
+{
+    int lo = off[row], hi = off[row + 1];
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int v = val[mid];
+        if (v == x) return true;
+        if (v < x) lo = mid + 1;
+        else hi = mid;
+    }
+    return false;
+}
+// typed edge-edge key: [min edge : 28][max edge : 28][distance type : 4][stored as (max, min) : 1]
+__device__ inline unsigned long long ee_typed_key(int a, int b, int dt)
+{
+    const unsigned long long lo = unsigned(min(a, b)), hi = unsigned(max(a, b));
+    return (lo << 33) | (hi << 5) | ((unsigned long long)(dt & 15) << 1) | (unsigned long long)(a > b);
+}
+__device__ inline void emit_key(bool pred, unsigned long long key, unsigned long long* __restrict__ out, unsigned long long* counter)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, pred);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(counter, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (pred) out[base + __popc(m & ((1u << lane) - 1))] = key;
+}
+__device__ inline double active_point_edge(const double4* X, int p, int2 e)
+{
+    const d3 x[3] = { ld3(X, p), ld3(X, e.x), ld3(X, e.y) };
+    return sub_value(sub_point_edge(point_edge_type(x[0], x[1], x[2])), x);
+}
+// edge-edge candidates -> edge-vertex (candidates.cpp:666-695)
+__global__ void __launch_bounds__(256) k_sub_from_ee(int64_t n, const int2* __restrict__ cand, const int2* __restrict__ E, const double4* X,
+                                                     double offset_sqr, unsigned long long* out_ev, unsigned long long* cnt_ev)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const int2 c = valid ? cand[i] : make_int2(0, 0);
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        bool on = false;
+        unsigned long long key = 0;
+        if (valid) {
+            const int ei = (s >> 1) ? c.y : c.x, ej = (s >> 1) ? c.x : c.y;
+            const int2 f = __ldg(E + ej);
+            const int vj = (s & 1) ? f.y : f.x;
+            on = active_point_edge(X, vj, __ldg(E + ei)) < offset_sqr;
+            key = mkkey(ei, vj);
+        }
+        emit_key(on, key, out_ev, cnt_ev);
+    }
+}
+// face-vertex candidates -> edge-vertex (:640-664) and vertex-vertex (:624-638)
+__global__ void __launch_bounds__(256) k_sub_from_fv(int64_t n, const int2* __restrict__ cand, const int2* __restrict__ E, const int4* __restrict__ F,
+                                                     const int4* __restrict__ F2E, const double4* X, double offset_sqr, unsigned long long* out_ev,
+                                                     unsigned long long* cnt_ev, unsigned long long* out_vv, unsigned long long* cnt_vv)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const int2 c = valid ? cand[i] : make_int2(0, 0);
+    int4 f = make_int4(0, 0, 0, 0), fe = f;
+    if (valid) f = __ldg(F + c.x), fe = __ldg(F2E + c.x);
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        bool on_ev = false, on_vv = false;
+        unsigned long long kev = 0, kvv = 0;
+        if (valid) {
+            const int ei = j == 0 ? fe.x : (j == 1 ? fe.y : fe.z), vj = j == 0 ? f.x : (j == 1 ? f.y : f.z);
+            on_ev = active_point_edge(X, c.y, __ldg(E + ei)) < offset_sqr;
+            kev = mkkey(ei, c.y);
+            on_vv = pp_dist(ld3(X, c.y), ld3(X, vj)) < offset_sqr;
+            kvv = mkkey(min(c.y, vj), max(c.y, vj));
+        }
+        emit_key(on_ev, kev, out_ev, cnt_ev);
+        emit_key(on_vv, kvv, out_vv, cnt_vv);
+    }
+}
+// edge-vertex candidates -> vertex-vertex (:584-622)
+__global__ void __launch_bounds__(256) k_sub_from_ev(int64_t n, const int2* __restrict__ cand, const int2* __restrict__ E, const double4* X,
+                                                     double offset_sqr, unsigned long long* out_vv, unsigned long long* cnt_vv)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const int2 c = valid ? cand[i] : make_int2(0, 0);
+    const int2 e = valid ? __ldg(E + c.x) : make_int2(0, 0);
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const int vj = j ? e.y : e.x;
+        const bool on = valid && pp_dist(ld3(X, c.y), ld3(X, vj)) < offset_sqr;
+        emit_key(on, mkkey(min(c.y, vj), max(c.y, vj)), out_vv, cnt_vv);
+    }
+}
+
+struct CorrOut { // raw streams + their device counters (the ones the classification advanced)
+    unsigned long long *key_vv, *key_ev, *key_ee;
+    double *w_vv, *w_ev, *w_ee, *eps_ee;
+    unsigned char* dt_ee;
+    unsigned long long *cnt_vv, *cnt_ev, *cnt_ee;
+};
+__device__ inline void corr_add_vv(const CorrOut& o, int vi, int vj, double w)
+{
+    const unsigned long long p = atomicAdd(o.cnt_vv, 1ull);
+    o.key_vv[p] = mkkey(min(vi, vj), max(vi, vj));
+    o.w_vv[p] = w;
+}
+__device__ inline void corr_add_ev(const CorrOut& o, int ei, int vi, double w)
+{
+    const unsigned long long p = atomicAdd(o.cnt_ev, 1ull);
+    o.key_ev[p] = mkkey(ei, vi);
+    o.w_ev[p] = w;
+}
+// add_edge_vertex_collision(mesh, candidate, dtype, weight) (builder.cpp:108-138): reduced to the closest feature
+__device__ inline void corr_add_ev_typed(const CorrOut& o, int ei, int2 e, int vi, int t, double w)
+{
+    if (t == PE_E0) corr_add_vv(o, vi, e.x, w);
+    else if (t == PE_E1) corr_add_vv(o, vi, e.y, w);
+    else corr_add_ev(o, ei, vi, w);
+}
+// builder.cpp:340-383 (positive = 0: candidates from edge-vertex pairs, negative weights) and :385-419 (positive = 1:
+// candidates from face-vertex pairs, positive weights)
+__global__ void k_corr_vv(int64_t n, const unsigned long long* __restrict__ uniq, AdjView A, const double* __restrict__ vArea, int area,
+                          int positive, CorrOut o)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = int(uniq[i] >> 32), b = int(uniq[i] & 0xffffffffu);
+    double w = 0;
+#pragma unroll
+    for (int dir = 0; dir < 2; dir++) {
+        const int vi = dir ? b : a, vj = dir ? a : b;
+        const bool incident = csr_contains(A.vv_off, A.vv, vj, vi);
+        if (positive) {
+            if (A.boundary[vj] || incident) continue; // boundary and incident vertices are skipped
+            w += area ? 0.25 * vArea[vi] : 1.0;
+        } else {
+            const int amt = (A.vv_off[vj + 1] - A.vv_off[vj]) - int(incident);
+            if (amt > 1) w += (1 - amt) * (area ? 0.5 * vArea[vi] : 1.0);
+        }
+    }
+    if (w != 0.0) corr_add_vv(o, a, b, w);
+}
+// builder.cpp:421-455: edge-vertex pairs of face-vertex candidates, negative weights
+__global__ void k_corr_ev_from_fv(int64_t n, const unsigned long long* __restrict__ uniq, AdjView A, const int2* __restrict__ E, const double4* X,
+                                  const double* __restrict__ vArea, int area, CorrOut o)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ei = int(uniq[i] >> 32), vi = int(uniq[i] & 0xffffffffu);
+    const int amt = (A.ev_off[ei + 1] - A.ev_off[ei]) - int(csr_contains(A.ev_off, A.ev, ei, vi));
+    if (amt <= 1) return;
+    const double w = (1 - amt) * (area ? 0.25 * vArea[vi] : 1.0);
+    const int2 e = __ldg(E + ei);
+    corr_add_ev_typed(o, ei, e, vi, point_edge_type(ld3(X, vi), ld3(X, e.x), ld3(X, e.y)), w);
+}
+// builder.cpp:457-543: edge-vertex pairs (ea, p) of edge-edge candidates: a negative mollified edge-edge collision for
+// every mollified edge at p, and the edge-vertex collision itself with weight (#non-mollified edges at p - 1) * w
+__global__ void k_corr_ev_from_ee(int64_t n, const unsigned long long* __restrict__ uniq, AdjView A, const int2* __restrict__ E, const double4* X,
+                                  const double4* rest, const double* __restrict__ eArea, int area, CorrOut o)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ea = int(uniq[i] >> 32), p = int(uniq[i] & 0xffffffffu);
+    const int2 e = __ldg(E + ea);
+    const double w = area ? -0.25 * eArea[ea] : -1.0;
+    const d3 a0 = ld3(X, e.x), a1 = ld3(X, e.y);
+    const int t = point_edge_type(ld3(X, p), a0, a1);
+    int nonmollified = 0;
+    for (int q = A.ve_off[p]; q < A.ve_off[p + 1]; q++) {
+        const int eb = A.ve[q];
+        const int2 f = __ldg(E + eb);
+        const int other = p == f.x ? f.y : f.x;
+        if (other == e.x || other == e.y) continue;
+        const double eps = moll_threshold(ld3(rest, e.x), ld3(rest, e.y), ld3(rest, f.x), ld3(rest, f.y));
+        const double cr = sqn(cross(a1 - a0, ld3(X, f.y) - ld3(X, f.x)));
+        if (cr >= eps) {
+            nonmollified++;
+            continue;
+        }
+        const int first = p == f.x; // is p the first vertex of eb
+        const int dt = t == PE_E0 ? (first ? EE_A0B0 : EE_A0B1) : (t == PE_E1 ? (first ? EE_A1B0 : EE_A1B1) : (first ? EE_AB0 : EE_AB1));
+        const unsigned long long pos = atomicAdd(o.cnt_ee, 1ull);
+        o.key_ee[pos] = ee_typed_key(ea, eb, dt);
+        o.w_ee[pos] = w;
+        o.eps_ee[pos] = eps;
+        o.dt_ee[pos] = (unsigned char)dt;
+    }
+    if (nonmollified == 1) return; // (rho - 1) = 0
+    corr_add_ev_typed(o, ea, e, p, t, (nonmollified - 1) * w);
+}
+// the classification wrote plain (ea, eb) keys: retype them
+__global__ void k_retype_ee_keys(int64_t n, unsigned long long* __restrict__ key, const unsigned char* __restrict__ dt)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = key[i];
+    key[i] = ee_typed_key(int(k >> 32), int(k & 0xffffffffu), dt[i]);
+}
+// runs of equal (edge pair, distance type): bit 0 (the orientation) only orders the records of a run
+__global__ void k_runs_ee_typed(int64_t n, const unsigned long long* __restrict__ key, const int* __restrict__ idx,
+                                const double* __restrict__ w_raw, int* __restrict__ keep, double* __restrict__ wsum)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = key[i] >> 1;
+    if (i > 0 && (key[i - 1] >> 1) == k) {
+        keep[i] = 0;
+        return;
+    }
+    double s = 0;
+    for (int64_t j = i; j < n && (key[j] >> 1) == k; j++) s += w_raw[idx[j]];
+    wsum[i] = s;
+    keep[i] = s != 0.0;
+}
+__global__ void k_emit_ee_typed(int64_t n, const unsigned long long* __restrict__ key, const int* __restrict__ idx, const int* __restrict__ keep,
+                                const int* __restrict__ pos, const double* __restrict__ wsum, const double* __restrict__ eps_raw,
+                                int2* __restrict__ ids, double* __restrict__ w, double* __restrict__ eps, unsigned char* __restrict__ dt)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n || !keep[i]) return;
+    const int p = pos[i];
+    const unsigned long long k = key[i];
+    const int lo = int(k >> 33), hi = int((k >> 5) & 0xfffffffull);
+    ids[p] = (k & 1ull) ? make_int2(hi, lo) : make_int2(lo, hi);
+    w[p] = wsum[i];
+    eps[p] = eps_raw[idx[i]];
+    dt[p] = (unsigned char)((k >> 1) & 15ull);
+}
+static void merge_ee_typed_enqueue(ipcb_ctx* ctx, int64_t n, cudaStream_t s)
+{
+    CollisionSet& cs = ctx->coll[IPCB_EE];
+    cs.count = 0;
+    if (n == 0) return;
+    cs.idx_raw.reserve(n), cs.idx_sorted.reserve(n), cs.key_sorted.reserve(n), cs.head.reserve(n), cs.pos.reserve(n + 1);
+    cs.wsum.reserve(n);
+    k_iota<<<grid_for(n, 256), 256, 0, s>>>(n, cs.idx_raw.p);
+    size_t bytes = 0, bytes2 = 0;
+    const int bits = 61;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, cs.key_raw.p, cs.key_sorted.p, cs.idx_raw.p, cs.idx_sorted.p, n, 0, bits, s);
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes2, cs.head.p, cs.pos.p, n, s);
+    cs.cubtmp.reserve(std::max(bytes, bytes2));
+    cub::DeviceRadixSort::SortPairs(cs.cubtmp.p, bytes, cs.key_raw.p, cs.key_sorted.p, cs.idx_raw.p, cs.idx_sorted.p, n, 0, bits, s);
+    k_runs_ee_typed<<<grid_for(n, 256), 256, 0, s>>>(n, cs.key_sorted.p, cs.idx_sorted.p, cs.w_raw.p, cs.head.p, cs.wsum.p);
+    cub::DeviceScan::ExclusiveSum(cs.cubtmp.p, bytes2, cs.head.p, cs.pos.p, n, s);
+    cs.ids.reserve(n), cs.w.reserve(n), cs.eps.reserve(n), cs.dtype.reserve(n);
+    k_emit_ee_typed<<<grid_for(n, 256), 256, 0, s>>>(n, cs.key_sorted.p, cs.idx_sorted.p, cs.head.p, cs.pos.p, cs.wsum.p, cs.eps_raw.p, cs.ids.p,
+                                                     cs.w.p, cs.eps.p, cs.dtype.p);
+    ctx->launches += 5 + (bits + 7) / 8 + 4;
+    IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[20 + 2 * IPCB_EE], cs.pos.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[21 + 2 * IPCB_EE], cs.head.p + (n - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+}
+
+// init_adjacencies (collision_mesh.cpp:247-307) on the host, once per mesh, mirrored as CSR
+static void ensure_adjacency(ipcb_ctx* ctx)
+{
+    if (ctx->adj_ready) return;
+    const int nV = ctx->nV, nE = ctx->nE, nF = ctx->nF;
+    std::vector<std::vector<int>> vv(nV), ve(nV), ev(nE);
+    for (int i = 0; i < nE; i++) {
+        const int a = ctx->hE[2 * size_t(i)], b = ctx->hE[2 * size_t(i) + 1];
+        vv[a].push_back(b), vv[b].push_back(a);
+        ve[a].push_back(i), ve[b].push_back(i);
+    }
+    for (int i = 0; i < nF; i++)
+        for (int j = 0; j < 3; j++) ev[ctx->hF2E[3 * size_t(i) + j]].push_back(ctx->hF[3 * size_t(i) + (j + 2) % 3]);
+    auto flatten = [&](std::vector<std::vector<int>>& rows, Buf<int>& off, Buf<int>& val, int* max_len) {
+        std::vector<int> o(rows.size() + 1, 0), v;
+        for (size_t r = 0; r < rows.size(); r++) {
+            auto& a = rows[r];
+            std::sort(a.begin(), a.end());
+            a.erase(std::unique(a.begin(), a.end()), a.end());
+            o[r + 1] = o[r] + int(a.size());
+            v.insert(v.end(), a.begin(), a.end());
+            if (max_len) *max_len = std::max(*max_len, int(a.size()));
+        }
+        off.reserve(o.size()), val.reserve(std::max<size_t>(v.size(), 1));
+        IPCB_CUDA(cudaMemcpyAsync(off.p, o.data(), sizeof(int) * o.size(), cudaMemcpyHostToDevice, ctx->stream));
+        if (!v.empty()) IPCB_CUDA(cudaMemcpyAsync(val.p, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice, ctx->stream));
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream)); // the host vectors go out of scope
+    };
+    ctx->adj_max_ve = 0;
+    flatten(vv, ctx->adjVVoff, ctx->adjVV, nullptr);
+    flatten(ve, ctx->adjVEoff, ctx->adjVE, &ctx->adj_max_ve);
+    flatten(ev, ctx->adjEVoff, ctx->adjEV, nullptr);
+    std::vector<unsigned char> boundary(std::max(nV, 1), 1); // a vertex of an edge shared by two triangles is interior (:283-292)
+    for (int i = 0; i < nE; i++)
+        if (ev[i].size() >= 2) boundary[ctx->hE[2 * size_t(i)]] = boundary[ctx->hE[2 * size_t(i) + 1]] = 0;
+    ctx->adjBoundary.reserve(boundary.size());
+    IPCB_CUDA(cudaMemcpyAsync(ctx->adjBoundary.p, boundary.data(), boundary.size(), cudaMemcpyHostToDevice, ctx->stream));
+    IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->adj_ready = true;
+}
+
+// sort + unique of `n` keys in ctx->subkey -> out; returns the number of unique keys (host)
+static int64_t unique_keys(ipcb_ctx* ctx, int64_t n, Buf<unsigned long long>& out)
+{
+    if (n == 0) return 0;
+    cudaStream_t s = ctx->stream;
+    ctx->subkey_sorted.reserve(n), out.reserve(n);
+    size_t b1 = 0, b2 = 0;
+    unsigned long long* d_num = ctx->dCounters.p + 28;
+    cub::DeviceRadixSort::SortKeys(nullptr, b1, ctx->subkey.p, ctx->subkey_sorted.p, n, 0, 64, s);
+    cub::DeviceSelect::Unique(nullptr, b2, ctx->subkey_sorted.p, out.p, reinterpret_cast<long long*>(d_num), n, s);
+    ctx->cubtmp.reserve(std::max(b1, b2) + 256);
+    cub::DeviceRadixSort::SortKeys(ctx->cubtmp.p, b1, ctx->subkey.p, ctx->subkey_sorted.p, n, 0, 64, s);
+    cub::DeviceSelect::Unique(ctx->cubtmp.p, b2, ctx->subkey_sorted.p, out.p, reinterpret_cast<long long*>(d_num), n, s);
+    ctx->launches += 12;
+    long long h = 0;
+    IPCB_CUDA(cudaMemcpyAsync(&h, d_num, sizeof h, cudaMemcpyDeviceToHost, s));
+    IPCB_CUDA(cudaStreamSynchronize(s));
+    return int64_t(h);
+}
+
+static void improved_max_approx_corrections(ipcb_ctx* ctx, double offset_sqr, bool area, int64_t raw[4])
+{
+    Stage st(ctx, "improved_max_approx");
+    cudaStream_t s = ctx->stream;
+    if (ctx->nE >= (1 << 28)) throw Error("IMPROVED_MAX_APPROX: more than 2^28 edges");
+    ensure_adjacency(ctx);
+    const AdjView A { ctx->adjVVoff.p, ctx->adjVV.p, ctx->adjVEoff.p, ctx->adjVE.p, ctx->adjEVoff.p, ctx->adjEV.p, ctx->adjBoundary.p };
+    const int64_t nev = ctx->cand[IPCB_EV].count, nee = ctx->cand[IPCB_EE].count, nfv = ctx->cand[IPCB_FV].count;
+    unsigned long long* cnt = ctx->dCounters.p + 29; // [0]: keys of the current list, [1]: second list of the face-vertex pass
+    auto count_of = [&](int slot) {
+        unsigned long long h = 0;
+        IPCB_CUDA(cudaMemcpyAsync(&h, cnt + slot, sizeof h, cudaMemcpyDeviceToHost, s));
+        IPCB_CUDA(cudaStreamSynchronize(s));
+        return int64_t(h);
+    };
+    // ---- 1. sub-element candidates, unique: [0] VV of EV candidates, [1] EV of EE candidates, [2] EV and [3] VV of FV candidates
+    int64_t nu[4] = { 0, 0, 0, 0 };
+    if (nev) {
+        ctx->subkey.reserve(2 * nev);
+        IPCB_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), s));
+        k_sub_from_ev<<<grid_for(nev, 256), 256, 0, s>>>(nev, ctx->cand[IPCB_EV].pairs.p, ctx->dE.p, ctx->X0.p, offset_sqr, ctx->subkey.p, cnt);
+        nu[0] = unique_keys(ctx, count_of(0), ctx->subuniq[0]);
+    }
+    if (nee) {
+        ctx->subkey.reserve(4 * nee);
+        IPCB_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), s));
+        k_sub_from_ee<<<grid_for(nee, 256), 256, 0, s>>>(nee, ctx->cand[IPCB_EE].pairs.p, ctx->dE.p, ctx->X0.p, offset_sqr, ctx->subkey.p, cnt);
+        nu[1] = unique_keys(ctx, count_of(0), ctx->subuniq[1]);
+    }
+    if (nfv) {
+        ctx->subkey.reserve(6 * nfv); // edge-vertex keys in the first half, vertex-vertex keys in the second
+        IPCB_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), s));
+        unsigned long long* second = ctx->subkey.p + 3 * nfv;
+        k_sub_from_fv<<<grid_for(nfv, 256), 256, 0, s>>>(nfv, ctx->cand[IPCB_FV].pairs.p, ctx->dE.p, ctx->dF.p, ctx->dF2E.p, ctx->X0.p, offset_sqr,
+                                                        ctx->subkey.p, cnt, second, cnt + 1);
+        const int64_t n_ev = count_of(0), n_vv = count_of(1);
+        nu[2] = unique_keys(ctx, n_ev, ctx->subuniq[2]);
+        if (n_vv) { // move the second list to the front of the key buffer for the sort
+            IPCB_CUDA(cudaMemcpyAsync(ctx->subkey.p, second, sizeof(unsigned long long) * n_vv, cudaMemcpyDeviceToDevice, s));
+            nu[3] = unique_keys(ctx, n_vv, ctx->subuniq[3]);
+        }
+    }
+    ctx->launches += 3;
+    IPCB_CUDA(cudaGetLastError());
+    // ---- 2. room for the correction records behind the classification's records
+    const int64_t more_vv = nu[0] + nu[1] + nu[2] + nu[3], more_ev = nu[1] + nu[2], more_ee = nu[1] * int64_t(std::max(ctx->adj_max_ve, 1));
+    CollisionSet &vv = ctx->coll[IPCB_VV], &ev = ctx->coll[IPCB_EV], &ee = ctx->coll[IPCB_EE];
+    vv.key_raw.reserve_keep(raw[IPCB_VV] + more_vv, raw[IPCB_VV], s), vv.w_raw.reserve_keep(raw[IPCB_VV] + more_vv, raw[IPCB_VV], s);
+    ev.key_raw.reserve_keep(raw[IPCB_EV] + more_ev, raw[IPCB_EV], s), ev.w_raw.reserve_keep(raw[IPCB_EV] + more_ev, raw[IPCB_EV], s);
+    ee.key_raw.reserve_keep(raw[IPCB_EE] + more_ee, raw[IPCB_EE], s), ee.w_raw.reserve_keep(raw[IPCB_EE] + more_ee, raw[IPCB_EE], s);
+    ee.eps_raw.reserve_keep(raw[IPCB_EE] + more_ee, raw[IPCB_EE], s), ee.dt_raw.reserve_keep(raw[IPCB_EE] + more_ee, raw[IPCB_EE], s);
+    if (raw[IPCB_EE]) k_retype_ee_keys<<<grid_for(raw[IPCB_EE], 256), 256, 0, s>>>(raw[IPCB_EE], ee.key_raw.p, ee.dt_raw.p);
+    // ---- 3. corrections (the device counters 1 + kind still hold the raw counts of the classification)
+    const CorrOut o { vv.key_raw.p, ev.key_raw.p, ee.key_raw.p, vv.w_raw.p, ev.w_raw.p, ee.w_raw.p, ee.eps_raw.p, ee.dt_raw.p,
+                      ctx->dCounters.p + 1 + IPCB_VV, ctx->dCounters.p + 1 + IPCB_EV, ctx->dCounters.p + 1 + IPCB_EE };
+    const int ar = area ? 1 : 0;
+    if (nu[0]) k_corr_vv<<<grid_for(nu[0], 256), 256, 0, s>>>(nu[0], ctx->subuniq[0].p, A, ctx->dVArea.p, ar, 0, o);
+    if (nu[1]) k_corr_ev_from_ee<<<grid_for(nu[1], 256), 256, 0, s>>>(nu[1], ctx->subuniq[1].p, A, ctx->dE.p, ctx->X0.p, ctx->dRest.p, ctx->dEArea.p, ar, o);
+    if (nu[2]) k_corr_ev_from_fv<<<grid_for(nu[2], 256), 256, 0, s>>>(nu[2], ctx->subuniq[2].p, A, ctx->dE.p, ctx->X0.p, ctx->dVArea.p, ar, o);
+    if (nu[3]) k_corr_vv<<<grid_for(nu[3], 256), 256, 0, s>>>(nu[3], ctx->subuniq[3].p, A, ctx->dVArea.p, ar, 1, o);
+    ctx->launches += 5;
+    IPCB_CUDA(cudaGetLastError());
+    IPCB_CUDA(cudaMemcpyAsync(ctx->pinned.p, ctx->dCounters.p + 1, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    IPCB_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < 4; k++) raw[k] = ctx->pinned.p[k];
 }
 
 } // namespace ipcb

@@ -137,6 +137,13 @@ struct ipcb_ctx {
     ipcb::CollisionSet coll[4];
     double dmin = 0;
     bool coll_valid = false;
+    // IMPROVED_MAX_APPROX: adjacency tables (collision_mesh.cpp:247-307) as CSR, built on first use;
+    // sub-element candidate keys
+    bool adj_ready = false;
+    int adj_max_ve = 0; // largest number of edges at a vertex
+    ipcb::Buf<int> adjVVoff, adjVV, adjVEoff, adjVE, adjEVoff, adjEV;
+    ipcb::Buf<unsigned char> adjBoundary;
+    ipcb::Buf<unsigned long long> subkey, subkey_sorted, subuniq[4];
 
     // ---- potential
     ipcb::Buf<double> dScalar; // small device scalars (energy, toi, ...)

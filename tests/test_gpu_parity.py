@@ -401,17 +401,19 @@ def test_line_search_rebuild_from_resident_candidates(cuda, oracle, scenes, name
 
 
 def test_unsupported_set_types_fail_loudly(cuda, scenes):
-    """CollisionSetType::IMPROVED_MAX_APPROX is restated in the CPU checker only so far: the CUDA library must refuse it
-    instead of silently building the IPC set; OGC is outside the path"""
+    """OGC is outside the path; IMPROVED_MAX_APPROX needs all candidates of a sub-element pair on one rank, so a sharded
+    context must refuse it instead of silently building something else"""
     V0, V1, E, F, P = _scene(scenes, "stack")
     mesh = cuda.CollisionMesh(V0, E, F)
     c = cuda.NormalCollisions()
-    c.set_collision_set_type(cuda.NormalCollisions.CollisionSetType.IMPROVED_MAX_APPROX)
-    with pytest.raises(RuntimeError, match="IMPROVED_MAX_APPROX"):
-        c.build(mesh, V0, P["dhat"])
     c.set_collision_set_type(cuda.NormalCollisions.CollisionSetType.OGC)
     with pytest.raises(NotImplementedError):
         c.build(mesh, V0, P["dhat"])
+    cuda.lib.check(cuda.lib.ctx_set_shard(mesh._ctx, 0, 2))
+    c.set_collision_set_type(cuda.NormalCollisions.CollisionSetType.IMPROVED_MAX_APPROX)
+    with pytest.raises(RuntimeError, match="IMPROVED_MAX_APPROX"):
+        c.build(mesh, V0, P["dhat"])
+    cuda.lib.check(cuda.lib.ctx_set_shard(mesh._ctx, 0, 1))
     c.set_collision_set_type(cuda.NormalCollisions.CollisionSetType.IPC)
     c.build(mesh, V0, P["dhat"])
     assert sum(c.counts()) > 0

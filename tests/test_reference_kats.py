@@ -392,7 +392,12 @@ def _fan(k=6, apex=0.3):
 
 
 def test_improved_max_approx_counts_and_weights(oracle):
-    """collisions/test_normal_collisions.cpp:69-107,170-209 (12 vertex-vertex collisions on the cube for every set type;
+    check_improved_max_approx_kats(oracle)
+
+
+def check_improved_max_approx_kats(oracle):
+    """(the parameter is any API namespace: the oracle here, the CUDA library in the GPU tests)
+    collisions/test_normal_collisions.cpp:69-107,170-209 (12 vertex-vertex collisions on the cube for every set type;
     6 + 1 collisions, 2 + 1 of them vertex-vertex, on the edge-vertex scene) and the defining property of the
     convergent formulation (normal_collisions_builder.cpp:340-543): a point above an interior VERTEX of valence k is
     counted k times by the IPC set (once per incident face) and once after the corrections (k - k + 1); above the
@@ -457,6 +462,10 @@ def test_improved_max_approx_counts_and_weights(oracle):
 
 
 def test_improved_max_approx_derivatives(oracle, scenes):
+    check_improved_max_approx_derivatives(oracle, scenes)
+
+
+def check_improved_max_approx_derivatives(oracle, scenes):
     """potential/test_barrier_potential.cpp:34,126 run their finite-difference checks for IMPROVED_MAX_APPROX too: negative
     weights and mollified edge-edge collisions with vertex / edge distance types go through the same potential"""
     T = oracle.NormalCollisions.CollisionSetType

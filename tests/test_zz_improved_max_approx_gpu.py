@@ -1,0 +1,73 @@
+"""CollisionSetType::IMPROVED_MAX_APPROX on the CUDA path against the oracle.
+
+The CUDA side of this set type (`collisions.cu`: sub-element candidates, correction kernels, typed edge-edge merge) was
+written after the round's GPU budget had been used up: it compiles, but it has NOT run on hardware yet.  The tests are
+therefore marked xfail(strict=False) — they report XPASS if the code is right and cannot turn the suite red if it is not
+— and the file sorts last so that nothing runs after it in the same process.  Remove the marker once they pass.
+The oracle side is pinned in tests/test_reference_kats.py (CPU suite).
+"""
+import numpy as np
+import pytest
+
+import test_reference_kats as rk
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(reason="CUDA IMPROVED_MAX_APPROX not yet validated on hardware (written after the GPU budget ended)", strict=False)]
+
+RTOL = 1e-10
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    n = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / n if n > 0 else np.linalg.norm(a)
+
+
+def test_reference_kats_and_convergent_weights(cuda):
+    rk.check_improved_max_approx_kats(cuda)
+
+
+def test_derivatives(cuda, scenes):
+    rk.check_improved_max_approx_derivatives(cuda, scenes)
+
+
+@pytest.mark.parametrize("name", ["stack", "drape", "c1", "soup", "dense"])
+@pytest.mark.parametrize("area", [False, True])
+def test_parity_with_the_oracle(cuda, oracle, scenes, name, area):
+    V0, V1, E, F, P = {
+        "stack": lambda: scenes.cloth_stack(3, 30),
+        "drape": lambda: scenes.cloth_on_sphere(48, 24, drape=True),
+        "c1": lambda: scenes.cloth_on_sphere(64, 32),
+        "soup": lambda: scenes.random_soup(150, seed=7),
+        "dense": lambda: scenes.dense_sheet(10, 2.0),
+    }[name]()
+    dhat = P["dhat"]
+    X = V0 + 0.02 * dhat * np.sin(np.arange(V0.size).reshape(V0.shape))
+    res = {}
+    for key, api in (("cuda", cuda), ("oracle", oracle)):
+        mesh = api.CollisionMesh(V0, E, F)
+        c = api.NormalCollisions()
+        c.set_use_area_weighting(area)
+        c.set_collision_set_type(api.NormalCollisions.CollisionSetType.IMPROVED_MAX_APPROX)
+        c.build(mesh, V0, dhat)
+        sets = [getattr(c, k + "_collisions") for k in ("vv", "ev", "ee", "fv")]
+        B = api.BarrierPotential(dhat, 1.0, use_physical_barrier=area)
+        res[key] = dict(sets=sets, e=B(c, mesh, X), g=B.gradient(c, mesh, X), h0=B.hessian(c, mesh, X),
+                        h1=B.hessian(c, mesh, X, api.PSDProjectionMethod.CLAMP))
+    a, b = res["cuda"], res["oracle"]
+    assert sum(len(s.ids) for s in b["sets"]) > 0
+    for kind, (sa, sb) in enumerate(zip(a["sets"], b["sets"])):
+        # with area weighting, corrections that cancel a collision exactly in one summation order may leave a weight of a
+        # few ulps in another: compare the records whose weight is not numerically zero
+        scale = max(np.abs(sb.weight).max(), 1e-300) if len(sb.weight) else 1.0
+        ka, kb = np.abs(sa.weight) > 1e-12 * scale, np.abs(sb.weight) > 1e-12 * scale
+        assert np.array_equal(sa.ids[ka], sb.ids[kb]), "kind %d" % kind
+        assert np.array_equal(sa.dtype[ka], sb.dtype[kb]) and np.array_equal(sa.eps_x[ka], sb.eps_x[kb])
+        assert relerr(sa.weight[ka], sb.weight[kb]) <= 1e-12
+    assert abs(a["e"] - b["e"]) <= RTOL * abs(b["e"])
+    assert relerr(a["g"], b["g"]) <= RTOL
+    for h in ("h0", "h1"):
+        A, Bm = a[h], b[h]
+        D = A - Bm
+        assert np.sqrt(D.multiply(D).sum()) <= RTOL * np.sqrt(Bm.multiply(Bm).sum()), h
+        assert np.array_equal(A.indptr, Bm.indptr) and np.array_equal(A.indices, Bm.indices), h + ": sparsity pattern differs"
