@@ -175,6 +175,7 @@ template <int KIND, int MINB> __global__ void __launch_bounds__(256, MINB) k_cla
 }
 
 // ---- merge: sorted keys -> unique records with accumulated weights ---------------
+// [emu-begin merge]  (tests/test_kernel_emulation.py runs the kernels between these tags on the host, one lane per warp)
 __global__ void k_iota(int64_t n, int* __restrict__ idx)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -218,6 +219,8 @@ __global__ void k_emit_collisions(int64_t n, const unsigned long long* __restric
         dt[p] = dt_raw[idx[i]];
     }
 }
+
+// [emu-end merge]
 
 // Keys are (id0 << 32 | id1) with id0, id1 below these bounds per kind: the radix sort only has to look at
 // the low bits of id1 and of id0 (two bit ranges would need two sorts; one range from 0 to 32 + bits(id0) with
@@ -552,6 +555,7 @@ double collisions_min_distance(ipcb_ctx* ctx)
 //  3. the usual merge follows; edge-edge records are merged on (unordered edge pair, distance type) and keep their
 //     orientation (collisions/normal/edge_edge.cpp:123-142): correction collisions carry vertex / edge distance types
 //     and are not (min, max)-ordered.
+// [emu-begin improved]
 struct AdjView {
     const int *vv_off, *vv, *ve_off, *ve, *ev_off, *ev;
     const unsigned char* boundary;
@@ -785,6 +789,7 @@ __global__ void k_emit_ee_typed(int64_t n, const unsigned long long* __restrict_
     eps[p] = eps_raw[idx[i]];
     dt[p] = (unsigned char)((k >> 1) & 15ull);
 }
+// [emu-end improved]
 static void merge_ee_typed_enqueue(ipcb_ctx* ctx, int64_t n, cudaStream_t s)
 {
     CollisionSet& cs = ctx->coll[IPCB_EE];
