@@ -4,7 +4,8 @@ The CUDA side of this set type (`collisions.cu`: sub-element candidates, correct
 written after the round's GPU budget had been used up: it compiles, but it has NOT run on hardware yet.  The tests are
 therefore marked xfail(strict=False) — they report XPASS if the code is right and cannot turn the suite red if it is not
 — and the file sorts last so that nothing runs after it in the same process.  Remove the marker once they pass.
-The oracle side is pinned in tests/test_reference_kats.py (CPU suite).
+The oracle side is pinned in tests/test_reference_kats.py, and the kernels' logic is checked on the host by
+tests/test_kernel_emulation.py (both in the CPU suite).
 """
 import numpy as np
 import pytest
