@@ -82,10 +82,10 @@ class ClockSampler(threading.Thread):
 
 def ncu_traffic(workload):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the committed `ncu --set full` capture of
-    this workload (profiles/r1_ncu_full_<workload>_raw.csv), by kernel name; None when there is no capture"""
+    this workload (profiles/r2_ncu_full_<workload>_raw.csv), by kernel name; None when there is no capture"""
     import csv
 
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_%s_raw.csv" % workload)
+    path = os.path.join(ROOT, "profiles", "r2_ncu_full_%s_raw.csv" % workload)
     if not os.path.exists(path):
         return None
     rows = list(csv.reader(open(path)))
@@ -114,8 +114,10 @@ def cpu_step(api, mesh, V0, V1, dhat):
 
 
 def run_reference(args, desc, full_spec, sample_spec):
-    """--impl reference: the CPU restatement of the reference path (the upstream library cannot be built
-    here) with all host threads, on a bounded sample of the same workload."""
+    """--impl reference: the reference's CPU path for this step — the restatement in oracle/ (the upstream library cannot
+    be built here: no Eigen / TBB / Tight-Inclusion in the image) — on the FULL workload of the GPU arm, with
+    every host thread.  One step of C3 takes tens of seconds on the host, so the number of steps is bounded by a time
+    budget (IPCB_REFERENCE_BUDGET_S, default 240 s): the line reports the steps that really ran, never a scaled value."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -127,29 +129,64 @@ def run_reference(args, desc, full_spec, sample_spec):
     scenes = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(scenes)
     api = pyoracle.load(fast=True)
-    use = sample_spec or full_spec
-    V0, V1, E, F, P = make_scene(scenes, use)
-    full_tris = make_tris(full_spec)
-    scale = full_tris / F.shape[0]
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    api.set_num_threads(cores)  # torchrun exports OMP_NUM_THREADS=1: the baseline uses every core at every N
+    V0, V1, E, F, P = make_scene(scenes, full_spec)
     mesh = api.CollisionMesh(V0, E, F)
-    times = []
-    for it in range(args.warmup + args.steps):
+    budget = float(os.environ.get("IPCB_REFERENCE_BUDGET_S", "240"))
+    t_start = time.perf_counter()
+    times, warm = [], 0
+    out = None
+    n_warm = min(args.warmup, 1)  # one warm-up step (allocations, page-in); the rest of the budget goes to timed steps
+    while len(times) < args.steps:
         t = time.perf_counter()
         out = cpu_step(api, mesh, V0, V1, P["dhat"])
-        dt = (time.perf_counter() - t) * 1e3
-        if it >= args.warmup:
-            times.append(dt)
-    ms = float(np.mean(times)) * scale
-    cores = api.num_threads()
-    sample = "%d of %d triangles of the workload (same generator), ms scaled by %.3f" % (F.shape[0], full_tris, scale)
+        dt = time.perf_counter() - t
+        if warm < n_warm:
+            warm += 1
+        else:
+            times.append(dt * 1e3)
+        if len(times) >= 2 and (time.perf_counter() - t_start) + dt > budget:
+            break
+    ms = float(np.mean(times))
+    sample = ("the full workload (%d triangles); %d timed steps after %d warm-up steps inside a %.0f s budget (%d / %d requested)"
+              % (F.shape[0], len(times), warm, budget, args.steps, args.warmup))
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": len(times), "warmup": warm,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
         "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "triangles": full_tris},
+        "config": make_config(desc, full_spec, args.gpus, args.additive_hessian),
         "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "collisions_in_sample": out[4],
+        "counts": {"collisions": out[4], "hessian_nnz": int(out[2].nnz), "step": out[3], "energy": out[0]},
     }))
+
+
+def make_config(desc, full_spec, world, additive=False):
+    """the `config` object — identical for both arms (the reference arm times the SAME workload on the host cores)"""
+    nV, nE, nF = scene_sizes(full_spec)
+    return {"workload": desc, "triangles": nF, "vertices": nV, "edges": nE, "dhat": 1e-3, "psd": "CLAMP", "ccd": "TightInclusion",
+            "collision_set": "IPC", "l2": "GPU arm: flushed between timed steps (256 MB write); CPU arm: inputs larger than the caches",
+            "parallelism": ("single GPU" if world == 1 else
+                            "candidate shards by Morton range of query leaves; " +
+                            ("Hessian as additive rank contributions" if additive else
+                             "collision records all-gathered + merged, energy/gradient by collision range, "
+                             "Hessian by balanced row block (no collective)"))}
+
+
+def scene_sizes(spec):
+    """(vertices, edges, triangles) of a generator spec without building it"""
+    if spec["kind"] == "sphere":
+        n, res = spec["n"], spec["res"]
+        nV = (n + 1) ** 2 + res * (res - 1) + 2
+        nF = 2 * n * n + 2 * res * (res - 1)
+        nE = (3 * n * n + 2 * n) + 3 * res * (res - 1)
+        return nV, nE, nF
+    L, n = spec["layers"], spec["n"]
+    return L * (n + 1) ** 2, L * (3 * n * n + 2 * n), L * 2 * n * n
 
 
 def make_tris(spec):
@@ -169,6 +206,8 @@ def main():
     ap.add_argument("--additive-hessian", action="store_true",
                     help="N > 1: keep every rank's potential on its own collision shard (Hessian = additive contribution) "
                          "instead of the all-gathered set with row-block Hessians")
+    ap.add_argument("--single-context", action="store_true",
+                    help="A/B: run the five calls of the step one after the other on ONE context (no second lane for the CCD half)")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: warm up, then run ONE device step between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench line")
@@ -204,8 +243,12 @@ def main():
     V0, V1, E, F, P = make_scene(scenes, full_spec)
     dhat = P["dhat"]
     nV = V0.shape[0]
+    assert (nV, E.shape[0], F.shape[0]) == scene_sizes(full_spec)
     mesh = api.CollisionMesh(V0, E, F, device=local)
     ctx = mesh._ctx
+    # second context on the same mesh: the CCD half of the step runs on its own streams beside the potential half
+    ccd_mesh = None if args.single_context else api.CollisionMesh(V0, E, F, device=local)
+    contexts = [ctx] + ([ccd_mesh._ctx] if ccd_mesh is not None else [])
     lib.check(lib.ctx_set_shard(ctx, rank, world))
     stream = torch.cuda.ExternalStream(lib.ctx_stream(ctx), device=torch.device("cuda", local))
 
@@ -223,18 +266,26 @@ def main():
     info = {}
     stage_acc = {}
 
-    def collect_stages():
-        names = (C.c_char_p * 32)()
-        ms = (C.c_float * 32)()
-        n = lib.ctx_stage_times(ctx, 32, names, ms)
+    def collect_stages(c):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = lib.ctx_stage_times(c, 64, names, ms)
         for i in range(n):
             stage_acc.setdefault(names[i].decode(), []).append(ms[i])
 
+    def launch_count():
+        total = 0
+        for c in contexts:
+            n = C.c_int64()
+            lib.ctx_launch_count(c, C.byref(n))
+            total += n.value
+        return total
+
     # the step itself lives in the package (ipc-toolkit_b200/sharded.py) so that the tests exercise the same code:
-    # N = 1: the five library calls; N > 1: sharded broad phase, all-gather + merge of the collision records,
-    # energy / gradient by collision range, Hessian by balanced row block, all-reduces
+    # N = 1: the five library calls (the CCD half on the second context); N > 1: sharded broad phase, all-gather + merge of
+    # the collision records, energy / gradient by collision range, Hessian by balanced row block, all-reduces
     sharded = __import__("importlib").import_module("ipc_toolkit_b200.sharded")
-    stepper = sharded.DeviceShardedStep(api, mesh, rank, world, dist, torch, stream, row_block=not args.additive_hessian)
+    stepper = sharded.DeviceShardedStep(api, mesh, rank, world, dist, torch, stream, row_block=not args.additive_hessian, ccd_mesh=ccd_mesh)
 
     def device_step(record=False):
         stepper.after = collect_stages if record else None
@@ -278,22 +329,26 @@ def main():
         device_step()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
+        stepper.release()
         return
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = C.c_int64()
-    lib.ctx_launch_count(ctx, C.byref(l0))
+    l0 = launch_count()
     ms_dev = timed(device_step, args.steps, args.warmup)
-    l1 = C.c_int64()
-    lib.ctx_launch_count(ctx, C.byref(l1))
-    launches = (l1.value - l0.value) // (args.steps + args.warmup) * args.steps
-    lib.ctx_enable_stage_timing(ctx, 1)
-    device_step(record=True)  # one extra, untimed pass to read the per-stage device times
-    lib.ctx_enable_stage_timing(ctx, 0)
+    launches = (launch_count() - l0) // (args.steps + args.warmup) * args.steps
+    for c in contexts:
+        lib.ctx_enable_stage_timing(c, 1)
+    device_step(record=True)  # one extra, untimed pass to read the per-stage / per-kernel device times
+    for c in contexts:
+        lib.ctx_enable_stage_timing(c, 0)
     lib.check(lib.candidates_build_swept_dev(ctx, C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr()), nV, 0.0, counts))
     info["ccd_candidates"] = list(counts)
+    if world == 1:
+        hv = np.asfortranarray(V0)
+        lib.check(lib.candidates_build_static(ctx, hv.ctypes.data_as(C.c_void_p), nV, 0.5 * dhat, counts))
+        info["static_candidates"] = list(counts)
 
     # ---- the line-search inner loop of the reference's solver example (python/examples/solver.py:
     # 95-116) from RESIDENT candidates: swept candidates with inflation dhat built once, then per line-search point
@@ -316,6 +371,7 @@ def main():
         ls_ms = timed(rebuild, max(3, args.steps // 2), 2)
         line_search = {"ms_per_rebuild": ls_ms, "what": "collisions_build_from_candidates_dev + barrier_energy_dev at x0 + alpha/2 dx",
                        "resident_candidates": ls_cand, "collisions": list(ls_counts), "alpha": alpha}
+        del dX
 
     # ---- end to end through the host-buffer C ABI (pinned inputs, host results)
     hV0 = torch.from_numpy(np.asfortranarray(V0).T.copy()).pin_memory()
@@ -325,21 +381,32 @@ def main():
     e2e_bytes = {"h2d": 0, "d2h": 0}
     hbuf = {}
 
-    def host_step():
-        e, st = C.c_double(), C.c_double()
-        lib.check(lib.collisions_build(ctx, hv0p, nV, dhat, 0.0, 0, counts))
-        lib.check(lib.barrier_energy(ctx, hv0p, nV, C.byref(bp), C.byref(e)))
-        lib.check(lib.barrier_gradient(ctx, hv0p, nV, C.byref(bp), C.c_void_p(h_grad.data_ptr())))
-        lib.check(lib.barrier_hessian(ctx, hv0p, nV, C.byref(bp), 1, C.byref(nnz)))
-        n = nnz.value
+    def host_buffers(n):
         if hbuf.get("n", -1) < n:
             hbuf["outer"] = torch.zeros(3 * nV + 1, dtype=torch.int32).pin_memory()
             hbuf["inner"] = torch.zeros(int(n * 1.2) + 1, dtype=torch.int32).pin_memory()
             hbuf["vals"] = torch.zeros(int(n * 1.2) + 1, dtype=torch.float64).pin_memory()
             hbuf["n"] = int(n * 1.2)
+
+    def host_step():
+        """N = 1: the host-buffer C ABI — every call takes pinned HOST positions and returns HOST results (energy,
+        gradient, the CSR arrays, the step size); the step-size call runs on the second context beside the others"""
+        e, st = C.c_double(), C.c_double()
+        job = None
+        if stepper.lane is not None:
+            job = stepper.lane.submit(lambda: lib.check(lib.ccd_stepsize(stepper.ctx_b, hv0p, hv1p, nV, 0.0, C.byref(ccd), C.byref(st))))
+        lib.check(lib.collisions_build(ctx, hv0p, nV, dhat, 0.0, 0, counts))
+        lib.check(lib.barrier_energy(ctx, hv0p, nV, C.byref(bp), C.byref(e)))
+        lib.check(lib.barrier_gradient(ctx, hv0p, nV, C.byref(bp), C.c_void_p(h_grad.data_ptr())))
+        lib.check(lib.barrier_hessian(ctx, hv0p, nV, C.byref(bp), 1, C.byref(nnz)))
+        n = nnz.value
+        host_buffers(n)
         lib.check(lib.barrier_hessian_fetch(ctx, C.c_void_p(hbuf["outer"].data_ptr()), C.c_void_p(hbuf["inner"].data_ptr()),
                                             C.c_void_p(hbuf["vals"].data_ptr())))
-        lib.check(lib.ccd_stepsize(ctx, hv0p, hv1p, nV, 0.0, C.byref(ccd), C.byref(st)))
+        if job is None:
+            lib.check(lib.ccd_stepsize(ctx, hv0p, hv1p, nV, 0.0, C.byref(ccd), C.byref(st)))
+        else:
+            job.wait()
         e2e_bytes["h2d"] = 24 * nV * 4 + 24 * nV * 2  # V uploaded by build / energy / gradient / hessian + (V0, V1) by ccd
         e2e_bytes["d2h"] = 8 + 24 * nV + 4 * (3 * nV + 1) + 12 * n + 8
         info["step"], info["energy"] = st.value, e.value
@@ -359,11 +426,7 @@ def main():
             h_small[0:1].copy_(d_energy, non_blocking=True)
             h_small[1:2].copy_(d_step, non_blocking=True)
         n = nnz.value
-        if hbuf.get("n", -1) < n:
-            hbuf["outer"] = torch.zeros(3 * nV + 1, dtype=torch.int32).pin_memory()
-            hbuf["inner"] = torch.zeros(int(n * 1.2) + 1, dtype=torch.int32).pin_memory()
-            hbuf["vals"] = torch.zeros(int(n * 1.2) + 1, dtype=torch.float64).pin_memory()
-            hbuf["n"] = int(n * 1.2)
+        host_buffers(n)
         lib.check(lib.barrier_hessian_fetch(ctx, C.c_void_p(hbuf["outer"].data_ptr()), C.c_void_p(hbuf["inner"].data_ptr()),
                                             C.c_void_p(hbuf["vals"].data_ptr())))
         e2e_bytes["h2d"] = 24 * nV * 2
@@ -373,89 +436,138 @@ def main():
     ms_e2e = timed(host_step if world == 1 else sharded_host_step, max(2, args.steps // 2), 1)
     sampler.stop_flag = True
 
-    # ---- rooflines (algorithmic bytes per launch: DESIGN.md §4), kernel times = CUDA-event stage times
-    # of the extra recorded step (each stage below is one kernel, or one group of concurrent per-kind launches)
-    stages = {k: float(np.sum(v)) for k, v in stage_acc.items()}  # stages that run twice (static + swept) add up
+    # ---- roofline denominators measured on this device: HBM copy bandwidth (MEASURED_PEAKS.json, driver-written; the
+    # library's own copy kernel beside it) and the FP64 FMA rate (not in MEASURED_PEAKS.json: measured here)
     peak, peak_kind = load_peaks()
+    fp64_peak, copy_gbs = C.c_double(), C.c_double()
+    lib.check(lib.measure_fp64_peak(ctx, 5, C.byref(fp64_peak)))
+    lib.check(lib.measure_copy_bandwidth(ctx, 1 << 30, 5, C.byref(copy_gbs)))
+
+    # ---- rooflines (algorithmic bytes / flops per launch: DESIGN.md §4); kernel times = CUDA events around
+    # the kernel on its own stream in the extra recorded step ("k:" timers of the library)
+    stages = {k: float(np.sum(v)) for k, v in stage_acc.items()}  # stages that run twice (static + swept) add up
+    kernels_ms = {k[2:]: v for k, v in stages.items() if k.startswith("k:")}
+    stages = {k: v for k, v in stages.items() if not k.startswith("k:")}
     ncoll = info.get("collisions", [0, 0, 0, 0])
     npts = (2, 3, 4, 4)
     nitems = sum(c * n * n for c, n in zip(ncoll, npts))
     ninc = sum(c * n for c, n in zip(ncoll, npts))
     nnz_ = info.get("nnz", 0) or 0
     traffic = ncu_traffic(args.workload)
+    share = 1.0
+    if world > 1 and not args.additive_hessian:
+        # row-block mode: every rank holds the FULL set and assembles its row block, i.e. about 1 / world of the items and
+        # of the block rows; rank 0's share is what its kernels moved (ncu traffic is a single-GPU capture)
+        share, traffic = 1.0 / world, None
+    cs = info.get("static_candidates") or [0, 0, 0, 0]
+    cc = info.get("ccd_candidates") or [0, 0, 0, 0]
 
-    def roof(kernel, stage, alg_bytes, ncu_names, note):
-        ms = stages.get(stage)
-        if not ms:
+    def roof(kernel, ms, alg_bytes, ncu_names, note, flops=None, bound="hbm"):
+        if not ms or not alg_bytes:
             return None
         ach = alg_bytes / (ms * 1e-3) / 1e9
-        # ncu kernel names carry all template arguments: match by prefix
-        hit = [v for k, v in (traffic or {}).items() if any(k.startswith(n) for n in ncu_names)]
-        t = sum(hit) if len(hit) >= len(ncu_names) else None
-        return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": t,
-                "peak_source": peak_kind + " (MEASURED_PEAKS.json copy bandwidth)" if peak_kind == "measured" else "fallback",
-                "algorithmic_bytes": int(alg_bytes), "kernel_ms": ms, "note": note}
+        hit = [v for k, v in (traffic or {}).items() if any(k.startswith(n) for n in ncu_names)]  # names carry template arguments
+        t = sum(hit) if hit and len(hit) >= len(ncu_names) else None
+        r = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": t,
+             "peak_source": (peak_kind + " (MEASURED_PEAKS.json copy bandwidth)") if peak_kind == "measured" else "fallback",
+             "algorithmic_bytes": int(alg_bytes), "kernel_ms": ms, "note": note}
+        if flops:
+            tf = flops / (ms * 1e-3) / 1e12
+            r["fp64"] = {"achieved": tf, "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": tf / fp64_peak.value if fp64_peak.value else None,
+                         "algorithmic_flops": int(flops), "peak_source": "measured here (ipcb_measure_fp64_peak: 8 FMA chains per thread)"}
+            if bound == "fp64":
+                r["achieved"], r["peak"], r["unit"], r["frac"] = tf, fp64_peak.value, "TFLOP/s", r["fp64"]["frac"]
+        return r
 
     # local Hessians: per collision 24 B record + 32 B per stencil point in; 16 B ids + 32 B masks + 8 B per incidence +
-    # 72 B per 3x3 block out
-    if world > 1 and not args.additive_hessian:
-        # row-block mode: every rank holds the FULL set (ncoll) and assembles its row block, i.e. about 1 / world of
-        # the items and of the block rows; rank 0's share is what its kernels moved (ncu traffic is a single-GPU capture)
-        ncoll = [c / world for c in ncoll]
-        nitems, ninc, traffic = nitems / world, ninc / world, None
-    hl_bytes = sum(c * (24 + 32 * n + 16 + 32 + 8 * n + 72 * n * n) for c, n in zip(ncoll, npts))
+    # 72 B per stored (upper-triangular) 3x3 block out.  FP64: FLOPS_HFAST per collision (from the ncu
+    # instruction counts of the capture in profiles/)
+    tri = (3, 6, 10, 10)
+    FLOPS_HFAST = (900.0, 5200.0, 11600.0, 11600.0)
+    k_ms = lambda name: kernels_ms.get(name)
+    hf_names = ("k_hessian_fast<VV>", "k_hessian_fast<EV>", "k_hessian_fast<EE>", "k_hessian_fast<FV>")
+    hl_bytes = [c * share * (24 + 32 * n + 16 + 32 + 8 * n + 72 * t) for c, n, t in zip(ncoll, npts, tri)]
+    hl_flops = [c * share * f for c, f in zip(ncoll, FLOPS_HFAST)]
+    hf_ms = sum(k_ms(n) or 0.0 for n in hf_names)
     # numeric pass: 4 B reference + 72 B block per item in, 8 B per unique block (~nnz / 9), 12 B per entry out
-    hn_bytes = nitems * 76 + nnz_ * 12 + (nnz_ // 9) * 8
+    hn_bytes = nitems * share * 76 + nnz_ * 12 + (nnz_ // 9) * 8
     # symbolic pass: 8 B incidence + 16 B ids + 8 B masks per incidence in, 4 B per item + 8 B per unique block out
-    hs_bytes = ninc * 32 + nitems * 4 + (nnz_ // 9) * 8
+    hs_bytes = ninc * share * 32 + nitems * share * 4 + (nnz_ // 9) * 8
     rooflines = [r for r in (
-        roof("k_hessian_fast<VV|EV|EE|FV> (4 concurrent launches)", "hessian_local", hl_bytes,
+        roof("k_hessian_fast<VV|EV|EE|FV> (the four kinds, timed one by one)", hf_ms, sum(hl_bytes),
              ["k_hessian_fast<0", "k_hessian_fast<1", "k_hessian_fast<2", "k_hessian_fast<3"],
-             "FP64-pipe bound (register Jacobi PSD projection, ~44% FP64 pipe at 25% occupancy, 128 registers); stores coalesced through shared memory"),
-        roof("k_hess_numeric", "hess_numeric", hn_bytes, ["k_hess_numeric"], "HBM gather of 72-byte blocks, software-pipelined"),
-        roof("k_hess_symbolic", "hess_symbolic", hs_bytes, ["k_hess_symbolic"], "shared-memory hash + sort per column; instruction / latency bound"),
+             "register Jacobi PSD projection in the analytic (3+p)-subspace; upper-triangular blocks staged through shared memory",
+             flops=sum(hl_flops), bound="fp64"),
+        roof("k_hessian_fast<EE>", k_ms(hf_names[2]), hl_bytes[2], ["k_hessian_fast<2"], "the dominant kernel of the step", flops=hl_flops[2], bound="fp64"),
+        roof("k_hess_numeric", stages.get("hess_numeric"), hn_bytes, ["k_hess_numeric"], "HBM gather of 72-byte blocks, software-pipelined"),
+        roof("k_hess_symbolic", stages.get("hess_symbolic"), hs_bytes, ["k_hess_symbolic"],
+             "shared-memory hash + sort per column; instruction / latency bound"),
+        roof("radix sort of the (vertex, collision) incidences (cub)", k_ms("radix_sort(incidences)"), ninc * share * 8 * 2 * 4, ["DeviceRadixSort"],
+             "3 onesweep passes + histogram over 8-byte keys"),
+        # classification: 8 B ids + 2 x 8 B edge / 16 B face ids + 4 x 32 B vertices per candidate; ~150 (EE) / 250 (FV) flop
+        roof("k_classify<EE>", k_ms("k_classify<EE>"), cs[2] * 152.0, ["k_classify<2"], "one thread per candidate: dependent gathers out of L2",
+             flops=cs[2] * 150.0),
+        roof("k_classify<FV>", k_ms("k_classify<FV>"), cs[3] * 152.0, ["k_classify<3"], "one thread per candidate: dependent gathers out of L2",
+             flops=cs[3] * 250.0),
+        # traversal: 40 B per query leaf + 8 B per emitted pair (static + swept passes); the node fetches (64 B each) hit L2
+        roof("k_traverse<EE> (static + swept)", k_ms("k_traverse<EE>"), 2 * E.shape[0] * 40.0 + (cs[2] + cc[2]) * 8.0, ["k_traverse<2, 2, 2"],
+             "one thread per query leaf, stack walk: bound by dependent node fetches (L2 latency), not by DRAM"),
+        roof("k_traverse<FV> (static + swept)", k_ms("k_traverse<FV>"), 2 * nV * 40.0 + (cs[3] + cc[3]) * 8.0, ["k_traverse<1, 1, 3"],
+             "one thread per query leaf, stack walk: bound by dependent node fetches (L2 latency), not by DRAM"),
+        # CCD pre-filter: 8 B ids + 16 B edge ids + 8 x 32 B vertices (t0, t1) per candidate; ~400 flop
+        roof("k_ti_filter", k_ms("k_ti_filter"), (cc[2] + cc[3]) * 280.0, ["k_ti_filter"], "separating-direction test per swept candidate",
+             flops=(cc[2] + cc[3]) * 400.0),
     ) if r]
     roof_main = rooflines[0] if rooflines else None
+    if roof_main is not None:  # the contract's `roofline` object: the dominant kernel against the MEASURED HBM bandwidth; its FP64 view rides along
+        hbm = roof("k_hessian_fast<VV|EV|EE|FV>", hf_ms, sum(hl_bytes), ["k_hessian_fast<0", "k_hessian_fast<1", "k_hessian_fast<2", "k_hessian_fast<3"],
+                   roof_main["note"], flops=sum(hl_flops), bound="hbm")
+        hbm["binding"] = "fp64 (see the fp64 object: the kernel is bound by the FP64 pipe, its HBM fraction is reported as the contract asks)"
+        roof_main = hbm
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the CPU restatement on the SAME workload, every host core, ONE step (C3: ~20-30 s): a reported baseline
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import pyoracle
 
         oapi = pyoracle.load(fast=True)
-        use = sample_spec or full_spec
-        sV0, sV1, sE, sF, sP = make_scene(scenes, use)
-        scale = F.shape[0] / sF.shape[0]
-        omesh = oapi.CollisionMesh(sV0, sE, sF)
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        oapi.set_num_threads(cores)
+        omesh = oapi.CollisionMesh(V0, E, F)
         t = time.perf_counter()
-        cpu_step(oapi, omesh, sV0, sV1, sP["dhat"])
-        cpu_ms = (time.perf_counter() - t) * 1e3 * scale
-        cpu = {"value": cpu_ms, "unit": "ms", "cores": oapi.num_threads(), "kind": "port",
-               "sample": "%d of %d triangles (same generator), one step, ms scaled by %.3f" % (sF.shape[0], F.shape[0], scale)}
+        cpu_out = cpu_step(oapi, omesh, V0, V1, dhat)
+        cpu_ms = (time.perf_counter() - t) * 1e3
+        cpu = {"value": cpu_ms, "unit": "ms", "cores": cores, "kind": "port",
+               "sample": "the full workload (%d triangles), one step, no warm-up" % F.shape[0],
+               "collisions": cpu_out[4], "step": cpu_out[3]}
+        del omesh, cpu_out
 
     if rank == 0:
         out = {
             "metric": METRIC, "value": ms_dev, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": desc, "triangles": int(F.shape[0]), "vertices": int(nV), "edges": int(E.shape[0]), "dhat": dhat,
-                       "psd": "CLAMP", "ccd": "TightInclusion", "l2": "flushed between timed steps (256 MB write)",
-                       "parallelism": ("single GPU" if world == 1 else
-                                       "candidate shards by Morton range of query leaves; " +
-                                       ("Hessian as additive rank contributions" if args.additive_hessian else
-                                        "collision records all-gathered + merged, energy/gradient by collision range, "
-                                        "Hessian by balanced row block (no collective)"))},
+            "config": make_config(desc, full_spec, world, args.additive_hessian),
             "e2e": None if ms_e2e is None else {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": e2e_bytes["h2d"],
                                                 "d2h_bytes_per_step": e2e_bytes["d2h"]},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": roof_main,
             "rooflines": rooflines,
+            "peaks": {"hbm_gbs": peak, "hbm_source": peak_kind, "copy_kernel_gbs": copy_gbs.value, "fp64_tflops": fp64_peak.value,
+                      "fp64_source": "ipcb_measure_fp64_peak on this device"},
             "cpu_baseline": cpu,
             "stages_ms": stages,
+            "kernels_ms": kernels_ms,
+            "lanes": "two contexts: build + potential || swept broad phase + CCD" if ccd_mesh is not None else "one context, sequential calls",
             "line_search_rebuild": line_search,
             "counts": {"collisions_rank0": info.get("collisions"), "shard_collisions_rank0": info.get("shard_collisions"),
                        "hessian_rows_rank0": info.get("rows"), "ccd_candidates_rank0": info.get("ccd_candidates"),
+                       "static_candidates": info.get("static_candidates"),
                        "hessian_nnz_rank0": info.get("nnz"), "step": info.get("step"),
                        "energy": info.get("energy")},
         }
@@ -464,14 +576,25 @@ def main():
             sys.stdout.write(line)
         else:
             os.write(json_fd, line.encode())
+    # ---- orderly teardown (no os._exit: the driver's exit hook records the loaded libraries).  Everything that was used
+    # on the library's streams (wrapped as torch ExternalStreams) is released BEFORE the contexts — and with them the
+    # streams — are destroyed: tensors first, then torch's cached blocks, then NCCL, then the contexts.
+    torch.cuda.synchronize()
+    stepper.release()
+    del stepper, dV0, dV1, d_energy, d_grad, d_step, flush, hV0, hV1, h_grad, h_small, stream
+    hbuf.clear()
+    import gc
+
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     if dist is not None:
         dist.destroy_process_group()
-    # The library's stream (wrapped as a torch ExternalStream) dies with the mesh; pinned / device tensors that were
-    # last used on it must not outlive it.  Leave without running destructors in an arbitrary order.
-    torch.cuda.synchronize()
+    mesh.close()
+    if ccd_mesh is not None:
+        ccd_mesh.close()
     sys.stdout.flush()
     sys.stderr.flush()
-    os._exit(0)
 
 
 if __name__ == "__main__":

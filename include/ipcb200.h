@@ -258,6 +258,11 @@ int IPCB_FN(ctx_launch_count)(ipcb_ctx* ctx, int64_t* n);
  * with ctx_enable_stage_timing(ctx, 1) for a profiling pass (bench.py does, outside its timed region). */
 int IPCB_FN(ctx_enable_stage_timing)(ipcb_ctx* ctx, int32_t on);
 int IPCB_FN(ctx_stage_times)(ipcb_ctx* ctx, int32_t max_stages, const char** names, float* ms);
+/* roofline denominators measured on the context's device (bench.py): the FP64 FMA rate of a register-only kernel with
+ * eight independent chains per thread (TFLOP/s, 2 flop per FMA) and the bandwidth of a device-to-device copy kernel
+ * over `bytes` (GB/s, read + write); best of `repeats` launches, CUDA events on the context's stream */
+int IPCB_FN(measure_fp64_peak)(ipcb_ctx* ctx, int32_t repeats, double* tflops);
+int IPCB_FN(measure_copy_bandwidth)(ipcb_ctx* ctx, int64_t bytes, int32_t repeats, double* gbs);
 #endif
 
 #ifdef __cplusplus

@@ -77,6 +77,8 @@ DEVICE_API = {
     "ctx_launch_count": (C.c_int, [P, C.POINTER(c_i64)]),
     "ctx_enable_stage_timing": (C.c_int, [P, c_i32]),
     "ctx_stage_times": (C.c_int, [P, c_i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
+    "measure_fp64_peak": (C.c_int, [P, c_i32, C.POINTER(c_f64)]),
+    "measure_copy_bandwidth": (C.c_int, [P, c_i64, c_i32, C.POINTER(c_f64)]),
 }
 
 

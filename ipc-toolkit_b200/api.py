@@ -114,10 +114,14 @@ def make_api(lib):
             self._cand_gen = 0
             self._coll_gen = 0
 
-        def __del__(self):
+        def close(self):
+            """destroy the library context now (device buffers, streams); the object is unusable afterwards"""
             if getattr(self, "_ctx", None):
                 lib.ctx_destroy(self._ctx)
                 self._ctx = None
+
+        def __del__(self):
+            self.close()
 
         def num_vertices(self):
             return self.rest_positions.shape[0]

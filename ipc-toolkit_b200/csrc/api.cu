@@ -28,6 +28,29 @@ template <typename F> int guarded(F&& f)
 
 void use_device(ipcb_ctx* ctx) { IPCB_CUDA(cudaSetDevice(ctx->device)); }
 
+// ---- roofline denominators (measure_fp64_peak / measure_copy_bandwidth)
+constexpr int PEAK_ITERS = 2048, PEAK_CHAINS = 8;
+__global__ void __launch_bounds__(256) k_fp64_peak(double seed, double* out)
+{
+    double x[PEAK_CHAINS];
+#pragma unroll
+    for (int k = 0; k < PEAK_CHAINS; k++) x[k] = seed + double(threadIdx.x + k);
+    const double a = 1.0 + 1e-9 * seed, b = 1e-9;
+#pragma unroll 1
+    for (int it = 0; it < PEAK_ITERS; it++) {
+#pragma unroll
+        for (int k = 0; k < PEAK_CHAINS; k++) x[k] = fma(x[k], a, b); // 8 independent FMA chains
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < PEAK_CHAINS; k++) s += x[k];
+    if (s == 12345.678) out[0] = s; // never true: keeps the chains alive
+}
+__global__ void __launch_bounds__(256) k_copy16(size_t n, const uint4* __restrict__ in, uint4* __restrict__ out)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) out[i] = in[i];
+}
+
 template <typename T> void upload(ipcb_ctx* ctx, Buf<T>& dst, const std::vector<T>& src)
 {
     dst.reserve(std::max<size_t>(src.size(), 1));
@@ -106,8 +129,11 @@ void ipcb_ctx_destroy(ipcb_ctx* ctx)
         cudaEventDestroy(ctx->ev_join[k]);
     }
     cudaEventDestroy(ctx->ev_fork);
-    cudaStreamDestroy(ctx->stream);
-    delete ctx;
+    ti_work_free(ctx->ti_work);
+    ctx->ti_work = nullptr;
+    cudaStream_t s = ctx->stream;
+    delete ctx; // frees the device buffers (cudaFree synchronises)
+    cudaStreamDestroy(s);
 }
 void* ipcb_ctx_stream(ipcb_ctx* ctx) { return ctx->stream; }
 
@@ -163,6 +189,56 @@ int ipcb_ctx_stage_times(ipcb_ctx* ctx, int32_t max_stages, const char** names, 
         ms[n] = ctx->stage_ms[i].second;
     }
     return n;
+}
+
+int ipcb_measure_fp64_peak(ipcb_ctx* ctx, int32_t repeats, double* tflops)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        cudaEvent_t a, b;
+        IPCB_CUDA(cudaEventCreate(&a));
+        IPCB_CUDA(cudaEventCreate(&b));
+        const int grid = NUM_SMS * 8, block = 256;
+        double best = 0;
+        for (int r = 0; r < std::max(repeats, 1) + 1; r++) { // the first launch warms up
+            IPCB_CUDA(cudaEventRecord(a, ctx->stream));
+            k_fp64_peak<<<grid, block, 0, ctx->stream>>>(1.0, ctx->dScalar.p);
+            IPCB_CUDA(cudaEventRecord(b, ctx->stream));
+            IPCB_CUDA(cudaEventSynchronize(b));
+            float ms = 0;
+            IPCB_CUDA(cudaEventElapsedTime(&ms, a, b));
+            const double flops = 2.0 * PEAK_ITERS * PEAK_CHAINS * double(grid) * block;
+            if (r > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        cudaEventDestroy(a), cudaEventDestroy(b);
+        *tflops = best;
+    });
+}
+int ipcb_measure_copy_bandwidth(ipcb_ctx* ctx, int64_t bytes, int32_t repeats, double* gbs)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (bytes < 16) throw Error("measure_copy_bandwidth: at least 16 bytes");
+        Buf<uint4> src, dst;
+        const size_t n = size_t(bytes) / 16;
+        src.reserve(n), dst.reserve(n);
+        IPCB_CUDA(cudaMemsetAsync(src.p, 1, n * 16, ctx->stream));
+        cudaEvent_t a, b;
+        IPCB_CUDA(cudaEventCreate(&a));
+        IPCB_CUDA(cudaEventCreate(&b));
+        double best = 0;
+        for (int r = 0; r < std::max(repeats, 1) + 1; r++) {
+            IPCB_CUDA(cudaEventRecord(a, ctx->stream));
+            k_copy16<<<NUM_SMS * 16, 256, 0, ctx->stream>>>(n, src.p, dst.p);
+            IPCB_CUDA(cudaEventRecord(b, ctx->stream));
+            IPCB_CUDA(cudaEventSynchronize(b));
+            float ms = 0;
+            IPCB_CUDA(cudaEventElapsedTime(&ms, a, b));
+            if (r > 0) best = std::max(best, 2.0 * double(n) * 16 / (ms * 1e-3) / 1e9);
+        }
+        cudaEventDestroy(a), cudaEventDestroy(b);
+        *gbs = best;
+    });
 }
 
 // ---- CollisionMesh: collision_mesh.cpp:15-127 (host tables) + device mirrors
@@ -401,6 +477,15 @@ int ipcb_candidates_set(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_
                 throw Error("candidate index out of range");
         PairList& pl = ctx->cand[kind];
         pl.pairs.reserve(std::max<int64_t>(count, 1));
+        // unordered kinds are kept as (min, max) like the broad phase emits them: a distance type of an edge-edge
+        // collision is always relative to that order (vertex_vertex.hpp / edge_edge.hpp compare unordered pairs)
+        std::vector<int32_t> canon;
+        if ((kind == IPCB_VV || kind == IPCB_EE) && count) {
+            canon.assign(pairs, pairs + 2 * count);
+            for (int64_t i = 0; i < count; i++)
+                if (canon[2 * i] > canon[2 * i + 1]) std::swap(canon[2 * i], canon[2 * i + 1]);
+            pairs = canon.data();
+        }
         if (count) IPCB_CUDA(cudaMemcpyAsync(pl.pairs.p, pairs, sizeof(int2) * count, cudaMemcpyHostToDevice, ctx->stream));
         IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
         pl.count = count;

@@ -464,7 +464,11 @@ static void build_tree(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, bool with_node
     t.sbox.reserve(n), t.sprim.reserve(n);
     const int bits = morton_bits(n);
     k_morton<<<grid_for(n, 256), 256, 0, s>>>(n, bits, getenv("IPCB_MORTON_PER_AXIS") ? 0 : 1, ps.box.p, ctx->scene.p, t.key.p, t.ord.p);
-    sort_keys(ctx, t, n, bits, s);
+    {
+        Stage kt(ctx, "k:radix_sort(morton)", s);
+        sort_keys(ctx, t, n, bits, s);
+    }
+    Stage kt(ctx, "k:lbvh_nodes", s);
     const bool bottom_up = getenv("IPCB_REFIT_BOTTOM_UP") != nullptr; // A/B + test hook: the arrival-counter refit
     if (!with_nodes || n < 2 || bottom_up) {
         k_apply_order<<<grid_for(n, 256), 256, 0, s>>>(n, t.ord_sorted.p, ps.box.p, ps.prim.p, t.sbox.p, t.sprim.p);
@@ -693,6 +697,7 @@ struct TraverseJob {
         IPCB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
         const unsigned long long cap = out->pairs.cap;
         const unsigned grid = grid_for(q_end - q_begin, TRAV_BLOCK);
+        Stage kt(ctx, mode == 2 && qn == 2 ? "k:k_traverse<EE>" : (mode == 1 && tn == 3 ? "k:k_traverse<FV>" : "k:k_traverse<other>"), s);
 #define IPCB_TRAVERSE(M, QN, TN)                                                                                                    \
     k_traverse<M, QN, TN><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes.p, t->n, t->sbox.p, t->sprim.p, \
                                                       out->pairs.p, counter, cap, check_shared)

@@ -887,7 +887,8 @@ struct TIWork {
     Buf<int> list; // candidates that survive the pre-filter
     Buf<int> hard; // queries deferred to the warp-cooperative search
 };
-static std::map<ipcb_ctx*, TIWork*> g_work; // one per context
+// the scratch belongs to its context (allocated on the context's device, freed by ipcb_ctx_destroy)
+void ti_work_free(TIWork* w) { delete w; }
 
 static unsigned long long read_counter(ipcb_ctx* ctx, const unsigned long long* d)
 {
@@ -951,9 +952,8 @@ static void ti_run(ipcb_ctx* ctx, const MultiSource& ms, double min_distance, do
     if (total == 0) return;
     if (total > 0x7fffffffll) throw Error("ccd: more than 2^31 candidates in one search");
     cudaStream_t s = ctx->stream;
-    TIWork*& wp = g_work[ctx];
-    if (!wp) wp = new TIWork();
-    TIWork& W = *wp;
+    if (!ctx->ti_work) ctx->ti_work = new TIWork();
+    TIWork& W = *ctx->ti_work;
     unsigned long long* nq_d = ctx->dCounters.p + 1;
     unsigned long long* cnt = ctx->dCounters.p + 2; // units in the global queue (directly after nq_d)
     unsigned long long* nactive_d = ctx->dCounters.p + 3;
@@ -990,11 +990,18 @@ static void ti_run(ipcb_ctx* ctx, const MultiSource& ms, double min_distance, do
         // phase, then inside a tight window.
         auto phase = [&](int st, bool probe) {
             IPCB_CUDA(cudaMemsetAsync(nlist_d, 0, 4 * sizeof(unsigned long long), s)); // list lengths and work counters
-            k_ti_filter<<<grid_for((total + st - 1) / st, 256), 256, 0, s>>>(ms, st, 0, min_distance, tmax, p.tolerance, out, W.list.p, nlist_d);
-            k_ti_query<<<NUM_SMS * 2, 128, 0, s>>>(ms, W.list.p, nlist_d, next_d, min_distance, tmax, p.tolerance, p.conservative_rescaling,
-                                                   dfs_budget(), W.hard.p, nhard_d, out);
+            {
+                Stage kt(ctx, probe ? "k:k_ti_filter(sample)" : "k:k_ti_filter", s);
+                k_ti_filter<<<grid_for((total + st - 1) / st, 256), 256, 0, s>>>(ms, st, 0, min_distance, tmax, p.tolerance, out, W.list.p, nlist_d);
+            }
+            {
+                Stage kt(ctx, probe ? "k:k_ti_query(sample)" : "k:k_ti_query", s);
+                k_ti_query<<<NUM_SMS * 2, 128, 0, s>>>(ms, W.list.p, nlist_d, next_d, min_distance, tmax, p.tolerance, p.conservative_rescaling,
+                                                       dfs_budget(), W.hard.p, nhard_d, out);
+            }
             ctx->launches += 2;
             if (!probe) {
+                Stage kt(ctx, "k:k_ti_warp", s);
                 k_ti_warp<<<NUM_SMS * 5, 32 * WARP_SEARCH_WARPS, 0, s>>>(ms, W.hard.p, nhard_d, next2_d, min_distance, tmax, p.tolerance,
                                                                         p.conservative_rescaling, warp_stack_cap(), (long long)p.max_iterations, Z, out);
                 ctx->launches++;

@@ -47,13 +47,11 @@ struct ClassifyArgs {
 __device__ inline d3 ld3(const double4* X, int i) { return load_vertex(X, i); }
 __device__ inline unsigned long long mkkey(int a, int b) { return ((unsigned long long)(unsigned)a << 32) | (unsigned)b; }
 
-__global__ void k_ids_to_keys(int64_t n, const int2* __restrict__ ids, int unordered, unsigned long long* __restrict__ key)
-{
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int2 c = ids[i];
-    key[i] = unordered ? mkkey(min(c.x, c.y), max(c.x, c.y)) : mkkey(c.x, c.y);
-}
+// record ids -> merge keys.  mode 0: ordered pair (edge-vertex, face-vertex); 1: unordered pair (vertex-vertex);
+// 2: edge-edge, TYPED key (unordered edge pair, distance type, orientation bit — ee_typed_key below): a record whose
+// edges are stored as (max, min) keeps its orientation, so its distance type never has to be re-expressed
+__global__ void k_ids_to_keys(int64_t n, const int2* __restrict__ ids, int mode, const unsigned char* __restrict__ dt,
+                              unsigned long long* __restrict__ key);
 
 // warp-aggregated append of one record per participating lane
 __device__ inline void append(const StreamOut& o, bool pred, unsigned long long key, double w, double eps, unsigned char dt)
@@ -305,6 +303,8 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
             a.n = ctx->cand[k].count;
             if (a.n == 0) continue;
             const unsigned grid = grid_for(a.n, 256);
+            static const char* const names[4] = { "k:k_classify<VV>", "k:k_classify<EV>", "k:k_classify<EE>", "k:k_classify<FV>" };
+            Stage kt(ctx, names[k], k == IPCB_FV ? ctx->aux[0] : s);
             static const bool sparse = getenv("IPCB_CLASSIFY_SPARSE") != nullptr; // A/B switch: 3 resident blocks, no spill
             if (k == IPCB_VV) k_classify<IPCB_VV, 4><<<grid, 256, 0, s>>>(a);
             if (k == IPCB_EV) k_classify<IPCB_EV, 4><<<grid, 256, 0, s>>>(a);
@@ -321,18 +321,29 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
     }
     int64_t raw[4] = { ctx->pinned.p[0], ctx->pinned.p[1], ctx->pinned.p[2], ctx->pinned.p[3] };
     if (improved) improved_max_approx_corrections(ctx, (dmin + dhat) * (dmin + dhat), (flags & IPCB_USE_AREA_WEIGHTING) != 0, raw);
-    merge_streams(ctx, raw, false, improved);
+    // IPC set: every edge-edge / face-vertex record comes from its own candidate, so those two streams hold no
+    // duplicates and need no merge — only vertex-vertex / edge-vertex records are united.  Their canonical order
+    // (sorted ids) is what a caller SEES, not what the potential needs: it is restored lazily when somebody fetches the
+    // records (collisions_sort), which takes the two large sorts out of the contact step.  IPCB_EAGER_SORT=1: A/B switch.
+    static const bool eager = getenv("IPCB_EAGER_SORT") != nullptr;
+    merge_streams(ctx, raw, !improved && !eager, improved);
 }
 
 // records -> final arrays without sorting or merging (every record is kept)
+// typed: edge-edge keys are [min edge : 28][max edge : 28][distance type : 4][stored as (max, min) : 1] (ee_typed_key)
 __global__ void k_keep_all(int64_t n, const unsigned long long* __restrict__ key, const double* __restrict__ w_raw,
-                           const double* __restrict__ eps_raw, const unsigned char* __restrict__ dt_raw, int2* __restrict__ ids,
+                           const double* __restrict__ eps_raw, const unsigned char* __restrict__ dt_raw, int typed, int2* __restrict__ ids,
                            double* __restrict__ w, double* __restrict__ eps, unsigned char* __restrict__ dt)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long k = key[i];
-    ids[i] = make_int2(int(k >> 32), int(k & 0xffffffffu));
+    if (typed) {
+        const int lo = int(k >> 33), hi = int((k >> 5) & 0xfffffffull);
+        ids[i] = (k & 1ull) ? make_int2(hi, lo) : make_int2(lo, hi);
+    } else {
+        ids[i] = make_int2(int(k >> 32), int(k & 0xffffffffu));
+    }
     w[i] = w_raw[i];
     if (eps_raw) eps[i] = eps_raw[i], dt[i] = dt_raw[i];
 }
@@ -359,7 +370,7 @@ static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4], bool disjoint, bo
             cs.ids.reserve(n), cs.w.reserve(n);
             if (k == IPCB_EE) cs.eps.reserve(n), cs.dtype.reserve(n);
             k_keep_all<<<grid_for(n, 256), 256, 0, where[k]>>>(n, cs.key_raw.p, cs.w_raw.p, k == IPCB_EE ? cs.eps_raw.p : nullptr, cs.dt_raw.p,
-                                                             cs.ids.p, cs.w.p, cs.eps.p, cs.dtype.p);
+                                                             typed_ee && k == IPCB_EE, cs.ids.p, cs.w.p, cs.eps.p, cs.dtype.p);
             ctx->launches++;
         } else if (typed_ee && k == IPCB_EE) {
             merge_ee_typed_enqueue(ctx, raw[k], where[k]);
@@ -389,14 +400,16 @@ void collisions_sort(ipcb_ctx* ctx, int kind)
     const int64_t n = cs.count;
     cs.key_raw.reserve(n), cs.w_raw.reserve(n);
     if (kind == IPCB_EE) cs.eps_raw.reserve(n), cs.dt_raw.reserve(n);
-    k_ids_to_keys<<<grid_for(n, 256), 256, 0, s>>>(n, cs.ids.p, kind == IPCB_VV || kind == IPCB_EE, cs.key_raw.p);
+    const bool typed = kind == IPCB_EE && ctx->nE < (1 << 28); // beyond: only IPC records exist (always (min, max) ordered)
+    k_ids_to_keys<<<grid_for(n, 256), 256, 0, s>>>(n, cs.ids.p, typed ? 2 : (kind == IPCB_VV || kind == IPCB_EE ? 1 : 0), cs.dtype.p, cs.key_raw.p);
     IPCB_CUDA(cudaMemcpyAsync(cs.w_raw.p, cs.w.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
     if (kind == IPCB_EE) {
         IPCB_CUDA(cudaMemcpyAsync(cs.eps_raw.p, cs.eps.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
         IPCB_CUDA(cudaMemcpyAsync(cs.dt_raw.p, cs.dtype.p, n, cudaMemcpyDeviceToDevice, s));
     }
     ctx->launches++;
-    merge_stream_enqueue(ctx, kind, n, s);
+    if (typed) merge_ee_typed_enqueue(ctx, n, s);
+    else merge_stream_enqueue(ctx, kind, n, s);
     IPCB_CUDA(cudaStreamSynchronize(s));
     cs.count = int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[20 + 2 * kind])) + int64_t(*reinterpret_cast<int*>(&ctx->pinned.p[21 + 2 * kind]));
     cs.sorted = true;
@@ -416,26 +429,14 @@ struct UnpackArgs {
     double* eps_out;
     unsigned char* dt_out;
 };
-__global__ void k_unpack(UnpackArgs a, int64_t total)
-{
-    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= total) return;
-    const int k = t >= a.first[3] ? 3 : (t >= a.first[2] ? 2 : (t >= a.first[1] ? 1 : 0));
-    const int64_t i = t - a.first[k];
-    const int2 c = reinterpret_cast<const int2*>(a.in + a.ids[k])[i];
-    a.key[k][i] = (k == IPCB_VV || k == IPCB_EE) ? mkkey(min(c.x, c.y), max(c.x, c.y)) : mkkey(c.x, c.y);
-    a.wout[k][i] = reinterpret_cast<const double*>(a.in + a.w[k])[i];
-    if (k == IPCB_EE) {
-        a.eps_out[i] = reinterpret_cast<const double*>(a.in + a.eps)[i];
-        a.dt_out[i] = reinterpret_cast<const unsigned char*>(a.in + a.dt)[i];
-    }
-}
+__global__ void k_unpack(UnpackArgs a, int64_t total);
 void collisions_append_packed_dev(ipcb_ctx* ctx, const void* d_buffer, const int64_t n[4], const int64_t ids_off[4], const int64_t w_off[4],
                                   int64_t eps_off, int64_t dt_off)
 {
     cudaStream_t s = ctx->stream;
     UnpackArgs a;
     a.in = static_cast<const char*>(d_buffer);
+    if (n[IPCB_EE] && ctx->nE >= (1 << 28)) throw Error("edge-edge collision records: more than 2^28 edges");
     int64_t total = 0;
     for (int k = 0; k < 4; k++) {
         CollisionSet& cs = ctx->coll[k];
@@ -471,11 +472,13 @@ void collisions_append_dev(ipcb_ctx* ctx, int kind, int64_t n, const int32_t* d_
     if (want > 0x7fffffffull) throw Error("more than 2^31 collision records of one kind");
     cs.key_raw.reserve_keep(want, have, s), cs.w_raw.reserve_keep(want, have, s);
     if (kind == IPCB_EE) cs.eps_raw.reserve_keep(want, have, s), cs.dt_raw.reserve_keep(want, have, s);
-    k_ids_to_keys<<<grid_for(n, 256), 256, 0, s>>>(n, reinterpret_cast<const int2*>(d_ids), kind == IPCB_VV || kind == IPCB_EE, cs.key_raw.p + have);
+    if (kind == IPCB_EE && (!d_eps || !d_dt)) throw Error("edge-edge collision records need eps_x and dtype");
+    if (kind == IPCB_EE && ctx->nE >= (1 << 28)) throw Error("edge-edge collision records: more than 2^28 edges");
+    k_ids_to_keys<<<grid_for(n, 256), 256, 0, s>>>(n, reinterpret_cast<const int2*>(d_ids), kind == IPCB_EE ? 2 : (kind == IPCB_VV ? 1 : 0), d_dt,
+                                                   cs.key_raw.p + have);
     ctx->launches++;
     IPCB_CUDA(cudaMemcpyAsync(cs.w_raw.p + have, d_w, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
     if (kind == IPCB_EE) {
-        if (!d_eps || !d_dt) throw Error("edge-edge collision records need eps_x and dtype");
         IPCB_CUDA(cudaMemcpyAsync(cs.eps_raw.p + have, d_eps, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
         IPCB_CUDA(cudaMemcpyAsync(cs.dt_raw.p + have, d_dt, n, cudaMemcpyDeviceToDevice, s));
     }
@@ -488,7 +491,9 @@ void collisions_merge(ipcb_ctx* ctx, double dmin, int flags)
     ctx->coll_valid = true;
     const int64_t raw[4] = { ctx->coll[0].raw_count, ctx->coll[1].raw_count, ctx->coll[2].raw_count, ctx->coll[3].raw_count };
     for (auto& c : ctx->coll) c.count = 0, c.raw_count = 0;
-    merge_streams(ctx, raw, (flags & IPCB_MERGE_DISJOINT_SHARDS) != 0);
+    // appended edge-edge records carry TYPED keys: records are united on (unordered edge pair, distance type) like
+    // EdgeEdgeNormalCollision::operator== (collisions/normal/edge_edge.cpp:123-142) and keep their stored orientation
+    merge_streams(ctx, raw, (flags & IPCB_MERGE_DISJOINT_SHARDS) != 0, true);
 }
 
 // ---- compute_minimum_distance (normal_collisions.cpp:209-233) ----------------------
@@ -790,6 +795,29 @@ __global__ void k_emit_ee_typed(int64_t n, const unsigned long long* __restrict_
     dt[p] = (unsigned char)((k >> 1) & 15ull);
 }
 // [emu-end improved]
+__global__ void k_ids_to_keys(int64_t n, const int2* __restrict__ ids, int mode, const unsigned char* __restrict__ dt,
+                              unsigned long long* __restrict__ key)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = ids[i];
+    key[i] = mode == 2 ? ee_typed_key(c.x, c.y, dt[i]) : (mode == 1 ? mkkey(min(c.x, c.y), max(c.x, c.y)) : mkkey(c.x, c.y));
+}
+__global__ void k_unpack(UnpackArgs a, int64_t total)
+{
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int k = t >= a.first[3] ? 3 : (t >= a.first[2] ? 2 : (t >= a.first[1] ? 1 : 0));
+    const int64_t i = t - a.first[k];
+    const int2 c = reinterpret_cast<const int2*>(a.in + a.ids[k])[i];
+    a.key[k][i] = k == IPCB_EE ? ee_typed_key(c.x, c.y, reinterpret_cast<const unsigned char*>(a.in + a.dt)[i])
+                                : (k == IPCB_VV ? mkkey(min(c.x, c.y), max(c.x, c.y)) : mkkey(c.x, c.y));
+    a.wout[k][i] = reinterpret_cast<const double*>(a.in + a.w[k])[i];
+    if (k == IPCB_EE) {
+        a.eps_out[i] = reinterpret_cast<const double*>(a.in + a.eps)[i];
+        a.dt_out[i] = reinterpret_cast<const unsigned char*>(a.in + a.dt)[i];
+    }
+}
 static void merge_ee_typed_enqueue(ipcb_ctx* ctx, int64_t n, cudaStream_t s)
 {
     CollisionSet& cs = ctx->coll[IPCB_EE];

@@ -12,7 +12,6 @@
 #include "common.cuh"
 #include <array>
 #include <chrono>
-#include <map>
 
 namespace ipcb {
 
@@ -75,9 +74,8 @@ struct CollisionSet {
     int64_t raw_count = 0; // records appended through collisions_append since the last collisions_clear
 };
 
-struct StageTimer {
-    std::vector<std::pair<std::string, float>> stages;
-};
+struct TIWork; // Tight-Inclusion scratch (ccd.cu), owned by the context
+void ti_work_free(TIWork* w);
 
 } // namespace ipcb
 
@@ -172,7 +170,7 @@ struct ipcb_ctx {
     ipcb::Buf<char> cubtmp;
 
     // ---- ccd
-    ipcb::Buf<char> ccd_work;
+    ipcb::TIWork* ti_work = nullptr;
 
     // ---- counters read back through pinned memory
     ipcb::Pinned pinned;
@@ -185,22 +183,25 @@ struct ipcb_ctx {
 
 namespace ipcb {
 
-// RAII stage timer using CUDA events on the context's stream; a no-op unless ctx->timing is set
+// RAII stage timer using CUDA events on the context's stream; a no-op unless ctx->timing is set.
+// With a stream argument it times ONE kernel (or one group of launches) on the stream it was launched on — the
+// per-kernel durations behind bench.py's rooflines; the names of such timers start with "k:".
 struct Stage {
     ipcb_ctx* ctx;
     const char* name;
+    cudaStream_t s;
     cudaEvent_t a = nullptr, b = nullptr;
-    Stage(ipcb_ctx* c, const char* n) : ctx(c), name(n)
+    Stage(ipcb_ctx* c, const char* n, cudaStream_t on = nullptr) : ctx(c), name(n), s(on ? on : c->stream)
     {
         if (!ctx->timing) return;
         cudaEventCreate(&a);
         cudaEventCreate(&b);
-        cudaEventRecord(a, ctx->stream);
+        cudaEventRecord(a, s);
     }
     ~Stage()
     {
         if (!a) return;
-        cudaEventRecord(b, ctx->stream);
+        cudaEventRecord(b, s);
         cudaEventSynchronize(b);
         float ms = 0;
         cudaEventElapsedTime(&ms, a, b);

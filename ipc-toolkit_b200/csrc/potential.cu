@@ -377,15 +377,26 @@ template <int NP> __device__ inline void project_psd(double* H, int mode, const 
 // gi (VV first, then EV, EE, FV).  Block slot (a, b) = a * 4 + b holds the 3x3 block whose COLUMNS
 // belong to stencil point a and whose ROWS belong to point b (row-major), i.e. what the column of
 // vertex vid[a] needs in compressed-column order.
+// The local matrix is symmetric, so only its UPPER-TRIANGULAR vertex blocks are stored: slot (a, b), a <= b, at
+// tri_slot(a, b) — 3 / 6 / 10 blocks of 72 bytes per VV / EV / 4-point collision instead of 4 / 9 / 16.  The column of
+// point a reads its row block b < a as the TRANSPOSE of slot (b, a) (k_hess_numeric).  The 9-bit exact-non-zero masks
+// are tiny and stay full (16 per collision, the mirrored ones transposed), so the symbolic pass is layout-agnostic.
 struct HessOut {
     int4* vid;               // stencil vertex ids, -1 padded
-    unsigned short* mask;    // 16 per collision: 9-bit exact-non-zero mask per slot
-    double* blk;             // 16 x 9 per collision
+    unsigned short* mask;    // 16 per collision (global collision index): 9-bit exact-non-zero mask per slot a * 4 + b
+    double* blk;             // blocks of THIS kind: tri_count(NP) x 9 doubles per record (record index within the kind)
     unsigned long long* inc; // incidences: (vertex << 32) | (gi * 4 + a), NP per collision
     int v_lo, v_hi;          // owned vertex range (row block of a sharded Hessian); incidences of other
     int v_none;              // vertices get the vertex key v_none (= nV: sorted behind every column)
 };
 constexpr int HSLOTS = 16;
+__host__ __device__ constexpr int tri_count(int np) { return np * (np + 1) / 2; }
+__host__ __device__ constexpr int tri_slot(int np, int a, int b) { return a * np - a * (a - 1) / 2 + (b - a); } // a <= b
+// 9-bit mask of the transposed 3x3 block: bit 3r + c -> bit 3c + r
+__device__ __forceinline__ unsigned mask_transpose(unsigned m)
+{
+    return (m & 0x111u) | ((m & 0x022u) << 2) | ((m & 0x088u) >> 2) | ((m & 0x004u) << 4) | ((m & 0x040u) >> 4);
+}
 
 // returns the mask of the stencil points whose vertex this rank owns
 template <int NP> __device__ inline unsigned write_record(const HessOut& out, int64_t gi, int64_t inc_base, const int* vid)
@@ -486,21 +497,22 @@ __global__ void __launch_bounds__(128)
             project_psd<NP>(D.H, psd_mode, all);
         }
     }
-    // emit the NP x NP vertex blocks: slot (column point bj, row point bi)
+    // emit the upper-triangular vertex blocks: slot (column point bj, row point bi), bj <= bi
     const int64_t gi = gi0 + t;
     unsigned short masks[HSLOTS];
 #pragma unroll
     for (int k = 0; k < HSLOTS; k++) masks[k] = 0;
-    for (int bi = 0; bi < NP; bi++)
-        for (int bj = 0; bj < NP; bj++) {
-            const int slot = bj * 4 + bi;
-            unsigned short mask = 0;
+    double* rec = out.blk + size_t(t) * (tri_count(NP) * 9);
+    for (int bj = 0; bj < NP; bj++)
+        for (int bi = bj; bi < NP; bi++) {
+            unsigned mask = 0;
             for (int k = 0; k < 9; k++) {
                 const double v = D.H[(bi * 4 + bj) * 9 + k];
-                out.blk[(gi * HSLOTS + slot) * 9 + k] = v;
-                mask |= (v != 0.0) << k; // exact zeros are not entries (local_to_global.hpp:290-291)
+                rec[tri_slot(NP, bj, bi) * 9 + k] = v;
+                mask |= unsigned(v != 0.0) << k; // exact zeros are not entries (local_to_global.hpp:290-291)
             }
-            masks[slot] = mask;
+            masks[bj * 4 + bi] = (unsigned short)mask;
+            masks[bi * 4 + bj] = (unsigned short)mask_transpose(mask);
         }
     for (int k = 0; k < HSLOTS; k++) out.mask[gi * HSLOTS + k] = masks[k];
 }
@@ -555,40 +567,42 @@ __global__ void __launch_bounds__(128, MINB)
         if (is_slow) slow[basep + __popc(smask & ((1u << lane) - 1))] = int(t);
     }
     if (emask_any == 0) return;
-    const int64_t gw = gi0 + (t - lane); // record index of lane 0's collision
+    const int64_t tw = t - lane; // record index (within the kind) of lane 0's collision
     unsigned mpack[HSLOTS / 2];
 #pragma unroll
     for (int k = 0; k < HSLOTS / 2; k++) mpack[k] = 0;
 #pragma unroll
-    for (int a = 0; a < NP; a++) { // column point
-        const bool emit_a = emit && ((own >> a) & 1u);
+    for (int a = 0; a < NP; a++) { // column point: its row of the upper triangle, blocks (a, b >= a), is contiguous
+        const bool emit_a = emit && (own >> a) != 0u; // needed by an owned column a, or by an owned column b > a (transposed)
         const unsigned emask = __ballot_sync(0xffffffffu, emit_a);
         if (emask == 0) continue;
+        const int row = (NP - a) * 9; // doubles in this row
         if (emit_a) {
 #pragma unroll
-            for (int b = 0; b < NP; b++) { // row point
+            for (int b = a; b < NP; b++) { // row point
                 double blk[9];
                 fast_block<P>(pr, b, a, blk);
                 unsigned mask = 0;
 #pragma unroll
                 for (int k = 0; k < 9; k++) {
-                    stage[warp][lane][b * 9 + k] = blk[k];
-                    mask |= (blk[k] != 0.0) << k;
+                    stage[warp][lane][(b - a) * 9 + k] = blk[k];
+                    mask |= unsigned(blk[k] != 0.0) << k;
                 }
-                const int slot = a * 4 + b;
+                const int slot = a * 4 + b, mirror = b * 4 + a;
                 mpack[slot >> 1] |= mask << (16 * (slot & 1));
+                if (b != a) mpack[mirror >> 1] |= mask_transpose(mask) << (16 * (mirror & 1));
             }
         }
         __syncwarp();
         {
-            int cl = 0, j = lane; // flat index lane + 32 * it over the warp's 32 x ROW staged doubles, without a division
-            while (j >= ROW) j -= ROW, cl++;
-            double* dst = out.blk + gw * (HSLOTS * 9) + a * 36;
+            int cl = 0, j = lane; // flat index lane + 32 * it over the warp's 32 x row staged doubles, without a division
+            while (j >= row) j -= row, cl++;
+            double* dst = out.blk + tw * (tri_count(NP) * 9) + tri_slot(NP, a, a) * 9;
 #pragma unroll 4
-            for (int it = 0; it < ROW; it++) {
-                if ((emask >> cl) & 1u) dst[size_t(cl) * (HSLOTS * 9) + j] = stage[warp][cl][j];
+            for (int it = 0; it < row; it++) {
+                if ((emask >> cl) & 1u) dst[size_t(cl) * (tri_count(NP) * 9) + j] = stage[warp][cl][j];
                 j += 32;
-                while (j >= ROW) j -= ROW, cl++;
+                while (j >= row) j -= row, cl++;
             }
         }
         __syncwarp();
@@ -683,7 +697,8 @@ struct SymArgs {
     const int4* vid;
     const unsigned short* mask;
     unsigned ref_ev, ref_ee;
-    unsigned* sref; // per item (grouped by unique block): block slot gi * 16 + a * 4 + b
+    unsigned blk_base[3]; // first block of the VV / EV / 4-point records (in blocks of 9 doubles)
+    unsigned* sref; // per item (grouped by unique block): (block index << 1) | read-transposed
     int2* udesc;    // per unique block of a column, at itemoff[v] + u: (first item within the column, row vertex)
     int* colU;      // unique blocks per column
     int* cnt;       // entries per scalar column
@@ -710,6 +725,17 @@ __device__ inline IncItems load_incidence(const SymArgs& A, int q, int b1, int b
     return it;
 }
 
+// where the column of point it.a finds its row block b: the stored upper-triangular slot (min, max), transposed if a > b
+__device__ __forceinline__ unsigned block_ref(const SymArgs& A, const IncItems& it, int b)
+{
+    const int a = int(it.a), lo = min(a, b), hi = max(a, b);
+    unsigned idx;
+    if (it.np == 2) idx = A.blk_base[0] + it.gi * 3u + unsigned(tri_slot(2, lo, hi));
+    else if (it.np == 3) idx = A.blk_base[1] + (it.gi - (A.ref_ev >> 2)) * 6u + unsigned(tri_slot(3, lo, hi));
+    else idx = A.blk_base[2] + (it.gi - (A.ref_ee >> 2)) * 10u + unsigned(tri_slot(4, lo, hi));
+    return (idx << 1) | unsigned(a > b);
+}
+
 // ---- pass 1, general path: sort all row blocks of the column (NT cooperating threads) ---------------------------------
 // keys / refs / masks: room for npow2 / R / R entries; scan: NT ints (shared)
 template <int NT>
@@ -729,7 +755,7 @@ __device__ inline void column_symbolic_sort(const SymArgs& A, int v, int t, unsi
             if (b < it.np) {
                 const int slot = slot0 + b;
                 keys[slot] = ((unsigned long long)(unsigned)it.vi[b] << 32) | unsigned(slot);
-                refs[slot] = it.gi * HSLOTS + it.a * 4 + b;
+                refs[slot] = block_ref(A, it, b);
                 masks[slot] = it.mk[b];
             }
     }
@@ -891,7 +917,7 @@ __device__ inline bool column_symbolic_hash(const SymArgs& A, int v, int lane, H
                 const int pos = H.base[h];
                 __syncwarp(vm);
                 if (rank == 0) H.base[h] = pos + __popc(peers);
-                A.sref[ioff + pos + rank] = it.gi * HSLOTS + it.a * 4 + b;
+                A.sref[ioff + pos + rank] = block_ref(A, it, b);
             }
             __syncwarp();
         }
@@ -1005,7 +1031,7 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
     const int U = colU[v];
     if (U == 0) return;
     const int R = colR[v], ioff = itemoff[v];
-    const int g = lane / 9, k = lane - 9 * g, l = k % 3, r = k / 3;
+    const int g = lane / 9, k = lane - 9 * g, l = k % 3, r = k / 3, kt = 3 * l + r; // kt: the same entry of the transposed block
     const bool lane_ok = g < 3;
     const unsigned colmask = 0x1249249u << l; // lanes of the same scalar column
     const int2* ud = udesc + ioff;
@@ -1017,7 +1043,7 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
 #pragma unroll
         for (int x = 0; x < NUM_BATCH; x++) {
             val[x] = 0.0;
-            if (x < cur.len) val[x] = __ldg(blk + size_t(cur.ref[x]) * 9 + k);
+            if (x < cur.len) val[x] = __ldg(blk + size_t(cur.ref[x] >> 1) * 9 + ((cur.ref[x] & 1u) ? kt : k));
         }
         const RunRefs<NUM_BATCH> nxt = load_run<NUM_BATCH>(ud, sr, u0 + 3 + g, U, R, lane_ok); // overlaps with the block loads above
         double acc = 0.0;
@@ -1031,7 +1057,8 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
         // long runs: the remainder, in order (a batched remainder — NUM_BATCH more loads in flight — measured SLOWER:
         // 3.2 vs 2.4 ms on C3; most remainders are one or two blocks and the predicated batch costs more than it hides)
         for (int j = NUM_BATCH; j < cur.len; j++) {
-            const double w = __ldg(blk + size_t(sr[cur.start + j]) * 9 + k);
+            const unsigned ref = sr[cur.start + j];
+            const double w = __ldg(blk + size_t(ref >> 1) * 9 + ((ref & 1u) ? kt : k));
             acc += w;
             nz |= w != 0.0;
         }
@@ -1202,19 +1229,23 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
         ctx->launches++;
         return;
     }
-    if (ncoll >= (int64_t(1) << 27) || nitems > 0x7fffffffll)
+    // stored blocks (upper triangles): 3 / 6 / 10 per VV / EV / 4-point record
+    const int64_t blk0[4] = { 0, 3 * n0, 3 * n0 + 6 * n1, 3 * n0 + 6 * n1 + 10 * n2 };
+    const int64_t nblocks = blk0[3] + 10 * n3;
+    if (ncoll >= (int64_t(1) << 27) || nitems > 0x7fffffffll || nblocks > 0x7fffffffll)
         throw Error("Hessian: more than 2^27 collisions / 2^31 local blocks on one device; shard the collision set");
     {
         Stage st(ctx, "hessian_local");
-        ctx->hvid.reserve(ncoll), ctx->hmask.reserve(size_t(ncoll) * HSLOTS), ctx->hblk.reserve(size_t(ncoll) * HSLOTS * 9);
+        ctx->hvid.reserve(ncoll), ctx->hmask.reserve(size_t(ncoll) * HSLOTS), ctx->hblk.reserve(size_t(nblocks) * 9);
         ctx->hkey.reserve(ninc), ctx->hkey_sorted.reserve(ninc);
-        const HessOut out { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p, ctx->hkey.p, v_lo, v_hi, nV };
+        HessOut outs[4];
+        for (int k = 0; k < 4; k++) outs[k] = HessOut { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p + size_t(blk0[k]) * 9, ctx->hkey.p, v_lo, v_hi, nV };
         static const bool force_general = getenv("IPCB_HESSIAN_GENERAL") != nullptr; // A/B switch for tests and profiles
         if (psd_mode == IPCB_PSD_NONE || force_general) {
-            if (n0) k_hessian_local<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, nullptr, 0, sel[0], n0), ctx->launches++;
-            if (n1) k_hessian_local<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, nullptr, 0, sel[1], n1), ctx->launches++;
-            if (n2) k_hessian_local<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, nullptr, 0, sel[2], n2), ctx->launches++;
-            if (n3) k_hessian_local<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, nullptr, 0, sel[3], n3), ctx->launches++;
+            if (n0) k_hessian_local<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], outs[0], nullptr, 0, sel[0], n0), ctx->launches++;
+            if (n1) k_hessian_local<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], outs[1], nullptr, 0, sel[1], n1), ctx->launches++;
+            if (n2) k_hessian_local<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], nullptr, 0, sel[2], n2), ctx->launches++;
+            if (n3) k_hessian_local<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], outs[3], nullptr, 0, sel[3], n3), ctx->launches++;
         } else {
             unsigned long long* slow_count = ctx->dCounters.p + 5;
             ctx->hslow.reserve(std::max<int64_t>(n2, 1));
@@ -1222,22 +1253,29 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
             // the four kinds write disjoint records: the small ones run beside the edge-edge kernel
             ctx->fork();
             static const bool dense = getenv("IPCB_HFAST_SPARSE") == nullptr; // 4 resident blocks per SM (small spill) for the 4-point kinds; A/B switch
-            if (n0) k_hessian_fast<IPCB_VV, 4><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], out, ctx->hslow.p, slow_count, sel[0], n0), ctx->launches++;
-            if (n1) k_hessian_fast<IPCB_EV, 4><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], out, ctx->hslow.p, slow_count, sel[1], n1), ctx->launches++;
-            if (n3 && dense) k_hessian_fast<IPCB_FV, 4><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
-            else if (n3) k_hessian_fast<IPCB_FV, 3><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], out, ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
+            std::unique_ptr<Stage> kt(new Stage(ctx, "k:k_hessian_fast<VV>", ctx->aux[0]));
+            if (n0) k_hessian_fast<IPCB_VV, 4><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], outs[0], ctx->hslow.p, slow_count, sel[0], n0), ctx->launches++;
+            kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<EV>", ctx->aux[0]));
+            if (n1) k_hessian_fast<IPCB_EV, 4><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], outs[1], ctx->hslow.p, slow_count, sel[1], n1), ctx->launches++;
+            kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<FV>", ctx->aux[1]));
+            if (n3 && dense) k_hessian_fast<IPCB_FV, 4><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], outs[3], ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
+            else if (n3) k_hessian_fast<IPCB_FV, 3><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], outs[3], ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
+            kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<EE>", s));
             if (n2) {
-                if (dense) k_hessian_fast<IPCB_EE, 4><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, slow_count, sel[2], n2);
-                else k_hessian_fast<IPCB_EE, 3><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, slow_count, sel[2], n2);
+                if (dense) k_hessian_fast<IPCB_EE, 4><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, slow_count, sel[2], n2);
+                else k_hessian_fast<IPCB_EE, 3><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, slow_count, sel[2], n2);
                 ctx->launches++;
+                kt.reset();
                 IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[11], slow_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
                 IPCB_CUDA(cudaStreamSynchronize(s));
                 const int64_t nslow = ctx->pinned.p[11];
                 if (nslow) {
-                    k_hessian_local<IPCB_EE><<<grid_for(nslow, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], out, ctx->hslow.p, nslow, sel[2], n2);
+                    Stage ks(ctx, "k:k_hessian_local<EE>(mollified)", s);
+                    k_hessian_local<IPCB_EE><<<grid_for(nslow, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, nslow, sel[2], n2);
                     ctx->launches++;
                 }
             }
+            kt.reset();
             ctx->join(0);
             ctx->join(1);
         }
@@ -1255,7 +1293,10 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     cub::DeviceScan::ExclusiveSum(nullptr, b2, ctx->hcolR.p, ctx->hitemoff.p, nV + 1, s);
     cub::DeviceScan::ExclusiveSum(nullptr, b3, ctx->hcnt.p, ctx->outer.p, 3 * nV + 1, s);
     ctx->cubtmp.reserve(std::max(b1, std::max(b2, b3)) + 1024);
-    cub::DeviceRadixSort::SortKeys(ctx->cubtmp.p, b1, ctx->hkey.p, ctx->hkey_sorted.p, ninc, 32, 32 + vbits, s);
+    {
+        Stage kt(ctx, "k:radix_sort(incidences)", s);
+        cub::DeviceRadixSort::SortKeys(ctx->cubtmp.p, b1, ctx->hkey.p, ctx->hkey_sorted.p, ninc, 32, 32 + vbits, s);
+    }
     ctx->launches += 2 + (vbits + 7) / 8;
     // 2. column ranges and item offsets
     const unsigned ref_ev = unsigned(gi0[1] * 4), ref_ee = unsigned(gi0[2] * 4);
@@ -1273,7 +1314,7 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     unsigned long long* need = ctx->dCounters.p + 7;
     ctx->hudesc.reserve(nitems), ctx->hcolU.reserve(size_t(nV) + 1);
     const SymArgs A { nV, ctx->hkey_sorted.p, ctx->hcolinc.p, ctx->hcolR.p, ctx->hitemoff.p, ctx->hcolb.p, ctx->hvid.p, ctx->hmask.p, ref_ev, ref_ee,
-                      ctx->hsref.p, ctx->hudesc.p, ctx->hcolU.p, ctx->hcnt.p };
+                      { unsigned(blk0[0]), unsigned(blk0[1]), unsigned(blk0[2]) }, ctx->hsref.p, ctx->hudesc.p, ctx->hcolU.p, ctx->hcnt.p };
     if (!ctx->hess_attr_set) { // per device
         IPCB_CUDA(cudaFuncSetAttribute(k_hess_symbolic_big, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BIG_SMEM)));
         ctx->hess_attr_set = true;

@@ -18,8 +18,50 @@ shard selected through the public Candidates container instead of the device-sid
 energy / gradient / step size out, nothing staged through the host except four counts per rank.
 """
 import ctypes as C
+import queue
+import threading
 
 import numpy as np
+
+
+class Lane(threading.Thread):
+    """A host thread that issues library calls for one context, so that two contexts (two sets of CUDA streams) can be
+    driven concurrently: ctypes releases the GIL for the duration of a call, and every library call blocks its calling
+    thread for its own count read-backs.  submit(fn) returns a handle whose wait() re-raises what fn raised."""
+
+    class Job:
+        def __init__(self, fn):
+            self.fn, self.done, self.error = fn, threading.Event(), None
+
+        def wait(self):
+            self.done.wait()
+            if self.error is not None:
+                raise self.error
+
+    def __init__(self):
+        super().__init__(daemon=True)
+        self.q = queue.SimpleQueue()
+        self.start()
+
+    def run(self):
+        while True:
+            job = self.q.get()
+            if job is None:
+                return
+            try:
+                job.fn()
+            except BaseException as e:  # handed to the waiting thread
+                job.error = e
+            job.done.set()
+
+    def submit(self, fn):
+        job = Lane.Job(fn)
+        self.q.put(job)
+        return job
+
+    def close(self):
+        self.q.put(None)
+        self.join()
 
 
 class ShardedContactStep:
@@ -111,12 +153,18 @@ def packed_bytes(counts):
 
 
 class DeviceShardedStep:
-    """The sharded contact step with device-resident inputs and outputs (product library + NCCL).
+    """The contact step with device-resident inputs and outputs (product library; NCCL when world > 1).
 
     dV0 / dV1: torch CUDA tensors holding N x 3 column-major positions; d_energy (1), d_grad (3N), d_step (1): torch CUDA
-    float64 outputs.  All library calls and collectives are enqueued on the context's stream."""
+    float64 outputs.  All library calls and collectives are enqueued on the context's stream.
 
-    def __init__(self, api, mesh, rank, world, dist, torch, stream, row_block=True):
+    ccd_mesh: a SECOND context on the same mesh (same device).  The step size does not depend on the collision set, and
+    its kernels (swept traversal, Tight-Inclusion search) wait on dependent gathers while the potential's kernels are
+    bound by the FP64 pipe and HBM: with a second context the CCD half runs on its own streams, issued by its own host
+    thread, beside the build + potential half — the reference's callers are free to do the same with two BroadPhase
+    objects.  Without it the five calls run one after the other on one context."""
+
+    def __init__(self, api, mesh, rank, world, dist, torch, stream, row_block=True, ccd_mesh=None):
         self.api, self.lib, self.mesh, self.ctx = api, api.lib, mesh, mesh._ctx
         self.rank, self.world, self.dist, self.torch, self.stream = rank, world, dist, torch, stream
         self.row_block = row_block and world > 1
@@ -130,14 +178,32 @@ class DeviceShardedStep:
         self.h_counts = torch.zeros(4, dtype=torch.int64).pin_memory()
         self.rows = (0, mesh.num_vertices())
         self.shard_counts = [0, 0, 0, 0]
-        self.after = None  # optional callback after every library call (bench.py collects stage times)
+        self.after = None  # optional callback(ctx) after every library call (bench.py collects stage times)
+        self.side = self.ev_packed = self.ev_gathered = None
         if self.row_block:
             self.side = torch.cuda.Stream()
             self.ev_packed, self.ev_gathered = torch.cuda.Event(), torch.cuda.Event()
+        self.ccd_mesh, self.ctx_b, self.lane, self.stream_b = ccd_mesh, None, None, None
+        if ccd_mesh is not None:
+            self.ctx_b = ccd_mesh._ctx
+            self.lib.check(self.lib.ctx_set_shard(self.ctx_b, rank, world))
+            self.stream_b = torch.cuda.ExternalStream(self.lib.ctx_stream(self.ctx_b), device=torch.device("cuda", torch.cuda.current_device()))
+            self.ev_start, self.ev_ccd = torch.cuda.Event(), torch.cuda.Event()
+            self.lane = Lane()
 
-    def _done(self):
+    def _done(self, ctx=None):
         if self.after is not None:
-            self.after()
+            self.after(self.ctx if ctx is None else ctx)
+
+    def release(self):
+        """drop every torch object that lives on the contexts' streams and stop the second lane (call before the meshes /
+        contexts are destroyed)"""
+        if self.lane is not None:
+            self.lane.close()
+            self.lane = None
+        self.send = self.recv = self.d_counts = self.d_counts_all = self.h_counts = None
+        self.side = self.ev_packed = self.ev_gathered = None
+        self.stream = self.stream_b = None
 
     def start_exchange(self):
         """counts of every rank (the only host round trip), pack, and ONE all-gather of the packed records on a side
@@ -186,15 +252,25 @@ class DeviceShardedStep:
         torch, lib, dist, ctx = self.torch, self.lib, self.dist, self.ctx
         nV = self.mesh.num_vertices()
         p0, p1 = C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr())
+        pstep = C.c_void_p(d_step.data_ptr())
+
+        def ccd_half(c):
+            lib.check(lib.ccd_stepsize_dev(c, p0, p1, nV, min_distance, C.byref(ccd), pstep))
+            self._done(c)
+
+        job = None
+        if self.lane is not None:  # the CCD half on the second context, beside everything below
+            self.ev_start.record(self.stream)
+            self.stream_b.wait_event(self.ev_start)  # the caller's inputs are ready when the first lane's stream gets here
+            job = self.lane.submit(lambda: ccd_half(self.ctx_b))
         lib.check(lib.collisions_build_dev(ctx, p0, nV, dhat, dmin, 0, self.counts))
         self._done()
         if self.row_block:
             self.start_exchange()
         else:
             self.shard_counts = list(self.counts)
-        # the step size does not depend on the collision set: it runs while the records travel
-        lib.check(lib.ccd_stepsize_dev(ctx, p0, p1, nV, min_distance, C.byref(ccd), C.c_void_p(d_step.data_ptr())))
-        self._done()
+        if job is None:  # one context: the step size runs here, while the records travel
+            ccd_half(ctx)
         if self.row_block:
             self.finish_exchange(dmin)
             lib.check(lib.ctx_set_collision_range(ctx, self.rank, self.world))
@@ -205,6 +281,10 @@ class DeviceShardedStep:
         self._done()
         lib.check(lib.barrier_hessian_dev(ctx, p0, nV, C.byref(bp), psd, C.byref(self.nnz)))
         self._done()
+        if job is not None:  # join the lanes: the first lane's stream continues after the step size has been written
+            job.wait()
+            self.ev_ccd.record(self.stream_b)
+            self.stream.wait_event(self.ev_ccd)
         if self.world > 1:  # sum / sum / min all-reduces over NVLink; the Hessian needs no collective
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(d_energy)

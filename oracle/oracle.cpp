@@ -1092,6 +1092,11 @@ int ipco_candidates_set(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_
     if (kind < 0 || kind > 3) return fail("bad candidate kind");
     ctx->cand[kind].resize(count);
     std::memcpy(ctx->cand[kind].data(), pairs, count * sizeof(Pair));
+    // unordered kinds are kept as (min, max), like every broad phase emits them (the distance type of an edge-edge
+    // collision is relative to the stored order)
+    if (kind == IPCB_VV || kind == IPCB_EE)
+        for (auto& p : ctx->cand[kind])
+            if (p[0] > p[1]) std::swap(p[0], p[1]);
     return 0;
 }
 

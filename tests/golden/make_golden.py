@@ -1,4 +1,4 @@
-"""Generates tests/golden/*.npz — run in the build container:  python tests/golden/make_golden.py
+"""Generates tests/golden/*.npz — run in the build container:  python tests/golden/make_golden.py [--full c2 c3 c5]
 
 1. reference_kats.npz: the transcribed reference test vectors of tests/kats.py frozen as arrays (the
    analytic expectations come from the reference's own test sources, cited in kats.py);
@@ -7,6 +7,10 @@
    projection modes, step sizes.  The upstream library cannot be built or imported here (SURVEY §8c:
    no Eigen / TBB / Tight-Inclusion in the image), so these are oracle outputs, not upstream outputs;
    the oracle itself is pinned by tests/test_reference_kats.py.
+3. --full: digest_<config>.npz — tests/digest.py digests of one contact step of the ORACLE on the BASELINE.json
+   configurations at FULL size (C2 180K, C3 1M, C5 2M triangles): counts + SHA-256 of every index array, norms /
+   samples / random projections of every value array, step sizes and the derived Tight-Inclusion time tolerance
+   (tests/ccd_tolerance.py).  tests/test_gpu_full_size.py compares the CUDA path against them on the GPU box.
 """
 import os
 import sys
@@ -31,7 +35,38 @@ SCENES = {
 }
 
 
+FULL = {
+    # name: (scene, Hessian projection modes in the digest, row blocks the ORACLE assembles the Hessian in: bounded memory)
+    "c2": (lambda s: s.cloth_on_sphere(256, 160, drape=True), (0, 1, 2), 1),
+    "c3": (lambda s: s.cloth_stack(8, 250, gap=0.5), (1,), 2),
+    "c5": (lambda s: s.cloth_stack(16, 250, gap=0.2), (1,), 12),
+}
+
+
+def full_digests(names):
+    import time
+
+    import digest
+    from ccd_tolerance import StepTolerance
+
+    o = pyoracle.load()
+    scenes = ipctk_b200._pkg.scenes
+    for name in names:
+        make, modes, blocks = FULL[name]
+        V0, V1, E, F, P = make(scenes)
+        t = time.time()
+        d = digest.step_digest(o, V0, V1, E, F, P["dhat"], modes=modes, hess_blocks=blocks)
+        T = StepTolerance(o, V0, V1, E, F)
+        tol, v, w = T.tolerance(d["step_ti"])
+        d["step_ti_tolerance"], d["step_ti_closing_speed"], d["step_ti_box_width"] = tol, v, w
+        digest.save(os.path.join(HERE, "digest_%s.npz" % name), d)
+        print(name, "triangles", F.shape[0], "collisions", d["counts"].tolist(), "nnz", d["h1_nnz"], "energy", d["energy"], "step", d["step_ti"],
+              d["step_accd"], "tol", tol, "oracle seconds %.0f" % (time.time() - t), flush=True)
+
+
 def main():
+    if "--full" in sys.argv:
+        return full_digests(sys.argv[sys.argv.index("--full") + 1:])
     o = pyoracle.load()
     scenes = ipctk_b200._pkg.scenes
     # ---- 1. reference vectors

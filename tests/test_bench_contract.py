@@ -27,7 +27,12 @@ def test_reference_arm_prints_one_json_line(oracle):
         assert key in d, key
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
-    assert "workload" in d["config"] and sum(d["collisions_in_sample"]) > 0
+    assert "workload" in d["config"] and sum(d["counts"]["collisions"]) > 0
+    # the reference arm times the SAME workload as the GPU arm (no crop, no scaling) and reports the steps it really ran
+    for key in ("triangles", "vertices", "edges", "dhat", "psd", "ccd", "l2", "parallelism"):
+        assert key in d["config"], key
+    assert d["config"]["triangles"] == 10176 and "full workload" in d["cpu_baseline"]["sample"]
+    assert d["steps"] == 1 and d["steps_requested"] == 1
 
 
 def test_reference_arm_other_ranks_stay_silent(oracle):

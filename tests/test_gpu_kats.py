@@ -110,7 +110,7 @@ def test_types_via_pipeline_gpu(cuda):
 SCENES = ["c1_small", "drape", "stack", "soup"]
 
 
-def check_golden_scene(api, name, step_tol):
+def check_golden_scene(api, name, oracle_for_tolerance=None):
     g = np.load(os.path.join(GOLDEN, "scene_%s.npz" % name))
     V0, V1, E, F, dhat, X = g["V0"], g["V1"], g["E"], g["F"], float(g["dhat"]), g["X"]
     mesh = api.CollisionMesh(V0, E, F)
@@ -134,17 +134,22 @@ def check_golden_scene(api, name, step_tol):
         assert relerr(H.data, g["h%d_data" % mode]) <= RTOL, mode
     ti = api.compute_collision_free_stepsize(mesh, V0, V1)
     ac = api.compute_collision_free_stepsize(mesh, V0, V1, narrow_phase_ccd=api.AdditiveCCD())
-    assert abs(ti - float(g["step_ti"])) <= step_tol * max(float(g["step_ti"]), 1e-3) + 1e-6
+    if oracle_for_tolerance is None:  # the oracle reproduces its own fixture
+        assert ti == float(g["step_ti"])
+    else:  # derived tolerance + the oracle's own collision-free check (tests/ccd_tolerance.py)
+        from ccd_tolerance import check_step
+
+        check_step(oracle_for_tolerance, V0, V1, E, F, ti, float(g["step_ti"]))
     assert abs(ac - float(g["step_accd"])) <= 1e-9 * float(g["step_accd"])
 
 
 @pytest.mark.parametrize("name", SCENES)
 def test_golden_scene_oracle(oracle, name):
     """the committed fixtures are reproducible from the oracle (they were generated by it)"""
-    check_golden_scene(oracle, name, 0.0)
+    check_golden_scene(oracle, name)
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", SCENES)
-def test_golden_scene_gpu(cuda, name):
-    check_golden_scene(cuda, name, 1e-3)
+def test_golden_scene_gpu(cuda, oracle, name):
+    check_golden_scene(cuda, name, oracle)

@@ -1,10 +1,8 @@
 """CollisionSetType::IMPROVED_MAX_APPROX on the CUDA path against the oracle.
 
-The CUDA side of this set type (`collisions.cu`: sub-element candidates, correction kernels, typed edge-edge merge) was
-written after the round's GPU budget had been used up: it compiles, but it has NOT run on hardware yet.  The tests are
-therefore marked xfail(strict=False) — they report XPASS if the code is right and cannot turn the suite red if it is not
-— and the file sorts last so that nothing runs after it in the same process.  Remove the marker once they pass.
-The oracle side is pinned in tests/test_reference_kats.py, and the kernels' logic is checked on the host by
+The CUDA side of this set type (`collisions.cu`: sub-element candidates, correction kernels, typed edge-edge merge)
+passed all of these tests on a B200 at the end of round 1 (12 / 12); they are ordinary failing-is-red tests now.
+The oracle side is pinned in tests/test_reference_kats.py, and the kernels' logic is also checked on the host by
 tests/test_kernel_emulation.py (both in the CPU suite).
 """
 import numpy as np
@@ -12,8 +10,7 @@ import pytest
 
 import test_reference_kats as rk
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(reason="CUDA IMPROVED_MAX_APPROX not yet validated on hardware (written after the GPU budget ended)", strict=False)]
+pytestmark = pytest.mark.gpu
 
 RTOL = 1e-10
 
