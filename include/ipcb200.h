@@ -107,6 +107,19 @@ void* IPCB_FN(ctx_stream)(ipcb_ctx* ctx);
  * host and keeps device mirrors.  E is nE x 2, F is nF x 3. */
 int IPCB_FN(mesh_set)(ipcb_ctx* ctx, int32_t nV, const double* rest_positions, int32_t ld_rest,
                       int32_t nE, const int32_t* E, int32_t ldE, int32_t nF, const int32_t* F, int32_t ldF);
+/* CollisionMesh::can_collide (collision_mesh.hpp:338, CollisionFilter collision_filter.hpp:30-111): which pairs of
+ * vertices — and the primitives containing them (broad_phase.cpp:127-202: no shared vertex AND some pair of their
+ * vertices can collide) — may become candidates.  The descriptor is the INTERSECTION of the factories of
+ * collision_filter.hpp:113-143 that are data, not code:
+ *   patch_ids (nV labels, or NULL = off): make_vertex_patches_filter / make_connected_components_filter —
+ *       vertices with equal labels never collide;
+ *   n_dynamic (< 0 = off): make_static_obstacle_filter — pairs of vertices with index >= n_dynamic never collide.
+ * Arbitrary callables, unions and negations cannot cross a C ABI: the toolkit adapter applies those as a host
+ * post-filter on the fetched candidates (cpp/ipc_toolkit_adapter.hpp).  The filter applies to every later broad-phase
+ * / candidate / collision / step-size build on this context; mesh_set resets it to accept-all.
+ * Like the reference, the codimensional vertex-vertex and edge-vertex passes of Candidates::build evaluate the filter
+ * on the ids of their re-indexed vertex subsets (candidates.cpp:61,66-77,83-108). */
+int IPCB_FN(mesh_set_collision_filter)(ipcb_ctx* ctx, const int32_t* patch_ids /* nV or NULL */, int32_t n_dynamic);
 int IPCB_FN(mesh_num_codim_vertices)(ipcb_ctx* ctx, int32_t* n);
 int IPCB_FN(mesh_num_codim_edges)(ipcb_ctx* ctx, int32_t* n);
 int IPCB_FN(mesh_faces_to_edges)(ipcb_ctx* ctx, int32_t* f2e /* nF x 3 col-major, ld = nF */);

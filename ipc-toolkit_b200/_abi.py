@@ -26,6 +26,7 @@ HOST_API = {
     "backend_name": (C.c_char_p, []),
     "ctx_stream": (P, [P]),
     "mesh_set": (C.c_int, [P, c_i32, P, c_i32, c_i32, P, c_i32, c_i32, P, c_i32]),
+    "mesh_set_collision_filter": (C.c_int, [P, P, c_i32]),
     "mesh_num_codim_vertices": (C.c_int, [P, C.POINTER(c_i32)]),
     "mesh_num_codim_edges": (C.c_int, [P, C.POINTER(c_i32)]),
     "mesh_faces_to_edges": (C.c_int, [P, P]),

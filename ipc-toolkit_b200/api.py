@@ -65,6 +65,50 @@ class AdditiveCCD:  # ccd/additive_ccd.hpp:21-26
         return _abi.CcdParams(1, 0.0, self.max_iterations, self.conservative_rescaling)
 
 
+class CollisionFilter:
+    """ipc::CollisionFilter (collision_filter.hpp:30-111) restricted to what is DATA: the intersection of a vertex-patch
+    filter and a static-obstacle filter (the factories of collision_filter.hpp:113-143).  `a & b` composes two of them;
+    unions, negations and arbitrary callables cannot cross the C ABI (the C++ adapter post-filters those on the host)."""
+
+    def __init__(self, patch_ids=None, n_dynamic=None):
+        self.patch_ids = None if patch_ids is None else np.ascontiguousarray(patch_ids, dtype=np.int32).reshape(-1)
+        self.n_dynamic = None if n_dynamic is None else int(n_dynamic)
+
+    def __call__(self, vi, vj):
+        ok = True
+        if self.patch_ids is not None:
+            ok = ok and self.patch_ids[vi] != self.patch_ids[vj]
+        if self.n_dynamic is not None:
+            ok = ok and (vi < self.n_dynamic or vj < self.n_dynamic)
+        return bool(ok)
+
+    def __and__(self, other):
+        if self.patch_ids is not None and other.patch_ids is not None:
+            raise NotImplementedError("the intersection of two patch filters is not a patch filter")
+        n = [x for x in (self.n_dynamic, other.n_dynamic) if x is not None]
+        return CollisionFilter(self.patch_ids if self.patch_ids is not None else other.patch_ids, min(n) if n else None)
+
+
+def make_vertex_patches_filter(patch_ids):  # collision_filter.hpp:113-118
+    return CollisionFilter(patch_ids=patch_ids)
+
+
+def make_static_obstacle_filter(n_dynamic):  # collision_filter.hpp:120-131
+    return CollisionFilter(n_dynamic=n_dynamic)
+
+
+def make_connected_components_filter(faces, num_vertices=None):  # collision_filter.cpp:9-18
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import connected_components
+
+    f = np.asarray(faces, dtype=np.int64).reshape(-1, 3)
+    n = int(f.max()) + 1 if num_vertices is None else int(num_vertices)
+    i = np.concatenate([f[:, 0], f[:, 1], f[:, 2]])
+    j = np.concatenate([f[:, 1], f[:, 2], f[:, 0]])
+    A = sp.coo_matrix((np.ones(i.size), (i, j)), shape=(n, n))
+    return CollisionFilter(patch_ids=connected_components(A, directed=False)[1])
+
+
 def _f64(a):
     """column-major float64 view/copy (Eigen::MatrixXd layout) and its leading dimension"""
     a = np.asfortranarray(a, dtype=np.float64)
@@ -94,6 +138,10 @@ def make_api(lib):
     ns.TightInclusionCCD = TightInclusionCCD
     ns.AdditiveCCD = AdditiveCCD
     ns.edges_from_faces = edges_from_faces
+    ns.CollisionFilter = CollisionFilter
+    ns.make_vertex_patches_filter = make_vertex_patches_filter
+    ns.make_static_obstacle_filter = make_static_obstacle_filter
+    ns.make_connected_components_filter = make_connected_components_filter
 
     class CollisionMesh:
         """ipc::CollisionMesh(rest_positions, edges, faces) — collision_mesh.cpp:15-127"""
@@ -113,6 +161,24 @@ def make_api(lib):
             lib.check(lib.mesh_set(self._ctx, rest.shape[0], rp, rld, e.shape[0], ep, eld, f.shape[0], fp, fld))
             self._cand_gen = 0
             self._coll_gen = 0
+            self._can_collide = CollisionFilter()
+
+        @property
+        def can_collide(self):
+            """CollisionMesh::can_collide (collision_mesh.hpp:338): a CollisionFilter descriptor"""
+            return self._can_collide
+
+        @can_collide.setter
+        def can_collide(self, f):
+            if not isinstance(f, CollisionFilter):
+                raise TypeError("can_collide must be a CollisionFilter descriptor (patch labels and / or n_dynamic)")
+            ids = f.patch_ids
+            if ids is not None and ids.size != self.num_vertices():
+                raise ValueError("patch_ids must hold one label per vertex")
+            lib.check(lib.mesh_set_collision_filter(self._ctx, None if ids is None else ids.ctypes.data_as(C.c_void_p),
+                                                    -1 if f.n_dynamic is None else f.n_dynamic))
+            self._can_collide = f
+            self._cand_gen += 1  # resident candidates of the old filter are stale
 
         def close(self):
             """destroy the library context now (device buffers, streams); the object is unusable afterwards"""

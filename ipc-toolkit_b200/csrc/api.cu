@@ -340,11 +340,43 @@ int ipcb_mesh_set(ipcb_ctx* ctx, int32_t nV, const double* rest, int32_t ld_rest
         upload(ctx, ctx->dCodimV, ctx->codimV);
         upload(ctx, ctx->dCodimE, ctx->codimE);
         IPCB_CUDA(cudaStreamSynchronize(ctx->stream)); // host vectors go out of scope
+        // ids of the codim edges' endpoints in the re-indexed vertex set of the codimensional edge-vertex pass:
+        // [codim vertices; referenced vertices of the codim edges, ascending] (candidates.cpp:83-108)
+        {
+            std::vector<int32_t> ref;
+            for (int e : ctx->codimE) ref.push_back(ctx->hE[2 * size_t(e)]), ref.push_back(ctx->hE[2 * size_t(e) + 1]);
+            std::sort(ref.begin(), ref.end());
+            ref.erase(std::unique(ref.begin(), ref.end()), ref.end());
+            const int nCV = int(ctx->codimV.size());
+            auto local = [&](int v) { return nCV + int(std::lower_bound(ref.begin(), ref.end(), v) - ref.begin()); };
+            std::vector<int2> le(ctx->codimE.size());
+            for (size_t i = 0; i < le.size(); i++)
+                le[i] = make_int2(local(ctx->hE[2 * size_t(ctx->codimE[i])]), local(ctx->hE[2 * size_t(ctx->codimE[i]) + 1]));
+            upload(ctx, ctx->dCodimELocal, le);
+            IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        ctx->filter_patches = false, ctx->filter_n_dynamic = -1; // a new mesh accepts all pairs
         ctx->built = false;
         ctx->coll_valid = false;
         ctx->adj_ready = false;
         for (auto& c : ctx->cand) c.count = 0;
         for (auto& c : ctx->coll) c.count = 0;
+        for (auto& c : ctx->detected) c.count = 0;
+    });
+}
+int ipcb_mesh_set_collision_filter(ipcb_ctx* ctx, const int32_t* patch_ids, int32_t n_dynamic)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        ctx->filter_patches = patch_ids != nullptr && ctx->nV > 0;
+        if (ctx->filter_patches) {
+            ctx->dPatch.reserve(ctx->nV);
+            IPCB_CUDA(cudaMemcpyAsync(ctx->dPatch.p, patch_ids, sizeof(int32_t) * ctx->nV, cudaMemcpyHostToDevice, ctx->stream));
+            IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+        ctx->filter_n_dynamic = n_dynamic;
+        ctx->built = false; // resident candidates of the old filter are stale
+        for (auto& c : ctx->cand) c.count = 0;
         for (auto& c : ctx->detected) c.count = 0;
     });
 }

@@ -158,13 +158,20 @@ __global__ void k_face_boxes(int n, const int4* __restrict__ F, const FBox* __re
     prim[i] = make_int4(f.x, f.y, f.z, i);
 }
 // gather a subset (codimensional vertices / edges) of a PrimSet
+// local: the codimensional passes of Candidates::build work on RE-INDEXED vertex subsets, and the collision filter sees
+// those ids (candidates.cpp:61,66-77,83-108).  With a filter the vertex ids of the gathered primitives are replaced by
+// the local ones (0: keep global ids; 1: a vertex's position in the subset; 2: the table `local_ids`); the primitive id
+// (.w, what candidates are made of) stays global.  These passes never test for shared vertices.
 __global__ void k_gather_set(int n, const int* __restrict__ ids, const FBox* __restrict__ box, const int4* __restrict__ prim,
-                             FBox* __restrict__ obox, int4* __restrict__ oprim)
+                             FBox* __restrict__ obox, int4* __restrict__ oprim, int local, const int2* __restrict__ local_ids)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     obox[i] = box[ids[i]];
-    oprim[i] = prim[ids[i]];
+    int4 p = prim[ids[i]];
+    if (local == 1) p.x = i;
+    if (local == 2) p.x = local_ids[i].x, p.y = local_ids[i].y;
+    oprim[i] = p;
 }
 
 // ---------------------------------------------------------------------------
@@ -551,13 +558,36 @@ template <int QN, int TN> __device__ __forceinline__ bool shares_vertex(int4 a, 
     return s;
 }
 
+// CollisionFilter descriptor on the device (ipcb_mesh_set_collision_filter)
+struct FilterView {
+    const int* patch; // per-vertex labels or nullptr
+    int n_dynamic;    // < 0: off
+};
+__device__ __forceinline__ bool can_vertices_collide(const FilterView& f, int vi, int vj)
+{
+    return (!f.patch || __ldg(f.patch + vi) != __ldg(f.patch + vj)) && (f.n_dynamic < 0 || vi < f.n_dynamic || vj < f.n_dynamic);
+}
+// broad_phase.cpp:127-202: some pair of vertices of the two primitives can collide
+template <int QN, int TN> __device__ __forceinline__ bool any_can_collide(const FilterView& f, int4 a, int4 b)
+{
+    const int qa[3] = { a.x, a.y, a.z }, tb[3] = { b.x, b.y, b.z };
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < QN; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) any |= can_vertices_collide(f, qa[i], tb[j]);
+    return any;
+}
+
 // MODE 0: emit (query, target); 1: emit (target, query); 2: self, emit (min, max)
+// flags: bit 0 = reject pairs that share a vertex, bit 1 = apply the collision filter
 template <int MODE, int QN, int TN>
 __global__ void __launch_bounds__(TRAV_BLOCK)
     k_traverse(int q_begin, int q_end, const FBox* __restrict__ qbox, const int4* __restrict__ qprim,
                const Node* __restrict__ nodes, int n_target, const FBox* __restrict__ tbox, const int4* __restrict__ tprim,
-               int2* __restrict__ out, unsigned long long* counter, unsigned long long capacity, int check_shared)
+               int2* __restrict__ out, unsigned long long* counter, unsigned long long capacity, int flags, FilterView filter)
 {
+    const bool check_shared = flags & 1, filtered = flags & 2;
     __shared__ int2 stage[TRAV_BLOCK / 32][STAGE_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -603,7 +633,7 @@ __global__ void __launch_bounds__(TRAV_BLOCK)
                 const int4 tp = h == 0 ? tp0 : tp1;
                 bool emit = false;
                 int2 pr = make_int2(0, 0);
-                if (hit >= 0 && (!check_shared || !shares_vertex<QN, TN>(qp, tp))) {
+                if (hit >= 0 && (!check_shared || !shares_vertex<QN, TN>(qp, tp)) && (!filtered || any_can_collide<QN, TN>(filter, qp, tp))) {
                     emit = true;
                     if (MODE == 0) pr = make_int2(qp.w, tp.w);
                     else if (MODE == 1) pr = make_int2(tp.w, qp.w);
@@ -698,9 +728,11 @@ struct TraverseJob {
         const unsigned long long cap = out->pairs.cap;
         const unsigned grid = grid_for(q_end - q_begin, TRAV_BLOCK);
         Stage kt(ctx, mode == 2 && qn == 2 ? "k:k_traverse<EE>" : (mode == 1 && tn == 3 ? "k:k_traverse<FV>" : "k:k_traverse<other>"), s);
+        const int flags = (check_shared ? 1 : 0) | (ctx->filter_on() ? 2 : 0);
+        const FilterView filter { ctx->filter_patches ? ctx->dPatch.p : nullptr, ctx->filter_n_dynamic };
 #define IPCB_TRAVERSE(M, QN, TN)                                                                                                    \
     k_traverse<M, QN, TN><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes.p, t->n, t->sbox.p, t->sprim.p, \
-                                                      out->pairs.p, counter, cap, check_shared)
+                                                      out->pairs.p, counter, cap, flags, filter)
         switch (mode * 100 + qn * 10 + tn) {
         case 211: IPCB_TRAVERSE(2, 1, 1); break; // vertex - vertex
         case 21: IPCB_TRAVERSE(0, 2, 1); break;  // edges walk the vertex tree
@@ -864,8 +896,9 @@ void candidates_build(ipcb_ctx* ctx, bool swept, double r)
         cudaStream_t s = ctx->stream;
         ctx->cvset.n = ncv;
         ctx->cvset.box.reserve(ncv), ctx->cvset.prim.reserve(ncv);
+        const bool filtered = ctx->filter_on();
         k_gather_set<<<grid_for(ncv, 256), 256, 0, s>>>(ncv, ctx->dCodimV.p, ctx->vset.box.p, ctx->vset.prim.p, ctx->cvset.box.p,
-                                                      ctx->cvset.prim.p);
+                                                      ctx->cvset.prim.p, filtered ? 1 : 0, nullptr);
         ctx->launches++;
         build_tree(ctx, ctx->cvset, ctx->cvtree, true);
         if (ncv >= 2 && ctx->shard_rank == 0) // tiny sets are not sharded: rank 0 owns them
@@ -874,7 +907,7 @@ void candidates_build(ipcb_ctx* ctx, bool swept, double r)
             ctx->ceset.n = nce;
             ctx->ceset.box.reserve(nce), ctx->ceset.prim.reserve(nce);
             k_gather_set<<<grid_for(nce, 256), 256, 0, s>>>(nce, ctx->dCodimE.p, ctx->eset.box.p, ctx->eset.prim.p, ctx->ceset.box.p,
-                                                          ctx->ceset.prim.p);
+                                                          ctx->ceset.prim.p, filtered ? 2 : 0, ctx->dCodimELocal.p);
             ctx->launches++;
             build_tree(ctx, ctx->ceset, ctx->cetree, false);
             if (ctx->shard_rank == 0) run_traverse(ctx, ctx->cetree, ctx->cvtree, 0, 2, 1, false, ctx->cand[IPCB_EV], false);

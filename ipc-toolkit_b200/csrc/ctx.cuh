@@ -116,6 +116,14 @@ struct ipcb_ctx {
     ipcb::Buf<double4> dRest;
     ipcb::Buf<double> dVArea, dEArea;
     ipcb::Buf<int> dCodimV, dCodimE;
+    // CollisionMesh::can_collide as a descriptor (ipcb_mesh_set_collision_filter): per-vertex patch labels and / or the
+    // number of dynamic vertices; dCodimELocal: ids of the codim edges' endpoints in the re-indexed vertex set of the
+    // codimensional edge-vertex pass (candidates.cpp:83-108)
+    bool filter_patches = false;
+    int filter_n_dynamic = -1;
+    ipcb::Buf<int> dPatch;
+    ipcb::Buf<int2> dCodimELocal;
+    bool filter_on() const { return filter_patches || filter_n_dynamic >= 0; }
 
     // ---- positions
     ipcb::Buf<double> stageA, stageB; // col-major staging for host entry points

@@ -92,6 +92,14 @@ struct ipcb_ctx {
     // hessian
     std::vector<int32_t> outer, inner;
     std::vector<double> vals;
+    // CollisionMesh::can_collide (collision_mesh.hpp:338) as the intersection of the two descriptor-expressible
+    // factories of collision_filter.hpp:113-143
+    std::vector<int32_t> patch_ids; // make_vertex_patches_filter (empty: off)
+    int32_t n_dynamic = -1;         // make_static_obstacle_filter (< 0: off)
+    bool can_vertices_collide(int vi, int vj) const
+    {
+        return (patch_ids.empty() || patch_ids[vi] != patch_ids[vj]) && (n_dynamic < 0 || vi < n_dynamic || vj < n_dynamic);
+    }
 };
 
 namespace {
@@ -331,51 +339,39 @@ void detect_pairs(const ipcb_ctx* ctx, const std::vector<Box>& A, const std::vec
 
 void sort_pairs(std::vector<Pair>& p) { __gnu_parallel::sort(p.begin(), p.end()); }
 
-// share-a-vertex rejection (lbvh.cpp:801-873) with can_vertices_collide == true
+// share-a-vertex rejection + can_vertices_collide on some pair of vertices of the two primitives (lbvh.cpp:801-873)
 void broad_detect_kind(ipcb_ctx* ctx, int kind, std::vector<Pair>& out)
 {
     const int32_t* E = ctx->E.data();
     const int32_t* F = ctx->F.data();
+    // na / nb vertices of the two primitives: no shared vertex, and at least one pair of vertices that can collide
+    auto ok = [ctx](const int32_t* a, int na, const int32_t* b, int nb) {
+        bool any = false;
+        for (int i = 0; i < na; i++)
+            for (int j = 0; j < nb; j++) {
+                if (a[i] == b[j]) return false;
+                any |= ctx->can_vertices_collide(a[i], b[j]);
+            }
+        return any;
+    };
     switch (kind) {
     case IPCB_VV:
-        detect_pairs(ctx, ctx->vbox, ctx->vbox, true, [](int, int) { return true; }, out);
+        detect_pairs(ctx, ctx->vbox, ctx->vbox, true, [=](int a, int b) { return ctx->can_vertices_collide(a, b); }, out);
         break;
     case IPCB_EV:
-        detect_pairs(ctx, ctx->ebox, ctx->vbox, false, [=](int e, int v) { return v != E[2 * e] && v != E[2 * e + 1]; }, out);
+        detect_pairs(ctx, ctx->ebox, ctx->vbox, false, [=](int e, int v) { return ok(E + 2 * e, 2, &v, 1); }, out);
         break;
     case IPCB_EE:
-        detect_pairs(
-            ctx, ctx->ebox, ctx->ebox, true,
-            [=](int a, int b) {
-                return E[2 * a] != E[2 * b] && E[2 * a] != E[2 * b + 1] && E[2 * a + 1] != E[2 * b] && E[2 * a + 1] != E[2 * b + 1];
-            },
-            out);
+        detect_pairs(ctx, ctx->ebox, ctx->ebox, true, [=](int a, int b) { return ok(E + 2 * a, 2, E + 2 * b, 2); }, out);
         break;
     case IPCB_FV:
-        detect_pairs(ctx, ctx->fbox, ctx->vbox, false, [=](int f, int v) { return v != F[3 * f] && v != F[3 * f + 1] && v != F[3 * f + 2]; },
-                     out);
+        detect_pairs(ctx, ctx->fbox, ctx->vbox, false, [=](int f, int v) { return ok(F + 3 * f, 3, &v, 1); }, out);
         break;
     case IPCB_EF:
-        detect_pairs(
-            ctx, ctx->ebox, ctx->fbox, false,
-            [=](int e, int f) {
-                for (int a = 0; a < 2; a++)
-                    for (int b = 0; b < 3; b++)
-                        if (E[2 * e + a] == F[3 * f + b]) return false;
-                return true;
-            },
-            out);
+        detect_pairs(ctx, ctx->ebox, ctx->fbox, false, [=](int e, int f) { return ok(E + 2 * e, 2, F + 3 * f, 3); }, out);
         break;
     case IPCB_FF:
-        detect_pairs(
-            ctx, ctx->fbox, ctx->fbox, true,
-            [=](int fa, int fb) {
-                for (int a = 0; a < 3; a++)
-                    for (int b = 0; b < 3; b++)
-                        if (F[3 * fa + a] == F[3 * fb + b]) return false;
-                return true;
-            },
-            out);
+        detect_pairs(ctx, ctx->fbox, ctx->fbox, true, [=](int fa, int fb) { return ok(F + 3 * fa, 3, F + 3 * fb, 3); }, out);
         break;
     }
     sort_pairs(out);
@@ -401,7 +397,9 @@ void candidates_build(ipcb_ctx* ctx, const std::vector<V3>& V0, const std::vecto
         std::vector<Box> vb(cv.size());
         for (size_t i = 0; i < cv.size(); i++) vb[i] = ctx->vbox[cv[i]];
         std::vector<Pair> vv;
-        detect_pairs(ctx, vb, vb, true, [](int, int) { return true; }, vv);
+        // the reference leaves broad_phase->can_vertices_collide = mesh.can_collide in place for this pass, whose vertex
+        // ids are positions in codim_vertices (candidates.cpp:61,66-77): the filter sees those LOCAL ids — mirrored as is
+        detect_pairs(ctx, vb, vb, true, [=](int a, int b) { return ctx->can_vertices_collide(a, b); }, vv);
         for (auto& p : vv) p = { std::min(cv[p[0]], cv[p[1]]), std::max(cv[p[0]], cv[p[1]]) };
         sort_pairs(vv);
         ctx->cand[IPCB_VV] = vv;
@@ -411,8 +409,21 @@ void candidates_build(ipcb_ctx* ctx, const std::vector<V3>& V0, const std::vecto
         for (size_t i = 0; i < cv.size(); i++) vb[i] = ctx->vbox[cv[i]];
         for (size_t i = 0; i < ce.size(); i++) eb[i] = ctx->ebox[ce[i]];
         std::vector<Pair> ev;
-        // codim vertices are never endpoints of an edge, so no share-vertex case
-        detect_pairs(ctx, eb, vb, false, [](int, int) { return true; }, ev);
+        // codim vertices are never endpoints of an edge, so no share-vertex case.  The filter of this pass is
+        // make_codim_cross_filter(nCV) & mesh.can_collide on the ids of the re-indexed vertex set [codim vertices;
+        // referenced vertices of the codim edges in ascending order] (candidates.cpp:83-108, igl::remove_unreferenced):
+        // the cross filter always passes for (codim vertex, edge endpoint) and can_collide sees those LOCAL ids
+        std::vector<int32_t> ref;
+        for (int e : ce) ref.push_back(ctx->E[2 * e]), ref.push_back(ctx->E[2 * e + 1]);
+        std::sort(ref.begin(), ref.end());
+        ref.erase(std::unique(ref.begin(), ref.end()), ref.end());
+        const int nCV = int(cv.size());
+        auto local = [&](int v) { return nCV + int(std::lower_bound(ref.begin(), ref.end(), v) - ref.begin()); };
+        std::vector<Pair> le(ce.size());
+        for (size_t i = 0; i < ce.size(); i++) le[i] = { local(ctx->E[2 * ce[i]]), local(ctx->E[2 * ce[i] + 1]) };
+        detect_pairs(
+            ctx, eb, vb, false, [&](int e, int v) { return ctx->can_vertices_collide(v, le[e][0]) || ctx->can_vertices_collide(v, le[e][1]); },
+            ev);
         for (auto& p : ev) p = { ce[p[0]], cv[p[1]] };
         sort_pairs(ev);
         ctx->cand[IPCB_EV] = ev;
@@ -913,6 +924,7 @@ int ipco_mesh_set(ipcb_ctx* ctx, int32_t nV, const double* rest, int32_t ld_rest
                   int32_t nF, const int32_t* F, int32_t ldF)
 {
     ctx->nV = nV, ctx->nE = nE, ctx->nF = nF;
+    ctx->patch_ids.clear(), ctx->n_dynamic = -1; // a new mesh accepts all pairs
     ctx->rest = load_vertices(nV, rest, ld_rest);
     ctx->E.resize(2 * size_t(nE));
     ctx->F.resize(3 * size_t(nF));
@@ -1000,6 +1012,13 @@ int ipco_mesh_set(ipcb_ctx* ctx, int32_t nV, const double* rest, int32_t ld_rest
     ctx->built = false;
     for (auto& c : ctx->cand) c.clear();
     for (auto& c : ctx->coll) c.clear();
+    return 0;
+}
+int ipco_mesh_set_collision_filter(ipcb_ctx* ctx, const int32_t* patch_ids, int32_t n_dynamic)
+{
+    ctx->patch_ids.clear();
+    if (patch_ids) ctx->patch_ids.assign(patch_ids, patch_ids + ctx->nV);
+    ctx->n_dynamic = n_dynamic;
     return 0;
 }
 int ipco_mesh_num_codim_vertices(ipcb_ctx* ctx, int32_t* n)
