@@ -462,7 +462,7 @@ def main():
     cs = info.get("static_candidates") or [0, 0, 0, 0]
     cc = info.get("ccd_candidates") or [0, 0, 0, 0]
 
-    def roof(kernel, ms, alg_bytes, ncu_names, note, flops=None, bound="hbm"):
+    def roof(kernel, ms, alg_bytes, ncu_names, note, flops=None, bound="hbm", fp64_inst=None):
         if not ms or not alg_bytes:
             return None
         ach = alg_bytes / (ms * 1e-3) / 1e9
@@ -475,19 +475,31 @@ def main():
             tf = flops / (ms * 1e-3) / 1e12
             r["fp64"] = {"achieved": tf, "peak": fp64_peak.value, "unit": "TFLOP/s", "frac": tf / fp64_peak.value if fp64_peak.value else None,
                          "algorithmic_flops": int(flops), "peak_source": "measured here (ipcb_measure_fp64_peak: 8 FMA chains per thread)"}
+            if fp64_inst:
+                # what binds an FP64 kernel is the ISSUE rate of the FP64 pipe: a DMUL or a DADD takes the slot of a DFMA.
+                # achieved = FP64 thread instructions / s against the measured FMA issue rate (peak TFLOP/s / 2)
+                ti, pk = fp64_inst / (ms * 1e-3) / 1e12, fp64_peak.value / 2
+                r["fp64"].update({"issue_achieved": ti, "issue_peak": pk, "issue_unit": "T FP64 thread-inst/s", "issue_frac": ti / pk if pk else None})
             if bound == "fp64":
                 r["achieved"], r["peak"], r["unit"], r["frac"] = tf, fp64_peak.value, "TFLOP/s", r["fp64"]["frac"]
+                if fp64_inst:
+                    r["achieved"], r["peak"], r["unit"], r["frac"] = (r["fp64"]["issue_achieved"], r["fp64"]["issue_peak"],
+                                                                      "T FP64 thread-inst/s", r["fp64"]["issue_frac"])
         return r
 
     # local Hessians: per collision 24 B record + 32 B per stencil point in; 16 B ids + 32 B masks + 8 B per incidence +
     # 72 B per stored (upper-triangular) 3x3 block out.  FP64: FLOPS_HFAST per collision (from the ncu
     # instruction counts of the capture in profiles/)
     tri = (3, 6, 10, 10)
-    FLOPS_HFAST = (900.0, 5200.0, 11600.0, 11600.0)
+    # FP64 work of k_hessian_fast per collision, from the ncu instruction counts of profiles/r2_ncu_full_c3_raw.csv
+    # (smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on): thread instructions, and flop with an FMA as two
+    FP64_INST = (469.0, 2028.0, 3876.0, 3993.0)
+    FLOPS_HFAST = (640.0, 2820.0, 5460.0, 5630.0)
     k_ms = lambda name: kernels_ms.get(name)
     hf_names = ("k_hessian_fast<VV>", "k_hessian_fast<EV>", "k_hessian_fast<EE>", "k_hessian_fast<FV>")
     hl_bytes = [c * share * (24 + 32 * n + 16 + 32 + 8 * n + 72 * t) for c, n, t in zip(ncoll, npts, tri)]
     hl_flops = [c * share * f for c, f in zip(ncoll, FLOPS_HFAST)]
+    hl_inst = [c * share * f for c, f in zip(ncoll, FP64_INST)]
     hf_ms = sum(k_ms(n) or 0.0 for n in hf_names)
     # numeric pass: 4 B reference + 72 B block per item in, 8 B per unique block (~nnz / 9), 12 B per entry out
     hn_bytes = nitems * share * 76 + nnz_ * 12 + (nnz_ // 9) * 8
@@ -497,8 +509,9 @@ def main():
         roof("k_hessian_fast<VV|EV|EE|FV> (the four kinds, timed one by one)", hf_ms, sum(hl_bytes),
              ["k_hessian_fast<0", "k_hessian_fast<1", "k_hessian_fast<2", "k_hessian_fast<3"],
              "register Jacobi PSD projection in the analytic (3+p)-subspace; upper-triangular blocks staged through shared memory",
-             flops=sum(hl_flops), bound="fp64"),
-        roof("k_hessian_fast<EE>", k_ms(hf_names[2]), hl_bytes[2], ["k_hessian_fast<2"], "the dominant kernel of the step", flops=hl_flops[2], bound="fp64"),
+             flops=sum(hl_flops), bound="fp64", fp64_inst=sum(hl_inst)),
+        roof("k_hessian_fast<EE>", k_ms(hf_names[2]), hl_bytes[2], ["k_hessian_fast<2"], "the dominant kernel of the step", flops=hl_flops[2], bound="fp64",
+             fp64_inst=hl_inst[2]),
         roof("k_hess_numeric", stages.get("hess_numeric"), hn_bytes, ["k_hess_numeric"], "HBM gather of 72-byte blocks, software-pipelined"),
         roof("k_hess_symbolic", stages.get("hess_symbolic"), hs_bytes, ["k_hess_symbolic"],
              "shared-memory hash + sort per column; instruction / latency bound"),
@@ -521,7 +534,7 @@ def main():
     roof_main = rooflines[0] if rooflines else None
     if roof_main is not None:  # the contract's `roofline` object: the dominant kernel against the MEASURED HBM bandwidth; its FP64 view rides along
         hbm = roof("k_hessian_fast<VV|EV|EE|FV>", hf_ms, sum(hl_bytes), ["k_hessian_fast<0", "k_hessian_fast<1", "k_hessian_fast<2", "k_hessian_fast<3"],
-                   roof_main["note"], flops=sum(hl_flops), bound="hbm")
+                   roof_main["note"], flops=sum(hl_flops), bound="hbm", fp64_inst=sum(hl_inst))
         hbm["binding"] = "fp64 (see the fp64 object: the kernel is bound by the FP64 pipe, its HBM fraction is reported as the contract asks)"
         roof_main = hbm
 

@@ -212,6 +212,15 @@ int IPCB_FN(ccd_stepsize)(ipcb_ctx* ctx, const double* V0, const double* V1, int
 /* Candidates::compute_collision_free_stepsize on the RESIDENT candidates */
 int IPCB_FN(ccd_stepsize_from_candidates)(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld,
                                           double min_distance, const ipcb_ccd_params* ccd, double* step);
+/* Candidates::compute_noncandidate_conservative_stepsize (candidates.cpp:294-338) on the RESIDENT candidates:
+ * 0.5 * dhat / max |displacement| over the vertices that belong to some candidate; 1 when there are no candidates (not
+ * clamped otherwise, like the reference).  displacements: nV x 3 column-major. */
+int IPCB_FN(candidates_noncandidate_stepsize)(ipcb_ctx* ctx, const double* displacements, int32_t ld, double dhat, double* step);
+/* Candidates::compute_cfl_stepsize (candidates.cpp:340-363) on the RESIDENT candidates: alpha_C = their collision-free
+ * step size, alpha_F = the non-candidate bound for V1 - V0; if alpha_F < alpha_C / 2 the full
+ * compute_collision_free_stepsize (new swept broad phase; the resident candidates are replaced), else min of the two. */
+int IPCB_FN(candidates_cfl_stepsize)(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double dhat, double min_distance,
+                                     const ipcb_ccd_params* ccd, double* step);
 /* NarrowPhaseCCD batch (ccd/narrow_phase_ccd.hpp:8-119): n independent
  * queries; x_t0 / x_t1 hold 12 doubles per query (4 points xyz: EE ea0 ea1 eb0
  * eb1; FV p t0 t1 t2; EV p e0 e1 -; VV p0 p1 - -).  hit[i] in {0,1}, toi[i]

@@ -56,6 +56,8 @@ HOST_API = {
     "barrier_hessian_fetch": (C.c_int, [P, P, P, P]),
     "ccd_stepsize": (C.c_int, [P, P, P, c_i32, c_f64, C.POINTER(CcdParams), C.POINTER(c_f64)]),
     "ccd_stepsize_from_candidates": (C.c_int, [P, P, P, c_i32, c_f64, C.POINTER(CcdParams), C.POINTER(c_f64)]),
+    "candidates_noncandidate_stepsize": (C.c_int, [P, P, c_i32, c_f64, C.POINTER(c_f64)]),
+    "candidates_cfl_stepsize": (C.c_int, [P, P, P, c_i32, c_f64, c_f64, C.POINTER(CcdParams), C.POINTER(c_f64)]),
     "ccd_narrow_phase": (C.c_int, [P, c_i32, c_i64, P, P, c_f64, c_f64, C.POINTER(CcdParams), P, P]),
 }
 

@@ -366,6 +366,24 @@ def make_api(lib):
             lib.check(lib.ccd_stepsize_from_candidates(mesh._ctx, p0, p1, ld, min_distance, C.byref(ccd), C.byref(step)))
             return step.value
 
+        def compute_noncandidate_conservative_stepsize(self, mesh, displacements, dhat):
+            """candidates.cpp:294-338"""
+            self._live()
+            d, p, ld = _f64(displacements)
+            step = C.c_double()
+            lib.check(lib.candidates_noncandidate_stepsize(mesh._ctx, p, ld, dhat, C.byref(step)))
+            return step.value
+
+        def compute_cfl_stepsize(self, mesh, vertices_t0, vertices_t1, dhat, min_distance=0.0, broad_phase=None, narrow_phase_ccd=None):
+            """candidates.cpp:340-363 (the resident candidates are replaced when the full CCD had to run)"""
+            self._live()
+            ccd = (narrow_phase_ccd or TightInclusionCCD())._params()
+            v0, p0, ld = _f64(vertices_t0)
+            v1, p1, _ = _f64(vertices_t1)
+            step = C.c_double()
+            lib.check(lib.candidates_cfl_stepsize(mesh._ctx, p0, p1, ld, dhat, min_distance, C.byref(ccd), C.byref(step)))
+            return step.value
+
         def is_step_collision_free(self, mesh, vertices_t0, vertices_t1, min_distance=0.0, narrow_phase_ccd=None):
             # candidates.cpp:224-250: no candidate has an impact in [0, 1]
             return self.compute_collision_free_stepsize(mesh, vertices_t0, vertices_t1, min_distance, narrow_phase_ccd) >= 1.0

@@ -860,6 +860,40 @@ int ipcb_ccd_stepsize(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t
         IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }
+int ipcb_candidates_noncandidate_stepsize(ipcb_ctx* ctx, const double* displacements, int32_t ld, double dhat, double* step)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        stage_positions(ctx, displacements, ld, true); // X1 <- displacements
+        *step = noncandidate_stepsize(ctx, false, dhat);
+    });
+}
+int ipcb_candidates_cfl_stepsize(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double dhat, double min_distance,
+                                 const ipcb_ccd_params* ccd, double* step)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        stage_positions(ctx, V0, ld, false);
+        stage_positions(ctx, V1, ld, true);
+        double* d_out = reinterpret_cast<double*>(ctx->dCounters.p + 13);
+        auto fetch = [&] {
+            double v = 0;
+            IPCB_CUDA(cudaMemcpyAsync(&v, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+            return v;
+        };
+        ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_out);
+        const double alpha_c = fetch();
+        const double alpha_f = noncandidate_stepsize(ctx, true, dhat);
+        if (alpha_f < 0.5 * alpha_c) { // candidates.cpp:356-360: do the full CCD
+            candidates_build(ctx, true, 0.5 * min_distance);
+            ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_out);
+            *step = fetch();
+        } else {
+            *step = std::min(alpha_c, alpha_f);
+        }
+    });
+}
 int ipcb_ccd_narrow_phase(ipcb_ctx* ctx, int32_t kind, int64_t n, const double* x_t0, const double* x_t1, double min_distance, double tmax,
                           const ipcb_ccd_params* ccd, uint8_t* hit, double* toi)
 {

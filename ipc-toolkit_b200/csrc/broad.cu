@@ -48,6 +48,7 @@ void upload_positions(ipcb_ctx* ctx, const double* hV, int ld, Buf<double>& stag
 void convert_positions(ipcb_ctx* ctx, const double* dV, int ld, Buf<double4>& X)
 {
     X.reserve(ctx->nV);
+    ctx->scene_covers_positions = false; // new positions: the scene box of an earlier build no longer bounds them
     if (ctx->nV == 0) return;
     k_to_aos<<<grid_for(ctx->nV, 256), 256, 0, ctx->stream>>>(ctx->nV, dV, ld, X.p);
     ctx->launches++;
@@ -527,10 +528,12 @@ void broad_build(ipcb_ctx* ctx, bool swept, double r)
     if (nF) k_face_boxes<<<grid_for(nF, 256), 256, 0, s>>>(nF, ctx->dF.p, ctx->vset.box.p, ctx->fset.box.p, ctx->fset.prim.p);
     ctx->launches += 4;
     ctx->vtree_ok = ctx->etree_ok = ctx->ftree_ok = false;
+    ctx->vorder_valid = false;
     ctx->vtree.n = ctx->etree.n = ctx->ftree.n = 0;
     ctx->vtree.has_nodes = ctx->etree.has_nodes = ctx->ftree.has_nodes = false;
     ctx->built = true;
     ctx->swept = swept;
+    ctx->scene_covers_positions = swept; // reduced from the boxes of X0 and X1
     IPCB_CUDA(cudaGetLastError());
 }
 
@@ -581,13 +584,14 @@ template <int QN, int TN> __device__ __forceinline__ bool any_can_collide(const 
 
 // MODE 0: emit (query, target); 1: emit (target, query); 2: self, emit (min, max)
 // flags: bit 0 = reject pairs that share a vertex, bit 1 = apply the collision filter
-template <int MODE, int QN, int TN>
+template <int MODE, int QN, int TN, bool FILTERED>
 __global__ void __launch_bounds__(TRAV_BLOCK)
     k_traverse(int q_begin, int q_end, const FBox* __restrict__ qbox, const int4* __restrict__ qprim,
                const Node* __restrict__ nodes, int n_target, const FBox* __restrict__ tbox, const int4* __restrict__ tprim,
                int2* __restrict__ out, unsigned long long* counter, unsigned long long capacity, int flags, FilterView filter)
 {
-    const bool check_shared = flags & 1, filtered = flags & 2;
+    const bool check_shared = flags & 1;
+    constexpr bool filtered = FILTERED; // a template parameter: the unfiltered kernel keeps its 56 registers
     __shared__ int2 stage[TRAV_BLOCK / 32][STAGE_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int qi = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
@@ -730,9 +734,13 @@ struct TraverseJob {
         Stage kt(ctx, mode == 2 && qn == 2 ? "k:k_traverse<EE>" : (mode == 1 && tn == 3 ? "k:k_traverse<FV>" : "k:k_traverse<other>"), s);
         const int flags = (check_shared ? 1 : 0) | (ctx->filter_on() ? 2 : 0);
         const FilterView filter { ctx->filter_patches ? ctx->dPatch.p : nullptr, ctx->filter_n_dynamic };
-#define IPCB_TRAVERSE(M, QN, TN)                                                                                                    \
-    k_traverse<M, QN, TN><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes.p, t->n, t->sbox.p, t->sprim.p, \
-                                                      out->pairs.p, counter, cap, flags, filter)
+#define IPCB_TRAVERSE(M, QN, TN)                                                                                                         \
+    if (flags & 2)                                                                                                                      \
+        k_traverse<M, QN, TN, true><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes.p, t->n, t->sbox.p, t->sprim.p, \
+                                                                out->pairs.p, counter, cap, flags, filter);                             \
+    else                                                                                                                                \
+        k_traverse<M, QN, TN, false><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes.p, t->n, t->sbox.p, t->sprim.p, \
+                                                                 out->pairs.p, counter, cap, flags, filter)
         switch (mode * 100 + qn * 10 + tn) {
         case 211: IPCB_TRAVERSE(2, 1, 1); break; // vertex - vertex
         case 21: IPCB_TRAVERSE(0, 2, 1); break;  // edges walk the vertex tree
@@ -774,7 +782,7 @@ static void run_traverse(ipcb_ctx* ctx, const Tree& q, const Tree& t, int mode, 
 static Tree& ensure_tree(ipcb_ctx* ctx, int which)
 {
     if (which == 0) {
-        if (!ctx->vtree_ok) build_tree(ctx, ctx->vset, ctx->vtree, true), ctx->vtree_ok = true;
+        if (!ctx->vtree_ok) build_tree(ctx, ctx->vset, ctx->vtree, true), ctx->vtree_ok = true, ctx->vorder_valid = true;
         return ctx->vtree;
     }
     if (which == 1) {
@@ -879,7 +887,7 @@ void candidates_build(ipcb_ctx* ctx, bool swept, double r)
         }
         if (do_fv) {
             if (!ctx->ftree_ok) build_tree(ctx, ctx->fset, ctx->ftree, true, ctx->aux[1]), ctx->ftree_ok = true;
-            if (!ctx->vtree_ok) build_tree(ctx, ctx->vset, ctx->vtree, false, ctx->aux[2]);
+            if (!ctx->vtree_ok) build_tree(ctx, ctx->vset, ctx->vtree, false, ctx->aux[2]), ctx->vorder_valid = true;
             ctx->join(2); // not needed by the main stream itself, but keeps every later main-stream consumer ordered
             IPCB_CUDA(cudaEventRecord(ctx->ev_fork, ctx->aux[2]));
             IPCB_CUDA(cudaStreamWaitEvent(ctx->aux[1], ctx->ev_fork, 0)); // the vertex order feeds the face-vertex traversal

@@ -491,7 +491,7 @@ __device__ inline unsigned long long warp_reserve(unsigned long long* counter, b
 // dropped here; survivors are compacted into `list` for the full per-query kernel.
 __global__ void __launch_bounds__(256, 3)
     k_ti_filter(MultiSource ms, int stride, int prev_stride, double min_distance, double tmax_in, double tolerance, CcdOut out,
-                int* __restrict__ list, unsigned long long* nlist)
+                int* __restrict__ list, unsigned long long* nlist, const float* __restrict__ scene)
 {
     const unsigned long long* bound = out.bound;
     // thread t looks at candidate g = t * stride, unless an earlier (coarser) phase already did: g % prev_stride == 0
@@ -504,10 +504,17 @@ __global__ void __launch_bounds__(256, 3)
         if (q.kind >= IPCB_EE) { // point-point / point-edge queries are few (codimensional): always kept
             d3 a[4], b[4];
             load_query(q, i, a, b);
+            // largest |coordinate| for the floating-point filter: the scene box of the swept broad phase bounds every
+            // query's own maximum (a larger value only widens the margin: conservative); raw queries compute their own
             double mx = 1.0;
+            if (scene) {
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                mx = fmax(mx, fmax(fmax(fmax(fabs(a[k].x), fabs(a[k].y)), fabs(a[k].z)), fmax(fmax(fabs(b[k].x), fabs(b[k].y)), fabs(b[k].z))));
+                for (int k = 0; k < 6; k++) mx = fmax(mx, fabs(double(__ldg(scene + k))));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    mx = fmax(mx, fmax(fmax(fmax(fabs(a[k].x), fabs(a[k].y)), fabs(a[k].z)), fmax(fmax(fabs(b[k].x), fabs(b[k].y)), fabs(b[k].z))));
+            }
             const int is_vf = q.kind == IPCB_FV;
             const double err = (is_vf ? 7.549516567451064e-15 : 7.105427357601002e-15) * mx * mx * mx;
             const double margin = (err + min_distance + 1e-4 + tolerance) * (1.0 + 1e-9);
@@ -948,6 +955,9 @@ static int warp_stack_cap()
 // Nothing is read back until the end; stack overflows (rare) are collected in the global queue and drained last.
 static void ti_run(ipcb_ctx* ctx, const MultiSource& ms, double min_distance, double tmax, const ipcb_ccd_params& p, CcdOut out)
 {
+    // the scene box bounds the coordinates of resident-candidate queries when the swept broad phase of THESE positions
+    // built it (ccd_stepsize right after candidates_build); otherwise every query takes its own maximum
+    const float* scene = (ms.cand[0] && ctx->scene_covers_positions) ? ctx->scene.p : nullptr;
     const int64_t total = ms.off[ms.nk];
     if (total == 0) return;
     if (total > 0x7fffffffll) throw Error("ccd: more than 2^31 candidates in one search");
@@ -992,7 +1002,7 @@ static void ti_run(ipcb_ctx* ctx, const MultiSource& ms, double min_distance, do
             IPCB_CUDA(cudaMemsetAsync(nlist_d, 0, 4 * sizeof(unsigned long long), s)); // list lengths and work counters
             {
                 Stage kt(ctx, probe ? "k:k_ti_filter(sample)" : "k:k_ti_filter", s);
-                k_ti_filter<<<grid_for((total + st - 1) / st, 256), 256, 0, s>>>(ms, st, 0, min_distance, tmax, p.tolerance, out, W.list.p, nlist_d);
+                k_ti_filter<<<grid_for((total + st - 1) / st, 256), 256, 0, s>>>(ms, st, 0, min_distance, tmax, p.tolerance, out, W.list.p, nlist_d, scene);
             }
             {
                 Stage kt(ctx, probe ? "k:k_ti_query(sample)" : "k:k_ti_query", s);
@@ -1098,6 +1108,69 @@ void ccd_stepsize(ipcb_ctx* ctx, double min_distance, const ipcb_ccd_params& p, 
         ti_run(ctx, multi_source(ctx, { IPCB_FV, IPCB_EE }), min_distance, 1.0, p, out);
     }
     IPCB_CUDA(cudaMemcpyAsync(d_out, bound, sizeof(double), cudaMemcpyDeviceToDevice, s));
+}
+
+// ---- Candidates::compute_noncandidate_conservative_stepsize (candidates.cpp:294-338)
+__global__ void k_mark_candidate_vertices(int kind, int64_t n, const int2* __restrict__ cand, const int2* __restrict__ E, const int4* __restrict__ F,
+                                          unsigned char* __restrict__ flag)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = cand[i];
+    if (kind == IPCB_VV) {
+        flag[c.x] = 1, flag[c.y] = 1;
+    } else if (kind == IPCB_EV) {
+        const int2 e = __ldg(E + c.x);
+        flag[c.y] = 1, flag[e.x] = 1, flag[e.y] = 1;
+    } else if (kind == IPCB_EE) {
+        const int2 ea = __ldg(E + c.x), eb = __ldg(E + c.y);
+        flag[ea.x] = 1, flag[ea.y] = 1, flag[eb.x] = 1, flag[eb.y] = 1;
+    } else {
+        const int4 f = __ldg(F + c.x);
+        flag[c.y] = 1, flag[f.x] = 1, flag[f.y] = 1, flag[f.z] = 1;
+    }
+}
+// max over flagged vertices of |displacement| (X1 holds the displacements, or X1 - X0 is formed when X0 is given)
+__global__ void k_max_displacement(int n, const unsigned char* __restrict__ flag, const double4* __restrict__ X0, const double4* __restrict__ X1,
+                                   unsigned long long* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double d = 0;
+    if (i < n && flag[i]) {
+        double4 u = X1[i];
+        if (X0) {
+            const double4 a = X0[i];
+            u.x -= a.x, u.y -= a.y, u.z -= a.z;
+        }
+        d = sqrt((u.x * u.x + u.y * u.y) + u.z * u.z); // Eigen's linear reduction of a dynamic row
+    }
+    for (int o = 16; o > 0; o >>= 1) d = fmax(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0 && d > 0) atomicMax(out, (unsigned long long)__double_as_longlong(d));
+}
+// X0 == nullptr: ctx->X1 holds the displacements
+double noncandidate_stepsize(ipcb_ctx* ctx, bool difference, double dhat)
+{
+    int64_t total = 0;
+    for (auto& c : ctx->cand) total += c.count;
+    if (total == 0) return 1.0; // no possible collisions: full step
+    cudaStream_t s = ctx->stream;
+    ctx->hflag.reserve(size_t(ctx->nV) + 1);
+    IPCB_CUDA(cudaMemsetAsync(ctx->hflag.p, 0, size_t(ctx->nV) + 1, s));
+    for (int k = 0; k < 4; k++) {
+        const PairList& pl = ctx->cand[k];
+        if (pl.count == 0) continue;
+        k_mark_candidate_vertices<<<grid_for(pl.count, 256), 256, 0, s>>>(k, pl.count, pl.pairs.p, ctx->dE.p, ctx->dF.p, ctx->hflag.p);
+        ctx->launches++;
+    }
+    unsigned long long* out = ctx->dCounters.p + 14;
+    IPCB_CUDA(cudaMemsetAsync(out, 0, sizeof(unsigned long long), s));
+    k_max_displacement<<<grid_for(ctx->nV, 256), 256, 0, s>>>(ctx->nV, ctx->hflag.p, difference ? ctx->X0.p : nullptr, ctx->X1.p, out);
+    ctx->launches++;
+    IPCB_CUDA(cudaGetLastError());
+    const unsigned long long bits = read_counter(ctx, out);
+    double m;
+    memcpy(&m, &bits, sizeof m);
+    return 0.5 * dhat / m;
 }
 
 void ccd_narrow_phase(ipcb_ctx* ctx, int kind, int64_t n, const double* h_t0, const double* h_t1, double min_distance, double tmax,

@@ -323,10 +323,14 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
     if (improved) improved_max_approx_corrections(ctx, (dmin + dhat) * (dmin + dhat), (flags & IPCB_USE_AREA_WEIGHTING) != 0, raw);
     // IPC set: every edge-edge / face-vertex record comes from its own candidate, so those two streams hold no
     // duplicates and need no merge — only vertex-vertex / edge-vertex records are united.  Their canonical order
-    // (sorted ids) is what a caller SEES, not what the potential needs: it is restored lazily when somebody fetches the
-    // records (collisions_sort), which takes the two large sorts out of the contact step.  IPCB_EAGER_SORT=1: A/B switch.
-    static const bool eager = getenv("IPCB_EAGER_SORT") != nullptr;
-    merge_streams(ctx, raw, !improved && !eager, improved);
+    // (sorted ids) is what a caller SEES, not what the potential needs, so it could be restored lazily when somebody
+    // fetches the records (collisions_sort; IPCB_LAZY_SORT=1).  Measured on C3 that is a wash — the 0.35 ms the two large
+    // sorts cost come back as better locality of the energy / gradient / symbolic kernels on id-ordered records — and the
+    // sorted order makes every later sum reproducible run to run, so the eager sort stays the default.
+    // On a sharded context the rank's records are concatenated with the other ranks' ones right away (disjoint merge),
+    // so sorting the shard first would be wasted work: lazy there.
+    static const bool lazy = getenv("IPCB_LAZY_SORT") != nullptr;
+    merge_streams(ctx, raw, !improved && (lazy || ctx->shard_world > 1), improved);
 }
 
 // records -> final arrays without sorting or merging (every record is kept)

@@ -135,7 +135,9 @@ struct ipcb_ctx {
     ipcb::PrimSet vset, eset, fset, cvset, ceset;
     ipcb::Tree vtree, etree, ftree, cvtree, cetree;
     bool vtree_ok = false, etree_ok = false, ftree_ok = false;
+    bool vorder_valid = false; // vtree.ord_sorted holds a permutation of all vertices (Morton order of the last build)
     ipcb::Buf<float> scene; // 6 floats: min xyz, max xyz
+    bool scene_covers_positions = false; // the scene box was reduced from the CURRENT X0 / X1 (swept build of this call)
     ipcb::PairList detected[6];
 
     // ---- candidates / collisions
@@ -248,6 +250,7 @@ void hessian_balanced_row_blocks(ipcb_ctx* ctx, int world, int32_t* bounds);
 
 // ccd (ccd.cu)
 void ccd_stepsize(ipcb_ctx* ctx, double min_distance, const ipcb_ccd_params& p, double* d_out);
+double noncandidate_stepsize(ipcb_ctx* ctx, bool difference, double dhat);
 void ccd_narrow_phase(ipcb_ctx* ctx, int kind, int64_t n, const double* h_t0, const double* h_t1, double min_distance, double tmax,
                       const ipcb_ccd_params& p, uint8_t* h_hit, double* h_toi);
 

@@ -936,12 +936,18 @@ union WarpSmem {
         int scan[32];
     } srt;
 };
-__global__ void __launch_bounds__(32 * SYM_WARPS) k_hess_symbolic(SymArgs A, int warp_cap, int use_hash, int* __restrict__ big, unsigned long long* nbig)
+// order (optional): the columns are visited in the MORTON order of their vertices (the broad phase's vertex order)
+// instead of by vertex id.  A stored upper-triangular block is read by the columns of BOTH its vertices; vertices in
+// contact are neighbours in space, not in id (the next cloth layer is 63 K ids away), so a spatial visiting order lets the
+// second read (and the shared id / mask records) hit L2.  The output position of a column does not depend on the order.
+__global__ void __launch_bounds__(32 * SYM_WARPS)
+    k_hess_symbolic(SymArgs A, int warp_cap, int use_hash, int* __restrict__ big, unsigned long long* nbig, const int* __restrict__ order)
 {
     __shared__ WarpSmem sm[SYM_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int v = blockIdx.x * SYM_WARPS + warp;
-    if (v > A.nV) return;
+    const int w = blockIdx.x * SYM_WARPS + warp;
+    if (w > A.nV) return;
+    const int v = (order && w < A.nV) ? order[w] : w;
     if (v == A.nV) { // closing entry of the count array
         if (lane == 0) A.cnt[3 * size_t(v)] = 0;
         return;
@@ -1023,11 +1029,12 @@ template <int NUM_BATCH>
 __global__ void __launch_bounds__(32 * SYM_WARPS)
     k_hess_numeric(int nV, const int* __restrict__ colR, const int* __restrict__ colU, const int* __restrict__ itemoff,
                    const unsigned* __restrict__ sref, const int2* __restrict__ udesc, const double* __restrict__ blk,
-                   const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals)
+                   const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals, const int* __restrict__ order)
 {
     const int lane = threadIdx.x & 31;
-    const int v = blockIdx.x * SYM_WARPS + (threadIdx.x >> 5);
-    if (v >= nV) return;
+    const int w = blockIdx.x * SYM_WARPS + (threadIdx.x >> 5);
+    if (w >= nV) return;
+    const int v = order ? order[w] : w; // spatial visiting order of the columns (see k_hess_symbolic)
     const int U = colU[v];
     if (U == 0) return;
     const int R = colR[v], ioff = itemoff[v];
@@ -1319,6 +1326,9 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
         IPCB_CUDA(cudaFuncSetAttribute(k_hess_symbolic_big, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BIG_SMEM)));
         ctx->hess_attr_set = true;
     }
+    // Morton order of the vertices from the last broad phase on this context (any permutation is valid)
+    static const bool id_order = getenv("IPCB_HESS_COLUMN_ID_ORDER") != nullptr; // A/B switch
+    const int* order = (!id_order && ctx->vorder_valid && ctx->vtree.n == nV) ? ctx->vtree.ord_sorted.p : nullptr;
     const int big_grid = NUM_SMS;
     // test hooks: lower the hand-over thresholds so that small scenes exercise the block / global-scratch paths
     int warp_cap = WARP_CAP, cta_cap = CTA_CAP;
@@ -1327,7 +1337,7 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     const int use_hash = getenv("IPCB_HESS_NO_HASH") ? 0 : 1;
     for (int attempt = 0;; attempt++) {
         IPCB_CUDA(cudaMemsetAsync(nbig, 0, 2 * sizeof(unsigned long long), s));
-        k_hess_symbolic<<<grid_for(size_t(nV) + 1, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(A, warp_cap, use_hash, ctx->hbig.p, nbig);
+        k_hess_symbolic<<<grid_for(size_t(nV) + 1, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(A, warp_cap, use_hash, ctx->hbig.p, nbig, order);
         k_hess_symbolic_big<<<big_grid, BIG_THREADS, BIG_SMEM, s>>>(A, cta_cap, ctx->hbig.p, nbig, ctx->hscratch.p, ctx->hscratch_items, need);
         ctx->launches += 2;
         // 4. scalar column pointers, nnz
@@ -1352,13 +1362,13 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
     const unsigned ngrid = grid_for(nV, SYM_WARPS);
     if (nb == 16)
         k_hess_numeric<16><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,
-                                                           ctx->outer.p, ctx->inner.p, ctx->vals.p);
+                                                           ctx->outer.p, ctx->inner.p, ctx->vals.p, order);
     else if (nb == 12)
         k_hess_numeric<12><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,
-                                                           ctx->outer.p, ctx->inner.p, ctx->vals.p);
+                                                           ctx->outer.p, ctx->inner.p, ctx->vals.p, order);
     else
         k_hess_numeric<8><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,
-                                                          ctx->outer.p, ctx->inner.p, ctx->vals.p);
+                                                          ctx->outer.p, ctx->inner.p, ctx->vals.p, order);
     ctx->launches++;
     IPCB_CUDA(cudaGetLastError());
 }

@@ -173,9 +173,8 @@ class DeviceShardedStep:
         self.nnz = C.c_int64()
         self.send = self.recv = None
         self.cap = 0
-        self.d_counts = torch.zeros(4, dtype=torch.int64, device="cuda")
-        self.d_counts_all = torch.zeros(4 * world, dtype=torch.int64, device="cuda")
         self.h_counts = torch.zeros(4, dtype=torch.int64).pin_memory()
+        self.h_headers = None
         self.rows = (0, mesh.num_vertices())
         self.shard_counts = [0, 0, 0, 0]
         self.after = None  # optional callback(ctx) after every library call (bench.py collects stage times)
@@ -201,48 +200,72 @@ class DeviceShardedStep:
         if self.lane is not None:
             self.lane.close()
             self.lane = None
-        self.send = self.recv = self.d_counts = self.d_counts_all = self.h_counts = None
+        self.send = self.recv = self.h_counts = self.h_headers = None
         self.side = self.ev_packed = self.ev_gathered = None
         self.stream = self.stream_b = None
 
-    def start_exchange(self):
-        """counts of every rank (the only host round trip), pack, and ONE all-gather of the packed records on a side
-        stream: it overlaps with whatever the caller enqueues next on the context's stream (the CCD stage)"""
+    HEADER = 32  # bytes in front of every rank's slot: its four record counts (int64)
+
+    def _resize_exchange(self, need):
+        torch = self.torch
+        self.cap = int(need * 1.25) + 4096
+        self.cap -= self.cap % 16
+        self.send = torch.empty(self.cap, dtype=torch.uint8, device="cuda")
+        self.recv = torch.empty(self.cap * self.world, dtype=torch.uint8, device="cuda")
+        self.h_headers = torch.zeros(self.world * 4, dtype=torch.int64).pin_memory()
+
+    def _gather_once(self):
+        """[header | packed records] of every rank in ONE all-gather of `cap` bytes per rank on the side stream.  The slot
+        size was agreed on in an earlier step (every rank derives it from the same gathered counts), so nothing has to be
+        exchanged — or waited for — before the records travel; a rank whose records do not fit sends its header only and
+        the exchange is repeated with a larger slot (every rank sees that in the headers)."""
         torch, lib, dist = self.torch, self.lib, self.dist
-        self.shard_counts = list(self.counts)
+        need = self.HEADER + packed_bytes(self.shard_counts)
         self.h_counts.copy_(torch.tensor(self.shard_counts, dtype=torch.int64))
         with torch.cuda.stream(self.stream):
-            self.d_counts.copy_(self.h_counts, non_blocking=True)
-            dist.all_gather_into_tensor(self.d_counts_all, self.d_counts)
-            self.all_counts = self.d_counts_all.cpu().view(self.world, 4).tolist()
-        need = max(packed_bytes(c) for c in self.all_counts)
-        if need > self.cap:
-            self.cap = int(need * 1.25) + 1024
-            self.cap -= self.cap % 16
-            self.send = torch.empty(self.cap, dtype=torch.uint8, device="cuda")
-            self.recv = torch.empty(self.cap * self.world, dtype=torch.uint8, device="cuda")
-        self.used = (need + 15) // 16 * 16  # only the used prefix of every slot travels
-        if self.used == 0:  # no rank found a collision (all ranks see the same `need`): nothing to move
-            self.ev_gathered.record(self.stream)
-            return
-        nbytes = C.c_int64()
-        lib.check(lib.collisions_pack_dev(self.ctx, C.c_void_p(self.send.data_ptr()), self.cap, C.byref(nbytes)))
+            self.send[:self.HEADER].view(torch.int64).copy_(self.h_counts, non_blocking=True)
+        if need <= self.cap and sum(self.shard_counts) > 0:
+            nbytes = C.c_int64()
+            lib.check(lib.collisions_pack_dev(self.ctx, C.c_void_p(self.send.data_ptr() + self.HEADER), self.cap - self.HEADER, C.byref(nbytes)))
         self.ev_packed.record(self.stream)
         with torch.cuda.stream(self.side):
             self.side.wait_event(self.ev_packed)
-            dist.all_gather_into_tensor(self.recv[:self.used * self.world], self.send[:self.used])
+            dist.all_gather_into_tensor(self.recv, self.send)
+            self.h_headers.view(self.world, 4).copy_(self.recv.view(self.world, self.cap)[:, :self.HEADER].contiguous().view(torch.int64).view(self.world, 4),
+                                                     non_blocking=True)
             self.ev_gathered.record(self.side)
+
+    def start_exchange(self):
+        """pack and all-gather the rank's records on a side stream: it overlaps with whatever runs next (the CCD half)"""
+        self.shard_counts = list(self.counts)
+        if self.cap == 0:  # first step: a generous slot from this rank's own records (ranks hold similar shares)
+            self._resize_exchange(2 * (self.HEADER + packed_bytes(self.shard_counts)) + (1 << 20))
+            # the ranks must agree on the slot size: one MAX all-reduce, first step only
+            t = self.torch.tensor([self.cap], dtype=self.torch.int64, device="cuda")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            self._resize_exchange(int(t.item()))
+        self._gather_once()
 
     def finish_exchange(self, dmin):
         """NormalCollisionsBuilder::merge over the ranks' records, then the balanced row blocks"""
         lib = self.lib
+        for attempt in range(3):
+            self.ev_gathered.synchronize()  # the headers are on the host now
+            self.all_counts = self.h_headers.view(self.world, 4).tolist()
+            need = max(self.HEADER + packed_bytes(c) for c in self.all_counts)
+            if need <= self.cap:
+                break
+            self._resize_exchange(need)  # identical decision on every rank: repeat the exchange with room
+            self._gather_once()
+        else:
+            raise RuntimeError("collision exchange: slot overflow persisted")
         self.stream.wait_event(self.ev_gathered)
         lib.check(lib.collisions_clear(self.ctx))
         for r in range(self.world):
             if sum(self.all_counts[r]) == 0:
                 continue
             c = (C.c_int64 * 4)(*self.all_counts[r])
-            lib.check(lib.collisions_append_packed_dev(self.ctx, C.c_void_p(self.recv.data_ptr() + r * self.used), c))
+            lib.check(lib.collisions_append_packed_dev(self.ctx, C.c_void_p(self.recv.data_ptr() + r * self.cap + self.HEADER), c))
         lib.check(lib.collisions_merge(self.ctx, dmin, 1, self.counts))  # 1 = IPCB_MERGE_DISJOINT_SHARDS
         self._done()
         bounds = self.mesh.balanced_row_blocks(self.world)
@@ -285,7 +308,7 @@ class DeviceShardedStep:
             job.wait()
             self.ev_ccd.record(self.stream_b)
             self.stream.wait_event(self.ev_ccd)
-        if self.world > 1:  # sum / sum / min all-reduces over NVLink; the Hessian needs no collective
+        if self.world > 1:  # sum / sum / min all-reduces over NVLink (one coalesced group); the Hessian needs no collective
             with torch.cuda.stream(self.stream):
                 dist.all_reduce(d_energy)
                 dist.all_reduce(d_grad)

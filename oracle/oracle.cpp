@@ -1364,6 +1364,42 @@ int ipco_ccd_stepsize(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t
     *step = stepsize_from_candidates(ctx, v0, v1, min_distance, resolve_ccd(ccd));
     return 0;
 }
+// Candidates::compute_noncandidate_conservative_stepsize (candidates.cpp:294-338)
+static double noncandidate_stepsize(ipcb_ctx* ctx, const std::vector<V3>& disp, double dhat)
+{
+    size_t total = 0;
+    for (auto& c : ctx->cand) total += c.size();
+    if (total == 0) return 1.0;
+    std::vector<char> is_candidate(ctx->nV, 0);
+    for (int k = 0; k < 4; k++)
+        for (const Pair& p : ctx->cand[k]) {
+            int32_t ids[4];
+            const int n = stencil_ids(ctx, k, p[0], p[1], ids);
+            for (int j = 0; j < n; j++) is_candidate[ids[j]] = 1;
+        }
+    double m = 0;
+    for (int i = 0; i < ctx->nV; i++)
+        if (is_candidate[i]) m = std::max(m, std::sqrt((disp[i][0] * disp[i][0] + disp[i][1] * disp[i][1]) + disp[i][2] * disp[i][2]));
+    return 0.5 * dhat / m;
+}
+int ipco_candidates_noncandidate_stepsize(ipcb_ctx* ctx, const double* displacements, int32_t ld, double dhat, double* step)
+{
+    *step = noncandidate_stepsize(ctx, load_vertices(ctx->nV, displacements, ld), dhat);
+    return 0;
+}
+// Candidates::compute_cfl_stepsize (candidates.cpp:340-363)
+int ipco_candidates_cfl_stepsize(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double dhat, double min_distance,
+                                 const ipcb_ccd_params* ccd, double* step)
+{
+    const auto v0 = load_vertices(ctx->nV, V0, ld), v1 = load_vertices(ctx->nV, V1, ld);
+    const double alpha_c = stepsize_from_candidates(ctx, v0, v1, min_distance, resolve_ccd(ccd));
+    std::vector<V3> disp(ctx->nV);
+    for (int i = 0; i < ctx->nV; i++) disp[i] = { v1[i][0] - v0[i][0], v1[i][1] - v0[i][1], v1[i][2] - v0[i][2] };
+    const double alpha_f = noncandidate_stepsize(ctx, disp, dhat);
+    if (alpha_f < 0.5 * alpha_c) return ipco_ccd_stepsize(ctx, V0, V1, ld, min_distance, ccd, step);
+    *step = std::min(alpha_c, alpha_f);
+    return 0;
+}
 int ipco_ccd_narrow_phase(ipcb_ctx*, int32_t kind, int64_t n, const double* x_t0, const double* x_t1, double min_distance, double tmax,
                           const ipcb_ccd_params* ccd, uint8_t* hit, double* toi)
 {

@@ -174,7 +174,10 @@ def test_filtered_contact_step_matches_the_oracle(cuda, oracle, scenes):
             out[key] = dict(free=free, counts=c.counts(), ids=[s.ids.copy() for s in sets], e=B(c, mesh, V0),
                             step=api.compute_collision_free_stepsize(mesh, V0, V1, narrow_phase_ccd=api.AdditiveCCD()))
         a, b = out["cuda"], out["oracle"]
-        assert a["counts"] == b["counts"] and a["free"] == b["free"] and sum(a["counts"]) < sum(a["free"]), name
+        assert a["counts"] == b["counts"] and a["free"] == b["free"], name
+        # the static-obstacle filter only removes sphere-sphere candidates (no collisions among them in this scene);
+        # the patch filter removes the contacts between the two sheets that share a patch
+        assert sum(a["counts"]) < sum(a["free"]) if name == "patches&static" else sum(a["counts"]) <= sum(a["free"]), name
         for x, y in zip(a["ids"], b["ids"]):
             assert np.array_equal(x, y)
         assert abs(a["e"] - b["e"]) <= 1e-10 * abs(b["e"])
