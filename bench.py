@@ -32,12 +32,19 @@ WORKLOADS = {
            dict(kind="stack", layers=3, n=100, gap=0.5, h=1.0 / 250)),
     "c5": ("C5 16-layer compressed stack (2.0M tris), gap 0.2*dhat, PSD=CLAMP", dict(kind="stack", layers=16, n=250, gap=0.2),
            dict(kind="stack", layers=3, n=100, gap=0.2, h=1.0 / 250)),
+    # BASELINE config 4: broad phase + CCD stress — only the collision-free step size is the step
+    "c4": ("C4 20 perturbed 500x500 sheets (10.0M tris), vertices displaced U(-1,1)*2h: swept broad phase + CCD step size only",
+           dict(kind="sheets", layers=20, n=500, spacing=2.0, disp=2.0, ccd_only=True), None),
+    "c4s": ("C4 at 1/10 size: 8 perturbed 250x250 sheets (1.0M tris), vertices displaced U(-1,1)*2h: swept broad phase + CCD step size only",
+            dict(kind="sheets", layers=8, n=250, spacing=2.0, disp=2.0, ccd_only=True), None),
 }
 
 
 def make_scene(scenes, spec):
     if spec["kind"] == "sphere":
         return scenes.cloth_on_sphere(spec["n"], spec["res"], drape=spec["drape"])
+    if spec["kind"] == "sheets":
+        return scenes.perturbed_sheets(spec["layers"], spec["n"], spacing=spec["spacing"], disp=spec["disp"])
     return scenes.cloth_stack(spec["layers"], spec["n"], gap=spec["gap"], h=spec.get("h"))
 
 
@@ -101,8 +108,13 @@ def ncu_traffic(workload):
     return out
 
 
-def cpu_step(api, mesh, V0, V1, dhat):
+def cpu_step(api, mesh, V0, V1, dhat, ccd_only=False):
     """one contact step through the oracle's (reference-equivalent) CPU path"""
+    if ccd_only:
+        import scipy.sparse as sp
+
+        step = api.compute_collision_free_stepsize(mesh, V0, V1)
+        return 0.0, None, sp.csc_matrix((1, 1)), step, [0, 0, 0, 0]
     c = api.NormalCollisions()
     c.build(mesh, V0, dhat)
     B = api.BarrierPotential(dhat, 1.0)
@@ -143,7 +155,7 @@ def run_reference(args, desc, full_spec, sample_spec):
     n_warm = min(args.warmup, 1)  # one warm-up step (allocations, page-in); the rest of the budget goes to timed steps
     while len(times) < args.steps:
         t = time.perf_counter()
-        out = cpu_step(api, mesh, V0, V1, P["dhat"])
+        out = cpu_step(api, mesh, V0, V1, P["dhat"], full_spec.get("ccd_only", False))
         dt = time.perf_counter() - t
         if warm < n_warm:
             warm += 1
@@ -168,7 +180,8 @@ def run_reference(args, desc, full_spec, sample_spec):
 def make_config(desc, full_spec, world, additive=False):
     """the `config` object — identical for both arms (the reference arm times the SAME workload on the host cores)"""
     nV, nE, nF = scene_sizes(full_spec)
-    return {"workload": desc, "triangles": nF, "vertices": nV, "edges": nE, "dhat": 1e-3, "psd": "CLAMP", "ccd": "TightInclusion",
+    return {"workload": desc, "triangles": nF, "vertices": nV, "edges": nE, "dhat": 1e-3 if full_spec["kind"] != "sheets" else None,
+            "psd": "CLAMP", "ccd": "TightInclusion",
             "collision_set": "IPC", "l2": "GPU arm: flushed between timed steps (256 MB write); CPU arm: inputs larger than the caches",
             "parallelism": ("single GPU" if world == 1 else
                             "candidate shards by Morton range of query leaves; " +
@@ -208,6 +221,7 @@ def main():
                          "instead of the all-gathered set with row-block Hessians")
     ap.add_argument("--single-context", action="store_true",
                     help="A/B: run the five calls of the step one after the other on ONE context (no second lane for the CCD half)")
+    ap.add_argument("--broad", default="lbvh", choices=["lbvh", "sap"], help="broad-phase method of the CUDA library (A/B: LBVH or sweep-and-prune)")
     ap.add_argument("--ncu-step", action="store_true",
                     help="profiling aid: warm up, then run ONE device step between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench line")
@@ -247,7 +261,11 @@ def main():
     mesh = api.CollisionMesh(V0, E, F, device=local)
     ctx = mesh._ctx
     # second context on the same mesh: the CCD half of the step runs on its own streams beside the potential half
-    ccd_mesh = None if args.single_context else api.CollisionMesh(V0, E, F, device=local)
+    ccd_only = bool(full_spec.get("ccd_only"))
+    ccd_mesh = None if (args.single_context or ccd_only) else api.CollisionMesh(V0, E, F, device=local)
+    for m in (mesh, ccd_mesh):
+        if m is not None:
+            m.set_broad_phase_method(args.broad)
     contexts = [ctx] + ([ccd_mesh._ctx] if ccd_mesh is not None else [])
     lib.check(lib.ctx_set_shard(ctx, rank, world))
     stream = torch.cuda.ExternalStream(lib.ctx_stream(ctx), device=torch.device("cuda", local))
@@ -287,7 +305,15 @@ def main():
     sharded = __import__("importlib").import_module("ipc_toolkit_b200.sharded")
     stepper = sharded.DeviceShardedStep(api, mesh, rank, world, dist, torch, stream, row_block=not args.additive_hessian, ccd_mesh=ccd_mesh)
 
+    def ccd_only_step(record=False):
+        lib.check(lib.ccd_stepsize_dev(ctx, C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr()), nV, 0.0, C.byref(ccd), C.c_void_p(d_step.data_ptr())))
+        if record:
+            collect_stages(ctx)
+        info["nnz"], info["collisions"], info["shard_collisions"], info["rows"] = 0, [0, 0, 0, 0], [0, 0, 0, 0], [0, nV]
+
     def device_step(record=False):
+        if ccd_only:
+            return ccd_only_step(record)
         stepper.after = collect_stages if record else None
         info["nnz"] = stepper.step(dV0, dV1, d_energy, d_grad, d_step, dhat, bp, ccd)
         info["collisions"] = list(stepper.counts)
@@ -345,7 +371,7 @@ def main():
         lib.ctx_enable_stage_timing(c, 0)
     lib.check(lib.candidates_build_swept_dev(ctx, C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr()), nV, 0.0, counts))
     info["ccd_candidates"] = list(counts)
-    if world == 1:
+    if world == 1 and not ccd_only:
         hv = np.asfortranarray(V0)
         lib.check(lib.candidates_build_static(ctx, hv.ctypes.data_as(C.c_void_p), nV, 0.5 * dhat, counts))
         info["static_candidates"] = list(counts)
@@ -354,7 +380,7 @@ def main():
     # 95-116) from RESIDENT candidates: swept candidates with inflation dhat built once, then per line-search point
     # NormalCollisions::build(candidates, mesh, X, dhat) + the barrier energy — no broad phase inside the loop
     line_search = None
-    if world == 1:
+    if world == 1 and not ccd_only:
         p0, p1 = C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr())
         lib.check(lib.candidates_build_swept_dev(ctx, p0, p1, nV, dhat, counts))
         ls_cand = list(counts)
@@ -392,6 +418,11 @@ def main():
         """N = 1: the host-buffer C ABI — every call takes pinned HOST positions and returns HOST results (energy,
         gradient, the CSR arrays, the step size); the step-size call runs on the second context beside the others"""
         e, st = C.c_double(), C.c_double()
+        if ccd_only:
+            lib.check(lib.ccd_stepsize(ctx, hv0p, hv1p, nV, 0.0, C.byref(ccd), C.byref(st)))
+            e2e_bytes["h2d"], e2e_bytes["d2h"] = 24 * nV * 2, 8
+            info["step"], info["energy"] = st.value, 0.0
+            return
         job = None
         if stepper.lane is not None:
             job = stepper.lane.submit(lambda: lib.check(lib.ccd_stepsize(stepper.ctx_b, hv0p, hv1p, nV, 0.0, C.byref(ccd), C.byref(st))))
@@ -535,8 +566,9 @@ def main():
     if roof_main is not None:  # the contract's `roofline` object: the dominant kernel against the MEASURED HBM bandwidth; its FP64 view rides along
         hbm = roof("k_hessian_fast<VV|EV|EE|FV>", hf_ms, sum(hl_bytes), ["k_hessian_fast<0", "k_hessian_fast<1", "k_hessian_fast<2", "k_hessian_fast<3"],
                    roof_main["note"], flops=sum(hl_flops), bound="hbm", fp64_inst=sum(hl_inst))
-        hbm["binding"] = "fp64 (see the fp64 object: the kernel is bound by the FP64 pipe, its HBM fraction is reported as the contract asks)"
-        roof_main = hbm
+        if hbm is not None:
+            hbm["binding"] = "fp64 (see the fp64 object: the kernel is bound by the FP64 pipe, its HBM fraction is reported as the contract asks)"
+            roof_main = hbm
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -552,7 +584,7 @@ def main():
         oapi.set_num_threads(cores)
         omesh = oapi.CollisionMesh(V0, E, F)
         t = time.perf_counter()
-        cpu_out = cpu_step(oapi, omesh, V0, V1, dhat)
+        cpu_out = cpu_step(oapi, omesh, V0, V1, dhat, ccd_only)
         cpu_ms = (time.perf_counter() - t) * 1e3
         cpu = {"value": cpu_ms, "unit": "ms", "cores": cores, "kind": "port",
                "sample": "the full workload (%d triangles), one step, no warm-up" % F.shape[0],
@@ -577,6 +609,7 @@ def main():
             "stages_ms": stages,
             "kernels_ms": kernels_ms,
             "lanes": "two contexts: build + potential || swept broad phase + CCD" if ccd_mesh is not None else "one context, sequential calls",
+            "broad_phase": args.broad,
             "line_search_rebuild": line_search,
             "counts": {"collisions_rank0": info.get("collisions"), "shard_collisions_rank0": info.get("shard_collisions"),
                        "hessian_rows_rank0": info.get("rows"), "ccd_candidates_rank0": info.get("ccd_candidates"),

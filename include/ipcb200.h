@@ -47,6 +47,7 @@ extern "C" {
 #define IPCB_FN(name) IPCB_CAT(IPCB_PREFIX, name)
 
 typedef struct ipcb_ctx ipcb_ctx;
+typedef struct ipcb_collision_set ipcb_collision_set;
 
 /* candidate / collision kinds (candidates/candidates.hpp:240-244) */
 enum { IPCB_VV = 0, IPCB_EV = 1, IPCB_EE = 2, IPCB_FV = 3, IPCB_EF = 4, IPCB_FF = 5 };
@@ -61,6 +62,11 @@ enum { IPCB_CCD_TIGHT_INCLUSION = 0, IPCB_CCD_ADDITIVE = 1 };
  * boxes (broad_phase/lbvh.cpp:29-41, lbvh.hpp:66-70); DOUBLE = BruteForce /
  * HashGrid double boxes (broad_phase/aabb.cpp:29-33).  Cross-check switch. */
 enum { IPCB_BOXES_FLOAT = 0, IPCB_BOXES_DOUBLE = 1 };
+
+/* broad-phase method of a context (north_star subsystem 1): the LBVH (default) or a sweep-and-prune over the boxes sorted
+ * along the longest scene axis (reference semantics broad_phase/sweep_and_prune.cpp:106-119).  Same predicate, hence the
+ * same candidate sets; only the cost differs (bench.py --broad sap). */
+enum { IPCB_BROAD_LBVH = 0, IPCB_BROAD_SAP = 1 };
 
 /* flags for collisions_build (collisions/normal/normal_collisions.hpp:191-194: use_area_weighting; :29-39
  * CollisionSetType).  IPCB_SET_IMPROVED_MAX_APPROX selects CollisionSetType::IMPROVED_MAX_APPROX (the negative /
@@ -177,6 +183,15 @@ int IPCB_FN(collisions_clear)(ipcb_ctx* ctx);
 int IPCB_FN(collisions_append)(ipcb_ctx* ctx, int32_t kind, int64_t count, const int32_t* ids, const double* weight,
                                const double* eps_x, const uint8_t* dtype);
 int IPCB_FN(collisions_merge)(ipcb_ctx* ctx, double dmin, int32_t flags, int64_t counts[4]);
+/* Independent collision sets on one mesh.  A context works on ONE resident set; the reference's NormalCollisions are plain
+ * containers of which a caller may hold several per mesh (a lagged set for friction, the sets of a line search).  A
+ * collision-set object parks a set outside the context: collisions_swap exchanges the context's resident set with the
+ * object's content in O(1) (device buffers change owner, nothing is copied; an empty object receives the resident set and
+ * leaves the context without one).  The host mirrors give every NormalCollisions its own object and swap it in when the
+ * potential is evaluated on it. */
+int IPCB_FN(collision_set_create)(ipcb_ctx* ctx, ipcb_collision_set** out);
+void IPCB_FN(collision_set_destroy)(ipcb_collision_set* set);
+int IPCB_FN(collisions_swap)(ipcb_ctx* ctx, ipcb_collision_set* set, int64_t counts[4] /* of the now-resident set */);
 /* Sharding of the potential over ranks, for contexts that all hold the SAME collision set:
  *  - collision range: energy and gradient only visit the slice [rank*n/world, (rank+1)*n/world) of every
  *    kind's collisions (the results need a sum all-reduce);
@@ -273,6 +288,8 @@ int IPCB_FN(ccd_stepsize_from_candidates_dev)(ipcb_ctx* ctx, const double* dV0, 
  * gradient and step size then need a sum / sum / min all-reduce by the caller
  * (NCCL), the Hessian is the rank's additive contribution. */
 int IPCB_FN(ctx_set_shard)(ipcb_ctx* ctx, int32_t rank, int32_t world);
+/* IPCB_BROAD_LBVH / IPCB_BROAD_SAP for every later broad-phase build on this context */
+int IPCB_FN(ctx_set_broad_phase_method)(ipcb_ctx* ctx, int32_t method);
 /* number of kernels this context has launched so far (bench.py gpu_launches) */
 int IPCB_FN(ctx_launch_count)(ipcb_ctx* ctx, int64_t* n);
 /* per-stage device time of the last call in ms, by stage name; returns the number of stages filled.

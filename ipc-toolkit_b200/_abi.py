@@ -47,6 +47,9 @@ HOST_API = {
     "collisions_clear": (C.c_int, [P]),
     "collisions_append": (C.c_int, [P, c_i32, c_i64, P, P, P, P]),
     "collisions_merge": (C.c_int, [P, c_f64, c_i32, C.POINTER(c_i64)]),
+    "collision_set_create": (C.c_int, [P, C.POINTER(P)]),
+    "collision_set_destroy": (None, [P]),
+    "collisions_swap": (C.c_int, [P, P, C.POINTER(c_i64)]),
     "ctx_set_collision_range": (C.c_int, [P, c_i32, c_i32]),
     "ctx_set_row_block": (C.c_int, [P, c_i32, c_i32]),
     "hessian_balanced_row_blocks": (C.c_int, [P, c_i32, P]),
@@ -77,6 +80,7 @@ DEVICE_API = {
     "ccd_stepsize_dev": (C.c_int, [P, P, P, c_i32, c_f64, C.POINTER(CcdParams), P]),
     "ccd_stepsize_from_candidates_dev": (C.c_int, [P, P, P, c_i32, c_f64, C.POINTER(CcdParams), P]),
     "ctx_set_shard": (C.c_int, [P, c_i32, c_i32]),
+    "ctx_set_broad_phase_method": (C.c_int, [P, c_i32]),
     "ctx_launch_count": (C.c_int, [P, C.POINTER(c_i64)]),
     "ctx_enable_stage_timing": (C.c_int, [P, c_i32]),
     "ctx_stage_times": (C.c_int, [P, c_i32, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),

@@ -20,6 +20,7 @@ handles (using them raises ``RuntimeError``).
 import ctypes as C
 import enum
 import types
+import weakref
 
 import numpy as np
 
@@ -160,7 +161,7 @@ def make_api(lib):
             f, fp, fld = _i32(self.faces, 3)
             lib.check(lib.mesh_set(self._ctx, rest.shape[0], rp, rld, e.shape[0], ep, eld, f.shape[0], fp, fld))
             self._cand_gen = 0
-            self._coll_gen = 0
+            self._resident = None  # weak reference to the NormalCollisions whose records are the context's resident set
             self._can_collide = CollisionFilter()
 
         @property
@@ -221,6 +222,12 @@ def make_api(lib):
 
         def edge_areas(self):
             return self._areas()[1]
+
+        def set_broad_phase_method(self, method):
+            """"lbvh" (default) or "sap": the CUDA broad phase behind every later build on this mesh (product only)"""
+            m = {"lbvh": 0, "sap": 1}[method] if isinstance(method, str) else int(method)
+            lib.check(lib.ctx_set_broad_phase_method(self._ctx, m))
+            self._cand_gen += 1
 
         # ---- sharding of the potential over ranks holding the same collision set (include/ipcb200.h)
         def set_collision_range(self, rank, world):
@@ -398,7 +405,8 @@ def make_api(lib):
 
         def __init__(self):
             self.mesh = None
-            self._gen = -1
+            self._set = None
+            self._built = False
             self._counts = [0, 0, 0, 0]
             self._host = {}
             self.use_area_weighting = False
@@ -419,6 +427,10 @@ def make_api(lib):
             """build(mesh, V, dhat, dmin=0, broad_phase=None) or build(candidates, mesh, V, dhat, dmin=0)"""
             counts = (C.c_int64 * 4)()
             flags = self._flags()
+            mesh = args[1] if isinstance(args[0], Candidates) else args[0]
+            if self.mesh is not None and self.mesh is not mesh and self._set is not None:
+                raise RuntimeError("a NormalCollisions object cannot move to another mesh")
+            NormalCollisions._park_resident(mesh, keep=self)  # another set's records leave the context before it is overwritten
             if isinstance(args[0], Candidates):
                 cand, mesh, V, dhat = args[:4]
                 dmin = args[4] if len(args) > 4 else kw.get("dmin", 0.0)
@@ -439,6 +451,7 @@ def make_api(lib):
             weight == 0 dropped).  `builders`: iterable of 4-tuples (vv, ev, ee, fv) of record namespaces as the
             *_collisions properties return them (ids, weight, eps_x, dtype) — e.g. the sets of the other ranks.
             disjoint_shards=True promises that the builders worked on disjoint candidate shards (IPCB_MERGE_DISJOINT_SHARDS)."""
+            NormalCollisions._park_resident(mesh, keep=self)
             lib.check(lib.collisions_clear(mesh._ctx))
             for kinds in builders:
                 for kind, rec in enumerate(kinds):
@@ -455,17 +468,54 @@ def make_api(lib):
             lib.check(lib.collisions_merge(mesh._ctx, dmin, 1 if disjoint_shards else 0, counts))
             self._bind(mesh, counts, dmin)
 
+        # ---- several sets per mesh: the context works on ONE resident set; every NormalCollisions owns a collision-set
+        # object of the library and is swapped in (O(1), ipcb_collisions_swap) when it is used, the previous owner's
+        # records are parked in its own object first
+        def _handle(self):
+            if self._set is None:
+                self._set = C.c_void_p()
+                lib.check(lib.collision_set_create(self.mesh._ctx, C.byref(self._set)))
+            return self._set
+
+        @staticmethod
+        def _park_resident(mesh, keep=None):
+            owner = mesh._resident() if mesh._resident is not None else None
+            if owner is not None and owner is not keep and owner.mesh is mesh:
+                counts = (C.c_int64 * 4)()
+                lib.check(lib.collisions_swap(mesh._ctx, owner._handle(), counts))  # the owner's records move into its object
+            if owner is not keep:
+                mesh._resident = None
+
         def _bind(self, mesh, counts, dmin):
             self.mesh = mesh
-            mesh._coll_gen += 1
-            self._gen = mesh._coll_gen
+            mesh._resident = weakref.ref(self)
+            self._built = True
             self._counts = list(counts)
             self._host = {}
             self.dmin = dmin
 
         def _live(self):
-            if self.mesh is None or self._gen != self.mesh._coll_gen:
-                raise RuntimeError("stale NormalCollisions handle: a newer collision set was built on this mesh")
+            """make this set the resident one of its mesh"""
+            if self.mesh is None or not self._built:
+                raise RuntimeError("NormalCollisions has not been built")
+            mesh = self.mesh
+            if getattr(mesh, "_ctx", None) is None:
+                raise RuntimeError("the CollisionMesh of this NormalCollisions has been closed")
+            if mesh._resident is not None and mesh._resident() is self:
+                return
+            NormalCollisions._park_resident(mesh)
+            counts = (C.c_int64 * 4)()
+            lib.check(lib.collisions_swap(mesh._ctx, self._handle(), counts))  # this set's records become resident
+            assert list(counts) == self._counts
+            mesh._resident = weakref.ref(self)
+
+        def __del__(self):
+            try:
+                if self._set is not None and self.mesh is not None and getattr(self.mesh, "_ctx", None) is not None:
+                    lib.collision_set_destroy(self._set)
+            except Exception:  # interpreter shutdown
+                pass
+            self._set = None
 
         def _get(self, kind):
             self._live()

@@ -104,6 +104,16 @@ public:
         check(ipcb_mesh_faces_to_edges(ctx(), out.data()));
         return out;
     }
+    /// CollisionMesh::can_collide (collision_mesh.hpp:338) as the descriptor the C ABI carries: the intersection of
+    /// make_vertex_patches_filter(patch_ids) and make_static_obstacle_filter(n_dynamic) (collision_filter.hpp:113-143);
+    /// an empty vector / a negative count switches that factory off.  Arbitrary callables: see ipc_toolkit_adapter.hpp.
+    void set_collision_filter(const std::vector<index_t>& patch_ids, index_t n_dynamic = -1) const
+    {
+        if (!patch_ids.empty() && patch_ids.size() != size_t(m_nv)) throw std::invalid_argument("patch_ids must hold one label per vertex");
+        check(ipcb_mesh_set_collision_filter(ctx(), patch_ids.empty() ? nullptr : patch_ids.data(), n_dynamic));
+    }
+    /// IPCB_BROAD_LBVH (default) or IPCB_BROAD_SAP for every later broad-phase build on this mesh
+    void set_broad_phase_method(int method) const { check(ipcb_ctx_set_broad_phase_method(ctx(), method)); }
     std::vector<double> vertex_areas() const { return areas().first; }
     std::vector<double> edge_areas() const { return areas().second; }
     ipcb_ctx* ctx() const { return m_ctx.get(); }
@@ -185,6 +195,21 @@ public:
                                 const NarrowPhaseCCD& ccd = DEFAULT_NARROW_PHASE_CCD) const
     {
         return compute_collision_free_stepsize(mesh, vertices_t0, vertices_t1, min_distance, ccd) >= 1.0;
+    }
+    // candidates.cpp:294-338
+    double compute_noncandidate_conservative_stepsize(const CollisionMesh& mesh, MatrixXd displacements, double dhat) const
+    {
+        double step = 1.0;
+        check(ipcb_candidates_noncandidate_stepsize(mesh.ctx(), displacements.data, displacements.ld, dhat, &step));
+        return step;
+    }
+    // candidates.cpp:340-363 (the resident candidates are replaced when the full CCD had to run)
+    double compute_cfl_stepsize(const CollisionMesh& mesh, MatrixXd vertices_t0, MatrixXd vertices_t1, double dhat, double min_distance = 0.0,
+                                const NarrowPhaseCCD& ccd = DEFAULT_NARROW_PHASE_CCD) const
+    {
+        double step = 1.0;
+        check(ipcb_candidates_cfl_stepsize(mesh.ctx(), vertices_t0.data, vertices_t1.data, vertices_t0.ld, dhat, min_distance, &ccd.params, &step));
+        return step;
     }
 
 private:
@@ -287,6 +312,7 @@ public:
     }
     double dhat() const { return m_bp.dhat; }
     double stiffness() const { return m_bp.stiffness; }
+    bool use_physical_barrier() const { return m_bp.use_physical_barrier != 0; }
     double operator()(const NormalCollisions&, const CollisionMesh& mesh, MatrixXd X) const
     {
         double e;

@@ -145,6 +145,14 @@ int ipcb_ctx_set_shard(ipcb_ctx* ctx, int32_t rank, int32_t world)
         ctx->shard_world = world;
     });
 }
+int ipcb_ctx_set_broad_phase_method(ipcb_ctx* ctx, int32_t method)
+{
+    return guarded([&] {
+        if (method != IPCB_BROAD_LBVH && method != IPCB_BROAD_SAP) throw Error("unknown broad-phase method");
+        ctx->broad_method = method;
+        ctx->built = false;
+    });
+}
 int ipcb_ctx_set_collision_range(ipcb_ctx* ctx, int32_t rank, int32_t world)
 {
     return guarded([&] {
@@ -646,6 +654,32 @@ int ipcb_collisions_merge(ipcb_ctx* ctx, double dmin, int32_t flags, int64_t cou
         coll_counts(ctx, counts);
     });
 }
+int ipcb_collision_set_create(ipcb_ctx* ctx, ipcb_collision_set** out)
+{
+    return guarded([&] {
+        *out = new ipcb_collision_set();
+        (*out)->device = ctx->device;
+    });
+}
+void ipcb_collision_set_destroy(ipcb_collision_set* set)
+{
+    if (!set) return;
+    cudaSetDevice(set->device);
+    delete set;
+}
+int ipcb_collisions_swap(ipcb_ctx* ctx, ipcb_collision_set* set, int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (!set) throw Error("collisions_swap: null collision set");
+        if (set->device != ctx->device) throw Error("collisions_swap: the set lives on another device");
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream)); // nothing in flight may still read the outgoing records
+        for (int k = 0; k < 4; k++) ctx->coll[k].swap_records(set->coll[k]);
+        std::swap(ctx->dmin, set->dmin);
+        std::swap(ctx->coll_valid, set->valid);
+        for (int k = 0; k < 4; k++) counts[k] = ctx->coll_valid ? ctx->coll[k].count : 0;
+    });
+}
 int ipcb_collisions_dev_ptrs(ipcb_ctx* ctx, int32_t kind, int64_t* count, const int32_t** d_ids, const double** d_weight,
                              const double** d_eps_x, const uint8_t** d_dtype)
 {
@@ -829,8 +863,10 @@ int ipcb_ccd_stepsize_dev(ipcb_ctx* ctx, const double* dV0, const double* dV1, i
         begin_call(ctx);
         convert_positions(ctx, dV0, ld, ctx->X0);
         convert_positions(ctx, dV1, ld, ctx->X1);
-        candidates_build(ctx, true, 0.5 * min_distance); // ipc.cpp:95-96
-        ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_step);
+        if (candidates_build(ctx, true, 0.5 * min_distance, true)) // ipc.cpp:95-96; too many pairs for one list: stream them
+            ccd_stepsize_streaming(ctx, min_distance, resolve_ccd(ccd), d_step);
+        else
+            ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_step);
     });
 }
 int ipcb_ccd_stepsize_from_candidates(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double min_distance,
@@ -853,9 +889,9 @@ int ipcb_ccd_stepsize(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t
         begin_call(ctx);
         stage_positions(ctx, V0, ld, false);
         stage_positions(ctx, V1, ld, true);
-        candidates_build(ctx, true, 0.5 * min_distance);
         double* d_out = reinterpret_cast<double*>(ctx->dCounters.p + 13);
-        ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_out);
+        if (candidates_build(ctx, true, 0.5 * min_distance, true)) ccd_stepsize_streaming(ctx, min_distance, resolve_ccd(ccd), d_out);
+        else ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_out);
         IPCB_CUDA(cudaMemcpyAsync(step, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
     });
@@ -886,8 +922,8 @@ int ipcb_candidates_cfl_stepsize(ipcb_ctx* ctx, const double* V0, const double* 
         const double alpha_c = fetch();
         const double alpha_f = noncandidate_stepsize(ctx, true, dhat);
         if (alpha_f < 0.5 * alpha_c) { // candidates.cpp:356-360: do the full CCD
-            candidates_build(ctx, true, 0.5 * min_distance);
-            ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_out);
+            if (candidates_build(ctx, true, 0.5 * min_distance, true)) ccd_stepsize_streaming(ctx, min_distance, resolve_ccd(ccd), d_out);
+            else ccd_stepsize(ctx, min_distance, resolve_ccd(ccd), d_out);
             *step = fetch();
         } else {
             *step = std::min(alpha_c, alpha_f);

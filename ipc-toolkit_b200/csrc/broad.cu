@@ -24,6 +24,8 @@
 #include "ctx.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cfloat>
+#include <algorithm>
+#include <cstdlib>
 
 namespace ipcb {
 
@@ -451,13 +453,13 @@ __global__ void k_karras_boxes(int n, const unsigned long long* __restrict__ key
 // (4 radix passes) up to 4M primitives, 13 (5 passes) up to 64M, the reference's 21 (8 passes) beyond.
 static int morton_bits(int n) { return n <= (1 << 22) ? 10 : (n <= (1 << 26) ? 13 : 21); }
 
-static void sort_keys(ipcb_ctx* ctx, Tree& t, int n, int bits, cudaStream_t s)
+static void sort_keys(ipcb_ctx* ctx, Tree& t, int n, int end_bit, cudaStream_t s)
 {
     size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 3 * bits, s);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, end_bit, s);
     t.tmp.reserve(bytes);
-    cub::DeviceRadixSort::SortPairs(t.tmp.p, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, 3 * bits, s);
-    ctx->launches += 2 + (3 * bits + 7) / 8; // onesweep: histogram + exclusive sum + one pass per 8 bits
+    cub::DeviceRadixSort::SortPairs(t.tmp.p, bytes, t.key.p, t.key_sorted.p, t.ord.p, t.ord_sorted.p, n, 0, end_bit, s);
+    ctx->launches += 2 + (end_bit + 7) / 8; // onesweep: histogram + exclusive sum + one pass per 8 bits
 }
 
 // Morton-sort a PrimSet; with_nodes additionally builds the hierarchy
@@ -474,7 +476,7 @@ static void build_tree(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, bool with_node
     k_morton<<<grid_for(n, 256), 256, 0, s>>>(n, bits, getenv("IPCB_MORTON_PER_AXIS") ? 0 : 1, ps.box.p, ctx->scene.p, t.key.p, t.ord.p);
     {
         Stage kt(ctx, "k:radix_sort(morton)", s);
-        sort_keys(ctx, t, n, bits, s);
+        sort_keys(ctx, t, n, 3 * bits, s);
     }
     Stage kt(ctx, "k:lbvh_nodes", s);
     const bool bottom_up = getenv("IPCB_REFIT_BOTTOM_UP") != nullptr; // A/B + test hook: the arrival-counter refit
@@ -510,6 +512,39 @@ static void build_tree(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, bool with_node
     t.has_nodes = true;
 }
 
+__global__ void k_axis_key(int n, int axis, const FBox* __restrict__ box, unsigned long long* __restrict__ key, int* __restrict__ ord);
+// sweep-and-prune view of a PrimSet: boxes and primitives sorted by the lower bound along ctx->sap_axis
+static void build_sap_view(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, cudaStream_t s)
+{
+    const int n = ps.n;
+    t.n = n;
+    t.has_nodes = false;
+    if (n == 0) return;
+    t.key.reserve(n), t.key_sorted.reserve(n), t.ord.reserve(n), t.ord_sorted.reserve(n);
+    t.sbox.reserve(n), t.sprim.reserve(n);
+    k_axis_key<<<grid_for(n, 256), 256, 0, s>>>(n, ctx->sap_axis, ps.box.p, t.key.p, t.ord.p);
+    sort_keys(ctx, t, n, 32, s);
+    k_apply_order<<<grid_for(n, 256), 256, 0, s>>>(n, t.ord_sorted.p, ps.box.p, ps.prim.p, t.sbox.p, t.sprim.p);
+    ctx->launches += 2;
+}
+// the sweep axis: the longest extent of the scene box (one 24-byte read-back per build in this mode)
+static void choose_sap_axis(ipcb_ctx* ctx)
+{
+    float h[6];
+    IPCB_CUDA(cudaMemcpyAsync(h, ctx->scene.p, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    const float e[3] = { h[3] - h[0], h[4] - h[1], h[5] - h[2] };
+    ctx->sap_axis = e[0] >= e[1] && e[0] >= e[2] ? 0 : (e[1] >= e[2] ? 1 : 2);
+}
+static Tree& ensure_sap_view(ipcb_ctx* ctx, int which)
+{
+    if (!ctx->sap_axis_ok) choose_sap_axis(ctx), ctx->sap_axis_ok = true;
+    Tree* t[3] = { &ctx->sap_v, &ctx->sap_e, &ctx->sap_f };
+    const PrimSet* ps[3] = { &ctx->vset, &ctx->eset, &ctx->fset };
+    if (!ctx->sap_ok[which]) build_sap_view(ctx, *ps[which], *t[which], ctx->stream), ctx->sap_ok[which] = true;
+    return *t[which];
+}
+
 void broad_build(ipcb_ctx* ctx, bool swept, double r)
 {
     Stage st(ctx, "broad_build");
@@ -528,6 +563,7 @@ void broad_build(ipcb_ctx* ctx, bool swept, double r)
     if (nF) k_face_boxes<<<grid_for(nF, 256), 256, 0, s>>>(nF, ctx->dF.p, ctx->vset.box.p, ctx->fset.box.p, ctx->fset.prim.p);
     ctx->launches += 4;
     ctx->vtree_ok = ctx->etree_ok = ctx->ftree_ok = false;
+    ctx->sap_ok[0] = ctx->sap_ok[1] = ctx->sap_ok[2] = false, ctx->sap_axis_ok = false;
     ctx->vorder_valid = false;
     ctx->vtree.n = ctx->etree.n = ctx->ftree.n = 0;
     ctx->vtree.has_nodes = ctx->etree.has_nodes = ctx->ftree.has_nodes = false;
@@ -694,6 +730,114 @@ __global__ void __launch_bounds__(TRAV_BLOCK)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Sweep and prune (north_star subsystem 1; reference semantics broad_phase/sweep_and_prune.cpp:106-119, GPU route
+// sweep_and_tiniest_queue.cu:121-212): the boxes are sorted by their lower bound along ONE axis (the longest scene
+// extent); every query scans the sorted targets forward while their lower bound does not pass its upper bound and
+// tests the two other axes.  No hierarchy, no stack: sequential coalesced box reads — the alternative to the LBVH for
+// scenes whose swept boxes overlap so much that a tree prunes little (BASELINE config 4).  The predicate (closed
+// float-box overlap, no shared vertex, collision filter) and therefore the candidate SET are those of the LBVH.
+__device__ __forceinline__ float axis_lo(const FBox& b, int ax) { return ax == 0 ? b.lo[0] : (ax == 1 ? b.lo[1] : b.lo[2]); }
+__device__ __forceinline__ float axis_hi(const FBox& b, int ax) { return ax == 0 ? b.hi[0] : (ax == 1 ? b.hi[1] : b.hi[2]); }
+// monotone float -> unsigned key
+__global__ void k_axis_key(int n, int axis, const FBox* __restrict__ box, unsigned long long* __restrict__ key, int* __restrict__ ord)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned u = __float_as_uint(axis_lo(box[i], axis));
+    key[i] = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    ord[i] = i;
+}
+// start: 0 = self (targets after the query), 1 = first target with lo >= query lo, 2 = first target with lo > query lo
+template <int MODE, int QN, int TN, bool FILTERED>
+__global__ void __launch_bounds__(TRAV_BLOCK)
+    k_sap_sweep(int q_begin, int q_end, const FBox* __restrict__ qbox, const int4* __restrict__ qprim, int n_target,
+                const FBox* __restrict__ tbox, const int4* __restrict__ tprim, int axis, int start_rule, int2* __restrict__ out,
+                unsigned long long* counter, unsigned long long capacity, int flags, FilterView filter)
+{
+    __shared__ int2 stage[TRAV_BLOCK / 32][STAGE_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool check_shared = flags & 1;
+    bool active = qi < q_end;
+    FBox q;
+    int4 qp = make_int4(-1, -1, -1, -1);
+    int j = n_target;
+    float qhi = -INFINITY;
+    if (active) {
+        q = qbox[qi];
+        qp = qprim[qi];
+        qhi = axis_hi(q, axis);
+        if (start_rule == 0) {
+            j = qi + 1;
+        } else { // binary search over the sorted lower bounds
+            const float qlo = axis_lo(q, axis);
+            int lo = 0, hi = n_target;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const float v = axis_lo(tbox[mid], axis);
+                if (start_rule == 1 ? v < qlo : v <= qlo) lo = mid + 1;
+                else hi = mid;
+            }
+            j = lo;
+        }
+    }
+    const int a1 = (axis + 1) % 3, a2 = (axis + 2) % 3;
+    int nstaged = 0;
+    while (__any_sync(0xffffffffu, active && j < n_target)) {
+        bool emit = false;
+        int2 pr = make_int2(0, 0);
+        if (active && j < n_target) {
+            const FBox b = tbox[j];
+            if (axis_lo(b, axis) > qhi) {
+                active = false; // sorted: no later target can overlap along the sweep axis
+            } else if (axis_lo(q, a1) <= axis_hi(b, a1) && axis_lo(b, a1) <= axis_hi(q, a1) && axis_lo(q, a2) <= axis_hi(b, a2)
+                       && axis_lo(b, a2) <= axis_hi(q, a2)) {
+                const int4 tp = __ldg(tprim + j);
+                if ((!check_shared || !shares_vertex<QN, TN>(qp, tp)) && (!FILTERED || any_can_collide<QN, TN>(filter, qp, tp))) {
+                    emit = true;
+                    if (MODE == 0) pr = make_int2(qp.w, tp.w);
+                    else if (MODE == 1) pr = make_int2(tp.w, qp.w);
+                    else pr = make_int2(min(qp.w, tp.w), max(qp.w, tp.w));
+                }
+            }
+            j++;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, emit);
+        if (m) {
+            if (emit) stage[warp][nstaged + __popc(m & ((1u << lane) - 1))] = pr;
+            nstaged += __popc(m);
+            if (nstaged > STAGE_CAP - 32) {
+                __syncwarp();
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(counter, (unsigned long long)nstaged);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (int k = lane; k < nstaged; k += 32)
+                    if (base + k < capacity) out[base + k] = stage[warp][k];
+                nstaged = 0;
+                __syncwarp();
+            }
+        }
+    }
+    if (nstaged > 0) {
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)nstaged);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int k = lane; k < nstaged; k += 32)
+            if (base + k < capacity) out[base + k] = stage[warp][k];
+    }
+}
+
+// Largest candidate list (pairs of one kind) the library materialises: beyond it the collision-free step size streams
+// the query leaves in chunks (ccd.cu: ccd_stepsize_streaming) and everything else fails loudly.  Default 2^29 pairs
+// (4 GiB per list); IPCB_MAX_PAIRS overrides it (the tests use tiny values to force the chunked path).
+size_t max_pairs()
+{
+    const char* e = getenv("IPCB_MAX_PAIRS"); // read per call: the tests switch it inside one process
+    return e ? std::max<size_t>(64, strtoull(e, nullptr, 10)) : (size_t(1) << 29);
+}
+
 // one detection: queries (sorted view) against a tree.  launch() enqueues the kernel and the read-back of the
 // pair count on the job's stream; finish() waits for it and, if the output buffer was too small, grows it and
 // repeats the pass.  Two jobs on different streams / counter slots run concurrently.
@@ -706,22 +850,39 @@ struct TraverseJob {
     PairList* out;
     cudaStream_t s;
     int slot; // device counter / pinned slot (0 or 1)
+    bool sap = false; // q / t are axis-sorted views and the pass is a sweep (two sweeps for two different sets)
     int q_begin = 0, q_end = 0;
     bool live = false;
+    unsigned long long overflow = 0; // pairs found by a pass that exceeded max_pairs() (the list is then invalid)
 
+    // the rank's Morton range of query leaves; false when there is nothing to traverse
+    bool full_range(bool shard)
+    {
+        if (q->n == 0 || t->n == 0 || (mode == 2 && t->n < 2)) return false;
+        q_begin = 0, q_end = q->n;
+        if (shard && ctx->shard_world > 1) {
+            q_begin = int((int64_t(q->n) * ctx->shard_rank) / ctx->shard_world);
+            q_end = int((int64_t(q->n) * (ctx->shard_rank + 1)) / ctx->shard_world);
+        }
+        return q_end - q_begin > 0;
+    }
     void launch(bool shard)
     {
         out->count = 0;
         out->sorted = false;
         live = false;
-        if (q->n == 0 || t->n == 0 || (mode == 2 && t->n < 2)) return;
-        q_begin = 0, q_end = q->n;
-        if (shard && ctx->shard_world > 1) { // contiguous Morton range of query leaves per rank
-            q_begin = int((int64_t(q->n) * ctx->shard_rank) / ctx->shard_world);
-            q_end = int((int64_t(q->n) * (ctx->shard_rank + 1)) / ctx->shard_world);
-        }
-        if (q_end - q_begin <= 0) return;
-        if (out->pairs.cap == 0) out->pairs.reserve(size_t(q_end - q_begin) * 8 + 1024);
+        overflow = 0;
+        if (!full_range(shard)) return;
+        launch_range(q_begin, q_end);
+    }
+    // queries [qb, qe) only (chunked emission: SURVEY §7 hard part 7)
+    void launch_range(int qb, int qe)
+    {
+        out->count = 0;
+        out->sorted = false;
+        overflow = 0;
+        q_begin = qb, q_end = qe;
+        if (out->pairs.cap == 0) out->pairs.reserve(std::min(size_t(q_end - q_begin) * 8 + 1024, max_pairs()));
         live = true;
         enqueue();
     }
@@ -734,6 +895,11 @@ struct TraverseJob {
         Stage kt(ctx, mode == 2 && qn == 2 ? "k:k_traverse<EE>" : (mode == 1 && tn == 3 ? "k:k_traverse<FV>" : "k:k_traverse<other>"), s);
         const int flags = (check_shared ? 1 : 0) | (ctx->filter_on() ? 2 : 0);
         const FilterView filter { ctx->filter_patches ? ctx->dPatch.p : nullptr, ctx->filter_n_dynamic };
+        if (sap) {
+            enqueue_sap(counter, cap, flags, filter);
+            IPCB_CUDA(cudaMemcpyAsync(ctx->pinned.p + 16 + slot, counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            return;
+        }
 #define IPCB_TRAVERSE(M, QN, TN)                                                                                                         \
     if (flags & 2)                                                                                                                      \
         k_traverse<M, QN, TN, true><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes.p, t->n, t->sbox.p, t->sprim.p, \
@@ -755,6 +921,47 @@ struct TraverseJob {
         IPCB_CUDA(cudaGetLastError());
         IPCB_CUDA(cudaMemcpyAsync(ctx->pinned.p + 16 + slot, counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     }
+    // sweep: self kinds one pass; two sets: the queries scan the targets that start inside them, then the targets scan
+    // the queries that start strictly inside them (every overlapping pair is found exactly once)
+    void enqueue_sap(unsigned long long* counter, unsigned long long cap, int flags, const FilterView& filter)
+    {
+        Stage kt(ctx, "k:k_sap_sweep", s);
+        const int axis = ctx->sap_axis;
+#define IPCB_SAP(M, QN, TN, QB, QE, QT, TT, RULE)                                                                                       \
+    if (flags & 2)                                                                                                                      \
+        k_sap_sweep<M, QN, TN, true><<<grid_for((QE) - (QB), TRAV_BLOCK), TRAV_BLOCK, 0, s>>>(QB, QE, (QT)->sbox.p, (QT)->sprim.p, (TT)->n, (TT)->sbox.p, \
+                                                                                             (TT)->sprim.p, axis, RULE, out->pairs.p, counter, cap, flags, filter); \
+    else                                                                                                                                \
+        k_sap_sweep<M, QN, TN, false><<<grid_for((QE) - (QB), TRAV_BLOCK), TRAV_BLOCK, 0, s>>>(QB, QE, (QT)->sbox.p, (QT)->sprim.p, (TT)->n, (TT)->sbox.p, \
+                                                                                              (TT)->sprim.p, axis, RULE, out->pairs.p, counter, cap, flags, filter)
+        // second pass of a two-set kind: the rank's share of the TARGET set scans the query set
+        int tb = 0, te = t->n;
+        if (ctx->shard_world > 1 && (q_begin != 0 || q_end != q->n)) {
+            tb = int((int64_t(t->n) * ctx->shard_rank) / ctx->shard_world);
+            te = int((int64_t(t->n) * (ctx->shard_rank + 1)) / ctx->shard_world);
+        }
+        switch (mode * 100 + qn * 10 + tn) {
+        case 211: IPCB_SAP(2, 1, 1, q_begin, q_end, q, t, 0); break;
+        case 222: IPCB_SAP(2, 2, 2, q_begin, q_end, q, t, 0); break;
+        case 233: IPCB_SAP(2, 3, 3, q_begin, q_end, q, t, 0); break;
+        case 21: // edges x vertices, emitted (edge, vertex)
+            IPCB_SAP(0, 2, 1, q_begin, q_end, q, t, 1);
+            if (te > tb) { IPCB_SAP(1, 1, 2, tb, te, t, q, 2); }
+            break;
+        case 113: // vertices x faces, emitted (face, vertex)
+            IPCB_SAP(1, 1, 3, q_begin, q_end, q, t, 1);
+            if (te > tb) { IPCB_SAP(0, 3, 1, tb, te, t, q, 2); }
+            break;
+        case 132: // faces x edges, emitted (edge, face)
+            IPCB_SAP(1, 3, 2, q_begin, q_end, q, t, 1);
+            if (te > tb) { IPCB_SAP(0, 2, 3, tb, te, t, q, 2); }
+            break;
+        default: throw Error("broad phase: unsupported sweep");
+        }
+#undef IPCB_SAP
+        ctx->launches += 2;
+        IPCB_CUDA(cudaGetLastError());
+    }
     void finish()
     {
         if (!live) return;
@@ -765,18 +972,53 @@ struct TraverseJob {
                 out->count = int64_t(found);
                 return;
             }
-            out->pairs.reserve(size_t(found) + size_t(found) / 8); // overflow: grow and repeat the pass
+            if (found > max_pairs()) { // more pairs than one list may hold: the caller chunks the queries (or gives up)
+                overflow = found;
+                out->count = 0;
+                return;
+            }
+            out->pairs.reserve(std::min(size_t(found) + size_t(found) / 8, max_pairs())); // overflow: grow and repeat the pass
             enqueue();
         }
         throw Error("broad phase: candidate buffer overflow persisted");
     }
 };
 
-static void run_traverse(ipcb_ctx* ctx, const Tree& q, const Tree& t, int mode, int qn, int tn, bool check_shared, PairList& out, bool shard)
+static void too_many_pairs(unsigned long long found)
+{
+    throw Error("broad phase: " + std::to_string(found) + " candidate pairs of one kind exceed the list limit of " + std::to_string(max_pairs())
+                + " (IPCB_MAX_PAIRS); only compute_collision_free_stepsize streams larger sets");
+}
+static void run_traverse(ipcb_ctx* ctx, const Tree& q, const Tree& t, int mode, int qn, int tn, bool check_shared, PairList& out, bool shard,
+                         bool sap = false)
 {
     TraverseJob job { ctx, &q, &t, mode, qn, tn, check_shared, &out, ctx->stream, 0 };
+    job.sap = sap;
     job.launch(shard);
     job.finish();
+    if (job.overflow) too_many_pairs(job.overflow);
+}
+
+// chunked emission for the streaming step size: the queries [qb, qe) of the rank's range of one main kind (edge-edge or
+// face-vertex) of the BUILT trees into ctx->cand[kind].  Returns the pairs found; a value above max_pairs() means the
+// chunk was too large (the list is invalid).  range: out-parameter with the rank's whole query range when qb < 0.
+unsigned long long traverse_chunk(ipcb_ctx* ctx, int kind, int qb, int qe, int* range)
+{
+    const bool ee = kind == IPCB_EE;
+    // the chunks walk the LBVH (also when the full pass was a sweep: its two-pass scheme does not split into query chunks)
+    if (ee && !ctx->etree_ok) build_tree(ctx, ctx->eset, ctx->etree, true), ctx->etree_ok = true;
+    if (!ee && !ctx->ftree_ok) build_tree(ctx, ctx->fset, ctx->ftree, true), ctx->ftree_ok = true;
+    if (!ee && !ctx->vorder_valid) build_tree(ctx, ctx->vset, ctx->vtree, false), ctx->vorder_valid = true;
+    TraverseJob job { ctx, ee ? &ctx->etree : &ctx->vtree, ee ? &ctx->etree : &ctx->ftree, ee ? 2 : 1, ee ? 2 : 1, ee ? 2 : 3, true, &ctx->cand[kind],
+                      ctx->stream, 0 };
+    if (qb < 0) {
+        const bool any = job.full_range(true);
+        range[0] = any ? job.q_begin : 0, range[1] = any ? job.q_end : 0;
+        return 0;
+    }
+    job.launch_range(qb, qe);
+    job.finish();
+    return job.overflow ? job.overflow : (unsigned long long)ctx->cand[kind].count;
 }
 
 static Tree& ensure_tree(ipcb_ctx* ctx, int which)
@@ -798,6 +1040,14 @@ void broad_detect(ipcb_ctx* ctx, int kind, PairList& out)
 {
     if (!ctx->built) throw Error("broad phase not built");
     Stage st(ctx, "broad_detect");
+    if (ctx->broad_method == IPCB_BROAD_SAP) { // same six kinds, same orientation of the pairs, by sweeps
+        static const int spec[6][5] = { { 0, 0, 2, 1, 1 }, { 1, 0, 0, 2, 1 }, { 1, 1, 2, 2, 2 }, { 0, 2, 1, 1, 3 }, { 2, 1, 1, 3, 2 }, { 2, 2, 2, 3, 3 } };
+        if (kind < 0 || kind > 5) throw Error("bad candidate kind");
+        Tree& q = ensure_sap_view(ctx, spec[kind][0]);
+        Tree& t = ensure_sap_view(ctx, spec[kind][1]);
+        run_traverse(ctx, q, t, spec[kind][2], spec[kind][3], spec[kind][4], true, out, true, true);
+        return;
+    }
     switch (kind) {
     case IPCB_VV: {
         Tree& v = ensure_tree(ctx, 0);
@@ -868,16 +1118,33 @@ void sort_pairs(ipcb_ctx* ctx, PairList& pl)
 
 // Candidates::build, 3D (candidates.cpp:43-222): EE + FV on the whole mesh,
 // VV between codim vertices, EV between codim edges and codim vertices
-void candidates_build(ipcb_ctx* ctx, bool swept, double r)
+// allow_overflow: a main kind with more than max_pairs() candidates does not throw; the function returns true and leaves
+// that kind empty (the trees stay built: the streaming step size traverses them in chunks)
+bool candidates_build(ipcb_ctx* ctx, bool swept, double r, bool allow_overflow)
 {
+    bool overflowed = false;
     broad_build(ctx, swept, r);
     for (auto& c : ctx->cand) c.count = 0, c.sorted = false;
     {
         // The edge tree + edge-edge traversal and the face tree + face-vertex traversal are independent: they run on
         // two auxiliary streams (the small sort / hierarchy kernels of one chain fill the tails of the other); the
         // vertex queries only need the Morton order, not a hierarchy (main stream).
-        Stage st(ctx, "lbvh_build+traverse");
+        Stage st(ctx, ctx->broad_method == IPCB_BROAD_SAP ? "sap_sort+sweep" : "lbvh_build+traverse");
         const bool do_ee = ctx->nE >= 2, do_fv = ctx->nF && ctx->nV;
+        if (ctx->broad_method == IPCB_BROAD_SAP) {
+            TraverseJob ee { ctx, nullptr, nullptr, 2, 2, 2, true, &ctx->cand[IPCB_EE], ctx->stream, 0 };
+            TraverseJob fv { ctx, nullptr, nullptr, 1, 1, 3, true, &ctx->cand[IPCB_FV], ctx->stream, 1 };
+            ee.sap = fv.sap = true;
+            if (do_ee) ee.q = ee.t = &ensure_sap_view(ctx, 1), ee.launch(true);
+            if (do_fv) fv.q = &ensure_sap_view(ctx, 0), fv.t = &ensure_sap_view(ctx, 2), fv.launch(true);
+            ee.finish();
+            fv.finish();
+            ctx->cand_overflow[IPCB_EE] = ee.overflow, ctx->cand_overflow[IPCB_FV] = fv.overflow;
+            if (ee.overflow || fv.overflow) {
+                if (!allow_overflow) too_many_pairs(std::max(ee.overflow, fv.overflow));
+                overflowed = true;
+            }
+        } else {
         ctx->fork();
         TraverseJob ee { ctx, &ctx->etree, &ctx->etree, 2, 2, 2, true, &ctx->cand[IPCB_EE], ctx->aux[0], 0 };
         TraverseJob fv { ctx, &ctx->vtree, &ctx->ftree, 1, 1, 3, true, &ctx->cand[IPCB_FV], ctx->aux[1], 1 };
@@ -897,6 +1164,12 @@ void candidates_build(ipcb_ctx* ctx, bool swept, double r)
         fv.finish();
         ctx->join(0);
         ctx->join(1);
+        ctx->cand_overflow[IPCB_EE] = ee.overflow, ctx->cand_overflow[IPCB_FV] = fv.overflow;
+        if (ee.overflow || fv.overflow) {
+            if (!allow_overflow) too_many_pairs(std::max(ee.overflow, fv.overflow));
+            overflowed = true;
+        }
+        }
     }
     const int ncv = int(ctx->codimV.size()), nce = int(ctx->codimE.size());
     if (ncv) {
@@ -921,6 +1194,7 @@ void candidates_build(ipcb_ctx* ctx, bool swept, double r)
             if (ctx->shard_rank == 0) run_traverse(ctx, ctx->cetree, ctx->cvtree, 0, 2, 1, false, ctx->cand[IPCB_EV], false);
         }
     }
+    return overflowed;
 }
 
 } // namespace ipcb

@@ -533,6 +533,123 @@ __global__ void __launch_bounds__(256, 3)
     }
 }
 
+// ---------------------------------------------------------------------------
+// The same pre-filter in FP32 on positions re-centred at the scene centre and packed as ONE 32-byte sector per vertex
+// (t0 | t1).  The separating-direction test holds for ANY direction n (n.F is multilinear, its extrema over the window
+// are at the 8 corners), so only the projections have to be bounded: their FP32 error (input rounding + three products
+// and sums per dot product, a few units of 2^-24 |n|_1 max|coordinate|) is added to the margin — 64 * 2^-23 * extent,
+// orders of magnitude below the 1e-4 the margin already contains.  Half the gathered sectors, half the registers, the
+// FP32 pipes instead of the FP64 one; survivors (~0.1 %) go through the exact FP64 set-up as before, so the answers
+// do not change.
+struct f3 {
+    float x, y, z;
+};
+__device__ __forceinline__ f3 operator-(f3 a, f3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+__device__ __forceinline__ float dotf(f3 a, f3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ f3 crossf(f3 a, f3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+__global__ void k_pack_f32(int n, const double4* __restrict__ X0, const double4* __restrict__ X1, const float* __restrict__ scene,
+                           float4* __restrict__ XF)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double cx = 0.5 * (double(scene[0]) + double(scene[3])), cy = 0.5 * (double(scene[1]) + double(scene[4])),
+                 cz = 0.5 * (double(scene[2]) + double(scene[5]));
+    const double4 a = X0[i], b = X1[i];
+    XF[2 * size_t(i)] = make_float4(float(a.x - cx), float(a.y - cy), float(a.z - cz), 0.f);
+    XF[2 * size_t(i) + 1] = make_float4(float(b.x - cx), float(b.y - cy), float(b.z - cz), 0.f);
+}
+__device__ __forceinline__ bool ti_separated_f32(const f3* p0, const f3* e4, int is_vf, float tmax, float margin)
+{
+    f3 axes[4];
+    int na;
+    if (is_vf) {
+        const f3 n = crossf(p0[2] - p0[1], p0[3] - p0[1]);
+        axes[0] = n, axes[1] = crossf(p0[2] - p0[1], n), axes[2] = crossf(p0[3] - p0[2], n), axes[3] = crossf(p0[1] - p0[3], n);
+        na = 4;
+    } else {
+        const f3 ua = p0[1] - p0[0], ub = p0[3] - p0[2], n = crossf(ua, ub);
+        axes[0] = n, axes[1] = crossf(ua, n), axes[2] = crossf(ub, n);
+        na = 3;
+    }
+    for (int a = 0; a < na; a++) {
+        const f3 n = axes[a];
+        const float l1 = (fabsf(n.x) + fabsf(n.y) + fabsf(n.z)) * margin;
+        float mn = INFINITY, mx = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            float pr[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float d0 = dotf(n, p0[k]);
+                pr[k] = t == 0 ? d0 : (dotf(n, e4[k]) - d0) * tmax + d0;
+            }
+            float lo, hi;
+            if (is_vf) {
+                const float q = pr[2] + pr[3] - pr[1];
+                lo = pr[0] - fmaxf(fmaxf(pr[1], pr[2]), fmaxf(pr[3], q));
+                hi = pr[0] - fminf(fminf(pr[1], pr[2]), fminf(pr[3], q));
+            } else {
+                lo = fminf(pr[0], pr[1]) - fmaxf(pr[2], pr[3]);
+                hi = fmaxf(pr[0], pr[1]) - fminf(pr[2], pr[3]);
+            }
+            mn = fminf(mn, lo), mx = fmaxf(mx, hi);
+        }
+        if (mn > l1 || mx < -l1) return true;
+    }
+    return false;
+}
+__global__ void __launch_bounds__(256, 4)
+    k_ti_filter32(MultiSource ms, int stride, double min_distance, double tmax_in, double tolerance, const unsigned long long* __restrict__ bound,
+                  int* __restrict__ list, unsigned long long* nlist, const float* __restrict__ scene, const float4* __restrict__ XF)
+{
+    const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * stride;
+    bool keep = false;
+    if (g < ms.off[ms.nk]) {
+        int64_t i;
+        const QuerySource q = locate(ms, g, i);
+        keep = true;
+        if (q.kind >= IPCB_EE) {
+            const int2 c = q.cand[i];
+            int vid[4];
+            if (q.kind == IPCB_EE) {
+                const int2 ea = __ldg(q.E + c.x), eb = __ldg(q.E + c.y);
+                vid[0] = ea.x, vid[1] = ea.y, vid[2] = eb.x, vid[3] = eb.y;
+            } else {
+                const int4 f = __ldg(q.F + c.x);
+                vid[0] = c.y, vid[1] = f.x, vid[2] = f.y, vid[3] = f.z;
+            }
+            f3 a[4], b[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float4 u = __ldg(XF + 2 * size_t(vid[k])), v = __ldg(XF + 2 * size_t(vid[k]) + 1);
+                a[k] = { u.x, u.y, u.z }, b[k] = { v.x, v.y, v.z };
+            }
+            // margins: the FP64 filter's (floating-point filter of the root finder from the largest |coordinate| of the
+            // scene, min_distance, the 1e-4 cap, the tolerance) plus the FP32 projection error for the re-centred extent
+            double mxc = 1.0, ext = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const double lo = double(__ldg(scene + k)), hi = double(__ldg(scene + 3 + k));
+                mxc = fmax(mxc, fmax(fabs(lo), fabs(hi)));
+                ext = fmax(ext, 0.5 * (hi - lo));
+            }
+            const int is_vf = q.kind == IPCB_FV;
+            const double err = (is_vf ? 7.549516567451064e-15 : 7.105427357601002e-15) * mxc * mxc * mxc;
+            const double margin = (err + min_distance + 1e-4 + tolerance) * (1.0 + 1e-6) + 64.0 * 1.1920929e-7 * ext;
+            const double tmax = bound ? fmin(tmax_in, load_bound(bound)) : tmax_in;
+            keep = !ti_separated_f32(a, b, is_vf, __double2float_ru(tmax), __double2float_ru(margin));
+        }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+        const int lane = threadIdx.x & 31;
+        unsigned long long base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(nlist, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (keep) list[base + __popc(m & ((1u << lane) - 1))] = int(g);
+    }
+}
+
 // Query set-up shared by the per-thread and the per-warp search (tight_inclusion_ccd.cpp:222-336 and
 // ccd_strategy :33-75).  Returns false when the query is already answered (and reported).
 __device__ inline bool ti_setup(const QuerySource& q, int64_t i, double min_distance, double tmax_in, double tolerance, double rescale,
@@ -893,6 +1010,7 @@ struct TIWork {
     Buf<TIUnit> ua, ub;
     Buf<int> list; // candidates that survive the pre-filter
     Buf<int> hard; // queries deferred to the warp-cooperative search
+    Buf<float4> XF; // FP32 positions (t0 | t1 per vertex, re-centred) for the FP32 pre-filter
 };
 // the scratch belongs to its context (allocated on the context's device, freed by ipcb_ctx_destroy)
 void ti_work_free(TIWork* w) { delete w; }
@@ -974,6 +1092,16 @@ static void ti_run(ipcb_ctx* ctx, const MultiSource& ms, double min_distance, do
     size_t qcap = std::max<size_t>(W.queries.cap, 1024);
     size_t ucap = std::max<size_t>(W.ua.cap, size_t(1) << 16);
     W.list.reserve(total), W.hard.reserve(total);
+    // FP32 pre-filter: resident candidates of the face-vertex / edge-edge kinds with the scene box of THESE positions,
+    // no per-query outputs (a dropped query only needs reporting in the narrow-phase batch API); IPCB_TI_FILTER_F64: A/B
+    static const bool force_f64 = getenv("IPCB_TI_FILTER_F64") != nullptr;
+    bool use_f32 = scene != nullptr && !out.hit && !force_f64;
+    for (int k = 0; k < ms.nk; k++) use_f32 = use_f32 && ms.kind[k] >= IPCB_EE;
+    if (use_f32) {
+        W.XF.reserve(2 * size_t(ctx->nV));
+        k_pack_f32<<<grid_for(ctx->nV, 256), 256, 0, s>>>(ctx->nV, ctx->X0.p, ctx->X1.p, scene, W.XF.p);
+        ctx->launches++;
+    }
     // strided samples, coarse to fine (default: one sample of ~64K candidates, then everything else; IPCB_TI_GROWTH
     // inserts intermediate samples)
     int64_t sample = 65536;
@@ -1002,7 +1130,11 @@ static void ti_run(ipcb_ctx* ctx, const MultiSource& ms, double min_distance, do
             IPCB_CUDA(cudaMemsetAsync(nlist_d, 0, 4 * sizeof(unsigned long long), s)); // list lengths and work counters
             {
                 Stage kt(ctx, probe ? "k:k_ti_filter(sample)" : "k:k_ti_filter", s);
-                k_ti_filter<<<grid_for((total + st - 1) / st, 256), 256, 0, s>>>(ms, st, 0, min_distance, tmax, p.tolerance, out, W.list.p, nlist_d, scene);
+                if (use_f32)
+                    k_ti_filter32<<<grid_for((total + st - 1) / st, 256), 256, 0, s>>>(ms, st, min_distance, tmax, p.tolerance, out.bound, W.list.p, nlist_d,
+                                                                                     scene, W.XF.p);
+                else
+                    k_ti_filter<<<grid_for((total + st - 1) / st, 256), 256, 0, s>>>(ms, st, 0, min_distance, tmax, p.tolerance, out, W.list.p, nlist_d, scene);
             }
             {
                 Stage kt(ctx, probe ? "k:k_ti_query(sample)" : "k:k_ti_query", s);
@@ -1171,6 +1303,59 @@ double noncandidate_stepsize(ipcb_ctx* ctx, bool difference, double dhat)
     double m;
     memcpy(&m, &bits, sizeof m);
     return 0.5 * dhat / m;
+}
+
+// compute_collision_free_stepsize when a candidate list would exceed max_pairs() (SURVEY §7 hard part 7; BASELINE config
+// 4: 10^8 .. 10^9 swept candidates): the query leaves of the rank's range are traversed in CHUNKS, every chunk's pairs
+// go straight through the narrow phase and are dropped.  The earliest time of impact found so far prunes the later
+// chunks exactly like the shared bound prunes later queries, so most of them end in the pre-filter.  A chunk that
+// still overflows is halved; chunks grow again while their lists stay below a quarter of the limit.
+void ccd_stepsize_streaming(ipcb_ctx* ctx, double min_distance, const ipcb_ccd_params& p, double* d_out)
+{
+    Stage st(ctx, "ccd_streaming");
+    cudaStream_t s = ctx->stream;
+    unsigned long long* bound = ctx->dCounters.p + 8;
+    k_set_bits<<<1, 1, 0, s>>>(bound, 1.0);
+    ctx->launches++;
+    CcdOut out { bound, nullptr, nullptr };
+    auto narrow = [&](std::initializer_list<int> kinds) {
+        if (p.kind == IPCB_CCD_ADDITIVE) {
+            for (int kind : kinds) {
+                const QuerySource src = cand_source(ctx, kind);
+                if (src.n == 0) continue;
+                k_additive<<<grid_for(src.n, 128), 128, 0, s>>>(src, min_distance, 1.0, (long long)p.max_iterations, p.conservative_rescaling, out);
+                ctx->launches++;
+            }
+            IPCB_CUDA(cudaGetLastError());
+        } else {
+            ti_run(ctx, multi_source(ctx, kinds), min_distance, 1.0, p, out);
+        }
+    };
+    narrow({ IPCB_VV, IPCB_EV }); // the few codimensional candidates are resident
+    for (int kind : { IPCB_FV, IPCB_EE }) {
+        if (ctx->cand_overflow[kind] == 0) { // this kind fitted: its list is resident
+            narrow({ kind });
+            continue;
+        }
+        int range[2];
+        traverse_chunk(ctx, kind, -1, -1, range);
+        const double per_query = double(ctx->cand_overflow[kind]) / std::max(1, range[1] - range[0]);
+        int len = std::max(64, int(0.5 * double(max_pairs()) / std::max(per_query, 1e-9)));
+        for (int q = range[0]; q < range[1];) {
+            const int qe = int(std::min<int64_t>(range[1], int64_t(q) + len));
+            const unsigned long long found = traverse_chunk(ctx, kind, q, qe, nullptr);
+            if (found > max_pairs()) {
+                if (qe - q <= 1) throw Error("ccd: one query leaf has more candidates than IPCB_MAX_PAIRS allows");
+                len = std::max(1, int(0.8 * double(qe - q) * double(max_pairs()) / double(found)));
+                continue;
+            }
+            narrow({ kind });
+            q = qe;
+            if (found < max_pairs() / 4) len = int(std::min<int64_t>(int64_t(len) * 2, 1 << 30));
+        }
+        ctx->cand[kind].count = 0; // the last chunk is not the kind's candidate set
+    }
+    IPCB_CUDA(cudaMemcpyAsync(d_out, bound, sizeof(double), cudaMemcpyDeviceToDevice, s));
 }
 
 void ccd_narrow_phase(ipcb_ctx* ctx, int kind, int64_t n, const double* h_t0, const double* h_t1, double min_distance, double tmax,

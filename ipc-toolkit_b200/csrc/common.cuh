@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
+#include <utility>
 #include <string>
 #include <vector>
 #include "../../include/ipcb200.h"
@@ -35,6 +36,11 @@ template <typename T> struct Buf {
     Buf() = default;
     Buf(const Buf&) = delete;
     Buf& operator=(const Buf&) = delete;
+    void swap(Buf& o)
+    {
+        std::swap(p, o.p);
+        std::swap(cap, o.cap);
+    }
     void release()
     {
         if (p) cudaFree(p);

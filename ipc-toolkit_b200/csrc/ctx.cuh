@@ -72,8 +72,26 @@ struct CollisionSet {
     int64_t count = 0;
     bool sorted = true;    // false after a disjoint merge concatenated the builders' records (collisions_sort restores it)
     int64_t raw_count = 0; // records appended through collisions_append since the last collisions_clear
+    // exchange the FINAL records (what a NormalCollisions object is) with another set; the build scratch stays
+    void swap_records(CollisionSet& o)
+    {
+        ids.swap(o.ids), w.swap(o.w), eps.swap(o.eps), dtype.swap(o.dtype);
+        std::swap(count, o.count);
+        std::swap(sorted, o.sorted);
+    }
 };
 
+} // namespace ipcb
+// A NormalCollisions object that is NOT the resident set of its context: the reference lets any number of collision sets
+// exist per mesh (normal_collisions.hpp: plain containers); here a set is resident while the potential works on it and
+// can be parked in / revived from one of these with ipcb_collisions_swap (O(1): buffers are exchanged, not copied).
+struct ipcb_collision_set {
+    int device = 0;
+    ipcb::CollisionSet coll[4];
+    double dmin = 0;
+    bool valid = false;
+};
+namespace ipcb {
 struct TIWork; // Tight-Inclusion scratch (ccd.cu), owned by the context
 void ti_work_free(TIWork* w);
 
@@ -136,12 +154,18 @@ struct ipcb_ctx {
     ipcb::Tree vtree, etree, ftree, cvtree, cetree;
     bool vtree_ok = false, etree_ok = false, ftree_ok = false;
     bool vorder_valid = false; // vtree.ord_sorted holds a permutation of all vertices (Morton order of the last build)
+    // sweep and prune (IPCB_BROAD_SAP): axis-sorted views of the three primitive sets
+    int broad_method = 0;
+    int sap_axis = 0;
+    bool sap_axis_ok = false, sap_ok[3] = { false, false, false };
+    ipcb::Tree sap_v, sap_e, sap_f;
     ipcb::Buf<float> scene; // 6 floats: min xyz, max xyz
     bool scene_covers_positions = false; // the scene box was reduced from the CURRENT X0 / X1 (swept build of this call)
     ipcb::PairList detected[6];
 
     // ---- candidates / collisions
     ipcb::PairList cand[4];
+    unsigned long long cand_overflow[4] = { 0, 0, 0, 0 }; // pairs a kind would have had when it exceeded max_pairs()
     ipcb::CollisionSet coll[4];
     double dmin = 0;
     bool coll_valid = false;
@@ -228,7 +252,9 @@ void convert_positions(ipcb_ctx* ctx, const double* dV, int ld, Buf<double4>& X)
 // broad phase (broad.cu)
 void broad_build(ipcb_ctx* ctx, bool swept, double inflation_radius);
 void broad_detect(ipcb_ctx* ctx, int kind, PairList& out);
-void candidates_build(ipcb_ctx* ctx, bool swept, double inflation_radius);
+bool candidates_build(ipcb_ctx* ctx, bool swept, double inflation_radius, bool allow_overflow = false);
+size_t max_pairs();
+unsigned long long traverse_chunk(ipcb_ctx* ctx, int kind, int qb, int qe, int* range);
 void sort_pairs(ipcb_ctx* ctx, PairList& pl);
 
 // collisions (collisions.cu)
@@ -250,6 +276,7 @@ void hessian_balanced_row_blocks(ipcb_ctx* ctx, int world, int32_t* bounds);
 
 // ccd (ccd.cu)
 void ccd_stepsize(ipcb_ctx* ctx, double min_distance, const ipcb_ccd_params& p, double* d_out);
+void ccd_stepsize_streaming(ipcb_ctx* ctx, double min_distance, const ipcb_ccd_params& p, double* d_out);
 double noncandidate_stepsize(ipcb_ctx* ctx, bool difference, double dhat);
 void ccd_narrow_phase(ipcb_ctx* ctx, int kind, int64_t n, const double* h_t0, const double* h_t1, double min_distance, double tmax,
                       const ipcb_ccd_params& p, uint8_t* h_hit, double* h_toi);

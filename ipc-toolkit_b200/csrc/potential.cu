@@ -512,7 +512,9 @@ __global__ void __launch_bounds__(128)
                 mask |= unsigned(v != 0.0) << k; // exact zeros are not entries (local_to_global.hpp:290-291)
             }
             masks[bj * 4 + bi] = (unsigned short)mask;
-            masks[bi * 4 + bj] = (unsigned short)mask_transpose(mask);
+            // a diagonal block keeps its OWN mask: its exact-zero pattern need not be symmetric at rounding level, and
+            // the numeric pass decides from the values it reads — mask and values must describe the same block
+            if (bi != bj) masks[bi * 4 + bj] = (unsigned short)mask_transpose(mask);
         }
     for (int k = 0; k < HSLOTS; k++) out.mask[gi * HSLOTS + k] = masks[k];
 }

@@ -1177,6 +1177,23 @@ int ipco_collisions_merge(ipcb_ctx* ctx, double dmin, int32_t /* flags: a hint, 
     coll_counts(ctx, counts);
     return 0;
 }
+struct ipcb_collision_set {
+    std::vector<Coll> coll[4];
+    double dmin = 0;
+};
+int ipco_collision_set_create(ipcb_ctx*, ipcb_collision_set** out)
+{
+    *out = new ipcb_collision_set();
+    return 0;
+}
+void ipco_collision_set_destroy(ipcb_collision_set* set) { delete set; }
+int ipco_collisions_swap(ipcb_ctx* ctx, ipcb_collision_set* set, int64_t counts[4])
+{
+    for (int k = 0; k < 4; k++) ctx->coll[k].swap(set->coll[k]);
+    std::swap(ctx->dmin, set->dmin);
+    coll_counts(ctx, counts);
+    return 0;
+}
 int ipco_ctx_set_collision_range(ipcb_ctx* ctx, int32_t rank, int32_t world)
 {
     if (world < 1 || rank < 0 || rank >= world) return fail("bad collision range");

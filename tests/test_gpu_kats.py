@@ -153,3 +153,8 @@ def test_golden_scene_oracle(oracle, name):
 @pytest.mark.parametrize("name", SCENES)
 def test_golden_scene_gpu(cuda, oracle, name):
     check_golden_scene(cuda, name, oracle)
+
+
+@pytest.mark.gpu
+def test_independent_collision_sets_gpu(cuda, scenes):
+    ref.check_independent_collision_sets(cuda, scenes)

@@ -466,3 +466,30 @@ def test_edge_edge_orientation_is_never_lost(cuda, oracle, scenes):
         out[key] = (e, got.ids.copy(), got.dtype.copy())
     assert np.array_equal(out["cuda"][1], out["oracle"][1]) and np.array_equal(out["cuda"][2], out["oracle"][2])
     assert abs(out["cuda"][0] - out["oracle"][0]) <= RTOL * abs(out["oracle"][0])
+
+
+@pytest.mark.parametrize("limit", [4000, 1500])
+def test_streaming_step_size_when_the_candidate_list_is_capped(cuda, oracle, scenes, limit, monkeypatch):
+    """SURVEY §7 hard part 7 / BASELINE config 4: more swept candidates than one list may hold (IPCB_MAX_PAIRS, here tiny)
+    -> compute_collision_free_stepsize traverses the query leaves in chunks and pushes every chunk through the narrow
+    phase; static candidate / collision builds beyond the limit fail loudly"""
+    V0, V1, E, F, P = _scene(scenes, "sheets")
+    ref = {}
+    for ccd in ("ti", "accd"):
+        mesh = cuda.CollisionMesh(V0, E, F)
+        ref[ccd] = cuda.compute_collision_free_stepsize(mesh, V0, V1, narrow_phase_ccd=cuda.AdditiveCCD() if ccd == "accd" else None)
+    mesh = cuda.CollisionMesh(V0, E, F)
+    cand = cuda.Candidates()
+    cand.build(mesh, V0, V1, 0.0)
+    assert len(cand.ee_candidates) > 4 * 4000  # the limits below really force chunks
+    monkeypatch.setenv("IPCB_MAX_PAIRS", str(limit))
+    mesh = cuda.CollisionMesh(V0, E, F)
+    ac = cuda.compute_collision_free_stepsize(mesh, V0, V1, narrow_phase_ccd=cuda.AdditiveCCD())
+    assert abs(ac - ref["accd"]) <= 1e-12 * ref["accd"]  # same arithmetic per candidate, minimum over the same set
+    ti = cuda.compute_collision_free_stepsize(mesh, V0, V1)
+    tol = StepTolerance(oracle, V0, V1, E, F).tolerance(min(ti, ref["ti"]))[0]
+    assert abs(ti - ref["ti"]) <= tol
+    with pytest.raises(RuntimeError, match="IPCB_MAX_PAIRS"):
+        cuda.Candidates().build(mesh, V0, V1, 0.0)
+    monkeypatch.delenv("IPCB_MAX_PAIRS")
+    assert cuda.compute_collision_free_stepsize(mesh, V0, V1, narrow_phase_ccd=cuda.AdditiveCCD()) == pytest.approx(ref["accd"], rel=1e-12)

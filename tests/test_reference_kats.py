@@ -497,3 +497,37 @@ def check_improved_max_approx_derivatives(oracle, scenes):
         assert np.linalg.norm(fd_g - H @ p.ravel()) <= 1e-5 * np.linalg.norm(fd_g)
         Hp = B.hessian(c, mesh, V0, oracle.PSDProjectionMethod.CLAMP).toarray()
         assert np.linalg.eigvalsh(0.5 * (Hp + Hp.T)).min() >= -1e-9 * np.abs(Hp).max()
+
+
+def check_independent_collision_sets(api, scenes):
+    """the reference's NormalCollisions are plain containers: any number of them may exist per mesh (a lagged set for
+    friction, the sets of a line search).  Here each object owns a collision-set object of the library and is swapped in
+    when it is used (ipcb_collisions_swap)."""
+    V0, V1, E, F, P = scenes.cloth_stack(3, 10)
+    dhat = P["dhat"]
+    mesh = api.CollisionMesh(V0, E, F)
+    B = api.BarrierPotential(dhat, 1.0)
+    a = api.NormalCollisions()
+    a.build(mesh, V0, dhat)
+    ea, ga, ids_a = B(a, mesh, V0), B.gradient(a, mesh, V0), a.ee_collisions.ids.copy()
+    X = V0 + 0.3 * (V1 - V0)
+    b = api.NormalCollisions()
+    b.build(mesh, X, dhat)  # a second set on the same mesh: `a` stays valid
+    eb = B(b, mesh, X)
+    assert b.counts() != a.counts() or not np.array_equal(b.ee_collisions.ids, ids_a)
+    close = lambda x, y: abs(x - y) <= 1e-13 * abs(y)  # the oracle's parallel reduction order is not fixed
+    assert close(B(a, mesh, V0), ea) and np.allclose(B.gradient(a, mesh, V0), ga, rtol=1e-12, atol=0)  # `a` swapped back in
+    assert np.array_equal(a.ee_collisions.ids, ids_a)
+    assert close(B(b, mesh, X), eb)  # and `b` again
+    Ha, Hb = B.hessian(a, mesh, V0), B.hessian(b, mesh, X)
+    assert Ha.nnz > 0 and Hb.nnz > 0 and (Ha.nnz != Hb.nnz or abs(Ha - Hb).max() > 0)
+    a.build(mesh, X, dhat)  # rebuilding one set leaves the other alone
+    assert a.counts() == b.counts() and close(B(a, mesh, X), eb) and close(B(b, mesh, X), eb)
+    with pytest.raises(RuntimeError):
+        B(api.NormalCollisions(), mesh, V0)  # never built
+
+
+def test_independent_collision_sets_oracle(oracle):
+    import ipctk_b200
+
+    check_independent_collision_sets(oracle, ipctk_b200._pkg.scenes)
