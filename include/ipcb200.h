@@ -218,6 +218,26 @@ int IPCB_FN(barrier_hessian)(ipcb_ctx* ctx, const double* V, int32_t ld, const i
 int IPCB_FN(barrier_hessian_fetch)(ipcb_ctx* ctx, int32_t* outer /* 3nV+1 */, int32_t* inner /* nnz */,
                                    double* values /* nnz */);
 
+/* ---- Friction ----------------------------------------- */
+/* TangentialCollisions::build(mesh, vertices, collisions, normal_potential, mu_s, mu_k)
+ * (collisions/tangential/tangential_collisions.cpp:62-171) from the RESIDENT normal collision set: per collision the
+ * lagged closest point, tangent basis (tangent/*.cpp), normal force magnitude N = -kappa b'(d^2) 2 d
+ * (barrier/barrier_force_magnitude.cpp:7-15) and the blended coefficients (default_blend_mu: the average).  Edge-edge
+ * collisions that are close to parallel (cross^2 < eps_x) are skipped like in the reference.  mu_s / mu_k: per vertex.
+ * Isotropic coefficients only (the anisotropic "matchstick" lagging and the force Jacobians are outside this path). */
+int IPCB_FN(tangential_build)(ipcb_ctx* ctx, const double* V, int32_t ld, const ipcb_barrier_params* normal_potential, const double* mu_s,
+                              const double* mu_k, int64_t counts[4]);
+/* ids count x 2 like collisions_fetch; closest_point count x 2, tangent_basis count x 6 (column 0 then column 1), row-major;
+ * records keep the order of the normal collisions; any pointer may be NULL */
+int IPCB_FN(tangential_fetch)(ipcb_ctx* ctx, int32_t kind, int32_t* ids, double* weight, double* normal_force, double* mu_s, double* mu_k,
+                              double* closest_point, double* tangent_basis);
+/* FrictionPotential(eps_v) operator() / gradient / hessian over the resident tangential set (potentials/potential.cpp:36-222
+ * with potentials/tangential_potential.cpp:162-325); `velocities` is the potential's argument (nV x 3, column-major).
+ * The Hessian lands in the same resident CSR as the barrier Hessian (barrier_hessian_fetch / _dev_ptrs). */
+int IPCB_FN(friction_energy)(ipcb_ctx* ctx, const double* velocities, int32_t ld, double eps_v, double* energy);
+int IPCB_FN(friction_gradient)(ipcb_ctx* ctx, const double* velocities, int32_t ld, double eps_v, double* grad /* 3*nV */);
+int IPCB_FN(friction_hessian)(ipcb_ctx* ctx, const double* velocities, int32_t ld, double eps_v, int32_t psd_mode, int64_t* nnz);
+
 /* ---- CCD (ipc.cpp:45-101, candidates.cpp:252-292) ----------------------- */
 /* compute_collision_free_stepsize(mesh,V0,V1,min_distance,bp,ccd):
  * candidates_build_swept with r = 0.5*min_distance, then the earliest time of

@@ -598,6 +598,97 @@ def make_api(lib):
                                                 inner.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p)))
             return sp.csc_matrix((vals, inner, outer), shape=(n, n))
 
+    class TangentialCollisions:
+        """ipc::TangentialCollisions — collisions/tangential/tangential_collisions.cpp:62-171 (isotropic coefficients).
+        One resident tangential set per mesh (the lagged set of a friction solve)."""
+
+        def __init__(self):
+            self.mesh = None
+            self._counts = [0, 0, 0, 0]
+            self._host = {}
+
+        def build(self, mesh, vertices, collisions, normal_potential, mu_s, mu_k=None):
+            """mu_s / mu_k: a scalar or one value per vertex (mu_k defaults to mu_s, like the single-mu overload)"""
+            collisions._live()
+            nV = mesh.num_vertices()
+            ms = np.ascontiguousarray(np.broadcast_to(np.asarray(mu_s, np.float64), (nV,)))
+            mk = ms if mu_k is None else np.ascontiguousarray(np.broadcast_to(np.asarray(mu_k, np.float64), (nV,)))
+            v, p, ld = _f64(vertices)
+            bp = normal_potential._bp()
+            counts = (C.c_int64 * 4)()
+            lib.check(lib.tangential_build(mesh._ctx, p, ld, C.byref(bp), ms.ctypes.data_as(C.c_void_p), mk.ctypes.data_as(C.c_void_p), counts))
+            self.mesh, self._counts, self._host = mesh, list(counts), {}
+            mesh._tang_gen = getattr(mesh, "_tang_gen", 0) + 1
+            self._gen = mesh._tang_gen
+
+        def _live(self):
+            if self.mesh is None or self._gen != self.mesh._tang_gen:
+                raise RuntimeError("stale TangentialCollisions handle: a newer tangential set was built on this mesh")
+
+        def _get(self, kind):
+            self._live()
+            if kind not in self._host:
+                n = self._counts[kind]
+                r = types.SimpleNamespace(ids=np.zeros((n, 2), np.int32), weight=np.zeros(n), normal_force_magnitude=np.zeros(n), mu_s=np.zeros(n),
+                                          mu_k=np.zeros(n), closest_point=np.zeros((n, 2)), tangent_basis=np.zeros((n, 2, 3)))
+                if n:
+                    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+                    lib.check(lib.tangential_fetch(self.mesh._ctx, kind, ptr(r.ids), ptr(r.weight), ptr(r.normal_force_magnitude), ptr(r.mu_s),
+                                                   ptr(r.mu_k), ptr(r.closest_point), ptr(r.tangent_basis)))
+                self._host[kind] = r
+            return self._host[kind]
+
+        vv_collisions = property(lambda self: self._get(VV))
+        ev_collisions = property(lambda self: self._get(EV))
+        ee_collisions = property(lambda self: self._get(EE))
+        fv_collisions = property(lambda self: self._get(FV))
+
+        def counts(self):
+            return list(self._counts)
+
+        def size(self):
+            return int(sum(self._counts))
+
+        __len__ = size
+
+        def empty(self):
+            return self.size() == 0
+
+    class FrictionPotential:
+        """ipc::FrictionPotential(eps_v) — potentials/friction_potential.hpp, tangential_potential.cpp:162-325"""
+
+        def __init__(self, eps_v):
+            if not eps_v > 0:
+                raise ValueError("eps_v must be positive")
+            self.eps_v = float(eps_v)
+
+        def __call__(self, collisions, mesh, velocities):
+            collisions._live()
+            x, p, ld = _f64(velocities)
+            e = C.c_double()
+            lib.check(lib.friction_energy(mesh._ctx, p, ld, self.eps_v, C.byref(e)))
+            return e.value
+
+        def gradient(self, collisions, mesh, velocities):
+            collisions._live()
+            x, p, ld = _f64(velocities)
+            g = np.zeros(3 * mesh.num_vertices())
+            lib.check(lib.friction_gradient(mesh._ctx, p, ld, self.eps_v, g.ctypes.data_as(C.c_void_p)))
+            return g
+
+        def hessian(self, collisions, mesh, velocities, project_hessian_to_psd=PSDProjectionMethod.NONE):
+            import scipy.sparse as sp
+
+            collisions._live()
+            x, p, ld = _f64(velocities)
+            nnz = C.c_int64()
+            lib.check(lib.friction_hessian(mesh._ctx, p, ld, self.eps_v, int(project_hessian_to_psd), C.byref(nnz)))
+            n = 3 * mesh.num_vertices()
+            outer, inner, vals = np.zeros(n + 1, np.int32), np.zeros(nnz.value, np.int32), np.zeros(nnz.value)
+            lib.check(lib.barrier_hessian_fetch(mesh._ctx, outer.ctypes.data_as(C.c_void_p), inner.ctypes.data_as(C.c_void_p),
+                                                vals.ctypes.data_as(C.c_void_p)))
+            return sp.csc_matrix((vals, inner, outer), shape=(n, n))
+
     def compute_collision_free_stepsize(mesh, vertices_t0, vertices_t1, min_distance=0.0, broad_phase=None,
                                         narrow_phase_ccd=None):
         """ipc::compute_collision_free_stepsize — ipc.cpp:45-101"""
@@ -636,6 +727,8 @@ def make_api(lib):
     ns.Candidates = Candidates
     ns.NormalCollisions = NormalCollisions
     ns.BarrierPotential = BarrierPotential
+    ns.TangentialCollisions = TangentialCollisions
+    ns.FrictionPotential = FrictionPotential
     ns.compute_collision_free_stepsize = compute_collision_free_stepsize
     ns.is_step_collision_free = is_step_collision_free
     ns.narrow_phase_ccd = narrow_phase_ccd

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libipcb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["api.cu", "broad.cu", "collisions.cu", "potential.cu", "ccd.cu"]
+SOURCES = ["api.cu", "broad.cu", "collisions.cu", "potential.cu", "friction.cu", "ccd.cu"]
 # -fmad=false everywhere: decisions taken in floating point (boxes, distance types, the dhat filter, CCD) must round
 # exactly like the CPU oracle, and in potential.cu an implicit contraction a * b - c * d -> fma(a, b, -(c * d)) would turn
 # the EXACT zeros of symmetric / axis-aligned configurations into rounding residue — entries the reference's sparse
@@ -55,7 +55,7 @@ def build(force=False, verbose=False):
             raise RuntimeError("nvcc failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
         return r.stderr
 
-    with ThreadPoolExecutor(max_workers=5) as ex:
+    with ThreadPoolExecutor(max_workers=6) as ex:
         logs = list(ex.map(run, jobs))
     if verbose:
         for l in logs:

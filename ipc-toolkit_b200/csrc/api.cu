@@ -366,6 +366,7 @@ int ipcb_mesh_set(ipcb_ctx* ctx, int32_t nV, const double* rest, int32_t ld_rest
         ctx->filter_patches = false, ctx->filter_n_dynamic = -1; // a new mesh accepts all pairs
         ctx->built = false;
         ctx->coll_valid = false;
+        ctx->tang_valid = false;
         ctx->adj_ready = false;
         for (auto& c : ctx->cand) c.count = 0;
         for (auto& c : ctx->coll) c.count = 0;
@@ -842,6 +843,80 @@ int ipcb_barrier_hessian_fetch(ipcb_ctx* ctx, int32_t* outer, int32_t* inner, do
             IPCB_CUDA(cudaMemcpyAsync(values, ctx->vals.p, sizeof(double) * ctx->nnz, cudaMemcpyDeviceToHost, s));
         }
         IPCB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+// ---- Friction
+int ipcb_tangential_build(ipcb_ctx* ctx, const double* V, int32_t ld, const ipcb_barrier_params* normal_potential, const double* mu_s,
+                          const double* mu_k, int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        require_collisions(ctx);
+        if (!mu_s || !mu_k) throw Error("tangential_build: mu_s and mu_k are per-vertex arrays");
+        stage_positions(ctx, V, ld, false);
+        const size_t n = std::max<size_t>(size_t(ctx->nV), 1);
+        ctx->dMuS.reserve(n), ctx->dMuK.reserve(n);
+        IPCB_CUDA(cudaMemcpyAsync(ctx->dMuS.p, mu_s, sizeof(double) * ctx->nV, cudaMemcpyHostToDevice, ctx->stream));
+        IPCB_CUDA(cudaMemcpyAsync(ctx->dMuK.p, mu_k, sizeof(double) * ctx->nV, cudaMemcpyHostToDevice, ctx->stream));
+        tangential_build(ctx, *normal_potential, ctx->dMuS.p, ctx->dMuK.p);
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < 4; k++) counts[k] = ctx->tang[k].count;
+    });
+}
+int ipcb_tangential_fetch(ipcb_ctx* ctx, int32_t kind, int32_t* ids, double* weight, double* normal_force, double* mu_s, double* mu_k,
+                          double* closest_point, double* tangent_basis)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (kind < 0 || kind > 3) throw Error("bad collision kind");
+        if (!ctx->tang_valid) throw Error("no tangential collision set has been built on this context");
+        const TangSet& t = ctx->tang[kind];
+        const size_t n = size_t(t.count);
+        if (n == 0) return;
+        cudaStream_t s = ctx->stream;
+        auto get = [&](void* dst, const void* src, size_t bytes) {
+            if (dst) IPCB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s));
+        };
+        get(ids, t.ids.p, sizeof(int2) * n), get(weight, t.w.p, 8 * n), get(normal_force, t.N.p, 8 * n), get(mu_s, t.mus.p, 8 * n);
+        get(mu_k, t.muk.p, 8 * n), get(closest_point, t.beta.p, 16 * n), get(tangent_basis, t.P.p, 48 * n);
+        IPCB_CUDA(cudaStreamSynchronize(s));
+    });
+}
+int ipcb_friction_energy(ipcb_ctx* ctx, const double* velocities, int32_t ld, double eps_v, double* energy)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (!(eps_v > 0)) throw Error("eps_v must be positive");
+        stage_positions(ctx, velocities, ld, false);
+        double* d_out = reinterpret_cast<double*>(ctx->dCounters.p + 12);
+        friction_energy(ctx, eps_v, d_out);
+        IPCB_CUDA(cudaMemcpyAsync(energy, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int ipcb_friction_gradient(ipcb_ctx* ctx, const double* velocities, int32_t ld, double eps_v, double* grad)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (!(eps_v > 0)) throw Error("eps_v must be positive");
+        stage_positions(ctx, velocities, ld, false);
+        ctx->dGrad.reserve(3 * size_t(ctx->nV) + 1);
+        friction_gradient(ctx, eps_v, ctx->dGrad.p);
+        IPCB_CUDA(cudaMemcpyAsync(grad, ctx->dGrad.p, sizeof(double) * 3 * size_t(ctx->nV), cudaMemcpyDeviceToHost, ctx->stream));
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int ipcb_friction_hessian(ipcb_ctx* ctx, const double* velocities, int32_t ld, double eps_v, int32_t psd_mode, int64_t* nnz)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (!(eps_v > 0)) throw Error("eps_v must be positive");
+        if (psd_mode < 0 || psd_mode > 2) throw Error("Invalid type of PSD projection!");
+        stage_positions(ctx, velocities, ld, false);
+        friction_hessian(ctx, eps_v, psd_mode);
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *nnz = ctx->nnz;
     });
 }
 

@@ -81,6 +81,15 @@ struct CollisionSet {
     }
 };
 
+// the lagged tangential collisions of one kind (collisions/tangential/tangential_collision.hpp), struct of arrays
+struct TangSet {
+    Buf<int2> ids;
+    Buf<double> w, N, mus, muk; // weight, normal force magnitude, blended static / kinetic coefficients
+    Buf<double2> beta;          // closest point
+    Buf<double> P;              // tangent basis: 6 per record (column 0, column 1)
+    int64_t count = 0;
+};
+
 } // namespace ipcb
 // A NormalCollisions object that is NOT the resident set of its context: the reference lets any number of collision sets
 // exist per mesh (normal_collisions.hpp: plain containers); here a set is resident while the potential works on it and
@@ -203,6 +212,11 @@ struct ipcb_ctx {
     int64_t nnz = 0;
     ipcb::Buf<char> cubtmp;
 
+    // ---- friction
+    ipcb::TangSet tang[4], tang_tmp;
+    bool tang_valid = false;
+    ipcb::Buf<double> dMuS, dMuK; // per-vertex coefficients of the last tangential build
+
     // ---- ccd
     ipcb::TIWork* ti_work = nullptr;
 
@@ -273,6 +287,12 @@ void barrier_energy(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_out)
 void barrier_gradient(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_grad);
 void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode);
 void hessian_balanced_row_blocks(ipcb_ctx* ctx, int world, int32_t* bounds);
+
+// friction (friction.cu)
+void tangential_build(ipcb_ctx* ctx, const ipcb_barrier_params& bp, const double* d_mu_s, const double* d_mu_k);
+void friction_energy(ipcb_ctx* ctx, double eps_v, double* d_out);
+void friction_gradient(ipcb_ctx* ctx, double eps_v, double* d_grad);
+void friction_hessian(ipcb_ctx* ctx, double eps_v, int psd_mode);
 
 // ccd (ccd.cu)
 void ccd_stepsize(ipcb_ctx* ctx, double min_distance, const ipcb_ccd_params& p, double* d_out);

@@ -23,8 +23,7 @@
 //    plumbing), run-length summed, and expanded to compressed columns with the
 //    reference's exact pattern: an entry exists iff some local matrix had an
 //    exactly non-zero value there (duplicates summed, never pruned).
-#include "ctx.cuh"
-#include "geom.cuh"
+#include "hessian_assembly.cuh"
 #include "hessian_fast.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -33,68 +32,6 @@
 #include <memory>
 
 namespace ipcb {
-
-struct BarrierDev {
-    double xhat;  // (2 dmin + dhat) dhat
-    double dmin2; // dmin^2
-    double kappa;
-    double scale; // physical barrier factor dhat / xhat^2, else 1
-    int physical;
-    __device__ double f(double d2) const { return kappa * (physical ? barrier_f(d2 - dmin2, xhat) * scale : barrier_f(d2 - dmin2, xhat)); }
-    __device__ double df(double d2) const { return kappa * (physical ? barrier_df(d2 - dmin2, xhat) * scale : barrier_df(d2 - dmin2, xhat)); }
-    __device__ double ddf(double d2) const { return kappa * (physical ? barrier_ddf(d2 - dmin2, xhat) * scale : barrier_ddf(d2 - dmin2, xhat)); }
-};
-static BarrierDev make_barrier(const ipcb_barrier_params& bp, double dmin)
-{
-    BarrierDev b;
-    b.xhat = (2 * dmin + bp.dhat) * bp.dhat;
-    b.dmin2 = dmin * dmin;
-    b.kappa = bp.stiffness;
-    b.physical = bp.use_physical_barrier != 0;
-    b.scale = b.physical ? bp.dhat / (b.xhat * b.xhat) : 1.0;
-    return b;
-}
-
-struct CollView {
-    int kind;
-    int64_t n;
-    const int2* ids;
-    const double* w;
-    const double* eps;
-    const unsigned char* dt;
-};
-struct MeshView {
-    const int2* E;
-    const int4* F;
-    const double4* X;
-};
-
-__device__ inline d3 ldx(const double4* X, int i) { return load_vertex(X, i); }
-// stencil vertex ids + positions (candidates/*.cpp vertex_ids): VV [v0,v1]; EV [v,e0,e1];
-// EE [ea0,ea1,eb0,eb1]; FV [v,f0,f1,f2]
-__device__ inline int load_stencil(int kind, int2 id, const MeshView& m, int* vid, d3* x)
-{
-    int n;
-    if (kind == IPCB_VV) {
-        vid[0] = id.x, vid[1] = id.y, n = 2;
-    } else if (kind == IPCB_EV) {
-        const int2 e = __ldg(m.E + id.x);
-        vid[0] = id.y, vid[1] = e.x, vid[2] = e.y, n = 3;
-    } else if (kind == IPCB_EE) {
-        const int2 ea = __ldg(m.E + id.x), eb = __ldg(m.E + id.y);
-        vid[0] = ea.x, vid[1] = ea.y, vid[2] = eb.x, vid[3] = eb.y, n = 4;
-    } else {
-        const int4 f = __ldg(m.F + id.x);
-        vid[0] = id.y, vid[1] = f.x, vid[2] = f.y, vid[3] = f.z, n = 4;
-    }
-    for (int k = 0; k < n; k++) x[k] = ldx(m.X, vid[k]);
-    return n;
-}
-__device__ inline Sub collision_sub(int kind, int dt)
-{
-    // known distance types: collisions/normal/{edge_vertex,face_vertex}.hpp:28-32, edge_edge.hpp:96
-    return kind == IPCB_VV ? Sub { 0, 0, 1, 0, 0 } : kind == IPCB_EV ? sub_point_edge(PE_E) : kind == IPCB_EE ? sub_edge_edge(dt) : sub_point_triangle(PT_T);
-}
 
 // ---------------------------------------------------------------------------
 // energy (potential.cpp:36-56, normal_potential.cpp:127-135)
@@ -134,24 +71,6 @@ __global__ void k_sum_partials(int n, const double* __restrict__ partial, double
     }
     if (threadIdx.x == 0) *out = sm[0];
 }
-
-static CollView view(const ipcb_ctx* ctx, int k)
-{
-    const CollisionSet& cs = ctx->coll[k];
-    return { k, cs.count, cs.ids.p, cs.w.p, cs.eps.p, cs.dtype.p };
-}
-// energy / gradient on a rank of a sharded potential: the slice [rank*n/world, (rank+1)*n/world) of the kind
-static CollView view_slice(const ipcb_ctx* ctx, int k)
-{
-    CollView c = view(ctx, k);
-    if (ctx->coll_world > 1) {
-        const int64_t lo = c.n * ctx->coll_rank / ctx->coll_world, hi = c.n * (ctx->coll_rank + 1) / ctx->coll_world;
-        c.ids += lo, c.w += lo, c.n = hi - lo;
-        if (k == IPCB_EE) c.eps += lo, c.dt += lo;
-    }
-    return c;
-}
-static MeshView mesh_view(const ipcb_ctx* ctx) { return { ctx->dE.p, ctx->dF.p, ctx->X0.p }; }
 
 void barrier_energy(ipcb_ctx* ctx, const ipcb_barrier_params& bp, double* d_out)
 {
@@ -377,41 +296,6 @@ template <int NP> __device__ inline void project_psd(double* H, int mode, const 
 // gi (VV first, then EV, EE, FV).  Block slot (a, b) = a * 4 + b holds the 3x3 block whose COLUMNS
 // belong to stencil point a and whose ROWS belong to point b (row-major), i.e. what the column of
 // vertex vid[a] needs in compressed-column order.
-// The local matrix is symmetric, so only its UPPER-TRIANGULAR vertex blocks are stored: slot (a, b), a <= b, at
-// tri_slot(a, b) — 3 / 6 / 10 blocks of 72 bytes per VV / EV / 4-point collision instead of 4 / 9 / 16.  The column of
-// point a reads its row block b < a as the TRANSPOSE of slot (b, a) (k_hess_numeric).  The 9-bit exact-non-zero masks
-// are tiny and stay full (16 per collision, the mirrored ones transposed), so the symbolic pass is layout-agnostic.
-struct HessOut {
-    int4* vid;               // stencil vertex ids, -1 padded
-    unsigned short* mask;    // 16 per collision (global collision index): 9-bit exact-non-zero mask per slot a * 4 + b
-    double* blk;             // blocks of THIS kind: tri_count(NP) x 9 doubles per record (record index within the kind)
-    unsigned long long* inc; // incidences: (vertex << 32) | (gi * 4 + a), NP per collision
-    int v_lo, v_hi;          // owned vertex range (row block of a sharded Hessian); incidences of other
-    int v_none;              // vertices get the vertex key v_none (= nV: sorted behind every column)
-};
-constexpr int HSLOTS = 16;
-__host__ __device__ constexpr int tri_count(int np) { return np * (np + 1) / 2; }
-__host__ __device__ constexpr int tri_slot(int np, int a, int b) { return a * np - a * (a - 1) / 2 + (b - a); } // a <= b
-// 9-bit mask of the transposed 3x3 block: bit 3r + c -> bit 3c + r
-__device__ __forceinline__ unsigned mask_transpose(unsigned m)
-{
-    return (m & 0x111u) | ((m & 0x022u) << 2) | ((m & 0x088u) >> 2) | ((m & 0x004u) << 4) | ((m & 0x040u) >> 4);
-}
-
-// returns the mask of the stencil points whose vertex this rank owns
-template <int NP> __device__ inline unsigned write_record(const HessOut& out, int64_t gi, int64_t inc_base, const int* vid)
-{
-    out.vid[gi] = make_int4(vid[0], vid[1], NP > 2 ? vid[2] : -1, NP > 3 ? vid[3] : -1);
-    unsigned own = 0;
-#pragma unroll
-    for (int a = 0; a < NP; a++) {
-        const bool mine = vid[a] >= out.v_lo && vid[a] < out.v_hi;
-        own |= unsigned(mine) << a;
-        out.inc[inc_base + a] = ((unsigned long long)(unsigned)(mine ? vid[a] : out.v_none) << 32) | (unsigned long long)(gi * 4 + a);
-    }
-    return own;
-}
-
 template <int KIND>
 __global__ void __launch_bounds__(128)
     k_hessian_local(CollView c, MeshView m, BarrierDev B, int psd_mode, int64_t gi0, int64_t inc0, HessOut out, const int* __restrict__ list,
@@ -1185,111 +1069,41 @@ __global__ void k_zero_int(int64_t n, int* p)
     if (i < n) p[i] = 0;
 }
 
-void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
+void hessian_empty(ipcb_ctx* ctx)
 {
-    cudaStream_t s = ctx->stream;
-    const BarrierDev B = make_barrier(bp, ctx->dmin);
-    const int nV = ctx->nV;
-    const int v_lo = ctx->row_hi < 0 ? 0 : std::max(0, ctx->row_lo), v_hi = ctx->row_hi < 0 ? nV : std::min(nV, ctx->row_hi);
-    const MeshView m = mesh_view(ctx);
-    // n_k: records of kind k = all its collisions, or (row block of a sharded Hessian) the ones touching an owned vertex
-    int64_t nk[4] = { ctx->coll[0].count, ctx->coll[1].count, ctx->coll[2].count, ctx->coll[3].count };
-    const int* sel[4] = { nullptr, nullptr, nullptr, nullptr };
-    ctx->outer.reserve(3 * size_t(nV) + 1);
+    ctx->outer.reserve(3 * size_t(ctx->nV) + 1);
     ctx->nnz = 0;
-    if ((v_lo > 0 || v_hi < nV) && nk[0] + nk[1] + nk[2] + nk[3] > 0) {
-        Stage st(ctx, "hess_select");
-        const int64_t all = nk[0] + nk[1] + nk[2] + nk[3];
-        ctx->hflag.reserve(all), ctx->hsel.reserve(all);
-        cudaStream_t where[4] = { ctx->aux[0], ctx->aux[1], s, ctx->aux[2] };
-        unsigned long long* d_cnt = ctx->dCounters.p + 24;
-        IPCB_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), s));
-        ctx->fork();
-        int64_t off = 0;
-        for (int k = 0; k < 4; k++) {
-            if (nk[k] == 0) continue;
-            unsigned char* flag = ctx->hflag.p + off;
-            int* list = ctx->hsel.p + off;
-            sel[k] = list;
-            off += nk[k];
-            k_touch_flags<<<grid_for(nk[k], 256), 256, 0, where[k]>>>(view(ctx, k), m, v_lo, v_hi, flag);
-            size_t bytes = 0;
-            cub::CountingInputIterator<int> iota(0);
-            int* d_num = reinterpret_cast<int*>(d_cnt + k);
-            cub::DeviceSelect::Flagged(nullptr, bytes, iota, flag, list, d_num, int(nk[k]), where[k]);
-            ctx->coll[k].cubtmp.reserve(bytes + 256);
-            cub::DeviceSelect::Flagged(ctx->coll[k].cubtmp.p, bytes, iota, flag, list, d_num, int(nk[k]), where[k]);
-            ctx->launches += 3;
-        }
-        for (int k = 0; k < ipcb_ctx::NAUX; k++) ctx->join(k);
-        IPCB_CUDA(cudaGetLastError());
-        IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[28], d_cnt, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-        IPCB_CUDA(cudaStreamSynchronize(s));
-        for (int k = 0; k < 4; k++) nk[k] = nk[k] ? int64_t(ctx->pinned.p[28 + k] & 0xffffffffll) : 0;
-    }
+    k_zero_int<<<grid_for(3 * size_t(ctx->nV) + 1, 256), 256, 0, ctx->stream>>>(3 * int64_t(ctx->nV) + 1, ctx->outer.p);
+    ctx->launches++;
+}
+
+void hessian_records(ipcb_ctx* ctx, const int64_t nk[4], int v_lo, int v_hi, HessOut outs[4])
+{
     const int64_t n0 = nk[0], n1 = nk[1], n2 = nk[2], n3 = nk[3];
     const int64_t ncoll = n0 + n1 + n2 + n3;
-    const int64_t gi0[4] = { 0, n0, n0 + n1, n0 + n1 + n2 };
-    const int64_t inc0[4] = { 0, 2 * n0, 2 * n0 + 3 * n1, 2 * n0 + 3 * n1 + 4 * n2 };
     const int64_t ninc = 2 * n0 + 3 * n1 + 4 * (n2 + n3);
     const int64_t nitems = 4 * n0 + 9 * n1 + 16 * (n2 + n3);
-    if (ncoll == 0) { // empty ndof x ndof matrix (potential.cpp:107-109)
-        k_zero_int<<<grid_for(3 * size_t(nV) + 1, 256), 256, 0, s>>>(3 * int64_t(nV) + 1, ctx->outer.p);
-        ctx->launches++;
-        return;
-    }
     // stored blocks (upper triangles): 3 / 6 / 10 per VV / EV / 4-point record
     const int64_t blk0[4] = { 0, 3 * n0, 3 * n0 + 6 * n1, 3 * n0 + 6 * n1 + 10 * n2 };
     const int64_t nblocks = blk0[3] + 10 * n3;
     if (ncoll >= (int64_t(1) << 27) || nitems > 0x7fffffffll || nblocks > 0x7fffffffll)
         throw Error("Hessian: more than 2^27 collisions / 2^31 local blocks on one device; shard the collision set");
-    {
-        Stage st(ctx, "hessian_local");
-        ctx->hvid.reserve(ncoll), ctx->hmask.reserve(size_t(ncoll) * HSLOTS), ctx->hblk.reserve(size_t(nblocks) * 9);
-        ctx->hkey.reserve(ninc), ctx->hkey_sorted.reserve(ninc);
-        HessOut outs[4];
-        for (int k = 0; k < 4; k++) outs[k] = HessOut { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p + size_t(blk0[k]) * 9, ctx->hkey.p, v_lo, v_hi, nV };
-        static const bool force_general = getenv("IPCB_HESSIAN_GENERAL") != nullptr; // A/B switch for tests and profiles
-        if (psd_mode == IPCB_PSD_NONE || force_general) {
-            if (n0) k_hessian_local<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], outs[0], nullptr, 0, sel[0], n0), ctx->launches++;
-            if (n1) k_hessian_local<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], outs[1], nullptr, 0, sel[1], n1), ctx->launches++;
-            if (n2) k_hessian_local<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], nullptr, 0, sel[2], n2), ctx->launches++;
-            if (n3) k_hessian_local<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], outs[3], nullptr, 0, sel[3], n3), ctx->launches++;
-        } else {
-            unsigned long long* slow_count = ctx->dCounters.p + 5;
-            ctx->hslow.reserve(std::max<int64_t>(n2, 1));
-            IPCB_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(unsigned long long), s));
-            // the four kinds write disjoint records: the small ones run beside the edge-edge kernel
-            ctx->fork();
-            static const bool dense = getenv("IPCB_HFAST_SPARSE") == nullptr; // 4 resident blocks per SM (small spill) for the 4-point kinds; A/B switch
-            std::unique_ptr<Stage> kt(new Stage(ctx, "k:k_hessian_fast<VV>", ctx->aux[0]));
-            if (n0) k_hessian_fast<IPCB_VV, 4><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], outs[0], ctx->hslow.p, slow_count, sel[0], n0), ctx->launches++;
-            kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<EV>", ctx->aux[0]));
-            if (n1) k_hessian_fast<IPCB_EV, 4><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], outs[1], ctx->hslow.p, slow_count, sel[1], n1), ctx->launches++;
-            kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<FV>", ctx->aux[1]));
-            if (n3 && dense) k_hessian_fast<IPCB_FV, 4><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], outs[3], ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
-            else if (n3) k_hessian_fast<IPCB_FV, 3><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], outs[3], ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
-            kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<EE>", s));
-            if (n2) {
-                if (dense) k_hessian_fast<IPCB_EE, 4><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, slow_count, sel[2], n2);
-                else k_hessian_fast<IPCB_EE, 3><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, slow_count, sel[2], n2);
-                ctx->launches++;
-                kt.reset();
-                IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[11], slow_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-                IPCB_CUDA(cudaStreamSynchronize(s));
-                const int64_t nslow = ctx->pinned.p[11];
-                if (nslow) {
-                    Stage ks(ctx, "k:k_hessian_local<EE>(mollified)", s);
-                    k_hessian_local<IPCB_EE><<<grid_for(nslow, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, nslow, sel[2], n2);
-                    ctx->launches++;
-                }
-            }
-            kt.reset();
-            ctx->join(0);
-            ctx->join(1);
-        }
-        IPCB_CUDA(cudaGetLastError());
-    }
+    ctx->hvid.reserve(ncoll), ctx->hmask.reserve(size_t(ncoll) * HSLOTS), ctx->hblk.reserve(size_t(nblocks) * 9);
+    ctx->hkey.reserve(ninc), ctx->hkey_sorted.reserve(ninc);
+    for (int k = 0; k < 4; k++) outs[k] = HessOut { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p + size_t(blk0[k]) * 9, ctx->hkey.p, v_lo, v_hi, ctx->nV };
+}
+
+// Assembly of the per-collision records into compressed columns (see the comment block above k_col_ranges)
+void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
+{
+    cudaStream_t s = ctx->stream;
+    const int nV = ctx->nV;
+    const int64_t n0 = nk[0], n1 = nk[1], n2 = nk[2], n3 = nk[3];
+    const int64_t gi0[4] = { 0, n0, n0 + n1, n0 + n1 + n2 };
+    const int64_t ninc = 2 * n0 + 3 * n1 + 4 * (n2 + n3);
+    const int64_t nitems = 4 * n0 + 9 * n1 + 16 * (n2 + n3);
+    const int64_t blk0[4] = { 0, 3 * n0, 3 * n0 + 6 * n1, 3 * n0 + 6 * n1 + 10 * n2 };
+    ctx->outer.reserve(3 * size_t(nV) + 1);
     // stage timers (only when ctx->timing is on): the three kernels of the assembly are timed one by one
     std::unique_ptr<Stage> st(new Stage(ctx, "hess_incidences"));
     int vbits = 1;
@@ -1373,6 +1187,103 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
                                                           ctx->outer.p, ctx->inner.p, ctx->vals.p, order);
     ctx->launches++;
     IPCB_CUDA(cudaGetLastError());
+}
+
+void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
+{
+    cudaStream_t s = ctx->stream;
+    const BarrierDev B = make_barrier(bp, ctx->dmin);
+    const int nV = ctx->nV;
+    const int v_lo = ctx->row_hi < 0 ? 0 : std::max(0, ctx->row_lo), v_hi = ctx->row_hi < 0 ? nV : std::min(nV, ctx->row_hi);
+    const MeshView m = mesh_view(ctx);
+    // n_k: records of kind k = all its collisions, or (row block of a sharded Hessian) the ones touching an owned vertex
+    int64_t nk[4] = { ctx->coll[0].count, ctx->coll[1].count, ctx->coll[2].count, ctx->coll[3].count };
+    const int* sel[4] = { nullptr, nullptr, nullptr, nullptr };
+    ctx->outer.reserve(3 * size_t(nV) + 1);
+    ctx->nnz = 0;
+    if ((v_lo > 0 || v_hi < nV) && nk[0] + nk[1] + nk[2] + nk[3] > 0) {
+        Stage st(ctx, "hess_select");
+        const int64_t all = nk[0] + nk[1] + nk[2] + nk[3];
+        ctx->hflag.reserve(all), ctx->hsel.reserve(all);
+        cudaStream_t where[4] = { ctx->aux[0], ctx->aux[1], s, ctx->aux[2] };
+        unsigned long long* d_cnt = ctx->dCounters.p + 24;
+        IPCB_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(unsigned long long), s));
+        ctx->fork();
+        int64_t off = 0;
+        for (int k = 0; k < 4; k++) {
+            if (nk[k] == 0) continue;
+            unsigned char* flag = ctx->hflag.p + off;
+            int* list = ctx->hsel.p + off;
+            sel[k] = list;
+            off += nk[k];
+            k_touch_flags<<<grid_for(nk[k], 256), 256, 0, where[k]>>>(view(ctx, k), m, v_lo, v_hi, flag);
+            size_t bytes = 0;
+            cub::CountingInputIterator<int> iota(0);
+            int* d_num = reinterpret_cast<int*>(d_cnt + k);
+            cub::DeviceSelect::Flagged(nullptr, bytes, iota, flag, list, d_num, int(nk[k]), where[k]);
+            ctx->coll[k].cubtmp.reserve(bytes + 256);
+            cub::DeviceSelect::Flagged(ctx->coll[k].cubtmp.p, bytes, iota, flag, list, d_num, int(nk[k]), where[k]);
+            ctx->launches += 3;
+        }
+        for (int k = 0; k < ipcb_ctx::NAUX; k++) ctx->join(k);
+        IPCB_CUDA(cudaGetLastError());
+        IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[28], d_cnt, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        IPCB_CUDA(cudaStreamSynchronize(s));
+        for (int k = 0; k < 4; k++) nk[k] = nk[k] ? int64_t(ctx->pinned.p[28 + k] & 0xffffffffll) : 0;
+    }
+    const int64_t n0 = nk[0], n1 = nk[1], n2 = nk[2], n3 = nk[3];
+    const int64_t gi0[4] = { 0, n0, n0 + n1, n0 + n1 + n2 };
+    const int64_t inc0[4] = { 0, 2 * n0, 2 * n0 + 3 * n1, 2 * n0 + 3 * n1 + 4 * n2 };
+    if (n0 + n1 + n2 + n3 == 0) { // empty ndof x ndof matrix (potential.cpp:107-109)
+        hessian_empty(ctx);
+        return;
+    }
+    {
+        Stage st(ctx, "hessian_local");
+        HessOut outs[4];
+        hessian_records(ctx, nk, v_lo, v_hi, outs);
+        static const bool force_general = getenv("IPCB_HESSIAN_GENERAL") != nullptr; // A/B switch for tests and profiles
+        if (psd_mode == IPCB_PSD_NONE || force_general) {
+            if (n0) k_hessian_local<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], outs[0], nullptr, 0, sel[0], n0), ctx->launches++;
+            if (n1) k_hessian_local<IPCB_EV><<<grid_for(n1, 128), 128, 0, s>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], outs[1], nullptr, 0, sel[1], n1), ctx->launches++;
+            if (n2) k_hessian_local<IPCB_EE><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], nullptr, 0, sel[2], n2), ctx->launches++;
+            if (n3) k_hessian_local<IPCB_FV><<<grid_for(n3, 128), 128, 0, s>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], outs[3], nullptr, 0, sel[3], n3), ctx->launches++;
+        } else {
+            unsigned long long* slow_count = ctx->dCounters.p + 5;
+            ctx->hslow.reserve(std::max<int64_t>(n2, 1));
+            IPCB_CUDA(cudaMemsetAsync(slow_count, 0, sizeof(unsigned long long), s));
+            // the four kinds write disjoint records: the small ones run beside the edge-edge kernel
+            ctx->fork();
+            static const bool dense = getenv("IPCB_HFAST_SPARSE") == nullptr; // 4 resident blocks per SM (small spill) for the 4-point kinds; A/B switch
+            std::unique_ptr<Stage> kt(new Stage(ctx, "k:k_hessian_fast<VV>", ctx->aux[0]));
+            if (n0) k_hessian_fast<IPCB_VV, 4><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], outs[0], ctx->hslow.p, slow_count, sel[0], n0), ctx->launches++;
+            kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<EV>", ctx->aux[0]));
+            if (n1) k_hessian_fast<IPCB_EV, 4><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], outs[1], ctx->hslow.p, slow_count, sel[1], n1), ctx->launches++;
+            kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<FV>", ctx->aux[1]));
+            if (n3 && dense) k_hessian_fast<IPCB_FV, 4><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], outs[3], ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
+            else if (n3) k_hessian_fast<IPCB_FV, 3><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], outs[3], ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
+            kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<EE>", s));
+            if (n2) {
+                if (dense) k_hessian_fast<IPCB_EE, 4><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, slow_count, sel[2], n2);
+                else k_hessian_fast<IPCB_EE, 3><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, slow_count, sel[2], n2);
+                ctx->launches++;
+                kt.reset();
+                IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[11], slow_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+                IPCB_CUDA(cudaStreamSynchronize(s));
+                const int64_t nslow = ctx->pinned.p[11];
+                if (nslow) {
+                    Stage ks(ctx, "k:k_hessian_local<EE>(mollified)", s);
+                    k_hessian_local<IPCB_EE><<<grid_for(nslow, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, nslow, sel[2], n2);
+                    ctx->launches++;
+                }
+            }
+            kt.reset();
+            ctx->join(0);
+            ctx->join(1);
+        }
+        IPCB_CUDA(cudaGetLastError());
+    }
+    hessian_assemble(ctx, nk);
 }
 
 } // namespace ipcb

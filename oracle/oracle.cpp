@@ -12,6 +12,7 @@
 #include "../include/ipcb200.h"
 
 #include "geom.hpp"
+#include "friction.hpp"
 #include "eig.hpp"
 #include "ccd.hpp"
 
@@ -92,6 +93,8 @@ struct ipcb_ctx {
     // hessian
     std::vector<int32_t> outer, inner;
     std::vector<double> vals;
+    // friction: the lagged tangential collision set (collisions/tangential/tangential_collisions.hpp)
+    std::vector<oracle::Tang> tang[4];
     // CollisionMesh::can_collide (collision_mesh.hpp:338) as the intersection of the two descriptor-expressible
     // factories of collision_filter.hpp:113-143
     std::vector<int32_t> patch_ids; // make_vertex_patches_filter (empty: off)
@@ -1296,15 +1299,43 @@ int ipco_barrier_gradient(ipcb_ctx* ctx, const double* Vp, int32_t ld, const ipc
     return 0;
 }
 
+struct Trip {
+    int32_t col, row;
+    double val;
+};
+// setFromTriplets (potential.cpp:218) into ctx->outer / inner / vals
+static void assemble_triplets(ipcb_ctx* ctx, std::vector<std::vector<Trip>>& loc, int ndof, int64_t* nnz)
+{
+    std::vector<Trip> all;
+    size_t total = 0;
+    for (auto& l : loc) total += l.size();
+    all.reserve(total);
+    for (auto& l : loc) all.insert(all.end(), l.begin(), l.end());
+    // setFromTriplets (potential.cpp:218; SURVEY B.4): compressed columns, rows ascending, duplicates summed
+    __gnu_parallel::stable_sort(all.begin(), all.end(), [](const Trip& a, const Trip& b) {
+        return a.col != b.col ? a.col < b.col : a.row < b.row;
+    });
+    ctx->outer.assign(ndof + 1, 0);
+    ctx->inner.clear();
+    ctx->vals.clear();
+    for (size_t i = 0; i < all.size();) {
+        size_t j = i;
+        double s = 0;
+        while (j < all.size() && all[j].col == all[i].col && all[j].row == all[i].row) s += all[j++].val;
+        ctx->inner.push_back(all[i].row);
+        ctx->vals.push_back(s);
+        ctx->outer[all[i].col + 1]++;
+        i = j;
+    }
+    for (int c = 0; c < ndof; c++) ctx->outer[c + 1] += ctx->outer[c];
+    *nnz = int64_t(ctx->inner.size());
+}
+
 int ipco_barrier_hessian(ipcb_ctx* ctx, const double* Vp, int32_t ld, const ipcb_barrier_params* bp, int32_t psd_mode, int64_t* nnz)
 {
     const auto V = load_vertices(ctx->nV, Vp, ld);
     const Barrier B = { bp->dhat, bp->stiffness, bp->use_physical_barrier != 0 };
     const int ndof = 3 * ctx->nV;
-    struct Trip {
-        int32_t col, row;
-        double val;
-    };
     const int nt = omp_get_max_threads();
     const int row_lo = ctx->row_hi < 0 ? 0 : ctx->row_lo, row_hi = ctx->row_hi < 0 ? ctx->nV : ctx->row_hi;
     std::vector<std::vector<Trip>> loc(nt);
@@ -1334,29 +1365,7 @@ int ipco_barrier_hessian(ipcb_ctx* ctx, const double* Vp, int32_t ld, const ipcb
                 }
         }
     }
-    std::vector<Trip> all;
-    size_t total = 0;
-    for (auto& l : loc) total += l.size();
-    all.reserve(total);
-    for (auto& l : loc) all.insert(all.end(), l.begin(), l.end());
-    // setFromTriplets (potential.cpp:218; SURVEY B.4): compressed columns, rows ascending, duplicates summed
-    __gnu_parallel::stable_sort(all.begin(), all.end(), [](const Trip& a, const Trip& b) {
-        return a.col != b.col ? a.col < b.col : a.row < b.row;
-    });
-    ctx->outer.assign(ndof + 1, 0);
-    ctx->inner.clear();
-    ctx->vals.clear();
-    for (size_t i = 0; i < all.size();) {
-        size_t j = i;
-        double s = 0;
-        while (j < all.size() && all[j].col == all[i].col && all[j].row == all[i].row) s += all[j++].val;
-        ctx->inner.push_back(all[i].row);
-        ctx->vals.push_back(s);
-        ctx->outer[all[i].col + 1]++;
-        i = j;
-    }
-    for (int c = 0; c < ndof; c++) ctx->outer[c + 1] += ctx->outer[c];
-    *nnz = int64_t(ctx->inner.size());
+    assemble_triplets(ctx, loc, ndof, nnz);
     return 0;
 }
 int ipco_barrier_hessian_fetch(ipcb_ctx* ctx, int32_t* outer, int32_t* inner, double* values)
@@ -1365,6 +1374,154 @@ int ipco_barrier_hessian_fetch(ipcb_ctx* ctx, int32_t* outer, int32_t* inner, do
     std::copy(ctx->inner.begin(), ctx->inner.end(), inner);
     std::copy(ctx->vals.begin(), ctx->vals.end(), values);
     return 0;
+}
+
+// ---- friction ------------------------------------------------------------------------------
+// TangentialCollisions::build(mesh, vertices, collisions, normal_potential, mu_s, mu_k) (tangential_collisions.cpp:62-171)
+// from the RESIDENT normal collision set
+int ipco_tangential_build(ipcb_ctx* ctx, const double* Vp, int32_t ld, const ipcb_barrier_params* bp, const double* mu_s, const double* mu_k,
+                          int64_t counts[4])
+{
+    using namespace oracle;
+    const auto V = load_vertices(ctx->nV, Vp, ld);
+    const Barrier B = { bp->dhat, bp->stiffness, bp->use_physical_barrier != 0 };
+    const double dmin = ctx->dmin;
+    // NormalPotential::force_magnitude (barrier_potential.cpp:33-44, barrier_force_magnitude.cpp:7-15)
+    auto force = [&](double d_sqr) {
+        const double grad_b = barrier_first_derivative(d_sqr - dmin * dmin, (2 * dmin + B.dhat) * B.dhat);
+        double N = -B.kappa * grad_b * 2 * std::sqrt(d_sqr);
+        if (B.physical) N *= B.scale(dmin);
+        return N;
+    };
+    auto blend = [](double a, double b) { return (a + b) / 2; }; // default_blend_mu (tangential_collisions.hpp:143-149)
+    for (int k = 0; k < 4; k++) {
+        ctx->tang[k].clear();
+        for (const Coll& c : ctx->coll[k]) {
+            int32_t ids[4];
+            const int n = stencil_ids(ctx, k, c.a, c.b, ids);
+            V3 x[4];
+            for (int j = 0; j < n; j++) x[j] = V[ids[j]];
+            Tang t {};
+            t.a = c.a, t.b = c.b, t.weight = c.w;
+            if (k == IPCB_VV) {
+                point_point_tangent_basis(x[0], x[1], t.P);
+                t.normal_force = force(point_point_distance(x[0], x[1]));
+                t.mu_s = blend(mu_s[ids[0]], mu_s[ids[1]]), t.mu_k = blend(mu_k[ids[0]], mu_k[ids[1]]);
+            } else if (k == IPCB_EV) {
+                t.beta[0] = point_edge_closest_point(x[0], x[1], x[2]);
+                point_edge_tangent_basis(x[0], x[1], x[2], t.P);
+                t.normal_force = force(point_edge_distance(x[0], x[1], x[2])); // known_dtype() == AUTO (candidates/edge_vertex.hpp:63-66)
+                t.mu_s = blend((mu_s[ids[2]] - mu_s[ids[1]]) * t.beta[0] + mu_s[ids[1]], mu_s[ids[0]]);
+                t.mu_k = blend((mu_k[ids[2]] - mu_k[ids[1]]) * t.beta[0] + mu_k[ids[1]], mu_k[ids[0]]);
+            } else if (k == IPCB_EE) {
+                if (edge_edge_cross_squarednorm(x[0], x[1], x[2], x[3]) < c.eps_x) continue; // close to parallel: skipped (:123-126)
+                edge_edge_closest_point(x[0], x[1], x[2], x[3], t.beta);
+                edge_edge_tangent_basis(x[0], x[1], x[2], x[3], t.P);
+                t.normal_force = force(edge_edge_distance(x[0], x[1], x[2], x[3], EE_EA_EB)); // collisions/tangential/edge_edge.hpp:27-31
+                t.mu_s = blend((mu_s[ids[1]] - mu_s[ids[0]]) * t.beta[0] + mu_s[ids[0]], (mu_s[ids[3]] - mu_s[ids[2]]) * t.beta[1] + mu_s[ids[2]]);
+                t.mu_k = blend((mu_k[ids[1]] - mu_k[ids[0]]) * t.beta[0] + mu_k[ids[0]], (mu_k[ids[3]] - mu_k[ids[2]]) * t.beta[1] + mu_k[ids[2]]);
+            } else {
+                point_triangle_closest_point(x[0], x[1], x[2], x[3], t.beta);
+                point_triangle_tangent_basis(x[0], x[1], x[2], x[3], t.P);
+                t.normal_force = force(point_triangle_distance(x[0], x[1], x[2], x[3])); // AUTO
+                t.mu_s = blend(mu_s[ids[1]] + t.beta[0] * (mu_s[ids[2]] - mu_s[ids[1]]) + t.beta[1] * (mu_s[ids[3]] - mu_s[ids[1]]), mu_s[ids[0]]);
+                t.mu_k = blend(mu_k[ids[1]] + t.beta[0] * (mu_k[ids[2]] - mu_k[ids[1]]) + t.beta[1] * (mu_k[ids[3]] - mu_k[ids[1]]), mu_k[ids[0]]);
+            }
+            ctx->tang[k].push_back(t);
+        }
+        counts[k] = int64_t(ctx->tang[k].size());
+    }
+    return 0;
+}
+int ipco_tangential_fetch(ipcb_ctx* ctx, int32_t kind, int32_t* ids, double* weight, double* normal_force, double* mu_s, double* mu_k,
+                          double* closest_point, double* tangent_basis)
+{
+    if (kind < 0 || kind > 3) return fail("bad collision kind");
+    const auto& ts = ctx->tang[kind];
+    for (size_t i = 0; i < ts.size(); i++) {
+        const auto& t = ts[i];
+        if (ids) ids[2 * i] = t.a, ids[2 * i + 1] = t.b;
+        if (weight) weight[i] = t.weight;
+        if (normal_force) normal_force[i] = t.normal_force;
+        if (mu_s) mu_s[i] = t.mu_s;
+        if (mu_k) mu_k[i] = t.mu_k;
+        if (closest_point) closest_point[2 * i] = t.beta[0], closest_point[2 * i + 1] = t.beta[1];
+        if (tangent_basis) {
+            const double P[6] = { t.P[0].x, t.P[0].y, t.P[0].z, t.P[1].x, t.P[1].y, t.P[1].z };
+            std::copy(P, P + 6, tangent_basis + 6 * i);
+        }
+    }
+    return 0;
+}
+// FrictionPotential(eps_v) over the resident tangential set: potential.cpp:36-222 with tangential_potential.cpp:162-325
+int ipco_friction_energy(ipcb_ctx* ctx, const double* Up, int32_t ld, double eps_v, double* energy)
+{
+    const auto U = load_vertices(ctx->nV, Up, ld);
+    double total = 0;
+    for (int k = 0; k < 4; k++) {
+        double sum = 0;
+        const auto& ts = ctx->tang[k];
+#pragma omp parallel for reduction(+ : sum) schedule(static)
+        for (size_t i = 0; i < ts.size(); i++) {
+            int32_t ids[4];
+            const int n = stencil_ids(ctx, k, ts[i].a, ts[i].b, ids);
+            V3 v[4];
+            for (int j = 0; j < n; j++) v[j] = U[ids[j]];
+            sum += oracle::friction_energy(k, ts[i], v, eps_v);
+        }
+        total += sum;
+    }
+    *energy = total;
+    return 0;
+}
+int ipco_friction_gradient(ipcb_ctx* ctx, const double* Up, int32_t ld, double eps_v, double* grad)
+{
+    const auto U = load_vertices(ctx->nV, Up, ld);
+    const size_t ndof = 3 * size_t(ctx->nV);
+    std::fill(grad, grad + ndof, 0.0);
+    for (int k = 0; k < 4; k++)
+        for (const auto& t : ctx->tang[k]) {
+            int32_t ids[4];
+            const int n = stencil_ids(ctx, k, t.a, t.b, ids);
+            V3 v[4];
+            for (int j = 0; j < n; j++) v[j] = U[ids[j]];
+            double g[12];
+            oracle::friction_gradient(k, t, v, eps_v, g);
+            for (int j = 0; j < n; j++)
+                for (int c = 0; c < 3; c++) grad[3 * size_t(ids[j]) + c] += g[3 * j + c];
+        }
+    return 0;
+}
+int ipco_friction_hessian(ipcb_ctx* ctx, const double* Up, int32_t ld, double eps_v, int32_t psd_mode, int64_t* nnz)
+{
+    const auto U = load_vertices(ctx->nV, Up, ld);
+    const int ndof = 3 * ctx->nV;
+    std::vector<std::vector<Trip>> loc(1);
+    for (int k = 0; k < 4; k++)
+        for (const auto& t : ctx->tang[k]) {
+            int32_t ids[4];
+            const int n = stencil_ids(ctx, k, t.a, t.b, ids);
+            V3 v[4];
+            for (int j = 0; j < n; j++) v[j] = U[ids[j]];
+            double H[144];
+            oracle::friction_hessian(k, t, v, eps_v, psd_mode, H);
+            for (int a = 0; a < n; a++)
+                for (int b = 0; b < n; b++)
+                    for (int r = 0; r < 3; r++)
+                        for (int c = 0; c < 3; c++) {
+                            const double val = H[(3 * a + r) + 12 * (3 * b + c)];
+                            if (val != 0) loc[0].push_back({ 3 * ids[b] + c, 3 * ids[a] + r, val }); // local_to_global.hpp:290-291
+                        }
+        }
+    assemble_triplets(ctx, loc, ndof, nnz);
+    return 0;
+}
+
+double ipco_unit_smooth_mu_f0(double y, double mu_s, double mu_k, double eps_v) { return oracle::smooth_mu_f0(y, mu_s, mu_k, eps_v); }
+double ipco_unit_smooth_mu_f1_over_x(double y, double mu_s, double mu_k, double eps_v) { return oracle::smooth_mu_f1_over_x(y, mu_s, mu_k, eps_v); }
+double ipco_unit_smooth_mu_f2_x_minus_mu_f1_over_x3(double y, double mu_s, double mu_k, double eps_v)
+{
+    return oracle::smooth_mu_f2_x_minus_mu_f1_over_x3(y, mu_s, mu_k, eps_v);
 }
 
 int ipco_ccd_stepsize_from_candidates(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld, double min_distance,
