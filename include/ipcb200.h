@@ -218,6 +218,11 @@ int IPCB_FN(barrier_hessian)(ipcb_ctx* ctx, const double* V, int32_t ld, const i
 int IPCB_FN(barrier_hessian_fetch)(ipcb_ctx* ctx, int32_t* outer /* 3nV+1 */, int32_t* inner /* nnz */,
                                    double* values /* nnz */);
 
+/* ipc::has_intersections(mesh, vertices) (ipc.cpp:105-166), 3D: edge-face candidates of a broad phase inflated by 1e-6 of
+ * the world bounding-box diagonal, then is_edge_intersecting_triangle (geometry/intersection.cpp:115-145) with an exact
+ * orientation test.  *result = 1 if some edge intersects some triangle (sharing no vertex, passing the collision filter). */
+int IPCB_FN(has_intersections)(ipcb_ctx* ctx, const double* V, int32_t ld, int32_t* result);
+
 /* ---- Friction ----------------------------------------- */
 /* TangentialCollisions::build(mesh, vertices, collisions, normal_potential, mu_s, mu_k)
  * (collisions/tangential/tangential_collisions.cpp:62-171) from the RESIDENT normal collision set: per collision the

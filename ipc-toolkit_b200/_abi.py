@@ -57,6 +57,7 @@ HOST_API = {
     "barrier_gradient": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), P]),
     "barrier_hessian": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), c_i32, C.POINTER(c_i64)]),
     "barrier_hessian_fetch": (C.c_int, [P, P, P, P]),
+    "has_intersections": (C.c_int, [P, P, c_i32, C.POINTER(c_i32)]),
     "tangential_build": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), P, P, C.POINTER(c_i64)]),
     "tangential_fetch": (C.c_int, [P, c_i32, P, P, P, P, P, P, P]),
     "friction_energy": (C.c_int, [P, P, c_i32, c_f64, C.POINTER(c_f64)]),

@@ -705,6 +705,14 @@ def make_api(lib):
         return compute_collision_free_stepsize(mesh, vertices_t0, vertices_t1, min_distance, broad_phase,
                                                narrow_phase_ccd) >= 1.0
 
+    def has_intersections(mesh, vertices, broad_phase=None):
+        """ipc::has_intersections — ipc.cpp:105-166 (3D: an edge crossing a triangle)"""
+        v, p, ld = _f64(vertices)
+        out = C.c_int32()
+        lib.check(lib.has_intersections(mesh._ctx, p, ld, C.byref(out)))
+        mesh._cand_gen += 1
+        return bool(out.value)
+
     def narrow_phase_ccd(kind, x_t0, x_t1, min_distance=0.0, tmax=1.0, ccd=None, mesh=None):
         """batched NarrowPhaseCCD queries (ccd/narrow_phase_ccd.hpp:8-119): x_* are (n, 4, 3) arrays"""
         a = np.ascontiguousarray(x_t0, dtype=np.float64).reshape(-1, 12)
@@ -732,4 +740,5 @@ def make_api(lib):
     ns.compute_collision_free_stepsize = compute_collision_free_stepsize
     ns.is_step_collision_free = is_step_collision_free
     ns.narrow_phase_ccd = narrow_phase_ccd
+    ns.has_intersections = has_intersections
     return ns

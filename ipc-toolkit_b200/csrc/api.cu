@@ -846,6 +846,28 @@ int ipcb_barrier_hessian_fetch(ipcb_ctx* ctx, int32_t* outer, int32_t* inner, do
     });
 }
 
+// world_bbox_diagonal_length (utils/world_bbox_diagonal_length.hpp:10-15) of column-major positions
+static double bbox_diagonal(const double* V, int n, int ld)
+{
+    double d2 = 0;
+    double ext[3] = { 0, 0, 0 };
+    for (int k = 0; k < 3; k++) {
+        double lo = INFINITY, hi = -INFINITY;
+        for (int i = 0; i < n; i++) lo = std::min(lo, V[i + size_t(ld) * k]), hi = std::max(hi, V[i + size_t(ld) * k]);
+        ext[k] = n ? hi - lo : 0.0;
+    }
+    d2 = (ext[0] * ext[0] + ext[1] * ext[1]) + ext[2] * ext[2];
+    return std::sqrt(d2);
+}
+int ipcb_has_intersections(ipcb_ctx* ctx, const double* V, int32_t ld, int32_t* result)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        stage_positions(ctx, V, ld, false);
+        *result = has_intersections(ctx, 1e-6 * bbox_diagonal(V, ctx->nV, ld)) ? 1 : 0; // ipc.cpp:120-121
+    });
+}
+
 // ---- Friction
 int ipcb_tangential_build(ipcb_ctx* ctx, const double* V, int32_t ld, const ipcb_barrier_params* normal_potential, const double* mu_s,
                           const double* mu_k, int64_t counts[4])

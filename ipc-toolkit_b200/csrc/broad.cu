@@ -22,6 +22,8 @@
 //   { (i,j) : fbox_i ∩ fbox_j ≠ ∅ (closed) ∧ no shared vertex }
 // exactly like the reference's default LBVH (SURVEY §7 hard part 1).
 #include "ctx.cuh"
+#include "exact_orient3d.hpp"
+#include "geom.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cfloat>
 #include <algorithm>
@@ -1084,6 +1086,133 @@ void broad_detect(ipcb_ctx* ctx, int kind, PairList& out)
     }
     default: throw Error("bad candidate kind");
     }
+}
+
+// ---------------------------------------------------------------------------
+// ipc::has_intersections (ipc.cpp:105-166), 3D: edge-face candidates of a broad phase inflated by 1e-6 of the scene
+// diagonal, then is_edge_intersecting_triangle (geometry/intersection.cpp:115-145): both end points strictly on one side
+// of the triangle's plane (exact orient3d) -> no; otherwise solve [t1 - t0, t2 - t0, e0 - e1] (u, v, t) = e0 - t0 with a
+// full-pivoting LU and test 0 <= u, v, u + v <= 1, 0 <= t <= 1.
+// The orientation is evaluated in FP64 with Shewchuk's static error bound; undecided candidates (status 2) get the
+// exact predicate on the host (exact_orient3d.hpp).
+__host__ __device__ inline bool edge_triangle_solve(d3 e0, d3 e1, d3 t0, d3 t1, d3 t2)
+{
+    // columns of M; full-pivoting Gaussian elimination like Eigen::FullPivLU (largest |entry| of the remaining block)
+    double M[3][3] = { { t1.x - t0.x, t2.x - t0.x, e0.x - e1.x }, { t1.y - t0.y, t2.y - t0.y, e0.y - e1.y }, { t1.z - t0.z, t2.z - t0.z, e0.z - e1.z } };
+    double b[3] = { e0.x - t0.x, e0.y - t0.y, e0.z - t0.z };
+    int colperm[3] = { 0, 1, 2 };
+    int rank = 3;
+    for (int k = 0; k < 3; k++) {
+        int pr = k, pc = k;
+        double best = 0;
+        for (int i = k; i < 3; i++)
+            for (int j = k; j < 3; j++)
+                if (fabs(M[i][j]) > best) best = fabs(M[i][j]), pr = i, pc = j;
+        if (best == 0) {
+            rank = k;
+            break;
+        }
+        if (pr != k) {
+            for (int j = 0; j < 3; j++) {
+                const double t = M[k][j];
+                M[k][j] = M[pr][j], M[pr][j] = t;
+            }
+            const double t = b[k];
+            b[k] = b[pr], b[pr] = t;
+        }
+        if (pc != k) {
+            for (int i = 0; i < 3; i++) {
+                const double t = M[i][k];
+                M[i][k] = M[i][pc], M[i][pc] = t;
+            }
+            const int t = colperm[k];
+            colperm[k] = colperm[pc], colperm[pc] = t;
+        }
+        for (int i = k + 1; i < 3; i++) {
+            const double l = M[i][k] / M[k][k];
+            for (int j = k + 1; j < 3; j++) M[i][j] -= l * M[k][j];
+            b[i] -= l * b[k];
+        }
+    }
+    double y[3] = { 0, 0, 0 };
+    for (int k = rank - 1; k >= 0; k--) {
+        double acc = b[k];
+        for (int j = k + 1; j < rank; j++) acc -= M[k][j] * y[j];
+        y[k] = acc / M[k][k];
+    }
+    double uvt[3] = { 0, 0, 0 };
+    for (int k = 0; k < 3; k++) uvt[colperm[k]] = y[k];
+    return uvt[0] >= 0.0 && uvt[1] >= 0.0 && uvt[0] + uvt[1] <= 1.0 && uvt[2] >= 0.0 && uvt[2] <= 1.0;
+}
+// FP64 orientation of d against the plane (a, b, c) with Shewchuk's static filter: +-1 certain, 0 undecided
+__device__ inline int orient3d_filtered(d3 a, d3 b, d3 c, d3 d)
+{
+    const double adx = a.x - d.x, bdx = b.x - d.x, cdx = c.x - d.x, ady = a.y - d.y, bdy = b.y - d.y, cdy = c.y - d.y;
+    const double adz = a.z - d.z, bdz = b.z - d.z, cdz = c.z - d.z;
+    const double bdxcdy = bdx * cdy, cdxbdy = cdx * bdy, cdxady = cdx * ady, adxcdy = adx * cdy, adxbdy = adx * bdy, bdxady = bdx * ady;
+    const double det = adz * (bdxcdy - cdxbdy) + bdz * (cdxady - adxcdy) + cdz * (adxbdy - bdxady);
+    const double permanent = (fabs(bdxcdy) + fabs(cdxbdy)) * fabs(adz) + (fabs(cdxady) + fabs(adxcdy)) * fabs(bdz) + (fabs(adxbdy) + fabs(bdxady)) * fabs(cdz);
+    const double errbound = 7.771561172376103e-16 * permanent; // (7 + 56 eps) eps, eps = 2^-53
+    if (det > errbound) return 1;
+    if (-det > errbound) return -1;
+    return 0;
+}
+__global__ void k_edge_face_intersect(int64_t n, const int2* __restrict__ pairs, const int2* __restrict__ E, const int4* __restrict__ F,
+                                      const double4* __restrict__ X, unsigned long long* counters, int* __restrict__ undecided)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 c = pairs[i]; // (edge, face)
+    const int2 e = __ldg(E + c.x);
+    const int4 f = __ldg(F + c.y);
+    const d3 e0 = load_vertex(X, e.x), e1 = load_vertex(X, e.y), t0 = load_vertex(X, f.x), t1 = load_vertex(X, f.y), t2 = load_vertex(X, f.z);
+    const int o1 = orient3d_filtered(t0, t1, t2, e0), o2 = orient3d_filtered(t0, t1, t2, e1);
+    if (o1 != 0 && o2 != 0) {
+        if (o1 == o2) return; // strictly on one side of the plane
+        if (edge_triangle_solve(e0, e1, t0, t1, t2)) atomicAdd(counters, 1ull);
+        return;
+    }
+    undecided[atomicAdd(counters + 1, 1ull)] = int(i); // the exact predicate decides on the host
+}
+
+bool has_intersections(ipcb_ctx* ctx, double inflation_radius)
+{
+    broad_build(ctx, false, inflation_radius);
+    PairList& pl = ctx->detected[IPCB_EF];
+    broad_detect(ctx, IPCB_EF, pl);
+    const int64_t n = pl.count;
+    if (n == 0) return false;
+    cudaStream_t s = ctx->stream;
+    unsigned long long* cnt = ctx->dCounters.p + 20;
+    IPCB_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), s));
+    ctx->hsel.reserve(size_t(n));
+    k_edge_face_intersect<<<grid_for(n, 256), 256, 0, s>>>(n, pl.pairs.p, ctx->dE.p, ctx->dF.p, ctx->X0.p, cnt, ctx->hsel.p);
+    ctx->launches++;
+    IPCB_CUDA(cudaGetLastError());
+    unsigned long long h[2];
+    IPCB_CUDA(cudaMemcpyAsync(h, cnt, sizeof h, cudaMemcpyDeviceToHost, s));
+    IPCB_CUDA(cudaStreamSynchronize(s));
+    if (h[0] > 0) return true;
+    if (h[1] == 0) return false;
+    // undecided orientations: exact predicate on the host
+    std::vector<int> idx(h[1]);
+    IPCB_CUDA(cudaMemcpyAsync(idx.data(), ctx->hsel.p, sizeof(int) * h[1], cudaMemcpyDeviceToHost, s));
+    std::vector<double4> X(size_t(ctx->nV));
+    IPCB_CUDA(cudaMemcpyAsync(X.data(), ctx->X0.p, sizeof(double4) * size_t(ctx->nV), cudaMemcpyDeviceToHost, s));
+    std::vector<int2> pairs(static_cast<size_t>(n));
+    IPCB_CUDA(cudaMemcpyAsync(pairs.data(), pl.pairs.p, sizeof(int2) * size_t(n), cudaMemcpyDeviceToHost, s));
+    IPCB_CUDA(cudaStreamSynchronize(s));
+    auto P = [&](int v) { return mk3(X[size_t(v)].x, X[size_t(v)].y, X[size_t(v)].z); };
+    for (int i : idx) {
+        const int2 c = pairs[size_t(i)];
+        const int ev[2] = { ctx->hE[2 * size_t(c.x)], ctx->hE[2 * size_t(c.x) + 1] };
+        const int fv[3] = { ctx->hF[3 * size_t(c.y)], ctx->hF[3 * size_t(c.y) + 1], ctx->hF[3 * size_t(c.y) + 2] };
+        const d3 e0 = P(ev[0]), e1 = P(ev[1]), t0 = P(fv[0]), t1 = P(fv[1]), t2 = P(fv[2]);
+        const int o1 = ipcb_exact::orient3d_sign(&t0.x, &t1.x, &t2.x, &e0.x), o2 = ipcb_exact::orient3d_sign(&t0.x, &t1.x, &t2.x, &e1.x);
+        if (o1 != 0 && o2 != 0 && o1 == o2) continue;
+        if (edge_triangle_solve(e0, e1, t0, t1, t2)) return true;
+    }
+    return false;
 }
 
 // sort pairs lexicographically (canonical order for fetch / parity checks)

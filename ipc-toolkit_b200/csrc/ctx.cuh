@@ -270,6 +270,7 @@ bool candidates_build(ipcb_ctx* ctx, bool swept, double inflation_radius, bool a
 size_t max_pairs();
 unsigned long long traverse_chunk(ipcb_ctx* ctx, int kind, int qb, int qe, int* range);
 void sort_pairs(ipcb_ctx* ctx, PairList& pl);
+bool has_intersections(ipcb_ctx* ctx, double inflation_radius);
 
 // collisions (collisions.cu)
 void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags);

@@ -1376,6 +1376,197 @@ int ipco_barrier_hessian_fetch(ipcb_ctx* ctx, int32_t* outer, int32_t* inner, do
     return 0;
 }
 
+// ---- ipc::has_intersections (ipc.cpp:105-166), 3D ------------------------------------------------------------------
+// exact orientation by rational-free expansion arithmetic is overkill for a checker: long double products of the
+// determinant are NOT exact, so the checker decides the sign with exact integer arithmetic on the doubles' binary
+// representation (every double is m * 2^e; the determinant's monomials are brought to a common exponent and summed in
+// arbitrary precision).
+namespace {
+struct Big { // signed arbitrary-precision integer, little-endian base 2^32 magnitude
+    std::vector<uint32_t> mag;
+    int sign = 0;
+};
+Big big_from(uint64_t v, int sign)
+{
+    Big b;
+    if (v == 0 || sign == 0) return b;
+    b.sign = sign;
+    b.mag = { uint32_t(v), uint32_t(v >> 32) };
+    while (!b.mag.empty() && b.mag.back() == 0) b.mag.pop_back();
+    return b;
+}
+Big big_mul(const Big& a, const Big& b)
+{
+    Big r;
+    if (a.sign == 0 || b.sign == 0) return r;
+    r.sign = a.sign * b.sign;
+    r.mag.assign(a.mag.size() + b.mag.size(), 0);
+    for (size_t i = 0; i < a.mag.size(); i++) {
+        uint64_t carry = 0;
+        for (size_t j = 0; j < b.mag.size() || carry; j++) {
+            uint64_t cur = r.mag[i + j] + carry + (j < b.mag.size() ? uint64_t(a.mag[i]) * b.mag[j] : 0);
+            r.mag[i + j] = uint32_t(cur);
+            carry = cur >> 32;
+        }
+    }
+    while (!r.mag.empty() && r.mag.back() == 0) r.mag.pop_back();
+    return r;
+}
+Big big_shl(const Big& a, int bits)
+{
+    Big r;
+    if (a.sign == 0) return r;
+    r.sign = a.sign;
+    r.mag.assign(a.mag.size() + size_t(bits / 32) + 1, 0);
+    const int w = bits / 32, s = bits % 32;
+    for (size_t i = 0; i < a.mag.size(); i++) {
+        const uint64_t v = uint64_t(a.mag[i]) << s;
+        r.mag[i + w] |= uint32_t(v);
+        r.mag[i + w + 1] |= uint32_t(v >> 32);
+    }
+    while (!r.mag.empty() && r.mag.back() == 0) r.mag.pop_back();
+    return r;
+}
+int big_cmp_mag(const Big& a, const Big& b)
+{
+    if (a.mag.size() != b.mag.size()) return a.mag.size() < b.mag.size() ? -1 : 1;
+    for (size_t i = a.mag.size(); i-- > 0;)
+        if (a.mag[i] != b.mag[i]) return a.mag[i] < b.mag[i] ? -1 : 1;
+    return 0;
+}
+Big big_add(const Big& a, const Big& b)
+{
+    if (a.sign == 0) return b;
+    if (b.sign == 0) return a;
+    Big r;
+    if (a.sign == b.sign) {
+        r.sign = a.sign;
+        r.mag.assign(std::max(a.mag.size(), b.mag.size()) + 1, 0);
+        uint64_t carry = 0;
+        for (size_t i = 0; i < r.mag.size(); i++) {
+            const uint64_t cur = carry + (i < a.mag.size() ? a.mag[i] : 0) + (i < b.mag.size() ? b.mag[i] : 0);
+            r.mag[i] = uint32_t(cur);
+            carry = cur >> 32;
+        }
+    } else {
+        const int c = big_cmp_mag(a, b);
+        if (c == 0) return r;
+        const Big& hi = c > 0 ? a : b;
+        const Big& lo = c > 0 ? b : a;
+        r.sign = hi.sign;
+        r.mag.assign(hi.mag.size(), 0);
+        int64_t borrow = 0;
+        for (size_t i = 0; i < hi.mag.size(); i++) {
+            int64_t cur = int64_t(hi.mag[i]) - borrow - (i < lo.mag.size() ? int64_t(lo.mag[i]) : 0);
+            borrow = cur < 0;
+            if (cur < 0) cur += (int64_t(1) << 32);
+            r.mag[i] = uint32_t(cur);
+        }
+    }
+    while (!r.mag.empty() && r.mag.back() == 0) r.mag.pop_back();
+    return r;
+}
+// exact sign of det [a - d; b - d; c - d]
+int orient3d_exact(const V3& a, const V3& b, const V3& c, const V3& d)
+{
+    // every coordinate as integer mantissa * 2^exp with a common exponent
+    const double* pts[4] = { &a.x, &b.x, &c.x, &d.x };
+    int emin = 100000;
+    for (int p = 0; p < 4; p++)
+        for (int k = 0; k < 3; k++) {
+            if (pts[p][k] == 0) continue;
+            int e;
+            std::frexp(pts[p][k], &e);
+            emin = std::min(emin, e - 53);
+        }
+    if (emin == 100000) return 0;
+    Big I[4][3];
+    for (int p = 0; p < 4; p++)
+        for (int k = 0; k < 3; k++) {
+            const double v = pts[p][k];
+            if (v == 0) continue;
+            int e;
+            const double m = std::frexp(std::abs(v), &e); // v = m 2^e, m in [0.5, 1)
+            const uint64_t mant = uint64_t(std::ldexp(m, 53));
+            I[p][k] = big_shl(big_from(mant, v < 0 ? -1 : 1), (e - 53) - emin);
+        }
+    auto sub = [](const Big& x, const Big& y) {
+        Big ny = y;
+        ny.sign = -ny.sign;
+        return big_add(x, ny);
+    };
+    Big m[3][3];
+    for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 3; k++) m[r][k] = sub(I[r][k], I[3][k]);
+    auto det2 = [&](int r0, int r1, int c0, int c1) { return sub(big_mul(m[r0][c0], m[r1][c1]), big_mul(m[r0][c1], m[r1][c0])); };
+    Big det = big_mul(m[0][0], det2(1, 2, 1, 2));
+    det = sub(det, big_mul(m[0][1], det2(1, 2, 0, 2)));
+    det = big_add(det, big_mul(m[0][2], det2(1, 2, 0, 1)));
+    return det.sign;
+}
+// geometry/intersection.cpp:115-145 (the LU solve in double like the default build of the reference)
+bool edge_intersects_triangle(const V3& e0, const V3& e1, const V3& t0, const V3& t1, const V3& t2)
+{
+    const int o1 = orient3d_exact(t0, t1, t2, e0), o2 = orient3d_exact(t0, t1, t2, e1);
+    if (o1 != 0 && o2 != 0 && o1 == o2) return false;
+    double M[3][3] = { { t1.x - t0.x, t2.x - t0.x, e0.x - e1.x }, { t1.y - t0.y, t2.y - t0.y, e0.y - e1.y }, { t1.z - t0.z, t2.z - t0.z, e0.z - e1.z } };
+    double b[3] = { e0.x - t0.x, e0.y - t0.y, e0.z - t0.z };
+    int perm[3] = { 0, 1, 2 }, rank = 3;
+    for (int k = 0; k < 3; k++) { // Eigen::FullPivLU
+        int pr = k, pc = k;
+        double best = 0;
+        for (int i = k; i < 3; i++)
+            for (int j = k; j < 3; j++)
+                if (std::abs(M[i][j]) > best) best = std::abs(M[i][j]), pr = i, pc = j;
+        if (best == 0) {
+            rank = k;
+            break;
+        }
+        for (int j = 0; j < 3; j++) std::swap(M[k][j], M[pr][j]);
+        std::swap(b[k], b[pr]);
+        for (int i = 0; i < 3; i++) std::swap(M[i][k], M[i][pc]);
+        std::swap(perm[k], perm[pc]);
+        for (int i = k + 1; i < 3; i++) {
+            const double l = M[i][k] / M[k][k];
+            for (int j = k + 1; j < 3; j++) M[i][j] -= l * M[k][j];
+            b[i] -= l * b[k];
+        }
+    }
+    double y[3] = { 0, 0, 0 }, uvt[3] = { 0, 0, 0 };
+    for (int k = rank - 1; k >= 0; k--) {
+        double acc = b[k];
+        for (int j = k + 1; j < rank; j++) acc -= M[k][j] * y[j];
+        y[k] = acc / M[k][k];
+    }
+    for (int k = 0; k < 3; k++) uvt[perm[k]] = y[k];
+    return uvt[0] >= 0.0 && uvt[1] >= 0.0 && uvt[0] + uvt[1] <= 1.0 && uvt[2] >= 0.0 && uvt[2] <= 1.0;
+}
+} // namespace
+int ipco_has_intersections(ipcb_ctx* ctx, const double* Vp, int32_t ld, int32_t* result)
+{
+    const auto V = load_vertices(ctx->nV, Vp, ld);
+    double ext[3] = { 0, 0, 0 };
+    for (int k = 0; k < 3; k++) {
+        double lo = INFINITY, hi = -INFINITY;
+        for (const V3& v : V) lo = std::min(lo, v[k]), hi = std::max(hi, v[k]);
+        ext[k] = V.empty() ? 0.0 : hi - lo;
+    }
+    const double r = 1e-6 * std::sqrt((ext[0] * ext[0] + ext[1] * ext[1]) + ext[2] * ext[2]); // ipc.cpp:120-121
+    build_boxes(ctx, V, nullptr, r, IPCB_BOXES_FLOAT);
+    std::vector<Pair> ef;
+    broad_detect_kind(ctx, IPCB_EF, ef);
+    *result = 0;
+    for (const Pair& p : ef) {
+        const int32_t* e = &ctx->E[2 * size_t(p[0])];
+        const int32_t* f = &ctx->F[3 * size_t(p[1])];
+        if (edge_intersects_triangle(V[e[0]], V[e[1]], V[f[0]], V[f[1]], V[f[2]])) {
+            *result = 1;
+            break;
+        }
+    }
+    return 0;
+}
+
 // ---- friction ------------------------------------------------------------------------------
 // TangentialCollisions::build(mesh, vertices, collisions, normal_potential, mu_s, mu_k) (tangential_collisions.cpp:62-171)
 // from the RESIDENT normal collision set
