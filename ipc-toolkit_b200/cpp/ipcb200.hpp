@@ -117,6 +117,8 @@ public:
     std::vector<double> vertex_areas() const { return areas().first; }
     std::vector<double> edge_areas() const { return areas().second; }
     ipcb_ctx* ctx() const { return m_ctx.get(); }
+    /// the NormalCollisions whose records are the context's resident set (several sets may exist per mesh; see NormalCollisions)
+    mutable const void* resident_collisions = nullptr;
 
 private:
     std::pair<std::vector<double>, std::vector<double>> areas() const
@@ -235,7 +237,10 @@ private:
     mutable bool m_fetched[4] = { false, false, false, false };
 };
 
-// collisions/normal/normal_collisions.hpp — IPC collision set type
+// collisions/normal/normal_collisions.hpp — IPC collision set type.
+// The reference's NormalCollisions are plain containers: any number may exist per mesh.  The context works on ONE
+// resident set, so every object here owns a collision-set object of the library (ipcb_collision_set) and is swapped in
+// (ipcb_collisions_swap, O(1)) when it is used; the previous owner's records are parked in ITS object first.
 class NormalCollisions {
 public:
     struct Records { // one typed vector of the reference, struct-of-arrays
@@ -243,23 +248,34 @@ public:
         std::vector<double> weight, eps_x;
         std::vector<uint8_t> dtype;
     };
+    NormalCollisions() = default;
+    NormalCollisions(const NormalCollisions&) = delete;
+    NormalCollisions& operator=(const NormalCollisions&) = delete;
+    ~NormalCollisions()
+    {
+        if (m_mesh && m_mesh->resident_collisions == this) m_mesh->resident_collisions = nullptr;
+        if (m_set) ipcb_collision_set_destroy(m_set);
+    }
     void set_use_area_weighting(bool v) { m_area = v; }
     bool use_area_weighting() const { return m_area; }
     void build(const CollisionMesh& mesh, MatrixXd vertices, double dhat, double dmin = 0)
     {
+        claim(mesh);
         check(ipcb_collisions_build(mesh.ctx(), vertices.data, vertices.ld, dhat, dmin, m_area ? IPCB_USE_AREA_WEIGHTING : 0, m_counts));
-        m_mesh = &mesh;
+        m_built = true;
     }
     void build(const Candidates&, const CollisionMesh& mesh, MatrixXd vertices, double dhat, double dmin = 0)
     {
+        claim(mesh);
         check(ipcb_collisions_build_from_candidates(mesh.ctx(), vertices.data, vertices.ld, dhat, dmin, m_area ? IPCB_USE_AREA_WEIGHTING : 0, m_counts));
-        m_mesh = &mesh;
+        m_built = true;
     }
     size_t size() const { return size_t(m_counts[0] + m_counts[1] + m_counts[2] + m_counts[3]); }
     bool empty() const { return size() == 0; }
     size_t count(int kind) const { return size_t(m_counts[kind]); }
     Records records(int kind) const
     {
+        make_resident();
         Records r;
         const size_t n = count(kind);
         r.ids.resize(n), r.weight.resize(n), r.eps_x.resize(n), r.dtype.resize(n);
@@ -268,6 +284,7 @@ public:
     }
     double compute_minimum_distance(const CollisionMesh& mesh, MatrixXd vertices) const
     {
+        make_resident();
         double d;
         check(ipcb_collisions_min_distance(mesh.ctx(), vertices.data, vertices.ld, &d));
         return d;
@@ -277,6 +294,7 @@ public:
     /// `builders[b][kind]`; disjoint_shards promises builders over disjoint candidate shards (ranks of a sharded build).
     void assign(const CollisionMesh& mesh, const std::vector<std::array<Records, 4>>& builders, double dmin = 0, bool disjoint_shards = false)
     {
+        claim(mesh);
         check(ipcb_collisions_clear(mesh.ctx()));
         for (const auto& b : builders)
             for (int kind = 0; kind < 4; kind++) {
@@ -286,13 +304,45 @@ public:
                                              kind == IPCB_EE ? r.eps_x.data() : nullptr, kind == IPCB_EE ? r.dtype.data() : nullptr));
             }
         check(ipcb_collisions_merge(mesh.ctx(), dmin, disjoint_shards ? IPCB_MERGE_DISJOINT_SHARDS : 0, m_counts));
-        m_mesh = &mesh;
+        m_built = true;
+    }
+    /// make this set the resident one of its mesh (the potentials call it before they evaluate)
+    void make_resident() const
+    {
+        if (!m_mesh || !m_built) throw std::runtime_error("NormalCollisions has not been built");
+        if (m_mesh->resident_collisions == this) return;
+        park_resident(*m_mesh);
+        int64_t counts[4];
+        check(ipcb_collisions_swap(m_mesh->ctx(), handle(), counts)); // this set's records become resident
+        m_mesh->resident_collisions = this;
     }
 
 private:
+    ipcb_collision_set* handle() const
+    {
+        if (!m_set) check(ipcb_collision_set_create(m_mesh->ctx(), &m_set));
+        return m_set;
+    }
+    static void park_resident(const CollisionMesh& mesh)
+    {
+        if (auto* owner = static_cast<const NormalCollisions*>(mesh.resident_collisions)) {
+            int64_t counts[4];
+            check(ipcb_collisions_swap(mesh.ctx(), owner->handle(), counts)); // the owner's records move into its object
+        }
+        mesh.resident_collisions = nullptr;
+    }
+    // before this object (re)builds on `mesh`: another set's records leave the context, this one becomes the owner
+    void claim(const CollisionMesh& mesh)
+    {
+        if (m_mesh && m_mesh != &mesh) throw std::runtime_error("a NormalCollisions object cannot move to another mesh");
+        m_mesh = &mesh;
+        if (mesh.resident_collisions != this) park_resident(mesh);
+        mesh.resident_collisions = this;
+    }
     const CollisionMesh* m_mesh = nullptr;
+    mutable ipcb_collision_set* m_set = nullptr;
     int64_t m_counts[4] = { 0, 0, 0, 0 };
-    bool m_area = false;
+    bool m_area = false, m_built = false;
 };
 
 // Eigen::SparseMatrix<double> in compressed-column form (== compressed rows of the symmetric matrix)
@@ -313,21 +363,24 @@ public:
     double dhat() const { return m_bp.dhat; }
     double stiffness() const { return m_bp.stiffness; }
     bool use_physical_barrier() const { return m_bp.use_physical_barrier != 0; }
-    double operator()(const NormalCollisions&, const CollisionMesh& mesh, MatrixXd X) const
+    double operator()(const NormalCollisions& c, const CollisionMesh& mesh, MatrixXd X) const
     {
+        c.make_resident();
         double e;
         check(ipcb_barrier_energy(mesh.ctx(), X.data, X.ld, &m_bp, &e));
         return e;
     }
-    std::vector<double> gradient(const NormalCollisions&, const CollisionMesh& mesh, MatrixXd X) const
+    std::vector<double> gradient(const NormalCollisions& c, const CollisionMesh& mesh, MatrixXd X) const
     {
+        c.make_resident();
         std::vector<double> g(mesh.ndof());
         check(ipcb_barrier_gradient(mesh.ctx(), X.data, X.ld, &m_bp, g.data()));
         return g;
     }
-    SparseMatrix hessian(const NormalCollisions&, const CollisionMesh& mesh, MatrixXd X,
+    SparseMatrix hessian(const NormalCollisions& c, const CollisionMesh& mesh, MatrixXd X,
                          PSDProjectionMethod project_hessian_to_psd = PSDProjectionMethod::NONE) const
     {
+        c.make_resident();
         int64_t nnz = 0;
         check(ipcb_barrier_hessian(mesh.ctx(), X.data, X.ld, &m_bp, int(project_hessian_to_psd), &nnz));
         SparseMatrix H;
@@ -340,6 +393,86 @@ public:
 private:
     ipcb_barrier_params m_bp;
 };
+
+// collisions/tangential/tangential_collisions.hpp — the lagged tangential set of the mesh's context (isotropic coefficients)
+class TangentialCollisions {
+public:
+    struct Records {
+        std::vector<Pair> ids;
+        std::vector<double> weight, normal_force_magnitude, mu_s, mu_k;
+        std::vector<std::array<double, 2>> closest_point;
+        std::vector<std::array<double, 6>> tangent_basis; // column 0, column 1
+    };
+    /// build(mesh, vertices, collisions, normal_potential, mu_s, mu_k) — tangential_collisions.cpp:62-171; per-vertex coefficients
+    void build(const CollisionMesh& mesh, MatrixXd vertices, const NormalCollisions& collisions, const BarrierPotential& normal_potential,
+               const std::vector<double>& mu_s, const std::vector<double>& mu_k)
+    {
+        collisions.make_resident();
+        if (mu_s.size() != mesh.num_vertices() || mu_k.size() != mesh.num_vertices()) throw std::invalid_argument("one coefficient per vertex");
+        const ipcb_barrier_params bp { normal_potential.dhat(), normal_potential.stiffness(), normal_potential.use_physical_barrier() ? 1 : 0 };
+        check(ipcb_tangential_build(mesh.ctx(), vertices.data, vertices.ld, &bp, mu_s.data(), mu_k.data(), m_counts));
+        m_mesh = &mesh;
+    }
+    size_t size() const { return size_t(m_counts[0] + m_counts[1] + m_counts[2] + m_counts[3]); }
+    bool empty() const { return size() == 0; }
+    size_t count(int kind) const { return size_t(m_counts[kind]); }
+    Records records(int kind) const
+    {
+        Records r;
+        const size_t n = count(kind);
+        r.ids.resize(n), r.weight.resize(n), r.normal_force_magnitude.resize(n), r.mu_s.resize(n), r.mu_k.resize(n);
+        r.closest_point.resize(n), r.tangent_basis.resize(n);
+        if (n)
+            check(ipcb_tangential_fetch(m_mesh->ctx(), kind, r.ids[0].data(), r.weight.data(), r.normal_force_magnitude.data(), r.mu_s.data(),
+                                        r.mu_k.data(), r.closest_point[0].data(), r.tangent_basis[0].data()));
+        return r;
+    }
+
+private:
+    const CollisionMesh* m_mesh = nullptr;
+    int64_t m_counts[4] = { 0, 0, 0, 0 };
+};
+
+// potentials/friction_potential.hpp
+class FrictionPotential {
+public:
+    explicit FrictionPotential(double eps_v) : m_eps_v(eps_v) { }
+    double eps_v() const { return m_eps_v; }
+    double operator()(const TangentialCollisions&, const CollisionMesh& mesh, MatrixXd velocities) const
+    {
+        double e;
+        check(ipcb_friction_energy(mesh.ctx(), velocities.data, velocities.ld, m_eps_v, &e));
+        return e;
+    }
+    std::vector<double> gradient(const TangentialCollisions&, const CollisionMesh& mesh, MatrixXd velocities) const
+    {
+        std::vector<double> g(mesh.ndof());
+        check(ipcb_friction_gradient(mesh.ctx(), velocities.data, velocities.ld, m_eps_v, g.data()));
+        return g;
+    }
+    SparseMatrix hessian(const TangentialCollisions&, const CollisionMesh& mesh, MatrixXd velocities,
+                         PSDProjectionMethod project_hessian_to_psd = PSDProjectionMethod::NONE) const
+    {
+        int64_t nnz = 0;
+        check(ipcb_friction_hessian(mesh.ctx(), velocities.data, velocities.ld, m_eps_v, int(project_hessian_to_psd), &nnz));
+        SparseMatrix H;
+        H.rows = H.cols = index_t(mesh.ndof());
+        H.outer.resize(mesh.ndof() + 1), H.inner.resize(size_t(nnz)), H.values.resize(size_t(nnz));
+        check(ipcb_barrier_hessian_fetch(mesh.ctx(), H.outer.data(), H.inner.data(), H.values.data()));
+        return H;
+    }
+
+private:
+    double m_eps_v;
+};
+
+// ipc.hpp / ipc.cpp:105-166 (3D)
+inline bool has_intersections(const CollisionMesh& mesh, MatrixXd vertices)
+{
+    int32_t r = 0;
+    check(ipcb_has_intersections(mesh.ctx(), vertices.data, vertices.ld, &r));
+    return r != 0;
+}
 
 // ipc.hpp:45-51 / ipc.cpp:45-101
 inline double compute_collision_free_stepsize(const CollisionMesh& mesh, MatrixXd vertices_t0, MatrixXd vertices_t1, double min_distance = 0.0,
