@@ -26,6 +26,7 @@
 #include "geom.cuh"
 #include <cub/device/device_radix_sort.cuh>
 #include <cfloat>
+#include <climits>
 #include <algorithm>
 #include <cstdlib>
 
@@ -450,6 +451,37 @@ __global__ void k_karras_boxes(int n, const unsigned long long* __restrict__ key
     nodes[i] = nd;
 }
 
+// 4-wide collapse: node i takes the children of its two children (a leaf child stays as it is)
+__global__ void k_collapse4(int n, const Node* __restrict__ nodes, Node4* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const Node nd = nodes[i];
+    Node4 w;
+    int cnt = 0;
+    auto put = [&](const float* lo, const float* hi, int child, int last) {
+        w.lox[cnt] = lo[0], w.loy[cnt] = lo[1], w.loz[cnt] = lo[2], w.hix[cnt] = hi[0], w.hiy[cnt] = hi[1], w.hiz[cnt] = hi[2];
+        w.child[cnt] = child, w.last[cnt] = last;
+        cnt++;
+    };
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int ch = nd.child[side];
+        if (ch < 0) {
+            put(nd.lo[side], nd.hi[side], ch, side == 0 ? nd.split : nd.last);
+        } else {
+            const Node k = nodes[ch];
+            put(k.lo[0], k.hi[0], k.child[0], k.split);
+            put(k.lo[1], k.hi[1], k.child[1], k.last);
+        }
+    }
+    for (; cnt < 4; cnt++) {
+        w.lox[cnt] = w.loy[cnt] = w.loz[cnt] = INFINITY, w.hix[cnt] = w.hiy[cnt] = w.hiz[cnt] = -INFINITY;
+        w.child[cnt] = INT_MIN, w.last[cnt] = -1;
+    }
+    out[i] = w;
+}
+
 // Morton resolution per axis.  The candidate SET does not depend on the tree (SURVEY §7 hard part 1), only the
 // traversal cost does, so the keys only need enough cells to separate neighbouring primitives: 10 bits per axis
 // (4 radix passes) up to 4M primitives, 13 (5 passes) up to 64M, the reference's 21 (8 passes) beyond.
@@ -512,6 +544,14 @@ static void build_tree(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, bool with_node
     k_karras_boxes<<<grid_for(n - 1, 256), 256, 0, s>>>(n, t.key_sorted.p, t.nodes.p, q);
     ctx->launches += 5;
     t.has_nodes = true;
+    static const bool wide = getenv("IPCB_BVH4") != nullptr; // A/B: 4-wide traversal (k_collapse4 + k_traverse4)
+    t.has_nodes4 = false;
+    if (wide) {
+        t.nodes4.reserve(n - 1);
+        k_collapse4<<<grid_for(n - 1, 256), 256, 0, s>>>(n, t.nodes.p, t.nodes4.p);
+        ctx->launches++;
+        t.has_nodes4 = true;
+    }
 }
 
 __global__ void k_axis_key(int n, int axis, const FBox* __restrict__ box, unsigned long long* __restrict__ key, int* __restrict__ ord);
@@ -732,6 +772,102 @@ __global__ void __launch_bounds__(TRAV_BLOCK)
     }
 }
 
+// 4-wide traversal: the same walk over Node4 (collapsed hierarchy): one 128-byte line per visit, up to four box tests, up to
+// four leaf hits (pipelined like above), up to three deferred subtrees.
+template <int MODE, int QN, int TN, bool FILTERED>
+__global__ void __launch_bounds__(TRAV_BLOCK)
+    k_traverse4(int q_begin, int q_end, const FBox* __restrict__ qbox, const int4* __restrict__ qprim, const Node4* __restrict__ nodes,
+                int n_target, const int4* __restrict__ tprim, int2* __restrict__ out, unsigned long long* counter, unsigned long long capacity,
+                int flags, FilterView filter)
+{
+    __shared__ int2 stage[TRAV_BLOCK / 32][STAGE_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool check_shared = flags & 1;
+    const bool active = qi < q_end;
+    FBox q;
+    int4 qp = make_int4(-1, -1, -1, -1);
+    if (active) {
+        q = qbox[qi];
+        qp = qprim[qi];
+    }
+    int stack[128];
+    int sp = 0, node = 0, nstaged = 0;
+    bool walking = active && n_target > 1;
+    int pend[4] = { -1, -1, -1, -1 };
+    int4 tp[4];
+#pragma unroll
+    for (int h = 0; h < 4; h++) tp[h] = make_int4(0, 0, 0, 0);
+    while (__any_sync(0xffffffffu, walking || pend[0] >= 0 || pend[1] >= 0 || pend[2] >= 0 || pend[3] >= 0)) {
+        float4 lx, ly, lz, hx, hy, hz;
+        int4 ch = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN), la = make_int4(0, 0, 0, 0);
+        lx = ly = lz = hx = hy = hz = make_float4(0, 0, 0, 0);
+        if (walking) {
+            const float4* np = reinterpret_cast<const float4*>(nodes + node);
+            lx = __ldg(np), ly = __ldg(np + 1), lz = __ldg(np + 2), hx = __ldg(np + 3), hy = __ldg(np + 4), hz = __ldg(np + 5);
+            ch = __ldg(reinterpret_cast<const int4*>(np + 6)), la = __ldg(reinterpret_cast<const int4*>(np + 7));
+        }
+        if (__any_sync(0xffffffffu, pend[0] >= 0 || pend[1] >= 0 || pend[2] >= 0 || pend[3] >= 0)) {
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                bool emit = false;
+                int2 pr = make_int2(0, 0);
+                if (pend[h] >= 0 && (!check_shared || !shares_vertex<QN, TN>(qp, tp[h])) && (!FILTERED || any_can_collide<QN, TN>(filter, qp, tp[h]))) {
+                    emit = true;
+                    if (MODE == 0) pr = make_int2(qp.w, tp[h].w);
+                    else if (MODE == 1) pr = make_int2(tp[h].w, qp.w);
+                    else pr = make_int2(min(qp.w, tp[h].w), max(qp.w, tp[h].w));
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, emit);
+                if (m) {
+                    if (emit) stage[warp][nstaged + __popc(m & ((1u << lane) - 1))] = pr;
+                    nstaged += __popc(m);
+                }
+            }
+            if (nstaged > STAGE_CAP - 128) {
+                __syncwarp();
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(counter, (unsigned long long)nstaged);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                for (int k = lane; k < nstaged; k += 32)
+                    if (base + k < capacity) out[base + k] = stage[warp][k];
+                nstaged = 0;
+                __syncwarp();
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; h++) pend[h] = -1;
+        if (walking) {
+            const float clx[4] = { lx.x, lx.y, lx.z, lx.w }, cly[4] = { ly.x, ly.y, ly.z, ly.w }, clz[4] = { lz.x, lz.y, lz.z, lz.w };
+            const float chx[4] = { hx.x, hx.y, hx.z, hx.w }, chy[4] = { hy.x, hy.y, hy.z, hy.w }, chz[4] = { hz.x, hz.y, hz.z, hz.w };
+            const int cc[4] = { ch.x, ch.y, ch.z, ch.w }, cl[4] = { la.x, la.y, la.z, la.w };
+            int next = -1;
+#pragma unroll
+            for (int h = 0; h < 4; h++) {
+                bool ov = cc[h] != INT_MIN && q.lo[0] <= chx[h] && clx[h] <= q.hi[0] && q.lo[1] <= chy[h] && cly[h] <= q.hi[1] && q.lo[2] <= chz[h]
+                    && clz[h] <= q.hi[2];
+                if (MODE == 2) ov = ov && cl[h] > qi; // only leaves after the query in Morton order
+                if (ov && cc[h] < 0) pend[h] = ~cc[h], tp[h] = __ldg(tprim + pend[h]);
+                if (ov && cc[h] >= 0) {
+                    if (next < 0) next = cc[h];
+                    else stack[sp++] = cc[h];
+                }
+            }
+            if (next >= 0) node = next;
+            else if (sp > 0) node = stack[--sp];
+            else walking = false;
+        }
+    }
+    if (nstaged > 0) {
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(counter, (unsigned long long)nstaged);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int k = lane; k < nstaged; k += 32)
+            if (base + k < capacity) out[base + k] = stage[warp][k];
+    }
+}
+
 // ---------------------------------------------------------------------------
 // Sweep and prune (north_star subsystem 1; reference semantics broad_phase/sweep_and_prune.cpp:106-119, GPU route
 // sweep_and_tiniest_queue.cu:121-212): the boxes are sorted by their lower bound along ONE axis (the longest scene
@@ -903,7 +1039,14 @@ struct TraverseJob {
             return;
         }
 #define IPCB_TRAVERSE(M, QN, TN)                                                                                                         \
-    if (flags & 2)                                                                                                                      \
+    if (t->has_nodes4 && t->n > 2) {                                                                                                    \
+        if (flags & 2)                                                                                                                  \
+            k_traverse4<M, QN, TN, true><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes4.p, t->n, t->sprim.p, \
+                                                                     out->pairs.p, counter, cap, flags, filter);                       \
+        else                                                                                                                            \
+            k_traverse4<M, QN, TN, false><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes4.p, t->n, t->sprim.p, \
+                                                                      out->pairs.p, counter, cap, flags, filter);                      \
+    } else if (flags & 2)                                                                                                                      \
         k_traverse<M, QN, TN, true><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes.p, t->n, t->sbox.p, t->sprim.p, \
                                                                 out->pairs.p, counter, cap, flags, filter);                             \
     else                                                                                                                                \

@@ -28,6 +28,16 @@ struct alignas(64) Node {
 };
 static_assert(sizeof(Node) == 64, "one node = one 64-byte fetch");
 
+// 4-wide node: the (up to) four grandchildren of a binary node in one 128-byte line — half the dependent fetches per
+// root-to-leaf path.  Boxes struct-of-arrays (one float4 per bound and axis); child as in Node, INT_MIN = empty slot;
+// last = last sorted leaf below the child (self-query pruning).
+struct alignas(128) Node4 {
+    float lox[4], loy[4], loz[4], hix[4], hiy[4], hiz[4];
+    int child[4];
+    int last[4];
+};
+static_assert(sizeof(Node4) == 128, "one 4-wide node = one 128-byte line");
+
 struct PrimSet {
     int n = 0;
     Buf<FBox> box;
@@ -43,6 +53,8 @@ struct Tree {
     Buf<FBox> sbox;
     Buf<int4> sprim;
     Buf<Node> nodes;
+    Buf<Node4> nodes4; // collapsed 4-wide hierarchy (one per binary node; the traversal only visits every other level)
+    bool has_nodes4 = false;
     Buf<FBox> rmq;   // range-union tables over the sorted leaf boxes (node boxes without a bottom-up pass)
     Buf<int> parent; // [0,n-1) internal nodes, [n-1,2n-1) leaves (bottom-up refit only)
     Buf<int> flag;
