@@ -855,10 +855,125 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
 
 constexpr int BIG_THREADS = 256;
 constexpr size_t BIG_SMEM = size_t(CTA_CAP) * (8 + 4 + 2);
+// ---- pass 1, block-wide hash path: the same scheme as column_symbolic_hash for a column with up to HB unique row
+// vertices and ANY number of items (a high-valence vertex inside a contact region: BASELINE config 2's sphere pole owns
+// 9 345 row blocks on 268 unique rows — sorting those items in global scratch took 2 ms, more than the rest of the
+// scene's symbolic pass).  Only the unique rows are sorted; items are placed chunk by chunk, warp after warp, so the
+// order inside every run is the incidence order (deterministic).
+constexpr int HB = 4096; // hash slots per block: 24 B each = 96 KB of the kernel's dynamic shared memory
+static_assert(size_t(HB) * 24 <= BIG_SMEM, "the block-wide hash table lives in the sort buffers");
+__device__ inline int hash_slot_big(int vi) { return int((unsigned(vi) * 2654435761u) >> 20); } // 12 bits
+__device__ inline bool column_symbolic_hash_cta(const SymArgs& A, int v, int t, char* smem, int* scan)
+{
+    unsigned long long* ukey = reinterpret_cast<unsigned long long*>(smem);
+    int* key = reinterpret_cast<int*>(smem + size_t(HB) * 8);
+    unsigned* msk = reinterpret_cast<unsigned*>(smem + size_t(HB) * 12);
+    int* cnt = reinterpret_cast<int*>(smem + size_t(HB) * 16);
+    int* base = reinterpret_cast<int*>(smem + size_t(HB) * 20);
+    __shared__ int nU;
+    const int s = A.colinc[v], e = A.colinc[v + 1];
+    const int2 bb = A.colb[v];
+    const int b1 = bb.x, b2 = bb.y;
+    for (int k = t; k < HB; k += BIG_THREADS) key[k] = -1, msk[k] = 0, cnt[k] = 0;
+    if (t == 0) nU = 0;
+    __syncthreads();
+    bool overflow = false;
+    for (int q = s + t; q < e; q += BIG_THREADS) {
+        const IncItems it = load_incidence(A, q, b1, b2);
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (b < it.np) {
+                int h = hash_slot_big(it.vi[b]), probe = 0;
+                for (; probe < HB; probe++) {
+                    const int old = atomicCAS(&key[h], -1, it.vi[b]);
+                    if (old == -1 || old == it.vi[b]) break;
+                    h = (h + 1) & (HB - 1);
+                }
+                if (probe == HB) overflow = true;
+                else atomicOr(&msk[h], unsigned(it.mk[b])), atomicAdd(&cnt[h], 1);
+            }
+    }
+    if (__syncthreads_or(overflow)) return false;
+    // unique row vertices (any order: sorted next)
+    for (int k = t; k < HB; k += BIG_THREADS)
+        if (key[k] != -1) ukey[atomicAdd(&nU, 1)] = ((unsigned long long)(unsigned)key[k] << 32) | unsigned(k);
+    __syncthreads();
+    const int U = nU;
+    int npow2 = 1;
+    while (npow2 < U) npow2 <<= 1;
+    for (int k = U + t; k < npow2; k += BIG_THREADS) ukey[k] = ~0ull;
+    __syncthreads();
+    bitonic_sort<BIG_THREADS>(ukey, npow2, t);
+    // run starts (thread t owns the contiguous unique rows [lo, hi)), descriptors, pattern counts
+    const int L = (U + BIG_THREADS - 1) / BIG_THREADS, lo = min(U, t * L), hi = min(U, lo + L);
+    int mine = 0;
+    for (int u = lo; u < hi; u++) mine += cnt[unsigned(ukey[u])];
+    scan[t] = mine;
+    __syncthreads();
+    int start = 0;
+    for (int k = 0; k < t; k++) start += scan[k];
+    const int ioff = A.itemoff[v];
+    int c0 = 0, c1 = 0, c2 = 0;
+    for (int u = lo; u < hi; u++) {
+        const int slot = int(unsigned(ukey[u]));
+        base[slot] = start;
+        A.udesc[ioff + u] = make_int2(start, int(unsigned(ukey[u] >> 32)));
+        start += cnt[slot];
+        const unsigned mk = msk[slot];
+        c0 += __popc(mk & 0x49u), c1 += __popc(mk & 0x92u), c2 += __popc(mk & 0x124u);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    __syncthreads(); // scan[] is reused for the block reduction
+    if ((t & 31) == 0) scan[3 * (t >> 5)] = c0, scan[3 * (t >> 5) + 1] = c1, scan[3 * (t >> 5) + 2] = c2;
+    __syncthreads();
+    if (t < 3) {
+        int sum = 0;
+        for (int w = 0; w < BIG_THREADS / 32; w++) sum += scan[3 * w + t];
+        A.cnt[3 * size_t(v) + t] = sum;
+    }
+    if (t == 0) A.colU[v] = U;
+    // stable placement: chunks of BIG_THREADS incidences in order, point by point, warp after warp
+    const int lane = t & 31, warp = t >> 5;
+    for (int q0 = s; q0 < e; q0 += BIG_THREADS) {
+        const int q = q0 + t;
+        IncItems it;
+        it.np = 0;
+        if (q < e) it = load_incidence(A, q, b1, b2);
+        for (int b = 0; b < 4; b++) {
+            int h = 0;
+            const bool valid = b < it.np;
+            if (valid) {
+                h = hash_slot_big(it.vi[b]);
+                while (key[h] != it.vi[b]) h = (h + 1) & (HB - 1);
+            }
+            for (int w = 0; w < BIG_THREADS / 32; w++) {
+                if (warp == w) {
+                    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+                    if (valid) {
+                        const unsigned peers = __match_any_sync(vm, h);
+                        const int rank = __popc(peers & ((1u << lane) - 1));
+                        const int pos = base[h];
+                        __syncwarp(vm);
+                        if (rank == 0) base[h] = pos + __popc(peers);
+                        A.sref[ioff + pos + rank] = block_ref(A, it, b);
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    return true;
+}
+
 // columns the warp kernel could not take: one block per column, looping over the list; columns beyond CTA_CAP
 // sort in a per-block global scratch region (need[0] reports the size required if it is too small)
 __global__ void __launch_bounds__(BIG_THREADS)
-    k_hess_symbolic_big(SymArgs A, int cta_cap, const int* __restrict__ big, const unsigned long long* nbig, char* scratch,
+    k_hess_symbolic_big(SymArgs A, int cta_cap, int use_hash, const int* __restrict__ big, const unsigned long long* nbig, char* scratch,
                         unsigned long long scratch_items, unsigned long long* need)
 {
     extern __shared__ __align__(16) char smem[];
@@ -867,6 +982,12 @@ __global__ void __launch_bounds__(BIG_THREADS)
     for (unsigned long long idx = blockIdx.x; idx < n; idx += gridDim.x) {
         const int v = big[idx];
         const int R = A.colR[v];
+        // columns the shared-memory sort cannot hold (and all of them under the test hook use_hash == 2): block-wide hash
+        if (use_hash && (R > cta_cap || use_hash == 2)) {
+            const bool done = column_symbolic_hash_cta(A, v, threadIdx.x, smem, scan);
+            __syncthreads();
+            if (done) continue;
+        }
         int npow2 = 1;
         while (npow2 < R) npow2 <<= 1;
         char* base = smem;
@@ -915,7 +1036,8 @@ template <int NUM_BATCH>
 __global__ void __launch_bounds__(32 * SYM_WARPS)
     k_hess_numeric(int nV, const int* __restrict__ colR, const int* __restrict__ colU, const int* __restrict__ itemoff,
                    const unsigned* __restrict__ sref, const int2* __restrict__ udesc, const double* __restrict__ blk,
-                   const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals, const int* __restrict__ order)
+                   const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals, const int* __restrict__ order,
+                   int big_items, int* __restrict__ big, unsigned long long* nbig)
 {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * SYM_WARPS + (threadIdx.x >> 5);
@@ -924,6 +1046,10 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
     const int U = colU[v];
     if (U == 0) return;
     const int R = colR[v], ioff = itemoff[v];
+    if (R > big_items) { // a giant column (high-valence vertex in contact): one block instead of one warp (k_hess_numeric_big)
+        if (lane == 0) big[atomicAdd(nbig, 1ull)] = v;
+        return;
+    }
     const int g = lane / 9, k = lane - 9 * g, l = k % 3, r = k / 3, kt = 3 * l + r; // kt: the same entry of the transposed block
     const bool lane_ok = g < 3;
     const unsigned colmask = 0x1249249u << l; // lanes of the same scalar column
@@ -964,6 +1090,100 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
         }
         base += __popc(pm);
         cur = nxt;
+    }
+}
+
+// giant columns: one block per column.  Phase 1: the 8 warps sum 24 unique blocks at a time (same 9-lanes-per-block layout and the
+// same item order as k_hess_numeric, so the values are bit-identical) into shared memory, with the 9-bit non-zero pattern of every
+// block; phase 2: positions inside the three scalar columns from a block-wide scan of the pattern counts, then the stores.
+// Columns with more than NUMERIC_UCAP unique blocks are processed in segments that carry the three running positions.
+constexpr int NUMERIC_UCAP = 1024;
+__global__ void __launch_bounds__(BIG_THREADS)
+    k_hess_numeric_big(const int* __restrict__ big, const unsigned long long* nbig, const int* __restrict__ colR, const int* __restrict__ colU,
+                       const int* __restrict__ itemoff, const unsigned* __restrict__ sref, const int2* __restrict__ udesc,
+                       const double* __restrict__ blk, const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals,
+                       int ucap)
+{
+    extern __shared__ __align__(16) char smem[];
+    double* acc_s = reinterpret_cast<double*>(smem);                                 // NUMERIC_UCAP x 9
+    unsigned short* pat = reinterpret_cast<unsigned short*>(acc_s + NUMERIC_UCAP * 9); // NUMERIC_UCAP
+    __shared__ int scan[3 * BIG_THREADS];
+    __shared__ int run_base[3];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int g = lane / 9, k = lane - 9 * g, l = k % 3, r = k / 3, kt = 3 * l + r;
+    const bool lane_ok = g < 3;
+    const unsigned long long n = *nbig;
+    for (unsigned long long idx = blockIdx.x; idx < n; idx += gridDim.x) {
+        const int v = big[idx];
+        const int U = colU[v], R = colR[v], ioff = itemoff[v];
+        const int2* ud = udesc + ioff;
+        const unsigned* sr = sref + ioff;
+        if (t < 3) run_base[t] = outer[3 * size_t(v) + t];
+        __syncthreads();
+        for (int seg = 0; seg < U; seg += ucap) {
+            const int nseg = min(ucap, U - seg);
+            for (int u0 = 3 * warp; u0 < nseg; u0 += 3 * (BIG_THREADS / 32)) {
+                const int u = seg + u0 + g;
+                double acc = 0.0;
+                bool nz = false;
+                const bool has = lane_ok && u0 + g < nseg;
+                if (has) {
+                    const int start = ud[u].x, len = (u + 1 < U ? ud[u + 1].x : R) - start;
+                    int j = 0;
+                    for (; j + 4 <= len; j += 4) { // four gathers in flight, added in item order
+                        const unsigned r0 = sr[start + j], r1 = sr[start + j + 1], r2 = sr[start + j + 2], r3 = sr[start + j + 3];
+                        const double w0 = __ldg(blk + size_t(r0 >> 1) * 9 + ((r0 & 1u) ? kt : k));
+                        const double w1 = __ldg(blk + size_t(r1 >> 1) * 9 + ((r1 & 1u) ? kt : k));
+                        const double w2 = __ldg(blk + size_t(r2 >> 1) * 9 + ((r2 & 1u) ? kt : k));
+                        const double w3 = __ldg(blk + size_t(r3 >> 1) * 9 + ((r3 & 1u) ? kt : k));
+                        acc += w0, acc += w1, acc += w2, acc += w3;
+                        nz |= (w0 != 0.0) | (w1 != 0.0) | (w2 != 0.0) | (w3 != 0.0);
+                    }
+                    for (; j < len; j++) {
+                        const unsigned ref = sr[start + j];
+                        const double w = __ldg(blk + size_t(ref >> 1) * 9 + ((ref & 1u) ? kt : k));
+                        acc += w;
+                        nz |= w != 0.0;
+                    }
+                    acc_s[(u0 + g) * 9 + k] = acc;
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, has && nz);
+                if (has && k == 0) pat[u0 + g] = (unsigned short)((pm >> (9 * g)) & 0x1ffu);
+            }
+            __syncthreads();
+            // entries per scalar column of the blocks thread t owns ([lo, hi) of the segment), then a serial prefix
+            const int L = (nseg + BIG_THREADS - 1) / BIG_THREADS, lo = min(nseg, t * L), hi = min(nseg, lo + L);
+            int c[3] = { 0, 0, 0 };
+            for (int u = lo; u < hi; u++) {
+                const unsigned m = pat[u];
+                c[0] += __popc(m & 0x49u), c[1] += __popc(m & 0x92u), c[2] += __popc(m & 0x124u);
+            }
+            scan[3 * t] = c[0], scan[3 * t + 1] = c[1], scan[3 * t + 2] = c[2];
+            __syncthreads();
+            int p[3] = { run_base[0], run_base[1], run_base[2] }, tot[3] = { 0, 0, 0 };
+            for (int q = 0; q < BIG_THREADS; q++)
+#pragma unroll
+                for (int x = 0; x < 3; x++) {
+                    const int cq = scan[3 * q + x];
+                    p[x] += q < t ? cq : 0;
+                    tot[x] += cq;
+                }
+            for (int u = lo; u < hi; u++) {
+                const unsigned m = pat[u];
+                const int row = ud[seg + u].y;
+#pragma unroll
+                for (int e = 0; e < 9; e++) // e = 3 r + l: rows ascend inside a scalar column
+                    if (m & (1u << e)) {
+                        const int x = e % 3;
+                        inner[p[x]] = 3 * row + e / 3;
+                        vals[p[x]] = acc_s[u * 9 + e];
+                        p[x]++;
+                    }
+            }
+            __syncthreads();
+            if (t < 3) run_base[t] += tot[t];
+            __syncthreads();
+        }
     }
 }
 
@@ -1140,6 +1360,7 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
                       { unsigned(blk0[0]), unsigned(blk0[1]), unsigned(blk0[2]) }, ctx->hsref.p, ctx->hudesc.p, ctx->hcolU.p, ctx->hcnt.p };
     if (!ctx->hess_attr_set) { // per device
         IPCB_CUDA(cudaFuncSetAttribute(k_hess_symbolic_big, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BIG_SMEM)));
+        IPCB_CUDA(cudaFuncSetAttribute(k_hess_numeric_big, cudaFuncAttributeMaxDynamicSharedMemorySize, int(NUMERIC_UCAP) * (72 + 2)));
         ctx->hess_attr_set = true;
     }
     // Morton order of the vertices from the last broad phase on this context (any permutation is valid)
@@ -1151,10 +1372,15 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
     if (const char* e = getenv("IPCB_HESS_WARP_CAP")) warp_cap = std::min(WARP_CAP, std::max(1, atoi(e)));
     if (const char* e = getenv("IPCB_HESS_CTA_CAP")) cta_cap = std::min(CTA_CAP, std::max(1, atoi(e)));
     const int use_hash = getenv("IPCB_HESS_NO_HASH") ? 0 : 1;
+    // block-wide hash for columns beyond the shared-memory sort; IPCB_HESS_BIG_HASH=0 disables it (the global-scratch sort then
+    // takes those columns), =2 sends every column of the block kernel through it (test hook)
+    int big_hash = use_hash;
+    if (const char* e = getenv("IPCB_HESS_BIG_HASH")) big_hash = atoi(e);
     for (int attempt = 0;; attempt++) {
         IPCB_CUDA(cudaMemsetAsync(nbig, 0, 2 * sizeof(unsigned long long), s));
         k_hess_symbolic<<<grid_for(size_t(nV) + 1, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(A, warp_cap, use_hash, ctx->hbig.p, nbig, order);
-        k_hess_symbolic_big<<<big_grid, BIG_THREADS, BIG_SMEM, s>>>(A, cta_cap, ctx->hbig.p, nbig, ctx->hscratch.p, ctx->hscratch_items, need);
+        k_hess_symbolic_big<<<big_grid, BIG_THREADS, BIG_SMEM, s>>>(A, cta_cap, big_hash, ctx->hbig.p, nbig, ctx->hscratch.p, ctx->hscratch_items,
+                                                                    need);
         ctx->launches += 2;
         // 4. scalar column pointers, nnz
         cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, b3, ctx->hcnt.p, ctx->outer.p, 3 * nV + 1, s);
@@ -1176,15 +1402,24 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
     const char* nb_env = getenv("IPCB_NUM_BATCH");
     const int nb = nb_env ? atoi(nb_env) : 12; // measured on C3: 2.43 ms (8), 2.24 ms (12)
     const unsigned ngrid = grid_for(nV, SYM_WARPS);
-    if (nb == 16)
-        k_hess_numeric<16><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,
-                                                           ctx->outer.p, ctx->inner.p, ctx->vals.p, order);
-    else if (nb == 12)
-        k_hess_numeric<12><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,
-                                                           ctx->outer.p, ctx->inner.p, ctx->vals.p, order);
-    else
-        k_hess_numeric<8><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,
-                                                          ctx->outer.p, ctx->inner.p, ctx->vals.p, order);
+    // columns with more items than this go to the block-per-column kernel (test hook: IPCB_HESS_NUMERIC_BIG lowers it)
+    int big_items = 4096;
+    if (const char* e = getenv("IPCB_HESS_NUMERIC_BIG")) big_items = std::max(1, atoi(e));
+    int ucap = NUMERIC_UCAP; // unique blocks per shared-memory segment (test hook: IPCB_HESS_NUMERIC_UCAP)
+    if (const char* e = getenv("IPCB_HESS_NUMERIC_UCAP")) ucap = std::min(NUMERIC_UCAP, std::max(3, atoi(e)));
+    unsigned long long* nbig2 = ctx->dCounters.p + 15;
+    IPCB_CUDA(cudaMemsetAsync(nbig2, 0, sizeof(unsigned long long), s));
+#define IPCB_NUMERIC(NB)                                                                                                                  \
+    k_hess_numeric<NB><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p, \
+                                                        ctx->outer.p, ctx->inner.p, ctx->vals.p, order, big_items, ctx->hbig.p, nbig2)
+    if (nb == 16) IPCB_NUMERIC(16);
+    else if (nb == 12) IPCB_NUMERIC(12);
+    else IPCB_NUMERIC(8);
+#undef IPCB_NUMERIC
+    constexpr size_t NUMERIC_SMEM = size_t(NUMERIC_UCAP) * (72 + 2);
+    k_hess_numeric_big<<<NUM_SMS, BIG_THREADS, NUMERIC_SMEM, s>>>(ctx->hbig.p, nbig2, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p,
+                                                                 ctx->hudesc.p, ctx->hblk.p, ctx->outer.p, ctx->inner.p, ctx->vals.p, ucap);
+    ctx->launches += 2;
     ctx->launches++;
     IPCB_CUDA(cudaGetLastError());
 }

@@ -138,10 +138,13 @@ def test_step_size(cuda, oracle, scenes, name):
     {"IPCB_HESS_NO_HASH": "1"},  # warp sort path, block path for columns beyond 512 row blocks
     {"IPCB_HESS_NO_HASH": "1", "IPCB_HESS_WARP_CAP": "64"},  # most columns on the block-per-column kernel
     {"IPCB_HESS_NO_HASH": "1", "IPCB_HESS_WARP_CAP": "32", "IPCB_HESS_CTA_CAP": "128"},  # ... sorting in global scratch
+    {"IPCB_HESS_NO_HASH": "1", "IPCB_HESS_WARP_CAP": "32", "IPCB_HESS_BIG_HASH": "2"},  # ... block-wide hash (giant columns)
+    {"IPCB_HESS_NUMERIC_BIG": "40"},  # numeric pass: most columns on the block-per-column kernel
+    {"IPCB_HESS_NUMERIC_BIG": "40", "IPCB_HESS_NUMERIC_UCAP": "7"},  # ... in several shared-memory segments per column
 ])
 def test_hessian_column_paths(cuda, oracle, scenes, hooks, monkeypatch):
     """Hessian assembly: every per-column path (hash de-duplication in one warp, warp sort, block-per-column sort in
-    shared memory, block sort in global scratch) must produce the oracle's matrix"""
+    shared memory, block sort in global scratch, block-wide hash de-duplication) must produce the oracle's matrix"""
     V0, V1, E, F, P = scenes.dense_sheet(14, 6.0)
     for k, v in hooks.items():
         monkeypatch.setenv(k, v)
