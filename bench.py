@@ -518,10 +518,10 @@ def main():
                                                                       "T FP64 thread-inst/s", r["fp64"]["issue_frac"])
         return r
 
+    tri = (3, 6, 10, 10)
     # local Hessians: per collision 24 B record + 32 B per stencil point in; 16 B ids + 32 B masks + 8 B per incidence +
     # 72 B per stored (upper-triangular) 3x3 block out.  FP64: FLOPS_HFAST per collision (from the ncu
     # instruction counts of the capture in profiles/)
-    tri = (3, 6, 10, 10)
     # FP64 work of k_hessian_fast per collision, from the ncu instruction counts of profiles/r2_ncu_full_c3_raw.csv
     # (smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on): thread instructions, and flop with an FMA as two
     FP64_INST = (469.0, 2028.0, 3876.0, 3993.0)
@@ -532,8 +532,10 @@ def main():
     hl_flops = [c * share * f for c, f in zip(ncoll, FLOPS_HFAST)]
     hl_inst = [c * share * f for c, f in zip(ncoll, FP64_INST)]
     hf_ms = sum(k_ms(n) or 0.0 for n in hf_names)
-    # numeric pass: 4 B reference + 72 B block per item in, 8 B per unique block (~nnz / 9), 12 B per entry out
-    hn_bytes = nitems * share * 76 + nnz_ * 12 + (nnz_ // 9) * 8
+    # numeric pass: every stored (upper-triangular) 72 B block once — the second read of an off-diagonal block, by the column of
+    # its other vertex, is an L2 hit in the Morton visiting order and is not counted —, 4 B reference per item, 8 B per unique
+    # block (~nnz / 9) in; 12 B per entry out
+    hn_bytes = sum(c * share * 72 * t for c, t in zip(ncoll, tri)) + nitems * share * 4 + (nnz_ // 9) * 8 + nnz_ * 12
     # symbolic pass: 8 B incidence + 16 B ids + 8 B masks per incidence in, 4 B per item + 8 B per unique block out
     hs_bytes = ninc * share * 32 + nitems * share * 4 + (nnz_ // 9) * 8
     rooflines = [r for r in (
@@ -546,7 +548,7 @@ def main():
         roof("k_hess_numeric", stages.get("hess_numeric"), hn_bytes, ["k_hess_numeric"], "HBM gather of 72-byte blocks, software-pipelined"),
         roof("k_hess_symbolic", stages.get("hess_symbolic"), hs_bytes, ["k_hess_symbolic"],
              "shared-memory hash + sort per column; instruction / latency bound"),
-        roof("radix sort of the (vertex, collision) incidences (cub)", k_ms("radix_sort(incidences)"), ninc * share * 8 * 2 * 4, ["DeviceRadixSort"],
+        roof("radix sort of the (vertex, collision) incidences (cub)", k_ms("radix_sort(incidences)"), ninc * share * 8 * 2 * 4, ["(no per-sort capture)"],
              "3 onesweep passes + histogram over 8-byte keys"),
         # classification: 8 B ids + 2 x 8 B edge / 16 B face ids + 4 x 32 B vertices per candidate; ~150 (EE) / 250 (FV) flop
         roof("k_classify<EE>", k_ms("k_classify<EE>"), cs[2] * 152.0, ["k_classify<2"], "one thread per candidate: dependent gathers out of L2",
@@ -554,13 +556,14 @@ def main():
         roof("k_classify<FV>", k_ms("k_classify<FV>"), cs[3] * 152.0, ["k_classify<3"], "one thread per candidate: dependent gathers out of L2",
              flops=cs[3] * 250.0),
         # traversal: 40 B per query leaf + 8 B per emitted pair (static + swept passes); the node fetches (64 B each) hit L2
-        roof("k_traverse<EE> (static + swept)", k_ms("k_traverse<EE>"), 2 * E.shape[0] * 40.0 + (cs[2] + cc[2]) * 8.0, ["k_traverse<2, 2, 2"],
+        roof("k_traverse<EE> (static + swept)", k_ms("k_traverse<EE>"), 2 * E.shape[0] * 40.0 + (cs[2] + cc[2]) * 8.0, ["k_traverse<2,2,2"],
              "one thread per query leaf, stack walk: bound by dependent node fetches (L2 latency), not by DRAM"),
-        roof("k_traverse<FV> (static + swept)", k_ms("k_traverse<FV>"), 2 * nV * 40.0 + (cs[3] + cc[3]) * 8.0, ["k_traverse<1, 1, 3"],
+        roof("k_traverse<FV> (static + swept)", k_ms("k_traverse<FV>"), 2 * nV * 40.0 + (cs[3] + cc[3]) * 8.0, ["k_traverse<1,1,3"],
              "one thread per query leaf, stack walk: bound by dependent node fetches (L2 latency), not by DRAM"),
-        # CCD pre-filter: 8 B ids + 16 B edge ids + 8 x 32 B vertices (t0, t1) per candidate; ~400 flop
-        roof("k_ti_filter", k_ms("k_ti_filter"), (cc[2] + cc[3]) * 280.0, ["k_ti_filter"], "separating-direction test per swept candidate",
-             flops=(cc[2] + cc[3]) * 400.0),
+        # CCD pre-filter (FP32, conservative): 8 B ids + 16 B edge / face ids + 4 x 32 B re-centred float vertices (t0 | t1) per
+        # candidate; the vertex table (16 MB) is L2-resident, so these are L2 -> SM bytes, not DRAM bytes; ~250 FP32 flop
+        roof("k_ti_filter32", k_ms("k_ti_filter"), (cc[2] + cc[3]) * 152.0, ["k_ti_filter32"],
+             "separating-direction test per swept candidate in FP32 with a conservative margin; gathers out of L2 (bytes = L2->SM traffic)"),
     ) if r]
     roof_main = rooflines[0] if rooflines else None
     if roof_main is not None:  # the contract's `roofline` object: the dominant kernel against the MEASURED HBM bandwidth; its FP64 view rides along

@@ -544,7 +544,12 @@ static void build_tree(ipcb_ctx* ctx, const PrimSet& ps, Tree& t, bool with_node
     k_karras_boxes<<<grid_for(n - 1, 256), 256, 0, s>>>(n, t.key_sorted.p, t.nodes.p, q);
     ctx->launches += 5;
     t.has_nodes = true;
-    static const bool wide = getenv("IPCB_BVH4") != nullptr; // A/B: 4-wide traversal (k_collapse4 + k_traverse4)
+    // 4-wide collapse (k_collapse4 + k_traverse4).  Measured (C3 / C5, ms): vertex queries against the FACE tree 1.08 -> 0.79 /
+    // 7.5 -> 2.3 — a vertex box overlaps few faces, the walk is a chain of dependent fetches and the collapse halves it —,
+    // edge self-queries 1.99 -> 2.55 / 6.7 -> 9.1 — the self-query pruning already skips half of every level and four box
+    // tests per visit cost more than they save.  Default: the face tree only; IPCB_BVH4=0 none, =1 every tree (A/B, tests).
+    static const int wide_mode = getenv("IPCB_BVH4") ? atoi(getenv("IPCB_BVH4")) : -1;
+    const bool wide = wide_mode == 1 || (wide_mode == -1 && &t == &ctx->ftree);
     t.has_nodes4 = false;
     if (wide) {
         t.nodes4.reserve(n - 1);
