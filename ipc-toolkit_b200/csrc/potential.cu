@@ -721,24 +721,28 @@ __device__ inline bool column_symbolic_hash(const SymArgs& A, int v, int lane, H
     bool overflow = false;
     IncItems keep0, keep1;
     keep0.np = keep1.np = 0;
-    for (int q = s + lane; q < e; q += 32) {
-        const IncItems it = load_incidence(A, q, b1, b2);
-        if (q < s + 32) keep0 = it;
-        else if (q < s + 64) keep1 = it;
+    for (int q0 = s; q0 < e; q0 += 32) {
+        const int q = q0 + lane;
+        if (q < e) {
+            const IncItems it = load_incidence(A, q, b1, b2);
+            if (q < s + 32) keep0 = it;
+            else if (q < s + 64) keep1 = it;
 #pragma unroll
-        for (int b = 0; b < 4; b++)
-            if (b < it.np) {
-                int h = hash_slot(it.vi[b]), probe = 0;
-                for (; probe < HT; probe++) {
-                    const int old = atomicCAS(&H.key[h], -1, it.vi[b]);
-                    if (old == -1 || old == it.vi[b]) break;
-                    h = (h + 1) & (HT - 1);
+            for (int b = 0; b < 4; b++)
+                if (b < it.np) {
+                    int h = hash_slot(it.vi[b]), probe = 0;
+                    for (; probe < HT; probe++) {
+                        const int old = atomicCAS(&H.key[h], -1, it.vi[b]);
+                        if (old == -1 || old == it.vi[b]) break;
+                        h = (h + 1) & (HT - 1);
+                    }
+                    if (probe == HT) overflow = true;
+                    else atomicOr(&H.msk[h], unsigned(it.mk[b])), atomicAdd(&H.cnt[h], 1);
                 }
-                if (probe == HT) overflow = true;
-                else atomicOr(&H.msk[h], unsigned(it.mk[b])), atomicAdd(&H.cnt[h], 1);
-            }
+        }
+        // a full table makes every further item probe all of it: leave at once (a 9 345-item column spent 1 ms here)
+        if (__any_sync(0xffffffffu, overflow)) return false;
     }
-    if (__any_sync(0xffffffffu, overflow)) return false;
     __syncwarp();
     // B. unique row vertices, sorted
     int U = 0;
@@ -844,7 +848,8 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
         if (lane == 0) A.colU[v] = 0;
         return;
     }
-    if (use_hash && column_symbolic_hash(A, v, lane, sm[warp].h)) return;
+    // columns far beyond what 128 hash slots can de-duplicate go straight to the block kernel (its hash has 4 096 slots)
+    if (use_hash && R <= 8 * WARP_CAP && column_symbolic_hash(A, v, lane, sm[warp].h)) return;
     __syncwarp();
     if (R > warp_cap) { // handed to the block-per-column kernel
         if (lane == 0) big[atomicAdd(nbig, 1ull)] = v;
@@ -1093,12 +1098,87 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
     }
 }
 
+// ---- pass 2, column-lane variant: 3 lanes per unique block (one per scalar column of the block), ten blocks at a time.  A lane
+// sums the three entries of its column over the run, so the reference decode / address arithmetic is paid once per three gathered
+// entries and a warp covers ten blocks per round instead of three.  Same item order per entry as k_hess_numeric: bit-identical.
+template <int NUM_BATCH>
+__global__ void __launch_bounds__(32 * SYM_WARPS)
+    k_hess_numeric_col(int nV, const int* __restrict__ colR, const int* __restrict__ colU, const int* __restrict__ itemoff,
+                       const unsigned* __restrict__ sref, const int2* __restrict__ udesc, const double* __restrict__ blk,
+                       const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals, const int* __restrict__ order,
+                       int big_items, int* __restrict__ big, unsigned long long* nbig)
+{
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * SYM_WARPS + (threadIdx.x >> 5);
+    if (w >= nV) return;
+    const int v = order ? order[w] : w;
+    const int U = colU[v];
+    if (U == 0) return;
+    const int R = colR[v], ioff = itemoff[v];
+    if (R > big_items) {
+        if (lane == 0) big[atomicAdd(nbig, 1ull)] = v;
+        return;
+    }
+    const int g = lane / 3, l = lane - 3 * g;
+    const bool lane_ok = lane < 30;
+    const unsigned colmask = 0x09249249u << l; // lanes of the same scalar column (bits l, l + 3, ..., l + 27)
+    const unsigned below = (1u << lane) - 1;
+    const int2* ud = udesc + ioff;
+    const unsigned* sr = sref + ioff;
+    int base = lane_ok ? outer[3 * size_t(v) + l] : 0;
+    RunRefs<NUM_BATCH> cur = load_run<NUM_BATCH>(ud, sr, g, U, R, lane_ok);
+    for (int u0 = 0; u0 < U; u0 += 10) {
+        double a0[NUM_BATCH], a1[NUM_BATCH], a2[NUM_BATCH];
+#pragma unroll
+        for (int x = 0; x < NUM_BATCH; x++) {
+            a0[x] = a1[x] = a2[x] = 0.0;
+            if (x < cur.len) {
+                const bool tr = cur.ref[x] & 1u; // stored by the other vertex: entry (r, l) is the stored (l, r)
+                const double* b = blk + size_t(cur.ref[x] >> 1) * 9 + (tr ? 3 * l : l);
+                const int st = tr ? 1 : 3;
+                a0[x] = __ldg(b), a1[x] = __ldg(b + st), a2[x] = __ldg(b + 2 * st);
+            }
+        }
+        const RunRefs<NUM_BATCH> nxt = load_run<NUM_BATCH>(ud, sr, u0 + 10 + g, U, R, lane_ok);
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        bool z0 = false, z1 = false, z2 = false;
+#pragma unroll
+        for (int x = 0; x < NUM_BATCH; x++)
+            if (x < cur.len) {
+                s0 += a0[x], s1 += a1[x], s2 += a2[x];
+                z0 |= a0[x] != 0.0, z1 |= a1[x] != 0.0, z2 |= a2[x] != 0.0;
+            }
+        for (int j = NUM_BATCH; j < cur.len; j++) {
+            const unsigned ref = sr[cur.start + j];
+            const bool tr = ref & 1u;
+            const double* b = blk + size_t(ref >> 1) * 9 + (tr ? 3 * l : l);
+            const int st = tr ? 1 : 3;
+            const double w0 = __ldg(b), w1 = __ldg(b + st), w2 = __ldg(b + 2 * st);
+            s0 += w0, s1 += w1, s2 += w2;
+            z0 |= w0 != 0.0, z1 |= w1 != 0.0, z2 |= w2 != 0.0;
+        }
+        const bool have = cur.len > 0;
+        const unsigned m0 = __ballot_sync(0xffffffffu, have && z0) & colmask;
+        const unsigned m1 = __ballot_sync(0xffffffffu, have && z1) & colmask;
+        const unsigned m2 = __ballot_sync(0xffffffffu, have && z2) & colmask;
+        if (have) { // inside a scalar column: blocks in order, rows ascending inside a block
+            int p = base + __popc(m0 & below) + __popc(m1 & below) + __popc(m2 & below);
+            if (z0) inner[p] = 3 * cur.row, vals[p] = s0, p++;
+            if (z1) inner[p] = 3 * cur.row + 1, vals[p] = s1, p++;
+            if (z2) inner[p] = 3 * cur.row + 2, vals[p] = s2;
+        }
+        base += __popc(m0) + __popc(m1) + __popc(m2);
+        cur = nxt;
+    }
+}
+
 // giant columns: one block per column.  Phase 1: the 8 warps sum 24 unique blocks at a time (same 9-lanes-per-block layout and the
 // same item order as k_hess_numeric, so the values are bit-identical) into shared memory, with the 9-bit non-zero pattern of every
 // block; phase 2: positions inside the three scalar columns from a block-wide scan of the pattern counts, then the stores.
 // Columns with more than NUMERIC_UCAP unique blocks are processed in segments that carry the three running positions.
 constexpr int NUMERIC_UCAP = 1024;
-__global__ void __launch_bounds__(BIG_THREADS)
+constexpr int NBIG_THREADS = 1024; // 32 warps x 3 blocks = 96 unique blocks per round
+__global__ void __launch_bounds__(NBIG_THREADS)
     k_hess_numeric_big(const int* __restrict__ big, const unsigned long long* nbig, const int* __restrict__ colR, const int* __restrict__ colU,
                        const int* __restrict__ itemoff, const unsigned* __restrict__ sref, const int2* __restrict__ udesc,
                        const double* __restrict__ blk, const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals,
@@ -1107,7 +1187,7 @@ __global__ void __launch_bounds__(BIG_THREADS)
     extern __shared__ __align__(16) char smem[];
     double* acc_s = reinterpret_cast<double*>(smem);                                 // NUMERIC_UCAP x 9
     unsigned short* pat = reinterpret_cast<unsigned short*>(acc_s + NUMERIC_UCAP * 9); // NUMERIC_UCAP
-    __shared__ int scan[3 * BIG_THREADS];
+    __shared__ int wtot[3 * (NBIG_THREADS / 32)];
     __shared__ int run_base[3];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int g = lane / 9, k = lane - 9 * g, l = k % 3, r = k / 3, kt = 3 * l + r;
@@ -1122,7 +1202,7 @@ __global__ void __launch_bounds__(BIG_THREADS)
         __syncthreads();
         for (int seg = 0; seg < U; seg += ucap) {
             const int nseg = min(ucap, U - seg);
-            for (int u0 = 3 * warp; u0 < nseg; u0 += 3 * (BIG_THREADS / 32)) {
+            for (int u0 = 3 * warp; u0 < nseg; u0 += 3 * (NBIG_THREADS / 32)) {
                 const int u = seg + u0 + g;
                 double acc = 0.0;
                 bool nz = false;
@@ -1130,14 +1210,15 @@ __global__ void __launch_bounds__(BIG_THREADS)
                 if (has) {
                     const int start = ud[u].x, len = (u + 1 < U ? ud[u + 1].x : R) - start;
                     int j = 0;
-                    for (; j + 4 <= len; j += 4) { // four gathers in flight, added in item order
-                        const unsigned r0 = sr[start + j], r1 = sr[start + j + 1], r2 = sr[start + j + 2], r3 = sr[start + j + 3];
-                        const double w0 = __ldg(blk + size_t(r0 >> 1) * 9 + ((r0 & 1u) ? kt : k));
-                        const double w1 = __ldg(blk + size_t(r1 >> 1) * 9 + ((r1 & 1u) ? kt : k));
-                        const double w2 = __ldg(blk + size_t(r2 >> 1) * 9 + ((r2 & 1u) ? kt : k));
-                        const double w3 = __ldg(blk + size_t(r3 >> 1) * 9 + ((r3 & 1u) ? kt : k));
-                        acc += w0, acc += w1, acc += w2, acc += w3;
-                        nz |= (w0 != 0.0) | (w1 != 0.0) | (w2 != 0.0) | (w3 != 0.0);
+                    for (; j + 8 <= len; j += 8) { // eight gathers in flight, added in item order
+                        unsigned rf[8];
+                        double wv[8];
+#pragma unroll
+                        for (int x = 0; x < 8; x++) rf[x] = sr[start + j + x];
+#pragma unroll
+                        for (int x = 0; x < 8; x++) wv[x] = __ldg(blk + size_t(rf[x] >> 1) * 9 + ((rf[x] & 1u) ? kt : k));
+#pragma unroll
+                        for (int x = 0; x < 8; x++) acc += wv[x], nz |= wv[x] != 0.0;
                     }
                     for (; j < len; j++) {
                         const unsigned ref = sr[start + j];
@@ -1151,21 +1232,31 @@ __global__ void __launch_bounds__(BIG_THREADS)
                 if (has && k == 0) pat[u0 + g] = (unsigned short)((pm >> (9 * g)) & 0x1ffu);
             }
             __syncthreads();
-            // entries per scalar column of the blocks thread t owns ([lo, hi) of the segment), then a serial prefix
-            const int L = (nseg + BIG_THREADS - 1) / BIG_THREADS, lo = min(nseg, t * L), hi = min(nseg, lo + L);
+            // entries per scalar column of the blocks thread t owns ([lo, hi) of the segment): warp scan + scan of the warp totals
+            const int L = (nseg + NBIG_THREADS - 1) / NBIG_THREADS, lo = min(nseg, t * L), hi = min(nseg, lo + L);
             int c[3] = { 0, 0, 0 };
             for (int u = lo; u < hi; u++) {
                 const unsigned m = pat[u];
                 c[0] += __popc(m & 0x49u), c[1] += __popc(m & 0x92u), c[2] += __popc(m & 0x124u);
             }
-            scan[3 * t] = c[0], scan[3 * t + 1] = c[1], scan[3 * t + 2] = c[2];
-            __syncthreads();
-            int p[3] = { run_base[0], run_base[1], run_base[2] }, tot[3] = { 0, 0, 0 };
-            for (int q = 0; q < BIG_THREADS; q++)
+            int incl[3] = { c[0], c[1], c[2] };
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
 #pragma unroll
                 for (int x = 0; x < 3; x++) {
-                    const int cq = scan[3 * q + x];
-                    p[x] += q < t ? cq : 0;
+                    const int up = __shfl_up_sync(0xffffffffu, incl[x], o);
+                    if (lane >= o) incl[x] += up;
+                }
+            if (lane == 31) wtot[3 * warp] = incl[0], wtot[3 * warp + 1] = incl[1], wtot[3 * warp + 2] = incl[2];
+            __syncthreads();
+            int p[3], tot[3] = { 0, 0, 0 };
+#pragma unroll
+            for (int x = 0; x < 3; x++) p[x] = run_base[x] + incl[x] - c[x];
+            for (int q = 0; q < NBIG_THREADS / 32; q++)
+#pragma unroll
+                for (int x = 0; x < 3; x++) {
+                    const int cq = wtot[3 * q + x];
+                    p[x] += q < warp ? cq : 0;
                     tot[x] += cq;
                 }
             for (int u = lo; u < hi; u++) {
@@ -1409,15 +1500,23 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
     if (const char* e = getenv("IPCB_HESS_NUMERIC_UCAP")) ucap = std::min(NUMERIC_UCAP, std::max(3, atoi(e)));
     unsigned long long* nbig2 = ctx->dCounters.p + 15;
     IPCB_CUDA(cudaMemsetAsync(nbig2, 0, sizeof(unsigned long long), s));
-#define IPCB_NUMERIC(NB)                                                                                                                  \
-    k_hess_numeric<NB><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p, \
-                                                        ctx->outer.p, ctx->inner.p, ctx->vals.p, order, big_items, ctx->hbig.p, nbig2)
-    if (nb == 16) IPCB_NUMERIC(16);
-    else if (nb == 12) IPCB_NUMERIC(12);
-    else IPCB_NUMERIC(8);
+#define IPCB_NUMERIC(KERNEL, NB)                                                                                                          \
+    KERNEL<NB><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,      \
+                                                ctx->outer.p, ctx->inner.p, ctx->vals.p, order, big_items, ctx->hbig.p, nbig2)
+    // IPCB_NUMERIC_LANES=9: one lane per block entry (three blocks per round); =3: one lane per block column (ten blocks per round)
+    const char* nl_env = getenv("IPCB_NUMERIC_LANES");
+    const int nlanes = nl_env ? atoi(nl_env) : 9;
+    if (nlanes == 3) {
+        const int nb3 = nb_env ? atoi(nb_env) : 6;
+        if (nb3 >= 8) IPCB_NUMERIC(k_hess_numeric_col, 8);
+        else if (nb3 >= 6) IPCB_NUMERIC(k_hess_numeric_col, 6);
+        else IPCB_NUMERIC(k_hess_numeric_col, 4);
+    } else if (nb == 16) IPCB_NUMERIC(k_hess_numeric, 16);
+    else if (nb == 12) IPCB_NUMERIC(k_hess_numeric, 12);
+    else IPCB_NUMERIC(k_hess_numeric, 8);
 #undef IPCB_NUMERIC
     constexpr size_t NUMERIC_SMEM = size_t(NUMERIC_UCAP) * (72 + 2);
-    k_hess_numeric_big<<<NUM_SMS, BIG_THREADS, NUMERIC_SMEM, s>>>(ctx->hbig.p, nbig2, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p,
+    k_hess_numeric_big<<<NUM_SMS, NBIG_THREADS, NUMERIC_SMEM, s>>>(ctx->hbig.p, nbig2, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p,
                                                                  ctx->hudesc.p, ctx->hblk.p, ctx->outer.p, ctx->inner.p, ctx->vals.p, ucap);
     ctx->launches += 2;
     ctx->launches++;
