@@ -58,10 +58,10 @@ enum { IPCB_PSD_NONE = 0, IPCB_PSD_CLAMP = 1, IPCB_PSD_ABS = 2 };
 /* NarrowPhaseCCD implementations (ccd/tight_inclusion_ccd.hpp, ccd/additive_ccd.hpp) */
 enum { IPCB_CCD_TIGHT_INCLUSION = 0, IPCB_CCD_ADDITIVE = 1 };
 
-/* broad phase predicate: FLOAT = the default LBVH's outward-rounded float
- * boxes (broad_phase/lbvh.cpp:29-41, lbvh.hpp:66-70); DOUBLE = BruteForce /
- * HashGrid double boxes (broad_phase/aabb.cpp:29-33).  Cross-check switch. */
-enum { IPCB_BOXES_FLOAT = 0, IPCB_BOXES_DOUBLE = 1 };
+/* broad phase predicate: the default LBVH's outward-rounded FLOAT boxes (broad_phase/lbvh.cpp:29-41, lbvh.hpp:66-70),
+ * the only predicate this library implements.  (BruteForce / HashGrid compare double boxes, broad_phase/aabb.cpp:29-33;
+ * the oracle can switch to them as a cross-check; this library answers any other value with an error.) */
+enum { IPCB_BOXES_FLOAT = 0 };
 
 /* broad-phase method of a context (north_star subsystem 1): the LBVH (default) or a sweep-and-prune over the boxes sorted
  * along the longest scene axis (reference semantics broad_phase/sweep_and_prune.cpp:106-119).  Same predicate, hence the
@@ -134,14 +134,13 @@ int IPCB_FN(mesh_areas)(ipcb_ctx* ctx, double* vertex_areas /* nV */, double* ed
 /* ---- BroadPhase (broad_phase/broad_phase.hpp:19-133) -------------------- */
 /* build(V,E,F,r) :12-23 and build(V0,V1,E,F,r) :25-41 of broad_phase.cpp on
  * the context's mesh; detect_* replaces the six pure virtuals (:71-97).
- * `boxes` selects the predicate (IPCB_BOXES_*). */
+ * `boxes`: IPCB_BOXES_FLOAT (anything else is refused). */
 int IPCB_FN(broad_build_static)(ipcb_ctx* ctx, const double* V, int32_t ld, double inflation_radius, int32_t boxes);
 int IPCB_FN(broad_build_swept)(ipcb_ctx* ctx, const double* V0, const double* V1, int32_t ld,
                                double inflation_radius, int32_t boxes);
 int IPCB_FN(broad_detect)(ipcb_ctx* ctx, int32_t kind, int64_t* count);
 int IPCB_FN(broad_fetch)(ipcb_ctx* ctx, int32_t kind, int32_t* pairs /* count x 2 */);
-/* vertex boxes of the last build as 6 floats per vertex (min xyz, max xyz) or
- * 6 doubles when built with IPCB_BOXES_DOUBLE (aabb.cpp:35-87, lbvh.cpp:29-41) */
+/* vertex boxes of the last build as 6 floats per vertex (min xyz, max xyz) (aabb.cpp:35-87, lbvh.cpp:29-41) */
 int IPCB_FN(broad_vertex_boxes)(ipcb_ctx* ctx, void* boxes /* nV x 6 row-major */);
 
 /* ---- Candidates (candidates/candidates.cpp:43-222) ---------------------- */

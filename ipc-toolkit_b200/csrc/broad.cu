@@ -8,16 +8,24 @@
 //
 // Design (B200-first, not the reference's CPU layout):
 //  * positions are converted once per call to one 32-byte double4 per vertex;
-//  * the tree is a Karras radix tree over 63-bit Morton keys (sorted with
-//    cub::DeviceRadixSort, plumbing), refit bottom-up with arrival counters;
+//  * the tree is a Karras radix tree over Morton keys (sorted with
+//    cub::DeviceRadixSort, plumbing).  Node boxes are RANGE UNIONS over the
+//    sorted leaf boxes answered by a three-level min / max table (k_rmq_*),
+//    so the thread that builds a node also finishes it: no bottom-up pass, no
+//    arrival counters (the former k_refit stays behind IPCB_REFIT_BOTTOM_UP
+//    as the A/B and test alternative);
 //    one internal node = one 64-byte fetch holding BOTH child boxes, so leaves
-//    are never fetched during traversal;
+//    are never fetched during traversal; the face tree is additionally
+//    collapsed to 4-wide nodes (k_collapse4 / k_traverse4);
 //  * traversal is one thread per Morton-ordered query leaf, warp-synchronous,
 //    with hits staged in a per-warp shared-memory queue and flushed with ONE
 //    global atomic per ~100 pairs (warp-aggregated compaction) and coalesced
 //    int2 stores;
 //  * output capacity is learned from the previous step; on overflow the kernel
-//    keeps counting and the pass is repeated once with a larger buffer.
+//    keeps counting and the pass is repeated once with a larger buffer; beyond
+//    IPCB_MAX_PAIRS the query leaves are processed in chunks (traverse_chunk);
+//  * a sweep-and-prune over axis-sorted boxes is the second method
+//    (IPCB_BROAD_SAP), same predicate, same candidate sets.
 // The candidate SET is the tree-independent predicate
 //   { (i,j) : fbox_i ∩ fbox_j ≠ ∅ (closed) ∧ no shared vertex }
 // exactly like the reference's default LBVH (SURVEY §7 hard part 1).
