@@ -218,6 +218,7 @@ struct ipcb_ctx {
     ipcb::Buf<int> hbig;                             // columns too large for one warp's shared memory
     ipcb::Buf<char> hscratch;                        // global sort scratch for huge columns
     size_t hscratch_items = 0;
+    bool hfast_attr_set = false;
     bool hess_attr_set = false;
     ipcb::Buf<int> outer, inner;
     ipcb::Buf<double> vals;

@@ -123,6 +123,15 @@ inline CollView view_slice(const ipcb_ctx* ctx, int k)
 inline MeshView mesh_view(const ipcb_ctx* ctx) { return { ctx->dE.p, ctx->dF.p, ctx->X0.p }; }
 
 
+// first stored block of each kind's records in hblk (3 / 6 / 10 upper-triangular blocks of 72 bytes per VV / EV / 4-point record).
+// The vertex-vertex part is padded to an even number of blocks so that every 432- / 720-byte record behind it starts on a
+// 16-byte boundary (the TMA bulk stores of k_hessian_fast need it).
+inline void hess_block_offsets(const int64_t nk[4], int64_t blk0[4])
+{
+    const int64_t vv = 3 * nk[0] + ((3 * nk[0]) & 1);
+    blk0[0] = 0, blk0[1] = vv, blk0[2] = vv + 6 * nk[1], blk0[3] = vv + 6 * nk[1] + 10 * nk[2];
+}
+
 // records of nk[VV..FV] collisions (written by the local kernels at hvid / hmask / hblk / hkey, kinds in that order)
 // -> the context's resident compressed columns (outer / inner / vals, nnz); potential.cu
 void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4]);

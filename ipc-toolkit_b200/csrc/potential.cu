@@ -411,7 +411,14 @@ __global__ void __launch_bounds__(128)
 // registers would make every 8-byte store of a warp hit 32 different sectors; instead each block
 // row (NP blocks = NP*72 contiguous bytes per collision) is staged in shared memory (odd stride:
 // conflict-free) and written out by the whole warp with consecutive lanes on consecutive addresses.
-template <int KIND, int MINB>
+//
+// BULK (3- and 4-point kinds): the record of a collision is 432 / 720 contiguous, 16-byte aligned bytes, so the thread stages it in
+// its own shared-memory slot and hands it to the TMA unit (cp.async.bulk.global.shared::cta): one instruction per 288- or 432-byte
+// piece instead of a warp-wide copy loop (which was 30 % of the kernel's instructions); the store drains while the thread computes
+// the next piece.  A 4-point record goes in two pieces — row 0 (4 blocks) and rows 1..3 (6 blocks) — so that 432 bytes per thread
+// (54 KB per block, four blocks per SM) are enough.
+constexpr int BULK_STRIDE = 54; // doubles per thread
+template <int KIND, int MINB, bool BULK>
 __global__ void __launch_bounds__(128, MINB)
     k_hessian_fast(CollView c, MeshView m, BarrierDev B, int psd_mode, int64_t gi0, int64_t inc0, HessOut out, int* __restrict__ slow,
                    unsigned long long* slow_count, const int* __restrict__ sel, int64_t nsel)
@@ -419,8 +426,7 @@ __global__ void __launch_bounds__(128, MINB)
     constexpr int NP = KIND == IPCB_VV ? 2 : (KIND == IPCB_EV ? 3 : 4);
     constexpr int P = KIND == IPCB_VV ? 0 : (KIND == IPCB_EV ? 1 : 2);
     constexpr int PRIM = KIND == IPCB_VV ? 0 : (KIND == IPCB_EV ? 1 : (KIND == IPCB_FV ? 2 : 3));
-    constexpr int ROW = NP * 9, PAD = ROW | 1;
-    __shared__ double stage[4][32][PAD];
+    static_assert(!BULK || NP >= 3, "a vertex-vertex record (216 bytes) is not a multiple of 16 bytes");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // t = record index within the kind; i = collision index (sel: the collisions touching the rank's row block)
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -453,50 +459,98 @@ __global__ void __launch_bounds__(128, MINB)
         if (is_slow) slow[basep + __popc(smask & ((1u << lane) - 1))] = int(t);
     }
     if (emask_any == 0) return;
-    const int64_t tw = t - lane; // record index (within the kind) of lane 0's collision
     unsigned mpack[HSLOTS / 2];
 #pragma unroll
     for (int k = 0; k < HSLOTS / 2; k++) mpack[k] = 0;
+    if constexpr (BULK) {
+        extern __shared__ __align__(128) double bulk_stage[];
+        double* my = bulk_stage + threadIdx.x * BULK_STRIDE;
+        const unsigned my_s = unsigned(__cvta_generic_to_shared(my));
+        double* rec = out.blk + t * (tri_count(NP) * 9);
+        constexpr int NPH = NP == 4 ? 2 : 1;
 #pragma unroll
-    for (int a = 0; a < NP; a++) { // column point: its row of the upper triangle, blocks (a, b >= a), is contiguous
-        const bool emit_a = emit && (own >> a) != 0u; // needed by an owned column a, or by an owned column b > a (transposed)
-        const unsigned emask = __ballot_sync(0xffffffffu, emit_a);
-        if (emask == 0) continue;
-        const int row = (NP - a) * 9; // doubles in this row
-        if (emit_a) {
+        for (int ph = 0; ph < NPH; ph++) {
+            const int a_lo = NP == 4 ? ph : 0, a_hi = NP == 4 ? (ph == 0 ? 1 : 4) : NP;
+            // rows a_lo.. are needed by an owned column >= a_lo (directly, or transposed)
+            const bool need = emit && (own >> a_lo) != 0u;
+            if (ph > 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the slot has been read
+            if (need) {
+                int off = 0;
 #pragma unroll
-            for (int b = a; b < NP; b++) { // row point
-                double blk[9];
-                fast_block<P>(pr, b, a, blk);
-                unsigned mask = 0;
+                for (int a = a_lo; a < a_hi; a++)
 #pragma unroll
-                for (int k = 0; k < 9; k++) {
-                    stage[warp][lane][(b - a) * 9 + k] = blk[k];
-                    mask |= unsigned(blk[k] != 0.0) << k;
+                    for (int b = a; b < NP; b++) {
+                        double blk[9];
+                        fast_block<P>(pr, b, a, blk);
+                        unsigned mask = 0;
+#pragma unroll
+                        for (int k = 0; k < 9; k++) {
+                            my[off + k] = blk[k];
+                            mask |= unsigned(blk[k] != 0.0) << k;
+                        }
+                        off += 9;
+                        const int slot = a * 4 + b, mirror = b * 4 + a;
+                        mpack[slot >> 1] |= mask << (16 * (slot & 1));
+                        if (b != a) mpack[mirror >> 1] |= mask_transpose(mask) << (16 * (mirror & 1));
+                    }
+                asm volatile("fence.proxy.async;" ::: "memory"); // the staged values become visible to the async proxy
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rec + tri_slot(NP, a_lo, a_lo) * 9), "r"(my_s),
+                             "r"(off * 8)
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (emit) {
+            uint4* mp = reinterpret_cast<uint4*>(out.mask + (gi0 + t) * HSLOTS);
+            mp[0] = make_uint4(mpack[0], mpack[1], mpack[2], mpack[3]);
+            mp[1] = make_uint4(mpack[4], mpack[5], mpack[6], mpack[7]);
+        }
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the copy
+    } else {
+        constexpr int ROW = NP * 9, PAD = ROW | 1;
+        __shared__ double stage[4][32][PAD];
+        const int64_t tw = t - lane; // record index (within the kind) of lane 0's collision
+#pragma unroll
+        for (int a = 0; a < NP; a++) { // column point: its row of the upper triangle, blocks (a, b >= a), is contiguous
+            const bool emit_a = emit && (own >> a) != 0u; // needed by an owned column a, or by an owned column b > a (transposed)
+            const unsigned emask = __ballot_sync(0xffffffffu, emit_a);
+            if (emask == 0) continue;
+            const int row = (NP - a) * 9; // doubles in this row
+            if (emit_a) {
+#pragma unroll
+                for (int b = a; b < NP; b++) { // row point
+                    double blk[9];
+                    fast_block<P>(pr, b, a, blk);
+                    unsigned mask = 0;
+#pragma unroll
+                    for (int k = 0; k < 9; k++) {
+                        stage[warp][lane][(b - a) * 9 + k] = blk[k];
+                        mask |= unsigned(blk[k] != 0.0) << k;
+                    }
+                    const int slot = a * 4 + b, mirror = b * 4 + a;
+                    mpack[slot >> 1] |= mask << (16 * (slot & 1));
+                    if (b != a) mpack[mirror >> 1] |= mask_transpose(mask) << (16 * (mirror & 1));
                 }
-                const int slot = a * 4 + b, mirror = b * 4 + a;
-                mpack[slot >> 1] |= mask << (16 * (slot & 1));
-                if (b != a) mpack[mirror >> 1] |= mask_transpose(mask) << (16 * (mirror & 1));
             }
-        }
-        __syncwarp();
-        {
-            int cl = 0, j = lane; // flat index lane + 32 * it over the warp's 32 x row staged doubles, without a division
-            while (j >= row) j -= row, cl++;
-            double* dst = out.blk + tw * (tri_count(NP) * 9) + tri_slot(NP, a, a) * 9;
-#pragma unroll 4
-            for (int it = 0; it < row; it++) {
-                if ((emask >> cl) & 1u) dst[size_t(cl) * (tri_count(NP) * 9) + j] = stage[warp][cl][j];
-                j += 32;
+            __syncwarp();
+            {
+                int cl = 0, j = lane; // flat index lane + 32 * it over the warp's 32 x row staged doubles, without a division
                 while (j >= row) j -= row, cl++;
+                double* dst = out.blk + tw * (tri_count(NP) * 9) + tri_slot(NP, a, a) * 9;
+#pragma unroll 4
+                for (int it = 0; it < row; it++) {
+                    if ((emask >> cl) & 1u) dst[size_t(cl) * (tri_count(NP) * 9) + j] = stage[warp][cl][j];
+                    j += 32;
+                    while (j >= row) j -= row, cl++;
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
-    }
-    if (emit) {
-        uint4* mp = reinterpret_cast<uint4*>(out.mask + (gi0 + t) * HSLOTS);
-        mp[0] = make_uint4(mpack[0], mpack[1], mpack[2], mpack[3]);
-        mp[1] = make_uint4(mpack[4], mpack[5], mpack[6], mpack[7]);
+        if (emit) {
+            uint4* mp = reinterpret_cast<uint4*>(out.mask + (gi0 + t) * HSLOTS);
+            mp[0] = make_uint4(mpack[0], mpack[1], mpack[2], mpack[3]);
+            mp[1] = make_uint4(mpack[4], mpack[5], mpack[6], mpack[7]);
+        }
     }
 }
 
@@ -1395,7 +1449,8 @@ void hessian_records(ipcb_ctx* ctx, const int64_t nk[4], int v_lo, int v_hi, Hes
     const int64_t ninc = 2 * n0 + 3 * n1 + 4 * (n2 + n3);
     const int64_t nitems = 4 * n0 + 9 * n1 + 16 * (n2 + n3);
     // stored blocks (upper triangles): 3 / 6 / 10 per VV / EV / 4-point record
-    const int64_t blk0[4] = { 0, 3 * n0, 3 * n0 + 6 * n1, 3 * n0 + 6 * n1 + 10 * n2 };
+    int64_t blk0[4];
+    hess_block_offsets(nk, blk0);
     const int64_t nblocks = blk0[3] + 10 * n3;
     if (ncoll >= (int64_t(1) << 27) || nitems > 0x7fffffffll || nblocks > 0x7fffffffll)
         throw Error("Hessian: more than 2^27 collisions / 2^31 local blocks on one device; shard the collision set");
@@ -1413,7 +1468,8 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
     const int64_t gi0[4] = { 0, n0, n0 + n1, n0 + n1 + n2 };
     const int64_t ninc = 2 * n0 + 3 * n1 + 4 * (n2 + n3);
     const int64_t nitems = 4 * n0 + 9 * n1 + 16 * (n2 + n3);
-    const int64_t blk0[4] = { 0, 3 * n0, 3 * n0 + 6 * n1, 3 * n0 + 6 * n1 + 10 * n2 };
+    int64_t blk0[4];
+    hess_block_offsets(nk, blk0);
     ctx->outer.reserve(3 * size_t(nV) + 1);
     // stage timers (only when ctx->timing is on): the three kernels of the assembly are timed one by one
     std::unique_ptr<Stage> st(new Stage(ctx, "hess_incidences"));
@@ -1590,16 +1646,38 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
             ctx->fork();
             static const bool dense = getenv("IPCB_HFAST_SPARSE") == nullptr; // 4 resident blocks per SM (small spill) for the 4-point kinds; A/B switch
             std::unique_ptr<Stage> kt(new Stage(ctx, "k:k_hessian_fast<VV>", ctx->aux[0]));
-            if (n0) k_hessian_fast<IPCB_VV, 4><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], outs[0], ctx->hslow.p, slow_count, sel[0], n0), ctx->launches++;
+            if (n0) k_hessian_fast<IPCB_VV, 4, false><<<grid_for(n0, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], outs[0], ctx->hslow.p, slow_count, sel[0], n0), ctx->launches++;
             kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<EV>", ctx->aux[0]));
-            if (n1) k_hessian_fast<IPCB_EV, 4><<<grid_for(n1, 128), 128, 0, ctx->aux[0]>>>(view(ctx, 1), m, B, psd_mode, gi0[1], inc0[1], outs[1], ctx->hslow.p, slow_count, sel[1], n1), ctx->launches++;
+            // IPCB_HFAST_STAGED: the warp-wide staged copy instead of the TMA bulk stores (A/B switch, tests)
+            static const bool bulk = getenv("IPCB_HFAST_STAGED") == nullptr;
+            constexpr size_t BULK_SMEM = size_t(128) * BULK_STRIDE * sizeof(double);
+            if (bulk && !ctx->hfast_attr_set) { // per device
+                IPCB_CUDA(cudaFuncSetAttribute(k_hessian_fast<IPCB_EV, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BULK_SMEM)));
+                IPCB_CUDA(cudaFuncSetAttribute(k_hessian_fast<IPCB_FV, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BULK_SMEM)));
+                IPCB_CUDA(cudaFuncSetAttribute(k_hessian_fast<IPCB_EE, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(BULK_SMEM)));
+                ctx->hfast_attr_set = true;
+            }
+#define IPCB_HFAST(KIND, MINB, BULK, K, STREAM)                                                                                            \
+    k_hessian_fast<KIND, MINB, BULK><<<grid_for(nk[K], 128), 128, BULK ? BULK_SMEM : 0, STREAM>>>(view(ctx, K), m, B, psd_mode, gi0[K], inc0[K], \
+                                                                                                  outs[K], ctx->hslow.p, slow_count, sel[K], nk[K])
+            if (n1) {
+                if (bulk) IPCB_HFAST(IPCB_EV, 4, true, 1, ctx->aux[0]);
+                else IPCB_HFAST(IPCB_EV, 4, false, 1, ctx->aux[0]);
+                ctx->launches++;
+            }
             kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<FV>", ctx->aux[1]));
-            if (n3 && dense) k_hessian_fast<IPCB_FV, 4><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], outs[3], ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
-            else if (n3) k_hessian_fast<IPCB_FV, 3><<<grid_for(n3, 128), 128, 0, ctx->aux[1]>>>(view(ctx, 3), m, B, psd_mode, gi0[3], inc0[3], outs[3], ctx->hslow.p, slow_count, sel[3], n3), ctx->launches++;
+            if (n3) {
+                if (bulk) IPCB_HFAST(IPCB_FV, 4, true, 3, ctx->aux[1]);
+                else if (dense) IPCB_HFAST(IPCB_FV, 4, false, 3, ctx->aux[1]);
+                else IPCB_HFAST(IPCB_FV, 3, false, 3, ctx->aux[1]);
+                ctx->launches++;
+            }
             kt.reset(), kt.reset(new Stage(ctx, "k:k_hessian_fast<EE>", s));
             if (n2) {
-                if (dense) k_hessian_fast<IPCB_EE, 4><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, slow_count, sel[2], n2);
-                else k_hessian_fast<IPCB_EE, 3><<<grid_for(n2, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, slow_count, sel[2], n2);
+                if (bulk) IPCB_HFAST(IPCB_EE, 4, true, 2, s);
+                else if (dense) IPCB_HFAST(IPCB_EE, 4, false, 2, s);
+                else IPCB_HFAST(IPCB_EE, 3, false, 2, s);
+#undef IPCB_HFAST
                 ctx->launches++;
                 kt.reset();
                 IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[11], slow_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
