@@ -541,7 +541,7 @@ def main():
     rooflines = [r for r in (
         roof("k_hessian_fast<VV|EV|EE|FV> (the four kinds, timed one by one)", hf_ms, sum(hl_bytes),
              ["k_hessian_fast<0", "k_hessian_fast<1", "k_hessian_fast<2", "k_hessian_fast<3"],
-             "register Jacobi PSD projection in the analytic (3+p)-subspace; upper-triangular blocks staged through shared memory",
+             "register Jacobi PSD projection in the analytic (3+p)-subspace; upper-triangular block records leave through per-thread TMA bulk stores (cp.async.bulk)",
              flops=sum(hl_flops), bound="fp64", fp64_inst=sum(hl_inst)),
         roof("k_hessian_fast<EE>", k_ms(hf_names[2]), hl_bytes[2], ["k_hessian_fast<2"], "the dominant kernel of the step", flops=hl_flops[2], bound="fp64",
              fp64_inst=hl_inst[2]),
