@@ -181,6 +181,29 @@ __global__ void k_iota(int64_t n, int* __restrict__ idx)
 }
 // head of a run (or every element when merge == 0); head threads sum the run's
 // weights and flag the record as kept when the sum is non-zero (builder.cpp:668-688)
+// Sum of the weights of one run of equal keys, ADDED IN ASCENDING ORDER OF VALUE: the records of a run arrive in the order of
+// the warp-aggregated appends (not reproducible from run to run), and with area weighting they differ in value, so a sum
+// in arrival order is not bit-reproducible.  Runs are short (one to a few records); the selection loop is O(length x
+// distinct values).
+template <class KeyEq> __device__ inline double run_weight_sum(int64_t i, int64_t n, const int* __restrict__ idx, const double* __restrict__ w_raw, KeyEq same)
+{
+    int64_t len = 1;
+    while (i + len < n && same(i + len)) len++;
+    if (len == 1) return w_raw[idx[i]];
+    double s = 0, last = -INFINITY;
+    for (int64_t done = 0; done < len;) {
+        double m = INFINITY;
+        int64_t c = 0;
+        for (int64_t j = i; j < i + len; j++) {
+            const double w = w_raw[idx[j]];
+            if (w > last && w < m) m = w, c = 1;
+            else if (w == m) c++;
+        }
+        for (int64_t r = 0; r < c; r++) s += m;
+        last = m, done += c;
+    }
+    return s;
+}
 __global__ void k_runs(int64_t n, const unsigned long long* __restrict__ key, const int* __restrict__ idx,
                        const double* __restrict__ w_raw, int merge, int* __restrict__ keep, double* __restrict__ wsum)
 {
@@ -196,8 +219,7 @@ __global__ void k_runs(int64_t n, const unsigned long long* __restrict__ key, co
         keep[i] = 0;
         return;
     }
-    double s = 0;
-    for (int64_t j = i; j < n && key[j] == k; j++) s += w_raw[idx[j]];
+    const double s = run_weight_sum(i, n, idx, w_raw, [&](int64_t j) { return key[j] == k; });
     wsum[i] = s;
     keep[i] = s != 0.0;
 }
@@ -779,8 +801,7 @@ __global__ void k_runs_ee_typed(int64_t n, const unsigned long long* __restrict_
         keep[i] = 0;
         return;
     }
-    double s = 0;
-    for (int64_t j = i; j < n && (key[j] >> 1) == k; j++) s += w_raw[idx[j]];
+    const double s = run_weight_sum(i, n, idx, w_raw, [&](int64_t j) { return (key[j] >> 1) == k; });
     wsum[i] = s;
     keep[i] = s != 0.0;
 }

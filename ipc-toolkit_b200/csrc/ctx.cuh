@@ -205,6 +205,8 @@ struct ipcb_ctx {
     ipcb::Buf<unsigned long long> hkey, hkey_sorted; // incidence keys (vertex << 32 | collision * 4 + point); also pair sorting
     ipcb::Buf<int4> hvid;                            // stencil vertex ids per collision (-1 padded)
     ipcb::Buf<unsigned short> hmask;                 // 16 x 9-bit non-zero masks per collision (slot = col point * 4 + row point)
+    ipcb::Buf<int> hactive;                          // columns with anything to assemble, in visiting order
+    ipcb::Buf<char> hseltmp;
     ipcb::Buf<double> hblk;                          // 16 x 9 doubles per collision
     ipcb::Buf<unsigned char> hflag;                  // row block: does the collision touch an owned vertex
     ipcb::Buf<int> hsel;                             // row block: per kind, the collisions that do (ascending)

@@ -885,17 +885,14 @@ union WarpSmem {
 // contact are neighbours in space, not in id (the next cloth layer is 63 K ids away), so a spatial visiting order lets the
 // second read (and the shared id / mask records) hit L2.  The output position of a column does not depend on the order.
 __global__ void __launch_bounds__(32 * SYM_WARPS)
-    k_hess_symbolic(SymArgs A, int warp_cap, int use_hash, int* __restrict__ big, unsigned long long* nbig, const int* __restrict__ order)
+    k_hess_symbolic(SymArgs A, int warp_cap, int use_hash, int* __restrict__ big, unsigned long long* nbig, const int* __restrict__ active,
+                    const int* __restrict__ nactive)
 {
     __shared__ WarpSmem sm[SYM_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int w = blockIdx.x * SYM_WARPS + warp;
-    if (w > A.nV) return;
-    const int v = (order && w < A.nV) ? order[w] : w;
-    if (v == A.nV) { // closing entry of the count array
-        if (lane == 0) A.cnt[3 * size_t(v)] = 0;
-        return;
-    }
+    if (w >= *nactive) return; // the counts of every other column were zeroed by the caller
+    const int v = active[w];
     const int R = A.colR[v];
     if (R == 0) {
         if (lane < 3) A.cnt[3 * size_t(v) + lane] = 0;
@@ -1095,13 +1092,13 @@ template <int NUM_BATCH>
 __global__ void __launch_bounds__(32 * SYM_WARPS)
     k_hess_numeric(int nV, const int* __restrict__ colR, const int* __restrict__ colU, const int* __restrict__ itemoff,
                    const unsigned* __restrict__ sref, const int2* __restrict__ udesc, const double* __restrict__ blk,
-                   const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals, const int* __restrict__ order,
+                   const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals, const int* __restrict__ active, const int* __restrict__ nactive,
                    int big_items, int* __restrict__ big, unsigned long long* nbig)
 {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * SYM_WARPS + (threadIdx.x >> 5);
-    if (w >= nV) return;
-    const int v = order ? order[w] : w; // spatial visiting order of the columns (see k_hess_symbolic)
+    if (w >= *nactive) return;
+    const int v = active[w]; // spatial visiting order of the columns (see k_hess_symbolic)
     const int U = colU[v];
     if (U == 0) return;
     const int R = colR[v], ioff = itemoff[v];
@@ -1159,13 +1156,13 @@ template <int NUM_BATCH>
 __global__ void __launch_bounds__(32 * SYM_WARPS)
     k_hess_numeric_col(int nV, const int* __restrict__ colR, const int* __restrict__ colU, const int* __restrict__ itemoff,
                        const unsigned* __restrict__ sref, const int2* __restrict__ udesc, const double* __restrict__ blk,
-                       const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals, const int* __restrict__ order,
+                       const int* __restrict__ outer, int* __restrict__ inner, double* __restrict__ vals, const int* __restrict__ active, const int* __restrict__ nactive,
                        int big_items, int* __restrict__ big, unsigned long long* nbig)
 {
     const int lane = threadIdx.x & 31;
     const int w = blockIdx.x * SYM_WARPS + (threadIdx.x >> 5);
-    if (w >= nV) return;
-    const int v = order ? order[w] : w;
+    if (w >= *nactive) return;
+    const int v = active[w];
     const int U = colU[v];
     if (U == 0) return;
     const int R = colR[v], ioff = itemoff[v];
@@ -1459,6 +1456,11 @@ void hessian_records(ipcb_ctx* ctx, const int64_t nk[4], int v_lo, int v_hi, Hes
     for (int k = 0; k < 4; k++) outs[k] = HessOut { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p + size_t(blk0[k]) * 9, ctx->hkey.p, v_lo, v_hi, ctx->nV };
 }
 
+struct ActiveColumn {
+    const int* colR;
+    __device__ bool operator()(int v) const { return colR[v] > 0; }
+};
+
 // Assembly of the per-collision records into compressed columns (see the comment block above k_col_ranges)
 void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
 {
@@ -1479,7 +1481,7 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
     size_t b1 = 0, b2 = 0, b3 = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, b1, ctx->hkey.p, ctx->hkey_sorted.p, ninc, 32, 32 + vbits, s);
     ctx->hcolinc.reserve(size_t(nV) + 2), ctx->hcolR.reserve(size_t(nV) + 2), ctx->hitemoff.reserve(size_t(nV) + 2);
-    ctx->hcnt.reserve(3 * size_t(nV) + 1);
+    ctx->hcnt.reserve(3 * size_t(nV) + 1), ctx->hcolU.reserve(size_t(nV) + 1);
     cub::DeviceScan::ExclusiveSum(nullptr, b2, ctx->hcolR.p, ctx->hitemoff.p, nV + 1, s);
     cub::DeviceScan::ExclusiveSum(nullptr, b3, ctx->hcnt.p, ctx->outer.p, 3 * nV + 1, s);
     ctx->cubtmp.reserve(std::max(b1, std::max(b2, b3)) + 1024);
@@ -1495,6 +1497,27 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
                                                             ctx->hcolb.p);
     cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, b2, ctx->hcolR.p, ctx->hitemoff.p, nV + 1, s);
     ctx->launches += 3;
+    // 2b. the columns that have anything to assemble, in the Morton order of their vertices (from the last broad phase on this
+    // context; any order is valid).  On a row block of a sharded Hessian three quarters (N = 4) of the columns are empty, on a
+    // scene like C2 most vertices are not in contact: the per-column kernels run one warp per ACTIVE column, so that every
+    // resident block is full of working warps (with one warp per vertex the working warps were 1 in 4 and the passes did not
+    // scale with the rank count).
+    static const bool id_order = getenv("IPCB_HESS_COLUMN_ID_ORDER") != nullptr; // A/B switch
+    const int* order = (!id_order && ctx->vorder_valid && ctx->vtree.n == nV) ? ctx->vtree.ord_sorted.p : nullptr;
+    ctx->hactive.reserve(size_t(nV) + 1);
+    int* nactive = reinterpret_cast<int*>(ctx->dCounters.p + 25);
+    {
+        const ActiveColumn is_active { ctx->hcolR.p };
+        size_t b4 = 0;
+        if (order) cub::DeviceSelect::If(nullptr, b4, order, ctx->hactive.p, nactive, nV, is_active, s);
+        else cub::DeviceSelect::If(nullptr, b4, cub::CountingInputIterator<int>(0), ctx->hactive.p, nactive, nV, is_active, s);
+        ctx->hseltmp.reserve(b4 + 256);
+        if (order) cub::DeviceSelect::If(ctx->hseltmp.p, b4, order, ctx->hactive.p, nactive, nV, is_active, s);
+        else cub::DeviceSelect::If(ctx->hseltmp.p, b4, cub::CountingInputIterator<int>(0), ctx->hactive.p, nactive, nV, is_active, s);
+        IPCB_CUDA(cudaMemsetAsync(ctx->hcnt.p, 0, (3 * size_t(nV) + 1) * sizeof(int), s));
+        IPCB_CUDA(cudaMemsetAsync(ctx->hcolU.p, 0, (size_t(nV) + 1) * sizeof(int), s));
+        ctx->launches += 2;
+    }
     st.reset();
     st.reset(new Stage(ctx, "hess_symbolic"));
     // 3. pass 1: per-column sort by row vertex, pattern counts
@@ -1510,9 +1533,6 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
         IPCB_CUDA(cudaFuncSetAttribute(k_hess_numeric_big, cudaFuncAttributeMaxDynamicSharedMemorySize, int(NUMERIC_UCAP) * (72 + 2)));
         ctx->hess_attr_set = true;
     }
-    // Morton order of the vertices from the last broad phase on this context (any permutation is valid)
-    static const bool id_order = getenv("IPCB_HESS_COLUMN_ID_ORDER") != nullptr; // A/B switch
-    const int* order = (!id_order && ctx->vorder_valid && ctx->vtree.n == nV) ? ctx->vtree.ord_sorted.p : nullptr;
     const int big_grid = NUM_SMS;
     // test hooks: lower the hand-over thresholds so that small scenes exercise the block / global-scratch paths
     int warp_cap = WARP_CAP, cta_cap = CTA_CAP;
@@ -1525,7 +1545,7 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
     if (const char* e = getenv("IPCB_HESS_BIG_HASH")) big_hash = atoi(e);
     for (int attempt = 0;; attempt++) {
         IPCB_CUDA(cudaMemsetAsync(nbig, 0, 2 * sizeof(unsigned long long), s));
-        k_hess_symbolic<<<grid_for(size_t(nV) + 1, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(A, warp_cap, use_hash, ctx->hbig.p, nbig, order);
+        k_hess_symbolic<<<grid_for(size_t(nV) + 1, SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(A, warp_cap, use_hash, ctx->hbig.p, nbig, ctx->hactive.p, nactive);
         k_hess_symbolic_big<<<big_grid, BIG_THREADS, BIG_SMEM, s>>>(A, cta_cap, big_hash, ctx->hbig.p, nbig, ctx->hscratch.p, ctx->hscratch_items,
                                                                     need);
         ctx->launches += 2;
@@ -1558,7 +1578,7 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
     IPCB_CUDA(cudaMemsetAsync(nbig2, 0, sizeof(unsigned long long), s));
 #define IPCB_NUMERIC(KERNEL, NB)                                                                                                          \
     KERNEL<NB><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,      \
-                                                ctx->outer.p, ctx->inner.p, ctx->vals.p, order, big_items, ctx->hbig.p, nbig2)
+                                                ctx->outer.p, ctx->inner.p, ctx->vals.p, ctx->hactive.p, nactive, big_items, ctx->hbig.p, nbig2)
     // IPCB_NUMERIC_LANES=9: one lane per block entry (three blocks per round); =3: one lane per block column (ten blocks per round)
     const char* nl_env = getenv("IPCB_NUMERIC_LANES");
     const int nlanes = nl_env ? atoi(nl_env) : 9;
