@@ -293,6 +293,22 @@ int IPCB_FN(barrier_hessian_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, co
 /* device pointers to the resident CSR of the last barrier_hessian (valid until the next one) */
 int IPCB_FN(barrier_hessian_dev_ptrs)(ipcb_ctx* ctx, const int32_t** d_outer, const int32_t** d_inner,
                                       const double** d_values);
+/* CollisionSetType::IMPROVED_MAX_APPROX on a SHARDED context (normal_collisions.cpp:84-128 at rank granularity).  A
+ * sub-element pair (candidates.cpp:584-695) can be derived from candidates of several ranks and its correction records
+ * (normal_collisions_builder.cpp:340-543) must be added once, so collisions_build*(…, IPCB_SET_IMPROVED_MAX_APPROX) on a
+ * sharded context stops after the rank's unique sub-element keys (it returns zero counts).  The ranks then exchange the keys:
+ *   corrections_keys_dev   n[k] = keys in the rank's list k (0: VV of EV, 1: EV of EE, 2: EV of FV, 3: VV of FV candidates)
+ *   corrections_pack_dev   the four lists, one after the other, into a device buffer of sum(n) 64-bit keys
+ *   (all-gather)
+ *   corrections_apply_dev  d_keys: for each list the keys of ALL ranks (n[k] of them, duplicates allowed), list after list;
+ *                          every rank unites them, adds the corrections of ITS slice of every united list and merges its
+ *                          records.  Afterwards the context holds the rank's part of the set: exchange it with
+ *                          collisions_pack_dev / _append_packed_dev and unite with collisions_merge(flags = 0) — correction
+ *                          records of different ranks can coincide, so the disjoint-shard shortcut does not apply. */
+int IPCB_FN(collisions_corrections_keys_dev)(ipcb_ctx* ctx, int64_t n[4]);
+int IPCB_FN(collisions_corrections_pack_dev)(ipcb_ctx* ctx, void* d_keys);
+int IPCB_FN(collisions_corrections_apply_dev)(ipcb_ctx* ctx, const void* d_keys, const int64_t n[4], int64_t counts[4]);
+
 /* The rank-to-rank exchange format of a sharded build: all records of the resident set in ONE device buffer,
  * so that one all-gather moves them.  Layout for counts n[VV..FV], every array 8-byte aligned, in this order:
  *   ids_vv (8 n0) | w_vv (8 n0) | ids_ev | w_ev | ids_ee | w_ee | eps_ee (8 n2) | ids_fv | w_fv | dtype_ee (n2, padded to 8)

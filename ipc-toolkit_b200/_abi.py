@@ -80,6 +80,9 @@ DEVICE_API = {
     "barrier_hessian_dev_ptrs": (C.c_int, [P, C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
     "collisions_dev_ptrs": (C.c_int, [P, c_i32, C.POINTER(c_i64), C.POINTER(P), C.POINTER(P), C.POINTER(P), C.POINTER(P)]),
     "collisions_append_dev": (C.c_int, [P, c_i32, c_i64, P, P, P, P]),
+    "collisions_corrections_keys_dev": (C.c_int, [P, C.POINTER(c_i64)]),
+    "collisions_corrections_pack_dev": (C.c_int, [P, P]),
+    "collisions_corrections_apply_dev": (C.c_int, [P, P, C.POINTER(c_i64), C.POINTER(c_i64)]),
     "collisions_pack_dev": (C.c_int, [P, P, c_i64, C.POINTER(c_i64)]),
     "collisions_append_packed_dev": (C.c_int, [P, P, C.POINTER(c_i64)]),
     "candidates_build_swept_dev": (C.c_int, [P, P, P, c_i32, c_f64, C.POINTER(c_i64)]),

@@ -541,7 +541,7 @@ int ipcb_collisions_build_from_candidates_dev(ipcb_ctx* ctx, const double* dV, i
     return guarded([&] {
         begin_call(ctx);
         convert_positions(ctx, dV, ld, ctx->X0);
-        collisions_build(ctx, dhat, dmin, flags);
+        collisions_build(ctx, dhat, dmin, flags, true);
         coll_counts(ctx, counts);
     });
 }
@@ -551,7 +551,29 @@ int ipcb_collisions_build_dev(ipcb_ctx* ctx, const double* dV, int32_t ld, doubl
         begin_call(ctx);
         convert_positions(ctx, dV, ld, ctx->X0);
         candidates_build(ctx, false, 0.5 * (dhat + dmin)); // normal_collisions.cpp:30
-        collisions_build(ctx, dhat, dmin, flags);
+        collisions_build(ctx, dhat, dmin, flags, true);
+        coll_counts(ctx, counts);
+    });
+}
+int ipcb_collisions_corrections_keys_dev(ipcb_ctx* ctx, int64_t n[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        collisions_corrections_keys(ctx, n);
+    });
+}
+int ipcb_collisions_corrections_pack_dev(ipcb_ctx* ctx, void* d_keys)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        collisions_corrections_pack(ctx, static_cast<unsigned long long*>(d_keys));
+    });
+}
+int ipcb_collisions_corrections_apply_dev(ipcb_ctx* ctx, const void* d_keys, const int64_t n[4], int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        collisions_corrections_apply(ctx, static_cast<const unsigned long long*>(d_keys), n);
         coll_counts(ctx, counts);
     });
 }

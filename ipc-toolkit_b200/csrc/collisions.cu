@@ -286,19 +286,31 @@ static void merge_stream_enqueue(ipcb_ctx* ctx, int kind, int64_t n, cudaStream_
 
 static void merge_streams(ipcb_ctx* ctx, const int64_t raw[4], bool disjoint = false, bool typed_ee = false);
 static void improved_max_approx_corrections(ipcb_ctx* ctx, double offset_sqr, bool area, int64_t raw[4]);
+static void improved_max_approx_keys(ipcb_ctx* ctx, double offset_sqr, int64_t nu[4]);
 
-void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
+void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags, bool may_defer)
 {
     const bool improved = (flags & IPCB_SET_IMPROVED_MAX_APPROX) != 0;
-    if (improved && ctx->shard_world > 1) // the corrections need every candidate of a sub-element pair on one rank
-        throw Error("CollisionSetType::IMPROVED_MAX_APPROX is not available on a sharded context (IPC set type only)");
+    ctx->ima_pending = false;
+    if (improved && ctx->shard_world > 1 && !may_defer) // the corrections need the sub-element keys of every rank
+        throw Error("CollisionSetType::IMPROVED_MAX_APPROX on a sharded context needs the device-resident build followed by the exchange of "
+                    "the sub-element keys (collisions_build_dev, collisions_corrections_*_dev)");
     cudaStream_t s = ctx->stream;
     int64_t total = 0;
     for (auto& c : ctx->cand) total += c.count;
     ctx->dmin = dmin;
     ctx->coll_valid = true;
     for (auto& c : ctx->coll) c.count = 0;
-    if (total == 0) return;
+    if (total == 0) {
+        if (improved && ctx->shard_world > 1) { // this rank has nothing, the others may: it still takes part in the exchange
+            for (int k = 0; k < 4; k++) ctx->ima_raw[k] = ctx->ima_nu[k] = 0;
+            ctx->ima_area = (flags & IPCB_USE_AREA_WEIGHTING) != 0;
+            ctx->ima_pending = true;
+            ctx->coll_valid = false;
+            IPCB_CUDA(cudaMemsetAsync(ctx->dCounters.p, 0, 8 * sizeof(unsigned long long), s));
+        }
+        return;
+    }
     if (total > 0x7fffffffll) throw Error("more than 2^31 candidates in one collision build");
     {
         Stage st(ctx, "classify");
@@ -342,6 +354,17 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags)
         IPCB_CUDA(cudaStreamSynchronize(s));
     }
     int64_t raw[4] = { ctx->pinned.p[0], ctx->pinned.p[1], ctx->pinned.p[2], ctx->pinned.p[3] };
+    if (improved && ctx->shard_world > 1) {
+        // A sub-element pair can be derived from candidates of several ranks, and its correction records must be added ONCE:
+        // the build stops after the rank's unique sub-element keys; the ranks exchange them (collisions_corrections_keys_dev /
+        // _pack_dev), and collisions_corrections_apply_dev finishes the rank's set from the united lists.
+        improved_max_approx_keys(ctx, (dmin + dhat) * (dmin + dhat), ctx->ima_nu);
+        for (int k = 0; k < 4; k++) ctx->ima_raw[k] = raw[k];
+        ctx->ima_area = (flags & IPCB_USE_AREA_WEIGHTING) != 0;
+        ctx->ima_pending = true;
+        ctx->coll_valid = false;
+        return;
+    }
     if (improved) improved_max_approx_corrections(ctx, (dmin + dhat) * (dmin + dhat), (flags & IPCB_USE_AREA_WEIGHTING) != 0, raw);
     // IPC set: every edge-edge / face-vertex record comes from its own candidate, so those two streams hold no
     // duplicates and need no merge — only vertex-vertex / edge-vertex records are united.  Their canonical order
@@ -928,13 +951,12 @@ static int64_t unique_keys(ipcb_ctx* ctx, int64_t n, Buf<unsigned long long>& ou
     return int64_t(h);
 }
 
-static void improved_max_approx_corrections(ipcb_ctx* ctx, double offset_sqr, bool area, int64_t raw[4])
+// step 1: the unique sub-element keys of this context's candidates: [0] VV of EV candidates, [1] EV of EE candidates, [2] EV and
+// [3] VV of FV candidates -> ctx->subuniq[k], nu[k]
+static void improved_max_approx_keys(ipcb_ctx* ctx, double offset_sqr, int64_t nu[4])
 {
-    Stage st(ctx, "improved_max_approx");
     cudaStream_t s = ctx->stream;
     if (ctx->nE >= (1 << 28)) throw Error("IMPROVED_MAX_APPROX: more than 2^28 edges");
-    ensure_adjacency(ctx);
-    const AdjView A { ctx->adjVVoff.p, ctx->adjVV.p, ctx->adjVEoff.p, ctx->adjVE.p, ctx->adjEVoff.p, ctx->adjEV.p, ctx->adjBoundary.p };
     const int64_t nev = ctx->cand[IPCB_EV].count, nee = ctx->cand[IPCB_EE].count, nfv = ctx->cand[IPCB_FV].count;
     unsigned long long* cnt = ctx->dCounters.p + 29; // [0]: keys of the current list, [1]: second list of the face-vertex pass
     auto count_of = [&](int slot) {
@@ -943,8 +965,7 @@ static void improved_max_approx_corrections(ipcb_ctx* ctx, double offset_sqr, bo
         IPCB_CUDA(cudaStreamSynchronize(s));
         return int64_t(h);
     };
-    // ---- 1. sub-element candidates, unique: [0] VV of EV candidates, [1] EV of EE candidates, [2] EV and [3] VV of FV candidates
-    int64_t nu[4] = { 0, 0, 0, 0 };
+    nu[0] = nu[1] = nu[2] = nu[3] = 0;
     if (nev) {
         ctx->subkey.reserve(2 * nev);
         IPCB_CUDA(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), s));
@@ -972,6 +993,14 @@ static void improved_max_approx_corrections(ipcb_ctx* ctx, double offset_sqr, bo
     }
     ctx->launches += 3;
     IPCB_CUDA(cudaGetLastError());
+}
+
+// steps 2 and 3: the correction records of the keys [first[k], first[k] + nu[k]) of ctx->subuniq[k], appended to the raw streams
+static void improved_max_approx_apply(ipcb_ctx* ctx, bool area, int64_t raw[4], const int64_t first[4], const int64_t nu[4])
+{
+    cudaStream_t s = ctx->stream;
+    ensure_adjacency(ctx);
+    const AdjView A { ctx->adjVVoff.p, ctx->adjVV.p, ctx->adjVEoff.p, ctx->adjVE.p, ctx->adjEVoff.p, ctx->adjEV.p, ctx->adjBoundary.p };
     // ---- 2. room for the correction records behind the classification's records
     const int64_t more_vv = nu[0] + nu[1] + nu[2] + nu[3], more_ev = nu[1] + nu[2], more_ee = nu[1] * int64_t(std::max(ctx->adj_max_ve, 1));
     CollisionSet &vv = ctx->coll[IPCB_VV], &ev = ctx->coll[IPCB_EV], &ee = ctx->coll[IPCB_EE];
@@ -984,15 +1013,74 @@ static void improved_max_approx_corrections(ipcb_ctx* ctx, double offset_sqr, bo
     const CorrOut o { vv.key_raw.p, ev.key_raw.p, ee.key_raw.p, vv.w_raw.p, ev.w_raw.p, ee.w_raw.p, ee.eps_raw.p, ee.dt_raw.p,
                       ctx->dCounters.p + 1 + IPCB_VV, ctx->dCounters.p + 1 + IPCB_EV, ctx->dCounters.p + 1 + IPCB_EE };
     const int ar = area ? 1 : 0;
-    if (nu[0]) k_corr_vv<<<grid_for(nu[0], 256), 256, 0, s>>>(nu[0], ctx->subuniq[0].p, A, ctx->dVArea.p, ar, 0, o);
-    if (nu[1]) k_corr_ev_from_ee<<<grid_for(nu[1], 256), 256, 0, s>>>(nu[1], ctx->subuniq[1].p, A, ctx->dE.p, ctx->X0.p, ctx->dRest.p, ctx->dEArea.p, ar, o);
-    if (nu[2]) k_corr_ev_from_fv<<<grid_for(nu[2], 256), 256, 0, s>>>(nu[2], ctx->subuniq[2].p, A, ctx->dE.p, ctx->X0.p, ctx->dVArea.p, ar, o);
-    if (nu[3]) k_corr_vv<<<grid_for(nu[3], 256), 256, 0, s>>>(nu[3], ctx->subuniq[3].p, A, ctx->dVArea.p, ar, 1, o);
+    if (nu[0]) k_corr_vv<<<grid_for(nu[0], 256), 256, 0, s>>>(nu[0], ctx->subuniq[0].p + first[0], A, ctx->dVArea.p, ar, 0, o);
+    if (nu[1])
+        k_corr_ev_from_ee<<<grid_for(nu[1], 256), 256, 0, s>>>(nu[1], ctx->subuniq[1].p + first[1], A, ctx->dE.p, ctx->X0.p, ctx->dRest.p, ctx->dEArea.p,
+                                                              ar, o);
+    if (nu[2]) k_corr_ev_from_fv<<<grid_for(nu[2], 256), 256, 0, s>>>(nu[2], ctx->subuniq[2].p + first[2], A, ctx->dE.p, ctx->X0.p, ctx->dVArea.p, ar, o);
+    if (nu[3]) k_corr_vv<<<grid_for(nu[3], 256), 256, 0, s>>>(nu[3], ctx->subuniq[3].p + first[3], A, ctx->dVArea.p, ar, 1, o);
     ctx->launches += 5;
     IPCB_CUDA(cudaGetLastError());
     IPCB_CUDA(cudaMemcpyAsync(ctx->pinned.p, ctx->dCounters.p + 1, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
     IPCB_CUDA(cudaStreamSynchronize(s));
     for (int k = 0; k < 4; k++) raw[k] = ctx->pinned.p[k];
+}
+
+static void improved_max_approx_corrections(ipcb_ctx* ctx, double offset_sqr, bool area, int64_t raw[4])
+{
+    Stage st(ctx, "improved_max_approx");
+    int64_t nu[4];
+    const int64_t first[4] = { 0, 0, 0, 0 };
+    improved_max_approx_keys(ctx, offset_sqr, nu);
+    improved_max_approx_apply(ctx, area, raw, first, nu);
+}
+
+// ---- IMPROVED_MAX_APPROX on a sharded context: the exchange of the sub-element keys -------------------------------------------
+void collisions_corrections_keys(ipcb_ctx* ctx, int64_t n[4])
+{
+    if (!ctx->ima_pending) throw Error("no deferred IMPROVED_MAX_APPROX build on this context");
+    for (int k = 0; k < 4; k++) n[k] = ctx->ima_nu[k];
+}
+// the four lists one after the other
+void collisions_corrections_pack(ipcb_ctx* ctx, unsigned long long* d_out)
+{
+    if (!ctx->ima_pending) throw Error("no deferred IMPROVED_MAX_APPROX build on this context");
+    int64_t off = 0;
+    for (int k = 0; k < 4; k++) {
+        if (ctx->ima_nu[k])
+            IPCB_CUDA(cudaMemcpyAsync(d_out + off, ctx->subuniq[k].p, sizeof(unsigned long long) * ctx->ima_nu[k], cudaMemcpyDeviceToDevice, ctx->stream));
+        off += ctx->ima_nu[k];
+    }
+    IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+// d_keys: for each of the four lists the keys of ALL ranks (n[k] of them, duplicates allowed), list after list.  Every rank
+// unites them (sort + unique: the same list everywhere) and adds the corrections of its slice of every list.
+void collisions_corrections_apply(ipcb_ctx* ctx, const unsigned long long* d_keys, const int64_t n[4])
+{
+    if (!ctx->ima_pending) throw Error("no deferred IMPROVED_MAX_APPROX build on this context");
+    Stage st(ctx, "improved_max_approx");
+    cudaStream_t s = ctx->stream;
+    int64_t first[4], nu[4], raw[4], off = 0;
+    for (int k = 0; k < 4; k++) {
+        first[k] = nu[k] = 0;
+        raw[k] = ctx->ima_raw[k];
+        if (n[k]) {
+            ctx->subkey.reserve(n[k]);
+            IPCB_CUDA(cudaMemcpyAsync(ctx->subkey.p, d_keys + off, sizeof(unsigned long long) * n[k], cudaMemcpyDeviceToDevice, s));
+            const int64_t u = unique_keys(ctx, n[k], ctx->subuniq[k]);
+            first[k] = u * ctx->shard_rank / ctx->shard_world;
+            nu[k] = u * (ctx->shard_rank + 1) / ctx->shard_world - first[k];
+        }
+        off += n[k];
+    }
+    // the append counters of the raw streams continue where the classification stopped (other calls may have used them since)
+    unsigned long long h_raw[4] = { (unsigned long long)raw[0], (unsigned long long)raw[1], (unsigned long long)raw[2], (unsigned long long)raw[3] };
+    IPCB_CUDA(cudaMemcpyAsync(ctx->dCounters.p + 1, h_raw, sizeof h_raw, cudaMemcpyHostToDevice, s));
+    IPCB_CUDA(cudaStreamSynchronize(s));
+    improved_max_approx_apply(ctx, ctx->ima_area, raw, first, nu);
+    ctx->ima_pending = false;
+    ctx->coll_valid = true;
+    merge_streams(ctx, raw, false, true);
 }
 
 } // namespace ipcb

@@ -193,6 +193,9 @@ struct ipcb_ctx {
     // IMPROVED_MAX_APPROX: adjacency tables (collision_mesh.cpp:247-307) as CSR, built on first use;
     // sub-element candidate keys
     bool adj_ready = false;
+    // deferred IMPROVED_MAX_APPROX build of a sharded context (collisions.cu: collisions_corrections_*)
+    bool ima_pending = false, ima_area = false;
+    int64_t ima_raw[4] = { 0, 0, 0, 0 }, ima_nu[4] = { 0, 0, 0, 0 };
     int adj_max_ve = 0; // largest number of edges at a vertex
     ipcb::Buf<int> adjVVoff, adjVV, adjVEoff, adjVE, adjEVoff, adjEV;
     ipcb::Buf<unsigned char> adjBoundary;
@@ -288,13 +291,16 @@ void sort_pairs(ipcb_ctx* ctx, PairList& pl);
 bool has_intersections(ipcb_ctx* ctx, double inflation_radius);
 
 // collisions (collisions.cu)
-void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags);
+void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags, bool may_defer = false);
 void collisions_clear(ipcb_ctx* ctx);
 void collisions_append_dev(ipcb_ctx* ctx, int kind, int64_t n, const int32_t* d_ids, const double* d_w, const double* d_eps,
                            const uint8_t* d_dt);
 void collisions_append_packed_dev(ipcb_ctx* ctx, const void* d_buffer, const int64_t n[4], const int64_t ids_off[4], const int64_t w_off[4],
                                   int64_t eps_off, int64_t dt_off);
 void collisions_merge(ipcb_ctx* ctx, double dmin, int flags);
+void collisions_corrections_keys(ipcb_ctx* ctx, int64_t n[4]);
+void collisions_corrections_pack(ipcb_ctx* ctx, unsigned long long* d_out);
+void collisions_corrections_apply(ipcb_ctx* ctx, const unsigned long long* d_keys, const int64_t n[4]);
 void collisions_sort(ipcb_ctx* ctx, int kind);
 double collisions_min_distance(ipcb_ctx* ctx);
 

@@ -178,6 +178,7 @@ class DeviceShardedStep:
         self.rows = (0, mesh.num_vertices())
         self.shard_counts = [0, 0, 0, 0]
         self.after = None  # optional callback(ctx) after every library call (bench.py collects stage times)
+        self.improved = False
         self.side = self.ev_packed = self.ev_gathered = None
         if self.row_block:
             self.side = torch.cuda.Stream()
@@ -266,13 +267,49 @@ class DeviceShardedStep:
                 continue
             c = (C.c_int64 * 4)(*self.all_counts[r])
             lib.check(lib.collisions_append_packed_dev(self.ctx, C.c_void_p(self.recv.data_ptr() + r * self.cap + self.HEADER), c))
-        lib.check(lib.collisions_merge(self.ctx, dmin, 1, self.counts))  # 1 = IPCB_MERGE_DISJOINT_SHARDS
+        # 1 = IPCB_MERGE_DISJOINT_SHARDS; IMPROVED_MAX_APPROX correction records of different ranks can coincide: full merge
+        lib.check(lib.collisions_merge(self.ctx, dmin, 0 if self.improved else 1, self.counts))
         self._done()
         bounds = self.mesh.balanced_row_blocks(self.world)
         self.rows = (int(bounds[self.rank]), int(bounds[self.rank + 1]))
 
-    def step(self, dV0, dV1, d_energy, d_grad, d_step, dhat, bp, ccd, dmin=0.0, min_distance=0.0, psd=1):
+    def exchange_correction_keys(self):
+        """CollisionSetType::IMPROVED_MAX_APPROX over ranks (include/ipcb200.h, collisions_corrections_*): the build stopped
+        after this rank's unique sub-element keys; all-gather the four key lists, let every rank unite them and add the
+        corrections of its slice.  Sizes first (one small all-gather), then one padded all-gather of the keys."""
+        torch, lib, dist = self.torch, self.lib, self.dist
+        n = (C.c_int64 * 4)()
+        lib.check(lib.collisions_corrections_keys_dev(self.ctx, n))
+        mine = torch.tensor(list(n), dtype=torch.int64, device="cuda")
+        every = torch.empty(self.world * 4, dtype=torch.int64, device="cuda")
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(every, mine)
+        self.stream.synchronize()
+        every = every.view(self.world, 4).tolist()
+        slot = max(1, max(sum(c) for c in every))
+        send = torch.zeros(slot, dtype=torch.int64, device="cuda")
+        recv = torch.empty(slot * self.world, dtype=torch.int64, device="cuda")
+        if sum(n) > 0:
+            lib.check(lib.collisions_corrections_pack_dev(self.ctx, C.c_void_p(send.data_ptr())))
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(recv, send)
+            parts, totals = [], []
+            for k in range(4):  # list k of every rank, one after the other
+                for r in range(self.world):
+                    off = r * slot + sum(every[r][:k])
+                    parts.append(recv[off:off + every[r][k]])
+                totals.append(sum(every[r][k] for r in range(self.world)))
+            keys = torch.cat(parts) if sum(totals) > 0 else torch.zeros(1, dtype=torch.int64, device="cuda")
+        self.stream.synchronize()
+        lib.check(lib.collisions_corrections_apply_dev(self.ctx, C.c_void_p(keys.data_ptr()), (C.c_int64 * 4)(*totals), self.counts))
+        self._done()
+
+    def step(self, dV0, dV1, d_energy, d_grad, d_step, dhat, bp, ccd, dmin=0.0, min_distance=0.0, psd=1, flags=0):
+        """flags: IPCB_USE_AREA_WEIGHTING (1) | IPCB_SET_IMPROVED_MAX_APPROX (2); the latter needs the row-block form"""
         torch, lib, dist, ctx = self.torch, self.lib, self.dist, self.ctx
+        self.improved = bool(flags & 2) and self.world > 1
+        if self.improved and not self.row_block:
+            raise ValueError("IMPROVED_MAX_APPROX over ranks needs the united set (row_block=True)")
         nV = self.mesh.num_vertices()
         p0, p1 = C.c_void_p(dV0.data_ptr()), C.c_void_p(dV1.data_ptr())
         pstep = C.c_void_p(d_step.data_ptr())
@@ -286,8 +323,10 @@ class DeviceShardedStep:
             self.ev_start.record(self.stream)
             self.stream_b.wait_event(self.ev_start)  # the caller's inputs are ready when the first lane's stream gets here
             job = self.lane.submit(lambda: ccd_half(self.ctx_b))
-        lib.check(lib.collisions_build_dev(ctx, p0, nV, dhat, dmin, 0, self.counts))
+        lib.check(lib.collisions_build_dev(ctx, p0, nV, dhat, dmin, flags, self.counts))
         self._done()
+        if self.improved:
+            self.exchange_correction_keys()
         if self.row_block:
             self.start_exchange()
         else:

@@ -407,8 +407,9 @@ def test_line_search_rebuild_from_resident_candidates(cuda, oracle, scenes, name
 
 
 def test_unsupported_set_types_fail_loudly(cuda, scenes):
-    """OGC is outside the path; IMPROVED_MAX_APPROX needs all candidates of a sub-element pair on one rank, so a sharded
-    context must refuse it instead of silently building something else"""
+    """OGC is outside the path; IMPROVED_MAX_APPROX on a sharded context needs the exchange of the sub-element keys
+    (collisions_corrections_*_dev, tests/test_zz_improved_max_approx_gpu.py), so the host-buffer build must refuse it
+    instead of silently building something else"""
     V0, V1, E, F, P = _scene(scenes, "stack")
     mesh = cuda.CollisionMesh(V0, E, F)
     c = cuda.NormalCollisions()

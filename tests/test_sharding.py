@@ -170,7 +170,7 @@ def test_two_rank_contact_step_nccl(cuda, row_block):
     _check(_run("nccl", row_block=row_block))
 
 
-def _device_worker(rank, world, port, queue):
+def _device_worker(rank, world, port, queue, flags=0):
     """the device-resident sharded step of bench.py (DeviceShardedStep) against the single-context step on the same GPU"""
     try:
         import ctypes as C
@@ -207,7 +207,7 @@ def _device_worker(rank, world, port, queue):
             steppers.append(st)
             e, g, s = (torch.zeros(n, dtype=torch.float64, device="cuda") for n in (1, 3 * nV, 1))
             for _ in range(2):  # twice: buffers are reused across steps
-                nnz = st.step(dV0, dV1, e, g, s, P["dhat"], bp, ccd)
+                nnz = st.step(dV0, dV1, e, g, s, P["dhat"], bp, ccd, flags=flags)
             torch.cuda.synchronize()
             outer, inner, vals = np.zeros(3 * nV + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
             lib.check(lib.barrier_hessian_fetch(mesh._ctx, outer.ctypes.data_as(C.c_void_p), inner.ctypes.data_as(C.c_void_p),
@@ -271,6 +271,31 @@ def test_device_sharded_step_nccl(cuda):
     rows = [r["rows"] for r in results]
     assert rows[0][0] == 0 and all(rows[k][1] == rows[k + 1][0] for k in range(world - 1))
     assert sum(r["nnz"] for r in results) == results[0]["nnz_all"]  # the row blocks tile the matrix
+
+
+@pytest.mark.gpu
+def test_device_sharded_step_improved_max_approx_nccl(cuda):
+    """CollisionSetType::IMPROVED_MAX_APPROX over NCCL ranks: the sub-element keys are exchanged before the corrections
+    (DeviceShardedStep.exchange_correction_keys), and the step equals the single-context step with the same set type"""
+    import torch
+    import torch.multiprocessing as mp
+
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_device_worker, args=(r, world, port, q, 2)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = _collect(q, procs)
+    tol = _step_tolerance(lambda s: s.cloth_stack(4, 40), [x for r in results for x in r["step"]])
+    for r in results:
+        assert r["same_set"] and r["outside"] == 0 and r["pattern"] and r["hess"] <= 1e-10, r
+        assert r["energy"] <= 1e-12 and r["grad"] <= 1e-12
+        assert abs(r["step"][0] - r["step"][1]) <= tol, (r["step"], tol)
+    assert sum(r["nnz"] for r in results) == results[0]["nnz_all"]
 
 
 def _empty_worker(rank, world, port, queue):

@@ -69,3 +69,88 @@ def test_parity_with_the_oracle(cuda, oracle, scenes, name, area):
         D = A - Bm
         assert np.sqrt(D.multiply(D).sum()) <= RTOL * np.sqrt(Bm.multiply(Bm).sum()), h
         assert np.array_equal(A.indptr, Bm.indptr) and np.array_equal(A.indices, Bm.indices), h + ": sparsity pattern differs"
+
+
+@pytest.mark.parametrize("name", ["stack", "drape", "dense"])
+@pytest.mark.parametrize("area", [False, True])
+def test_sharded_build_unites_to_the_single_context_set(cuda, scenes, name, area):
+    """IMPROVED_MAX_APPROX over ranks (include/ipcb200.h: collisions_corrections_*_dev): three pretend ranks on one device each
+    build from their candidate shard, exchange the sub-element keys (here: through one buffer), add the corrections of their
+    slice of the united key lists, and the united records are the single-context set — ids, distance types and eps_x
+    bit-exact, weights to rounding."""
+    import ctypes as C
+
+    import torch
+
+    V0, V1, E, F, P = {
+        "stack": lambda: scenes.cloth_stack(3, 30),
+        "drape": lambda: scenes.cloth_on_sphere(48, 24, drape=True),
+        "dense": lambda: scenes.dense_sheet(10, 2.0),
+    }[name]()
+    dhat, lib, world = P["dhat"], cuda.lib, 3
+    flags = 2 | (1 if area else 0)
+    nV = V0.shape[0]
+    one = cuda.CollisionMesh(V0, E, F)
+    c = cuda.NormalCollisions()
+    c.set_use_area_weighting(area)
+    c.set_collision_set_type(cuda.NormalCollisions.CollisionSetType.IMPROVED_MAX_APPROX)
+    c.build(one, V0, dhat)
+    want = [getattr(c, k + "_collisions") for k in ("vv", "ev", "ee", "fv")]
+    assert sum(len(s.ids) for s in want) > 0
+    dV = torch.from_numpy(np.asfortranarray(V0).T.copy()).cuda()
+    meshes = [cuda.CollisionMesh(V0, E, F) for _ in range(world)]
+    counts = (C.c_int64 * 4)()
+    key_counts, key_bufs = [], []
+    for r, m in enumerate(meshes):
+        lib.check(lib.ctx_set_shard(m._ctx, r, world))
+        lib.check(lib.collisions_build_dev(m._ctx, C.c_void_p(dV.data_ptr()), nV, dhat, 0.0, flags, counts))
+        assert list(counts) == [0, 0, 0, 0]  # deferred: nothing to see before the corrections
+        n = (C.c_int64 * 4)()
+        lib.check(lib.collisions_corrections_keys_dev(m._ctx, n))
+        buf = torch.zeros(max(1, sum(n)), dtype=torch.int64, device="cuda")
+        if sum(n):
+            lib.check(lib.collisions_corrections_pack_dev(m._ctx, C.c_void_p(buf.data_ptr())))
+        key_counts.append(list(n)), key_bufs.append(buf)
+    assert sum(sum(n) for n in key_counts) > 0
+    parts, totals = [], []
+    for k in range(4):
+        for r in range(world):
+            off = sum(key_counts[r][:k])
+            parts.append(key_bufs[r][off:off + key_counts[r][k]])
+        totals.append(sum(key_counts[r][k] for r in range(world)))
+    keys = torch.cat(parts)
+    packed = []
+    for m in meshes:
+        lib.check(lib.collisions_corrections_apply_dev(m._ctx, C.c_void_p(keys.data_ptr()), (C.c_int64 * 4)(*totals), counts))
+        cnt = list(counts)
+        nbytes = 16 * (cnt[0] + cnt[1] + cnt[3]) + 24 * cnt[2] + (cnt[2] + 7) // 8 * 8
+        buf = torch.zeros(max(16, nbytes), dtype=torch.uint8, device="cuda")
+        got = C.c_int64()
+        if sum(cnt):
+            lib.check(lib.collisions_pack_dev(m._ctx, C.c_void_p(buf.data_ptr()), buf.numel(), C.byref(got)))
+        packed.append((cnt, buf))
+    assert sum(sum(cnt) for cnt, _ in packed) > 0
+    united = meshes[0]
+    lib.check(lib.collisions_clear(united._ctx))
+    for cnt, buf in packed:
+        if sum(cnt):
+            lib.check(lib.collisions_append_packed_dev(united._ctx, C.c_void_p(buf.data_ptr()), (C.c_int64 * 4)(*cnt)))
+    lib.check(lib.collisions_merge(united._ctx, 0.0, 0, counts))
+    torch.cuda.synchronize()
+    got = cuda.NormalCollisions()
+    got._bind(united, counts, 0.0)  # the context's resident set, as the API object
+    have = [getattr(got, k + "_collisions") for k in ("vv", "ev", "ee", "fv")]
+    for kind, (sa, sb) in enumerate(zip(have, want)):
+        scale = max(np.abs(sb.weight).max(), 1e-300) if len(sb.weight) else 1.0
+        ka, kb = np.abs(sa.weight) > 1e-12 * scale, np.abs(sb.weight) > 1e-12 * scale
+        assert np.array_equal(sa.ids[ka], sb.ids[kb]), "kind %d" % kind
+        assert np.array_equal(sa.dtype[ka], sb.dtype[kb]) and np.array_equal(sa.eps_x[ka], sb.eps_x[kb])
+        assert relerr(sa.weight[ka], sb.weight[kb]) <= 1e-12
+    # a host-buffer build on a sharded context cannot run the exchange: it must refuse
+    with pytest.raises(RuntimeError, match="IMPROVED_MAX_APPROX"):
+        c2 = cuda.NormalCollisions()
+        c2.set_collision_set_type(cuda.NormalCollisions.CollisionSetType.IMPROVED_MAX_APPROX)
+        c2.build(meshes[1], V0, dhat)
+    del dV, keys, key_bufs, packed
+    for m in meshes:
+        m.close()
