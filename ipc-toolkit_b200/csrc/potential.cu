@@ -1705,7 +1705,9 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
                 const int64_t nslow = ctx->pinned.p[11];
                 if (nslow) {
                     Stage ks(ctx, "k:k_hessian_local<EE>(mollified)", s);
-                    k_hessian_local<IPCB_EE><<<grid_for(nslow, 128), 128, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, nslow, sel[2], n2);
+                    // a short list (a few thousand mollified pairs): one warp per block spreads it over every SM's FP64 pipe
+                    const int bs = nslow < int64_t(NUM_SMS) * 512 ? 32 : 128;
+                    k_hessian_local<IPCB_EE><<<grid_for(nslow, bs), bs, 0, s>>>(view(ctx, 2), m, B, psd_mode, gi0[2], inc0[2], outs[2], ctx->hslow.p, nslow, sel[2], n2);
                     ctx->launches++;
                 }
             }
