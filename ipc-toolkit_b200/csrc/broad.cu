@@ -679,50 +679,41 @@ template <int MODE, int QN, int TN, bool FILTERED>
 __global__ void __launch_bounds__(TRAV_BLOCK)
     k_traverse(int q_begin, int q_end, const FBox* __restrict__ qbox, const int4* __restrict__ qprim,
                const Node* __restrict__ nodes, int n_target, const FBox* __restrict__ tbox, const int4* __restrict__ tprim,
-               int2* __restrict__ out, unsigned long long* counter, unsigned long long capacity, int flags, FilterView filter, int chunk)
+               int2* __restrict__ out, unsigned long long* counter, unsigned long long capacity, int flags, FilterView filter)
 {
     const bool check_shared = flags & 1;
     constexpr bool filtered = FILTERED; // a template parameter: the unfiltered kernel keeps its 56 registers
     __shared__ int2 stage[TRAV_BLOCK / 32][STAGE_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // Every warp owns `chunk` consecutive (Morton-ordered) queries.  A lane that has finished its walk takes the next query of
-    // the chunk right away, so the warp does not idle behind its longest walk (the walks of neighbouring queries differ by 2-3x
-    // in length); chunk = 32 is one query per lane.
-    int next = q_begin + (blockIdx.x * (TRAV_BLOCK / 32) + warp) * chunk; // warp-uniform: first unassigned query
-    const int chunk_end = next < q_end ? min(q_end, next + chunk) : next;
-    int qi = -1;
+    const int qi = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = qi < q_end;
     FBox q;
     int4 qp = make_int4(-1, -1, -1, -1);
+    if (active) {
+        q = qbox[qi];
+        qp = qprim[qi];
+    }
     int stack[96];
     int sp = 0;
     int node = 0;
     int nstaged = 0;
-    bool walking = false;
+    int single = -1; // n_target == 1: the only leaf
+    if (n_target == 1) {
+        if (active && MODE != 2) {
+            const FBox b = tbox[0];
+            if (q.lo[0] <= b.hi[0] && b.lo[0] <= q.hi[0] && q.lo[1] <= b.hi[1] && b.lo[1] <= q.hi[1] && q.lo[2] <= b.hi[2]
+                && b.lo[2] <= q.hi[2])
+                single = 0;
+        }
+    }
+    bool walking = active && n_target > 1;
     // Leaf hits need the target primitive's vertex ids (shared-vertex rejection, primitive id): a dependent
     // scattered load.  It is software-pipelined: the ids of the hits found at one node are requested right away
     // and consumed one iteration later, after the NEXT node's fetch has been issued, so the two latencies overlap.
-    int pend0 = -1, pend1 = -1;
+    int pend0 = single, pend1 = -1;
     int4 tp0 = make_int4(0, 0, 0, 0), tp1 = tp0;
-    for (;;) {
-        const bool idle = !walking && pend0 < 0 && pend1 < 0;
-        const unsigned need = __ballot_sync(0xffffffffu, idle);
-        if (need && next < chunk_end) {
-            const int mine = next + __popc(need & ((1u << lane) - 1));
-            if (idle && mine < chunk_end) {
-                qi = mine, q = qbox[qi], qp = qprim[qi];
-                sp = 0, node = 0;
-                if (n_target > 1) {
-                    walking = true;
-                } else if (MODE != 2) { // the only leaf
-                    const FBox b = tbox[0];
-                    if (q.lo[0] <= b.hi[0] && b.lo[0] <= q.hi[0] && q.lo[1] <= b.hi[1] && b.lo[1] <= q.hi[1] && q.lo[2] <= b.hi[2]
-                        && b.lo[2] <= q.hi[2])
-                        pend0 = 0, tp0 = __ldg(tprim);
-                }
-            }
-            next += __popc(need);
-        }
-        if (!__any_sync(0xffffffffu, walking || pend0 >= 0 || pend1 >= 0)) break;
+    if (pend0 >= 0) tp0 = __ldg(tprim + pend0);
+    while (__any_sync(0xffffffffu, walking || pend0 >= 0 || pend1 >= 0)) {
         float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
         int4 d = make_int4(0, 0, 0, 0);
         if (walking) {
@@ -774,7 +765,11 @@ __global__ void __launch_bounds__(TRAV_BLOCK)
             const bool tl = ol && d.x >= 0, tr = orr && d.y >= 0;
             if (tl) {
                 node = d.x;
-                if (tr) stack[sp++] = d.y; // (an L1 prefetch of the deferred sibling was measured: no effect)
+                if (tr) {
+                    stack[sp++] = d.y;
+                    // the deferred sibling will be fetched when it is popped: ask for its line now (A/B: IPCB_TRAV_PREFETCH)
+                    if (flags & 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + d.y));
+                }
             } else if (tr) {
                 node = d.y;
             } else if (sp > 0) {
@@ -800,36 +795,27 @@ template <int MODE, int QN, int TN, bool FILTERED>
 __global__ void __launch_bounds__(TRAV_BLOCK)
     k_traverse4(int q_begin, int q_end, const FBox* __restrict__ qbox, const int4* __restrict__ qprim, const Node4* __restrict__ nodes,
                 int n_target, const int4* __restrict__ tprim, int2* __restrict__ out, unsigned long long* counter, unsigned long long capacity,
-                int flags, FilterView filter, int chunk)
+                int flags, FilterView filter)
 {
     __shared__ int2 stage[TRAV_BLOCK / 32][STAGE_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int qi = q_begin + blockIdx.x * blockDim.x + threadIdx.x;
     const bool check_shared = flags & 1;
-    int next = q_begin + (blockIdx.x * (TRAV_BLOCK / 32) + warp) * chunk; // see k_traverse
-    const int chunk_end = next < q_end ? min(q_end, next + chunk) : next;
-    int qi = -1;
+    const bool active = qi < q_end;
     FBox q;
     int4 qp = make_int4(-1, -1, -1, -1);
+    if (active) {
+        q = qbox[qi];
+        qp = qprim[qi];
+    }
     int stack[128];
     int sp = 0, node = 0, nstaged = 0;
-    bool walking = false;
+    bool walking = active && n_target > 1;
     int pend[4] = { -1, -1, -1, -1 };
     int4 tp[4];
 #pragma unroll
     for (int h = 0; h < 4; h++) tp[h] = make_int4(0, 0, 0, 0);
-    for (;;) {
-        const bool idle = !walking && pend[0] < 0 && pend[1] < 0 && pend[2] < 0 && pend[3] < 0;
-        const unsigned need = __ballot_sync(0xffffffffu, idle);
-        if (need && next < chunk_end) {
-            const int mine = next + __popc(need & ((1u << lane) - 1));
-            if (idle && mine < chunk_end) {
-                qi = mine, q = qbox[qi], qp = qprim[qi];
-                sp = 0, node = 0;
-                walking = n_target > 1;
-            }
-            next += __popc(need);
-        }
-        if (!__any_sync(0xffffffffu, walking || pend[0] >= 0 || pend[1] >= 0 || pend[2] >= 0 || pend[3] >= 0)) break;
+    while (__any_sync(0xffffffffu, walking || pend[0] >= 0 || pend[1] >= 0 || pend[2] >= 0 || pend[3] >= 0)) {
         float4 lx, ly, lz, hx, hy, hz;
         int4 ch = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN), la = make_int4(0, 0, 0, 0);
         lx = ly = lz = hx = hy = hz = make_float4(0, 0, 0, 0);
@@ -1060,11 +1046,10 @@ struct TraverseJob {
         unsigned long long* counter = ctx->dCounters.p + 16 + slot;
         IPCB_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s));
         const unsigned long long cap = out->pairs.cap;
-        // queries per warp (k_traverse: lanes refill from their warp's chunk); IPCB_TRAV_CHUNK=32 is one query per lane
-        static const int chunk = getenv("IPCB_TRAV_CHUNK") ? std::max(32, atoi(getenv("IPCB_TRAV_CHUNK"))) : 128;
-        const unsigned grid = grid_for(size_t((q_end - q_begin + chunk - 1) / chunk) * 32, TRAV_BLOCK);
+        const unsigned grid = grid_for(q_end - q_begin, TRAV_BLOCK);
         Stage kt(ctx, mode == 2 && qn == 2 ? "k:k_traverse<EE>" : (mode == 1 && tn == 3 ? "k:k_traverse<FV>" : "k:k_traverse<other>"), s);
-        const int flags = (check_shared ? 1 : 0) | (ctx->filter_on() ? 2 : 0);
+        static const int prefetch = getenv("IPCB_TRAV_PREFETCH") ? 4 : 0;
+        const int flags = (check_shared ? 1 : 0) | (ctx->filter_on() ? 2 : 0) | prefetch;
         const FilterView filter { ctx->filter_patches ? ctx->dPatch.p : nullptr, ctx->filter_n_dynamic };
         if (sap) {
             enqueue_sap(counter, cap, flags, filter);
@@ -1075,16 +1060,16 @@ struct TraverseJob {
     if (t->has_nodes4 && t->n > 2) {                                                                                                    \
         if (flags & 2)                                                                                                                  \
             k_traverse4<M, QN, TN, true><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes4.p, t->n, t->sprim.p, \
-                                                                     out->pairs.p, counter, cap, flags, filter, chunk);                       \
+                                                                     out->pairs.p, counter, cap, flags, filter);                       \
         else                                                                                                                            \
             k_traverse4<M, QN, TN, false><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes4.p, t->n, t->sprim.p, \
-                                                                      out->pairs.p, counter, cap, flags, filter, chunk);                      \
+                                                                      out->pairs.p, counter, cap, flags, filter);                      \
     } else if (flags & 2)                                                                                                                      \
         k_traverse<M, QN, TN, true><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes.p, t->n, t->sbox.p, t->sprim.p, \
-                                                                out->pairs.p, counter, cap, flags, filter, chunk);                             \
+                                                                out->pairs.p, counter, cap, flags, filter);                             \
     else                                                                                                                                \
         k_traverse<M, QN, TN, false><<<grid, TRAV_BLOCK, 0, s>>>(q_begin, q_end, q->sbox.p, q->sprim.p, t->nodes.p, t->n, t->sbox.p, t->sprim.p, \
-                                                                 out->pairs.p, counter, cap, flags, filter, chunk)
+                                                                 out->pairs.p, counter, cap, flags, filter)
         switch (mode * 100 + qn * 10 + tn) {
         case 211: IPCB_TRAVERSE(2, 1, 1); break; // vertex - vertex
         case 21: IPCB_TRAVERSE(0, 2, 1); break;  // edges walk the vertex tree
