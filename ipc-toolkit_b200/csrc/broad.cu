@@ -765,11 +765,10 @@ __global__ void __launch_bounds__(TRAV_BLOCK)
             const bool tl = ol && d.x >= 0, tr = orr && d.y >= 0;
             if (tl) {
                 node = d.x;
-                if (tr) {
-                    stack[sp++] = d.y;
-                    // the deferred sibling will be fetched when it is popped: ask for its line now (A/B: IPCB_TRAV_PREFETCH)
-                    if (flags & 4) asm volatile("prefetch.global.L1 [%0];" ::"l"(nodes + d.y));
-                }
+                // measured and rejected: an L1 prefetch of the deferred sibling (no effect); lanes refilling from a per-warp chunk of
+                // queries when their walk ends (persistent walk: 2.0 -> 3.0 ms — the lanes of a warp then sit at different depths
+                // of the tree and the fetches near the root, which all lanes share when they start together, stop coalescing)
+                if (tr) stack[sp++] = d.y;
             } else if (tr) {
                 node = d.y;
             } else if (sp > 0) {
@@ -1048,8 +1047,7 @@ struct TraverseJob {
         const unsigned long long cap = out->pairs.cap;
         const unsigned grid = grid_for(q_end - q_begin, TRAV_BLOCK);
         Stage kt(ctx, mode == 2 && qn == 2 ? "k:k_traverse<EE>" : (mode == 1 && tn == 3 ? "k:k_traverse<FV>" : "k:k_traverse<other>"), s);
-        static const int prefetch = getenv("IPCB_TRAV_PREFETCH") ? 4 : 0;
-        const int flags = (check_shared ? 1 : 0) | (ctx->filter_on() ? 2 : 0) | prefetch;
+        const int flags = (check_shared ? 1 : 0) | (ctx->filter_on() ? 2 : 0);
         const FilterView filter { ctx->filter_patches ? ctx->dPatch.p : nullptr, ctx->filter_n_dynamic };
         if (sap) {
             enqueue_sap(counter, cap, flags, filter);
