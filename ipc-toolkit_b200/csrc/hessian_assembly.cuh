@@ -80,6 +80,7 @@ struct HessOut {
     unsigned long long* inc; // incidences: (vertex << 32) | (gi * 4 + a), NP per collision
     int v_lo, v_hi;          // owned vertex range (row block of a sharded Hessian); incidences of other
     int v_none;              // vertices get the vertex key v_none (= nV: sorted behind every column)
+    int records_done;        // the ids / incidences were written by k_write_records already: write_record only reports `own`
 };
 constexpr int HSLOTS = 16;
 __host__ __device__ constexpr int tri_count(int np) { return np * (np + 1) / 2; }
@@ -93,13 +94,14 @@ __device__ __forceinline__ unsigned mask_transpose(unsigned m)
 // returns the mask of the stencil points whose vertex this rank owns
 template <int NP> __device__ inline unsigned write_record(const HessOut& out, int64_t gi, int64_t inc_base, const int* vid)
 {
-    out.vid[gi] = make_int4(vid[0], vid[1], NP > 2 ? vid[2] : -1, NP > 3 ? vid[3] : -1);
+    if (!out.records_done) out.vid[gi] = make_int4(vid[0], vid[1], NP > 2 ? vid[2] : -1, NP > 3 ? vid[3] : -1);
     unsigned own = 0;
 #pragma unroll
     for (int a = 0; a < NP; a++) {
         const bool mine = vid[a] >= out.v_lo && vid[a] < out.v_hi;
         own |= unsigned(mine) << a;
-        out.inc[inc_base + a] = ((unsigned long long)(unsigned)(mine ? vid[a] : out.v_none) << 32) | (unsigned long long)(gi * 4 + a);
+        if (!out.records_done)
+            out.inc[inc_base + a] = ((unsigned long long)(unsigned)(mine ? vid[a] : out.v_none) << 32) | (unsigned long long)(gi * 4 + a);
     }
     return own;
 }
@@ -135,6 +137,10 @@ inline void hess_block_offsets(const int64_t nk[4], int64_t blk0[4])
 // records of nk[VV..FV] collisions (written by the local kernels at hvid / hmask / hblk / hkey, kinds in that order)
 // -> the context's resident compressed columns (outer / inner / vals, nnz); potential.cu
 void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4]);
+// the same in two halves: everything that only needs the records' ids (incidence sort, column ranges, active columns) on
+// stream `s` — it can run beside the kernels that compute the blocks —, then the symbolic and numeric passes on the context's stream
+void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s);
+void hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4]);
 // buffers for the records of nk collisions; returns per-kind views of them (potential.cu)
 void hessian_records(ipcb_ctx* ctx, const int64_t nk[4], int v_lo, int v_hi, HessOut outs[4]);
 // all-zero ndof x ndof matrix

@@ -1361,6 +1361,20 @@ __global__ void k_touch_flags(CollView c, MeshView m, int v_lo, int v_hi, unsign
     flag[i] = any;
 }
 
+// the ids part of the Hessian records (stencil vertex ids, incidences): needs no arithmetic, so it runs — with the incidence sort
+// behind it — on a side stream while the local-Hessian kernels compute the blocks
+template <int KIND>
+__global__ void k_write_records(CollView c, MeshView m, int64_t gi0, int64_t inc0, HessOut out, const int* __restrict__ sel, int64_t nsel)
+{
+    constexpr int NP = KIND == IPCB_VV ? 2 : (KIND == IPCB_EV ? 3 : 4);
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nsel) return;
+    const int64_t i = sel ? sel[t] : t;
+    int vid[4];
+    stencil_ids_only(KIND, c.ids[i], m, vid);
+    write_record<NP>(out, gi0 + t, inc0 + t * NP, vid);
+}
+
 // ---- balanced row blocks of a sharded Hessian: per vertex, the number of 3x3 blocks its column receives ----------
 template <int KIND> __global__ void k_vertex_load(CollView c, MeshView m, int* __restrict__ load)
 {
@@ -1453,7 +1467,7 @@ void hessian_records(ipcb_ctx* ctx, const int64_t nk[4], int v_lo, int v_hi, Hes
         throw Error("Hessian: more than 2^27 collisions / 2^31 local blocks on one device; shard the collision set");
     ctx->hvid.reserve(ncoll), ctx->hmask.reserve(size_t(ncoll) * HSLOTS), ctx->hblk.reserve(size_t(nblocks) * 9);
     ctx->hkey.reserve(ninc), ctx->hkey_sorted.reserve(ninc);
-    for (int k = 0; k < 4; k++) outs[k] = HessOut { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p + size_t(blk0[k]) * 9, ctx->hkey.p, v_lo, v_hi, ctx->nV };
+    for (int k = 0; k < 4; k++) outs[k] = HessOut { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p + size_t(blk0[k]) * 9, ctx->hkey.p, v_lo, v_hi, ctx->nV, 0 };
 }
 
 struct ActiveColumn {
@@ -1464,7 +1478,12 @@ struct ActiveColumn {
 // Assembly of the per-collision records into compressed columns (see the comment block above k_col_ranges)
 void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
 {
-    cudaStream_t s = ctx->stream;
+    hessian_assemble_prepare(ctx, nk, ctx->stream);
+    hessian_assemble_finish(ctx, nk);
+}
+
+void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s)
+{
     const int nV = ctx->nV;
     const int64_t n0 = nk[0], n1 = nk[1], n2 = nk[2], n3 = nk[3];
     const int64_t gi0[4] = { 0, n0, n0 + n1, n0 + n1 + n2 };
@@ -1474,7 +1493,7 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
     hess_block_offsets(nk, blk0);
     ctx->outer.reserve(3 * size_t(nV) + 1);
     // stage timers (only when ctx->timing is on): the three kernels of the assembly are timed one by one
-    std::unique_ptr<Stage> st(new Stage(ctx, "hess_incidences"));
+    std::unique_ptr<Stage> st(new Stage(ctx, "hess_incidences", s));
     int vbits = 1;
     while ((1ll << vbits) <= nV) vbits++; // the value nV marks incidences of vertices outside the rank's row block
     // 1. incidences grouped by vertex (stable: each column keeps the collision order)
@@ -1518,8 +1537,23 @@ void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
         IPCB_CUDA(cudaMemsetAsync(ctx->hcolU.p, 0, (size_t(nV) + 1) * sizeof(int), s));
         ctx->launches += 2;
     }
-    st.reset();
-    st.reset(new Stage(ctx, "hess_symbolic"));
+    (void)nitems, (void)blk0;
+}
+
+void hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4])
+{
+    cudaStream_t s = ctx->stream;
+    const int nV = ctx->nV;
+    const int64_t n0 = nk[0], n1 = nk[1], n2 = nk[2], n3 = nk[3];
+    const int64_t gi0[4] = { 0, n0, n0 + n1, n0 + n1 + n2 };
+    const int64_t nitems = 4 * n0 + 9 * n1 + 16 * (n2 + n3);
+    int64_t blk0[4];
+    hess_block_offsets(nk, blk0);
+    const unsigned ref_ev = unsigned(gi0[1] * 4), ref_ee = unsigned(gi0[2] * 4);
+    int* nactive = reinterpret_cast<int*>(ctx->dCounters.p + 25);
+    size_t b3 = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, b3, ctx->hcnt.p, ctx->outer.p, 3 * nV + 1, s);
+    std::unique_ptr<Stage> st(new Stage(ctx, "hess_symbolic"));
     // 3. pass 1: per-column sort by row vertex, pattern counts
     ctx->hsref.reserve(nitems);
     ctx->hbig.reserve(size_t(nV) + 1);
@@ -1652,6 +1686,21 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
         Stage st(ctx, "hessian_local");
         HessOut outs[4];
         hessian_records(ctx, nk, v_lo, v_hi, outs);
+        // The incidences only depend on the ids: they are written and grouped by vertex (radix sort, column ranges, active columns:
+        // bandwidth- and latency-bound) on a side stream WHILE the local-Hessian kernels (FP64-bound) compute the blocks.
+        // IPCB_HESS_SERIAL: everything on one stream after the local kernels (A/B switch).
+        static const bool overlap = getenv("IPCB_HESS_SERIAL") == nullptr;
+        if (overlap) {
+            ctx->fork();
+            cudaStream_t side = ctx->aux[2];
+            if (n0) k_write_records<IPCB_VV><<<grid_for(n0, 256), 256, 0, side>>>(view(ctx, 0), m, gi0[0], inc0[0], outs[0], sel[0], n0);
+            if (n1) k_write_records<IPCB_EV><<<grid_for(n1, 256), 256, 0, side>>>(view(ctx, 1), m, gi0[1], inc0[1], outs[1], sel[1], n1);
+            if (n2) k_write_records<IPCB_EE><<<grid_for(n2, 256), 256, 0, side>>>(view(ctx, 2), m, gi0[2], inc0[2], outs[2], sel[2], n2);
+            if (n3) k_write_records<IPCB_FV><<<grid_for(n3, 256), 256, 0, side>>>(view(ctx, 3), m, gi0[3], inc0[3], outs[3], sel[3], n3);
+            ctx->launches += 4;
+            hessian_assemble_prepare(ctx, nk, side);
+            for (int k = 0; k < 4; k++) outs[k].records_done = 1;
+        }
         static const bool force_general = getenv("IPCB_HESSIAN_GENERAL") != nullptr; // A/B switch for tests and profiles
         if (psd_mode == IPCB_PSD_NONE || force_general) {
             if (n0) k_hessian_local<IPCB_VV><<<grid_for(n0, 128), 128, 0, s>>>(view(ctx, 0), m, B, psd_mode, gi0[0], inc0[0], outs[0], nullptr, 0, sel[0], n0), ctx->launches++;
@@ -1716,8 +1765,10 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
             ctx->join(1);
         }
         IPCB_CUDA(cudaGetLastError());
+        if (overlap) ctx->join(2);
+        else hessian_assemble_prepare(ctx, nk, s);
     }
-    hessian_assemble(ctx, nk);
+    hessian_assemble_finish(ctx, nk);
 }
 
 } // namespace ipcb
