@@ -269,6 +269,15 @@ int IPCB_FN(ccd_narrow_phase)(ipcb_ctx* ctx, int32_t kind, int64_t n, const doub
                               double* toi);
 
 #ifndef IPCB_ORACLE
+/* ---- friction, device-resident (see the host forms above) */
+/* device-resident forms (no reference equivalent, like the other _dev calls): positions / velocities, the per-vertex
+ * coefficients, energy (1 double) and gradient (3 nV doubles) are device pointers; the Hessian stays resident */
+int IPCB_FN(tangential_build_dev)(ipcb_ctx* ctx, const double* dV, int32_t ld, const ipcb_barrier_params* normal_potential,
+                                  const double* d_mu_s, const double* d_mu_k, int64_t counts[4]);
+int IPCB_FN(friction_energy_dev)(ipcb_ctx* ctx, const double* d_velocities, int32_t ld, double eps_v, double* d_energy);
+int IPCB_FN(friction_gradient_dev)(ipcb_ctx* ctx, const double* d_velocities, int32_t ld, double eps_v, double* d_grad);
+int IPCB_FN(friction_hessian_dev)(ipcb_ctx* ctx, const double* d_velocities, int32_t ld, double eps_v, int32_t psd_mode, int64_t* nnz);
+
 /* ---- device-resident variants (product only) ---------------------------- */
 /* V*, grad are DEVICE pointers (col-major, ld); scalar results are written to
  * HOST memory unless the name says _devout, in which case the pointer is a

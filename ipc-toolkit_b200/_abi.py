@@ -72,6 +72,10 @@ HOST_API = {
 
 # device-resident variants: product only
 DEVICE_API = {
+    "tangential_build_dev": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), P, P, C.POINTER(c_i64)]),
+    "friction_energy_dev": (C.c_int, [P, P, c_i32, c_f64, P]),
+    "friction_gradient_dev": (C.c_int, [P, P, c_i32, c_f64, P]),
+    "friction_hessian_dev": (C.c_int, [P, P, c_i32, c_f64, c_i32, C.POINTER(c_i64)]),
     "collisions_build_dev": (C.c_int, [P, P, c_i32, c_f64, c_f64, c_i32, C.POINTER(c_i64)]),
     "collisions_build_from_candidates_dev": (C.c_int, [P, P, c_i32, c_f64, c_f64, c_i32, C.POINTER(c_i64)]),
     "barrier_energy_dev": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), P]),

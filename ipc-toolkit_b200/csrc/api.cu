@@ -964,6 +964,51 @@ int ipcb_friction_hessian(ipcb_ctx* ctx, const double* velocities, int32_t ld, d
     });
 }
 
+// device-resident forms of the friction calls: positions / velocities, coefficients and results stay in HBM
+int ipcb_tangential_build_dev(ipcb_ctx* ctx, const double* dV, int32_t ld, const ipcb_barrier_params* normal_potential, const double* d_mu_s,
+                              const double* d_mu_k, int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        require_collisions(ctx);
+        if (!d_mu_s || !d_mu_k) throw Error("tangential_build: mu_s and mu_k are per-vertex arrays");
+        convert_positions(ctx, dV, ld, ctx->X0);
+        tangential_build(ctx, *normal_potential, d_mu_s, d_mu_k);
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < 4; k++) counts[k] = ctx->tang[k].count;
+    });
+}
+int ipcb_friction_energy_dev(ipcb_ctx* ctx, const double* d_velocities, int32_t ld, double eps_v, double* d_energy)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (!(eps_v > 0)) throw Error("eps_v must be positive");
+        convert_positions(ctx, d_velocities, ld, ctx->X0);
+        friction_energy(ctx, eps_v, d_energy);
+    });
+}
+int ipcb_friction_gradient_dev(ipcb_ctx* ctx, const double* d_velocities, int32_t ld, double eps_v, double* d_grad)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (!(eps_v > 0)) throw Error("eps_v must be positive");
+        convert_positions(ctx, d_velocities, ld, ctx->X0);
+        friction_gradient(ctx, eps_v, d_grad);
+    });
+}
+int ipcb_friction_hessian_dev(ipcb_ctx* ctx, const double* d_velocities, int32_t ld, double eps_v, int32_t psd_mode, int64_t* nnz)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        if (!(eps_v > 0)) throw Error("eps_v must be positive");
+        if (psd_mode < 0 || psd_mode > 2) throw Error("Invalid type of PSD projection!");
+        convert_positions(ctx, d_velocities, ld, ctx->X0);
+        friction_hessian(ctx, eps_v, psd_mode);
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *nnz = ctx->nnz;
+    });
+}
+
 // ---- CCD
 int ipcb_ccd_stepsize_from_candidates_dev(ipcb_ctx* ctx, const double* dV0, const double* dV1, int32_t ld, double min_distance,
                                           const ipcb_ccd_params* ccd, double* d_step)

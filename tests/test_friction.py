@@ -146,3 +146,49 @@ def test_friction_matches_the_oracle(cuda, oracle, scenes, name):
         A, Bm = ra["H"], rb["H"]
         assert np.array_equal(A.indptr, Bm.indptr) and np.array_equal(A.indices, Bm.indices)
         assert np.linalg.norm(A.data - Bm.data) <= 1e-10 * np.linalg.norm(Bm.data)
+
+
+@pytest.mark.gpu
+def test_device_resident_friction_calls(cuda, scenes):
+    """the _dev forms (device positions / velocities / coefficients in, results left on the device) give what the
+    host-buffer forms give"""
+    import ctypes as C
+
+    import scipy.sparse as sp
+    import torch
+
+    V0, V1, E, F, P = _scene(scenes, "stack")
+    nV, eps_v, lib = V0.shape[0], 1e-3, cuda.lib
+    mesh, c, t = build_sets(cuda, V0, E, F, P["dhat"])
+    rng = np.random.default_rng(5)
+    U = rng.normal(0, eps_v, V0.shape)
+    D = cuda.FrictionPotential(eps_v)
+    want = dict(counts=t.counts(), e=D(t, mesh, U), g=D.gradient(t, mesh, U), H=D.hessian(t, mesh, U, cuda.PSDProjectionMethod.CLAMP))
+    # the same through the device-resident entry points
+    r2 = np.random.default_rng(1)  # build_sets' coefficients
+    mu_s, mu_k = 0.5 * (1 + 0.2 * r2.random(nV)), 0.3 * (1 + 0.2 * r2.random(nV))
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    dV, dU = dev(np.asfortranarray(V0).T.copy()), dev(np.asfortranarray(U).T.copy())
+    d_ms, d_mk = dev(mu_s), dev(mu_k)
+    c._live()  # the normal set the lagged quantities come from must be the resident one
+    import ipctk_b200
+
+    bp = ipctk_b200._pkg._abi.BarrierParams(P["dhat"], 1e3, 0)
+    counts, nnz = (C.c_int64 * 4)(), C.c_int64()
+    ptr = lambda x: C.c_void_p(x.data_ptr())
+    lib.check(lib.tangential_build_dev(mesh._ctx, ptr(dV), nV, C.byref(bp), ptr(d_ms), ptr(d_mk), counts))
+    assert list(counts) == want["counts"]
+    d_e, d_g = torch.zeros(1, dtype=torch.float64, device="cuda"), torch.zeros(3 * nV, dtype=torch.float64, device="cuda")
+    lib.check(lib.friction_energy_dev(mesh._ctx, ptr(dU), nV, eps_v, ptr(d_e)))
+    lib.check(lib.friction_gradient_dev(mesh._ctx, ptr(dU), nV, eps_v, ptr(d_g)))
+    lib.check(lib.friction_hessian_dev(mesh._ctx, ptr(dU), nV, eps_v, 1, C.byref(nnz)))
+    torch.cuda.synchronize()
+    outer, inner, vals = np.zeros(3 * nV + 1, np.int32), np.zeros(nnz.value, np.int32), np.zeros(nnz.value)
+    lib.check(lib.barrier_hessian_fetch(mesh._ctx, outer.ctypes.data_as(C.c_void_p), inner.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p)))
+    H = sp.csc_matrix((vals, inner, outer), shape=(3 * nV, 3 * nV))
+    assert abs(float(d_e.item()) - want["e"]) <= 1e-13 * abs(want["e"])
+    assert np.linalg.norm(d_g.cpu().numpy() - want["g"]) <= 1e-13 * np.linalg.norm(want["g"])
+    W = want["H"]
+    assert np.array_equal(H.indptr, W.indptr) and np.array_equal(H.indices, W.indices)
+    assert np.linalg.norm(H.data - W.data) <= 1e-13 * np.linalg.norm(W.data)
+    del dV, dU, d_ms, d_mk, d_e, d_g
