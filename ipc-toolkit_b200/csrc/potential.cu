@@ -1686,10 +1686,11 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
         Stage st(ctx, "hessian_local");
         HessOut outs[4];
         hessian_records(ctx, nk, v_lo, v_hi, outs);
-        // The incidences only depend on the ids: they are written and grouped by vertex (radix sort, column ranges, active columns:
-        // bandwidth- and latency-bound) on a side stream WHILE the local-Hessian kernels (FP64-bound) compute the blocks.
-        // IPCB_HESS_SERIAL: everything on one stream after the local kernels (A/B switch).
-        static const bool overlap = getenv("IPCB_HESS_SERIAL") == nullptr;
+        // The incidences only depend on the ids: they could be written and grouped by vertex (radix sort, column ranges, active
+        // columns) on a side stream WHILE the local-Hessian kernels compute the blocks (IPCB_HESS_OVERLAP).  Measured on C3:
+        // no gain (16.29 vs 16.30 ms) — k_hessian_fast holds every SM's register file (4 blocks x 128 threads x 128 registers),
+        // so the side stream's kernels wait for its blocks to retire anyway.  Off by default.
+        static const bool overlap = getenv("IPCB_HESS_OVERLAP") != nullptr;
         if (overlap) {
             ctx->fork();
             cudaStream_t side = ctx->aux[2];
