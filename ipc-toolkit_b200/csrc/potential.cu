@@ -1088,7 +1088,29 @@ template <int NUM_BATCH> __device__ __forceinline__ RunRefs<NUM_BATCH> load_run(
     for (int x = 0; x < NUM_BATCH; x++) rr.ref[x] = x < rr.len ? sr[rr.start + x] : 0u;
     return rr;
 }
-template <int NUM_BATCH>
+// the two halves of load_run, for a three-deep pipeline: descriptors two rounds ahead, references one round ahead
+struct RunDesc {
+    int start, len, row;
+};
+__device__ __forceinline__ RunDesc load_desc(const int2* __restrict__ ud, int u, int U, int R, bool lane_ok)
+{
+    RunDesc d { 0, 0, 0 };
+    if (lane_ok && u < U) {
+        const int2 a = ud[u];
+        d.start = a.x, d.row = a.y;
+        d.len = (u + 1 < U ? ud[u + 1].x : R) - a.x;
+    }
+    return d;
+}
+template <int NUM_BATCH> __device__ __forceinline__ RunRefs<NUM_BATCH> load_refs(const unsigned* __restrict__ sr, const RunDesc& d)
+{
+    RunRefs<NUM_BATCH> rr;
+    rr.start = d.start, rr.len = d.len, rr.row = d.row;
+#pragma unroll
+    for (int x = 0; x < NUM_BATCH; x++) rr.ref[x] = x < d.len ? sr[d.start + x] : 0u;
+    return rr;
+}
+template <int NUM_BATCH, int REM>
 __global__ void __launch_bounds__(32 * SYM_WARPS)
     k_hess_numeric(int nV, const int* __restrict__ colR, const int* __restrict__ colU, const int* __restrict__ itemoff,
                    const unsigned* __restrict__ sref, const int2* __restrict__ udesc, const double* __restrict__ blk,
@@ -1112,7 +1134,10 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
     const int2* ud = udesc + ioff;
     const unsigned* sr = sref + ioff;
     int base = lane_ok ? outer[3 * size_t(v) + l] : 0;
+    // three-deep pipeline: while the blocks of round r are in flight, the references of round r + 1 (their descriptors arrived one
+    // round ago) and the descriptors of round r + 2 are requested — one memory latency per round instead of two chained ones
     RunRefs<NUM_BATCH> cur = load_run<NUM_BATCH>(ud, sr, g, U, R, lane_ok);
+    RunDesc dnext = load_desc(ud, 3 + g, U, R, lane_ok);
     for (int u0 = 0; u0 < U; u0 += 3) {
         double val[NUM_BATCH];
 #pragma unroll
@@ -1120,7 +1145,8 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
             val[x] = 0.0;
             if (x < cur.len) val[x] = __ldg(blk + size_t(cur.ref[x] >> 1) * 9 + ((cur.ref[x] & 1u) ? kt : k));
         }
-        const RunRefs<NUM_BATCH> nxt = load_run<NUM_BATCH>(ud, sr, u0 + 3 + g, U, R, lane_ok); // overlaps with the block loads above
+        const RunRefs<NUM_BATCH> nxt = load_refs<NUM_BATCH>(sr, dnext);
+        dnext = load_desc(ud, u0 + 6 + g, U, R, lane_ok);
         double acc = 0.0;
         bool nz = false;
 #pragma unroll
@@ -1129,13 +1155,26 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
                 acc += val[x];
                 nz |= val[x] != 0.0;
             }
-        // long runs: the remainder, in order (a batched remainder — NUM_BATCH more loads in flight — measured SLOWER:
-        // 3.2 vs 2.4 ms on C3; most remainders are one or two blocks and the predicated batch costs more than it hides)
-        for (int j = NUM_BATCH; j < cur.len; j++) {
-            const unsigned ref = sr[cur.start + j];
-            const double w = __ldg(blk + size_t(ref >> 1) * 9 + ((ref & 1u) ? kt : k));
-            acc += w;
-            nz |= w != 0.0;
+        // long runs (every column has one: its diagonal block gathers one block per incidence, ~46 on the dense scenes): the
+        // remainder in groups of REM independent gathers, added in item order.  One gather at a time made the diagonal run a
+        // chain of ~34 dependent DRAM latencies per column — the critical path of the kernel; a remainder as wide as the first
+        // batch (NUM_BATCH predicated loads) had been measured slower than that (3.2 vs 2.4 ms): REM = 4 is the middle.
+        for (int j = NUM_BATCH; j < cur.len; j += REM) {
+            double w[REM];
+#pragma unroll
+            for (int x = 0; x < REM; x++) {
+                w[x] = 0.0;
+                if (j + x < cur.len) {
+                    const unsigned ref = sr[cur.start + j + x];
+                    w[x] = __ldg(blk + size_t(ref >> 1) * 9 + ((ref & 1u) ? kt : k));
+                }
+            }
+#pragma unroll
+            for (int x = 0; x < REM; x++)
+                if (j + x < cur.len) {
+                    acc += w[x];
+                    nz |= w[x] != 0.0;
+                }
         }
         const bool present = cur.len > 0 && nz;
         const unsigned pm = __ballot_sync(0xffffffffu, present) & colmask;
@@ -1610,20 +1649,24 @@ void hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4])
     if (const char* e = getenv("IPCB_HESS_NUMERIC_UCAP")) ucap = std::min(NUMERIC_UCAP, std::max(3, atoi(e)));
     unsigned long long* nbig2 = ctx->dCounters.p + 15;
     IPCB_CUDA(cudaMemsetAsync(nbig2, 0, sizeof(unsigned long long), s));
-#define IPCB_NUMERIC(KERNEL, NB)                                                                                                          \
-    KERNEL<NB><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p,      \
-                                                ctx->outer.p, ctx->inner.p, ctx->vals.p, ctx->hactive.p, nactive, big_items, ctx->hbig.p, nbig2)
+#define IPCB_NUMERIC(KERNEL, ...)                                                                                                          \
+    KERNEL<__VA_ARGS__><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p, \
+                                                         ctx->outer.p, ctx->inner.p, ctx->vals.p, ctx->hactive.p, nactive, big_items, ctx->hbig.p, nbig2)
     // IPCB_NUMERIC_LANES=9: one lane per block entry (three blocks per round); =3: one lane per block column (ten blocks per round)
+    // IPCB_NUM_REM: gathers in flight in the remainder of a long run (1: the former one-at-a-time loop; default 4)
     const char* nl_env = getenv("IPCB_NUMERIC_LANES");
     const int nlanes = nl_env ? atoi(nl_env) : 9;
+    const int rem = getenv("IPCB_NUM_REM") ? atoi(getenv("IPCB_NUM_REM")) : 4;
     if (nlanes == 3) {
         const int nb3 = nb_env ? atoi(nb_env) : 6;
         if (nb3 >= 8) IPCB_NUMERIC(k_hess_numeric_col, 8);
         else if (nb3 >= 6) IPCB_NUMERIC(k_hess_numeric_col, 6);
         else IPCB_NUMERIC(k_hess_numeric_col, 4);
-    } else if (nb == 16) IPCB_NUMERIC(k_hess_numeric, 16);
-    else if (nb == 12) IPCB_NUMERIC(k_hess_numeric, 12);
-    else IPCB_NUMERIC(k_hess_numeric, 8);
+    } else if (nb == 16) IPCB_NUMERIC(k_hess_numeric, 16, 4);
+    else if (nb == 8) IPCB_NUMERIC(k_hess_numeric, 8, 4);
+    else if (rem == 1) IPCB_NUMERIC(k_hess_numeric, 12, 1);
+    else if (rem >= 8) IPCB_NUMERIC(k_hess_numeric, 12, 8);
+    else IPCB_NUMERIC(k_hess_numeric, 12, 4);
 #undef IPCB_NUMERIC
     constexpr size_t NUMERIC_SMEM = size_t(NUMERIC_UCAP) * (72 + 2);
     k_hess_numeric_big<<<NUM_SMS, NBIG_THREADS, NUMERIC_SMEM, s>>>(ctx->hbig.p, nbig2, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p,
