@@ -1156,9 +1156,9 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
                 nz |= val[x] != 0.0;
             }
         // long runs (every column has one: its diagonal block gathers one block per incidence, ~46 on the dense scenes): the
-        // remainder in groups of REM independent gathers, added in item order.  One gather at a time made the diagonal run a
-        // chain of ~34 dependent DRAM latencies per column — the critical path of the kernel; a remainder as wide as the first
-        // batch (NUM_BATCH predicated loads) had been measured slower than that (3.2 vs 2.4 ms): REM = 4 is the middle.
+        // remainder in groups of REM gathers, added in item order.  Measured on C3 (ms): REM = 1: 2.40, 4: 2.75, 8: 4.44 — more
+        // gathers in flight per lane make the pass SLOWER (as a remainder as wide as the first batch had in round 1), so one
+        // at a time stays the default (IPCB_NUM_REM selects the others).
         for (int j = NUM_BATCH; j < cur.len; j += REM) {
             double w[REM];
 #pragma unroll
@@ -1653,20 +1653,20 @@ void hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4])
     KERNEL<__VA_ARGS__><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p, \
                                                          ctx->outer.p, ctx->inner.p, ctx->vals.p, ctx->hactive.p, nactive, big_items, ctx->hbig.p, nbig2)
     // IPCB_NUMERIC_LANES=9: one lane per block entry (three blocks per round); =3: one lane per block column (ten blocks per round)
-    // IPCB_NUM_REM: gathers in flight in the remainder of a long run (1: the former one-at-a-time loop; default 4)
+    // IPCB_NUM_REM: gathers in flight in the remainder of a long run (default 1, see k_hess_numeric)
     const char* nl_env = getenv("IPCB_NUMERIC_LANES");
     const int nlanes = nl_env ? atoi(nl_env) : 9;
-    const int rem = getenv("IPCB_NUM_REM") ? atoi(getenv("IPCB_NUM_REM")) : 4;
+    const int rem = getenv("IPCB_NUM_REM") ? atoi(getenv("IPCB_NUM_REM")) : 1;
     if (nlanes == 3) {
         const int nb3 = nb_env ? atoi(nb_env) : 6;
         if (nb3 >= 8) IPCB_NUMERIC(k_hess_numeric_col, 8);
         else if (nb3 >= 6) IPCB_NUMERIC(k_hess_numeric_col, 6);
         else IPCB_NUMERIC(k_hess_numeric_col, 4);
-    } else if (nb == 16) IPCB_NUMERIC(k_hess_numeric, 16, 4);
-    else if (nb == 8) IPCB_NUMERIC(k_hess_numeric, 8, 4);
-    else if (rem == 1) IPCB_NUMERIC(k_hess_numeric, 12, 1);
+    } else if (nb == 16) IPCB_NUMERIC(k_hess_numeric, 16, 1);
+    else if (nb == 8) IPCB_NUMERIC(k_hess_numeric, 8, 1);
     else if (rem >= 8) IPCB_NUMERIC(k_hess_numeric, 12, 8);
-    else IPCB_NUMERIC(k_hess_numeric, 12, 4);
+    else if (rem >= 4) IPCB_NUMERIC(k_hess_numeric, 12, 4);
+    else IPCB_NUMERIC(k_hess_numeric, 12, 1);
 #undef IPCB_NUMERIC
     constexpr size_t NUMERIC_SMEM = size_t(NUMERIC_UCAP) * (72 + 2);
     k_hess_numeric_big<<<NUM_SMS, NBIG_THREADS, NUMERIC_SMEM, s>>>(ctx->hbig.p, nbig2, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p,

@@ -142,7 +142,7 @@ def test_step_size(cuda, oracle, scenes, name):
     {"IPCB_NUMERIC_LANES": "3"},  # numeric pass: one lane per block column, ten blocks per round
     {"IPCB_NUMERIC_LANES": "3", "IPCB_NUM_BATCH": "4"},  # ... with runs longer than the prefetch depth
     {"IPCB_NUMERIC_LANES": "9", "IPCB_NUM_BATCH": "8"},  # one lane per block entry (the other variant)
-    {"IPCB_NUM_REM": "1"},  # remainder of long runs one gather at a time
+    {"IPCB_NUM_REM": "4"},  # remainder of long runs four gathers at a time (default: one)
     {"IPCB_NUM_REM": "8"},  # ... eight at a time
     {"IPCB_HESS_NUMERIC_BIG": "40"},  # numeric pass: most columns on the block-per-column kernel
     {"IPCB_HESS_NUMERIC_BIG": "40", "IPCB_HESS_NUMERIC_UCAP": "7"},  # ... in several shared-memory segments per column
