@@ -1159,22 +1159,50 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
         // remainder in groups of REM gathers, added in item order.  Measured on C3 (ms): REM = 1: 2.40, 4: 2.75, 8: 4.44 — more
         // gathers in flight per lane make the pass SLOWER (as a remainder as wide as the first batch had in round 1), so one
         // at a time stays the default (IPCB_NUM_REM selects the others).
-        for (int j = NUM_BATCH; j < cur.len; j += REM) {
-            double w[REM];
-#pragma unroll
-            for (int x = 0; x < REM; x++) {
-                w[x] = 0.0;
-                if (j + x < cur.len) {
-                    const unsigned ref = sr[cur.start + j + x];
-                    w[x] = __ldg(blk + size_t(ref >> 1) * 9 + ((ref & 1u) ? kt : k));
+        if constexpr (REM == 0) {
+            // cooperative remainder: the three lane groups share the rest of every long run of the round (contiguous thirds,
+            // combined in group order: a fixed association, so the sum is reproducible) instead of idling behind its owner
+            unsigned longmask = __ballot_sync(0xffffffffu, lane_ok && k == 0 && cur.len > NUM_BATCH);
+            while (longmask) {
+                const int src = __ffs(longmask) - 1; // lane 9 * (owner group)
+                longmask &= longmask - 1;
+                const int st = __shfl_sync(0xffffffffu, cur.start, src), ln = __shfl_sync(0xffffffffu, cur.len, src);
+                const int part = (ln - NUM_BATCH + 2) / 3;
+                const int lo = NUM_BATCH + g * part, hi = min(ln, lo + part);
+                double p = 0.0;
+                bool pz = false;
+                if (lane_ok)
+                    for (int j = lo; j < hi; j++) {
+                        const unsigned ref = sr[st + j];
+                        const double w = __ldg(blk + size_t(ref >> 1) * 9 + ((ref & 1u) ? kt : k));
+                        p += w;
+                        pz |= w != 0.0;
+                    }
+                const double p0 = __shfl_sync(0xffffffffu, p, k), p1 = __shfl_sync(0xffffffffu, p, 9 + k), p2 = __shfl_sync(0xffffffffu, p, 18 + k);
+                const unsigned zm = __ballot_sync(0xffffffffu, pz);
+                if (lane_ok && 9 * g == src) {
+                    acc += p0, acc += p1, acc += p2;
+                    nz |= (((zm >> k) | (zm >> (9 + k)) | (zm >> (18 + k))) & 1u) != 0;
                 }
             }
+        } else {
+            for (int j = NUM_BATCH; j < cur.len; j += REM) {
+                double w[REM];
 #pragma unroll
-            for (int x = 0; x < REM; x++)
-                if (j + x < cur.len) {
-                    acc += w[x];
-                    nz |= w[x] != 0.0;
+                for (int x = 0; x < REM; x++) {
+                    w[x] = 0.0;
+                    if (j + x < cur.len) {
+                        const unsigned ref = sr[cur.start + j + x];
+                        w[x] = __ldg(blk + size_t(ref >> 1) * 9 + ((ref & 1u) ? kt : k));
+                    }
                 }
+#pragma unroll
+                for (int x = 0; x < REM; x++)
+                    if (j + x < cur.len) {
+                        acc += w[x];
+                        nz |= w[x] != 0.0;
+                    }
+            }
         }
         const bool present = cur.len > 0 && nz;
         const unsigned pm = __ballot_sync(0xffffffffu, present) & colmask;
@@ -1663,6 +1691,9 @@ void hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4])
         else if (nb3 >= 6) IPCB_NUMERIC(k_hess_numeric_col, 6);
         else IPCB_NUMERIC(k_hess_numeric_col, 4);
     } else if (nb == 16) IPCB_NUMERIC(k_hess_numeric, 16, 1);
+    else if (nb == 8 && rem == 0) IPCB_NUMERIC(k_hess_numeric, 8, 0);
+    else if (nb == 6 && rem == 0) IPCB_NUMERIC(k_hess_numeric, 6, 0);
+    else if (rem == 0) IPCB_NUMERIC(k_hess_numeric, 12, 0);
     else if (nb == 8) IPCB_NUMERIC(k_hess_numeric, 8, 1);
     else if (rem >= 8) IPCB_NUMERIC(k_hess_numeric, 12, 8);
     else if (rem >= 4) IPCB_NUMERIC(k_hess_numeric, 12, 4);

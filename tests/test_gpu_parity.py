@@ -142,6 +142,8 @@ def test_step_size(cuda, oracle, scenes, name):
     {"IPCB_NUMERIC_LANES": "3"},  # numeric pass: one lane per block column, ten blocks per round
     {"IPCB_NUMERIC_LANES": "3", "IPCB_NUM_BATCH": "4"},  # ... with runs longer than the prefetch depth
     {"IPCB_NUMERIC_LANES": "9", "IPCB_NUM_BATCH": "8"},  # one lane per block entry (the other variant)
+    {"IPCB_NUM_REM": "0"},  # remainder of long runs shared by the three lane groups
+    {"IPCB_NUM_REM": "0", "IPCB_NUM_BATCH": "6"},  # ... behind a short first batch
     {"IPCB_NUM_REM": "4"},  # remainder of long runs four gathers at a time (default: one)
     {"IPCB_NUM_REM": "8"},  # ... eight at a time
     {"IPCB_HESS_NUMERIC_BIG": "40"},  # numeric pass: most columns on the block-per-column kernel
