@@ -1155,10 +1155,7 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
                 acc += val[x];
                 nz |= val[x] != 0.0;
             }
-        // long runs (every column has one: its diagonal block gathers one block per incidence, ~46 on the dense scenes): the
-        // remainder in groups of REM gathers, added in item order.  Measured on C3 (ms): REM = 1: 2.40, 4: 2.75, 8: 4.44 — more
-        // gathers in flight per lane make the pass SLOWER (as a remainder as wide as the first batch had in round 1), so one
-        // at a time stays the default (IPCB_NUM_REM selects the others).
+        // long runs (every column has one: its diagonal block gathers one block per incidence, ~46 on the dense scenes)
         if constexpr (REM == 0) {
             // cooperative remainder: the three lane groups share the rest of every long run of the round (contiguous thirds,
             // combined in group order: a fixed association, so the sum is reproducible) instead of idling behind its owner
@@ -1681,10 +1678,11 @@ void hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4])
     KERNEL<__VA_ARGS__><<<ngrid, 32 * SYM_WARPS, 0, s>>>(nV, ctx->hcolR.p, ctx->hcolU.p, ctx->hitemoff.p, ctx->hsref.p, ctx->hudesc.p, ctx->hblk.p, \
                                                          ctx->outer.p, ctx->inner.p, ctx->vals.p, ctx->hactive.p, nactive, big_items, ctx->hbig.p, nbig2)
     // IPCB_NUMERIC_LANES=9: one lane per block entry (three blocks per round); =3: one lane per block column (ten blocks per round)
-    // IPCB_NUM_REM: gathers in flight in the remainder of a long run (default 1, see k_hess_numeric)
+    // IPCB_NUM_REM: the remainder of a long run: 0 (default) shared by the three lane groups, n > 0: by its owner, n gathers at a
+    // time.  Measured on C3 (ms, NUM_BATCH 12): 0: 2.34, 1: 2.43, 4: 2.75, 8: 4.44; shorter first batches lose (0 / 8: 2.62, 0 / 6: 2.83)
     const char* nl_env = getenv("IPCB_NUMERIC_LANES");
     const int nlanes = nl_env ? atoi(nl_env) : 9;
-    const int rem = getenv("IPCB_NUM_REM") ? atoi(getenv("IPCB_NUM_REM")) : 1;
+    const int rem = getenv("IPCB_NUM_REM") ? atoi(getenv("IPCB_NUM_REM")) : 0;
     if (nlanes == 3) {
         const int nb3 = nb_env ? atoi(nb_env) : 6;
         if (nb3 >= 8) IPCB_NUMERIC(k_hess_numeric_col, 8);
