@@ -1110,7 +1110,7 @@ template <int NUM_BATCH> __device__ __forceinline__ RunRefs<NUM_BATCH> load_refs
     for (int x = 0; x < NUM_BATCH; x++) rr.ref[x] = x < d.len ? sr[d.start + x] : 0u;
     return rr;
 }
-template <int NUM_BATCH, int REM>
+template <int NUM_BATCH, int REM, int COOP_UNROLL = 1>
 __global__ void __launch_bounds__(32 * SYM_WARPS)
     k_hess_numeric(int nV, const int* __restrict__ colR, const int* __restrict__ colU, const int* __restrict__ itemoff,
                    const unsigned* __restrict__ sref, const int2* __restrict__ udesc, const double* __restrict__ blk,
@@ -1168,13 +1168,22 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
                 const int lo = NUM_BATCH + g * part, hi = min(ln, lo + part);
                 double p = 0.0;
                 bool pz = false;
-                if (lane_ok)
-                    for (int j = lo; j < hi; j++) {
-                        const unsigned ref = sr[st + j];
-                        const double w = __ldg(blk + size_t(ref >> 1) * 9 + ((ref & 1u) ? kt : k));
-                        p += w;
-                        pz |= w != 0.0;
+                // COOP_UNROLL gathers in flight, branch-free (the index is clamped, a slot past the end adds +0.0): the lanes of a
+                // group agree on lo / hi, the groups do not, and per-slot branches would serialise them
+                for (int j = lo; j < hi; j += COOP_UNROLL) {
+                    unsigned rf[COOP_UNROLL];
+                    double wv[COOP_UNROLL];
+#pragma unroll
+                    for (int x = 0; x < COOP_UNROLL; x++) rf[x] = sr[st + min(j + x, hi - 1)];
+#pragma unroll
+                    for (int x = 0; x < COOP_UNROLL; x++) wv[x] = __ldg(blk + size_t(rf[x] >> 1) * 9 + ((rf[x] & 1u) ? kt : k));
+#pragma unroll
+                    for (int x = 0; x < COOP_UNROLL; x++) {
+                        const bool in = j + x < hi;
+                        p += in ? wv[x] : 0.0;
+                        pz |= in && wv[x] != 0.0;
                     }
+                }
                 const double p0 = __shfl_sync(0xffffffffu, p, k), p1 = __shfl_sync(0xffffffffu, p, 9 + k), p2 = __shfl_sync(0xffffffffu, p, 18 + k);
                 const unsigned zm = __ballot_sync(0xffffffffu, pz);
                 if (lane_ok && 9 * g == src) {
@@ -1691,7 +1700,12 @@ void hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4])
     } else if (nb == 16) IPCB_NUMERIC(k_hess_numeric, 16, 1);
     else if (nb == 8 && rem == 0) IPCB_NUMERIC(k_hess_numeric, 8, 0);
     else if (nb == 6 && rem == 0) IPCB_NUMERIC(k_hess_numeric, 6, 0);
-    else if (rem == 0) IPCB_NUMERIC(k_hess_numeric, 12, 0);
+    else if (rem == 0) {
+        const int cu = getenv("IPCB_NUM_COOP") ? atoi(getenv("IPCB_NUM_COOP")) : 1; // gathers in flight in the cooperative remainder
+        if (cu >= 4) IPCB_NUMERIC(k_hess_numeric, 12, 0, 4);
+        else if (cu >= 2) IPCB_NUMERIC(k_hess_numeric, 12, 0, 2);
+        else IPCB_NUMERIC(k_hess_numeric, 12, 0, 1);
+    }
     else if (nb == 8) IPCB_NUMERIC(k_hess_numeric, 8, 1);
     else if (rem >= 8) IPCB_NUMERIC(k_hess_numeric, 12, 8);
     else if (rem >= 4) IPCB_NUMERIC(k_hess_numeric, 12, 4);

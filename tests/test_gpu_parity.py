@@ -143,6 +143,7 @@ def test_step_size(cuda, oracle, scenes, name):
     {"IPCB_NUMERIC_LANES": "3", "IPCB_NUM_BATCH": "4"},  # ... with runs longer than the prefetch depth
     {"IPCB_NUMERIC_LANES": "9", "IPCB_NUM_BATCH": "8"},  # one lane per block entry (the other variant)
     {"IPCB_NUM_REM": "0"},  # remainder of long runs shared by the three lane groups
+    {"IPCB_NUM_COOP": "4"},  # ... four gathers in flight per lane
     {"IPCB_NUM_REM": "0", "IPCB_NUM_BATCH": "6"},  # ... behind a short first batch
     {"IPCB_NUM_REM": "4"},  # remainder of long runs four gathers at a time (default: one)
     {"IPCB_NUM_REM": "8"},  # ... eight at a time
