@@ -558,8 +558,8 @@ def main():
         # traversal: 40 B per query leaf + 8 B per emitted pair (static + swept passes); the node fetches (64 B each) hit L2
         roof("k_traverse<EE> (static + swept)", k_ms("k_traverse<EE>"), 2 * E.shape[0] * 40.0 + (cs[2] + cc[2]) * 8.0, ["k_traverse<2,2,2"],
              "one thread per query leaf, stack walk: bound by dependent node fetches (L2 latency), not by DRAM"),
-        roof("k_traverse<FV> (static + swept)", k_ms("k_traverse<FV>"), 2 * nV * 40.0 + (cs[3] + cc[3]) * 8.0, ["k_traverse<1,1,3"],
-             "one thread per query leaf, stack walk: bound by dependent node fetches (L2 latency), not by DRAM"),
+        roof("k_traverse<FV> (static + swept)", k_ms("k_traverse<FV>"), 2 * nV * 40.0 + (cs[3] + cc[3]) * 8.0, ["k_traverse4<1,1,3"],
+             "one thread per query leaf, stack walk over the 4-wide face tree: bound by dependent node fetches (L2 latency), not by DRAM"),
         # CCD pre-filter (FP32, conservative): 8 B ids + 16 B edge / face ids + 4 x 32 B re-centred float vertices (t0 | t1) per
         # candidate; the vertex table (16 MB) is L2-resident, so these are L2 -> SM bytes, not DRAM bytes; ~250 FP32 flop
         roof("k_ti_filter32", k_ms("k_ti_filter"), (cc[2] + cc[3]) * 152.0, ["k_ti_filter32"],
