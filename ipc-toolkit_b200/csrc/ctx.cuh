@@ -208,6 +208,7 @@ struct ipcb_ctx {
     ipcb::Buf<unsigned long long> hkey, hkey_sorted; // incidence keys (vertex << 32 | collision * 4 + point); also pair sorting
     ipcb::Buf<int4> hvid;                            // stencil vertex ids per collision (-1 padded)
     ipcb::Buf<unsigned short> hmask;                 // 16 x 9-bit non-zero masks per collision (slot = col point * 4 + row point)
+    ipcb::Buf<unsigned long long> hcount, hcursor;   // per vertex key: incidences by record size (3 x 21 bits), placement cursors
     ipcb::Buf<int> hactive;                          // columns with anything to assemble, in visiting order
     ipcb::Buf<char> hseltmp;
     ipcb::Buf<double> hblk;                          // 16 x 9 doubles per collision
@@ -223,7 +224,7 @@ struct ipcb_ctx {
     ipcb::Buf<int> hbig;                             // columns too large for one warp's shared memory
     ipcb::Buf<char> hscratch;                        // global sort scratch for huge columns
     size_t hscratch_items = 0;
-    bool hfast_attr_set = false;
+    bool hfast_attr_set = false, colsort_attr_set = false;
     bool hess_attr_set = false;
     ipcb::Buf<int> outer, inner;
     ipcb::Buf<double> vals;

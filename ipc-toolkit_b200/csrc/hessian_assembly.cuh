@@ -81,6 +81,7 @@ struct HessOut {
     int v_lo, v_hi;          // owned vertex range (row block of a sharded Hessian); incidences of other
     int v_none;              // vertices get the vertex key v_none (= nV: sorted behind every column)
     int records_done;        // the ids / incidences were written by k_write_records already: write_record only reports `own`
+    unsigned long long* cnt; // optional: per vertex key, the number of its incidences by record size (3 x 21 bits: 2- / 3- / 4-point)
 };
 constexpr int HSLOTS = 16;
 __host__ __device__ constexpr int tri_count(int np) { return np * (np + 1) / 2; }
@@ -100,8 +101,11 @@ template <int NP> __device__ inline unsigned write_record(const HessOut& out, in
     for (int a = 0; a < NP; a++) {
         const bool mine = vid[a] >= out.v_lo && vid[a] < out.v_hi;
         own |= unsigned(mine) << a;
-        if (!out.records_done)
-            out.inc[inc_base + a] = ((unsigned long long)(unsigned)(mine ? vid[a] : out.v_none) << 32) | (unsigned long long)(gi * 4 + a);
+        if (!out.records_done) {
+            const unsigned vkey = unsigned(mine ? vid[a] : out.v_none);
+            out.inc[inc_base + a] = ((unsigned long long)vkey << 32) | (unsigned long long)(gi * 4 + a);
+            if (out.cnt) atomicAdd(out.cnt + vkey, 1ull << (21 * (NP - 2))); // counting placement of the incidences (hessian_assemble)
+        }
     }
     return own;
 }

@@ -1526,6 +1526,7 @@ void hessian_empty(ipcb_ctx* ctx)
     ctx->launches++;
 }
 
+bool hess_counting_placement();
 void hessian_records(ipcb_ctx* ctx, const int64_t nk[4], int v_lo, int v_hi, HessOut outs[4])
 {
     const int64_t n0 = nk[0], n1 = nk[1], n2 = nk[2], n3 = nk[3];
@@ -1540,7 +1541,107 @@ void hessian_records(ipcb_ctx* ctx, const int64_t nk[4], int v_lo, int v_hi, Hes
         throw Error("Hessian: more than 2^27 collisions / 2^31 local blocks on one device; shard the collision set");
     ctx->hvid.reserve(ncoll), ctx->hmask.reserve(size_t(ncoll) * HSLOTS), ctx->hblk.reserve(size_t(nblocks) * 9);
     ctx->hkey.reserve(ninc), ctx->hkey_sorted.reserve(ninc);
-    for (int k = 0; k < 4; k++) outs[k] = HessOut { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p + size_t(blk0[k]) * 9, ctx->hkey.p, v_lo, v_hi, ctx->nV, 0 };
+    unsigned long long* cnt = nullptr;
+    if (hess_counting_placement()) {
+        ctx->hcount.reserve(size_t(ctx->nV) + 2);
+        IPCB_CUDA(cudaMemsetAsync(ctx->hcount.p, 0, (size_t(ctx->nV) + 2) * sizeof(unsigned long long), ctx->stream));
+        cnt = ctx->hcount.p;
+    }
+    for (int k = 0; k < 4; k++)
+        outs[k] = HessOut { ctx->hvid.p, ctx->hmask.p, ctx->hblk.p + size_t(blk0[k]) * 9, ctx->hkey.p, v_lo, v_hi, ctx->nV, 0, cnt };
+}
+
+// Grouping of the incidences by column vertex.  Default: counting placement — the kernels that write the records count the
+// incidences per vertex (one 64-bit atomic each, three 21-bit fields by record size), a scan gives the column ranges, a scatter
+// pass places every incidence in its column and record-size segment with one more atomic, and each column's few dozen
+// entries are sorted in shared memory, which restores exactly the order a stable global sort by vertex produces (collision
+// order: the summation order of the numeric pass stays reproducible).  IPCB_HESS_RADIX_INCIDENCES: the global radix sort
+// (three passes over 8-byte keys) + binary searches for the ranges, kept as the A/B and test alternative.
+constexpr int COLSORT_WARP_CAP = 1024; // incidences a warp sorts in shared memory
+bool hess_counting_placement()
+{
+    return getenv("IPCB_HESS_RADIX_INCIDENCES") == nullptr; // read per call: the tests switch it
+}
+__global__ void k_col_from_counts(int nV, const unsigned long long* __restrict__ cnt, int* __restrict__ colcount, int* __restrict__ colR,
+                                  unsigned long long* maxcount)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    int mine = 0;
+    if (v <= nV) {
+        const unsigned long long c = cnt[v];
+        const int n0 = int(c & 0x1fffffull), n1 = int((c >> 21) & 0x1fffffull), n2 = int((c >> 42) & 0x1fffffull);
+        colcount[v] = n0 + n1 + n2;
+        colR[v] = v < nV ? 2 * n0 + 3 * n1 + 4 * n2 : 0;
+        if (v < nV) mine = n0 + n1 + n2;
+    }
+    for (int o = 16; o > 0; o >>= 1) mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+    if ((threadIdx.x & 31) == 0 && mine > COLSORT_WARP_CAP) atomicMax(maxcount, (unsigned long long)mine);
+}
+__global__ void k_col_bounds(int nV, const unsigned long long* __restrict__ cnt, const int* __restrict__ colinc, int2* __restrict__ colb)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nV) return;
+    const unsigned long long c = cnt[v];
+    const int n0 = int(c & 0x1fffffull), n1 = int((c >> 21) & 0x1fffffull);
+    colb[v] = make_int2(colinc[v] + n0, colinc[v] + n0 + n1);
+}
+__global__ void k_scatter_incidences(int64_t n, const unsigned long long* __restrict__ key, unsigned ref_ev, unsigned ref_ee,
+                                     const unsigned long long* __restrict__ cnt, const int* __restrict__ colinc, unsigned long long* cursor,
+                                     unsigned long long* __restrict__ out)
+{
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = key[i];
+    const unsigned v = unsigned(k >> 32), ref = unsigned(k);
+    const int cls = ref < ref_ev ? 0 : (ref < ref_ee ? 1 : 2);
+    const unsigned long long c = cnt[v];
+    const int seg = cls == 0 ? 0 : (cls == 1 ? int(c & 0x1fffffull) : int(c & 0x1fffffull) + int((c >> 21) & 0x1fffffull));
+    const unsigned long long old = atomicAdd(cursor + v, 1ull << (21 * cls));
+    out[colinc[v] + seg + int((old >> (21 * cls)) & 0x1fffffull)] = k;
+}
+// every active column's incidences into ascending order (all of a column share the vertex bits: the order is the collision order)
+__global__ void __launch_bounds__(32 * SYM_WARPS)
+    k_sort_columns(const int* __restrict__ active, const int* __restrict__ nactive, const int* __restrict__ colinc, unsigned long long* inc,
+                   int* __restrict__ big, unsigned long long* nbig, int warp_cap)
+{
+    __shared__ unsigned long long keys[SYM_WARPS][COLSORT_WARP_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * SYM_WARPS + warp;
+    if (w >= *nactive) return;
+    const int v = active[w];
+    const int s = colinc[v], L = colinc[v + 1] - s;
+    if (L <= 1) return;
+    if (L > warp_cap) {
+        if (lane == 0) big[atomicAdd(nbig, 1ull)] = v;
+        return;
+    }
+    int npow2 = 2;
+    while (npow2 < L) npow2 <<= 1;
+    for (int q = lane; q < npow2; q += 32) keys[warp][q] = q < L ? inc[s + q] : ~0ull;
+    __syncwarp();
+    bitonic_sort<32>(keys[warp], npow2, lane);
+    for (int q = lane; q < L; q += 32) inc[s + q] = keys[warp][q];
+}
+// columns beyond the warp's shared memory: one block each (up to COLSORT_CTA_CAP entries)
+constexpr int COLSORT_CTA_CAP = 16384;
+__global__ void __launch_bounds__(BIG_THREADS)
+    k_sort_columns_big(const int* __restrict__ big, const unsigned long long* nbig, const int* __restrict__ colinc, unsigned long long* inc)
+{
+    extern __shared__ __align__(16) char smem[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
+    const unsigned long long n = *nbig;
+    for (unsigned long long idx = blockIdx.x; idx < n; idx += gridDim.x) {
+        const int v = big[idx];
+        const int s = colinc[v], L = colinc[v + 1] - s;
+        int npow2 = 2;
+        while (npow2 < L) npow2 <<= 1;
+        // (columns beyond `cap` entries never get here: hessian_assemble_prepare falls back to the radix sort for them)
+        for (int q = threadIdx.x; q < npow2; q += BIG_THREADS) keys[q] = q < L ? inc[s + q] : ~0ull;
+        __syncthreads();
+        bitonic_sort<BIG_THREADS>(keys, npow2, threadIdx.x);
+        for (int q = threadIdx.x; q < L; q += BIG_THREADS) inc[s + q] = keys[q];
+        __syncthreads();
+    }
 }
 
 struct ActiveColumn {
@@ -1574,21 +1675,47 @@ void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s
     cub::DeviceRadixSort::SortKeys(nullptr, b1, ctx->hkey.p, ctx->hkey_sorted.p, ninc, 32, 32 + vbits, s);
     ctx->hcolinc.reserve(size_t(nV) + 2), ctx->hcolR.reserve(size_t(nV) + 2), ctx->hitemoff.reserve(size_t(nV) + 2);
     ctx->hcnt.reserve(3 * size_t(nV) + 1), ctx->hcolU.reserve(size_t(nV) + 1);
-    cub::DeviceScan::ExclusiveSum(nullptr, b2, ctx->hcolR.p, ctx->hitemoff.p, nV + 1, s);
+    cub::DeviceScan::ExclusiveSum(nullptr, b2, ctx->hcolR.p, ctx->hitemoff.p, nV + 2, s);
     cub::DeviceScan::ExclusiveSum(nullptr, b3, ctx->hcnt.p, ctx->outer.p, 3 * nV + 1, s);
     ctx->cubtmp.reserve(std::max(b1, std::max(b2, b3)) + 1024);
-    {
-        Stage kt(ctx, "k:radix_sort(incidences)", s);
-        cub::DeviceRadixSort::SortKeys(ctx->cubtmp.p, b1, ctx->hkey.p, ctx->hkey_sorted.p, ninc, 32, 32 + vbits, s);
-    }
-    ctx->launches += 2 + (vbits + 7) / 8;
-    // 2. column ranges and item offsets
     const unsigned ref_ev = unsigned(gi0[1] * 4), ref_ee = unsigned(gi0[2] * 4);
     ctx->hcolb.reserve(size_t(nV) + 1);
-    k_col_ranges<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, int(ninc), ctx->hkey_sorted.p, ref_ev, ref_ee, ctx->hcolinc.p, ctx->hcolR.p,
-                                                            ctx->hcolb.p);
+    bool counting = hess_counting_placement();
+    if (counting) {
+        // counts (written with the records) -> column sizes; a column beyond what one block sorts in shared memory sends this
+        // assembly to the radix sort below (hkey still holds the unsorted incidences)
+        unsigned long long* maxcount = ctx->dCounters.p + 26;
+        IPCB_CUDA(cudaMemsetAsync(maxcount, 0, sizeof(unsigned long long), s));
+        // hitemoff doubles as the per-column incidence count until the item scan overwrites it
+        k_col_from_counts<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, ctx->hcount.p, ctx->hitemoff.p, ctx->hcolR.p, maxcount);
+        IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[12], maxcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        IPCB_CUDA(cudaStreamSynchronize(s));
+        ctx->launches++;
+        if (ctx->pinned.p[12] > (unsigned long long)COLSORT_CTA_CAP) counting = false;
+    }
+    if (counting) {
+        Stage kt(ctx, "k:place(incidences)", s);
+        cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, b2, ctx->hitemoff.p, ctx->hcolinc.p, nV + 2, s); // colinc[nV + 1] = all incidences
+        k_col_bounds<<<grid_for(nV, 256), 256, 0, s>>>(nV, ctx->hcount.p, ctx->hcolinc.p, ctx->hcolb.p);
+        ctx->hcursor.reserve(size_t(nV) + 2);
+        IPCB_CUDA(cudaMemsetAsync(ctx->hcursor.p, 0, (size_t(nV) + 2) * sizeof(unsigned long long), s));
+        k_scatter_incidences<<<grid_for(ninc, 256), 256, 0, s>>>(ninc, ctx->hkey.p, ref_ev, ref_ee, ctx->hcount.p, ctx->hcolinc.p, ctx->hcursor.p,
+                                                               ctx->hkey_sorted.p);
+        ctx->launches += 4;
+    } else {
+        {
+            Stage kt(ctx, "k:radix_sort(incidences)", s);
+            cub::DeviceRadixSort::SortKeys(ctx->cubtmp.p, b1, ctx->hkey.p, ctx->hkey_sorted.p, ninc, 32, 32 + vbits, s);
+        }
+        ctx->launches += 2 + (vbits + 7) / 8;
+        // 2. column ranges
+        k_col_ranges<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, int(ninc), ctx->hkey_sorted.p, ref_ev, ref_ee, ctx->hcolinc.p, ctx->hcolR.p,
+                                                                ctx->hcolb.p);
+        ctx->launches++;
+    }
+    // item offsets
     cub::DeviceScan::ExclusiveSum(ctx->cubtmp.p, b2, ctx->hcolR.p, ctx->hitemoff.p, nV + 1, s);
-    ctx->launches += 3;
+    ctx->launches += 2;
     // 2b. the columns that have anything to assemble, in the Morton order of their vertices (from the last broad phase on this
     // context; any order is valid).  On a row block of a sharded Hessian three quarters (N = 4) of the columns are empty, on a
     // scene like C2 most vertices are not in contact: the per-column kernels run one warp per ACTIVE column, so that every
@@ -1608,6 +1735,22 @@ void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s
         else cub::DeviceSelect::If(ctx->hseltmp.p, b4, cub::CountingInputIterator<int>(0), ctx->hactive.p, nactive, nV, is_active, s);
         IPCB_CUDA(cudaMemsetAsync(ctx->hcnt.p, 0, (3 * size_t(nV) + 1) * sizeof(int), s));
         IPCB_CUDA(cudaMemsetAsync(ctx->hcolU.p, 0, (size_t(nV) + 1) * sizeof(int), s));
+        ctx->launches += 2;
+    }
+    if (counting) { // the placed incidences of every active column into collision order
+        Stage kt(ctx, "k:sort_columns(incidences)", s);
+        ctx->hbig.reserve(size_t(nV) + 1);
+        unsigned long long* nbig = ctx->dCounters.p + 27;
+        IPCB_CUDA(cudaMemsetAsync(nbig, 0, sizeof(unsigned long long), s));
+        int cs_cap = COLSORT_WARP_CAP; // test hook: small scenes reach the block-per-column sort
+        if (const char* e = getenv("IPCB_HESS_COLSORT_WARP_CAP")) cs_cap = std::min(COLSORT_WARP_CAP, std::max(1, atoi(e)));
+        k_sort_columns<<<grid_for(size_t(nV), SYM_WARPS), 32 * SYM_WARPS, 0, s>>>(ctx->hactive.p, nactive, ctx->hcolinc.p, ctx->hkey_sorted.p,
+                                                                                ctx->hbig.p, nbig, cs_cap);
+        if (!ctx->colsort_attr_set) {
+            IPCB_CUDA(cudaFuncSetAttribute(k_sort_columns_big, cudaFuncAttributeMaxDynamicSharedMemorySize, COLSORT_CTA_CAP * 8));
+            ctx->colsort_attr_set = true;
+        }
+        k_sort_columns_big<<<NUM_SMS, BIG_THREADS, COLSORT_CTA_CAP * 8, s>>>(ctx->hbig.p, nbig, ctx->hcolinc.p, ctx->hkey_sorted.p);
         ctx->launches += 2;
     }
     (void)nitems, (void)blk0;
