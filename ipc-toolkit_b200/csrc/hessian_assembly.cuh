@@ -104,7 +104,9 @@ template <int NP> __device__ inline unsigned write_record(const HessOut& out, in
         if (!out.records_done) {
             const unsigned vkey = unsigned(mine ? vid[a] : out.v_none);
             out.inc[inc_base + a] = ((unsigned long long)vkey << 32) | (unsigned long long)(gi * 4 + a);
-            if (out.cnt) atomicAdd(out.cnt + vkey, 1ull << (21 * (NP - 2))); // counting placement of the incidences (hessian_assemble)
+            // counting placement of the incidences (hessian_assemble); parked incidences are never read: not counted (they
+            // would all hit one address)
+            if (out.cnt && mine) atomicAdd(out.cnt + vkey, 1ull << (21 * (NP - 2)));
         }
     }
     return own;

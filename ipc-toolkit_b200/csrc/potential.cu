@@ -1587,12 +1587,13 @@ __global__ void k_col_bounds(int nV, const unsigned long long* __restrict__ cnt,
 }
 __global__ void k_scatter_incidences(int64_t n, const unsigned long long* __restrict__ key, unsigned ref_ev, unsigned ref_ee,
                                      const unsigned long long* __restrict__ cnt, const int* __restrict__ colinc, unsigned long long* cursor,
-                                     unsigned long long* __restrict__ out)
+                                     unsigned long long* __restrict__ out, unsigned v_none)
 {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long k = key[i];
     const unsigned v = unsigned(k >> 32), ref = unsigned(k);
+    if (v >= v_none) return; // an incidence of a vertex outside the rank's row block: parked, never read
     const int cls = ref < ref_ev ? 0 : (ref < ref_ee ? 1 : 2);
     const unsigned long long c = cnt[v];
     const int seg = cls == 0 ? 0 : (cls == 1 ? int(c & 0x1fffffull) : int(c & 0x1fffffull) + int((c >> 21) & 0x1fffffull));
@@ -1700,7 +1701,7 @@ void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s
         ctx->hcursor.reserve(size_t(nV) + 2);
         IPCB_CUDA(cudaMemsetAsync(ctx->hcursor.p, 0, (size_t(nV) + 2) * sizeof(unsigned long long), s));
         k_scatter_incidences<<<grid_for(ninc, 256), 256, 0, s>>>(ninc, ctx->hkey.p, ref_ev, ref_ee, ctx->hcount.p, ctx->hcolinc.p, ctx->hcursor.p,
-                                                               ctx->hkey_sorted.p);
+                                                               ctx->hkey_sorted.p, unsigned(nV));
         ctx->launches += 4;
     } else {
         {
