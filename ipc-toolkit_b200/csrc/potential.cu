@@ -1616,6 +1616,31 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
         if (lane == 0) big[atomicAdd(nbig, 1ull)] = v;
         return;
     }
+    if (L <= 64) {
+        // the common case (a few dozen incidences): the 32-bit references (the vertex bits are the column's) sorted in registers,
+        // two per lane, by a bitonic network over shuffles
+        const unsigned long long hi = inc[s] & 0xffffffff00000000ull;
+        unsigned a0 = lane < L ? unsigned(inc[s + lane]) : 0xffffffffu, a1 = lane + 32 < L ? unsigned(inc[s + lane + 32]) : 0xffffffffu;
+#pragma unroll
+        for (int k = 2; k <= 64; k <<= 1)
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j == 32) { // k == 64: the partner is the lane's other element, ascending
+                    const unsigned lo = min(a0, a1), up = max(a0, a1);
+                    a0 = lo, a1 = up;
+                } else {
+                    const unsigned b0 = __shfl_xor_sync(0xffffffffu, a0, j), b1 = __shfl_xor_sync(0xffffffffu, a1, j);
+                    const bool lower = (lane & j) == 0;                             // this lane holds the pair's lower index
+                    const bool up0 = k >= 32 ? true : (lane & k) == 0;              // element lane: bit 5 clear
+                    const bool up1 = k == 64 ? true : (k == 32 ? false : (lane & k) == 0); // element lane + 32: bit 5 set
+                    a0 = (lower == up0) ? min(a0, b0) : max(a0, b0);
+                    a1 = (lower == up1) ? min(a1, b1) : max(a1, b1);
+                }
+            }
+        if (lane < L) inc[s + lane] = hi | a0;
+        if (lane + 32 < L) inc[s + lane + 32] = hi | a1;
+        return;
+    }
     int npow2 = 2;
     while (npow2 < L) npow2 <<= 1;
     for (int q = lane; q < npow2; q += 32) keys[warp][q] = q < L ? inc[s + q] : ~0ull;
