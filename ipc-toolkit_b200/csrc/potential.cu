@@ -1557,7 +1557,7 @@ void hessian_records(ipcb_ctx* ctx, const int64_t nk[4], int v_lo, int v_hi, Hes
 // entries are sorted in shared memory, which restores exactly the order a stable global sort by vertex produces (collision
 // order: the summation order of the numeric pass stays reproducible).  IPCB_HESS_RADIX_INCIDENCES: the global radix sort
 // (three passes over 8-byte keys) + binary searches for the ranges, kept as the A/B and test alternative.
-constexpr int COLSORT_WARP_CAP = 1024; // incidences a warp sorts in shared memory
+constexpr int COLSORT_WARP_CAP = 512; // incidences a warp sorts in shared memory (up to 256: in registers)
 bool hess_counting_placement()
 {
     return getenv("IPCB_HESS_RADIX_INCIDENCES") == nullptr; // read per call: the tests switch it
@@ -1600,6 +1600,45 @@ __global__ void k_scatter_incidences(int64_t n, const unsigned long long* __rest
     const unsigned long long old = atomicAdd(cursor + v, 1ull << (21 * cls));
     out[colinc[v] + seg + int((old >> (21 * cls)) & 0x1fffffull)] = k;
 }
+// bitonic network over 32 E values, E per lane (element e = lane + 32 h): partners at distance j < 32 by shuffle, at j >= 32
+// inside the lane; ascending where (e & k) == 0
+template <int E> __device__ __forceinline__ void warp_bitonic(unsigned (&a)[E], int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32 * E; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int hj = j / 32;
+#pragma unroll
+                for (int h = 0; h < E; h++)
+                    if ((h & hj) == 0) {
+                        const bool up = ((32 * h) & k) == 0;
+                        const unsigned lo = min(a[h], a[h | hj]), hi = max(a[h], a[h | hj]);
+                        a[h] = up ? lo : hi, a[h | hj] = up ? hi : lo;
+                    }
+            } else {
+                const bool lower = (lane & j) == 0;
+#pragma unroll
+                for (int h = 0; h < E; h++) {
+                    const unsigned b = __shfl_xor_sync(0xffffffffu, a[h], j);
+                    const bool up = k < 32 ? (lane & k) == 0 : ((32 * h) & k) == 0;
+                    a[h] = (lower == up) ? min(a[h], b) : max(a[h], b);
+                }
+            }
+        }
+}
+template <int E> __device__ __forceinline__ void sort_column_registers(unsigned long long* col, int L, int lane)
+{
+    const unsigned long long hi = col[0] & 0xffffffff00000000ull;
+    unsigned a[E];
+#pragma unroll
+    for (int h = 0; h < E; h++) a[h] = lane + 32 * h < L ? unsigned(col[lane + 32 * h]) : 0xffffffffu;
+    warp_bitonic<E>(a, lane);
+#pragma unroll
+    for (int h = 0; h < E; h++)
+        if (lane + 32 * h < L) col[lane + 32 * h] = hi | a[h];
+}
 // every active column's incidences into ascending order (all of a column share the vertex bits: the order is the collision order)
 __global__ void __launch_bounds__(32 * SYM_WARPS)
     k_sort_columns(const int* __restrict__ active, const int* __restrict__ nactive, const int* __restrict__ colinc, unsigned long long* inc,
@@ -1616,29 +1655,18 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
         if (lane == 0) big[atomicAdd(nbig, 1ull)] = v;
         return;
     }
+    // the common cases (a few dozen to a few hundred incidences): the 32-bit references (the vertex bits are the column's)
+    // sorted in registers, E per lane, by a bitonic network over shuffles
     if (L <= 64) {
-        // the common case (a few dozen incidences): the 32-bit references (the vertex bits are the column's) sorted in registers,
-        // two per lane, by a bitonic network over shuffles
-        const unsigned long long hi = inc[s] & 0xffffffff00000000ull;
-        unsigned a0 = lane < L ? unsigned(inc[s + lane]) : 0xffffffffu, a1 = lane + 32 < L ? unsigned(inc[s + lane + 32]) : 0xffffffffu;
-#pragma unroll
-        for (int k = 2; k <= 64; k <<= 1)
-#pragma unroll
-            for (int j = k >> 1; j > 0; j >>= 1) {
-                if (j == 32) { // k == 64: the partner is the lane's other element, ascending
-                    const unsigned lo = min(a0, a1), up = max(a0, a1);
-                    a0 = lo, a1 = up;
-                } else {
-                    const unsigned b0 = __shfl_xor_sync(0xffffffffu, a0, j), b1 = __shfl_xor_sync(0xffffffffu, a1, j);
-                    const bool lower = (lane & j) == 0;                             // this lane holds the pair's lower index
-                    const bool up0 = k >= 32 ? true : (lane & k) == 0;              // element lane: bit 5 clear
-                    const bool up1 = k == 64 ? true : (k == 32 ? false : (lane & k) == 0); // element lane + 32: bit 5 set
-                    a0 = (lower == up0) ? min(a0, b0) : max(a0, b0);
-                    a1 = (lower == up1) ? min(a1, b1) : max(a1, b1);
-                }
-            }
-        if (lane < L) inc[s + lane] = hi | a0;
-        if (lane + 32 < L) inc[s + lane + 32] = hi | a1;
+        sort_column_registers<2>(inc + s, L, lane);
+        return;
+    }
+    if (L <= 128) {
+        sort_column_registers<4>(inc + s, L, lane);
+        return;
+    }
+    if (L <= 256) {
+        sort_column_registers<8>(inc + s, L, lane);
         return;
     }
     int npow2 = 2;
