@@ -211,7 +211,7 @@ struct ipcb_ctx {
     ipcb::Buf<unsigned long long> hcount, hcursor;   // per vertex key: incidences by record size (3 x 21 bits), placement cursors
     ipcb::Buf<int> hactive;                          // columns with anything to assemble, in visiting order
     ipcb::Buf<char> hseltmp;
-    ipcb::Buf<double> hblk;                          // 16 x 9 doubles per collision
+    ipcb::Buf<double> hblk;                          // upper-triangular vertex blocks: 3 / 6 / 10 x 9 doubles per VV / EV / 4-point record
     ipcb::Buf<unsigned char> hflag;                  // row block: does the collision touch an owned vertex
     ipcb::Buf<int> hsel;                             // row block: per kind, the collisions that do (ascending)
     ipcb::Buf<int> hslow;                            // edge-edge collisions handed to the general kernel

@@ -407,10 +407,10 @@ __global__ void __launch_bounds__(128)
 // Edge-edge collisions whose mollifier is active at X (or whose distance type is not edge-edge) are
 // appended to `slow` for the general kernel.
 //
-// Stores: a thread owns one collision = 1152 contiguous bytes of blocks.  Writing them from
-// registers would make every 8-byte store of a warp hit 32 different sectors; instead each block
-// row (NP blocks = NP*72 contiguous bytes per collision) is staged in shared memory (odd stride:
-// conflict-free) and written out by the whole warp with consecutive lanes on consecutive addresses.
+// Stores: a thread owns one collision = 216 / 432 / 720 contiguous bytes of (upper-triangular) blocks.  Writing them from
+// registers would make every 8-byte store of a warp hit 32 different sectors.  !BULK (vertex-vertex records, and the A/B
+// alternative for the others): each row of the triangle is staged in shared memory (odd stride: conflict-free) and written
+// out by the whole warp with consecutive lanes on consecutive addresses.
 //
 // BULK (3- and 4-point kinds): the record of a collision is 432 / 720 contiguous, 16-byte aligned bytes, so the thread stages it in
 // its own shared-memory slot and hands it to the TMA unit (cp.async.bulk.global.shared::cta): one instruction per 288- or 432-byte
