@@ -549,7 +549,10 @@ def main():
         roof("k_hess_symbolic", stages.get("hess_symbolic"), hs_bytes, ["k_hess_symbolic"],
              "shared-memory hash + sort per column; instruction / latency bound"),
         roof("radix sort of the (vertex, collision) incidences (cub)", k_ms("radix_sort(incidences)"), ninc * share * 8 * 2 * 4, ["(no per-sort capture)"],
-             "3 onesweep passes + histogram over 8-byte keys"),
+             "3 onesweep passes + histogram over 8-byte keys (IPCB_HESS_RADIX_INCIDENCES; the default is the counting placement below)"),
+        # counting placement: the scatter reads and writes every 8-byte incidence once, the per-column sort once more
+        roof("k_scatter_incidences + k_sort_columns", (k_ms("place(incidences)") or 0.0) + (k_ms("sort_columns(incidences)") or 0.0), ninc * share * 32.0,
+             ["k_scatter_incidences", "k_sort_columns"], "counting placement of the incidences: atomics + register bitonic sorts per column"),
         # classification: 8 B ids + 2 x 8 B edge / 16 B face ids + 4 x 32 B vertices per candidate; ~150 (EE) / 250 (FV) flop
         roof("k_classify<EE>", k_ms("k_classify<EE>"), cs[2] * 152.0, ["k_classify<2"], "one thread per candidate: dependent gathers out of L2",
              flops=cs[2] * 150.0),
