@@ -225,6 +225,7 @@ struct ipcb_ctx {
     ipcb::Buf<char> hscratch;                        // global sort scratch for huge columns
     size_t hscratch_items = 0;
     bool hfast_attr_set = false, colsort_attr_set = false;
+    bool hess_counting_used = false; // the last hessian_assemble_prepare placed the incidences by counting
     bool hess_attr_set = false;
     ipcb::Buf<int> outer, inner;
     ipcb::Buf<double> vals;

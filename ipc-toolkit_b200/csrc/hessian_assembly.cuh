@@ -145,8 +145,10 @@ inline void hess_block_offsets(const int64_t nk[4], int64_t blk0[4])
 void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4]);
 // the same in two halves: everything that only needs the records' ids (incidence sort, column ranges, active columns) on
 // stream `s` — it can run beside the kernels that compute the blocks —, then the symbolic and numeric passes on the context's stream
-void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s);
-void hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4]);
+void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s, bool force_radix = false);
+// false: a column was too large for the counting placement (seen at the pass's own synchronisation point): prepare again with
+// force_radix and finish again
+bool hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4]);
 // buffers for the records of nk collisions; returns per-kind views of them (potential.cu)
 void hessian_records(ipcb_ctx* ctx, const int64_t nk[4], int v_lo, int v_hi, HessOut outs[4]);
 // all-zero ndof x ndof matrix

@@ -1563,7 +1563,7 @@ bool hess_counting_placement()
     return getenv("IPCB_HESS_RADIX_INCIDENCES") == nullptr; // read per call: the tests switch it
 }
 __global__ void k_col_from_counts(int nV, const unsigned long long* __restrict__ cnt, int* __restrict__ colcount, int* __restrict__ colR,
-                                  unsigned long long* maxcount)
+                                  unsigned long long* maxcount, int report_above)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     int mine = 0;
@@ -1575,7 +1575,7 @@ __global__ void k_col_from_counts(int nV, const unsigned long long* __restrict__
         if (v < nV) mine = n0 + n1 + n2;
     }
     for (int o = 16; o > 0; o >>= 1) mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, o));
-    if ((threadIdx.x & 31) == 0 && mine > COLSORT_WARP_CAP) atomicMax(maxcount, (unsigned long long)mine);
+    if ((threadIdx.x & 31) == 0 && mine > report_above) atomicMax(maxcount, (unsigned long long)mine); // rare: large columns only
 }
 __global__ void k_col_bounds(int nV, const unsigned long long* __restrict__ cnt, const int* __restrict__ colinc, int2* __restrict__ colb)
 {
@@ -1678,8 +1678,13 @@ __global__ void __launch_bounds__(32 * SYM_WARPS)
 }
 // columns beyond the warp's shared memory: one block each (up to COLSORT_CTA_CAP entries)
 constexpr int COLSORT_CTA_CAP = 16384;
+static int colsort_cta_cap() // test hook: a small scene reaches the redo with the radix sort
+{
+    const char* e = getenv("IPCB_HESS_COLSORT_CTA_CAP");
+    return e ? std::min(COLSORT_CTA_CAP, std::max(2, atoi(e))) : COLSORT_CTA_CAP;
+}
 __global__ void __launch_bounds__(BIG_THREADS)
-    k_sort_columns_big(const int* __restrict__ big, const unsigned long long* nbig, const int* __restrict__ colinc, unsigned long long* inc)
+    k_sort_columns_big(const int* __restrict__ big, const unsigned long long* nbig, const int* __restrict__ colinc, unsigned long long* inc, int cap)
 {
     extern __shared__ __align__(16) char smem[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem);
@@ -1689,7 +1694,7 @@ __global__ void __launch_bounds__(BIG_THREADS)
         const int s = colinc[v], L = colinc[v + 1] - s;
         int npow2 = 2;
         while (npow2 < L) npow2 <<= 1;
-        // (columns beyond `cap` entries never get here: hessian_assemble_prepare falls back to the radix sort for them)
+        if (L > cap) continue; // reported through maxcount: the assembly is redone with the radix sort
         for (int q = threadIdx.x; q < npow2; q += BIG_THREADS) keys[q] = q < L ? inc[s + q] : ~0ull;
         __syncthreads();
         bitonic_sort<BIG_THREADS>(keys, npow2, threadIdx.x);
@@ -1707,10 +1712,13 @@ struct ActiveColumn {
 void hessian_assemble(ipcb_ctx* ctx, const int64_t nk[4])
 {
     hessian_assemble_prepare(ctx, nk, ctx->stream);
-    hessian_assemble_finish(ctx, nk);
+    if (!hessian_assemble_finish(ctx, nk)) {
+        hessian_assemble_prepare(ctx, nk, ctx->stream, true);
+        hessian_assemble_finish(ctx, nk);
+    }
 }
 
-void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s)
+void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s, bool force_radix)
 {
     const int nV = ctx->nV;
     const int64_t n0 = nk[0], n1 = nk[1], n2 = nk[2], n3 = nk[3];
@@ -1734,18 +1742,18 @@ void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s
     ctx->cubtmp.reserve(std::max(b1, std::max(b2, b3)) + 1024);
     const unsigned ref_ev = unsigned(gi0[1] * 4), ref_ee = unsigned(gi0[2] * 4);
     ctx->hcolb.reserve(size_t(nV) + 1);
-    bool counting = hess_counting_placement();
+    const bool counting = hess_counting_placement() && !force_radix;
+    ctx->hess_counting_used = counting;
     if (counting) {
-        // counts (written with the records) -> column sizes; a column beyond what one block sorts in shared memory sends this
-        // assembly to the radix sort below (hkey still holds the unsorted incidences)
+        // counts (written with the records) -> column sizes.  A column beyond what one block sorts in shared memory is left
+        // unsorted and reported through `maxcount`; hessian_assemble_finish reads it at its own synchronisation point and the
+        // assembly is then redone with the radix sort (hkey still holds the unsorted incidences) — no extra host round trip
         unsigned long long* maxcount = ctx->dCounters.p + 26;
         IPCB_CUDA(cudaMemsetAsync(maxcount, 0, sizeof(unsigned long long), s));
         // hitemoff doubles as the per-column incidence count until the item scan overwrites it
-        k_col_from_counts<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, ctx->hcount.p, ctx->hitemoff.p, ctx->hcolR.p, maxcount);
-        IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[12], maxcount, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-        IPCB_CUDA(cudaStreamSynchronize(s));
+        k_col_from_counts<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, ctx->hcount.p, ctx->hitemoff.p, ctx->hcolR.p, maxcount,
+                                                                        std::min(COLSORT_WARP_CAP, colsort_cta_cap()));
         ctx->launches++;
-        if (ctx->pinned.p[12] > (unsigned long long)COLSORT_CTA_CAP) counting = false;
     }
     if (counting) {
         Stage kt(ctx, "k:place(incidences)", s);
@@ -1804,13 +1812,13 @@ void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s
             IPCB_CUDA(cudaFuncSetAttribute(k_sort_columns_big, cudaFuncAttributeMaxDynamicSharedMemorySize, COLSORT_CTA_CAP * 8));
             ctx->colsort_attr_set = true;
         }
-        k_sort_columns_big<<<NUM_SMS, BIG_THREADS, COLSORT_CTA_CAP * 8, s>>>(ctx->hbig.p, nbig, ctx->hcolinc.p, ctx->hkey_sorted.p);
+        k_sort_columns_big<<<NUM_SMS, BIG_THREADS, COLSORT_CTA_CAP * 8, s>>>(ctx->hbig.p, nbig, ctx->hcolinc.p, ctx->hkey_sorted.p, colsort_cta_cap());
         ctx->launches += 2;
     }
     (void)nitems, (void)blk0;
 }
 
-void hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4])
+bool hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4])
 {
     cudaStream_t s = ctx->stream;
     const int nV = ctx->nV;
@@ -1858,7 +1866,10 @@ void hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4])
         ctx->launches += 2;
         IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[9], ctx->outer.p + 3 * size_t(nV), sizeof(int), cudaMemcpyDeviceToHost, s));
         IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[10], need, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        if (ctx->hess_counting_used)
+            IPCB_CUDA(cudaMemcpyAsync(&ctx->pinned.p[12], ctx->dCounters.p + 26, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         IPCB_CUDA(cudaStreamSynchronize(s));
+        if (ctx->hess_counting_used && ctx->pinned.p[12] > (unsigned long long)colsort_cta_cap()) return false;
         const size_t want = size_t(ctx->pinned.p[10]);
         if (want == 0) break;
         if (attempt > 0) throw Error("Hessian: sort scratch for a huge column could not be provided");
@@ -1914,6 +1925,7 @@ void hessian_assemble_finish(ipcb_ctx* ctx, const int64_t nk[4])
     ctx->launches += 2;
     ctx->launches++;
     IPCB_CUDA(cudaGetLastError());
+    return true;
 }
 
 void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
@@ -2052,7 +2064,10 @@ void barrier_hessian(ipcb_ctx* ctx, const ipcb_barrier_params& bp, int psd_mode)
         if (overlap) ctx->join(2);
         else hessian_assemble_prepare(ctx, nk, s);
     }
-    hessian_assemble_finish(ctx, nk);
+    if (!hessian_assemble_finish(ctx, nk)) {
+        hessian_assemble_prepare(ctx, nk, s, true);
+        hessian_assemble_finish(ctx, nk);
+    }
 }
 
 } // namespace ipcb

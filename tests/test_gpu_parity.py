@@ -141,6 +141,7 @@ def test_step_size(cuda, oracle, scenes, name):
     {"IPCB_HESS_NO_HASH": "1", "IPCB_HESS_WARP_CAP": "32", "IPCB_HESS_BIG_HASH": "2"},  # ... block-wide hash (giant columns)
     {"IPCB_HESS_RADIX_INCIDENCES": "1"},  # incidences grouped by the global radix sort instead of the counting placement
     {"IPCB_HESS_COLSORT_WARP_CAP": "16"},  # counting placement: most columns sorted by the block-per-column kernel
+    {"IPCB_HESS_COLSORT_CTA_CAP": "8"},  # ... a column too large for it: the assembly is redone with the radix sort
     {"IPCB_NUMERIC_LANES": "3"},  # numeric pass: one lane per block column, ten blocks per round
     {"IPCB_NUMERIC_LANES": "3", "IPCB_NUM_BATCH": "4"},  # ... with runs longer than the prefetch depth
     {"IPCB_NUMERIC_LANES": "9", "IPCB_NUM_BATCH": "8"},  # one lane per block entry (the other variant)
