@@ -72,7 +72,7 @@ enum { IPCB_BROAD_LBVH = 0, IPCB_BROAD_SAP = 1 };
  * CollisionSetType).  IPCB_SET_IMPROVED_MAX_APPROX selects CollisionSetType::IMPROVED_MAX_APPROX (the negative /
  * positive correction collisions of normal_collisions.cpp:84-128, normal_collisions_builder.cpp:340-543).  Not
  * available on a sharded context (ctx_set_shard with world > 1): the call fails. */
-enum { IPCB_USE_AREA_WEIGHTING = 1, IPCB_SET_IMPROVED_MAX_APPROX = 2 };
+enum { IPCB_USE_AREA_WEIGHTING = 1, IPCB_SET_IMPROVED_MAX_APPROX = 2, IPCB_DEFER_CORRECTIONS = 4 };
 
 /* flags for collisions_merge: the appended builders worked on DISJOINT candidate shards (the ranks of a sharded
  * build), so their edge-edge and face-vertex records are unique across builders and only vertex-vertex /
@@ -165,6 +165,20 @@ int IPCB_FN(collisions_build)(ipcb_ctx* ctx, const double* V, int32_t ld, double
  * (IPC set type; dedup with weight accumulation, builder.cpp:547-689). */
 int IPCB_FN(collisions_build_from_candidates)(ipcb_ctx* ctx, const double* V, int32_t ld, double dhat, double dmin,
                                               int32_t flags, int64_t counts[4]);
+/* CollisionSetType::IMPROVED_MAX_APPROX built by SEVERAL builders (ranks, or host threads with their own contexts) over
+ * disjoint candidate shards (normal_collisions.cpp:84-128 at builder granularity).  A sub-element pair (candidates.cpp:584-695)
+ * can be derived from candidates of several builders while its correction records (normal_collisions_builder.cpp:340-543)
+ * must be added once.  collisions_build* with IPCB_SET_IMPROVED_MAX_APPROX | IPCB_DEFER_CORRECTIONS stops after the
+ * classification and the builder's unique sub-element pairs (zero counts are returned); then
+ *   corrections_keys   n[k] = pairs in the builder's list k (0: VV of EV, 1: EV of EE, 2: EV of FV, 3: VV of FV candidates)
+ *   corrections_pack   the four lists, one after the other, as 64-bit keys (opaque: only to be handed to corrections_apply)
+ *   corrections_apply  keys: for each list the keys of ALL builders (n[k] of them, duplicates allowed), list after list; the
+ *                      builder unites them, adds the corrections of slice `rank` of `world` of every united list and merges
+ *                      its records.  The builders' sets are then united with collisions_clear / _append / _merge(flags = 0). */
+int IPCB_FN(collisions_corrections_keys)(ipcb_ctx* ctx, int64_t n[4]);
+int IPCB_FN(collisions_corrections_pack)(ipcb_ctx* ctx, uint64_t* keys);
+int IPCB_FN(collisions_corrections_apply)(ipcb_ctx* ctx, const uint64_t* keys, const int64_t n[4], int32_t rank, int32_t world,
+                                          int64_t counts[4]);
 /* ids: count x 2 (VV (v0<v1), EV (edge,vertex), EE (ea<eb), FV (face,vertex)),
  * sorted lexicographically; weight: count; eps_x, dtype: EE only (may be NULL) */
 int IPCB_FN(collisions_fetch)(ipcb_ctx* ctx, int32_t kind, int32_t* ids, double* weight, double* eps_x,
@@ -225,7 +239,7 @@ int IPCB_FN(has_intersections)(ipcb_ctx* ctx, const double* V, int32_t ld, int32
 /* ---- Friction ----------------------------------------- */
 /* TangentialCollisions::build(mesh, vertices, collisions, normal_potential, mu_s, mu_k)
  * (collisions/tangential/tangential_collisions.cpp:62-171) from the RESIDENT normal collision set: per collision the
- * lagged closest point, tangent basis (tangent/*.cpp), normal force magnitude N = -kappa b'(d^2) 2 d
+ * lagged closest point, tangent basis (tangent/ *.cpp), normal force magnitude N = -kappa b'(d^2) 2 d
  * (barrier/barrier_force_magnitude.cpp:7-15) and the blended coefficients (default_blend_mu: the average).  Edge-edge
  * collisions that are close to parallel (cross^2 < eps_x) are skipped like in the reference.  mu_s / mu_k: per vertex.
  * Isotropic coefficients only (the anisotropic "matchstick" lagging and the force Jacobians are outside this path). */
@@ -304,8 +318,9 @@ int IPCB_FN(barrier_hessian_dev_ptrs)(ipcb_ctx* ctx, const int32_t** d_outer, co
                                       const double** d_values);
 /* CollisionSetType::IMPROVED_MAX_APPROX on a SHARDED context (normal_collisions.cpp:84-128 at rank granularity).  A
  * sub-element pair (candidates.cpp:584-695) can be derived from candidates of several ranks and its correction records
- * (normal_collisions_builder.cpp:340-543) must be added once, so collisions_build*(…, IPCB_SET_IMPROVED_MAX_APPROX) on a
- * sharded context stops after the rank's unique sub-element keys (it returns zero counts).  The ranks then exchange the keys:
+ * (normal_collisions_builder.cpp:340-543) must be added once, so collisions_build*_dev(…, IPCB_SET_IMPROVED_MAX_APPROX) on a
+ * sharded context stops after the rank's unique sub-element keys (it returns zero counts; the host-buffer calls need the
+ * explicit IPCB_DEFER_CORRECTIONS flag and have their own corrections_* entry points above).  The ranks then exchange the keys:
  *   corrections_keys_dev   n[k] = keys in the rank's list k (0: VV of EV, 1: EV of EE, 2: EV of FV, 3: VV of FV candidates)
  *   corrections_pack_dev   the four lists, one after the other, into a device buffer of sum(n) 64-bit keys
  *   (all-gather)

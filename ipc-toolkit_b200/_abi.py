@@ -53,6 +53,9 @@ HOST_API = {
     "ctx_set_collision_range": (C.c_int, [P, c_i32, c_i32]),
     "ctx_set_row_block": (C.c_int, [P, c_i32, c_i32]),
     "hessian_balanced_row_blocks": (C.c_int, [P, c_i32, P]),
+    "collisions_corrections_keys": (C.c_int, [P, C.POINTER(c_i64)]),
+    "collisions_corrections_pack": (C.c_int, [P, P]),
+    "collisions_corrections_apply": (C.c_int, [P, P, C.POINTER(c_i64), c_i32, c_i32, C.POINTER(c_i64)]),
     "barrier_energy": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), C.POINTER(c_f64)]),
     "barrier_gradient": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), P]),
     "barrier_hessian": (C.c_int, [P, P, c_i32, C.POINTER(BarrierParams), c_i32, C.POINTER(c_i64)]),

@@ -424,9 +424,12 @@ def make_api(lib):
             return (1 if self.use_area_weighting else 0) | (2 if self.collision_set_type else 0)
 
         def build(self, *args, **kw):
-            """build(mesh, V, dhat, dmin=0, broad_phase=None) or build(candidates, mesh, V, dhat, dmin=0)"""
+            """build(mesh, V, dhat, dmin=0, broad_phase=None) or build(candidates, mesh, V, dhat, dmin=0).
+            defer_corrections=True (IMPROVED_MAX_APPROX built by several builders over candidate shards, include/ipcb200.h:
+            IPCB_DEFER_CORRECTIONS): the build stops after this builder's sub-element pairs; exchange correction_keys() and
+            finish with apply_corrections()."""
             counts = (C.c_int64 * 4)()
-            flags = self._flags()
+            flags = self._flags() | (4 if kw.get("defer_corrections") else 0)
             mesh = args[1] if isinstance(args[0], Candidates) else args[0]
             if self.mesh is not None and self.mesh is not mesh and self._set is not None:
                 raise RuntimeError("a NormalCollisions object cannot move to another mesh")
@@ -443,7 +446,38 @@ def make_api(lib):
                 v, p, ld = _f64(V)
                 lib.check(lib.collisions_build(mesh._ctx, p, ld, dhat, dmin, flags, counts))
                 mesh._cand_gen += 1  # the resident candidates were rebuilt too
+            if flags & 4:  # nothing to see yet: the records arrive with apply_corrections
+                self.mesh_pending, self._pending_dmin = mesh, dmin
+                return
             self._bind(mesh, counts, dmin)
+
+        def correction_keys(self):
+            """the four lists of this builder's unique sub-element pairs after a deferred build (opaque 64-bit keys)"""
+            if getattr(self, "mesh_pending", None) is None:
+                raise RuntimeError("no deferred build (build(..., defer_corrections=True)) on this NormalCollisions")
+            n = (C.c_int64 * 4)()
+            lib.check(lib.collisions_corrections_keys(self.mesh_pending._ctx, n))
+            keys = np.zeros(max(1, sum(n)), np.uint64)
+            if sum(n):
+                lib.check(lib.collisions_corrections_pack(self.mesh_pending._ctx, keys.ctypes.data_as(C.c_void_p)))
+            out, o = [], 0
+            for k in range(4):
+                out.append(keys[o:o + n[k]].copy())
+                o += n[k]
+            return out
+
+        def apply_corrections(self, lists, rank, world):
+            """lists: for each of the four lists the keys of ALL builders (concatenated, duplicates allowed); adds the
+            corrections of slice `rank` of `world` and merges this builder's records"""
+            mesh = getattr(self, "mesh_pending", None)
+            if mesh is None:
+                raise RuntimeError("no deferred build (build(..., defer_corrections=True)) on this NormalCollisions")
+            n = (C.c_int64 * 4)(*[len(x) for x in lists])
+            keys = np.ascontiguousarray(np.concatenate([np.asarray(x, np.uint64) for x in lists]) if sum(n) else np.zeros(1, np.uint64))
+            counts = (C.c_int64 * 4)()
+            lib.check(lib.collisions_corrections_apply(mesh._ctx, keys.ctypes.data_as(C.c_void_p), n, rank, world, counts))
+            self._bind(mesh, counts, self._pending_dmin)
+            self.mesh_pending = None
 
         def assign(self, mesh, builders, dmin=0.0, disjoint_shards=False):
             """Fill the set from the records of several builders and merge them like

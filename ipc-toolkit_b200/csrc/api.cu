@@ -573,7 +573,40 @@ int ipcb_collisions_corrections_apply_dev(ipcb_ctx* ctx, const void* d_keys, con
 {
     return guarded([&] {
         begin_call(ctx);
-        collisions_corrections_apply(ctx, static_cast<const unsigned long long*>(d_keys), n);
+        collisions_corrections_apply(ctx, static_cast<const unsigned long long*>(d_keys), n, ctx->shard_rank, ctx->shard_world);
+        coll_counts(ctx, counts);
+    });
+}
+// host-buffer forms (several builders in one process or over any transport: include/ipcb200.h)
+int ipcb_collisions_corrections_keys(ipcb_ctx* ctx, int64_t n[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        collisions_corrections_keys(ctx, n);
+    });
+}
+int ipcb_collisions_corrections_pack(ipcb_ctx* ctx, uint64_t* keys)
+{
+    return guarded([&] {
+        begin_call(ctx);
+        int64_t n[4];
+        collisions_corrections_keys(ctx, n);
+        const int64_t total = n[0] + n[1] + n[2] + n[3];
+        if (total == 0) return;
+        ctx->hkey.reserve(total);
+        collisions_corrections_pack(ctx, ctx->hkey.p);
+        IPCB_CUDA(cudaMemcpyAsync(keys, ctx->hkey.p, sizeof(uint64_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
+        IPCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+int ipcb_collisions_corrections_apply(ipcb_ctx* ctx, const uint64_t* keys, const int64_t n[4], int32_t rank, int32_t world, int64_t counts[4])
+{
+    return guarded([&] {
+        begin_call(ctx);
+        const int64_t total = n[0] + n[1] + n[2] + n[3];
+        ctx->hkey.reserve(std::max<int64_t>(total, 1));
+        if (total) IPCB_CUDA(cudaMemcpyAsync(ctx->hkey.p, keys, sizeof(uint64_t) * total, cudaMemcpyHostToDevice, ctx->stream));
+        collisions_corrections_apply(ctx, ctx->hkey.p, n, rank, world);
         coll_counts(ctx, counts);
     });
 }

@@ -292,9 +292,10 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags, bool m
 {
     const bool improved = (flags & IPCB_SET_IMPROVED_MAX_APPROX) != 0;
     ctx->ima_pending = false;
-    if (improved && ctx->shard_world > 1 && !may_defer) // the corrections need the sub-element keys of every rank
-        throw Error("CollisionSetType::IMPROVED_MAX_APPROX on a sharded context needs the device-resident build followed by the exchange of "
-                    "the sub-element keys (collisions_build_dev, collisions_corrections_*_dev)");
+    const bool defer = improved && ((flags & IPCB_DEFER_CORRECTIONS) || (ctx->shard_world > 1 && may_defer));
+    if (improved && ctx->shard_world > 1 && !defer) // the corrections need the sub-element keys of every rank
+        throw Error("CollisionSetType::IMPROVED_MAX_APPROX on a sharded context needs the deferred build (IPCB_DEFER_CORRECTIONS or "
+                    "collisions_build_dev) followed by the exchange of the sub-element keys (collisions_corrections_*)");
     cudaStream_t s = ctx->stream;
     int64_t total = 0;
     for (auto& c : ctx->cand) total += c.count;
@@ -302,7 +303,7 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags, bool m
     ctx->coll_valid = true;
     for (auto& c : ctx->coll) c.count = 0;
     if (total == 0) {
-        if (improved && ctx->shard_world > 1) { // this rank has nothing, the others may: it still takes part in the exchange
+        if (defer) { // this rank has nothing, the others may: it still takes part in the exchange
             for (int k = 0; k < 4; k++) ctx->ima_raw[k] = ctx->ima_nu[k] = 0;
             ctx->ima_area = (flags & IPCB_USE_AREA_WEIGHTING) != 0;
             ctx->ima_pending = true;
@@ -354,7 +355,7 @@ void collisions_build(ipcb_ctx* ctx, double dhat, double dmin, int flags, bool m
         IPCB_CUDA(cudaStreamSynchronize(s));
     }
     int64_t raw[4] = { ctx->pinned.p[0], ctx->pinned.p[1], ctx->pinned.p[2], ctx->pinned.p[3] };
-    if (improved && ctx->shard_world > 1) {
+    if (defer) {
         // A sub-element pair can be derived from candidates of several ranks, and its correction records must be added ONCE:
         // the build stops after the rank's unique sub-element keys; the ranks exchange them (collisions_corrections_keys_dev /
         // _pack_dev), and collisions_corrections_apply_dev finishes the rank's set from the united lists.
@@ -1055,8 +1056,9 @@ void collisions_corrections_pack(ipcb_ctx* ctx, unsigned long long* d_out)
 }
 // d_keys: for each of the four lists the keys of ALL ranks (n[k] of them, duplicates allowed), list after list.  Every rank
 // unites them (sort + unique: the same list everywhere) and adds the corrections of its slice of every list.
-void collisions_corrections_apply(ipcb_ctx* ctx, const unsigned long long* d_keys, const int64_t n[4])
+void collisions_corrections_apply(ipcb_ctx* ctx, const unsigned long long* d_keys, const int64_t n[4], int rank, int world)
 {
+    if (world < 1 || rank < 0 || rank >= world) throw Error("corrections_apply: bad slice");
     if (!ctx->ima_pending) throw Error("no deferred IMPROVED_MAX_APPROX build on this context");
     Stage st(ctx, "improved_max_approx");
     cudaStream_t s = ctx->stream;
@@ -1068,8 +1070,8 @@ void collisions_corrections_apply(ipcb_ctx* ctx, const unsigned long long* d_key
             ctx->subkey.reserve(n[k]);
             IPCB_CUDA(cudaMemcpyAsync(ctx->subkey.p, d_keys + off, sizeof(unsigned long long) * n[k], cudaMemcpyDeviceToDevice, s));
             const int64_t u = unique_keys(ctx, n[k], ctx->subuniq[k]);
-            first[k] = u * ctx->shard_rank / ctx->shard_world;
-            nu[k] = u * (ctx->shard_rank + 1) / ctx->shard_world - first[k];
+            first[k] = u * rank / world;
+            nu[k] = u * (rank + 1) / world - first[k];
         }
         off += n[k];
     }

@@ -302,7 +302,7 @@ void collisions_append_packed_dev(ipcb_ctx* ctx, const void* d_buffer, const int
 void collisions_merge(ipcb_ctx* ctx, double dmin, int flags);
 void collisions_corrections_keys(ipcb_ctx* ctx, int64_t n[4]);
 void collisions_corrections_pack(ipcb_ctx* ctx, unsigned long long* d_out);
-void collisions_corrections_apply(ipcb_ctx* ctx, const unsigned long long* d_keys, const int64_t n[4]);
+void collisions_corrections_apply(ipcb_ctx* ctx, const unsigned long long* d_keys, const int64_t n[4], int rank, int world);
 void collisions_sort(ipcb_ctx* ctx, int kind);
 double collisions_min_distance(ipcb_ctx* ctx);
 

@@ -99,7 +99,7 @@ class ShardedContactStep:
         self.dist.all_reduce(t, op=op)
         return t.cpu().numpy().reshape(np.shape(array))
 
-    def _gather_collisions(self, coll, dmin):
+    def _gather_collisions(self, coll, dmin, disjoint=True):
         """all ranks' records -> the merged, canonical set on every rank"""
         mine = (coll.vv_collisions, coll.ev_collisions, coll.ee_collisions, coll.fv_collisions)
         parts = [None] * self.world
@@ -108,20 +108,35 @@ class ShardedContactStep:
 
         builders = [[types.SimpleNamespace(ids=k[0], weight=k[1], eps_x=k[2], dtype=k[3]) for k in p] for p in parts]
         full = self.api.NormalCollisions()
-        full.assign(self.mesh, builders, dmin, disjoint_shards=True)
+        full.assign(self.mesh, builders, dmin, disjoint_shards=disjoint)
         return full
 
-    def step(self, V0, V1, dhat, stiffness=1.0, psd=None, dmin=0.0, min_distance=0.0, ccd=None):
+    def step(self, V0, V1, dhat, stiffness=1.0, psd=None, dmin=0.0, min_distance=0.0, ccd=None, improved_max_approx=False,
+             use_area_weighting=False):
         api = self.api
         cand = api.Candidates()
         cand.build(self.mesh, V0, 0.5 * (dhat + dmin))
         cand = self._shard_candidates(cand)
         coll = api.NormalCollisions()
-        coll.build(cand, self.mesh, V0, dhat, dmin)
+        coll.set_use_area_weighting(use_area_weighting)
+        improved = improved_max_approx and self.world > 1
+        if improved_max_approx:
+            coll.set_collision_set_type(api.NormalCollisions.CollisionSetType.IMPROVED_MAX_APPROX)
+        if improved:
+            # CollisionSetType::IMPROVED_MAX_APPROX over ranks: a sub-element pair can come from candidates of several ranks and
+            # its corrections must be added once — exchange the pairs, every rank takes a slice of the united lists
+            if not self.row_block:
+                raise ValueError("IMPROVED_MAX_APPROX over ranks needs the united set (row_block=True)")
+            coll.build(cand, self.mesh, V0, dhat, dmin, defer_corrections=True)
+            parts = [None] * self.world
+            self.dist.all_gather_object(parts, coll.correction_keys())
+            coll.apply_corrections([np.concatenate([p[k] for p in parts]) for k in range(4)], self.rank, self.world)
+        else:
+            coll.build(cand, self.mesh, V0, dhat, dmin)
         shard_counts = coll.counts()
         rows = None
         if self.row_block:
-            coll = self._gather_collisions(coll, dmin)
+            coll = self._gather_collisions(coll, dmin, disjoint=not improved)
             bounds = self.mesh.balanced_row_blocks(self.world)
             rows = (int(bounds[self.rank]), int(bounds[self.rank + 1]))
             self.mesh.set_collision_range(self.rank, self.world)

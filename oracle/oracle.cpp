@@ -87,6 +87,13 @@ struct ipcb_ctx {
     std::vector<Pair> cand[4];
     std::vector<Coll> coll[4];
     std::vector<Coll> appended[4]; // collisions_append since the last collisions_clear
+    // IMPROVED_MAX_APPROX over several builders (IPCB_DEFER_CORRECTIONS): the build stops after the classification and this
+    // builder's unique sub-element pairs; collisions_corrections_apply finishes it from the pairs of all builders
+    bool ima_pending = false, ima_area = false;
+    double ima_offset_sqr = 0, ima_dmin = 0;
+    std::vector<V3> ima_V;
+    std::vector<Coll> ima_raw[4];
+    std::vector<Pair> ima_keys[4]; // 0: VV of EV, 1: EV of EE, 2: EV of FV, 3: VV of FV candidates
     double dmin = 0;
     int coll_rank = 0, coll_world = 1; // energy / gradient: slice of every kind's collisions
     int row_lo = 0, row_hi = -1;       // Hessian: owned vertex range (row_hi < 0: all)
@@ -478,24 +485,13 @@ void merge_collisions(ipcb_ctx* ctx, int k, std::vector<Coll>& all)
     }
 }
 
-// CollisionSetType::IMPROVED_MAX_APPROX (normal_collisions.cpp:84-128): after the IPC passes, sub-element candidates
-// are derived from the element candidates (candidates.cpp:584-695: active vertex-vertex / edge-vertex pairs of every
-// edge-vertex / edge-edge / face-vertex candidate, duplicates removed) and each adds a NEGATIVE or POSITIVE correction
-// collision whose weight counts how often the IPC passes over-counted the pair (builder.cpp:340-543).
-template <typename Active>
-void improved_max_approx_corrections(ipcb_ctx* ctx, const std::vector<V3>& V, bool area, const Active& is_active, std::vector<std::vector<Coll>> (&loc)[4])
+// step 1 (candidates.cpp:584-695): the unique ACTIVE sub-element pairs of this context's candidates
+// keys[0]: vertex-vertex of edge-vertex candidates, [1]: edge-vertex of edge-edge, [2]: edge-vertex and [3]: vertex-vertex of
+// face-vertex candidates
+template <typename Active> void improved_max_approx_keys(ipcb_ctx* ctx, const std::vector<V3>& V, const Active& is_active, std::vector<Pair> (&keys)[4])
 {
     const int32_t* E = ctx->E.data();
     const int32_t* F = ctx->F.data();
-    auto contains = [](const std::vector<int32_t>& sorted, int32_t v) { return std::binary_search(sorted.begin(), sorted.end(), v); };
-    auto add_vv = [&](int vi, int vj, double w) { loc[IPCB_VV][0].push_back({ std::min(vi, vj), std::max(vi, vj), w, 0, 0 }); };
-    auto add_ev = [&](int ei, int vi, double w) { loc[IPCB_EV][0].push_back({ ei, vi, w, 0, 0 }); };
-    // add_edge_vertex_collision(mesh, candidate, dtype, weight) :108-138: reduced to the closest feature
-    auto add_ev_typed = [&](int ei, int vi, PE dtype, double w) {
-        if (dtype == PE_P_E0) add_vv(vi, E[2 * ei], w);
-        else if (dtype == PE_P_E1) add_vv(vi, E[2 * ei + 1], w);
-        else add_ev(ei, vi, w);
-    };
     auto unique_unordered = [](std::vector<Pair>& p) { // VertexVertexCandidate: order and equality ignore orientation
         for (auto& q : p)
             if (q[0] > q[1]) std::swap(q[0], q[1]);
@@ -506,102 +502,128 @@ void improved_max_approx_corrections(ipcb_ctx* ctx, const std::vector<V3>& V, bo
         std::sort(p.begin(), p.end());
         p.erase(std::unique(p.begin(), p.end()), p.end());
     };
-
-    // ---- edge-vertex candidates -> vertex-vertex (:584-622), negative corrections (builder.cpp:340-383)
-    if (!ctx->cand[IPCB_EV].empty()) {
-        std::vector<Pair> vv;
-        for (const Pair& c : ctx->cand[IPCB_EV])
+    for (auto& k : keys) k.clear();
+    for (const Pair& c : ctx->cand[IPCB_EV]) // :584-622
+        for (int j = 0; j < 2; j++) {
+            const int vi = c[1], vj = E[2 * c[0] + j];
+            if (is_active(point_point_distance(V[vi], V[vj]))) keys[0].push_back({ vi, vj });
+        }
+    unique_unordered(keys[0]);
+    for (const Pair& c : ctx->cand[IPCB_EE]) // :666-695
+        for (int i = 0; i < 2; i++) {
+            const int ei = c[i], ej = c[1 - i];
             for (int j = 0; j < 2; j++) {
-                const int vi = c[1], vj = E[2 * c[0] + j];
-                if (is_active(point_point_distance(V[vi], V[vj]))) vv.push_back({ vi, vj });
+                const int vj = E[2 * ej + j];
+                const V3 p = V[vj], e0 = V[E[2 * ei]], e1 = V[E[2 * ei + 1]];
+                if (is_active(point_edge_distance(p, e0, e1, point_edge_distance_type(p, e0, e1)))) keys[1].push_back({ ei, vj });
             }
-        unique_unordered(vv);
-        for (const Pair& c : vv) {
-            double w = 0;
-            auto add_weight = [&](int vi, int vj) {
-                const auto& inc = ctx->vv_adj[vj];
-                const int amt = int(inc.size()) - int(contains(inc, vi));
-                if (amt > 1) w += (1 - amt) * (area ? 0.5 * ctx->vertex_areas[vi] : 1.0); // / 2: double counting
-            };
-            add_weight(c[0], c[1]);
-            add_weight(c[1], c[0]);
-            if (w != 0) add_vv(c[0], c[1], w);
+        }
+    unique_ordered(keys[1]);
+    for (const Pair& c : ctx->cand[IPCB_FV]) { // :624-664
+        const int fi = c[0], vi = c[1];
+        for (int j = 0; j < 3; j++) {
+            const int ei = ctx->F2E[3 * fi + j];
+            const V3 p = V[vi], e0 = V[E[2 * ei]], e1 = V[E[2 * ei + 1]];
+            if (is_active(point_edge_distance(p, e0, e1, point_edge_distance_type(p, e0, e1)))) keys[2].push_back({ ei, vi });
+            const int vj = F[3 * fi + j];
+            if (is_active(point_point_distance(V[vi], V[vj]))) keys[3].push_back({ vi, vj });
         }
     }
-    // ---- edge-edge candidates -> edge-vertex (:666-695), negative corrections (builder.cpp:457-543)
-    if (!ctx->cand[IPCB_EE].empty()) {
-        std::vector<Pair> ev;
-        for (const Pair& c : ctx->cand[IPCB_EE])
-            for (int i = 0; i < 2; i++) {
-                const int ei = c[i], ej = c[1 - i];
-                for (int j = 0; j < 2; j++) {
-                    const int vj = E[2 * ej + j];
-                    const V3 p = V[vj], e0 = V[E[2 * ei]], e1 = V[E[2 * ei + 1]];
-                    if (is_active(point_edge_distance(p, e0, e1, point_edge_distance_type(p, e0, e1)))) ev.push_back({ ei, vj });
-                }
-            }
-        unique_ordered(ev);
-        for (const Pair& c : ev) {
-            const int ea = c[0], p = c[1];
-            const int ea0 = E[2 * ea], ea1 = E[2 * ea + 1];
-            const double w = area ? -0.25 * ctx->edge_areas[ea] : -1.0; // / 4: double counting and PT + EE
-            const PE dtype = point_edge_distance_type(V[p], V[ea0], V[ea1]);
-            int nonmollified = 0;
-            for (const int32_t eb : ctx->ve_adj[p]) {
-                const int eb0 = E[2 * eb], eb1 = E[2 * eb + 1];
-                const int q = p == eb0 ? eb1 : eb0;
-                if (q == ea0 || q == ea1) continue;
-                const double eps_x = edge_edge_mollifier_threshold(ctx->rest[ea0], ctx->rest[ea1], ctx->rest[eb0], ctx->rest[eb1]);
-                if (edge_edge_cross_squarednorm(V[ea0], V[ea1], V[eb0], V[eb1]) >= eps_x) {
-                    nonmollified++;
-                    continue;
-                }
-                // a mollified edge-edge collision with the point-edge type lifted to the edge pair (ea, eb)
-                EE ee;
-                if (dtype == PE_P_E0) ee = p == eb0 ? EE_EA0_EB0 : EE_EA0_EB1;
-                else if (dtype == PE_P_E1) ee = p == eb0 ? EE_EA1_EB0 : EE_EA1_EB1;
-                else ee = p == eb0 ? EE_EA_EB0 : EE_EA_EB1;
-                loc[IPCB_EE][0].push_back({ ea, eb, w, eps_x, uint8_t(ee) });
-            }
-            if (nonmollified == 1) continue; // (rho - 1) = 0
-            add_ev_typed(ea, p, dtype, (nonmollified - 1) * w);
-        }
-    }
-    // ---- face-vertex candidates -> edge-vertex (:640-664) negative, -> vertex-vertex (:624-638) positive
-    if (!ctx->cand[IPCB_FV].empty()) {
-        std::vector<Pair> ev, vv;
-        for (const Pair& c : ctx->cand[IPCB_FV]) {
-            const int fi = c[0], vi = c[1];
-            for (int j = 0; j < 3; j++) {
-                const int ei = ctx->F2E[3 * fi + j];
-                const V3 p = V[vi], e0 = V[E[2 * ei]], e1 = V[E[2 * ei + 1]];
-                if (is_active(point_edge_distance(p, e0, e1, point_edge_distance_type(p, e0, e1)))) ev.push_back({ ei, vi });
-                const int vj = F[3 * fi + j];
-                if (is_active(point_point_distance(V[vi], V[vj]))) vv.push_back({ vi, vj });
-            }
-        }
-        unique_ordered(ev);
-        unique_unordered(vv);
-        for (const Pair& c : ev) { // builder.cpp:421-455
-            const int ei = c[0], vi = c[1];
-            const auto& inc = ctx->ev_adj[ei];
+    unique_ordered(keys[2]);
+    unique_unordered(keys[3]);
+}
+
+// step 2 (builder.cpp:340-543): the NEGATIVE / POSITIVE correction collisions of the pairs [first[k], first[k] + count[k]) of
+// keys[k], whose weight counts how often the IPC passes over-counted the pair
+inline void improved_max_approx_apply(ipcb_ctx* ctx, const std::vector<V3>& V, bool area, const std::vector<Pair> (&keys)[4], const size_t first[4],
+                                      const size_t count[4], std::vector<std::vector<Coll>> (&loc)[4])
+{
+    const int32_t* E = ctx->E.data();
+    auto contains = [](const std::vector<int32_t>& sorted, int32_t v) { return std::binary_search(sorted.begin(), sorted.end(), v); };
+    auto add_vv = [&](int vi, int vj, double w) { loc[IPCB_VV][0].push_back({ std::min(vi, vj), std::max(vi, vj), w, 0, 0 }); };
+    auto add_ev = [&](int ei, int vi, double w) { loc[IPCB_EV][0].push_back({ ei, vi, w, 0, 0 }); };
+    // add_edge_vertex_collision(mesh, candidate, dtype, weight) :108-138: reduced to the closest feature
+    auto add_ev_typed = [&](int ei, int vi, PE dtype, double w) {
+        if (dtype == PE_P_E0) add_vv(vi, E[2 * ei], w);
+        else if (dtype == PE_P_E1) add_vv(vi, E[2 * ei + 1], w);
+        else add_ev(ei, vi, w);
+    };
+    // ---- vertex-vertex pairs of edge-vertex candidates: negative corrections (builder.cpp:340-383)
+    for (size_t i = first[0]; i < first[0] + count[0]; i++) {
+        const Pair& c = keys[0][i];
+        double w = 0;
+        auto add_weight = [&](int vi, int vj) {
+            const auto& inc = ctx->vv_adj[vj];
             const int amt = int(inc.size()) - int(contains(inc, vi));
-            if (amt > 1) {
-                const double w = (1 - amt) * (area ? 0.25 * ctx->vertex_areas[vi] : 1.0);
-                add_ev_typed(ei, vi, point_edge_distance_type(V[vi], V[E[2 * ei]], V[E[2 * ei + 1]]), w);
+            if (amt > 1) w += (1 - amt) * (area ? 0.5 * ctx->vertex_areas[vi] : 1.0); // / 2: double counting
+        };
+        add_weight(c[0], c[1]);
+        add_weight(c[1], c[0]);
+        if (w != 0) add_vv(c[0], c[1], w);
+    }
+    // ---- edge-vertex pairs of edge-edge candidates: negative corrections (builder.cpp:457-543)
+    for (size_t i = first[1]; i < first[1] + count[1]; i++) {
+        const Pair& c = keys[1][i];
+        const int ea = c[0], p = c[1];
+        const int ea0 = E[2 * ea], ea1 = E[2 * ea + 1];
+        const double w = area ? -0.25 * ctx->edge_areas[ea] : -1.0; // / 4: double counting and PT + EE
+        const PE dtype = point_edge_distance_type(V[p], V[ea0], V[ea1]);
+        int nonmollified = 0;
+        for (const int32_t eb : ctx->ve_adj[p]) {
+            const int eb0 = E[2 * eb], eb1 = E[2 * eb + 1];
+            const int q = p == eb0 ? eb1 : eb0;
+            if (q == ea0 || q == ea1) continue;
+            const double eps_x = edge_edge_mollifier_threshold(ctx->rest[ea0], ctx->rest[ea1], ctx->rest[eb0], ctx->rest[eb1]);
+            if (edge_edge_cross_squarednorm(V[ea0], V[ea1], V[eb0], V[eb1]) >= eps_x) {
+                nonmollified++;
+                continue;
             }
+            // a mollified edge-edge collision with the point-edge type lifted to the edge pair (ea, eb)
+            EE ee;
+            if (dtype == PE_P_E0) ee = p == eb0 ? EE_EA0_EB0 : EE_EA0_EB1;
+            else if (dtype == PE_P_E1) ee = p == eb0 ? EE_EA1_EB0 : EE_EA1_EB1;
+            else ee = p == eb0 ? EE_EA_EB0 : EE_EA_EB1;
+            loc[IPCB_EE][0].push_back({ ea, eb, w, eps_x, uint8_t(ee) });
         }
-        for (const Pair& c : vv) { // builder.cpp:385-419
-            double w = 0;
-            auto add_weight = [&](int vi, int vj) {
-                if (ctx->on_boundary[vj] || contains(ctx->vv_adj[vj], vi)) return; // boundary and incident vertices are skipped
-                w += area ? 0.25 * ctx->vertex_areas[vi] : 1.0;
-            };
-            add_weight(c[0], c[1]);
-            add_weight(c[1], c[0]);
-            if (w != 0) add_vv(c[0], c[1], w);
+        if (nonmollified == 1) continue; // (rho - 1) = 0
+        add_ev_typed(ea, p, dtype, (nonmollified - 1) * w);
+    }
+    // ---- edge-vertex pairs of face-vertex candidates: negative (builder.cpp:421-455)
+    for (size_t i = first[2]; i < first[2] + count[2]; i++) {
+        const Pair& c = keys[2][i];
+        const int ei = c[0], vi = c[1];
+        const auto& inc = ctx->ev_adj[ei];
+        const int amt = int(inc.size()) - int(contains(inc, vi));
+        if (amt > 1) {
+            const double w = (1 - amt) * (area ? 0.25 * ctx->vertex_areas[vi] : 1.0);
+            add_ev_typed(ei, vi, point_edge_distance_type(V[vi], V[E[2 * ei]], V[E[2 * ei + 1]]), w);
         }
     }
+    // ---- vertex-vertex pairs of face-vertex candidates: positive (builder.cpp:385-419)
+    for (size_t i = first[3]; i < first[3] + count[3]; i++) {
+        const Pair& c = keys[3][i];
+        double w = 0;
+        auto add_weight = [&](int vi, int vj) {
+            if (ctx->on_boundary[vj] || contains(ctx->vv_adj[vj], vi)) return; // boundary and incident vertices are skipped
+            w += area ? 0.25 * ctx->vertex_areas[vi] : 1.0;
+        };
+        add_weight(c[0], c[1]);
+        add_weight(c[1], c[0]);
+        if (w != 0) add_vv(c[0], c[1], w);
+    }
+}
+
+// CollisionSetType::IMPROVED_MAX_APPROX (normal_collisions.cpp:84-128): after the IPC passes, sub-element candidates
+// are derived from the element candidates (candidates.cpp:584-695: active vertex-vertex / edge-vertex pairs of every
+// edge-vertex / edge-edge / face-vertex candidate, duplicates removed) and each adds a NEGATIVE or POSITIVE correction
+// collision whose weight counts how often the IPC passes over-counted the pair (builder.cpp:340-543).
+template <typename Active>
+void improved_max_approx_corrections(ipcb_ctx* ctx, const std::vector<V3>& V, bool area, const Active& is_active, std::vector<std::vector<Coll>> (&loc)[4])
+{
+    std::vector<Pair> keys[4];
+    improved_max_approx_keys(ctx, V, is_active, keys);
+    const size_t first[4] = { 0, 0, 0, 0 }, count[4] = { keys[0].size(), keys[1].size(), keys[2].size(), keys[3].size() };
+    improved_max_approx_apply(ctx, V, area, keys, first, count, loc);
 }
 
 // NormalCollisions::build(candidates, ...) — normal_collisions.cpp:38-158 with
@@ -688,6 +710,19 @@ void collisions_build(ipcb_ctx* ctx, const std::vector<V3>& V, double dhat, doub
         default: loc[IPCB_FV][t].push_back({ fi, vi, w, 0, 0 }); break;
         }
     }
+    ctx->ima_pending = false;
+    if ((flags & IPCB_SET_IMPROVED_MAX_APPROX) && (flags & IPCB_DEFER_CORRECTIONS)) {
+        // one of several builders: stop after the classification and this builder's sub-element pairs
+        improved_max_approx_keys(ctx, V, is_active, ctx->ima_keys);
+        for (int k = 0; k < 4; k++) {
+            ctx->ima_raw[k].clear();
+            for (auto& l : loc[k]) ctx->ima_raw[k].insert(ctx->ima_raw[k].end(), l.begin(), l.end());
+            ctx->coll[k].clear();
+        }
+        ctx->ima_V = V, ctx->ima_area = area, ctx->ima_offset_sqr = offset_sqr, ctx->ima_dmin = dmin;
+        ctx->ima_pending = true;
+        return;
+    }
     if (flags & IPCB_SET_IMPROVED_MAX_APPROX) improved_max_approx_corrections(ctx, V, area, is_active, loc);
     for (int k = 0; k < 4; k++) {
         std::vector<Coll> all;
@@ -695,6 +730,28 @@ void collisions_build(ipcb_ctx* ctx, const std::vector<V3>& V, double dhat, doub
         merge_collisions(ctx, k, all);
     }
     ctx->dmin = dmin; // normal_collisions.cpp:154-157
+}
+
+// the deferred build's second half: `keys` = the pairs of ALL builders (duplicates allowed); this builder adds the corrections
+// of its slice [rank, world) of every united list
+void collisions_corrections_apply(ipcb_ctx* ctx, std::vector<Pair> (&keys)[4], int rank, int world)
+{
+    size_t first[4], count[4];
+    for (int k = 0; k < 4; k++) {
+        std::sort(keys[k].begin(), keys[k].end());
+        keys[k].erase(std::unique(keys[k].begin(), keys[k].end()), keys[k].end());
+        const size_t u = keys[k].size();
+        first[k] = u * size_t(rank) / size_t(world);
+        count[k] = u * size_t(rank + 1) / size_t(world) - first[k];
+    }
+    std::vector<std::vector<Coll>> loc[4];
+    for (int k = 0; k < 4; k++) loc[k].assign(1, ctx->ima_raw[k]);
+    improved_max_approx_apply(ctx, ctx->ima_V, ctx->ima_area, keys, first, count, loc);
+    for (int k = 0; k < 4; k++) merge_collisions(ctx, k, loc[k][0]);
+    ctx->dmin = ctx->ima_dmin;
+    ctx->ima_pending = false;
+    for (auto& r : ctx->ima_raw) r.clear();
+    ctx->ima_V.clear();
 }
 
 // ---------------------------------------------------------------------------
@@ -1138,6 +1195,32 @@ int ipco_collisions_build(ipcb_ctx* ctx, const double* V, int32_t ld, double dha
     const auto v = load_vertices(ctx->nV, V, ld);
     candidates_build(ctx, v, nullptr, 0.5 * (dhat + dmin)); // normal_collisions.cpp:30
     collisions_build(ctx, v, dhat, dmin, flags);
+    coll_counts(ctx, counts);
+    return 0;
+}
+int ipco_collisions_corrections_keys(ipcb_ctx* ctx, int64_t n[4])
+{
+    if (!ctx->ima_pending) return fail("no deferred IMPROVED_MAX_APPROX build on this context");
+    for (int k = 0; k < 4; k++) n[k] = int64_t(ctx->ima_keys[k].size());
+    return 0;
+}
+int ipco_collisions_corrections_pack(ipcb_ctx* ctx, uint64_t* keys)
+{
+    if (!ctx->ima_pending) return fail("no deferred IMPROVED_MAX_APPROX build on this context");
+    size_t o = 0;
+    for (int k = 0; k < 4; k++)
+        for (const Pair& p : ctx->ima_keys[k]) keys[o++] = (uint64_t(uint32_t(p[0])) << 32) | uint32_t(p[1]);
+    return 0;
+}
+int ipco_collisions_corrections_apply(ipcb_ctx* ctx, const uint64_t* keys, const int64_t n[4], int32_t rank, int32_t world, int64_t counts[4])
+{
+    if (!ctx->ima_pending) return fail("no deferred IMPROVED_MAX_APPROX build on this context");
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad slice");
+    std::vector<Pair> lists[4];
+    size_t o = 0;
+    for (int k = 0; k < 4; k++)
+        for (int64_t i = 0; i < n[k]; i++, o++) lists[k].push_back({ int32_t(keys[o] >> 32), int32_t(keys[o] & 0xffffffffu) });
+    collisions_corrections_apply(ctx, lists, rank, world);
     coll_counts(ctx, counts);
     return 0;
 }

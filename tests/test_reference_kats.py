@@ -461,6 +461,55 @@ def check_improved_max_approx_kats(oracle):
     assert summary(X, T.IPC)[0] == summary(X, T.IMPROVED_MAX_APPROX)[0] == [0, 0, 0, 1]
 
 
+def check_improved_max_approx_builders(api, scenes, world=3):
+    """IMPROVED_MAX_APPROX built by several builders over disjoint candidate shards (IPCB_DEFER_CORRECTIONS: deferred build,
+    exchange of the sub-element pairs, every builder adds the corrections of its slice) unites to the single-builder set"""
+    import types
+
+    for name, area in (("stack", False), ("stack", True), ("drape", False), ("dense", True)):
+        V0, V1, E, F, P = {"stack": lambda: scenes.cloth_stack(3, 20), "drape": lambda: scenes.cloth_on_sphere(32, 16, drape=True),
+                           "dense": lambda: scenes.dense_sheet(8, 2.0)}[name]()
+        dhat = P["dhat"]
+        IMA = api.NormalCollisions.CollisionSetType.IMPROVED_MAX_APPROX
+        mesh = api.CollisionMesh(V0, E, F)
+        cand = api.Candidates()
+        cand.build(mesh, V0, 0.5 * dhat)
+        one = api.NormalCollisions()
+        one.set_use_area_weighting(area), one.set_collision_set_type(IMA)
+        one.build(cand, mesh, V0, dhat)
+        want = [getattr(one, k + "_collisions") for k in ("vv", "ev", "ee", "fv")]
+        full = [np.asarray(getattr(cand, k + "_candidates")).copy() for k in ("vv", "ev", "ee", "fv")]
+        meshes = [api.CollisionMesh(V0, E, F) for _ in range(world)]
+        builders = []
+        for r, m in enumerate(meshes):
+            c = api.Candidates()
+            c.set(m, *[a[(len(a) * r) // world:(len(a) * (r + 1)) // world] for a in full])
+            b = api.NormalCollisions()
+            b.set_use_area_weighting(area), b.set_collision_set_type(IMA)
+            b.build(c, m, V0, dhat, defer_corrections=True)
+            builders.append(b)
+        keys = [b.correction_keys() for b in builders]
+        assert sum(len(k) for ks in keys for k in ks) > 0
+        united = [np.concatenate([ks[k] for ks in keys]) for k in range(4)]
+        parts = []
+        for r, b in enumerate(builders):
+            b.apply_corrections(united, r, world)
+            parts.append([getattr(b, k + "_collisions") for k in ("vv", "ev", "ee", "fv")])
+        m = api.NormalCollisions()
+        m.assign(mesh, [[types.SimpleNamespace(ids=x.ids, weight=x.weight, eps_x=x.eps_x, dtype=x.dtype) for x in p] for p in parts], 0.0)
+        have = [getattr(m, k + "_collisions") for k in ("vv", "ev", "ee", "fv")]
+        for kind, (sa, sb) in enumerate(zip(have, want)):
+            scale = max(np.abs(sb.weight).max(), 1e-300) if len(sb.weight) else 1.0
+            ka, kb = np.abs(sa.weight) > 1e-12 * scale, np.abs(sb.weight) > 1e-12 * scale
+            assert np.array_equal(sa.ids[ka], sb.ids[kb]), (name, area, kind)
+            assert np.array_equal(sa.dtype[ka], sb.dtype[kb]) and np.array_equal(sa.eps_x[ka], sb.eps_x[kb])
+            assert np.allclose(sa.weight[ka], sb.weight[kb], rtol=1e-12, atol=0)
+
+
+def test_improved_max_approx_over_several_builders(oracle, scenes):
+    check_improved_max_approx_builders(oracle, scenes)
+
+
 def test_improved_max_approx_derivatives(oracle, scenes):
     check_improved_max_approx_derivatives(oracle, scenes)
 

@@ -25,7 +25,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, backend, row_block, queue):
+def _worker(rank, world, port, backend, row_block, queue, improved=False):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -53,7 +53,7 @@ def _worker(rank, world, port, backend, row_block, queue):
             api.set_num_threads(2)
             mesh = api.CollisionMesh(V0, E, F)
         out = sharded.ShardedContactStep(api, mesh, rank, world, dist=dist, device=device, native=backend == "nccl",
-                                         row_block=row_block).step(V0, V1, P["dhat"])
+                                         row_block=row_block).step(V0, V1, P["dhat"], improved_max_approx=improved)
         H = np.ascontiguousarray(out["hessian_local"].toarray())
         Hmine = H.copy()
         t = torch.from_numpy(H)
@@ -62,7 +62,7 @@ def _worker(rank, world, port, backend, row_block, queue):
         dist.all_reduce(t)  # test only: the product keeps the Hessian per rank
         # single-rank reference on the same library
         mesh1 = api.CollisionMesh(V0, E, F, **({"device": rank} if backend == "nccl" else {}))
-        one = sharded.ShardedContactStep(api, mesh1, 0, 1, native=backend == "nccl").step(V0, V1, P["dhat"])
+        one = sharded.ShardedContactStep(api, mesh1, 0, 1, native=backend == "nccl").step(V0, V1, P["dhat"], improved_max_approx=improved)
         H1 = one["hessian_local"].toarray()
         Hs = t.cpu().numpy()
         tiles = None
@@ -89,13 +89,13 @@ def _worker(rank, world, port, backend, row_block, queue):
         queue.put(dict(rank=rank, error=traceback.format_exc() + repr(e)))
 
 
-def _run(backend, world=2, row_block=True):
+def _run(backend, world=2, row_block=True, improved=False):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, row_block, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, row_block, q, improved)) for r in range(world)]
     for p in procs:
         p.start()
     return _collect(q, procs)
@@ -135,12 +135,13 @@ def _step_tolerance(make_scene, steps):
     return StepTolerance(pyoracle.load(), V0, V1, E, F).tolerance(min(steps))[0]
 
 
-def _check(results):
+def _check(results, improved=False):
     tol = _step_tolerance(lambda s: s.cloth_stack(3, 14), [x for r in results for x in r["step"]])
     total = np.sum([r["shard_collisions"] for r in results], axis=0)
-    # the shards partition the candidates: FV / EE collisions are disjoint, VV / EV ones may be derived on both ranks
-    assert total[2] == results[0]["all_collisions"][2] and total[3] == results[0]["all_collisions"][3]
-    assert total[0] >= results[0]["all_collisions"][0] and total[1] >= results[0]["all_collisions"][1]
+    if not improved:  # (the correction records of IMPROVED_MAX_APPROX cancel and coincide across ranks)
+        # the shards partition the candidates: FV / EE collisions are disjoint, VV / EV ones may be derived on both ranks
+        assert total[2] == results[0]["all_collisions"][2] and total[3] == results[0]["all_collisions"][3]
+        assert total[0] >= results[0]["all_collisions"][0] and total[1] >= results[0]["all_collisions"][1]
     assert all(sum(r["shard_collisions"]) > 0 for r in results)
     for r in results:
         assert r["energy"] <= 1e-12 and r["grad"] <= 1e-12
@@ -158,6 +159,21 @@ def _check(results):
 @pytest.mark.parametrize("row_block", [True, False], ids=["row_block", "additive"])
 def test_two_rank_contact_step_gloo(oracle, row_block):  # the fixture builds the oracle before the ranks race for it
     _check(_run("gloo", row_block=row_block))
+
+
+def test_two_rank_improved_max_approx_gloo(oracle):
+    """CollisionSetType::IMPROVED_MAX_APPROX over two ranks (deferred build, exchange of the sub-element pairs, per-rank slices
+    of the corrections: include/ipcb200.h, IPCB_DEFER_CORRECTIONS) equals the single-rank step with the same set type"""
+    _check(_run("gloo", row_block=True, improved=True), improved=True)
+
+
+@pytest.mark.gpu
+def test_two_rank_improved_max_approx_nccl_host_buffers(cuda):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _check(_run("nccl", row_block=True, improved=True), improved=True)
 
 
 @pytest.mark.gpu

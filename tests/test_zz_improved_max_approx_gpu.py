@@ -25,6 +25,10 @@ def test_reference_kats_and_convergent_weights(cuda):
     rk.check_improved_max_approx_kats(cuda)
 
 
+def test_several_builders_through_the_host_buffers(cuda, scenes):
+    rk.check_improved_max_approx_builders(cuda, scenes)
+
+
 def test_derivatives(cuda, scenes):
     rk.check_improved_max_approx_derivatives(cuda, scenes)
 
