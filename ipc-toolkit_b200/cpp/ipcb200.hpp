@@ -258,16 +258,48 @@ public:
     }
     void set_use_area_weighting(bool v) { m_area = v; }
     bool use_area_weighting() const { return m_area; }
-    void build(const CollisionMesh& mesh, MatrixXd vertices, double dhat, double dmin = 0)
+    /// normal_collisions.hpp:29-39; OGC is outside this path
+    enum class CollisionSetType { IPC, IMPROVED_MAX_APPROX, OGC };
+    void set_collision_set_type(CollisionSetType t)
     {
-        claim(mesh);
-        check(ipcb_collisions_build(mesh.ctx(), vertices.data, vertices.ld, dhat, dmin, m_area ? IPCB_USE_AREA_WEIGHTING : 0, m_counts));
-        m_built = true;
+        if (t == CollisionSetType::OGC) throw std::invalid_argument("CollisionSetType::OGC is outside this path");
+        m_type = t;
     }
-    void build(const Candidates&, const CollisionMesh& mesh, MatrixXd vertices, double dhat, double dmin = 0)
+    CollisionSetType collision_set_type() const { return m_type; }
+    /// defer_corrections (IMPROVED_MAX_APPROX built by several builders over disjoint candidate shards, IPCB_DEFER_CORRECTIONS): the
+    /// build stops after this builder's sub-element pairs; exchange correction_keys() and finish with apply_corrections()
+    void build(const CollisionMesh& mesh, MatrixXd vertices, double dhat, double dmin = 0, bool defer_corrections = false)
     {
         claim(mesh);
-        check(ipcb_collisions_build_from_candidates(mesh.ctx(), vertices.data, vertices.ld, dhat, dmin, m_area ? IPCB_USE_AREA_WEIGHTING : 0, m_counts));
+        check(ipcb_collisions_build(mesh.ctx(), vertices.data, vertices.ld, dhat, dmin, flags(defer_corrections), m_counts));
+        m_built = !defer_corrections;
+    }
+    void build(const Candidates&, const CollisionMesh& mesh, MatrixXd vertices, double dhat, double dmin = 0, bool defer_corrections = false)
+    {
+        claim(mesh);
+        check(ipcb_collisions_build_from_candidates(mesh.ctx(), vertices.data, vertices.ld, dhat, dmin, flags(defer_corrections), m_counts));
+        m_built = !defer_corrections;
+    }
+    /// the four lists of this builder's unique sub-element pairs after a deferred build (opaque 64-bit keys)
+    std::array<std::vector<uint64_t>, 4> correction_keys() const
+    {
+        int64_t n[4];
+        check(ipcb_collisions_corrections_keys(m_mesh->ctx(), n));
+        std::vector<uint64_t> all(size_t(n[0] + n[1] + n[2] + n[3]) + 1);
+        check(ipcb_collisions_corrections_pack(m_mesh->ctx(), all.data()));
+        std::array<std::vector<uint64_t>, 4> out;
+        size_t o = 0;
+        for (int k = 0; k < 4; k++) out[k].assign(all.begin() + o, all.begin() + o + n[k]), o += size_t(n[k]);
+        return out;
+    }
+    /// lists: for each of the four lists the keys of ALL builders (duplicates allowed); adds the corrections of slice `rank` of `world`
+    void apply_corrections(const std::array<std::vector<uint64_t>, 4>& lists, int rank, int world)
+    {
+        std::vector<uint64_t> all;
+        int64_t n[4];
+        for (int k = 0; k < 4; k++) n[k] = int64_t(lists[k].size()), all.insert(all.end(), lists[k].begin(), lists[k].end());
+        all.push_back(0);
+        check(ipcb_collisions_corrections_apply(m_mesh->ctx(), all.data(), n, rank, world, m_counts));
         m_built = true;
     }
     size_t size() const { return size_t(m_counts[0] + m_counts[1] + m_counts[2] + m_counts[3]); }
@@ -343,6 +375,12 @@ private:
     mutable ipcb_collision_set* m_set = nullptr;
     int64_t m_counts[4] = { 0, 0, 0, 0 };
     bool m_area = false, m_built = false;
+    CollisionSetType m_type = CollisionSetType::IPC;
+    int32_t flags(bool defer) const
+    {
+        return (m_area ? IPCB_USE_AREA_WEIGHTING : 0) | (m_type == CollisionSetType::IMPROVED_MAX_APPROX ? IPCB_SET_IMPROVED_MAX_APPROX : 0)
+            | (defer ? IPCB_DEFER_CORRECTIONS : 0);
+    }
 };
 
 // Eigen::SparseMatrix<double> in compressed-column form (== compressed rows of the symmetric matrix)

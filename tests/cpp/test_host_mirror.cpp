@@ -47,6 +47,17 @@ int main()
             const double nf = std::sqrt(f[0] * f[0] + f[1] * f[1] + f[2] * f[2]), nx = std::sqrt(0.75);
             for (int k = 0; k < 3; k++) CHECK(std::abs(f[k] / nf - x[k] / nx) < 1e-9);
         }
+        { // CollisionSetType::IMPROVED_MAX_APPROX on the cube of points (test_normal_collisions.cpp:69-107): 12 collisions; and the
+          // same set from a deferred build finished with the builder's own pairs (one builder = slice 0 of 1)
+            NormalCollisions ima, two;
+            ima.set_collision_set_type(NormalCollisions::CollisionSetType::IMPROVED_MAX_APPROX);
+            ima.build(mesh, MatrixXd(V, 8, 3), dhat, min_distance);
+            CHECK(ima.size() == 12);
+            two.set_collision_set_type(NormalCollisions::CollisionSetType::IMPROVED_MAX_APPROX);
+            two.build(mesh, MatrixXd(V, 8, 3), dhat, min_distance, true);
+            two.apply_corrections(two.correction_keys(), 0, 1);
+            CHECK(two.size() == ima.size());
+        }
         const SparseMatrix H = B.hessian(collisions, mesh, MatrixXd(V, 8, 3), PSDProjectionMethod::CLAMP);
         CHECK(H.rows == 24 && H.nonZeros() > 0 && H.outer.back() == index_t(H.nonZeros()));
         CHECK(compute_collision_free_stepsize(mesh, MatrixXd(V, 8, 3), MatrixXd(V, 8, 3)) == 1.0);
