@@ -1573,6 +1573,8 @@ __global__ void k_col_from_counts(int nV, const unsigned long long* __restrict__
         colcount[v] = n0 + n1 + n2;
         colR[v] = v < nV ? 2 * n0 + 3 * n1 + 4 * n2 : 0;
         if (v < nV) mine = n0 + n1 + n2;
+    } else if (v == nV + 1) {
+        colcount[v] = 0; // the scan over nV + 2 entries reads it
     }
     for (int o = 16; o > 0; o >>= 1) mine = max(mine, __shfl_xor_sync(0xffffffffu, mine, o));
     if ((threadIdx.x & 31) == 0 && mine > report_above) atomicMax(maxcount, (unsigned long long)mine); // rare: large columns only
@@ -1751,7 +1753,7 @@ void hessian_assemble_prepare(ipcb_ctx* ctx, const int64_t nk[4], cudaStream_t s
         unsigned long long* maxcount = ctx->dCounters.p + 26;
         IPCB_CUDA(cudaMemsetAsync(maxcount, 0, sizeof(unsigned long long), s));
         // hitemoff doubles as the per-column incidence count until the item scan overwrites it
-        k_col_from_counts<<<grid_for(size_t(nV) + 1, 256), 256, 0, s>>>(nV, ctx->hcount.p, ctx->hitemoff.p, ctx->hcolR.p, maxcount,
+        k_col_from_counts<<<grid_for(size_t(nV) + 2, 256), 256, 0, s>>>(nV, ctx->hcount.p, ctx->hitemoff.p, ctx->hcolR.p, maxcount,
                                                                         std::min(COLSORT_WARP_CAP, colsort_cta_cap()));
         ctx->launches++;
     }
