@@ -127,6 +127,52 @@ def test_friction_potential_fd_oracle(oracle, scenes, name):
     check_potential_fd(oracle, scenes, name, 1e-3)
 
 
+def check_reference_tangent_kats(api):
+    """the reference's known answers for tangent bases and closest points (tests/src/tests/tangent/test_tangent_basis.cpp:12-31,
+    51-70,86-105,119-137; test_closest_point.cpp:48-56,78-83), reached through TangentialCollisions::build on one-collision meshes"""
+    X, Y, Z = np.eye(3)
+
+    def one(V, E, F, key, dhat=2.0):
+        V = np.asarray(V, float)
+        E = np.asarray(E, np.int32).reshape(-1, 2)
+        F = np.asarray(F, np.int32).reshape(-1, 3)
+        mesh = api.CollisionMesh(V, E, F)
+        c = api.NormalCollisions()
+        c.build(mesh, V, dhat)
+        counts = dict(zip(("vv", "ev", "ee", "fv"), c.counts()))
+        assert counts[key] == 1 and sum(counts.values()) == 1, counts
+        t = api.TangentialCollisions()
+        t.build(mesh, V, c, api.BarrierPotential(dhat, 1.0), np.full(len(V), 0.5), np.full(len(V), 0.5))
+        r = getattr(t, key + "_collisions")
+        assert len(r.ids) == 1
+        return r.tangent_basis[0], r.closest_point[0]  # 2 x 3 (the columns of the 3 x 2 basis), closest-point coordinates
+
+    # point-triangle: p above the triangle's plane y = 0 (the reference evaluates the basis for exactly these points)
+    B, cp = one([[0, 1, 0], [-1, 0, 1], [1, 0, 1], [0, 0, -1]], [[1, 2], [2, 3], [3, 1]], [[1, 2, 3]], "fv")
+    assert abs(abs(B[0] @ X) - 1) < 1e-12 and abs(abs(B[1] @ Z) - 1) < 1e-12
+    assert np.allclose(cp, [0.25, 0.5], atol=1e-12)  # t0 + u (t1 - t0) + v (t2 - t0) = (0, 0, 0)
+    # edge-edge: the reference's crossing edges, the second one lifted by 1 (the basis does not depend on the lift)
+    B, cp = one([[-1, 0, 0], [1, 0, 0], [0, 1, -1], [0, 1, 1]], [[0, 1], [2, 3]], [], "ee")
+    assert abs(abs(B[0] @ X) - 1) < 1e-12 and abs(abs(B[1] @ Z) - 1) < 1e-12
+    assert np.allclose(cp, [0.5, 0.5], atol=1e-12)
+    # point-edge
+    B, cp = one([[0, 1, 0], [-1, 0, 0], [1, 0, 0]], [[1, 2]], [], "ev")
+    assert abs(abs(B[0] @ X) - 1) < 1e-12 and abs(abs(B[1] @ Z) - 1) < 1e-12
+    assert abs(cp[0] - 0.5) < 1e-12
+    # point-point
+    B, cp = one([[0, 0, 0], [0, 0, 1]], [], [], "vv")
+    assert abs(abs(B[0] @ X) - 1) < 1e-12 and abs(abs(B[1] @ Y) - 1) < 1e-12
+
+
+def test_reference_tangent_known_answers_oracle(oracle):
+    check_reference_tangent_kats(oracle)
+
+
+@pytest.mark.gpu
+def test_reference_tangent_known_answers(cuda):
+    check_reference_tangent_kats(cuda)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["stack", "drape", "soup"])
 def test_friction_matches_the_oracle(cuda, oracle, scenes, name):
