@@ -164,13 +164,50 @@ def check_reference_tangent_kats(api):
     assert abs(abs(B[0] @ X) - 1) < 1e-12 and abs(abs(B[1] @ Y) - 1) < 1e-12
 
 
+def check_reference_relative_velocity_kats(api):
+    """test_relative_velocity.cpp:13-69: with the other primitive at rest the relative velocity IS the moving point's velocity
+    (at the closest point), and a common translation gives none — observed through the one-collision friction potential
+    E(u) = w N mu f0(|P^T u_rel|) with the reference's f0 (friction/smooth_friction_mollifier.cpp:7-14)"""
+    eps_v, mu, dhat = 1e-2, 0.4, 2.0
+    f0 = lambda y: y if abs(y) >= eps_v else y * y * (1 - y / (3 * eps_v)) / eps_v + eps_v / 3
+    cases = [  # (V, E, F, kind, moving vertices: the first primitive)
+        ([[0, 1, 0], [-1, 0, 1], [1, 0, 1], [0, 0, -1]], [[1, 2], [2, 3], [3, 1]], [[1, 2, 3]], "fv", [0]),
+        ([[-1, 0, 0], [1, 0, 0], [0, 1, -1], [0, 1, 1]], [[0, 1], [2, 3]], [], "ee", [0, 1]),
+        ([[0, 1, 0], [-1, 0, 0], [1, 0, 0]], [[1, 2]], [], "ev", [0]),
+        ([[0, 0, 0], [0, 0, 1]], [], [], "vv", [0]),
+    ]
+    rng = np.random.default_rng(11)
+    for V, E, F, key, moving in cases:
+        V = np.asarray(V, float)
+        mesh = api.CollisionMesh(V, np.asarray(E, np.int32).reshape(-1, 2), np.asarray(F, np.int32).reshape(-1, 3))
+        c = api.NormalCollisions()
+        c.build(mesh, V, dhat)
+        t = api.TangentialCollisions()
+        t.build(mesh, V, c, api.BarrierPotential(dhat, 1.0), np.full(len(V), mu), np.full(len(V), mu))
+        r = getattr(t, key + "_collisions")
+        assert t.size() == 1 and len(r.ids) == 1
+        P, N, w = r.tangent_basis[0], r.normal_force_magnitude[0], r.weight[0]
+        D = api.FrictionPotential(eps_v)
+        for scale in (0.3 * eps_v, 5 * eps_v):  # sticking and sliding
+            dp = rng.normal(0, 1, 3) * scale
+            U = np.zeros_like(V)
+            U[moving] = dp  # the whole first primitive moves with dp, the other one rests
+            want = w * N * mu * f0(np.linalg.norm(P @ dp))
+            assert D(t, mesh, U) == pytest.approx(want, rel=1e-11)
+            U[:] = dp  # common translation: no relative velocity
+            assert D(t, mesh, U) == pytest.approx(w * N * mu * eps_v / 3, rel=1e-11)
+            assert np.abs(D.gradient(t, mesh, U)).max() <= 1e-12 * N
+
+
 def test_reference_tangent_known_answers_oracle(oracle):
     check_reference_tangent_kats(oracle)
+    check_reference_relative_velocity_kats(oracle)
 
 
 @pytest.mark.gpu
 def test_reference_tangent_known_answers(cuda):
     check_reference_tangent_kats(cuda)
+    check_reference_relative_velocity_kats(cuda)
 
 
 @pytest.mark.gpu
