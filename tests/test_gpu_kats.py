@@ -32,6 +32,7 @@ def test_broad_phase_kats_gpu(cuda):
 @pytest.mark.gpu
 def test_codim_kats_gpu(cuda):
     ref.check_codim_kats(cuda)
+    ref.check_faces_to_edges_kats(cuda)
 
 
 @pytest.mark.gpu

@@ -364,6 +364,23 @@ def test_broad_phase_kats(oracle):
     check_broad_phase_kats(oracle)
 
 
+def check_faces_to_edges_kats(api):
+    """tests/src/tests/test_collision_mesh.cpp:70-110 (CollisionMesh::construct_faces_to_edges, collision_mesh.cpp:510-543)"""
+    V = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], float)
+    F = np.array([[0, 1, 2]], np.int32)
+    for E, want in (([[0, 1], [1, 2], [2, 0]], [0, 1, 2]), ([[2, 0], [2, 1], [1, 0]], [2, 1, 0]), ([[0, 1], [2, 0], [2, 1]], [0, 2, 1])):
+        mesh = api.CollisionMesh(V, np.array(E, np.int32), F)
+        assert mesh.faces_to_edges().tolist() == [want]
+    with pytest.raises(RuntimeError, match="Unable to find edge!"):
+        api.CollisionMesh(V, np.array([[0, 1], [1, 2], [0, 3]], np.int32), F)
+    # codim points (:112-122): every vertex of a mesh without edges is codimensional
+    assert api.CollisionMesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], float)).num_codim_vertices() == 4
+
+
+def test_faces_to_edges_kats(oracle):
+    check_faces_to_edges_kats(oracle)
+
+
 def test_codim_kats(oracle):
     check_codim_kats(oracle)
 
