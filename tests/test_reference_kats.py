@@ -84,6 +84,42 @@ def _fd_grad(f, x, h=1e-7):
     return g
 
 
+def test_point_point_and_point_edge_distance(oracle):
+    """distance/test_point_point.cpp:19-33 (aligned / diagonal vectors of length d -> d^2) and test_point_edge.cpp:21-37,
+    61-97 (p at height d over a long edge; p = e0 + alpha (e1 - e0) + d n over random edges: d^2 inside, end-point distances
+    outside)"""
+    ds = (-10, -1, -1e-12, 0, 1e-12, 1, 10)
+    for d in ds:
+        assert distance(oracle, 0, ([0, 0, 0], [d, 0, 0])) == pytest.approx(d * d)
+        assert distance(oracle, 0, ([0, 0, 0], np.ones(3) / np.sqrt(3) * d)) == pytest.approx(d * d)
+        assert distance(oracle, 1, ([0, d, 0], [-10, 0, 0], [10, 0, 0])) == pytest.approx(d * d)
+    rng = np.random.default_rng(5)
+    for alpha in np.arange(-1.0, 2.0, 0.1):
+        for d in np.arange(-10.0, 10.0, 1.0):
+            for _ in range(4):
+                e0, e1 = rng.uniform(-1, 1, 3), rng.uniform(-1, 1, 3)
+                n = np.cross(e1 - e0, [1.0, 0, 0])
+                n /= np.linalg.norm(n)
+                pnt = (e1 - e0) * alpha + e0 + d * n
+                want = np.linalg.norm(e0 - pnt) if alpha < 0 else (np.linalg.norm(e1 - pnt) if alpha > 1 else d)
+                got = distance(oracle, 1, (pnt, e0, e1))
+                # alpha within rounding of 0 or 1 may be classified either way: both answers agree to rounding there
+                assert got == pytest.approx(want * want, rel=1e-9, abs=1e-12), (alpha, d)
+
+
+def test_point_plane_and_line_line_distance(oracle):
+    """distance/test_point_plane.cpp:17-31 (plane y = y_plane through t0, t1, t2: (y - y_plane)^2) and test_line_line.cpp:37-46
+    (perpendicular lines at heights ya, yb: (ya - yb)^2), i.e. the point-triangle / edge-edge distances with the interior types"""
+    rng = np.random.default_rng(9)
+    for _ in range(200):
+        x, y, z, yp = rng.uniform(-10, 10, 4)
+        d = distance(oracle, 3, ([x, y, z], [-1, yp, 0], [1, yp, -1], [1, yp, 0]), kats.P_T)
+        assert d == pytest.approx((y - yp) ** 2, rel=1e-12, abs=1e-12)
+        ya, yb = rng.uniform(-100, 100, 2)
+        d = distance(oracle, 2, ([-1, ya, 0], [1, ya, 0], [0, yb, -1], [0, yb, 1]), kats.EA_EB)
+        assert d == pytest.approx((ya - yb) ** 2, rel=1e-12, abs=1e-12)
+
+
 def test_distance_derivatives_match_finite_differences(oracle):
     """the reference checks every gradient / Hessian against finite differences (distance/test_*.cpp "gradient"/"hessian"
     cases); same check on random stencils for every kind and every explicit distance type"""
